@@ -1,0 +1,140 @@
+/*
+ * esper_b200.h -- C ABI of libesper_b200.so: the B200 (sm_100a) implementation of ESPER's
+ * per-projection-direction (PD) diffusion-map embedding and Nd eigen-rotation histogram sweep.
+ *
+ * The reference (evanseitz/ManifoldEM_ESPER) is pure Python and has no FFI; the surface this
+ * library sits behind is the reference's module-function surface.  Each entry point below
+ * names the reference interface it replaces (path:line in the upstream tree).  The Python host
+ * layer (manifoldem_esper_b200/*.py) mirrors those module functions one-to-one and binds this
+ * ABI with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every array is dense row-major; `double` = IEEE binary64.
+ *   - pointers are HOST pointers unless the parameter name ends in `_d` (device pointer).
+ *   - the caller owns every array it passes; outputs are caller-allocated; the library never
+ *     frees caller memory.  An opaque `esper_ctx` owns device buffers, one stream, workspaces.
+ *   - a NULL input pointer where documented means "use the copy the previous stage left on the
+ *     device"; a NULL output pointer means "leave the result on the device only".  This lets the
+ *     stages chain without PCIe round trips.
+ *   - return value: 0 = ok; <0 = error (ESPER_E_*); message via esper_last_error().
+ *   - one ctx per (process, GPU); calls on one ctx are serialised on its stream; ctxs are
+ *     independent of each other.  There is NO CPU fallback: without a B200 the calls fail.
+ */
+#ifndef ESPER_B200_H
+#define ESPER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESPER_ABI_VERSION 1
+
+#define ESPER_OK              0
+#define ESPER_E_ARG          -1   /* bad argument (Python wrapper raises ValueError)        */
+#define ESPER_E_CUDA         -2   /* CUDA runtime / driver error (RuntimeError)            */
+#define ESPER_E_NOMEM        -3   /* device or host allocation failed                      */
+#define ESPER_E_NOCONV       -4   /* eigensolver did not converge within max_iter          */
+#define ESPER_E_STATE        -5   /* a NULL "use resident copy" argument with nothing resident */
+#define ESPER_E_ARCH         -6   /* device is not sm_100 (no fallback path exists)        */
+
+typedef struct esper_ctx esper_ctx;
+
+/* ---- context -------------------------------------------------------------------------- */
+int         esper_abi_version(void);
+/* device: CUDA ordinal.  stream: a cudaStream_t to launch on (e.g. torch's), or NULL to let the
+ * ctx create its own non-blocking stream. */
+esper_ctx*  esper_create(int device, void* stream);
+void        esper_destroy(esper_ctx* ctx);
+const char* esper_last_error(esper_ctx* ctx);          /* ctx may be NULL: last create error */
+int         esper_sync(esper_ctx* ctx);                 /* cudaStreamSynchronize              */
+/* Per-kernel CUDA-event timing of the calls that follow (off by default). */
+int         esper_set_profiling(esper_ctx* ctx, int on);
+/* Sum / count of the kernel launches recorded under `name` since the last reset.
+ * names: "prep", "gram", "dist_finalize", "refine", "sweep", "markov", "lanczos", "rot".    */
+int         esper_get_kernel_ms(esper_ctx* ctx, const char* name, double* total_ms, int* launches);
+int         esper_reset_profiling(esper_ctx* ctx);
+/* Total kernels launched by this ctx since creation (the bench's `gpu_launches` claim). */
+long long   esper_launch_count(esper_ctx* ctx);
+
+/* ---- stage 1: pairwise RMS image distances -------------------------------------------
+ * Replaces the non-CTF branch of 1_Embedding/DM/Distances.py:87-104:
+ *     x_i <- (x_i - mean)/std per image (float32, ddof 0)              :88-92
+ *     D_ij = sqrt( sum_p (x_ip - x_jp)^2 / P ), D_ii = 0, symmetric      :96-104
+ * computed as a 3xTF32 split-precision Gram contraction on tcgen05 tensor cores with short FP32
+ * accumulation chains combined in FP64, ||x||^2+||y||^2-2x.y epilogue, clamp at 0, sqrt.
+ * flags: */
+#define ESPER_DIST_STANDARDIZE  1u  /* apply the per-image z-score of Distances.py:88-92        */
+#define ESPER_DIST_CENTER       2u  /* subtract the PD mean image before the Gram (distance-
+                                       invariant; removes the common-mode term)   */
+#define ESPER_DIST_REFINE       4u  /* recompute pairs with D^2*P < refine_tau*(|x|^2+|y|^2) by
+                                       direct differences in FP64 (near-duplicate images)     */
+#define ESPER_DIST_DEFAULT      (ESPER_DIST_STANDARDIZE | ESPER_DIST_CENTER | ESPER_DIST_REFINE)
+
+/* imgs: [n, P] float32 (an MRC stack [n, N, N] flattened, P = N*N), or NULL = resident stack
+ * uploaded by esper_upload_images.  D: [n, n] float64 out, or NULL = keep on device.         */
+int esper_dist_rms(esper_ctx* ctx, const float* imgs, int n, int P, unsigned flags, double* D);
+/* Asynchronous H2D of a stack into the ctx (pinned host memory recommended); becomes resident. */
+int esper_upload_images(esper_ctx* ctx, const float* imgs, int n, int P);
+/* Tuning knobs of stage 1 (defaults in parentheses): split_k = number of K chunks whose FP32
+ * partial Grams are combined in FP64 (0 = auto: chunks of ~2048 pixels, rounded so the work
+ * units fill the SMs); refine_tau (0.05). */
+int esper_dist_config(esper_ctx* ctx, int split_k, double refine_tau);
+/* Upload a distance matrix so that stages 2/3 can use it as the resident D. */
+int esper_upload_dist(esper_ctx* ctx, const double* D, int m);
+
+/* ---- stage 2: epsilon sweep -------------------------------------------------------------
+ * Replaces the loop of 1_Embedding/DM/GaussianBandwidth.py:36-44:
+ *     logSum[k] = log sum_{ij : t < thr} exp(-t),  t = coef[k] * D_ij^2
+ * coef[k] = 1/(2*exp(logEps[k])) is computed by the caller exactly as the reference does
+ * (`1./(2.*eps)`), so the inclusion test `t < thr` is bit-identical.  D: [m, m] or NULL=resident.
+ * thr: GaussianBandwidth.find_threshold (:26-32); pass +inf for "no truncation".          */
+int esper_eps_sweep(esper_ctx* ctx, const double* D, int m, const double* coef, int n_eps,
+                    double thr, double* logSum);
+
+/* ---- stage 3: kernel, degree normalisation, leading eigenpairs ---------------------------
+ * Replaces 1_Embedding/DM/DiffusionMaps.py:109 (A = exp(-D^2/(2 eps))), :131-152
+ * (Ms = D^-1/2 A D^-1/2, i.e. alpha = 0) and :166-169 (svd; saves s^2 and U).
+ * esper_markov exposes the intermediate for tests: degree [m] and Ms [m, m] (either may be NULL). */
+int esper_markov(esper_ctx* ctx, const double* D, int m, double eps, double* degree, double* Ms);
+/* Leading k eigenpairs of Ms by deflated Lanczos with full reorthogonalisation.
+ *   val: [k]   = lambda^2, descending (what the reference saves as PD_%s_val.npy)
+ *   vec: [m,k] row-major; column 0 = sqrt(degree)/|sqrt(degree)| (steady state), unit columns,
+ *              sign fixed so that the entry of largest magnitude is positive
+ *   tol: relative residual |Ms v - lambda v| <= tol*lambda_1  (0 = 1e-11)
+ *   max_iter: Lanczos steps (0 = min(m-1, 1024));  iters (optional) receives the steps used.  */
+int esper_dmap_embed(esper_ctx* ctx, const double* D, int m, double eps, int k, double tol,
+                     int max_iter, double* val, double* vec, int* iters);
+
+/* ---- stage 4: Nd rotation + 2-D histogram sweep -----------------------------------------
+ * esper_nd_rotation: host-side restatement of 2_Manifold_Rotations/Generate_Nd_Rot.py:4-45,
+ * R = G_0 G_1 ... G_{T-1} (T = n(n-1)/2, lexicographic planes), left to right, round-to-nearest
+ * mul/add without FMA.  R: [n, n].  Returns ESPER_E_ARG unless n_theta == T (ValueError :7-12). */
+int esper_nd_rotation(int n, const double* theta, int n_theta, double* R);
+/* numpy.linspace(lo, hi, bins+1) as used by numpy.histogramdd; edges: [bins+1]. */
+int esper_hist_edges(int bins, double lo, double hi, double* edges);
+/* Batch of independent evaluations of the sweep body, Rotation_Histograms.py:304-312:
+ *   U_rot = (R_e @ Uinit[pd_e].T).T ; H = histogramdd(U_rot[:, (v1_e, v2_e)], bins, range lo..hi)
+ * Uinit: [n_pd, m, dim]; R: [n_eval, dim, dim]; nonzero: [n_eval] = count_nonzero(H);
+ * H (optional): [n_eval, bins, bins] int32 counts.                                           */
+int esper_rot_hist_eval(esper_ctx* ctx, const double* Uinit, int n_pd, int m, int dim,
+                        const double* R, const int* pd_of_eval, const int* v1, const int* v2,
+                        int n_eval, int bins, double lo, double hi, int* nonzero, int* H);
+/* The whole sequential search of Rotation_Histograms.py:283-365 for a batch of PDs on device:
+ * for every PD and subspace (v1,v2) of its comboList, for each Rij in order, evaluate all
+ * n_theta angles, keep the FIRST argmax of the empty-bin score, move on to the next Rij.
+ *   combo:  [n_pd, max_sub, 2] int (v1, v2), n_sub: [n_pd];  rij: [n_pd, n_rij] int
+ *   theta_grid: [n_theta] radians (np.arange(start,stop,step)*pi/180 computed by the caller)
+ *   thetas_out: [n_pd, max_sub, T] radians (rows >= n_sub[p] are zero)
+ *   counts_out (optional): [n_pd, max_sub, n_rij, n_theta] non-zero-bin counts               */
+int esper_rot_sweep(esper_ctx* ctx, const double* Uinit, int n_pd, int m, int dim,
+                    const int* combo, const int* n_sub, int max_sub, const int* rij, int n_rij,
+                    const double* theta_grid, int n_theta, int bins, double lo, double hi,
+                    double* thetas_out, int* counts_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESPER_B200_H */

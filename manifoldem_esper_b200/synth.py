@@ -1,0 +1,87 @@
+"""Seeded synthetic PD image stacks of the shape the reference pipeline consumes.
+
+The reference's own inputs (0_Data_Inputs/2_PDs_2D/PD_00x.mrcs: 400 states = 20 x 20, two
+degrees of freedom, 0_Data_Inputs/README.md:6) are not shipped, so benchmarks and parity
+tests use this generator: a toy molecule with a central blob and two
+satellites whose polar angles are the two conformational coordinates, then tau noisy copies
+per state at a target SNR following 0_Data_Inputs/Pristine_AddTauSNR/AddNoise.py:17-86
+(signal = pixels outside +-0.25 std; noise_std = sqrt(var(signal)/SNR); noise mean = signal
+mean; standardise with the mean/std of the pixels outside the inscribed circle).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def pristine_states(box: int = 250, n_side: int = 20, pd: int = 1, n_pd: int = 126) -> np.ndarray:
+    """float32 [n_side**2, box, box]: state (i, j) has satellite angles (a_i, b_j)."""
+    c = (box - 1) / 2.0
+    y, x = np.arange(box, dtype=np.float64), np.arange(box, dtype=np.float64)
+    rad = 0.22 * box
+    phase = pd * np.pi / n_pd  # in-plane rotation so PDs differ
+
+    def blob(cx, cy, sig):
+        ex = np.exp(-((x - cx) ** 2) / (2 * sig * sig))
+        ey = np.exp(-((y - cy) ** 2) / (2 * sig * sig))
+        return np.outer(ey, ex)
+
+    core = blob(c, c, 0.10 * box)
+    ang = (np.pi / 3.0) * np.arange(n_side) / max(n_side - 1, 1)
+    satA = [0.8 * blob(c + rad * np.cos(phase + a), c + rad * np.sin(phase + a), 0.05 * box) for a in ang]
+    satB = [0.5 * blob(c + rad * np.cos(phase + np.pi + b), c + rad * np.sin(phase + np.pi + b), 0.05 * box)
+            for b in ang]
+    out = np.empty((n_side * n_side, box, box), dtype=np.float32)
+    for i in range(n_side):
+        for j in range(n_side):
+            out[i * n_side + j] = core + satA[i] + satB[j]
+    return out
+
+
+def _background_mask(box: int) -> np.ndarray:
+    Y, X = np.ogrid[:box, :box]
+    return np.sqrt((X - int(box / 2)) ** 2 + (Y - int(box / 2)) ** 2) > int(box / 2)
+
+
+def noisy_stack(pristine: np.ndarray, tau: int = 5, snr: float = 0.1, seed: int = 0) -> np.ndarray:
+    """float32 [n_states*tau, box, box]; image index = state*tau + copy (Generate_TauSNR.py:56-64)."""
+    ns, box, _ = pristine.shape
+    rng = np.random.default_rng(seed)
+    bg = _background_mask(box)
+    out = np.empty((ns * tau, box, box), dtype=np.float32)
+    for s in range(ns):
+        img = pristine[s].astype(np.float64)
+        std = img.std()
+        sig = img[(img <= -0.25 * std) | (img >= 0.25 * std)]
+        sig_mean, noise_std = sig.mean(), np.sqrt(sig.var() / snr)
+        for t in range(tau):
+            g = rng.standard_normal((box, box), dtype=np.float32)
+            noisy = img + (sig_mean + noise_std * g)
+            b = noisy[bg]
+            out[s * tau + t] = (noisy - b.mean()) / b.std()
+    return out
+
+
+def synthetic_pd(pd: int = 1, box: int = 250, n_side: int = 20, tau: int = 5, snr: float | None = 0.1,
+                 seed: int | None = None) -> np.ndarray:
+    """One PD stack, float32 [n_side**2 * tau, box, box].  `snr=None` -> tau exact duplicates."""
+    pr = pristine_states(box, n_side, pd)
+    if snr is None:
+        return np.repeat(pr, tau, axis=0)
+    return noisy_stack(pr, tau, snr, 1000 * pd if seed is None else seed)
+
+
+def random_manifold(m: int = 2000, ncol: int = 15, seed: int = 0) -> np.ndarray:
+    """float64 [m, ncol] stand-in for a PD_xxx_vec.npy manifold (config 5 throughput shape):
+    two parabolic pairs (psi_1, psi_2), (psi_3, psi_4) like a 2-CM diffusion map, mixed by a
+    small random rotation, plus noise columns."""
+    rng = np.random.default_rng(seed)
+    a, b = rng.uniform(-1, 1, m), rng.uniform(-1, 1, m)
+    cols = [a, b, 2 * a * a - 1, 2 * b * b - 1, a * b, 4 * a ** 3 - 3 * a, 4 * b ** 3 - 3 * b]
+    U = np.zeros((m, ncol))
+    for c in range(ncol):
+        U[:, c] = cols[c] if c < len(cols) else rng.standard_normal(m) * 0.3
+    U[:, :7] += 0.05 * rng.standard_normal((m, 7))
+    k = min(ncol, 8)
+    Q, _ = np.linalg.qr(np.eye(k) + 0.15 * rng.standard_normal((k, k)))
+    U[:, :k] = U[:, :k] @ Q
+    return np.ascontiguousarray(U * (1.0 / np.sqrt(m)))
