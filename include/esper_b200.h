@@ -5,7 +5,7 @@
  * The reference (evanseitz/ManifoldEM_ESPER) is pure Python and has no FFI; the surface this
  * library sits behind is the reference's module-function surface.  Each entry point below
  * names the reference interface it replaces (path:line in the upstream tree).  The Python host
- * layer (manifoldem_esper_b200/*.py) mirrors those module functions one-to-one and binds this
+ * layer (the modules under manifoldem_esper_b200/) mirrors those module functions one-to-one and binds this
  * ABI with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
  *
  * Conventions
@@ -110,8 +110,8 @@ int esper_dmap_embed(esper_ctx* ctx, const double* D, int m, double eps, int k, 
 
 /* ---- stage 4: Nd rotation + 2-D histogram sweep -----------------------------------------
  * esper_nd_rotation: host-side restatement of 2_Manifold_Rotations/Generate_Nd_Rot.py:4-45,
- * R = G_0 G_1 ... G_{T-1} (T = n(n-1)/2, lexicographic planes), left to right, round-to-nearest
- * mul/add without FMA.  R: [n, n].  Returns ESPER_E_ARG unless n_theta == T (ValueError :7-12). */
+ * R = G_0 G_1 ... G_{T-1} (T = n(n-1)/2, lexicographic planes), left to right, each two-term sum
+ * accumulated as a dgemm micro-kernel does (first product rounded, second fused).  R: [n, n].  Returns ESPER_E_ARG unless n_theta == T (ValueError :7-12). */
 int esper_nd_rotation(int n, const double* theta, int n_theta, double* R);
 /* numpy.linspace(lo, hi, bins+1) as used by numpy.histogramdd; edges: [bins+1]. */
 int esper_hist_edges(int bins, double lo, double hi, double* edges);

@@ -1,0 +1,293 @@
+"""ctypes binding of libesper_b200.so (include/esper_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or no sm_100 device is present, the
+calls raise.  Everything numeric in this package goes through this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libesper_b200.so')
+
+ESPER_OK = 0
+E_ARG, E_CUDA, E_NOMEM, E_NOCONV, E_STATE, E_ARCH = -1, -2, -3, -4, -5, -6
+DIST_STANDARDIZE, DIST_CENTER, DIST_REFINE = 1, 2, 4
+DIST_DEFAULT = DIST_STANDARDIZE | DIST_CENTER | DIST_REFINE
+
+_lib = None
+_lib_lock = threading.Lock()
+
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+_i32p = C.POINTER(C.c_int)
+
+# name -> (restype, argtypes); must list every symbol include/esper_b200.h declares
+SIGNATURES = {
+    'esper_abi_version': (C.c_int, []),
+    'esper_create': (C.c_void_p, [C.c_int, C.c_void_p]),
+    'esper_destroy': (None, [C.c_void_p]),
+    'esper_last_error': (C.c_char_p, [C.c_void_p]),
+    'esper_sync': (C.c_int, [C.c_void_p]),
+    'esper_set_profiling': (C.c_int, [C.c_void_p, C.c_int]),
+    'esper_get_kernel_ms': (C.c_int, [C.c_void_p, C.c_char_p, _f64p, _i32p]),
+    'esper_reset_profiling': (C.c_int, [C.c_void_p]),
+    'esper_launch_count': (C.c_longlong, [C.c_void_p]),
+    'esper_dist_rms': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p]),
+    'esper_upload_images': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    'esper_dist_config': (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
+    'esper_upload_dist': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    'esper_eps_sweep': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
+    'esper_markov': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
+    'esper_dmap_embed': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int,
+                                   C.c_void_p, C.c_void_p, _i32p]),
+    'esper_nd_rotation': (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    'esper_hist_edges': (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_void_p]),
+    'esper_rot_hist_eval': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
+                                      C.c_void_p, C.c_void_p]),
+    'esper_rot_sweep': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
+                                  C.c_void_p, C.c_void_p]),
+}
+
+
+def load_library(path: str | None = None):
+    """dlopen libesper_b200.so and declare every prototype.  Raises OSError if it is not built."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None and path is None:
+            return _lib
+        p = path or LIB_PATH
+        if not os.path.exists(p):
+            raise OSError('%s not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                          '(or `make -C manifoldem_esper_b200/csrc`); there is no CPU fallback' % p)
+        lib = C.CDLL(p)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        if lib.esper_abi_version() != 1:
+            raise OSError('libesper_b200.so ABI version mismatch')
+        if path is None:
+            _lib = lib
+        return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _as(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class EsperError(RuntimeError):
+    pass
+
+
+class Context:
+    """One esper_ctx: device buffers, a stream and the stage calls.  Not thread-safe (one per thread)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._lib = load_library()
+        self._h = self._lib.esper_create(int(device), C.c_void_p(stream) if stream else None)
+        if not self._h:
+            raise EsperError(self._lib.esper_last_error(None).decode())
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.esper_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc):
+        if rc == ESPER_OK:
+            return
+        msg = self._lib.esper_last_error(self._h).decode()
+        if rc in (E_ARG, E_STATE):
+            raise ValueError(msg)
+        raise EsperError('esper error %d: %s' % (rc, msg))
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def sync(self):
+        self._check(self._lib.esper_sync(self._h))
+
+    def set_profiling(self, on=True):
+        self._check(self._lib.esper_set_profiling(self._h, int(bool(on))))
+
+    def reset_profiling(self):
+        self._check(self._lib.esper_reset_profiling(self._h))
+
+    def kernel_ms(self, name):
+        ms, n = C.c_double(0), C.c_int(0)
+        self._check(self._lib.esper_get_kernel_ms(self._h, name.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def launch_count(self):
+        return int(self._lib.esper_launch_count(self._h))
+
+    # -- stage 1 ----------------------------------------------------------------------------
+    def dist_config(self, split_k=0, refine_tau=0.05):
+        self._check(self._lib.esper_dist_config(self._h, int(split_k), float(refine_tau)))
+
+    def upload_images(self, imgs):
+        """Asynchronous H2D of a [n, P] float32 stack; `imgs` must stay alive until the next sync."""
+        imgs = _check_stack(imgs)
+        self._keep = imgs
+        self._check(self._lib.esper_upload_images(self._h, _ptr(imgs), imgs.shape[0], imgs.shape[1]))
+        return imgs.shape
+
+    def dist_rms(self, imgs=None, n=None, P=None, flags=DIST_DEFAULT, download=True, out=None):
+        """Distances.py:87-104 (non-CTF).  imgs=None -> resident stack of shape (n, P)."""
+        if imgs is not None:
+            imgs = _check_stack(imgs)
+            n, P = imgs.shape
+        if n is None or P is None:
+            raise ValueError('dist_rms: n and P are required when imgs is None')
+        D = None
+        if download:
+            D = out if out is not None else np.empty((n, n), dtype=np.float64)
+            if D.shape != (n, n) or D.dtype != np.float64 or not D.flags.c_contiguous:
+                raise ValueError('dist_rms: out must be a C-contiguous float64 [n, n] array')
+        self._check(self._lib.esper_dist_rms(self._h, _ptr(imgs), int(n), int(P), int(flags), _ptr(D)))
+        return D
+
+    def upload_dist(self, D):
+        D = _check_square(D)
+        self._keep = D
+        self._check(self._lib.esper_upload_dist(self._h, _ptr(D), D.shape[0]))
+        self.sync()
+
+    # -- stage 2 ----------------------------------------------------------------------------
+    def eps_sweep(self, D, coef, thr, m=None):
+        """GaussianBandwidth.py:36-44.  D=None -> resident distance matrix of order m."""
+        if D is not None:
+            D = _check_square(D)
+            m = D.shape[0]
+        if m is None:
+            raise ValueError('eps_sweep: m is required when D is None')
+        coef = _as(coef, np.float64).reshape(-1)
+        out = np.empty(coef.shape[0], dtype=np.float64)
+        self._check(self._lib.esper_eps_sweep(self._h, _ptr(D), int(m), _ptr(coef), coef.shape[0], float(thr), _ptr(out)))
+        return out
+
+    # -- stage 3 ----------------------------------------------------------------------------
+    def markov(self, D, eps, m=None, want_matrix=True):
+        if D is not None:
+            D = _check_square(D)
+            m = D.shape[0]
+        deg = np.empty(m, dtype=np.float64)
+        Ms = np.empty((m, m), dtype=np.float64) if want_matrix else None
+        self._check(self._lib.esper_markov(self._h, _ptr(D), int(m), float(eps), _ptr(deg), _ptr(Ms)))
+        return deg, Ms
+
+    def dmap_embed(self, D, eps, k=16, tol=0.0, max_iter=0, m=None):
+        """DiffusionMaps.py:109-169 at a given eps -> (val[k] = lambda^2, vec[m, k], lanczos steps)."""
+        if D is not None:
+            D = _check_square(D)
+            m = D.shape[0]
+        if m is None:
+            raise ValueError('dmap_embed: m is required when D is None')
+        k = int(k)
+        val = np.empty(max(k, 1), dtype=np.float64)
+        vec = np.empty((m, max(k, 1)), dtype=np.float64)
+        it = C.c_int(0)
+        self._check(self._lib.esper_dmap_embed(self._h, _ptr(D), int(m), float(eps), k, float(tol), int(max_iter),
+                                               _ptr(val), _ptr(vec), C.byref(it)))
+        return val, vec, it.value
+
+    # -- stage 4 ----------------------------------------------------------------------------
+    def rot_hist_eval(self, Uinit, R, pd_of_eval, v1, v2, bins=51, lo=-1.5, hi=1.5, want_hist=False):
+        Uinit = _as(Uinit, np.float64)
+        if Uinit.ndim == 2:
+            Uinit = Uinit[None]
+        n_pd, m, dim = Uinit.shape
+        R = _as(R, np.float64).reshape(-1, dim, dim)
+        ne = R.shape[0]
+        pd_of_eval, v1, v2 = (_as(a, np.int32).reshape(-1) for a in (pd_of_eval, v1, v2))
+        if not (pd_of_eval.shape[0] == v1.shape[0] == v2.shape[0] == ne):
+            raise ValueError('rot_hist_eval: R, pd_of_eval, v1, v2 must have one entry per evaluation')
+        nz = np.empty(ne, dtype=np.int32)
+        H = np.empty((ne, bins, bins), dtype=np.int32) if want_hist else None
+        self._check(self._lib.esper_rot_hist_eval(self._h, _ptr(Uinit), n_pd, m, dim, _ptr(R), _ptr(pd_of_eval), _ptr(v1),
+                                                  _ptr(v2), ne, int(bins), float(lo), float(hi), _ptr(nz), _ptr(H)))
+        return (nz, H) if want_hist else nz
+
+    def rot_sweep(self, Uinit, combo, n_sub, rij, theta_grid, bins=51, lo=-1.5, hi=1.5, want_counts=False):
+        Uinit = _as(Uinit, np.float64)
+        n_pd, m, dim = Uinit.shape
+        combo = _as(combo, np.int32)
+        max_sub = combo.shape[1]
+        n_sub = _as(n_sub, np.int32).reshape(-1)
+        rij = _as(rij, np.int32).reshape(n_pd, -1)
+        n_rij = rij.shape[1]
+        theta_grid = _as(theta_grid, np.float64).reshape(-1)
+        T = dim * (dim - 1) // 2
+        if combo.shape != (n_pd, max_sub, 2) or n_sub.shape[0] != n_pd:
+            raise ValueError('rot_sweep: combo must be [n_pd, max_sub, 2] and n_sub [n_pd]')
+        out = np.empty((n_pd, max_sub, T), dtype=np.float64)
+        cnt = np.empty((n_pd, max_sub, max(n_rij, 1), theta_grid.shape[0]), dtype=np.int32) if want_counts else None
+        self._check(self._lib.esper_rot_sweep(self._h, _ptr(Uinit), n_pd, m, dim, _ptr(combo), _ptr(n_sub), max_sub,
+                                              _ptr(rij), n_rij, _ptr(theta_grid), theta_grid.shape[0], int(bins),
+                                              float(lo), float(hi), _ptr(out), _ptr(cnt)))
+        return (out, cnt) if want_counts else out
+
+
+def _check_stack(imgs):
+    imgs = np.asarray(imgs)
+    if imgs.ndim == 3:
+        imgs = imgs.reshape(imgs.shape[0], -1)
+    if imgs.ndim != 2 or imgs.shape[0] < 1 or imgs.shape[1] < 1:
+        raise ValueError('image stack must be [n, N, N] or [n, P] with n >= 1')
+    return _as(imgs, np.float32)
+
+
+def _check_square(D):
+    D = np.asarray(D)
+    if D.ndim != 2 or D.shape[0] != D.shape[1] or D.shape[0] < 1:
+        raise ValueError('distance matrix must be square [m, m] with m >= 1')
+    return _as(D, np.float64)
+
+
+def nd_rotation(n, theta):
+    """Host-only: esper_nd_rotation (Generate_Nd_Rot.py:4-45)."""
+    lib = load_library()
+    theta = _as(theta, np.float64).reshape(-1)
+    R = np.empty((n, n), dtype=np.float64)
+    rc = lib.esper_nd_rotation(int(n), _ptr(theta), theta.shape[0], _ptr(R))
+    if rc != ESPER_OK:
+        raise ValueError('%s angles required' % (int(n * (n - 1) / 2)))
+    return R
+
+
+def hist_edges(bins, lo, hi):
+    lib = load_library()
+    e = np.empty(bins + 1, dtype=np.float64)
+    if lib.esper_hist_edges(int(bins), float(lo), float(hi), _ptr(e)) != ESPER_OK:
+        raise ValueError('bad histogram specification')
+    return e
+
+
+_default_ctx = {}
+
+
+def default_context(device: int = 0) -> Context:
+    """Process-wide context per device for the module-level reference-style functions."""
+    key = (os.getpid(), threading.get_ident(), device)
+    ctx = _default_ctx.get(key)
+    if ctx is None:
+        ctx = _default_ctx[key] = Context(device)
+    return ctx

@@ -1,0 +1,256 @@
+// api.cu -- the extern "C" surface declared in include/esper_b200.h.
+#include "common.cuh"
+
+using namespace esper;
+
+static std::string g_create_error;
+
+#define ESPER_ENTER(c)                                                                      \
+    do {                                                                                    \
+        if (!(c)) return ESPER_E_ARG;                                                       \
+        cudaError_t e__ = cudaSetDevice((c)->device);                                       \
+        if (e__ != cudaSuccess) return fail((c), ESPER_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e__)); \
+    } while (0)
+
+extern "C" {
+
+int esper_abi_version(void) { return ESPER_ABI_VERSION; }
+
+esper_ctx* esper_create(int device, void* stream) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        g_create_error = std::string("no CUDA device available: ") + cudaGetErrorString(e) +
+                         " (libesper_b200 has no CPU fallback)";
+        return nullptr;
+    }
+    if (device < 0 || device >= count) { g_create_error = "device ordinal out of range"; return nullptr; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        g_create_error = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+        return nullptr;
+    }
+    if (prop.major != 10) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "device %d (%s) is sm_%d%d; libesper_b200 contains sm_100a code only (tcgen05/TMEM/TMA)",
+                 device, prop.name, prop.major, prop.minor);
+        g_create_error = buf;
+        return nullptr;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return nullptr;
+    }
+    esper_ctx* c = new esper_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (stream) {
+        c->stream = reinterpret_cast<cudaStream_t>(stream);
+    } else {
+        if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+            g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+            delete c;
+            return nullptr;
+        }
+        c->own_stream = true;
+    }
+    return c;
+}
+
+void esper_destroy(esper_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& kv : c->timers)
+        for (auto& pr : kv.second.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto ev : c->event_pool) cudaEventDestroy(ev);
+    DevBuf* bufs[] = {&c->imgs, &c->dist, &c->plane_hi, &c->plane_lo, &c->row_stats, &c->col_part, &c->gram_part,
+                      &c->pair_list, &c->sweep_part, &c->sweep_aux, &c->markov, &c->degree, &c->lan_V, &c->lan_w,
+                      &c->lan_h, &c->lan_small, &c->rot_U, &c->rot_R, &c->rot_idx, &c->rot_out, &c->rot_H,
+                      &c->rot_theta, &c->rot_aux};
+    for (DevBuf* b : bufs) b->release();
+    c->pin.release();
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* esper_last_error(esper_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int esper_sync(esper_ctx* c) {
+    ESPER_ENTER(c);
+    ESPER_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ESPER_OK;
+}
+
+int esper_set_profiling(esper_ctx* c, int on) {
+    ESPER_ENTER(c);
+    c->profiling = on != 0;
+    return ESPER_OK;
+}
+
+static void drain_timers(esper_ctx* c) {
+    for (auto& kv : c->timers) {
+        for (auto& pr : kv.second.pending) {
+            float ms = 0.f;
+            cudaEventSynchronize(pr.second);
+            if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+                kv.second.total_ms += ms;
+                kv.second.launches += 1;
+            }
+            c->event_pool.push_back(pr.first);
+            c->event_pool.push_back(pr.second);
+        }
+        kv.second.pending.clear();
+    }
+}
+
+int esper_get_kernel_ms(esper_ctx* c, const char* name, double* total_ms, int* launches) {
+    ESPER_ENTER(c);
+    if (!name) return fail(c, ESPER_E_ARG, "name is NULL");
+    drain_timers(c);
+    auto it = c->timers.find(name);
+    if (total_ms) *total_ms = it == c->timers.end() ? 0.0 : it->second.total_ms;
+    if (launches) *launches = it == c->timers.end() ? 0 : it->second.launches;
+    return ESPER_OK;
+}
+
+int esper_reset_profiling(esper_ctx* c) {
+    ESPER_ENTER(c);
+    drain_timers(c);
+    for (auto& kv : c->timers) { kv.second.total_ms = 0.0; kv.second.launches = 0; }
+    return ESPER_OK;
+}
+
+long long esper_launch_count(esper_ctx* c) { return c ? c->launches : 0; }
+
+// ---- stage 1 -----------------------------------------------------------------------------------
+int esper_upload_images(esper_ctx* c, const float* imgs, int n, int P) {
+    ESPER_ENTER(c);
+    if (!imgs || n < 1 || P < 1) return fail(c, ESPER_E_ARG, "upload_images: need imgs != NULL, n >= 1, P >= 1");
+    ESPER_RESERVE(c, c->imgs, sizeof(float) * (size_t)n * P);
+    ESPER_CUDA(c, cudaMemcpyAsync(c->imgs.p, imgs, sizeof(float) * (size_t)n * P, cudaMemcpyHostToDevice, c->stream));
+    c->img_n = n; c->img_P = P;
+    return ESPER_OK;
+}
+
+int esper_dist_config(esper_ctx* c, int split_k, double refine_tau) {
+    ESPER_ENTER(c);
+    if (split_k < 0 || refine_tau < 0.0) return fail(c, ESPER_E_ARG, "dist_config: negative value");
+    c->split_k = split_k;
+    c->refine_tau = refine_tau;
+    return ESPER_OK;
+}
+
+int esper_dist_rms(esper_ctx* c, const float* imgs, int n, int P, unsigned flags, double* D) {
+    ESPER_ENTER(c);
+    if (n < 1 || P < 1) return fail(c, ESPER_E_ARG, "dist_rms: need n >= 1 and P >= 1 (got n=%d, P=%d)", n, P);
+    if (imgs) {
+        int rc = esper_upload_images(c, imgs, n, P);
+        if (rc) return rc;
+    } else if (c->img_n != n || c->img_P != P || !c->imgs.p) {
+        return fail(c, ESPER_E_STATE, "dist_rms: imgs == NULL but no resident [%d, %d] stack (resident: [%d, %d])",
+                    n, P, c->img_n, c->img_P);
+    }
+    const int rows_pad = (int)round_up((size_t)n, 128);
+    const int ld = (int)round_up((size_t)P, 32);
+    ESPER_RESERVE(c, c->dist, sizeof(double) * (size_t)n * n);
+    c->dist_m = 0;
+    int rc = run_prep(c, n, P, flags, rows_pad, ld);
+    if (rc) return rc;
+    rc = run_gram(c, n, P, rows_pad, ld, flags);
+    if (rc) return rc;
+    c->dist_m = n;
+    if (D) {
+        ESPER_CUDA(c, cudaMemcpyAsync(D, c->dist.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, c->stream));
+        ESPER_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return ESPER_OK;
+}
+
+int esper_upload_dist(esper_ctx* c, const double* D, int m) {
+    ESPER_ENTER(c);
+    if (!D || m < 1) return fail(c, ESPER_E_ARG, "upload_dist: need D != NULL and m >= 1");
+    ESPER_RESERVE(c, c->dist, sizeof(double) * (size_t)m * m);
+    ESPER_CUDA(c, cudaMemcpyAsync(c->dist.p, D, sizeof(double) * (size_t)m * m, cudaMemcpyHostToDevice, c->stream));
+    c->dist_m = m;
+    return ESPER_OK;
+}
+
+static int need_dist(esper_ctx* c, const double* D, int m, const char* who) {
+    if (m < 1) return fail(c, ESPER_E_ARG, "%s: need m >= 1", who);
+    if (D) return esper_upload_dist(c, D, m);
+    if (c->dist_m != m || !c->dist.p)
+        return fail(c, ESPER_E_STATE, "%s: D == NULL but no resident %dx%d distance matrix (resident m=%d)", who, m, m, c->dist_m);
+    return ESPER_OK;
+}
+
+// ---- stage 2 -----------------------------------------------------------------------------------
+int esper_eps_sweep(esper_ctx* c, const double* D, int m, const double* coef, int n_eps, double thr, double* logSum) {
+    ESPER_ENTER(c);
+    if (!coef || !logSum || n_eps < 1) return fail(c, ESPER_E_ARG, "eps_sweep: need coef, logSum != NULL and n_eps >= 1");
+    int rc = need_dist(c, D, m, "eps_sweep");
+    if (rc) return rc;
+    return run_sweep(c, m, coef, n_eps, thr, logSum);
+}
+
+// ---- stage 3 -----------------------------------------------------------------------------------
+int esper_markov(esper_ctx* c, const double* D, int m, double eps, double* degree, double* Ms) {
+    ESPER_ENTER(c);
+    if (!(eps > 0.0)) return fail(c, ESPER_E_ARG, "markov: eps must be > 0");
+    int rc = need_dist(c, D, m, "markov");
+    if (rc) return rc;
+    rc = run_markov(c, m, eps);
+    if (rc) return rc;
+    if (degree) ESPER_CUDA(c, cudaMemcpyAsync(degree, c->degree.p, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, c->stream));
+    if (Ms) ESPER_CUDA(c, cudaMemcpyAsync(Ms, c->markov.p, sizeof(double) * (size_t)m * m, cudaMemcpyDeviceToHost, c->stream));
+    ESPER_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ESPER_OK;
+}
+
+int esper_dmap_embed(esper_ctx* c, const double* D, int m, double eps, int k, double tol, int max_iter,
+                     double* val, double* vec, int* iters) {
+    ESPER_ENTER(c);
+    if (!(eps > 0.0)) return fail(c, ESPER_E_ARG, "dmap_embed: eps must be > 0");
+    if (k < 1 || k > m) return fail(c, ESPER_E_ARG, "dmap_embed: need 1 <= k <= m (k=%d, m=%d)", k, m);
+    int rc = need_dist(c, D, m, "dmap_embed");
+    if (rc) return rc;
+    rc = run_markov(c, m, eps);
+    if (rc) return rc;
+    return run_lanczos(c, m, k, tol, max_iter, val, vec, iters);
+}
+
+// ---- stage 4 -----------------------------------------------------------------------------------
+int esper_nd_rotation(int n, const double* theta, int n_theta, double* R) {
+    if (n < 1 || !R || (n > 1 && !theta)) return ESPER_E_ARG;
+    if (n_theta != n * (n - 1) / 2) return ESPER_E_ARG;
+    nd_rotation_host(n, theta, R);
+    return ESPER_OK;
+}
+
+int esper_hist_edges(int bins, double lo, double hi, double* edges) {
+    if (bins < 1 || !edges) return ESPER_E_ARG;
+    hist_edges_host(bins, lo, hi, edges);
+    return ESPER_OK;
+}
+
+int esper_rot_hist_eval(esper_ctx* c, const double* Uinit, int n_pd, int m, int dim, const double* R,
+                        const int* pd_of_eval, const int* v1, const int* v2, int n_eval, int bins,
+                        double lo, double hi, int* nonzero, int* H) {
+    ESPER_ENTER(c);
+    if (!Uinit || !R || !pd_of_eval || !v1 || !v2 || !nonzero || n_pd < 1 || m < 1 || n_eval < 1)
+        return fail(c, ESPER_E_ARG, "rot_hist_eval: NULL argument or empty batch");
+    return run_rot_eval(c, Uinit, n_pd, m, dim, R, pd_of_eval, v1, v2, n_eval, bins, lo, hi, nonzero, H);
+}
+
+int esper_rot_sweep(esper_ctx* c, const double* Uinit, int n_pd, int m, int dim, const int* combo,
+                    const int* n_sub, int max_sub, const int* rij, int n_rij, const double* theta_grid,
+                    int n_theta, int bins, double lo, double hi, double* thetas_out, int* counts_out) {
+    ESPER_ENTER(c);
+    if (!Uinit || !combo || !n_sub || (!rij && n_rij > 0) || !theta_grid || !thetas_out || n_pd < 1 || m < 1)
+        return fail(c, ESPER_E_ARG, "rot_sweep: NULL argument or empty batch");
+    return run_rot_sweep(c, Uinit, n_pd, m, dim, combo, n_sub, max_sub, rij, n_rij, theta_grid, n_theta, bins, lo,
+                         hi, thetas_out, counts_out);
+}
+
+}  // extern "C"

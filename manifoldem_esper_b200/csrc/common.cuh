@@ -1,0 +1,164 @@
+// common.cuh -- context, error handling, device-buffer and profiling plumbing shared by the kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/esper_b200.h"
+
+namespace esper {
+
+// A growable device buffer owned by the ctx.
+struct DevBuf {
+    void*  p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return -1; }
+        cap = bytes;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf {
+    void*  p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return -1; }
+        cap = bytes;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct KernelTimer {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    double total_ms = 0.0;
+    int launches = 0;
+};
+
+}  // namespace esper
+
+struct esper_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+
+    // profiling
+    bool profiling = false;
+    std::map<std::string, esper::KernelTimer> timers;
+    std::vector<cudaEvent_t> event_pool;
+    long long launches = 0;
+
+    bool attr_gram = false, attr_sweep = false;
+    // stage-1 configuration
+    int split_k = 0;
+    double refine_tau = 0.05;
+
+    // resident data
+    esper::DevBuf imgs;     int img_n = 0, img_P = 0;          // raw float32 stack [n, P]
+    esper::DevBuf dist;     int dist_m = 0;                    // float64 [m, m]
+    // stage-1 workspaces
+    esper::DevBuf plane_hi, plane_lo;                          // [rows_pad, ld] float32 (tf32 values)
+    esper::DevBuf row_stats;                                   // per image: mean32, std32 (float2) + norm (double)
+    esper::DevBuf col_part;                                    // column-mean partials
+    esper::DevBuf gram_part;                                   // split-K partial tiles
+    esper::DevBuf pair_list;                                   // refine: flagged pairs + counter
+    // stage-2/3 workspaces
+    esper::DevBuf sweep_part, sweep_aux;
+    esper::DevBuf markov, degree;                              // Ms [m,m], d [m]
+    esper::DevBuf lan_V, lan_w, lan_h, lan_small;              // Lanczos basis etc.
+    // stage-4 workspaces
+    esper::DevBuf rot_U, rot_R, rot_idx, rot_out, rot_H, rot_theta, rot_aux;
+    esper::PinBuf pin;                                         // small pinned staging area
+};
+
+namespace esper {
+
+inline int fail(esper_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define ESPER_CUDA(c, call)                                                                    \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            cudaGetLastError();                                                                \
+            return esper::fail((c), ESPER_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,   \
+                               cudaGetErrorString(e__));                                       \
+        }                                                                                      \
+    } while (0)
+
+#define ESPER_RESERVE(c, buf, bytes)                                                           \
+    do {                                                                                       \
+        if ((buf).reserve(bytes) != 0)                                                         \
+            return esper::fail((c), ESPER_E_NOMEM, "device allocation of %zu bytes failed (%s)", \
+                               (size_t)(bytes), #buf);                                         \
+    } while (0)
+
+// Scoped CUDA-event timer around one kernel launch (only when profiling is on).
+struct LaunchScope {
+    esper_ctx* c;
+    cudaEvent_t a = nullptr, b = nullptr;
+    const char* name;
+    LaunchScope(esper_ctx* ctx, const char* nm) : c(ctx), name(nm) {
+        c->launches++;
+        if (!c->profiling) return;
+        a = get(); b = get();
+        cudaEventRecord(a, c->stream);
+    }
+    ~LaunchScope() {
+        if (!a) return;
+        cudaEventRecord(b, c->stream);
+        c->timers[name].pending.emplace_back(a, b);
+    }
+    cudaEvent_t get() {
+        if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+};
+
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// ---- per-stage entry points implemented in the .cu files (host side) ----
+int prep_and_gram(esper_ctx* c, int n, int P, unsigned flags);                 // k0_prep.cu + k1_gram.cu
+int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld);
+int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags);
+int run_sweep(esper_ctx* c, int m, const double* coef_h, int n_eps, double thr, double* logsum_h);
+int run_markov(esper_ctx* c, int m, double eps);
+int run_lanczos(esper_ctx* c, int m, int k, double tol, int max_iter, double* val_h, double* vec_h, int* iters);
+int run_rot_eval(esper_ctx* c, const double* Uinit, int n_pd, int m, int dim, const double* R,
+                 const int* pd_of_eval, const int* v1, const int* v2, int n_eval, int bins,
+                 double lo, double hi, int* nonzero, int* H);
+int run_rot_sweep(esper_ctx* c, const double* Uinit, int n_pd, int m, int dim, const int* combo,
+                  const int* n_sub, int max_sub, const int* rij, int n_rij, const double* theta_grid,
+                  int n_theta, int bins, double lo, double hi, double* thetas_out, int* counts_out);
+void nd_rotation_host(int n, const double* theta, double* R);
+void hist_edges_host(int bins, double lo, double hi, double* edges);
+
+}  // namespace esper

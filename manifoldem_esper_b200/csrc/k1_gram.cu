@@ -1,0 +1,467 @@
+// k1_gram.cu -- K1: symmetric 3xTF32 Gram contraction on tcgen05 tensor cores (TMA -> smem -> UMMA ->
+// TMEM), split-K partial tiles combined in FP64 by the distance epilogue, plus the direct-difference
+// refinement for cancelling pairs.  Replaces the double loop of 1_Embedding/DM/Distances.py:96-104.
+//
+// Work decomposition
+//   G = C C^T with C [n, K] the centred standardised images (K = ld, zero padded), only the upper
+//   triangle of 128x128 output tiles is computed.  A work unit is (k-chunk, tile); units are ordered
+//   chunk-major so that the CTAs resident at any time stream the SAME K range of the planes and the
+//   operand working set (n x chunk x 8 B) stays in L2.  Each unit accumulates
+//       hi*hi + hi*lo + lo*hi          (3xTF32: operands split into two TF32 values, FP32 accumulate)
+//   over its chunk in TMEM and writes an FP32 partial tile; chains are kept short (<= ~2048 pixels)
+//   because tensor-core FP32 accumulation is not round-to-nearest; partials are summed in FP64.
+//
+// Kernel structure (one CTA per SM, persistent over units, 192 threads):
+//   warp 0     TMA producer   (cp.async.bulk.tensor.2d, 128B swizzle, mbarrier complete_tx)
+//   warp 1     MMA issuer     (tcgen05.mma.cta_group::1.kind::tf32, one elected lane) + TMEM alloc
+//   warps 2-5  epilogue       (tcgen05.ld 32x32b -> registers -> coalesced FP32 partial tile)
+//   smem ring: 3 stages x {A_hi, A_lo, B_hi, B_lo} x (128 rows x 32 fp32) = 3 x 64 KB
+//   TMEM: 2 accumulator buffers x 128 columns (double buffered against the epilogue)
+#include <cuda.h>
+#include "common.cuh"
+#include "devutil.cuh"
+
+namespace esper {
+namespace gram {
+
+constexpr int BM = 128;                 // tile rows  (UMMA M)
+constexpr int BN = 128;                 // tile cols  (UMMA N)
+constexpr int BK = 32;                  // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int UK = 8;                   // UMMA K for kind::tf32 (32 bytes)
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 4; // 16 KB
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = ACC_STAGES * BN;  // 256
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (rows of 128 B, 8-row groups 1024 B apart).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);   // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                     // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;           // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                     // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                     // layout: SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor: D=F32, A=B=TF32, both K-major, N=128, M=128.
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Upper-triangular tile index t -> (ti, tj), tj >= ti, row-major over the triangle.
+__device__ __forceinline__ void tile_coords(int t, int nt, int& ti, int& tj) {
+    int i = 0, rem = t;
+    while (rem >= nt - i) { rem -= nt - i; ++i; }
+    ti = i; tj = i + rem;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The Gram kernel
+//   part: [split_k * n_tiles] tiles of 128x128 FP32 in "tile-native" order: element (r, c) of a
+//         tile lives at ((c>>2)*128 + r)*4 + (c&3)  (so that a warp's 32 rows store 512 contiguous B)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gram_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+            int nt, int n_tiles, int tile0, int nkb, int split_k, float* __restrict__ part) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // 1024-byte aligned operand ring
+    const uint32_t bars = base + STAGES * STAGE_BYTES;
+    const uint32_t full_bar = bars;                                     // STAGES x 8 B
+    const uint32_t empty_bar = bars + 8 * STAGES;                       // STAGES x 8 B
+    const uint32_t tfull_bar = bars + 16 * STAGES;                      // ACC_STAGES x 8 B
+    const uint32_t tempty_bar = tfull_bar + 8 * ACC_STAGES;             // ACC_STAGES x 8 B
+    const uint32_t tmem_slot = tempty_bar + 8 * ACC_STAGES;             // 4 B
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_units = n_tiles * split_k;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_hi);
+        tma_prefetch_desc(&map_lo);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar + 8 * a, 1); mbar_init(tempty_bar + 8 * a, 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+                const int chunk = u / n_tiles, t = tile0 + (u % n_tiles);
+                int ti, tj; tile_coords(t, nt, ti, tj);
+                const bool diag = (ti == tj);
+                const int kb0 = (int)((long long)nkb * chunk / split_k);
+                const int kb1 = (int)((long long)nkb * (chunk + 1) / split_k);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                    const uint32_t sa = base + stage * STAGE_BYTES;
+                    const uint32_t fb = full_bar + 8 * stage;
+                    mbar_expect_tx(fb, diag ? 2 * TILE_BYTES : 4 * TILE_BYTES);
+                    tma_load_2d(sa, &map_hi, fb, kb * BK, ti * BM);
+                    tma_load_2d(sa + TILE_BYTES, &map_lo, fb, kb * BK, ti * BM);
+                    if (!diag) {
+                        tma_load_2d(sa + 2 * TILE_BYTES, &map_hi, fb, kb * BK, tj * BN);
+                        tma_load_2d(sa + 3 * TILE_BYTES, &map_lo, fb, kb * BK, tj * BN);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+                const int chunk = u / n_tiles, t = tile0 + (u % n_tiles);
+                int ti, tj; tile_coords(t, nt, ti, tj);
+                const bool diag = (ti == tj);
+                const int kb0 = (int)((long long)nkb * chunk / split_k);
+                const int kb1 = (int)((long long)nkb * (chunk + 1) / split_k);
+                mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                uint32_t accumulate = 0;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(full_bar + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * STAGE_BYTES;
+                    const uint32_t a_hi = sa, a_lo = sa + TILE_BYTES;
+                    const uint32_t b_hi = diag ? a_hi : sa + 2 * TILE_BYTES;
+                    const uint32_t b_lo = diag ? a_lo : sa + 3 * TILE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UK; ++k) {
+                        const uint32_t off = k * UK * 4;   // 32 bytes per UMMA K step inside the swizzle row
+                        const uint64_t dah = make_smem_desc(a_hi + off), dal = make_smem_desc(a_lo + off);
+                        const uint64_t dbh = make_smem_desc(b_hi + off), dbl = make_smem_desc(b_lo + off);
+                        umma_tf32(tmem_d, dal, dbh, accumulate);   // small cross terms first
+                        umma_tf32(tmem_d, dah, dbl, 1);
+                        umma_tf32(tmem_d, dah, dbh, 1);
+                        accumulate = 1;
+                    }
+                    umma_commit(empty_bar + 8 * stage);            // frees the smem stage when the MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull_bar + 8 * acc);                  // accumulator complete -> epilogue
+                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+        const int row = quad * 32 + lane;          // tile row held by this thread
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+            mbar_wait(tfull_bar + 8 * acc, acc_phase);
+            tc_fence_after();
+            float4* out = reinterpret_cast<float4*>(part + (size_t)u * (BM * BN));
+#pragma unroll 1
+            for (int cc = 0; cc < BN / 32; ++cc) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + cc * 32), r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                           __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                    out[(size_t)(cc * 8 + q) * BM + row] = v;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Distance epilogue: D_ij = sqrt(max(|c_i|^2 + |c_j|^2 - 2 sum_chunks G_ij, 0) / P), mirrored, diag 0.
+// One block per tile; thread -> (row r, 4 columns).  FP64 combination in fixed chunk order.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dist_finalize_kernel(const float* __restrict__ part, int nt, int n_tiles, int tile0, int split_k, int n, int P,
+                     const RowStat* __restrict__ st, double* __restrict__ D) {
+    const int lt = blockIdx.x;
+    int ti, tj; tile_coords(tile0 + lt, nt, ti, tj);
+    const bool diag = (ti == tj);
+    const double invP = 1.0 / (double)P;
+    for (int e = threadIdx.x; e < BM * (BN / 4); e += blockDim.x) {
+        const int r = e & (BM - 1), c4 = e >> 7;
+        const int i = ti * BM + r;
+        if (i >= n) continue;
+        double g[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int ch = 0; ch < split_k; ++ch) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(part + (size_t)(ch * n_tiles + lt) * (BM * BN)) + e);
+            g[0] += (double)v.x; g[1] += (double)v.y; g[2] += (double)v.z; g[3] += (double)v.w;
+        }
+        const double ni = st[i].norm2;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = c4 * 4 + q;
+            const int j = tj * BN + c;
+            if (j >= n) continue;
+            if (diag && c <= r) { if (c == r) D[(size_t)i * n + i] = 0.0; continue; }
+            double d2 = (ni + st[j].norm2 - 2.0 * g[q]) * invP;
+            d2 = d2 > 0.0 ? d2 : 0.0;
+            const double d = sqrt(d2);
+            D[(size_t)i * n + j] = d;
+            D[(size_t)j * n + i] = d;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Refinement of cancelling pairs by direct differences (the reference's own arithmetic:
+// float64 sum of squared differences of the float32 standardised images).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+flag_pairs_kernel(const double* __restrict__ D, int n, int P, const RowStat* __restrict__ st, double tau,
+                  int2* __restrict__ pairs, unsigned int* __restrict__ count, unsigned int cap) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n * n) return;
+    const int i = (int)(idx / n), j = (int)(idx % n);
+    if (j <= i) return;
+    const double d = D[idx];
+    if (d * d * (double)P < tau * (st[i].norm2 + st[j].norm2)) {
+        const unsigned int k = atomicAdd(count, 1u);
+        if (k < cap) pairs[k] = make_int2(i, j);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+refine_pairs_kernel(const float* __restrict__ raw, int n, int P, const RowStat* __restrict__ st,
+                    const int2* __restrict__ pairs, const unsigned int* __restrict__ count, unsigned int cap,
+                    double* __restrict__ D) {
+    __shared__ double sh[32];
+    unsigned int total = *count;
+    if (total > cap) total = cap;
+    for (unsigned int k = blockIdx.x; k < total; k += gridDim.x) {
+        const int2 pr = pairs[k];
+        const float* a = raw + (size_t)pr.x * P;
+        const float* b = raw + (size_t)pr.y * P;
+        const float ma = st[pr.x].mean, sa = st[pr.x].stdv, mb = st[pr.y].mean, sb = st[pr.y].stdv;
+        double acc = 0.0;
+        for (int p = threadIdx.x; p < P; p += blockDim.x) {
+            const double df = (double)zscore(__ldg(a + p), ma, sa) - (double)zscore(__ldg(b + p), mb, sb);
+            acc += df * df;
+        }
+        acc = block_sum(acc, sh);
+        if (threadIdx.x == 0) {
+            const double d = sqrt(acc / (double)P);
+            D[(size_t)pr.x * n + pr.y] = d;
+            D[(size_t)pr.y * n + pr.x] = d;
+        }
+    }
+}
+
+}  // namespace gram
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+static int make_plane_map(esper_ctx* c, CUtensorMap* map, float* plane, int rows_pad, int ld) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(c, ESPER_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows_pad};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)gram::BK, (cuuint32_t)gram::BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, plane, gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(c, ESPER_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return ESPER_OK;
+}
+
+// Choose the number of K chunks: chains of <= ~2048 pixels, and a unit count that fills the SMs.
+static int choose_split_k(int requested, int nkb, int n_tiles, int sms) {
+    if (requested > 0) return requested < nkb ? requested : nkb;
+    int s = ceil_div(nkb, 64);                     // 64 k-blocks = 2048 pixels per chain
+    if (s < 1) s = 1;
+    if (n_tiles * s < sms) s = ceil_div(sms, n_tiles);
+    // nudge s upward (at most +25%) to the value with the best last-wave fill
+    int best = s; double best_eff = 0.0;
+    for (int cand = s; cand <= s + s / 4 + 1; ++cand) {
+        long long units = (long long)n_tiles * cand;
+        long long waves = (units + sms - 1) / sms;
+        double eff = (double)units / (double)(waves * sms);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = cand; }
+    }
+    if (best > nkb) best = nkb;
+    return best < 1 ? 1 : best;
+}
+
+int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags) {
+    using namespace gram;
+    const int nt = rows_pad / BM;
+    const int tiles_total = nt * (nt + 1) / 2;
+    const int nkb = ld / BK;
+    const int sms = c->sm_count;
+    const RowStat* st = c->row_stats.as<RowStat>();
+    double* D = c->dist.as<double>();
+
+    CUtensorMap map_hi, map_lo;
+    int rc = make_plane_map(c, &map_hi, c->plane_hi.as<float>(), rows_pad, ld);
+    if (rc) return rc;
+    rc = make_plane_map(c, &map_lo, c->plane_lo.as<float>(), rows_pad, ld);
+    if (rc) return rc;
+
+    if (!c->attr_gram) {
+        ESPER_CUDA(c, cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        c->attr_gram = true;
+    }
+
+    // Bound the split-K workspace: process the triangle in batches of tiles.
+    const size_t tile_bytes = (size_t)BM * BN * sizeof(float);
+    const size_t ws_cap = (size_t)3 << 30;   // 3 GiB
+    int batch = tiles_total;
+    int split_k = choose_split_k(c->split_k, nkb, batch, sms);
+    while ((size_t)batch * split_k * tile_bytes > ws_cap && batch > sms) {
+        batch = (batch + 1) / 2;
+        split_k = choose_split_k(c->split_k, nkb, batch, sms);
+    }
+    ESPER_RESERVE(c, c->gram_part, (size_t)batch * split_k * tile_bytes);
+    float* part = c->gram_part.as<float>();
+
+    for (int tile0 = 0; tile0 < tiles_total; tile0 += batch) {
+        const int nb = (tiles_total - tile0 < batch) ? tiles_total - tile0 : batch;
+        int sk = choose_split_k(c->split_k, nkb, nb, sms);
+        if (sk > split_k) sk = split_k;
+        const int units = nb * sk;
+        const int grid = units < sms ? units : sms;
+        {
+            LaunchScope ls(c, "gram");
+            gram_kernel<<<grid, NUM_THREADS, SMEM_BYTES, c->stream>>>(map_hi, map_lo, nt, nb, tile0, nkb, sk, part);
+        }
+        {
+            LaunchScope ls(c, "dist_finalize");
+            dist_finalize_kernel<<<nb, 256, 0, c->stream>>>(part, nt, nb, tile0, sk, n, P, st, D);
+        }
+    }
+    ESPER_CUDA(c, cudaGetLastError());
+
+    if ((flags & ESPER_DIST_REFINE) && c->refine_tau > 0.0 && n > 1) {
+        const unsigned int cap = (unsigned int)(((size_t)n * (n - 1) / 2 < (size_t)1 << 26) ? (size_t)n * (n - 1) / 2 : (size_t)1 << 26);
+        ESPER_RESERVE(c, c->pair_list, sizeof(int2) * (size_t)cap + 256);
+        unsigned int* count = c->pair_list.as<unsigned int>();
+        int2* pairs = reinterpret_cast<int2*>(c->pair_list.as<char>() + 256);
+        ESPER_CUDA(c, cudaMemsetAsync(count, 0, sizeof(unsigned int), c->stream));
+        {
+            LaunchScope ls(c, "refine");
+            const long long tot = (long long)n * n;
+            flag_pairs_kernel<<<ceil_div(tot, 256), 256, 0, c->stream>>>(D, n, P, st, c->refine_tau, pairs, count, cap);
+        }
+        {
+            LaunchScope ls(c, "refine");
+            refine_pairs_kernel<<<sms * 8, 256, 0, c->stream>>>(c->imgs.as<float>(), n, P, st, pairs, count, cap, D);
+        }
+        ESPER_CUDA(c, cudaGetLastError());
+    }
+    return ESPER_OK;
+}
+
+}  // namespace esper

@@ -1,0 +1,162 @@
+// k2_sweep.cu -- K2: the epsilon sweep of 1_Embedding/DM/GaussianBandwidth.py:36-44,
+//     logSum[k] = log sum_{ij : t < thr} exp(-t),   t = coef[k] * D_ij^2,   k = 0 .. n_eps-1.
+//
+// The reference evaluates all m^2 * n_eps terms.  For a block of elements the sweep value is known
+// in closed form for most k: if coef[k]*min_nonzero(D^2) >= thr every non-zero element is truncated
+// (only exact zeros, e.g. the diagonal, contribute 1), and if coef[k]*max(D^2) < 2^-60 every term is
+// exp(-t) == 1.0 in binary64.  Only the k in between (~220 of 1001 for a span of e^0.2 per step) need
+// exp().  The inclusion test uses the same products t = coef*D2 as the reference, so it is bit-exact.
+//
+// One pass over D (coalesced, 8 elements per thread), per-k sums accumulated in shared memory per
+// persistent block, fixed-order FP64 reductions (deterministic).  FP64-ALU bound on the active k.
+#include "common.cuh"
+#include "devutil.cuh"
+
+namespace esper {
+namespace sweep {
+
+constexpr int THREADS = 256;
+constexpr int EPT = 8;                       // elements per thread per chunk
+constexpr int CHUNK = THREADS * EPT;         // 2048 elements
+constexpr int KB = 8;                        // k values reduced per barrier pair
+constexpr int WARPS = THREADS / 32;
+
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__global__ void __launch_bounds__(THREADS)
+sweep_kernel(const double* __restrict__ D, long long total, const double* __restrict__ coef, int n_eps,
+             double thr, double* __restrict__ part /*[gridDim.x][n_eps]*/) {
+    extern __shared__ double sm[];
+    double* acc = sm;                         // [n_eps]
+    double* cf = sm + n_eps;                  // [n_eps]
+    double* red = cf + n_eps;                 // [WARPS][KB]
+    double* stat = red + WARPS * KB;          // [4][WARPS] min, max, n_zero, n_valid
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double TINY = 8.673617379884035e-19;   // 2^-60: exp(-t) == 1.0 for 0 <= t < TINY
+
+    for (int k = threadIdx.x; k < n_eps; k += THREADS) { acc[k] = 0.0; cf[k] = coef[k]; }
+    __syncthreads();
+
+    const long long n_chunks = (total + CHUNK - 1) / CHUNK;
+    for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+        double d2[EPT];
+        double mn = INFINITY, mx = 0.0, nz = 0.0, nv = 0.0;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const long long idx = ch * CHUNK + (long long)e * THREADS + threadIdx.x;
+            d2[e] = INFINITY;                // out of range / NaN: never included (t = inf or NaN is not < thr)
+            if (idx < total) {
+                const double d = __ldg(D + idx);
+                const double q = d * d;
+                if (q == q) {
+                    d2[e] = q;
+                    nv += 1.0;
+                    if (q == 0.0) nz += 1.0; else mn = fmin(mn, q);
+                    mx = fmax(mx, q);
+                }
+            }
+        }
+        mn = warp_min(mn); mx = warp_max(mx); nz = warp_sum(nz); nv = warp_sum(nv);
+        if (lane == 0) { stat[warp] = mn; stat[WARPS + warp] = mx; stat[2 * WARPS + warp] = nz; stat[3 * WARPS + warp] = nv; }
+        __syncthreads();
+        mn = stat[0]; mx = stat[WARPS]; nz = 0.0; nv = 0.0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            mn = fmin(mn, stat[w]); mx = fmax(mx, stat[WARPS + w]);
+            nz += stat[2 * WARPS + w]; nv += stat[3 * WARPS + w];
+        }
+        const double zero_term = (0.0 < thr) ? nz : 0.0;
+
+        for (int k0 = 0; k0 < n_eps; k0 += KB) {
+#pragma unroll
+            for (int j = 0; j < KB; ++j) {
+                const int k = k0 + j;
+                double s = 0.0;
+                if (k < n_eps) {
+                    const double c = cf[k];
+                    const bool shortcut = (c >= 0.0) && (c < INFINITY);   // monotone t = c*d2, no NaN products
+                    if (shortcut && (mn == INFINITY || !(c * mn < thr))) {
+                        // no non-zero element passes the truncation; exact zeros give exp(-0) = 1
+                        s = (threadIdx.x == 0) ? zero_term : 0.0;
+                    } else if (shortcut && c * mx < TINY && c * mx < thr) {
+                        // every element passes and exp(-t) == 1.0 in binary64
+                        s = (threadIdx.x == 0) ? nv : 0.0;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < EPT; ++e) {
+                            const double t = c * d2[e];
+                            if (t < thr) s += exp(-t);
+                        }
+                    }
+                    s = warp_sum(s);
+                }
+                if (lane == 0) red[warp * KB + j] = s;
+            }
+            __syncthreads();
+            if (threadIdx.x < KB && k0 + threadIdx.x < n_eps) {
+                double t = 0.0;
+#pragma unroll
+                for (int w = 0; w < WARPS; ++w) t += red[w * KB + threadIdx.x];
+                acc[k0 + threadIdx.x] += t;
+            }
+            __syncthreads();
+        }
+    }
+    for (int k = threadIdx.x; k < n_eps; k += THREADS) part[(size_t)blockIdx.x * n_eps + k] = acc[k];
+}
+
+__global__ void __launch_bounds__(256)
+sweep_final_kernel(const double* __restrict__ part, int n_blocks, int n_eps, double* __restrict__ logsum) {
+    __shared__ double sh[32];
+    const int k = blockIdx.x;
+    double s = 0.0;
+    for (int b = threadIdx.x; b < n_blocks; b += blockDim.x) s += part[(size_t)b * n_eps + k];
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) logsum[k] = log(s);
+}
+
+}  // namespace sweep
+
+int run_sweep(esper_ctx* c, int m, const double* coef_h, int n_eps, double thr, double* logsum_h) {
+    using namespace sweep;
+    const long long total = (long long)m * m;
+    const long long n_chunks = (total + CHUNK - 1) / CHUNK;
+    int grid = c->sm_count * 4;
+    if (grid > n_chunks) grid = (int)n_chunks;
+    if (grid < 1) grid = 1;
+    ESPER_RESERVE(c, c->sweep_part, sizeof(double) * (size_t)grid * n_eps);
+    ESPER_RESERVE(c, c->sweep_aux, sizeof(double) * (size_t)n_eps * 2);
+    double* coef_d = c->sweep_aux.as<double>();
+    double* logsum_d = coef_d + n_eps;
+    ESPER_CUDA(c, cudaMemcpyAsync(coef_d, coef_h, sizeof(double) * n_eps, cudaMemcpyHostToDevice, c->stream));
+    const size_t smem = sizeof(double) * ((size_t)2 * n_eps + WARPS * KB + 4 * WARPS);
+    if (smem > 200 * 1024) return fail(c, ESPER_E_ARG, "n_eps=%d too large for the sweep kernel", n_eps);
+    if (!c->attr_sweep) {
+        ESPER_CUDA(c, cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        c->attr_sweep = true;
+    }
+    {
+        LaunchScope ls(c, "sweep");
+        sweep_kernel<<<grid, THREADS, smem, c->stream>>>(c->dist.as<double>(), total, coef_d, n_eps, thr,
+                                                         c->sweep_part.as<double>());
+    }
+    {
+        LaunchScope ls(c, "sweep");
+        sweep_final_kernel<<<n_eps, 256, 0, c->stream>>>(c->sweep_part.as<double>(), grid, n_eps, logsum_d);
+    }
+    ESPER_CUDA(c, cudaGetLastError());
+    ESPER_CUDA(c, cudaMemcpyAsync(logsum_h, logsum_d, sizeof(double) * n_eps, cudaMemcpyDeviceToHost, c->stream));
+    ESPER_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ESPER_OK;
+}
+
+}  // namespace esper

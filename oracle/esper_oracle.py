@@ -254,22 +254,30 @@ def gen_nd_rotations(n: int, theta) -> np.ndarray:
     return R
 
 
-def gen_nd_rotations_givens(n: int, theta) -> np.ndarray:
-    """Same product as `gen_nd_rotations`, applied as T column-pair updates without FMA.
+def _fma(a: float, b: float, c: float) -> float:
+    """Correctly rounded a*b + c (exact rational arithmetic; slow, small cases only)."""
+    from fractions import Fraction
+    return float(Fraction(a) * Fraction(b) + Fraction(c))
 
-    Multiplying on the right by G_r only changes columns (k, j):
-        R[:,k] <- R[:,k]*c + R[:,j]*s ;  R[:,j] <- R[:,k]*(-s) + R[:,j]*c
-    every other column is multiplied by 1 and summed with exact zeros.  This is the
-    arithmetic the CUDA kernel performs (explicit round-to-nearest mul/add).  It can differ
-    from the BLAS product in the last bit when the BLAS kernel fuses the two-term sums.
+
+def gen_nd_rotations_givens(n: int, theta) -> np.ndarray:
+    """Same product as `gen_nd_rotations`, applied as T column-pair updates.
+
+    Multiplying on the right by G_r only changes columns (k, j); every other column is
+    multiplied by 1 and summed with exact zeros.  A dgemm micro-kernel accumulates each output
+    over the inner index in ascending order with fused multiply-adds, so the two-term sums are
+        R[:,k] <- fma(R[:,j], s, fl(R[:,k]*c)) ;  R[:,j] <- fma(R[:,j], c, fl(R[:,k]*(-s)))
+    which is the arithmetic of the C/CUDA code (esper_nd_rotation, K5) and reproduces the
+    reference's `ndarray.dot` chain bit for bit on the golden vectors (tests/test_oracle.py).
     """
     theta = np.asarray(theta, dtype=np.float64).reshape(-1)
     R = np.eye(n)
     for r, (k, j) in enumerate(plane_list(n)):
         c, s = math.cos(theta[r]), math.sin(theta[r])
-        ck, cj = R[:, k].copy(), R[:, j].copy()
-        R[:, k] = ck * c + cj * s
-        R[:, j] = ck * (-1. * s) + cj * c
+        for i in range(n):
+            a, b = float(R[i, k]), float(R[i, j])
+            R[i, k] = _fma(b, s, a * c)
+            R[i, j] = _fma(b, c, a * (-1. * s))
     return R
 
 
