@@ -2,7 +2,7 @@
 
 Host-side glue called by Rotation_Histograms.findParabolas.  The reference solves the normal
 equations with sympy's `Matrix.rref`; for floating-point entries that routine is a fraction-free
-Gauss-Jordan elimination in 53-bit arithmetic (first non-zero pivot, rows normalised last), which
+Gauss-Jordan elimination in 53-bit arithmetic (largest-magnitude pivot, rows normalised last), which
 `_rref_solve` restates in numpy float64 so no symbolic package is needed.
 """
 import numpy as np
@@ -17,11 +17,12 @@ def _rref_solve(A_aug):
     for piv_col in range(cols):
         if piv_row >= rows:
             break
-        nz = np.nonzero(M[piv_row:, piv_col])[0]
-        if nz.size == 0:
+        col_abs = np.abs(M[piv_row:, piv_col])
+        off = int(np.argmax(col_abs))                 # numeric column: partial pivoting, first maximum
+        if col_abs[off] == 0:
             continue
-        if nz[0] != 0:
-            r = piv_row + nz[0]
+        if off != 0:
+            r = piv_row + off
             M[[piv_row, r]] = M[[r, piv_row]]
         pivots.append(piv_col)
         pv = M[piv_row, piv_col]

@@ -243,7 +243,7 @@ def gen_nd_rotations(n: int, theta) -> np.ndarray:
         raise ValueError('%sx1 array of angles required' % (total))
     R = None
     for r, (k, j) in enumerate(plane_list(n)):
-        t = theta[r]
+        t = float(np.asarray(theta[r]).reshape(-1)[0])
         c, s = math.cos(t), math.sin(t)
         G = np.eye(n)
         G[k, k] = c

@@ -1,0 +1,252 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU oracle and the
+golden vectors generated from the reference.  Tolerances are the ones BASELINE.json's north_star
+states: distances 1e-5 relative, eigenvalues 1e-6 relative at identical epsilon, eigenvectors 1e-4
+up to sign, histograms / rotation angles bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from manifoldem_esper_b200 import (DiffusionMaps, Distances, GaussianBandwidth, Rotation_Histograms as RH, _capi, mrc,
+                                   synth)
+from oracle import esper_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+D_TOL = 1e-5          # relative, on D
+D_FLOOR = 1e-2        # |dD| <= D_TOL * max(D, D_FLOOR)  (exact duplicates have D = 0)
+VAL_TOL = 1e-6
+VEC_TOL = 1e-4
+LOG_EPS = np.arange(-100, 100.2, 0.2)
+
+
+def d_err(D, Dr):
+    return float(np.max(np.abs(D - Dr) / np.maximum(Dr, D_FLOOR)))
+
+
+def vec_err(u, v):
+    return min(np.abs(u - v).max(), np.abs(u + v).max())
+
+
+# ---- stage 1 ----------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['stage123_small', 'stage123_pristine', 'stage1_dupes'])
+def test_distances_vs_reference_golden(ctx, name):
+    g = golden(name + '.npz')
+    D = ctx.dist_rms(g['stack'])
+    assert d_err(D, g['D']) < D_TOL
+    assert np.array_equal(D, D.T) and np.all(np.diag(D) == 0) and np.all(np.isfinite(D))
+    if name == 'stage1_dupes':
+        n = D.shape[0]
+        assert np.all(D[np.arange(0, n, 2), np.arange(1, n, 2)] == 0)       # exact duplicates -> exactly 0
+
+
+@pytest.mark.parametrize('n', [1, 2, 3, 127, 129, 257])
+@pytest.mark.parametrize('P', [16, 1000, 128 * 128])
+def test_distances_tile_and_k_tails(ctx, n, P):
+    X = np.random.default_rng(n * 7 + P).standard_normal((n, P)).astype(np.float32)
+    D = ctx.dist_rms(X)
+    Dr = O.distances_gram_f64(O.standardize_stack(X.reshape(n, 1, P)))
+    assert D.shape == (n, n) and d_err(D, Dr) < D_TOL
+
+
+def test_distances_unstandardized_and_unaligned_P(ctx):
+    X = np.random.default_rng(5).standard_normal((70, 999)).astype(np.float32) * 3 + 1
+    D = ctx.dist_rms(X, flags=_capi.DIST_CENTER)                             # no z-score: caller's values as is
+    Dr = O.distances_gram_f64(X.astype(np.float64).reshape(70, 1, 999))
+    assert d_err(D, Dr) < D_TOL
+
+
+def test_distances_linearity_property(ctx):
+    """Size-independent property: scaling all images by s scales D by s (no standardisation)."""
+    X = np.random.default_rng(9).standard_normal((300, 2048)).astype(np.float32)
+    D1 = ctx.dist_rms(X, flags=_capi.DIST_CENTER)
+    D2 = ctx.dist_rms(X * np.float32(4.0), flags=_capi.DIST_CENTER)          # exact power-of-two scaling
+    assert np.array_equal(D2, 4.0 * D1)
+
+
+def test_distances_full_size_vs_f64_gram(ctx):
+    """BASELINE config 2 shape: N=2000, 250x250, tau=5, SNR 0.1 against the float64 Gram oracle."""
+    stack = synth.synthetic_pd(pd=1, box=250, n_side=20, tau=5, snr=0.1)
+    Dr = O.distances_gram_f64(O.standardize_stack(stack))
+    D = ctx.dist_rms(stack)
+    assert d_err(D, Dr) < D_TOL
+    d2, d2r = D * D, Dr * Dr
+    off = ~np.eye(D.shape[0], dtype=bool)
+    assert abs(np.mean((d2 - d2r)[off] / d2r[off])) < 1e-7                   # no systematic accumulation bias
+    # resident-stack chaining gives the same bits as the host-pointer call
+    assert np.array_equal(ctx.dist_rms(None, n=2000, P=62500), D)
+
+
+def test_distances_errors(ctx):
+    with pytest.raises(ValueError):
+        ctx.dist_rms(None, n=7, P=9)                                          # nothing resident of that shape
+    with pytest.raises(ValueError):
+        ctx.dist_rms(np.zeros((0, 4), np.float32))
+
+
+def test_distances_op_files(ctx, tmp_path):
+    g = golden('stage123_small.npz')
+    root = tmp_path / 'tree'
+    dm = root / '1_Embedding' / 'DM'
+    data = root / '0_Data_Inputs' / 'CTF5k15k_SNRpt1_ELS_2D'
+    os.makedirs(dm); os.makedirs(data)
+    mrc.write_stack(str(data / 'PD003_SNR_tau5_stack.mrcs'), g['stack'])
+    Distances.op(str(dm), '003', ctx=ctx)
+    D = np.load(str(dm / 'Data_Distances' / 'PD_003_dist.npy'))
+    assert D.dtype == np.float64 and D.flags.c_contiguous and d_err(D, g['D']) < D_TOL
+    DiffusionMaps.op(str(dm), '003', k=8, ctx=ctx)
+    val = np.load(str(dm / 'Data_Manifolds' / 'PD_003_val.npy'))
+    vec = np.load(str(dm / 'Data_Manifolds' / 'PD_003_vec.npy'))
+    assert val.shape == (8,) and vec.shape == (D.shape[0], 8) and abs(val[0] - 1) < 1e-12
+
+
+# ---- stage 2 ----------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['stage123_small', 'stage123_pristine', 'stage23_medium', 'stage1_dupes'])
+def test_eps_sweep_vs_reference_golden(ctx, name):
+    g = golden(name + '.npz')
+    D = g['D']
+    L = GaussianBandwidth.sweep(D, LOG_EPS, ctx=ctx)
+    Lr = g['logSumWij'] if 'logSumWij' in g else O.eps_sweep_logsum(D, LOG_EPS)
+    assert np.max(np.abs(L - Lr)) < 1e-9
+    m = D.shape[0]
+    assert abs(L[0] - np.log(m + (D == 0).sum() - m)) < 1e-12 or abs(L[0] - np.log((D == 0).sum())) < 1e-12
+    assert abs(L[-1] - np.log(m * m)) < 1e-12                                  # plateaus: log(#zeros), log(m^2)
+
+
+def test_bandwidth_op_same_seed_same_epsilon(ctx):
+    g = golden('stage23_medium.npz')
+    np.random.seed(int(g['seed']))
+    a0 = 1 * (np.random.rand(4, 1) - .5)
+    popt, L, resnorm, R2 = GaussianBandwidth.op(g['D'], LOG_EPS, a0, ctx=ctx)
+    eps = np.exp(-(popt[1] / popt[0]))
+    assert abs(eps - float(g['eps'])) / float(g['eps']) < 1e-7
+    assert abs(R2 - float(g['R2'])) < 1e-9
+
+
+def test_eps_sweep_general_coefficients(ctx):
+    """Unsorted coefficients, no truncation, zero coefficient: the closed-form shortcuts stay exact."""
+    D = golden('stage123_small.npz')['D']
+    coef = np.array([0.0, 1e-30, 3.0, 0.5, 1e6, 2.0, 1e-3])
+    for thr in (10.0, np.inf, 0.5):
+        L = ctx.eps_sweep(D, coef, thr)
+        ref = []
+        for c in coef:
+            d = c * (D * D)
+            ref.append(np.log(np.sum(np.exp(-d[d < thr]))))
+        assert np.allclose(L, ref, rtol=0, atol=1e-12)
+
+
+# ---- stage 3 ----------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['stage123_pristine', 'stage23_medium'])
+def test_markov_matrix_vs_oracle(ctx, name):
+    g = golden(name + '.npz')
+    A, d, Ms_r = O.markov_symmetric(g['D'], float(g['eps']))
+    deg, Ms = ctx.markov(g['D'], float(g['eps']))
+    assert np.max(np.abs(deg - d) / d) < 1e-14
+    assert np.max(np.abs(Ms - Ms_r)) / np.max(np.abs(Ms_r)) < 1e-14
+    assert np.allclose(Ms, Ms.T, rtol=1e-8, atol=1e-8)                         # the reference's is_symmetric check
+
+
+@pytest.mark.parametrize('name,k', [('stage123_pristine', 12), ('stage23_medium', 16), ('stage123_small', 16)])
+def test_embedding_vs_reference_golden_at_fixed_eps(ctx, name, k):
+    g = golden(name + '.npz')
+    val, vec, iters = ctx.dmap_embed(g['D'], float(g['eps']), k=k)
+    assert np.max(np.abs(val - g['val'][:k]) / g['val'][:k]) < VAL_TOL
+    assert vec_err(vec[:, 0], g['vec'][:, 0]) < VEC_TOL and np.all(vec[:, 0] > 0)
+    lam = np.sqrt(g['val'][:k + 1])
+    gaps = np.minimum(np.abs(np.diff(lam))[:-1], np.abs(np.diff(lam))[1:]) if k > 2 else []
+    for i in range(1, k - 1):                                                 # well separated -> per vector
+        if gaps[i - 1] > 1e-3 * lam[1]:
+            assert vec_err(vec[:, i], g['vec'][:, i]) < VEC_TOL, i
+    # all k as a subspace (principal angles), orthonormality, residuals
+    s = np.linalg.svd(vec.T @ g['vec'][:, :k], compute_uv=False)
+    assert s.min() > 1 - 1e-6 or lam[k - 1] - lam[k] < 1e-3 * lam[1]
+    assert np.max(np.abs(vec.T @ vec - np.eye(k))) < 1e-10
+    Ms = O.markov_symmetric(g['D'], float(g['eps']))[2]
+    assert np.max(np.linalg.norm(Ms @ vec - vec * np.sqrt(val)[None, :], axis=0)) < 1e-9
+
+
+def test_embed_end_to_end_matches_reference_run(ctx):
+    """Distances -> sweep -> seeded fit -> embedding on the GPU vs the reference run with the same seed."""
+    g = golden('stage123_pristine.npz')
+    D = ctx.dist_rms(g['stack'])
+    np.random.seed(int(g['seed']))
+    res = DiffusionMaps.embed(D, k=8, ctx=ctx, verbose=False)
+    assert abs(res['eps'] - float(g['eps'])) / float(g['eps']) < 1e-4
+    val_r, U_r = O.dmap_embed(g['D'], res['eps'])                             # parity at identical epsilon
+    assert np.max(np.abs(res['val'] - val_r[:8]) / val_r[:8]) < 2e-5          # carries the 1e-5 distance error
+    for i in range(4):
+        assert vec_err(res['vec'][:, i], U_r[:, i]) < 1e-3
+
+
+def test_embed_argument_errors(ctx):
+    D = golden('stage123_small.npz')['D']
+    with pytest.raises(ValueError):
+        ctx.dmap_embed(D, -1.0, k=4)
+    with pytest.raises(ValueError):
+        ctx.dmap_embed(D, 0.3, k=D.shape[0] + 1)
+    val, vec, _ = ctx.dmap_embed(D, 0.3, k=1)
+    assert val[0] == 1.0 and vec.shape == (D.shape[0], 1)
+
+
+# ---- stage 4 ----------------------------------------------------------------------------------
+def test_histograms_bit_exact_vs_numpy(ctx):
+    fx = golden('rot_inputs.npz')
+    rng = np.random.default_rng(3)
+    for key, dim in [('PD001', 6), ('PD064', 8)]:
+        Ui = O.initial_subspace(fx[key], dim, PCA=True)
+        T = dim * (dim - 1) // 2
+        Rs, v1s, v2s, Href = [], [], [], []
+        for e in range(24):
+            th = np.zeros((T, 1)); th[rng.integers(0, T, 3)] = rng.uniform(-0.7, 0.7, (3, 1))
+            R = O.gen_nd_rotations(dim, th)
+            v1, v2 = sorted(rng.choice(dim, 2, replace=False))
+            H, _ = O.rot_hist_eval(Ui, R, v1, v2)
+            Rs.append(R); v1s.append(v1); v2s.append(v2); Href.append(H.astype(np.int32))
+        nz, H = ctx.rot_hist_eval(Ui, np.stack(Rs), [0] * 24, v1s, v2s, want_hist=True)
+        assert np.array_equal(H, np.stack(Href))
+        assert np.array_equal(nz, [np.count_nonzero(h) for h in Href])
+        assert np.all(H.sum(axis=(1, 2)) <= Ui.shape[0])
+
+
+def test_histogram_edge_rule(ctx):
+    U = np.array([[-1.5, 1.5], [1.5, -1.5], [0.0, 0.0], [1.6, 0.0], [np.nextafter(1.5, 2), 0.0], [np.nan, 0.0]])
+    nz, H = ctx.rot_hist_eval(U, np.eye(2)[None], [0], [0], [1], want_hist=True)
+    Hr, _ = O.rot_hist_eval(U[:5], np.eye(2), 0, 1)
+    assert np.array_equal(H[0], Hr.astype(np.int32)) and nz[0] == 3
+
+
+@pytest.mark.parametrize('dim', [6, 8])
+def test_rotation_sweep_vs_reference_run(ctx, dim):
+    """RotMatrices for the 12 committed fixtures equal the reference's output bit for bit; per-evaluation
+    non-zero-bin counts equal the ones spied from the reference run."""
+    fx, ref, cnt = golden('rot_inputs.npz'), golden('rot_ref_dim%d.npz' % dim), golden('rot_counts_dim8.npz')
+    keys = list(fx.keys())
+    preps = [RH.prepare(fx[k], dim=dim, PCA=True, CTF=True) for k in keys]
+    thetas, counts = RH.sweep_many(preps, dim, ctx=ctx, want_counts=True)
+    for i, k in enumerate(keys):
+        assert np.array_equal(thetas[i], ref['RotMatrices_' + k[2:]]), k
+        assert np.array_equal(preps[i]['saveEigs'], ref['RotEigenfunctions_' + k[2:]])
+        if dim == 8 and k in cnt:
+            assert np.array_equal(counts[i, :len(preps[i]['comboList'])].reshape(-1), cnt[k])
+
+
+def test_rotation_op_files(ctx, tmp_path):
+    fx, ref = golden('rot_inputs.npz'), golden('rot_ref_dim6.npz')
+    root = tmp_path / 'tree'
+    os.makedirs(root / '2_Manifold_Rotations'); os.makedirs(root / '1_Embedding' / 'PCA' / 'Data_Manifold')
+    np.save(str(root / '1_Embedding' / 'PCA' / 'Data_Manifold' / 'PD_017_vec.npy'), fx['PD017'])
+    RH.op(str(root / '2_Manifold_Rotations'), '017', dim=6, PCA=True, ctx=ctx)
+    out = root / '2_Manifold_Rotations' / 'Data_Rotations' / 'PD017'
+    assert np.array_equal(np.load(str(out / 'PD017_RotMatrices.npy')), ref['RotMatrices_017'])
+    assert np.array_equal(np.load(str(out / 'PD017_RotEigenfunctions.npy')), ref['RotEigenfunctions_017'])
+    assert np.array_equal(np.load(str(out / 'PD017_RotParameters.npy')), np.array([6]))
+
+
+def test_rotation_sweep_argument_errors(ctx):
+    U = np.zeros((1, 10, 6))
+    with pytest.raises(ValueError):
+        ctx.rot_sweep(U, np.array([[[0, 9]]]), [1], [[0]], RH.theta_grid())   # v2 out of range
+    with pytest.raises(ValueError):
+        ctx.rot_sweep(U, np.array([[[0, 1]]]), [1], [[15]], RH.theta_grid())  # Rij out of range

@@ -1,0 +1,145 @@
+"""CPU: host-side logic, the C-ABI surface and the no-fallback rule (no GPU needed)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden
+from manifoldem_esper_b200 import (ConicFit, Distances, Generate_Nd_Rot, Rotation_Histograms as RH, _capi,
+                                   launcher, mrc, synth)
+from oracle import esper_oracle as O
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, 'include', 'esper_b200.h')).read()
+    txt = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)
+    return sorted(set(re.findall(r'\b(esper_[a-z_0-9]+)\s*\(', txt)))
+
+
+def test_library_exports_every_declared_symbol(lib_built):
+    lib = ctypes.CDLL(lib_built)
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), 'libesper_b200.so does not export %s' % s
+    assert sorted(_capi.SIGNATURES) == syms                      # the ctypes table covers the whole header
+    assert _capi.load_library().esper_abi_version() == 1
+
+
+def test_library_is_sm100a_tcgen05_code(lib_built):
+    import subprocess
+    sass = subprocess.run(['cuobjdump', '-sass', lib_built], capture_output=True, text=True).stdout
+    assert 'sm_100a' in sass
+    for mnemonic in ('UTCHMMA', 'UTMALDG', 'LDTM'):               # tcgen05.mma, TMA, tcgen05.ld
+        assert mnemonic in sass, mnemonic
+
+
+def test_no_cpu_fallback(lib_built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    with pytest.raises(_capi.EsperError):
+        _capi.Context(0)
+    with pytest.raises(_capi.EsperError):
+        Distances.distances(np.zeros((4, 16), np.float32))
+
+
+def test_nd_rotation_bits_and_errors(lib_built):
+    g = golden('nd_rot.npz')
+    for n in (2, 3, 6, 8):
+        th, R = g['theta_%d' % n], g['R_%d' % n]
+        T = n * (n - 1) // 2
+        for i in range(th.shape[0]):
+            assert np.array_equal(Generate_Nd_Rot.genNdRotations(n, th[i].reshape(T, 1)), R[i])
+            assert np.array_equal(Generate_Nd_Rot.genNdRotations(n, th[i]), R[i])
+            assert np.array_equal(Generate_Nd_Rot.genNdRotations(n, list(th[i])), R[i])
+        with pytest.raises(ValueError):
+            Generate_Nd_Rot.genNdRotations(n, [0.0] * (T + 1))
+        with pytest.raises(ValueError):
+            Generate_Nd_Rot.genNdRotations(n, np.zeros((T + 1, 1)))
+    assert np.array_equal(Generate_Nd_Rot.genNdRotations(1, []), np.eye(1))
+
+
+def test_hist_edges_equal_numpy_linspace(lib_built):
+    for bins, lo, hi in [(51, -1.5, 1.5), (7, 0.1, 0.9), (64, -3.0, 2.0)]:
+        assert np.array_equal(_capi.hist_edges(bins, lo, hi), np.linspace(lo, hi, bins + 1))
+
+
+def test_conic_fits_equal_sympy_rref():
+    U0 = golden('rot_inputs.npz')['PD017']
+    Ui = O.initial_subspace(U0, 6, True)
+    for v1, v2 in [(0, 1), (0, 2), (1, 4), (3, 5)]:
+        a = ConicFit.fit2(Ui, v1, v2)
+        cF1, R2 = O.conic_fit2(Ui, v1, v2)
+        assert np.array_equal(a[0], cF1) and a[3] == R2
+        b = ConicFit.fit3(Ui, v1, v2)
+        cF, R2b = O.conic_fit3(Ui, v1, v2)
+        assert np.array_equal(b[0], cF) and b[1] == R2b
+
+
+@pytest.mark.parametrize('dim', [6, 8])
+def test_rotation_plan_equals_oracle(dim):
+    fx = golden('rot_inputs.npz')
+    for key in ['PD001', 'PD048', 'PD126']:
+        p = RH.prepare(fx[key], dim=dim, PCA=True, CTF=True)
+        Ui = O.initial_subspace(fx[key], dim, True)
+        psi, Ui2, it = O.find_parabolas(dim, Ui, 1, True)
+        cl, se, cf, rij = O.rotation_plan(dim, psi)
+        assert p['comboList'] == [(a, int(b)) for a, b in cl]
+        assert p['Rij_final'] == rij and p['itIdx'] == it
+        assert np.array_equal(p['saveEigs'], se) and np.array_equal(p['U_init'], Ui2)
+    assert np.array_equal(RH.normalize(fx['PD001']), O.normalize_manifold(fx['PD001']))
+    assert np.array_equal(RH.theta_grid(), np.arange(-40, 40, .5) * np.pi / 180)
+
+
+def test_mrc_roundtrip(tmp_path):
+    st = np.random.default_rng(0).standard_normal((5, 8, 8)).astype(np.float32)
+    p = str(tmp_path / 'PD_001.mrcs')
+    mrc.write_stack(p, st)
+    assert os.path.getsize(p) == 1024 + st.nbytes
+    m = mrc.mmap(p, 'r')
+    assert m.data.shape == (5, 8, 8) and np.array_equal(np.asarray(m.data), st)
+    m.close()
+    with open(p, 'r+b') as f:
+        f.truncate(1024 + 10)
+    with pytest.raises(ValueError):
+        mrc.mmap(p)
+
+
+def test_distances_ctf_branch_is_out_of_scope(tmp_path):
+    with pytest.raises(NotImplementedError):
+        Distances.op(str(tmp_path), '001', CTF=True)
+
+
+def test_argument_errors_raise_valueerror():
+    with pytest.raises(ValueError):
+        _capi._check_stack(np.zeros((0, 4), np.float32))
+    with pytest.raises(ValueError):
+        _capi._check_square(np.zeros((3, 4)))
+
+
+def test_synthetic_generator_is_seeded():
+    a = synth.synthetic_pd(pd=2, box=16, n_side=3, tau=2, snr=0.1)
+    b = synth.synthetic_pd(pd=2, box=16, n_side=3, tau=2, snr=0.1)
+    assert a.dtype == np.float32 and a.shape == (18, 16, 16) and np.array_equal(a, b)
+    d = synth.synthetic_pd(pd=2, box=16, n_side=3, tau=2, snr=None)
+    assert np.array_equal(d[0], d[1]) and not np.array_equal(d[0], d[2])
+
+
+def test_pd_parsing_and_sharding():
+    pds = launcher.parse_pds('1-5,9,12-13')
+    assert pds == ['001', '002', '003', '004', '005', '009', '012', '013']
+    parts = [launcher.shard(pds, r, 3) for r in range(3)]
+    assert sorted(sum(parts, [])) == pds and max(map(len, parts)) - min(map(len, parts)) <= 1
+    with pytest.raises(ValueError):
+        launcher.shard(pds, 3, 3)
+
+    def work(pd):
+        if pd == '003':
+            raise RuntimeError('boom')
+        return {'x': int(pd)}
+    recs = launcher.run_sharded(pds, work, 0, 1)
+    assert [r['ok'] for r in recs] == [True, True, False, True, True, True, True, True]
+    assert 'boom' in recs[2]['error']
