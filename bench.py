@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark: PDs embedded per second (BASELINE.json metric), B200 arm and CPU reference arm.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one projection direction (PD) through the hot path: pairwise RMS distances (K0+K1) ->
+epsilon sweep (K2) -> host tanh fit -> Gaussian kernel / degree normalisation (K3) -> leading
+eigenpairs (K4).  Workload at every N: BASELINE config 2, one synthetic PD of N=2000 images,
+250x250 px, tau=5, SNR 0.1, 1001-point eps sweep, top-10 eigenpairs; with N GPUs every rank embeds
+its own PDs (config 3 sharding, no data-path collective) -> weak scaling.
+
+`value`  : inputs resident in HBM when the timed region starts (each PD stack is 500 MB > the 126 MB L2).
+`e2e`    : the same steps through the reference-facing Python API with HOST (pinned) image stacks,
+           H2D of every stack and D2H of the distance matrix / sweep / eigenpairs inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_IMG, BOX, TAU, SNR, K_EIG = 2000, 250, 5, 0.1, 10
+P = BOX * BOX
+LOG_EPS = np.arange(-100, 100.2, 0.2)
+METRIC = 'PDs embedded per second (N=2000 images, 250x250 px; dist + eps sweep + top-10 eigenpairs)'
+UNIT = 'PD/s'
+WORKLOAD = 'C2: single synthetic PD, N=2000 images of 250x250 px (tau=5, SNR 0.1), eps sweep (1001) + top-10 eigenvectors'
+
+
+def env_rank():
+    return int(os.environ.get('RANK', '0')), int(os.environ.get('LOCAL_RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference algorithm on a bounded sample of the same workload
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(stack, n_loop=64, n_eps_sample=8, full_eig=True):
+    """Time the reference algorithm (oracle port, as written) on a bounded sample and scale to one PD.
+
+    distances : the per-pair Python loop of Distances.py:96-104 on the first `n_loop` images, scaled by
+                the pair count to N=2000;
+    eps sweep : GaussianBandwidth.py:36-44 on the full N=2000 distance matrix for `n_eps_sample` of the
+                1001 epsilons spread over the grid (sequential float64 sum), scaled by 1001/n_eps_sample;
+    kernel + degree + normalisation + full SVD (DiffusionMaps.py:109-169) at full size, not scaled.
+    Returns (seconds per PD, detail dict).
+    """
+    from oracle import esper_oracle as O
+    n = stack.shape[0]
+    t0 = time.perf_counter()
+    X = O.standardize_stack(stack[:n_loop])
+    O.distances_as_written(X)
+    t_loop = time.perf_counter() - t0
+    pairs_s, pairs_full = n_loop * (n_loop - 1) // 2, n * (n - 1) // 2
+    t_dist = t_loop * pairs_full / pairs_s
+    t0 = time.perf_counter()
+    D = O.distances_gram_f64(O.standardize_stack(stack))            # only to obtain D for the later stages
+    t_vec_dist = time.perf_counter() - t0
+    ks = np.linspace(0, len(LOG_EPS) - 1, n_eps_sample).astype(int)
+    t0 = time.perf_counter()
+    O.eps_sweep_logsum(D, LOG_EPS[ks], sequential=True)
+    t_sweep = (time.perf_counter() - t0) * len(LOG_EPS) / len(ks)
+    t_eig = 0.0
+    if full_eig:
+        t0 = time.perf_counter()
+        O.dmap_embed(D, 0.2834)
+        t_eig = time.perf_counter() - t0
+    total = t_dist + t_sweep + t_eig
+    detail = dict(dist_loop_s=t_dist, sweep_s=t_sweep, kernel_svd_s=t_eig, vectorised_dist_s=t_vec_dist,
+                  vectorised_total_s=t_vec_dist + t_sweep + t_eig)
+    return total, detail
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([i.get('num_threads', 1) for i in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank, _, world = env_rank()
+    if rank != 0:
+        return 0
+    from manifoldem_esper_b200 import synth
+    stack = synth.synthetic_pd(pd=1, box=BOX, n_side=20, tau=TAU, snr=SNR)
+    times, detail = [], {}
+    for it in range(args.warmup + args.steps):
+        t, detail = cpu_sample(stack, n_loop=48, n_eps_sample=4, full_eig=True)
+        if it >= args.warmup:
+            times.append(t)
+    sec = float(np.mean(times))
+    sample = ('oracle port of the reference as written: pair loop on 48 images scaled x%d to N=2000, eps sweep on 4 of 1001 '
+              'eps scaled x250, full-size kernel+SVD; per step' % (N_IMG * (N_IMG - 1) // 2 // (48 * 47 // 2)))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': 1.0 / sec, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic', 'config': {'workload': WORKLOAD, 'host': 'cpu'},
+        'cpu_baseline': {'value': 1.0 / sec, 'unit': UNIT, 'cores': blas_threads(), 'kind': 'port', 'sample': sample,
+                         'detail_s_per_pd': detail},
+        'e2e': {'value': 1.0 / sec, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.proc, self.lines, self.idx = None, [], gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def embed_step(ctx, GB, coef, a0, n, p, imgs=None, download=False):
+    """One PD through stages 1-3 on `ctx`.  imgs=None -> the ctx-resident stack."""
+    D = ctx.dist_rms(imgs, n=n, P=p, download=download)
+    L = ctx.eps_sweep(None, coef, 10.0, m=n)
+    popt, resnorm, R2 = GB.fit(LOG_EPS, L, a0)
+    eps = float(np.exp(-(popt[1] / popt[0])))
+    val, vec, iters = ctx.dmap_embed(None, eps, k=K_EIG, m=n)
+    return D, eps, val, vec, iters
+
+
+def run_ours(args):
+    import torch
+    from manifoldem_esper_b200 import GaussianBandwidth as GB, _capi, synth
+    rank, local_rank, world = env_rank()
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    torch.cuda.set_device(local_rank)
+    stream = torch.cuda.Stream()
+    ctx = _capi.Context(local_rank, stream=stream.cuda_stream)
+
+    # two distinct PD stacks per rank in pinned host memory (inputs of successive steps differ)
+    n_stacks = 2
+    pinned = []
+    for s in range(n_stacks):
+        st = synth.synthetic_pd(pd=1 + rank * n_stacks + s, box=BOX, n_side=20, tau=TAU, snr=SNR).reshape(N_IMG, P)
+        t = torch.from_numpy(st).pin_memory()
+        pinned.append(t)
+    coef = 1. / (2. * np.exp(LOG_EPS))
+    a0 = np.array([[-0.2], [0.3], [-0.4], [0.1]])          # fixed tanh-fit start (the reference draws it at random)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- kernel-resident arm: stacks already in HBM; alternate two resident ctxs' worth of data ----
+    # (one ctx holds one resident stack; a second ctx on the same stream holds the other)
+    ctx_b = _capi.Context(local_rank, stream=stream.cuda_stream)
+    ctxs = [ctx, ctx_b]
+    for c, t in zip(ctxs, pinned):
+        c.upload_images(t.numpy())
+        c.sync()
+    for w in range(args.warmup):
+        embed_step(ctxs[w % 2], GB, coef, a0, N_IMG, P)
+    for c in ctxs:
+        c.set_profiling(True); c.reset_profiling()
+    launches0 = sum(c.launch_count() for c in ctxs)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    iters_used = []
+    for s in range(args.steps):
+        out = embed_step(ctxs[s % 2], GB, coef, a0, N_IMG, P)
+        iters_used.append(out[4])
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = sum(c.launch_count() for c in ctxs) - launches0
+    kern = {}
+    for name in ('prep', 'gram', 'dist_finalize', 'refine', 'sweep', 'markov', 'lanczos'):
+        tot, cnt = 0.0, 0
+        for c in ctxs:
+            a, b = c.kernel_ms(name)
+            tot += a; cnt += b
+        kern[name] = (tot, cnt)
+    for c in ctxs:
+        c.set_profiling(False)
+
+    # ---- end-to-end arm: host stacks -> H2D -> stages -> D2H of D, sweep, eigenpairs --------------
+    for w in range(min(args.warmup, 2)):
+        embed_step(ctx, GB, coef, a0, N_IMG, P, imgs=pinned[w % 2].numpy(), download=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for s in range(args.steps):
+        embed_step(ctx, GB, coef, a0, N_IMG, P, imgs=pinned[s % 2].numpy(), download=True)
+    e1.record(stream)
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    tms = torch.tensor([ms, ms_e2e, float(launches)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        import torch.distributed as dist
+        mx = tms.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tms.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, ms_e2e, launches = float(mx[0]), float(mx[1]), int(sm[2])
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return 0
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    bf16_sus = peaks.get('bf16_tflops_sustained')
+    peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained / 2: dense TF32 is half the bf16 rate on tcgen05)'
+    if not bf16_sus:
+        bf16_sus, peak_src = 1400.0, 'fallback (B200_PROFILING.md sustained 1.4 PFLOP/s bf16 / 2)'
+    tf32_peak = bf16_sus / 2.0
+    gram_ms = kern['gram'][0] / max(kern['gram'][1], 1)
+    alg_flops = 2.0 * N_IMG * N_IMG * P                           # GEMM convention, SURVEY 8(d)
+    n_tiles = (N_IMG + 127) // 128
+    issued_flops = 3.0 * (n_tiles * (n_tiles + 1) // 2) * 128 * 128 * ((P + 31) // 32 * 32) * 2.0
+    achieved = alg_flops / (gram_ms * 1e-3) / 1e12 if gram_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'gram_traffic.json'))).get('dram_bytes_per_launch')
+    except Exception:
+        pass
+    hbm_peak = peaks.get('hbm_gbs', 6650.0)
+    lan_ms_per_step = kern['lanczos'][0] / max(args.steps, 1)
+    per_step = {k: round(v[0] / max(args.steps, 1), 4) for k, v in kern.items()}
+
+    pds = world * args.steps
+    line = {
+        'metric': METRIC, 'value': pds / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32x3+f64',
+        'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'pd_per_rank_per_step': 1, 'sharding': 'independent PDs per rank, no data-path collective',
+                   'l2': 'inputs larger than L2 (500 MB stack per PD, two alternating stacks per rank)',
+                   'lanczos_steps': iters_used[-1] if iters_used else None},
+        'e2e': {'value': pds / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(N_IMG * P * 4),
+                'd2h_bytes_per_step': int(N_IMG * N_IMG * 8 + len(LOG_EPS) * 8 + K_EIG * 8 + N_IMG * K_EIG * 8),
+                'ms_per_step': ms_e2e / args.steps},
+        'gpu_launches': launches,
+        'clocks': clocks,
+        'roofline': {'bound': 'tensor', 'kernel': 'gram_kernel (tcgen05 kind::tf32, 3xTF32, upper triangle)',
+                     'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': achieved / tf32_peak if tf32_peak else None,
+                     'traffic': traffic, 'peak_source': peak_src, 'flops_per_launch': alg_flops,
+                     'flops_convention': '2*N^2*P (full GEMM); the kernel issues 3 TF32 MMAs per product on the upper triangle only',
+                     'issued_tflops': issued_flops / (gram_ms * 1e-3) / 1e12 if gram_ms > 0 else 0.0,
+                     'avg_launch_ms': gram_ms, 'launches_timed': kern['gram'][1]},
+        'kernel_ms_per_step': per_step,
+        'roofline_hbm': {'bound': 'hbm', 'kernel': 'lanczos (symv + reorthogonalisation), Ms L2-resident at N=2000',
+                         'achieved': (np.mean(iters_used) * N_IMG * N_IMG * 8 / (lan_ms_per_step * 1e-3) / 1e9) if lan_ms_per_step > 0 else 0.0,
+                         'peak': hbm_peak, 'unit': 'GB/s'},
+    }
+    line['roofline_hbm']['frac'] = line['roofline_hbm']['achieved'] / hbm_peak if hbm_peak else None
+    if world == 1 and not args.no_cpu_baseline:
+        t0 = time.time()
+        sec, detail = cpu_sample(pinned[0].numpy().reshape(N_IMG, BOX, BOX), n_loop=160, n_eps_sample=16, full_eig=True)
+        line['cpu_baseline'] = {
+            'value': 1.0 / sec, 'unit': UNIT, 'cores': blas_threads(), 'kind': 'port',
+            'sample': 'oracle port of the reference as written: pair loop on 160 of 2000 images (12720 pairs) scaled x157 by pair '
+                      'count, eps sweep on 16 of 1001 eps scaled x62.6, kernel+degree+full SVD at full size; %.0f s of CPU work' % (time.time() - t0),
+            'detail_s_per_pd': detail, 'vectorised_value': 1.0 / detail['vectorised_total_s'],
+            'vectorised_note': 'same math restated with a float64 dgemm Gram instead of the pair loop (not the reference)'}
+    print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())
