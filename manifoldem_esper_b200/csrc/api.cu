@@ -161,6 +161,7 @@ int esper_dist_rms(esper_ctx* c, const float* imgs, int n, int P, unsigned flags
     rc = run_gram(c, n, P, rows_pad, ld, flags);
     if (rc) return rc;
     c->dist_m = n;
+    c->dist_symmetric = 1;                  // mirrored writes: symmetric by construction
     if (D) {
         ESPER_CUDA(c, cudaMemcpyAsync(D, c->dist.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, c->stream));
         ESPER_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -174,6 +175,7 @@ int esper_upload_dist(esper_ctx* c, const double* D, int m) {
     ESPER_RESERVE(c, c->dist, sizeof(double) * (size_t)m * m);
     ESPER_CUDA(c, cudaMemcpyAsync(c->dist.p, D, sizeof(double) * (size_t)m * m, cudaMemcpyHostToDevice, c->stream));
     c->dist_m = m;
+    c->dist_symmetric = -1;
     return ESPER_OK;
 }
 
@@ -215,6 +217,9 @@ int esper_dmap_embed(esper_ctx* c, const double* D, int m, double eps, int k, do
     if (k < 1 || k > m) return fail(c, ESPER_E_ARG, "dmap_embed: need 1 <= k <= m (k=%d, m=%d)", k, m);
     int rc = need_dist(c, D, m, "dmap_embed");
     if (rc) return rc;
+    if (c->dist_symmetric < 0 && (rc = check_symmetry(c, m))) return rc;
+    if (c->dist_symmetric == 0)
+        return fail(c, ESPER_E_ARG, "dmap_embed: the distance matrix is not symmetric (the Lanczos solver needs Ms = Ms^T)");
     rc = run_markov(c, m, eps);
     if (rc) return rc;
     return run_lanczos(c, m, k, tol, max_iter, val, vec, iters);

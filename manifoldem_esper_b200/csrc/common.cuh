@@ -76,6 +76,7 @@ struct esper_ctx {
     // resident data
     esper::DevBuf imgs;     int img_n = 0, img_P = 0;          // raw float32 stack [n, P]
     esper::DevBuf dist;     int dist_m = 0;                    // float64 [m, m]
+    int dist_symmetric = -1;                                   // 1 symmetric, 0 not, -1 unknown (checked lazily)
     // stage-1 workspaces
     esper::DevBuf plane_hi, plane_lo;                          // [rows_pad, ld] float32 (tf32 values)
     esper::DevBuf row_stats;                                   // per image: mean32, std32 (float2) + norm (double)
@@ -150,6 +151,7 @@ int prep_and_gram(esper_ctx* c, int n, int P, unsigned flags);                 /
 int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld);
 int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags);
 int run_sweep(esper_ctx* c, int m, const double* coef_h, int n_eps, double thr, double* logsum_h);
+int check_symmetry(esper_ctx* c, int m);
 int run_markov(esper_ctx* c, int m, double eps);
 int run_lanczos(esper_ctx* c, int m, int k, double tol, int max_iter, double* val_h, double* vec_h, int* iters);
 int run_rot_eval(esper_ctx* c, const double* Uinit, int n_pd, int m, int dim, const double* R,

@@ -17,7 +17,6 @@ namespace sweep {
 
 constexpr int THREADS = 256;
 constexpr int EPT = 8;                       // elements per thread per chunk
-constexpr int CHUNK = THREADS * EPT;         // 2048 elements
 constexpr int KB = 8;                        // k values reduced per barrier pair
 constexpr int WARPS = THREADS / 32;
 
@@ -32,8 +31,12 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
+constexpr int TR = 16;                       // tile rows
+constexpr int TC = 128;                      // tile columns (a warp reads 32 consecutive doubles of a row)
+
+// sym != 0: D is exactly symmetric; only elements j >= i are visited, off-diagonal ones weigh 2.
 __global__ void __launch_bounds__(THREADS)
-sweep_kernel(const double* __restrict__ D, long long total, const double* __restrict__ coef, int n_eps,
+sweep_kernel(const double* __restrict__ D, int m, int sym, const double* __restrict__ coef, int n_eps,
              double thr, double* __restrict__ part /*[gridDim.x][n_eps]*/) {
     extern __shared__ double sm[];
     double* acc = sm;                         // [n_eps]
@@ -42,30 +45,39 @@ sweep_kernel(const double* __restrict__ D, long long total, const double* __rest
     double* stat = red + WARPS * KB;          // [4][WARPS] min, max, n_zero, n_valid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const double TINY = 8.673617379884035e-19;   // 2^-60: exp(-t) == 1.0 for 0 <= t < TINY
+    const double SMALL = 7.450580596923828e-09;  // 2^-27: exp(-t) = 1 - t + t^2/2 to < 1e-25 relative
 
     for (int k = threadIdx.x; k < n_eps; k += THREADS) { acc[k] = 0.0; cf[k] = coef[k]; }
     __syncthreads();
 
-    const long long n_chunks = (total + CHUNK - 1) / CHUNK;
-    for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
-        double d2[EPT];
+    const int tiles_c = (m + TC - 1) / TC, tiles_r = (m + TR - 1) / TR;
+    const long long n_tiles = (long long)tiles_r * tiles_c;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int tr = (int)(tile / tiles_c), tc = (int)(tile % tiles_c);
+        const int row0 = tr * TR, col0 = tc * TC;
+        if (sym && col0 + TC - 1 < row0) continue;               // tile entirely below the diagonal
+        double d2[EPT], wt[EPT];
         double mn = INFINITY, mx = 0.0, nz = 0.0, nv = 0.0;
+        const int j = col0 + (threadIdx.x & (TC - 1));
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
-            const long long idx = ch * CHUNK + (long long)e * THREADS + threadIdx.x;
-            d2[e] = INFINITY;                // out of range / NaN: never included (t = inf or NaN is not < thr)
-            if (idx < total) {
-                const double d = __ldg(D + idx);
+            const int i = row0 + (threadIdx.x >> 7) * EPT + e;
+            d2[e] = INFINITY;                // excluded / NaN: never included (t = inf or NaN is not < thr)
+            wt[e] = 0.0;
+            if (i < m && j < m && (!sym || j >= i)) {
+                const double d = __ldg(D + (size_t)i * m + j);
                 const double q = d * d;
                 if (q == q) {
-                    d2[e] = q;
-                    nv += 1.0;
-                    if (q == 0.0) nz += 1.0; else mn = fmin(mn, q);
+                    const double w = (sym && j > i) ? 2.0 : 1.0;
+                    d2[e] = q; wt[e] = w;
+                    nv += w;
+                    if (q == 0.0) nz += w; else mn = fmin(mn, q);
                     mx = fmax(mx, q);
                 }
             }
         }
         mn = warp_min(mn); mx = warp_max(mx); nz = warp_sum(nz); nv = warp_sum(nv);
+        __syncthreads();
         if (lane == 0) { stat[warp] = mn; stat[WARPS + warp] = mx; stat[2 * WARPS + warp] = nz; stat[3 * WARPS + warp] = nv; }
         __syncthreads();
         mn = stat[0]; mx = stat[WARPS]; nz = 0.0; nv = 0.0;
@@ -78,8 +90,8 @@ sweep_kernel(const double* __restrict__ D, long long total, const double* __rest
 
         for (int k0 = 0; k0 < n_eps; k0 += KB) {
 #pragma unroll
-            for (int j = 0; j < KB; ++j) {
-                const int k = k0 + j;
+            for (int jj = 0; jj < KB; ++jj) {
+                const int k = k0 + jj;
                 double s = 0.0;
                 if (k < n_eps) {
                     const double c = cf[k];
@@ -90,16 +102,23 @@ sweep_kernel(const double* __restrict__ D, long long total, const double* __rest
                     } else if (shortcut && c * mx < TINY && c * mx < thr) {
                         // every element passes and exp(-t) == 1.0 in binary64
                         s = (threadIdx.x == 0) ? nv : 0.0;
+                    } else if (shortcut && c * mx < SMALL && c * mx < thr) {
+                        // every element passes; three-term series is exact to working precision
+#pragma unroll
+                        for (int e = 0; e < EPT; ++e) {
+                            const double t = c * d2[e];
+                            if (wt[e] != 0.0) s = fma(wt[e], fma(t, fma(t, 0.5, -1.0), 1.0), s);
+                        }
                     } else {
 #pragma unroll
                         for (int e = 0; e < EPT; ++e) {
                             const double t = c * d2[e];
-                            if (t < thr) s += exp(-t);
+                            if (t < thr) s = fma(wt[e], (t < SMALL) ? fma(t, fma(t, 0.5, -1.0), 1.0) : exp(-t), s);
                         }
                     }
                     s = warp_sum(s);
                 }
-                if (lane == 0) red[warp * KB + j] = s;
+                if (lane == 0) red[warp * KB + jj] = s;
             }
             __syncthreads();
             if (threadIdx.x < KB && k0 + threadIdx.x < n_eps) {
@@ -114,6 +133,17 @@ sweep_kernel(const double* __restrict__ D, long long total, const double* __rest
     for (int k = threadIdx.x; k < n_eps; k += THREADS) part[(size_t)blockIdx.x * n_eps + k] = acc[k];
 }
 
+// flag = 0 if D[i][j] != D[j][i] anywhere (bitwise comparison of the values).
+__global__ void __launch_bounds__(256) symmetry_kernel(const double* __restrict__ D, int m, int* __restrict__ flag) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)m * m) return;
+    const int i = (int)(idx / m), j = (int)(idx % m);
+    if (j > i) {
+        const double a = D[idx], b = D[(size_t)j * m + i];
+        if (!(a == b) && !(a != a && b != b)) *flag = 0;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 sweep_final_kernel(const double* __restrict__ part, int n_blocks, int n_eps, double* __restrict__ logsum) {
     __shared__ double sh[32];
@@ -126,16 +156,33 @@ sweep_final_kernel(const double* __restrict__ part, int n_blocks, int n_eps, dou
 
 }  // namespace sweep
 
+int check_symmetry(esper_ctx* c, int m) {
+    ESPER_RESERVE(c, c->sweep_aux, sizeof(double) * 4096);
+    int* flag = reinterpret_cast<int*>(c->sweep_aux.as<double>() + 4000);
+    int one = 1;
+    ESPER_CUDA(c, cudaMemcpyAsync(flag, &one, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    {
+        LaunchScope ls(c, "sweep");
+        sweep::symmetry_kernel<<<ceil_div((long long)m * m, 256), 256, 0, c->stream>>>(c->dist.as<double>(), m, flag);
+    }
+    int res = 0;
+    ESPER_CUDA(c, cudaMemcpyAsync(&res, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ESPER_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->dist_symmetric = res;
+    return ESPER_OK;
+}
+
 int run_sweep(esper_ctx* c, int m, const double* coef_h, int n_eps, double thr, double* logsum_h) {
     using namespace sweep;
-    const long long total = (long long)m * m;
-    const long long n_chunks = (total + CHUNK - 1) / CHUNK;
+    if (c->dist_symmetric < 0) { int rc = check_symmetry(c, m); if (rc) return rc; }
+    const int sym = c->dist_symmetric > 0 ? 1 : 0;
+    const long long n_tiles = (long long)ceil_div(m, TR) * ceil_div(m, TC);
     int grid = c->sm_count * 4;
-    if (grid > n_chunks) grid = (int)n_chunks;
+    if (grid > n_tiles) grid = (int)n_tiles;
     if (grid < 1) grid = 1;
     ESPER_RESERVE(c, c->sweep_part, sizeof(double) * (size_t)grid * n_eps);
-    ESPER_RESERVE(c, c->sweep_aux, sizeof(double) * (size_t)n_eps * 2);
-    double* coef_d = c->sweep_aux.as<double>();
+    ESPER_RESERVE(c, c->sweep_aux, sizeof(double) * ((size_t)n_eps * 2 + 4096));
+    double* coef_d = c->sweep_aux.as<double>() + 4096;
     double* logsum_d = coef_d + n_eps;
     ESPER_CUDA(c, cudaMemcpyAsync(coef_d, coef_h, sizeof(double) * n_eps, cudaMemcpyHostToDevice, c->stream));
     const size_t smem = sizeof(double) * ((size_t)2 * n_eps + WARPS * KB + 4 * WARPS);
@@ -146,7 +193,7 @@ int run_sweep(esper_ctx* c, int m, const double* coef_h, int n_eps, double thr, 
     }
     {
         LaunchScope ls(c, "sweep");
-        sweep_kernel<<<grid, THREADS, smem, c->stream>>>(c->dist.as<double>(), total, coef_d, n_eps, thr,
+        sweep_kernel<<<grid, THREADS, smem, c->stream>>>(c->dist.as<double>(), m, sym, coef_d, n_eps, thr,
                                                          c->sweep_part.as<double>());
     }
     {

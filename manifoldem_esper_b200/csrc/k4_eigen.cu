@@ -2,41 +2,24 @@
 // full SVD of 1_Embedding/DM/DiffusionMaps.py:166-169 (Ms is symmetric PSD, so singular values =
 // eigenvalues and U = eigenvectors; the reference saves s**2 and U).
 //
-// Method: Lanczos with full reorthogonalisation (classical Gram-Schmidt applied twice) on the
-// operator deflated by the analytically known top pair (lambda_0 = 1, v_0 = sqrt(d)/|sqrt(d)|),
-// which is kept as a locked vector in the orthogonalisation basis.  Every kernel is a streaming
-// pass: SYMV reads Ms once per step (m^2 x 8 B, L2-resident at m = 2000), the orthogonalisation
-// reads the basis twice.  The small tridiagonal eigenproblem (bisection + inverse iteration) runs
-// on the host every few steps to test convergence; Ritz vectors are assembled on the device.
+// Method: Lanczos with full reorthogonalisation on the operator deflated by the analytically known
+// top pair (lambda_0 = 1, v_0 = sqrt(d)/|sqrt(d)|), which is kept as a locked vector in the basis.
+// The iteration runs as ONE persistent cooperative kernel per batch of steps (one CTA per SM, grid
+// barriers between the phases of a step), so a step costs three grid barriers instead of six kernel
+// launches:
+//     S0  w = Ms q_j - alpha_{j-1} q_j - beta_{j-1} q_{j-1}   each CTA owns a row block; q_j staged in shared memory; SYMV reads Ms once
+//     S1  h = V^T w         one warp per basis vector (classical Gram-Schmidt coefficients)
+//     S2  w -= V h          CTA-owned rows; partial |w|^2; a second S1/S2 pass only when the DGKS
+//                           test (|w_after|^2 < |w_before|^2 / 2, "twice is enough") asks for it; S0
+//                           removes the predicted three-term components so that it rarely does
+// Every pass is a streaming FP64 pass (Ms: m^2 x 8 B per step, L2-resident at m = 2000); all
+// reductions have a fixed order (deterministic).  The host solves the small tridiagonal problem
+// (bisection + inverse iteration) to test convergence while the next batch already runs.
 #include "common.cuh"
 #include "devutil.cuh"
 #include <algorithm>
-
 namespace esper {
 namespace lanczos {
-
-// w = Ms q, one warp per row.
-__global__ void __launch_bounds__(256) symv_kernel(const double* __restrict__ Ms, int m,
-                                                   const double* __restrict__ q, double* __restrict__ w) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= m) return;
-    const double* a = Ms + (size_t)row * m;
-    double s = 0.0;
-    if ((m & 1) == 0) {
-        const double2* a2 = reinterpret_cast<const double2*>(a);
-        const double2* q2 = reinterpret_cast<const double2*>(q);
-        for (int j = lane; j < (m >> 1); j += 32) {
-            const double2 x = __ldg(a2 + j), y = __ldg(q2 + j);
-            s = fma(x.x, y.x, s);
-            s = fma(x.y, y.y, s);
-        }
-    } else {
-        for (int j = lane; j < m; j += 32) s = fma(__ldg(a + j), __ldg(q + j), s);
-    }
-    s = warp_sum(s);
-    if (lane == 0) w[row] = s;
-}
 
 // h[i] = V_i . w for i < nb (one block per basis vector).
 __global__ void __launch_bounds__(256) dots_kernel(const double* __restrict__ V, int m, const double* __restrict__ w,
@@ -60,6 +43,211 @@ __global__ void __launch_bounds__(256) update_kernel(const double* __restrict__ 
         w[r] = acc;
     }
     if (alpha_slot && blockIdx.x == 0 && threadIdx.x == 0) *alpha_slot += h[nb - 1];
+}
+
+__device__ __forceinline__ double ld_cg(const double* p) { return __ldcg(p); }
+
+struct StepParams {
+    const double* Ms; int m;
+    double* V;            // basis: V[0] = v0 (locked), V[j] = q_j
+    double* wbuf;         // [2][m] ping-pong work vectors
+    double* h;            // [>= max basis + 2] Gram-Schmidt coefficients (+ slot for w.w)
+    double* part;         // [gridDim.x] partial |w|^2
+    double* alpha;        // alpha[j-1] for q_j
+    double* beta;         // beta[j-1] = |w| after step j
+    int j_start;          // first Lanczos vector index of this batch (>= 1); V[j_start] is normalised
+    int n_steps;
+    unsigned int* bar;    // bar[0] arrival counter (zeroed before every launch), bar[1] abort flag
+};
+
+// Grid-wide barrier for a co-resident (cooperatively launched) grid: monotone arrival counter, the
+// k-th barrier completes when the counter reaches k * gridDim.x.  A barrier that does not complete
+// within ~2 s sets the abort flag instead of spinning forever; every CTA then leaves the kernel.
+struct GridBarrier {
+    unsigned int* bar;
+    unsigned int epoch = 0;
+    bool aborted = false;
+    __device__ GridBarrier(unsigned int* b) : bar(b) {}
+    __device__ __forceinline__ bool sync() {
+        __shared__ int s_abort;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ++epoch;
+            int ab = 0;
+            __threadfence();
+            atomicAdd(bar, 1u);
+            const unsigned int target = epoch * gridDim.x;
+            const long long t0 = clock64();
+            while (*((volatile unsigned int*)bar) < target) {
+                if (*((volatile unsigned int*)(bar + 1)) != 0u) { ab = 1; break; }
+                if (clock64() - t0 > 4000000000LL) { atomicExch(bar + 1, 1u); ab = 1; break; }
+            }
+            __threadfence();
+            s_abort = ab;
+        }
+        __syncthreads();
+        if (threadIdx.x != 0) ++epoch;
+        aborted = aborted || (s_abort != 0);
+        return !aborted;
+    }
+};
+
+constexpr int LAN_THREADS = 512;
+constexpr int LAN_WARPS = LAN_THREADS / 32;
+constexpr int LAN_CH = 2048;          // columns of the vector staged in shared memory at a time
+
+// Sum of the per-CTA partial norms, identical in every thread of every CTA (fixed reduction tree).
+__device__ __forceinline__ double sum_partials(const double* part, int nb, double* s_tmp /*[LAN_WARPS + 1]*/) {
+    double v = 0.0;
+    for (int q = threadIdx.x; q < nb; q += LAN_THREADS) v += ld_cg(part + q);
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_tmp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < LAN_WARPS; ++w) tot += s_tmp[w];
+        s_tmp[LAN_WARPS] = tot;
+    }
+    __syncthreads();
+    return s_tmp[LAN_WARPS];
+}
+
+// Persistent cooperative kernel: n_steps Lanczos steps with full reorthogonalisation.
+__global__ void __launch_bounds__(LAN_THREADS, 1) lanczos_steps_kernel(StepParams p) {
+    GridBarrier grid(p.bar);
+    __shared__ double s_vec[LAN_CH];
+    __shared__ double s_red[32 * 16];
+    __shared__ double s_nrm[16];
+    __shared__ double s_tmp[LAN_WARPS + 1];
+    const int m = p.m;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nb = gridDim.x, b = blockIdx.x;
+    const int chunk = (m + nb - 1) / nb;
+    const int row0 = min(b * chunk, m), row1 = min(row0 + chunk, m);
+    const int gwarp = warp * nb + b, total_warps = nb * LAN_WARPS;   // consecutive basis vectors on different SMs
+
+    int cur = 0;                                     // wbuf[cur] holds the un-normalised q_j (after the first step)
+    for (int step = 0; step < p.n_steps; ++step) {
+        const int j = p.j_start + step;
+        // ---- source of q_j: normalised V[j] on the first step, else wbuf[cur] / beta ----
+        const double* src; double scale = 1.0;
+        // Predicted large components, removed locally before the Gram-Schmidt pass (three-term recurrence
+        // with alpha_j predicted by alpha_{j-1}); the pass then measures only small corrections, which is
+        // what makes a single classical pass stable (Kahan-Parlett / DGKS: |w_after| >= 0.7 |w_before|).
+        double sigma = 0.0, beta_prev = 0.0;
+        if (j >= 2) { sigma = ld_cg(p.alpha + j - 2); beta_prev = ld_cg(p.beta + j - 2); }
+        if (step == 0) {
+            src = p.V + (size_t)j * m;
+        } else {
+            const double s2 = sum_partials(p.part, nb, s_tmp);
+            const double bt = sqrt(s2);
+            scale = bt > 0.0 ? 1.0 / bt : 0.0;
+            src = p.wbuf + (size_t)cur * m;
+            beta_prev = bt;
+            if (b == 0 && tid == 0) p.beta[j - 2] = bt;              // beta of the previous step (vector j-1)
+            for (int r = row0 + tid; r < row1; r += LAN_THREADS)       // owners publish the normalised q_j
+                p.V[(size_t)j * m + r] = ld_cg(src + r) * scale;
+        }
+        double* wnew = p.wbuf + (size_t)(cur ^ 1) * m;
+
+        // ---- S0: w = Ms q_j for the owned rows (one warp per row, vector staged in shared memory) ----
+        {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};                      // up to 4 rows per warp per sweep
+            const int rows_per_sweep = LAN_WARPS * 4;
+            for (int rbase = row0; rbase < row1; rbase += rows_per_sweep) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[q] = 0.0;
+                for (int c0 = 0; c0 < m; c0 += LAN_CH) {
+                    const int cn = min(LAN_CH, m - c0);
+                    __syncthreads();
+                    for (int cidx = tid; cidx < cn; cidx += LAN_THREADS) s_vec[cidx] = ld_cg(src + c0 + cidx);
+                    __syncthreads();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int r = rbase + q * LAN_WARPS + warp;
+                        if (r < row1) {
+                            const double* a = p.Ms + (size_t)r * m + c0;
+                            double sacc = 0.0;
+                            for (int cidx = lane; cidx < cn; cidx += 32) sacc = fma(__ldg(a + cidx), s_vec[cidx], sacc);
+                            acc[q] += sacc;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int r = rbase + q * LAN_WARPS + warp;
+                    const double tot = warp_sum(acc[q]);
+                    if (r < row1 && lane == 0) {
+                        double x = fma(-sigma, ld_cg(src + r) * scale, tot * scale);
+                        if (j >= 2) x = fma(-beta_prev, ld_cg(p.V + (size_t)(j - 1) * m + r), x);
+                        wnew[r] = x;
+                    }
+                }
+            }
+        }
+        if (!grid.sync()) return;
+
+        for (int pass = 0; pass < 2; ++pass) {
+            // ---- S1: h[i] = V_i . w for i <= j, and (first pass only) h[j+1] = w . w ----
+            // (the second pass must not touch h[j+1]: slower CTAs may still be reading it for the DGKS test)
+            const int i_end = (pass == 0) ? j + 1 : j;
+            for (int i = gwarp; i <= i_end; i += total_warps) {
+                const double* v = (i <= j) ? p.V + (size_t)i * m : wnew;
+                double sacc = 0.0;
+                for (int r = lane; r < m; r += 32) sacc = fma(ld_cg(v + r), ld_cg(wnew + r), sacc);
+                sacc = warp_sum(sacc);
+                if (lane == 0) p.h[i] = sacc;
+            }
+            if (!grid.sync()) return;
+
+            // ---- S2: w -= V h on the owned rows; partial |w|^2 ----
+            double nrm = 0.0;
+            for (int rbase = row0; rbase < row1; rbase += 16) {
+                const int r = rbase + (tid & 15), sub = tid >> 4;
+                double sacc = 0.0;
+                if (r < row1)
+                    for (int i = sub; i <= j; i += 32) sacc = fma(ld_cg(p.h + i), ld_cg(p.V + (size_t)i * m + r), sacc);
+                __syncthreads();
+                s_red[sub * 16 + (tid & 15)] = sacc;
+                __syncthreads();
+                if (tid < 16 && r < row1) {
+                    double tot = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) tot += s_red[q * 16 + tid];
+                    const double x = ld_cg(wnew + r) - tot;
+                    wnew[r] = x;
+                    nrm = fma(x, x, nrm);
+                }
+            }
+            if (tid < 16) s_nrm[tid] = nrm;
+            __syncthreads();
+            if (tid == 0) {
+                double tot = 0.0;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) tot += s_nrm[q];
+                p.part[b] = tot;
+                if (b == 0) { if (pass == 0) p.alpha[j - 1] = sigma + ld_cg(p.h + j); else p.alpha[j - 1] += ld_cg(p.h + j); }
+            }
+            if (!grid.sync()) return;
+            if (pass == 0) {                                           // DGKS: second pass iff |w_after|^2 < |w_before|^2 / 2
+                const double s2 = sum_partials(p.part, nb, s_tmp);
+                if (!(s2 < 0.5 * ld_cg(p.h + j + 1))) break;
+            }
+        }
+        cur ^= 1;
+    }
+    // ---- tail: publish beta of the last step and the normalised next vector ----
+    {
+        const int j = p.j_start + p.n_steps;                           // index of the next vector
+        const double s2 = sum_partials(p.part, nb, s_tmp);
+        const double bt = sqrt(s2);
+        const double scale = bt > 0.0 ? 1.0 / bt : 0.0;
+        const double* src = p.wbuf + (size_t)cur * m;
+        if (b == 0 && tid == 0) p.beta[j - 2] = bt;
+        for (int r = row0 + tid; r < row1; r += LAN_THREADS) p.V[(size_t)j * m + r] = ld_cg(src + r) * scale;
+    }
 }
 
 // beta = |w| ; out = w / beta (single block).
@@ -253,6 +441,22 @@ static void tridiag_eigenvectors(const std::vector<double>& a, const std::vector
     }
 }
 
+// Residual estimates |beta_j s_{j,i}| of the Ritz pairs i in [i0, i1) of T = tridiag(b, a, b); early exit.
+static bool ritz_converged(const std::vector<double>& a, const std::vector<double>& b, int n, int kw, int guard,
+                           double tol, std::vector<double>& theta, std::vector<double>& S) {
+    const int want = std::min(kw + guard, n);
+    tridiag_top_eigenvalues(a, b, n, want, theta);
+    tridiag_eigenvectors(a, b, n, theta, S);
+    const double scale = std::max(fabs(theta[0]), 1e-300);
+    const double beta_last = b[n - 1];
+    if (n < kw) return false;
+    for (int i = want - 1; i >= 0; --i) {                 // the smallest wanted pair converges last
+        const double res = fabs(beta_last * S[(size_t)(n - 1) * want + i]);
+        if (!(res <= (i < kw ? tol : 1e-5) * scale)) return false;
+    }
+    return true;
+}
+
 }  // namespace lanczos
 
 int run_lanczos(esper_ctx* c, int m, int k, double tol, int max_iter, double* val_h, double* vec_h, int* iters_out) {
@@ -263,21 +467,33 @@ int run_lanczos(esper_ctx* c, int m, int k, double tol, int max_iter, double* va
     const int kw = k - 1;                               // non-trivial pairs wanted
     int guard = (kw > 0) ? std::min(2, m - 1 - kw) : 0;
     if (guard < 0) guard = 0;
-    int cap = m - 1;                                    // Krylov dimension of the deflated operator
+    const int cap = m - 1;                              // Krylov dimension of the deflated operator
     if (max_iter <= 0) max_iter = 1024;
     if (max_iter > cap) max_iter = cap;
     const double* Ms = c->markov.as<double>();
+    cudaStream_t st = c->stream;
+
+    // cooperative grid: one CTA per SM (all must be co-resident for the grid barriers)
+    int coop = 0, per_sm = 0;
+    ESPER_CUDA(c, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
+    ESPER_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lanczos_steps_kernel, LAN_THREADS, 0));
+    if (!coop || per_sm < 1) return fail(c, ESPER_E_CUDA, "cooperative launch unavailable on this device");
+    const int grid = c->sm_count;
+
     ESPER_RESERVE(c, c->lan_V, sizeof(double) * (size_t)(max_iter + 3) * m);
     ESPER_RESERVE(c, c->lan_w, sizeof(double) * (size_t)m * 2);
-    ESPER_RESERVE(c, c->lan_h, sizeof(double) * (size_t)(max_iter + 4) * 3);
+    ESPER_RESERVE(c, c->lan_h, sizeof(double) * ((size_t)(max_iter + 8) * 3 + grid + 2));
+    if (c->pin.reserve(sizeof(double) * ((size_t)(max_iter + 8) * 2 * 2 + 4)) != 0) return fail(c, ESPER_E_NOMEM, "pinned alloc failed");
     double* V = c->lan_V.as<double>();
     double* w = c->lan_w.as<double>();
     double* w2 = w + m;
     double* h = c->lan_h.as<double>();
-    double* alpha_d = h + (max_iter + 4);
-    double* beta_d = alpha_d + (max_iter + 4);
-    cudaStream_t st = c->stream;
-    ESPER_CUDA(c, cudaMemsetAsync(alpha_d, 0, sizeof(double) * (size_t)(max_iter + 4) * 2, st));
+    const int stride = max_iter + 8;
+    double* alpha_d = h + stride;                       // alpha[stride], beta[stride] contiguous
+    double* beta_d = alpha_d + stride;
+    double* part_d = beta_d + stride;
+    unsigned int* bar_d = reinterpret_cast<unsigned int*>(part_d + grid);
+    ESPER_CUDA(c, cudaMemsetAsync(alpha_d, 0, sizeof(double) * (size_t)stride * 2, st));
 
     // locked vector v0 and the start vector q1 (orthogonal to v0)
     { LaunchScope ls(c, "lanczos"); init_kernel<<<ceil_div(m, 256), 256, 0, st>>>(c->degree.as<double>(), m, w, w2); }
@@ -290,47 +506,67 @@ int run_lanczos(esper_ctx* c, int m, int k, double tol, int max_iter, double* va
         { LaunchScope ls(c, "lanczos"); normalize_kernel<<<1, 1024, 0, st>>>(w2, m, V + m, nullptr); }
     }
 
+    // Batches of steps; the host tests batch n while batch n+1 already runs (speculatively).
     std::vector<double> a, b, theta, S;
-    int steps = 0;
+    int steps_done = 0;          // steps whose alpha/beta have been checked on the host
+    int steps_issued = 0;
     bool converged = (kw == 0);
-    int next_check = std::min(max_iter, std::max(2 * (kw + guard) + 8, 32));
-    std::vector<double> ab((size_t)(max_iter + 4) * 2);
-    while (!converged && steps < max_iter) {
-        const int j = steps + 1;                        // current Lanczos vector is V[j]
-        { LaunchScope ls(c, "lanczos"); symv_kernel<<<ceil_div(m, 8), 256, 0, st>>>(Ms, m, V + (size_t)j * m, w); }
-        for (int pass = 0; pass < 2; ++pass) {
-            { LaunchScope ls(c, "lanczos"); dots_kernel<<<j + 1, 256, 0, st>>>(V, m, w, h); }
-            { LaunchScope ls(c, "lanczos"); update_kernel<<<ceil_div(m, 256), 256, 0, st>>>(V, m, j + 1, h, w, alpha_d + steps); }
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    if (!converged) { ESPER_CUDA(c, cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming)); ESPER_CUDA(c, cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming)); }
+    double* pin = c->pin.as<double>();
+    unsigned int* pin_flag = reinterpret_cast<unsigned int*>(pin + (size_t)stride * 4);
+    int pending_steps[2] = {0, 0};
+    int slot = 0;
+    auto issue_batch = [&](int n_steps, int sl) -> int {
+        StepParams sp{Ms, m, V, w, h, part_d, alpha_d, beta_d, steps_issued + 1, n_steps, bar_d};
+        void* args[] = {&sp};
+        cudaMemsetAsync(bar_d, 0, 2 * sizeof(unsigned int), st);
+        {
+            LaunchScope ls(c, "lanczos");
+            cudaError_t e = cudaLaunchCooperativeKernel((void*)lanczos_steps_kernel, dim3(grid), dim3(LAN_THREADS), args, 0, st);
+            if (e != cudaSuccess) { cudaGetLastError(); return fail(c, ESPER_E_CUDA, "cooperative launch: %s", cudaGetErrorString(e)); }
         }
-        { LaunchScope ls(c, "lanczos"); normalize_kernel<<<1, 1024, 0, st>>>(w, m, V + (size_t)(j + 1) * m, beta_d + steps); }
-        ++steps;
-        if (steps >= next_check || steps == max_iter) {
-            ESPER_CUDA(c, cudaMemcpyAsync(ab.data(), alpha_d, sizeof(double) * (size_t)(max_iter + 4) * 2,
-                                          cudaMemcpyDeviceToHost, st));
-            ESPER_CUDA(c, cudaStreamSynchronize(st));
-            a.assign(ab.begin(), ab.begin() + steps);
-            b.assign(ab.begin() + (max_iter + 4), ab.begin() + (max_iter + 4) + steps);
-            const int want = std::min(kw + guard, steps);
-            tridiag_top_eigenvalues(a, b, steps, want, theta);
-            tridiag_eigenvectors(a, b, steps, theta, S);
-            const double scale = std::max(fabs(theta[0]), 1e-300);
-            bool ok = (steps >= kw);
-            const double beta_last = b[steps - 1];
-            bool breakdown = !(beta_last > 1e-14 * scale);
-            for (int i = 0; i < want && ok; ++i) {
-                const double res = fabs(beta_last * S[(size_t)(steps - 1) * want + i]);
-                const double lim = (i < kw ? tol : 1e-5) * scale;
-                if (!(res <= lim)) ok = false;
+        steps_issued += n_steps;
+        cudaMemcpyAsync(pin + (size_t)sl * stride * 2, alpha_d, sizeof(double) * (size_t)stride * 2, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(pin_flag + 2 * sl, bar_d, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st);
+        cudaEventRecord(ev[sl], st);
+        pending_steps[sl] = steps_issued;
+        return ESPER_OK;
+    };
+    int rc = ESPER_OK;
+    if (!converged) {
+        const int first = std::min(max_iter, std::max(3 * (kw + guard) + 8, 32));
+        const int batch = 16;
+        rc = issue_batch(first, slot);
+        while (rc == ESPER_OK) {
+            const int cur_slot = slot;
+            const bool more = steps_issued < max_iter;
+            if (more) { slot ^= 1; rc = issue_batch(std::min(batch, max_iter - steps_issued), slot); if (rc) break; }
+            cudaError_t e = cudaEventSynchronize(ev[cur_slot]);
+            if (e != cudaSuccess) { cudaGetLastError(); rc = fail(c, ESPER_E_CUDA, "lanczos: %s", cudaGetErrorString(e)); break; }
+            if (pin_flag[2 * cur_slot + 1] != 0u) { rc = fail(c, ESPER_E_CUDA, "lanczos: grid barrier timed out (CTAs not co-resident?)"); break; }
+            steps_done = pending_steps[cur_slot];
+            const double* ab = pin + (size_t)cur_slot * stride * 2;
+            a.assign(ab, ab + steps_done);
+            b.assign(ab + stride, ab + stride + steps_done);
+            if (getenv("ESPER_DEBUG_LANCZOS")) {
+                fprintf(stderr, "[lanczos] steps=%d issued=%d slot=%d\n", steps_done, steps_issued, cur_slot);
+                for (int i = 0; i < steps_done; ++i) fprintf(stderr, "  %3d alpha=%.6e beta=%.6e\n", i, a[i], b[i]);
             }
-            if (ok || breakdown || steps >= cap) converged = true;
-            next_check = steps + 16;
+            const double scale0 = std::max(fabs(a[0]), 1e-300);
+            const bool breakdown = !(b[steps_done - 1] > 1e-14 * scale0);
+            if (ritz_converged(a, b, steps_done, kw, guard, tol, theta, S) || breakdown || steps_done >= cap) { converged = true; break; }
+            if (!more) break;
         }
     }
+    for (int i = 0; i < 2; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
+    if (rc) return rc;
+    const int steps = steps_done;
     if (iters_out) *iters_out = steps;
-    if (!converged) return fail(c, ESPER_E_NOCONV, "Lanczos did not converge in %d steps", steps);
+    if (!converged) { cudaStreamSynchronize(st); return fail(c, ESPER_E_NOCONV, "Lanczos did not converge in %d steps", steps); }
 
     // Ritz vectors U = [v0, V_1..V_steps S]
-    ESPER_RESERVE(c, c->lan_small, sizeof(double) * ((size_t)m * k + (size_t)(max_iter + 4) * KMAX));
+    ESPER_RESERVE(c, c->lan_small, sizeof(double) * ((size_t)m * k + (size_t)(max_iter + 8) * KMAX));
     double* U = c->lan_small.as<double>();
     double* S_d = U + (size_t)m * k;
     std::vector<double> Sk;

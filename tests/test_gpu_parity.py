@@ -137,6 +137,18 @@ def test_eps_sweep_general_coefficients(ctx):
         assert np.allclose(L, ref, rtol=0, atol=1e-12)
 
 
+def test_eps_sweep_nonsymmetric_input(ctx):
+    """A caller-supplied D need not be symmetric for the sweep (the reference sums all m^2 entries)."""
+    D = np.abs(np.random.default_rng(2).standard_normal((150, 150))) + 0.1
+    np.fill_diagonal(D, 0.0)
+    coef = 1. / (2. * np.exp(np.arange(-12, 12, 0.2)))
+    L = ctx.eps_sweep(D, coef, 10.0)
+    ref = [np.log(np.sum(np.exp(-(c * D * D)[(c * D * D) < 10.0]))) for c in coef]
+    assert np.allclose(L, ref, rtol=0, atol=1e-12)
+    with pytest.raises(ValueError):
+        ctx.dmap_embed(D, 0.3, k=4)                                           # the eigensolver needs symmetry
+
+
 # ---- stage 3 ----------------------------------------------------------------------------------
 @pytest.mark.parametrize('name', ['stage123_pristine', 'stage23_medium'])
 def test_markov_matrix_vs_oracle(ctx, name):

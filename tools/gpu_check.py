@@ -120,7 +120,7 @@ def sec_eig(ctx, Dr=None, eps=None):
         print('eig m=%d k=%d iters=%d wall_ms=%.2f oracle_s=%.2f val_rel_max=%.3e vec_err=%s resid_max=%.3e orth=%.3e rep=%s' % (
             m, k, iters, tg * 1e3, tor, ev.max(), np.array2string(np.array(vs), precision=1), res.max(),
             np.abs(vec.T @ vec - np.eye(k)).max(), json.dumps(rep)), flush=True)
-        print('   lam', np.array2string(lam[:k], precision=6), flush=True)
+        print("   lam", np.array2string(lam[:k], precision=6), flush=True)
 
 
 def sec_rot(ctx):
