@@ -103,7 +103,7 @@ int esper_markov(esper_ctx* ctx, const double* D, int m, double eps, double* deg
  *   val: [k]   = lambda^2, descending (what the reference saves as PD_%s_val.npy)
  *   vec: [m,k] row-major; column 0 = sqrt(degree)/|sqrt(degree)| (steady state), unit columns,
  *              sign fixed so that the entry of largest magnitude is positive
- *   tol: relative residual |Ms v - lambda v| <= tol*lambda_1  (0 = 1e-11)
+ *   tol: relative residual |Ms v - lambda v| <= tol*lambda_1  (0 = 1e-10)
  *   max_iter: Lanczos steps (0 = min(m-1, 1024));  iters (optional) receives the steps used.  */
 int esper_dmap_embed(esper_ctx* ctx, const double* D, int m, double eps, int k, double tol,
                      int max_iter, double* val, double* vec, int* iters);

@@ -1,25 +1,20 @@
 // k0_prep.cu -- K0: per-image standardisation (Distances.py:88-92), PD mean-image centring and the
 // TF32 hi/lo operand split that feeds the tcgen05 Gram kernel.  HBM-bound streaming passes.
 //
-//   pass 1  row_stats      : per image sum / sum-of-squares (FP64)  -> mean32, std32
-//   pass 2  col_sum(+fin)  : column mean of the standardised images   -> xbar32[P]      (ESPER_DIST_CENTER)
-//   pass 3  split          : c = fl32(z - xbar); hi = tf32(c); lo = tf32(c - hi); |c|^2 in FP64
+//   pass 1  row_stats+col_sum : on a SUBSET of <= 256 images: mean32/std32, then the column mean of their
+//                               standardised pixels -> xbar32[P]  (ESPER_DIST_CENTER).  Distances are
+//                               invariant to subtracting ANY common image, so a subset mean serves.
+//   pass 2  stats_split       : per image (one CTA): sum / sum-of-squares (FP64) -> mean32, std32, then a
+//                               second sweep of the same row (L2-resident, 4P bytes per CTA):
+//                               c = fl32(z - xbar); hi = tf32(c); lo = tf32(c - hi); |c|^2 in FP64
 //
-// Algorithmic bytes per PD (n images, P pixels): read 4nP per pass (3 passes), write 8nP.
+// Algorithmic bytes per PD (n images, P pixels): read 4nP once from HBM (+4nP from L2), write 8nP.
 #include "common.cuh"
 #include "devutil.cuh"
 
 namespace esper {
 
-__global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict__ raw, int n, int P,
-                                                        int standardize, RowStat* __restrict__ st) {
-    __shared__ double sh[32];
-    int i = blockIdx.x;
-    if (!standardize) {
-        if (threadIdx.x == 0) { st[i].mean = 0.f; st[i].stdv = 1.f; st[i].norm2 = 0.0; }
-        return;
-    }
-    const float* row = raw + (size_t)i * P;
+__device__ __forceinline__ void row_stats(const float* __restrict__ row, int P, double* sh, float& mean32, float& std32) {
     double s = 0.0, s2 = 0.0;
     if ((P & 3) == 0) {
         const float4* r4 = reinterpret_cast<const float4*>(row);
@@ -36,28 +31,48 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict_
             s += a; s2 += a * a;
         }
     }
+    __shared__ double bc[2];
     s = block_sum(s, sh);
     s2 = block_sum(s2, sh);
     if (threadIdx.x == 0) {
         double mean = s / P;
         double var = s2 / P - mean * mean;
         if (var < 0.0) var = 0.0;
-        st[i].mean = (float)mean;
-        st[i].stdv = (float)sqrt(var);
-        st[i].norm2 = 0.0;
+        bc[0] = (double)(float)mean;
+        bc[1] = (double)(float)sqrt(var);
     }
+    __syncthreads();
+    mean32 = (float)bc[0];
+    std32 = (float)bc[1];
+    __syncthreads();
+}
+
+// Statistics of the images i = blockIdx.x * stride (the centring subset).
+__global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict__ raw, int n, int P, int stride,
+                                                        int standardize, RowStat* __restrict__ st) {
+    __shared__ double sh[32];
+    int i = blockIdx.x * stride;
+    if (i >= n) return;
+    if (!standardize) {
+        if (threadIdx.x == 0) { st[i].mean = 0.f; st[i].stdv = 1.f; st[i].norm2 = 0.0; }
+        return;
+    }
+    float m32, s32;
+    row_stats(raw + (size_t)i * P, P, sh, m32, s32);
+    if (threadIdx.x == 0) { st[i].mean = m32; st[i].stdv = s32; st[i].norm2 = 0.0; }
 }
 
 // Partial column sums of the standardised images: part[g][p] = sum_{i in group g} z_ip  (FP64).
-__global__ void __launch_bounds__(256) col_sum_kernel(const float* __restrict__ raw, int n, int P,
+__global__ void __launch_bounds__(256) col_sum_kernel(const float* __restrict__ raw, int n_sub, int stride, int P,
                                                       const RowStat* __restrict__ st, int groups,
                                                       double* __restrict__ part) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     int g = blockIdx.y;
-    int i0 = (int)((long long)n * g / groups), i1 = (int)((long long)n * (g + 1) / groups);
+    int k0 = (int)((long long)n_sub * g / groups), k1 = (int)((long long)n_sub * (g + 1) / groups);
     if (p >= P) return;
     double acc = 0.0;
-    for (int i = i0; i < i1; ++i) {
+    for (int k = k0; k < k1; ++k) {
+        const int i = k * stride;
         float m = st[i].mean, sd = st[i].stdv;
         acc += (double)zscore(__ldg(raw + (size_t)i * P + p), m, sd);
     }
@@ -80,16 +95,17 @@ __device__ __forceinline__ float tf32_rna(float x) {
 }
 
 // One block per image: write the hi / lo TF32 planes (row stride ld, zero padded) and |c|^2.
-__global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ raw, int n, int P, int ld,
-                                                    RowStat* __restrict__ st,
-                                                    const float* __restrict__ xbar, int center,
-                                                    float* __restrict__ hi, float* __restrict__ lo) {
+__global__ void __launch_bounds__(1024) stats_split_kernel(const float* __restrict__ raw, int n, int P, int ld,
+                                                          int standardize, RowStat* __restrict__ st,
+                                                          const float* __restrict__ xbar, int center,
+                                                          float* __restrict__ hi, float* __restrict__ lo) {
     __shared__ double sh[32];
     int i = blockIdx.x;
     const float* row = raw + (size_t)i * P;
     float4* hrow = reinterpret_cast<float4*>(hi + (size_t)i * ld);
     float4* lrow = reinterpret_cast<float4*>(lo + (size_t)i * ld);
-    const float m = st[i].mean, sd = st[i].stdv;
+    float m = 0.f, sd = 1.f;
+    if (standardize) row_stats(row, P, sh, m, sd);
     const bool vec = ((P & 3) == 0);
     double acc = 0.0;
     int nq = ld >> 2;
@@ -119,7 +135,7 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ ra
         lrow[q] = make_float4(l[0], l[1], l[2], l[3]);
     }
     acc = block_sum(acc, sh);
-    if (threadIdx.x == 0) st[i].norm2 = acc;
+    if (threadIdx.x == 0) { st[i].mean = m; st[i].stdv = sd; st[i].norm2 = acc; }
 }
 
 int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld) {
@@ -130,24 +146,26 @@ int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld) {
     RowStat* st = c->row_stats.as<RowStat>();
     const int standardize = (flags & ESPER_DIST_STANDARDIZE) ? 1 : 0;
     const int center = (flags & ESPER_DIST_CENTER) ? 1 : 0;
-    {
-        LaunchScope ls(c, "prep");
-        row_stats_kernel<<<n, 256, 0, c->stream>>>(raw, n, P, standardize, st);
-    }
     float* xbar = nullptr;
     if (center) {
-        const int groups = 16;
+        const int stride = n > 256 ? n / 256 : 1;                  // centring subset: images 0, stride, 2*stride, ...
+        const int n_sub = (n + stride - 1) / stride;
+        const int groups = n_sub >= 16 ? 16 : 1;
         ESPER_RESERVE(c, c->col_part, sizeof(double) * (size_t)(groups + 1) * P);
         double* part = c->col_part.as<double>();
         xbar = reinterpret_cast<float*>(part + (size_t)groups * P);
         {
             LaunchScope ls(c, "prep");
-            dim3 grid(ceil_div(P, 256), groups);
-            col_sum_kernel<<<grid, 256, 0, c->stream>>>(raw, n, P, st, groups, part);
+            row_stats_kernel<<<n_sub, 256, 0, c->stream>>>(raw, n, P, stride, standardize, st);
         }
         {
             LaunchScope ls(c, "prep");
-            col_mean_kernel<<<ceil_div(P, 256), 256, 0, c->stream>>>(part, groups, P, n, xbar);
+            dim3 grid(ceil_div(P, 256), groups);
+            col_sum_kernel<<<grid, 256, 0, c->stream>>>(raw, n_sub, stride, P, st, groups, part);
+        }
+        {
+            LaunchScope ls(c, "prep");
+            col_mean_kernel<<<ceil_div(P, 256), 256, 0, c->stream>>>(part, groups, P, n_sub, xbar);
         }
     }
     if (rows_pad > n) {
@@ -158,8 +176,8 @@ int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld) {
     }
     {
         LaunchScope ls(c, "prep");
-        split_kernel<<<n, 256, 0, c->stream>>>(raw, n, P, ld, st, xbar, center, c->plane_hi.as<float>(),
-                                               c->plane_lo.as<float>());
+        stats_split_kernel<<<n, 1024, 0, c->stream>>>(raw, n, P, ld, standardize, st, xbar, center,
+                                                     c->plane_hi.as<float>(), c->plane_lo.as<float>());
     }
     ESPER_CUDA(c, cudaGetLastError());
     return ESPER_OK;

@@ -270,10 +270,11 @@ __global__ void __launch_bounds__(256)
 dist_finalize_kernel(const float* __restrict__ part, int nt, int n_tiles, int tile0, int split_k, int n, int P,
                      const RowStat* __restrict__ st, double* __restrict__ D) {
     const int lt = blockIdx.x;
+    const int e_per = (BM * (BN / 4)) / gridDim.y;          // slice of the tile handled by this block
     int ti, tj; tile_coords(tile0 + lt, nt, ti, tj);
     const bool diag = (ti == tj);
     const double invP = 1.0 / (double)P;
-    for (int e = threadIdx.x; e < BM * (BN / 4); e += blockDim.x) {
+    for (int e = blockIdx.y * e_per + threadIdx.x; e < (blockIdx.y + 1) * e_per; e += blockDim.x) {
         const int r = e & (BM - 1), c4 = e >> 7;
         const int i = ti * BM + r;
         if (i >= n) continue;
@@ -439,7 +440,7 @@ int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags) {
         }
         {
             LaunchScope ls(c, "dist_finalize");
-            dist_finalize_kernel<<<nb, 256, 0, c->stream>>>(part, nt, nb, tile0, sk, n, P, st, D);
+            dist_finalize_kernel<<<dim3(nb, 8), 256, 0, c->stream>>>(part, nt, nb, tile0, sk, n, P, st, D);
         }
     }
     ESPER_CUDA(c, cudaGetLastError());

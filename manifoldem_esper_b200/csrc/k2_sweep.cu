@@ -31,23 +31,53 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
+// exp(-t) for 0 <= t: argument reduction by ln2 (hi/lo split), degree-13 Taylor polynomial on
+// |f| <= ln2/2 (truncation error 4e-18), exponent patched in place.  <= 1 ulp.  Callers route t > 700
+// (only reachable with thr = +inf) to the library exp, which handles gradual underflow.
+__device__ __forceinline__ double exp_neg_fast(double t) {     // requires 0 <= t <= 700
+    const double y = -t;
+    const double n = rint(y * 1.4426950408889634074);
+    double f = fma(n, -6.93147180369123816490e-01, y);
+    f = fma(n, -1.90821492927058770002e-10, f);
+    double p = 1.6059043836821613e-10;            // 1/13!
+    p = fma(p, f, 2.08767569878681e-09);           // 1/12!
+    p = fma(p, f, 2.505210838544172e-08);          // 1/11!
+    p = fma(p, f, 2.755731922398589e-07);          // 1/10!
+    p = fma(p, f, 2.7557319223985893e-06);         // 1/9!
+    p = fma(p, f, 2.48015873015873e-05);           // 1/8!
+    p = fma(p, f, 1.984126984126984e-04);          // 1/7!
+    p = fma(p, f, 1.388888888888889e-03);          // 1/6!
+    p = fma(p, f, 8.333333333333333e-03);          // 1/5!
+    p = fma(p, f, 4.1666666666666664e-02);         // 1/4!
+    p = fma(p, f, 1.6666666666666666e-01);         // 1/3!
+    p = fma(p, f, 0.5);
+    p = fma(p, f, 1.0);
+    p = fma(p, f, 1.0);
+    return __longlong_as_double(__double_as_longlong(p) + ((long long)(int)n << 52));
+}
+
 constexpr int TR = 16;                       // tile rows
 constexpr int TC = 128;                      // tile columns (a warp reads 32 consecutive doubles of a row)
 
 // sym != 0: D is exactly symmetric; only elements j >= i are visited, off-diagonal ones weigh 2.
 __global__ void __launch_bounds__(THREADS)
-sweep_kernel(const double* __restrict__ D, int m, int sym, const double* __restrict__ coef, int n_eps,
+sweep_kernel(const double* __restrict__ D, int m, int sym, int mono, const double* __restrict__ coef, int n_eps,
              double thr, double* __restrict__ part /*[gridDim.x][n_eps]*/) {
     extern __shared__ double sm[];
     double* acc = sm;                         // [n_eps]
     double* cf = sm + n_eps;                  // [n_eps]
     double* red = cf + n_eps;                 // [WARPS][KB]
     double* stat = red + WARPS * KB;          // [4][WARPS] min, max, n_zero, n_valid
+    double* below = stat + 4 * WARPS;         // [n_eps] difference array: closed-form A contributions
+    double* above = below + n_eps;            // [n_eps] difference array: closed-form B contributions
+    int* s_act = reinterpret_cast<int*>(above + n_eps);      // [n_eps] active k list (non-monotone coefficients)
+    int* s_nact = s_act + n_eps;
+    int* s_rng = s_nact + 1;                  // [2]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const double TINY = 8.673617379884035e-19;   // 2^-60: exp(-t) == 1.0 for 0 <= t < TINY
     const double SMALL = 7.450580596923828e-09;  // 2^-27: exp(-t) = 1 - t + t^2/2 to < 1e-25 relative
 
-    for (int k = threadIdx.x; k < n_eps; k += THREADS) { acc[k] = 0.0; cf[k] = coef[k]; }
+    for (int k = threadIdx.x; k < n_eps; k += THREADS) { acc[k] = 0.0; cf[k] = coef[k]; below[k] = 0.0; above[k] = 0.0; }
     __syncthreads();
 
     const int tiles_c = (m + TC - 1) / TC, tiles_r = (m + TR - 1) / TR;
@@ -62,7 +92,7 @@ sweep_kernel(const double* __restrict__ D, int m, int sym, const double* __restr
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
             const int i = row0 + (threadIdx.x >> 7) * EPT + e;
-            d2[e] = INFINITY;                // excluded / NaN: never included (t = inf or NaN is not < thr)
+            d2[e] = 0.0;                     // excluded (below the diagonal, out of range, NaN): weight 0
             wt[e] = 0.0;
             if (i < m && j < m && (!sym || j >= i)) {
                 const double d = __ldg(D + (size_t)i * m + j);
@@ -88,26 +118,67 @@ sweep_kernel(const double* __restrict__ D, int m, int sym, const double* __restr
         }
         const double zero_term = (0.0 < thr) ? nz : 0.0;
 
-        for (int k0 = 0; k0 < n_eps; k0 += KB) {
+        // Which k need evaluation for this tile?  (block-uniform facts)
+        //   A: no non-zero element passes the truncation  -> contribution zero_term (exact zeros give 1)
+        //   B: every element passes and exp(-t) == 1.0     -> contribution nv
+        // With non-increasing coefficients (the reference's grid) A holds for k < ka and B for k >= kb, so the
+        // closed forms go into two difference arrays (O(1) per tile) and [ka, kb) is evaluated; otherwise
+        // every k is classified and the active ones are queued.
+        int nact, ka = 0;
+        if (mono) {
+            if (threadIdx.x == 0) {
+                int lo_k = 0, hi_k = n_eps;                        // ka = first k with cf[k]*mn < thr
+                if (mn == INFINITY) lo_k = n_eps;
+                else while (lo_k < hi_k) { const int mid = (lo_k + hi_k) >> 1; if (cf[mid] * mn < thr) hi_k = mid; else lo_k = mid + 1; }
+                const int ka_ = lo_k;
+                lo_k = 0; hi_k = n_eps;                            // kb = first k with cf[k]*mx < min(TINY, thr)
+                while (lo_k < hi_k) { const int mid = (lo_k + hi_k) >> 1; if (cf[mid] * mx < TINY && cf[mid] * mx < thr) hi_k = mid; else lo_k = mid + 1; }
+                int kb_ = lo_k < ka_ ? ka_ : lo_k;
+                if (ka_ > 0) below[ka_ - 1] += zero_term;          // applies to all k <= ka-1 (suffix sum at the end)
+                if (kb_ < n_eps) above[kb_] += nv;                 // applies to all k >= kb   (prefix sum at the end)
+                s_rng[0] = ka_; s_rng[1] = kb_;
+            }
+            __syncthreads();
+            ka = s_rng[0];
+            nact = s_rng[1] - ka;
+        } else {
+            if (threadIdx.x == 0) *s_nact = 0;
+            __syncthreads();
+            for (int k = threadIdx.x; k < n_eps; k += THREADS) {
+                const double c = cf[k];
+                const bool shortcut = (c >= 0.0) && (c < INFINITY);      // monotone t = c*d2, no NaN products
+                if (shortcut && (mn == INFINITY || !(c * mn < thr))) acc[k] += zero_term;
+                else if (shortcut && c * mx < TINY && c * mx < thr) acc[k] += nv;
+                else s_act[atomicAdd(s_nact, 1)] = k;
+            }
+            __syncthreads();
+            nact = *s_nact;
+        }
+
+        for (int a0 = 0; a0 < nact; a0 += KB) {
 #pragma unroll
             for (int jj = 0; jj < KB; ++jj) {
-                const int k = k0 + jj;
                 double s = 0.0;
-                if (k < n_eps) {
-                    const double c = cf[k];
-                    const bool shortcut = (c >= 0.0) && (c < INFINITY);   // monotone t = c*d2, no NaN products
-                    if (shortcut && (mn == INFINITY || !(c * mn < thr))) {
-                        // no non-zero element passes the truncation; exact zeros give exp(-0) = 1
-                        s = (threadIdx.x == 0) ? zero_term : 0.0;
-                    } else if (shortcut && c * mx < TINY && c * mx < thr) {
-                        // every element passes and exp(-t) == 1.0 in binary64
-                        s = (threadIdx.x == 0) ? nv : 0.0;
-                    } else if (shortcut && c * mx < SMALL && c * mx < thr) {
-                        // every element passes; three-term series is exact to working precision
+                if (a0 + jj < nact) {
+                    const double c = cf[mono ? ka + a0 + jj : s_act[a0 + jj]];
+                    const double tmax = c * mx;
+                    if ((c >= 0.0) && tmax < SMALL && tmax < thr) {
+                        // every element passes; the three-term series is exact to working precision
 #pragma unroll
                         for (int e = 0; e < EPT; ++e) {
                             const double t = c * d2[e];
-                            if (wt[e] != 0.0) s = fma(wt[e], fma(t, fma(t, 0.5, -1.0), 1.0), s);
+                            s = fma(wt[e], fma(t, fma(t, 0.5, -1.0), 1.0), s);
+                        }
+                    } else if ((c >= 0.0) && tmax < 700.0) {
+                        // branch-free: all EPT exponentials are independent instruction streams
+                        double ev[EPT];
+#pragma unroll
+                        for (int e = 0; e < EPT; ++e) ev[e] = exp_neg_fast(fmin(c * d2[e], 700.0));
+#pragma unroll
+                        for (int e = 0; e < EPT; ++e) {
+                            const double t = c * d2[e];
+                            const double term = (t < SMALL) ? fma(t, fma(t, 0.5, -1.0), 1.0) : ev[e];
+                            s += (t < thr) ? wt[e] * term : 0.0;
                         }
                     } else {
 #pragma unroll
@@ -121,14 +192,24 @@ sweep_kernel(const double* __restrict__ D, int m, int sym, const double* __restr
                 if (lane == 0) red[warp * KB + jj] = s;
             }
             __syncthreads();
-            if (threadIdx.x < KB && k0 + threadIdx.x < n_eps) {
+            if (threadIdx.x < KB && a0 + threadIdx.x < nact) {
                 double t = 0.0;
 #pragma unroll
                 for (int w = 0; w < WARPS; ++w) t += red[w * KB + threadIdx.x];
-                acc[k0 + threadIdx.x] += t;
+                acc[mono ? ka + a0 + threadIdx.x : s_act[a0 + threadIdx.x]] += t;
             }
             __syncthreads();
         }
+    }
+    if (mono) {                                   // fold the difference arrays into acc (one thread; n_eps is small)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double run = 0.0;
+            for (int k = n_eps - 1; k >= 0; --k) { run += below[k]; acc[k] += run; }
+            run = 0.0;
+            for (int k = 0; k < n_eps; ++k) { run += above[k]; acc[k] += run; }
+        }
+        __syncthreads();
     }
     for (int k = threadIdx.x; k < n_eps; k += THREADS) part[(size_t)blockIdx.x * n_eps + k] = acc[k];
 }
@@ -185,7 +266,10 @@ int run_sweep(esper_ctx* c, int m, const double* coef_h, int n_eps, double thr, 
     double* coef_d = c->sweep_aux.as<double>() + 4096;
     double* logsum_d = coef_d + n_eps;
     ESPER_CUDA(c, cudaMemcpyAsync(coef_d, coef_h, sizeof(double) * n_eps, cudaMemcpyHostToDevice, c->stream));
-    const size_t smem = sizeof(double) * ((size_t)2 * n_eps + WARPS * KB + 4 * WARPS);
+    const size_t smem = sizeof(double) * ((size_t)4 * n_eps + WARPS * KB + 4 * WARPS) + sizeof(int) * ((size_t)n_eps + 4);
+    int mono = 1;                                  // non-increasing, finite, non-negative coefficients?
+    for (int k = 0; k < n_eps; ++k)
+        if (!(coef_h[k] >= 0.0) || !(coef_h[k] < INFINITY) || (k > 0 && coef_h[k] > coef_h[k - 1])) { mono = 0; break; }
     if (smem > 200 * 1024) return fail(c, ESPER_E_ARG, "n_eps=%d too large for the sweep kernel", n_eps);
     if (!c->attr_sweep) {
         ESPER_CUDA(c, cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -193,7 +277,7 @@ int run_sweep(esper_ctx* c, int m, const double* coef_h, int n_eps, double thr, 
     }
     {
         LaunchScope ls(c, "sweep");
-        sweep_kernel<<<grid, THREADS, smem, c->stream>>>(c->dist.as<double>(), m, sym, coef_d, n_eps, thr,
+        sweep_kernel<<<grid, THREADS, smem, c->stream>>>(c->dist.as<double>(), m, sym, mono, coef_d, n_eps, thr,
                                                          c->sweep_part.as<double>());
     }
     {

@@ -115,7 +115,7 @@ __device__ __forceinline__ double sum_partials(const double* part, int nb, doubl
 }
 
 // Persistent cooperative kernel: n_steps Lanczos steps with full reorthogonalisation.
-__global__ void __launch_bounds__(LAN_THREADS, 1) lanczos_steps_kernel(StepParams p) {
+__global__ void __launch_bounds__(LAN_THREADS, 2) lanczos_steps_kernel(StepParams p) {
     GridBarrier grid(p.bar);
     __shared__ double s_vec[LAN_CH];
     __shared__ double s_red[32 * 16];
@@ -126,9 +126,9 @@ __global__ void __launch_bounds__(LAN_THREADS, 1) lanczos_steps_kernel(StepParam
     const int nb = gridDim.x, b = blockIdx.x;
     const int chunk = (m + nb - 1) / nb;
     const int row0 = min(b * chunk, m), row1 = min(row0 + chunk, m);
-    const int gwarp = warp * nb + b, total_warps = nb * LAN_WARPS;   // consecutive basis vectors on different SMs
 
     int cur = 0;                                     // wbuf[cur] holds the un-normalised q_j (after the first step)
+    double s2_last = 0.0;                            // |w|^2 of the previous step (set by the DGKS test)
     for (int step = 0; step < p.n_steps; ++step) {
         const int j = p.j_start + step;
         // ---- source of q_j: normalised V[j] on the first step, else wbuf[cur] / beta ----
@@ -141,8 +141,7 @@ __global__ void __launch_bounds__(LAN_THREADS, 1) lanczos_steps_kernel(StepParam
         if (step == 0) {
             src = p.V + (size_t)j * m;
         } else {
-            const double s2 = sum_partials(p.part, nb, s_tmp);
-            const double bt = sqrt(s2);
+            const double bt = sqrt(s2_last);
             scale = bt > 0.0 ? 1.0 / bt : 0.0;
             src = p.wbuf + (size_t)cur * m;
             beta_prev = bt;
@@ -152,39 +151,37 @@ __global__ void __launch_bounds__(LAN_THREADS, 1) lanczos_steps_kernel(StepParam
         }
         double* wnew = p.wbuf + (size_t)(cur ^ 1) * m;
 
-        // ---- S0: w = Ms q_j for the owned rows (one warp per row, vector staged in shared memory) ----
-        {
-            double acc[4] = {0.0, 0.0, 0.0, 0.0};                      // up to 4 rows per warp per sweep
-            const int rows_per_sweep = LAN_WARPS * 4;
-            for (int rbase = row0; rbase < row1; rbase += rows_per_sweep) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) acc[q] = 0.0;
-                for (int c0 = 0; c0 < m; c0 += LAN_CH) {
-                    const int cn = min(LAN_CH, m - c0);
-                    __syncthreads();
-                    for (int cidx = tid; cidx < cn; cidx += LAN_THREADS) s_vec[cidx] = ld_cg(src + c0 + cidx);
-                    __syncthreads();
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int r = rbase + q * LAN_WARPS + warp;
-                        if (r < row1) {
-                            const double* a = p.Ms + (size_t)r * m + c0;
-                            double sacc = 0.0;
-                            for (int cidx = lane; cidx < cn; cidx += 32) sacc = fma(__ldg(a + cidx), s_vec[cidx], sacc);
-                            acc[q] += sacc;
-                        }
+        // ---- S0: w = Ms q_j - sigma q_j - beta q_{j-1} for the owned rows (one warp per row) ----
+        for (int rbase = row0; rbase < row1; rbase += LAN_WARPS) {
+            const int r = rbase + warp;
+            double acc = 0.0;
+            for (int c0 = 0; c0 < m; c0 += LAN_CH) {
+                const int cn = min(LAN_CH, m - c0);
+                __syncthreads();
+                for (int cidx = tid; cidx < cn; cidx += LAN_THREADS) s_vec[cidx] = ld_cg(src + c0 + cidx);
+                __syncthreads();
+                if (r < row1) {
+                    const double* a = p.Ms + (size_t)r * m + c0;
+                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                    int cidx = lane;
+                    for (; cidx + 224 < cn; cidx += 256) {            // 8 independent loads in flight per lane
+                        const double x0 = __ldg(a + cidx), x1 = __ldg(a + cidx + 32), x2 = __ldg(a + cidx + 64),
+                                     x3 = __ldg(a + cidx + 96), x4 = __ldg(a + cidx + 128), x5 = __ldg(a + cidx + 160),
+                                     x6 = __ldg(a + cidx + 192), x7 = __ldg(a + cidx + 224);
+                        a0 = fma(x0, s_vec[cidx], a0);       a1 = fma(x1, s_vec[cidx + 32], a1);
+                        a2 = fma(x2, s_vec[cidx + 64], a2);  a3 = fma(x3, s_vec[cidx + 96], a3);
+                        a0 = fma(x4, s_vec[cidx + 128], a0); a1 = fma(x5, s_vec[cidx + 160], a1);
+                        a2 = fma(x6, s_vec[cidx + 192], a2); a3 = fma(x7, s_vec[cidx + 224], a3);
                     }
+                    for (; cidx < cn; cidx += 32) a0 = fma(__ldg(a + cidx), s_vec[cidx], a0);
+                    acc += (a0 + a1) + (a2 + a3);
                 }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int r = rbase + q * LAN_WARPS + warp;
-                    const double tot = warp_sum(acc[q]);
-                    if (r < row1 && lane == 0) {
-                        double x = fma(-sigma, ld_cg(src + r) * scale, tot * scale);
-                        if (j >= 2) x = fma(-beta_prev, ld_cg(p.V + (size_t)(j - 1) * m + r), x);
-                        wnew[r] = x;
-                    }
-                }
+            }
+            const double tot = warp_sum(acc);
+            if (r < row1 && lane == 0) {
+                double x = fma(-sigma, ld_cg(src + r) * scale, tot * scale);
+                if (j >= 2) x = fma(-beta_prev, ld_cg(p.V + (size_t)(j - 1) * m + r), x);
+                wnew[r] = x;
             }
         }
         if (!grid.sync()) return;
@@ -192,13 +189,33 @@ __global__ void __launch_bounds__(LAN_THREADS, 1) lanczos_steps_kernel(StepParam
         for (int pass = 0; pass < 2; ++pass) {
             // ---- S1: h[i] = V_i . w for i <= j, and (first pass only) h[j+1] = w . w ----
             // (the second pass must not touch h[j+1]: slower CTAs may still be reading it for the DGKS test)
+            // Eight warps share one basis vector, two vectors per CTA per round.
             const int i_end = (pass == 0) ? j + 1 : j;
-            for (int i = gwarp; i <= i_end; i += total_warps) {
-                const double* v = (i <= j) ? p.V + (size_t)i * m : wnew;
+            const int grp = warp >> 3, gw = warp & 7;
+            for (int i0 = 0; i0 <= i_end; i0 += 2 * nb) {
+                const int i = i0 + grp * nb + b;
                 double sacc = 0.0;
-                for (int r = lane; r < m; r += 32) sacc = fma(ld_cg(v + r), ld_cg(wnew + r), sacc);
-                sacc = warp_sum(sacc);
-                if (lane == 0) p.h[i] = sacc;
+                if (i <= i_end) {
+                    const double* v = (i <= j) ? p.V + (size_t)i * m : wnew;
+                    double a0 = 0.0, a1 = 0.0;
+                    int r = gw * 32 + lane;
+                    for (; r + 768 < m; r += 1024) {                  // 4 independent load pairs per lane
+                        const double v0 = ld_cg(v + r), v1 = ld_cg(v + r + 256), v2 = ld_cg(v + r + 512), v3 = ld_cg(v + r + 768);
+                        const double w0 = ld_cg(wnew + r), w1 = ld_cg(wnew + r + 256), w2 = ld_cg(wnew + r + 512), w3 = ld_cg(wnew + r + 768);
+                        a0 = fma(v0, w0, a0); a1 = fma(v1, w1, a1); a0 = fma(v2, w2, a0); a1 = fma(v3, w3, a1);
+                    }
+                    for (; r < m; r += 256) a0 = fma(ld_cg(v + r), ld_cg(wnew + r), a0);
+                    sacc = warp_sum(a0 + a1);
+                }
+                __syncthreads();
+                if (lane == 0) s_red[warp] = sacc;
+                __syncthreads();
+                if (gw == 0 && lane == 0 && i <= i_end) {
+                    double tot = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) tot += s_red[grp * 8 + q];
+                    p.h[i] = tot;
+                }
             }
             if (!grid.sync()) return;
 
@@ -207,8 +224,18 @@ __global__ void __launch_bounds__(LAN_THREADS, 1) lanczos_steps_kernel(StepParam
             for (int rbase = row0; rbase < row1; rbase += 16) {
                 const int r = rbase + (tid & 15), sub = tid >> 4;
                 double sacc = 0.0;
-                if (r < row1)
-                    for (int i = sub; i <= j; i += 32) sacc = fma(ld_cg(p.h + i), ld_cg(p.V + (size_t)i * m + r), sacc);
+                if (r < row1) {
+                    double a0 = 0.0, a1 = 0.0;
+                    int i = sub;
+                    for (; i + 96 <= j; i += 128) {
+                        const double h0 = ld_cg(p.h + i), h1 = ld_cg(p.h + i + 32), h2 = ld_cg(p.h + i + 64), h3 = ld_cg(p.h + i + 96);
+                        const double v0 = ld_cg(p.V + (size_t)i * m + r), v1 = ld_cg(p.V + (size_t)(i + 32) * m + r),
+                                     v2 = ld_cg(p.V + (size_t)(i + 64) * m + r), v3 = ld_cg(p.V + (size_t)(i + 96) * m + r);
+                        a0 = fma(h0, v0, a0); a1 = fma(h1, v1, a1); a0 = fma(h2, v2, a0); a1 = fma(h3, v3, a1);
+                    }
+                    for (; i <= j; i += 32) a0 = fma(ld_cg(p.h + i), ld_cg(p.V + (size_t)i * m + r), a0);
+                    sacc = a0 + a1;
+                }
                 __syncthreads();
                 s_red[sub * 16 + (tid & 15)] = sacc;
                 __syncthreads();
@@ -231,18 +258,16 @@ __global__ void __launch_bounds__(LAN_THREADS, 1) lanczos_steps_kernel(StepParam
                 if (b == 0) { if (pass == 0) p.alpha[j - 1] = sigma + ld_cg(p.h + j); else p.alpha[j - 1] += ld_cg(p.h + j); }
             }
             if (!grid.sync()) return;
-            if (pass == 0) {                                           // DGKS: second pass iff |w_after|^2 < |w_before|^2 / 2
-                const double s2 = sum_partials(p.part, nb, s_tmp);
-                if (!(s2 < 0.5 * ld_cg(p.h + j + 1))) break;
-            }
+            s2_last = sum_partials(p.part, nb, s_tmp);
+            // DGKS ("twice is enough"): second pass iff |w_after|^2 < |w_before|^2 / 2
+            if (pass == 0 && !(s2_last < 0.5 * ld_cg(p.h + j + 1))) break;
         }
         cur ^= 1;
     }
     // ---- tail: publish beta of the last step and the normalised next vector ----
     {
         const int j = p.j_start + p.n_steps;                           // index of the next vector
-        const double s2 = sum_partials(p.part, nb, s_tmp);
-        const double bt = sqrt(s2);
+        const double bt = sqrt(s2_last);
         const double scale = bt > 0.0 ? 1.0 / bt : 0.0;
         const double* src = p.wbuf + (size_t)cur * m;
         if (b == 0 && tid == 0) p.beta[j - 2] = bt;
@@ -274,32 +299,23 @@ __global__ void __launch_bounds__(256) init_kernel(const double* __restrict__ de
     w_rand[r] = (double)x * (1.0 / 4294967296.0) - 0.5;
 }
 
-// U[r][1+i] = sum_l V_{1+l}[r] S[l][i]; U[r][0] = V_0[r].  One thread per row, S staged in shared memory.
-template <int KMAX>
+// U[r][1+i] = sum_l V_{1+l}[r] S[l][i]; U[r][0] = V_0[r].  One thread per (row, Ritz vector).
 __global__ void __launch_bounds__(128) ritz_kernel(const double* __restrict__ V, int m, int steps,
                                                    const double* __restrict__ S, int kw, double* __restrict__ U, int k) {
-    __shared__ double s_tile[32 * KMAX];
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    double acc[KMAX];
-#pragma unroll
-    for (int i = 0; i < KMAX; ++i) acc[i] = 0.0;
-    for (int l0 = 0; l0 < steps; l0 += 32) {
-        const int nl = min(32, steps - l0);
-        __syncthreads();
-        for (int t = threadIdx.x; t < nl * kw; t += blockDim.x) s_tile[(t / kw) * KMAX + (t % kw)] = S[(size_t)(l0 + t / kw) * kw + (t % kw)];
-        __syncthreads();
-        if (r < m) {
-            for (int l = 0; l < nl; ++l) {
-                const double v = __ldg(V + (size_t)(1 + l0 + l) * m + r);
-#pragma unroll
-                for (int i = 0; i < KMAX; ++i) if (i < kw) acc[i] = fma(v, s_tile[l * KMAX + i], acc[i]);
-            }
-        }
+    const int i = blockIdx.y;                       // 0 -> steady state, 1.. -> Ritz vector i-1
+    if (r >= m) return;
+    if (i == 0) { U[(size_t)r * k] = V[r]; return; }
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int l = 0;
+    for (; l + 3 < steps; l += 4) {
+        a0 = fma(__ldg(V + (size_t)(1 + l) * m + r), __ldg(S + (size_t)l * kw + (i - 1)), a0);
+        a1 = fma(__ldg(V + (size_t)(2 + l) * m + r), __ldg(S + (size_t)(l + 1) * kw + (i - 1)), a1);
+        a2 = fma(__ldg(V + (size_t)(3 + l) * m + r), __ldg(S + (size_t)(l + 2) * kw + (i - 1)), a2);
+        a3 = fma(__ldg(V + (size_t)(4 + l) * m + r), __ldg(S + (size_t)(l + 3) * kw + (i - 1)), a3);
     }
-    if (r < m) {
-        U[(size_t)r * k] = V[r];
-        for (int i = 0; i < kw; ++i) U[(size_t)r * k + 1 + i] = acc[i];
-    }
+    for (; l < steps; ++l) a0 = fma(__ldg(V + (size_t)(1 + l) * m + r), __ldg(S + (size_t)l * kw + (i - 1)), a0);
+    U[(size_t)r * k + i] = (a0 + a1) + (a2 + a3);
 }
 
 // Normalise each column to unit length and make its largest-magnitude entry positive (first on ties).
@@ -463,7 +479,7 @@ int run_lanczos(esper_ctx* c, int m, int k, double tol, int max_iter, double* va
     using namespace lanczos;
     constexpr int KMAX = 64;
     if (k < 1 || k > m || k > KMAX) return fail(c, ESPER_E_ARG, "k=%d out of range (1..min(m,%d))", k, KMAX);
-    if (tol <= 0.0) tol = 1e-11;
+    if (tol <= 0.0) tol = 1e-10;
     const int kw = k - 1;                               // non-trivial pairs wanted
     int guard = (kw > 0) ? std::min(2, m - 1 - kw) : 0;
     if (guard < 0) guard = 0;
@@ -578,7 +594,7 @@ int run_lanczos(esper_ctx* c, int m, int k, double tol, int max_iter, double* va
             for (int i = 0; i < kw; ++i) Sk[(size_t)l * kw + i] = S[(size_t)l * want + i];
         ESPER_CUDA(c, cudaMemcpyAsync(S_d, Sk.data(), sizeof(double) * Sk.size(), cudaMemcpyHostToDevice, st));
     }
-    { LaunchScope ls(c, "lanczos"); ritz_kernel<KMAX><<<ceil_div(m, 128), 128, 0, st>>>(V, m, kw > 0 ? steps : 0, S_d, kw, U, k); }
+    { LaunchScope ls(c, "lanczos"); ritz_kernel<<<dim3(ceil_div(m, 128), k), 128, 0, st>>>(V, m, kw > 0 ? steps : 0, S_d, kw, U, k); }
     { LaunchScope ls(c, "lanczos"); fix_columns_kernel<<<k, 256, 0, st>>>(U, m, k); }
     ESPER_CUDA(c, cudaGetLastError());
     if (vec_h) ESPER_CUDA(c, cudaMemcpyAsync(vec_h, U, sizeof(double) * (size_t)m * k, cudaMemcpyDeviceToHost, st));
