@@ -201,11 +201,13 @@ def run_ours(args):
     # ---- resident arm: stacks already in HBM.  Two PDs are in flight per GPU (one host thread + ctx +
     # stream each) so that the host-side tanh fit / Lanczos convergence tests of one PD overlap the
     # kernels of the other; a serial pass on one stream provides clean per-kernel timings. ----
-    stream_b = torch.cuda.Stream()
-    ctx_b = _capi.Context(local_rank, stream=stream_b.cuda_stream)
-    ctxs, streams = [ctx, ctx_b], [stream, stream_b]
-    for c, t in zip(ctxs, pinned):
-        c.upload_images(t.numpy())
+    NF = max(1, args.inflight)
+    ctxs, streams = [ctx], [stream]
+    for _ in range(NF - 1):
+        st_ = torch.cuda.Stream()
+        ctxs.append(_capi.Context(local_rank, stream=st_.cuda_stream)); streams.append(st_)
+    for i, c in enumerate(ctxs):
+        c.upload_images(pinned[i % n_stacks].numpy())
         c.sync()
     iters_used = []
 
@@ -216,25 +218,28 @@ def run_ours(args):
         def worker(t):
             try:
                 torch.cuda.set_device(local_rank)
-                for s in range(t, n_steps, 2):
+                for s in range(t, n_steps, NF):
                     if e2e:
-                        embed_step(ctxs[t], GB, coef, a0, N_IMG, P, imgs=pinned[t].numpy(), download=True)
+                        embed_step(ctxs[t], GB, coef, a0, N_IMG, P, imgs=pinned[t % n_stacks].numpy(), download=True)
                     else:
                         out = embed_step(ctxs[t], GB, coef, a0, N_IMG, P)
                         iters_used.append(out[4])
             except Exception as e:                     # noqa: BLE001
                 errs.append(e)
         barrier()
-        e0, e1, eb = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(streams[0])
-        streams[1].wait_event(e0)
-        th = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+        for st_ in streams[1:]:
+            st_.wait_event(e0)
+        th = [threading.Thread(target=worker, args=(t,)) for t in range(NF)]
         for x in th:
             x.start()
         for x in th:
             x.join()
-        eb.record(streams[1])
-        streams[0].wait_event(eb)
+        for st_ in streams[1:]:
+            eb = torch.cuda.Event()
+            eb.record(st_)
+            streams[0].wait_event(eb)
         e1.record(streams[0])
         barrier()
         if errs:
@@ -242,8 +247,8 @@ def run_ours(args):
         return e0.elapsed_time(e1)
 
     for w in range(args.warmup):
-        embed_step(ctxs[w % 2], GB, coef, a0, N_IMG, P)
-    pipelined(2, False)
+        embed_step(ctxs[w % NF], GB, coef, a0, N_IMG, P)
+    pipelined(NF, False)
     # serial profiled pass (per-kernel CUDA-event durations; single stream, nothing overlapping)
     for c in ctxs:
         c.set_profiling(True); c.reset_profiling()
@@ -276,7 +281,7 @@ def run_ours(args):
     launches = sum(c.launch_count() for c in ctxs) - launches0
 
     # ---- end-to-end arm: host stacks -> H2D -> stages -> D2H of D, sweep, eigenpairs (two in flight) ----
-    pipelined(2, True)
+    pipelined(NF, True)
     ms_e2e = pipelined(args.steps, True)
 
     tms = torch.tensor([ms, ms_e2e, float(launches), ms_serial], dtype=torch.float64, device='cuda')
@@ -321,7 +326,7 @@ def run_ours(args):
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32x3+f64',
         'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'pd_per_rank_per_step': 1, 'sharding': 'independent PDs per rank, no data-path collective',
-                   'pipelining': 'two PDs in flight per GPU (two host threads / ctxs / streams)', 'serial_ms_per_step': ms_serial / args.steps,
+                   'pipelining': '%d PDs in flight per GPU (one host thread / ctx / stream each)' % NF, 'serial_ms_per_step': ms_serial / args.steps,
                    'l2': 'inputs larger than L2 (500 MB stack per PD, two alternating stacks per rank)',
                    'lanczos_steps': iters_used[-1] if iters_used else None},
         'e2e': {'value': pds / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(N_IMG * P * 4),
@@ -364,6 +369,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--inflight', type=int, default=4, help='PDs in flight per GPU (host threads / ctxs / streams)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

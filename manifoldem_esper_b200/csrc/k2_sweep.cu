@@ -16,7 +16,7 @@ namespace esper {
 namespace sweep {
 
 constexpr int THREADS = 256;
-constexpr int EPT = 8;                       // elements per thread per chunk
+constexpr int EPT = 4;                       // elements per thread per tile
 constexpr int KB = 8;                        // k values reduced per barrier pair
 constexpr int WARPS = THREADS / 32;
 
@@ -56,13 +56,14 @@ __device__ __forceinline__ double exp_neg_fast(double t) {     // requires 0 <= 
     return __longlong_as_double(__double_as_longlong(p) + ((long long)(int)n << 52));
 }
 
-constexpr int TR = 16;                       // tile rows
+constexpr int TR = 8;                        // tile rows (THREADS / TC row groups x EPT)
 constexpr int TC = 128;                      // tile columns (a warp reads 32 consecutive doubles of a row)
 
 // sym != 0: D is exactly symmetric; only elements j >= i are visited, off-diagonal ones weigh 2.
 __global__ void __launch_bounds__(THREADS)
 sweep_kernel(const double* __restrict__ D, int m, int sym, int mono, const double* __restrict__ coef, int n_eps,
-             double thr, double* __restrict__ part /*[gridDim.x][n_eps]*/) {
+             double thr, const int* __restrict__ row_start /*[tiles_r+1] prefix of valid tiles*/,
+             unsigned int* __restrict__ next_tile, double* __restrict__ part /*[gridDim.x][n_eps]*/) {
     extern __shared__ double sm[];
     double* acc = sm;                         // [n_eps]
     double* cf = sm + n_eps;                  // [n_eps]
@@ -81,11 +82,20 @@ sweep_kernel(const double* __restrict__ D, int m, int sym, int mono, const doubl
     __syncthreads();
 
     const int tiles_c = (m + TC - 1) / TC, tiles_r = (m + TR - 1) / TR;
-    const long long n_tiles = (long long)tiles_r * tiles_c;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int tr = (int)(tile / tiles_c), tc = (int)(tile % tiles_c);
+    const int n_valid = row_start[tiles_r];
+    __shared__ int s_tile;
+    for (;;) {
+        // dynamic tile scheduler: valid tiles (on or above the diagonal when sym) are handed out in order
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = (int)atomicAdd(next_tile, 1u);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= n_valid) break;
+        int lo_r = 0, hi_r = tiles_r;                             // tr = last row with row_start[tr] <= tile
+        while (hi_r - lo_r > 1) { const int mid = (lo_r + hi_r) >> 1; if (row_start[mid] <= tile) lo_r = mid; else hi_r = mid; }
+        const int tr = lo_r;
+        const int tc = tiles_c - (row_start[tr + 1] - row_start[tr]) + (tile - row_start[tr]);
         const int row0 = tr * TR, col0 = tc * TC;
-        if (sym && col0 + TC - 1 < row0) continue;               // tile entirely below the diagonal
         double d2[EPT], wt[EPT];
         double mn = INFINITY, mx = 0.0, nz = 0.0, nv = 0.0;
         const int j = col0 + (threadIdx.x & (TC - 1));
@@ -257,15 +267,25 @@ int run_sweep(esper_ctx* c, int m, const double* coef_h, int n_eps, double thr, 
     using namespace sweep;
     if (c->dist_symmetric < 0) { int rc = check_symmetry(c, m); if (rc) return rc; }
     const int sym = c->dist_symmetric > 0 ? 1 : 0;
-    const long long n_tiles = (long long)ceil_div(m, TR) * ceil_div(m, TC);
+    const int tiles_r = ceil_div(m, TR), tiles_c = ceil_div(m, TC);
+    std::vector<int> row_start(tiles_r + 2, 0);                   // prefix count of valid tiles per tile row
+    for (int tr = 0; tr < tiles_r; ++tr) {
+        const int first = sym ? (tr * TR) / TC : 0;               // first tile column touching j >= i
+        row_start[tr + 1] = row_start[tr] + (tiles_c - first);
+    }
+    const int n_valid = row_start[tiles_r];
     int grid = c->sm_count * 4;
-    if (grid > n_tiles) grid = (int)n_tiles;
+    if (grid > n_valid) grid = n_valid;
     if (grid < 1) grid = 1;
     ESPER_RESERVE(c, c->sweep_part, sizeof(double) * (size_t)grid * n_eps);
-    ESPER_RESERVE(c, c->sweep_aux, sizeof(double) * ((size_t)n_eps * 2 + 4096));
+    ESPER_RESERVE(c, c->sweep_aux, sizeof(double) * ((size_t)n_eps * 2 + 4096) + sizeof(int) * (size_t)(tiles_r + 8));
     double* coef_d = c->sweep_aux.as<double>() + 4096;
     double* logsum_d = coef_d + n_eps;
+    int* row_start_d = reinterpret_cast<int*>(logsum_d + n_eps);
+    unsigned int* next_tile_d = reinterpret_cast<unsigned int*>(row_start_d + tiles_r + 2);
     ESPER_CUDA(c, cudaMemcpyAsync(coef_d, coef_h, sizeof(double) * n_eps, cudaMemcpyHostToDevice, c->stream));
+    ESPER_CUDA(c, cudaMemcpyAsync(row_start_d, row_start.data(), sizeof(int) * (size_t)(tiles_r + 1), cudaMemcpyHostToDevice, c->stream));
+    ESPER_CUDA(c, cudaMemsetAsync(next_tile_d, 0, sizeof(unsigned int), c->stream));
     const size_t smem = sizeof(double) * ((size_t)4 * n_eps + WARPS * KB + 4 * WARPS) + sizeof(int) * ((size_t)n_eps + 4);
     int mono = 1;                                  // non-increasing, finite, non-negative coefficients?
     for (int k = 0; k < n_eps; ++k)
@@ -278,7 +298,7 @@ int run_sweep(esper_ctx* c, int m, const double* coef_h, int n_eps, double thr, 
     {
         LaunchScope ls(c, "sweep");
         sweep_kernel<<<grid, THREADS, smem, c->stream>>>(c->dist.as<double>(), m, sym, mono, coef_d, n_eps, thr,
-                                                         c->sweep_part.as<double>());
+                                                         row_start_d, next_tile_d, c->sweep_part.as<double>());
     }
     {
         LaunchScope ls(c, "sweep");
