@@ -108,6 +108,36 @@ int esper_markov(esper_ctx* ctx, const double* D, int m, double eps, double* deg
 int esper_dmap_embed(esper_ctx* ctx, const double* D, int m, double eps, int k, double tol,
                      int max_iter, double* val, double* vec, int* iters);
 
+/* ---- oversized PD: distance-matrix row blocks (BASELINE config 4) ------------------
+ * One PD too large for one GPU is split by row blocks of D / A / Ms: rank g owns rows [row0, row0+nrows)
+ * (row0 a multiple of 128).  The same reference arithmetic as above (Distances.py:87-104,
+ * GaussianBandwidth.py:36-44, DiffusionMaps.py:109-169) is evaluated on the block; the collectives
+ * (sum of the sweep partials, all-gather of the degrees and of the Lanczos vector) are done by the host
+ * layer between these calls (manifoldem_esper_b200/rowblock.py, torch.distributed over NCCL).
+ * Tiles below the diagonal are computed as the mirror image of the upper-triangle tile, so the block holds
+ * bit-identical values to the corresponding rows of esper_dist_rms for the same split_k. */
+int esper_dist_rms_rows(esper_ctx* ctx, const float* imgs /*[n,P] or NULL=resident*/, int n, int P, unsigned flags,
+                        int row0, int nrows, double* D_rows /*[nrows,n] or NULL*/);
+/* sums[k] = sum over the resident block of exp(-t) with t < thr (NOT the logarithm: ranks add these). */
+int esper_eps_sweep_rows(esper_ctx* ctx, int nrows, int n, const double* coef, int n_eps, double thr, double* sums);
+/* degree of the owned rows (DiffusionMaps.py:131-137): degree_rows [nrows]. */
+int esper_degree_rows(esper_ctx* ctx, int nrows, int n, double eps, double* degree_rows);
+/* Ms rows from the gathered degrees of all n rows (DiffusionMaps.py:139-152); block stays resident. */
+int esper_markov_rows(esper_ctx* ctx, int nrows, int n, double eps, const double* degree_all);
+/* w_rows_d[nrows] = Ms_rows . q_d[n]   (device pointers; asynchronous on the ctx stream). */
+int esper_symv_rows_d(esper_ctx* ctx, int nrows, int n, const double* q_d, double* w_rows_d);
+/* Replicated Lanczos state, vectors owned by the caller on the device: V_d is [max_steps+2, n].
+ * start: V_d[0] = sqrt(degree)/|.| (locked), V_d[1] = start vector.  ortho (step j >= 1, w_d = gathered
+ * Ms V_d[j]): Gram-Schmidt twice against V_d[0..j], alpha_beta_d = {alpha_j, beta_j}, V_d[j+1] = w/beta_j. */
+int esper_lanczos_start_d(esper_ctx* ctx, int n, const double* degree_all, double* V_d);
+int esper_lanczos_ortho_d(esper_ctx* ctx, int n, int j, double* V_d, double* w_d, double* alpha_beta_d);
+/* Host only: Ritz values/vectors of T = tridiag(beta, alpha, beta) (steps x steps), convergence of the leading
+ * k-1 pairs to relative residual tol; theta [k-1] (may be NULL), S [steps, k-1] (may be NULL). */
+int esper_tridiag_ritz(const double* alpha, const double* beta, int steps, int k, double tol, int* converged,
+                       double* theta, double* S);
+/* vec [n, k] = [V_d[0], V_d[1..steps] S], unit columns, sign fixed (same convention as esper_dmap_embed). */
+int esper_ritz_vectors_d(esper_ctx* ctx, int n, int steps, int k, const double* V_d, const double* S, double* vec);
+
 /* ---- stage 4: Nd rotation + 2-D histogram sweep -----------------------------------------
  * esper_nd_rotation: host-side restatement of 2_Manifold_Rotations/Generate_Nd_Rot.py:4-45,
  * R = G_0 G_1 ... G_{T-1} (T = n(n-1)/2, lexicographic planes), left to right, each two-term sum

@@ -45,6 +45,15 @@ SIGNATURES = {
     'esper_markov': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     'esper_dmap_embed': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int,
                                    C.c_void_p, C.c_void_p, _i32p]),
+    'esper_dist_rms_rows': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int, C.c_void_p]),
+    'esper_eps_sweep_rows': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
+    'esper_degree_rows': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]),
+    'esper_markov_rows': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]),
+    'esper_symv_rows_d': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    'esper_lanczos_start_d': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    'esper_lanczos_ortho_d': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'esper_tridiag_ritz': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, _i32p, C.c_void_p, C.c_void_p]),
+    'esper_ritz_vectors_d': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     'esper_nd_rotation': (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     'esper_hist_edges': (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_void_p]),
     'esper_rot_hist_eval': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
@@ -209,6 +218,48 @@ class Context:
                                                _ptr(val), _ptr(vec), C.byref(it)))
         return val, vec, it.value
 
+    # -- oversized-PD row-block path (device pointers are plain ints, e.g. torch.Tensor.data_ptr()) ----
+    def dist_rms_rows(self, imgs, n, P, row0, nrows, flags=DIST_DEFAULT, download=False):
+        if imgs is not None:
+            imgs = _check_stack(imgs)
+            n, P = imgs.shape
+        D = np.empty((nrows, n), dtype=np.float64) if download else None
+        self._check(self._lib.esper_dist_rms_rows(self._h, _ptr(imgs), int(n), int(P), int(flags), int(row0), int(nrows), _ptr(D)))
+        return D
+
+    def eps_sweep_rows(self, nrows, n, coef, thr):
+        coef = _as(coef, np.float64).reshape(-1)
+        out = np.empty(coef.shape[0], dtype=np.float64)
+        self._check(self._lib.esper_eps_sweep_rows(self._h, int(nrows), int(n), _ptr(coef), coef.shape[0], float(thr), _ptr(out)))
+        return out
+
+    def degree_rows(self, nrows, n, eps):
+        out = np.empty(nrows, dtype=np.float64)
+        self._check(self._lib.esper_degree_rows(self._h, int(nrows), int(n), float(eps), _ptr(out)))
+        return out
+
+    def markov_rows(self, nrows, n, eps, degree_all):
+        degree_all = _as(degree_all, np.float64).reshape(-1)
+        if degree_all.shape[0] != n:
+            raise ValueError('markov_rows: degree_all must have n entries')
+        self._check(self._lib.esper_markov_rows(self._h, int(nrows), int(n), float(eps), _ptr(degree_all)))
+
+    def symv_rows_d(self, nrows, n, q_ptr, w_ptr):
+        self._check(self._lib.esper_symv_rows_d(self._h, int(nrows), int(n), C.c_void_p(q_ptr), C.c_void_p(w_ptr)))
+
+    def lanczos_start_d(self, n, degree_all, V_ptr):
+        degree_all = _as(degree_all, np.float64).reshape(-1)
+        self._check(self._lib.esper_lanczos_start_d(self._h, int(n), _ptr(degree_all), C.c_void_p(V_ptr)))
+
+    def lanczos_ortho_d(self, n, j, V_ptr, w_ptr, ab_ptr):
+        self._check(self._lib.esper_lanczos_ortho_d(self._h, int(n), int(j), C.c_void_p(V_ptr), C.c_void_p(w_ptr), C.c_void_p(ab_ptr)))
+
+    def ritz_vectors_d(self, n, steps, k, V_ptr, S):
+        S = _as(S, np.float64)
+        vec = np.empty((n, k), dtype=np.float64)
+        self._check(self._lib.esper_ritz_vectors_d(self._h, int(n), int(steps), int(k), C.c_void_p(V_ptr), _ptr(S), _ptr(vec)))
+        return vec
+
     # -- stage 4 ----------------------------------------------------------------------------
     def rot_hist_eval(self, Uinit, R, pd_of_eval, v1, v2, bins=51, lo=-1.5, hi=1.5, want_hist=False):
         Uinit = _as(Uinit, np.float64)
@@ -260,6 +311,20 @@ def _check_square(D):
     if D.ndim != 2 or D.shape[0] != D.shape[1] or D.shape[0] < 1:
         raise ValueError('distance matrix must be square [m, m] with m >= 1')
     return _as(D, np.float64)
+
+
+def tridiag_ritz(alpha, beta, k, tol=0.0):
+    """Host only: (converged, theta[k-1], S[steps, k-1]) of T = tridiag(beta, alpha, beta) (esper_tridiag_ritz)."""
+    lib = load_library()
+    alpha, beta = _as(alpha, np.float64).reshape(-1), _as(beta, np.float64).reshape(-1)
+    steps = alpha.shape[0]
+    if beta.shape[0] != steps or k < 2:
+        raise ValueError('tridiag_ritz: alpha and beta must have one entry per step and k >= 2')
+    theta = np.zeros(k - 1); S = np.zeros((steps, k - 1)); conv = C.c_int(0)
+    rc = lib.esper_tridiag_ritz(_ptr(alpha), _ptr(beta), steps, int(k), float(tol), C.byref(conv), _ptr(theta), _ptr(S))
+    if rc != ESPER_OK:
+        raise ValueError('tridiag_ritz: bad argument')
+    return bool(conv.value), theta, S
 
 
 def nd_rotation(n, theta):

@@ -160,7 +160,7 @@ int esper_dist_rms(esper_ctx* c, const float* imgs, int n, int P, unsigned flags
     if (rc) return rc;
     rc = run_gram(c, n, P, rows_pad, ld, flags);
     if (rc) return rc;
-    c->dist_m = n;
+    c->dist_m = n; c->dist_rows = 0; c->dist_row0 = -1;
     c->dist_symmetric = 1;                  // mirrored writes: symmetric by construction
     if (D) {
         ESPER_CUDA(c, cudaMemcpyAsync(D, c->dist.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, c->stream));
@@ -174,7 +174,7 @@ int esper_upload_dist(esper_ctx* c, const double* D, int m) {
     if (!D || m < 1) return fail(c, ESPER_E_ARG, "upload_dist: need D != NULL and m >= 1");
     ESPER_RESERVE(c, c->dist, sizeof(double) * (size_t)m * m);
     ESPER_CUDA(c, cudaMemcpyAsync(c->dist.p, D, sizeof(double) * (size_t)m * m, cudaMemcpyHostToDevice, c->stream));
-    c->dist_m = m;
+    c->dist_m = m; c->dist_rows = 0; c->dist_row0 = -1;
     c->dist_symmetric = -1;
     return ESPER_OK;
 }
@@ -182,7 +182,7 @@ int esper_upload_dist(esper_ctx* c, const double* D, int m) {
 static int need_dist(esper_ctx* c, const double* D, int m, const char* who) {
     if (m < 1) return fail(c, ESPER_E_ARG, "%s: need m >= 1", who);
     if (D) return esper_upload_dist(c, D, m);
-    if (c->dist_m != m || !c->dist.p)
+    if (c->dist_m != m || !c->dist.p || c->dist_row0 >= 0)
         return fail(c, ESPER_E_STATE, "%s: D == NULL but no resident %dx%d distance matrix (resident m=%d)", who, m, m, c->dist_m);
     return ESPER_OK;
 }
@@ -223,6 +223,103 @@ int esper_dmap_embed(esper_ctx* c, const double* D, int m, double eps, int k, do
     rc = run_markov(c, m, eps);
     if (rc) return rc;
     return run_lanczos(c, m, k, tol, max_iter, val, vec, iters);
+}
+
+// ---- oversized-PD row-block path ----------------------------------------------------------------
+int esper_dist_rms_rows(esper_ctx* c, const float* imgs, int n, int P, unsigned flags, int row0, int nrows, double* D_rows) {
+    ESPER_ENTER(c);
+    if (n < 1 || P < 1) return fail(c, ESPER_E_ARG, "dist_rms_rows: need n >= 1 and P >= 1");
+    if (row0 < 0 || nrows < 1 || row0 + nrows > n || (row0 % 128) != 0)
+        return fail(c, ESPER_E_ARG, "dist_rms_rows: need 0 <= row0 (multiple of 128), nrows >= 1, row0 + nrows <= n");
+    if (imgs) {
+        int rc = esper_upload_images(c, imgs, n, P);
+        if (rc) return rc;
+    } else if (c->img_n != n || c->img_P != P || !c->imgs.p) {
+        return fail(c, ESPER_E_STATE, "dist_rms_rows: imgs == NULL but no resident [%d, %d] stack", n, P);
+    }
+    const int rows_pad = (int)round_up((size_t)n, 128);
+    const int ld = (int)round_up((size_t)P, 32);
+    ESPER_RESERVE(c, c->dist, sizeof(double) * (size_t)nrows * n);
+    c->dist_m = 0;
+    int rc = run_prep(c, n, P, flags, rows_pad, ld);
+    if (rc) return rc;
+    rc = run_gram(c, n, P, rows_pad, ld, flags, row0, nrows);
+    if (rc) return rc;
+    c->dist_m = n; c->dist_rows = nrows; c->dist_row0 = row0; c->dist_symmetric = 0;
+    if (D_rows) {
+        ESPER_CUDA(c, cudaMemcpyAsync(D_rows, c->dist.p, sizeof(double) * (size_t)nrows * n, cudaMemcpyDeviceToHost, c->stream));
+        ESPER_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return ESPER_OK;
+}
+
+static int need_rows(esper_ctx* c, int nrows, int n, const char* who) {
+    if (c->dist_row0 < 0 || c->dist_rows != nrows || c->dist_m != n || !c->dist.p)
+        return fail(c, ESPER_E_STATE, "%s: no resident [%d, %d] distance row block (call esper_dist_rms_rows first)", who, nrows, n);
+    return ESPER_OK;
+}
+
+int esper_eps_sweep_rows(esper_ctx* c, int nrows, int n, const double* coef, int n_eps, double thr, double* sums) {
+    ESPER_ENTER(c);
+    if (!coef || !sums || n_eps < 1) return fail(c, ESPER_E_ARG, "eps_sweep_rows: need coef, sums != NULL and n_eps >= 1");
+    int rc = need_rows(c, nrows, n, "eps_sweep_rows");
+    if (rc) return rc;
+    return run_sweep_rows(c, nrows, n, coef, n_eps, thr, sums, 0);
+}
+
+int esper_degree_rows(esper_ctx* c, int nrows, int n, double eps, double* degree_rows) {
+    ESPER_ENTER(c);
+    if (!(eps > 0.0) || !degree_rows) return fail(c, ESPER_E_ARG, "degree_rows: need eps > 0 and degree_rows != NULL");
+    int rc = need_rows(c, nrows, n, "degree_rows");
+    if (rc) return rc;
+    return run_markov_rows(c, nrows, n, c->dist_row0, eps, nullptr, degree_rows, 0);
+}
+
+int esper_markov_rows(esper_ctx* c, int nrows, int n, double eps, const double* degree_all) {
+    ESPER_ENTER(c);
+    if (!(eps > 0.0) || !degree_all) return fail(c, ESPER_E_ARG, "markov_rows: need eps > 0 and degree_all != NULL");
+    int rc = need_rows(c, nrows, n, "markov_rows");
+    if (rc) return rc;
+    return run_markov_rows(c, nrows, n, c->dist_row0, eps, degree_all, nullptr, 1);
+}
+
+int esper_symv_rows_d(esper_ctx* c, int nrows, int n, const double* q_d, double* w_rows_d) {
+    ESPER_ENTER(c);
+    if (!q_d || !w_rows_d || nrows < 1 || n < 1 || !c->markov.p) return fail(c, ESPER_E_ARG, "symv_rows_d: bad argument or no resident Ms block");
+    return run_symv_rows(c, nrows, n, q_d, w_rows_d);
+}
+
+int esper_lanczos_start_d(esper_ctx* c, int n, const double* degree_all, double* V_d) {
+    ESPER_ENTER(c);
+    if (!degree_all || !V_d || n < 2) return fail(c, ESPER_E_ARG, "lanczos_start_d: bad argument");
+    return run_lanczos_start(c, n, degree_all, V_d);
+}
+
+int esper_lanczos_ortho_d(esper_ctx* c, int n, int j, double* V_d, double* w_d, double* alpha_beta_d) {
+    ESPER_ENTER(c);
+    if (!V_d || !w_d || !alpha_beta_d || n < 2 || j < 1) return fail(c, ESPER_E_ARG, "lanczos_ortho_d: bad argument");
+    return run_lanczos_ortho(c, n, j, V_d, w_d, alpha_beta_d);
+}
+
+int esper_tridiag_ritz(const double* alpha, const double* beta, int steps, int k, double tol, int* converged,
+                       double* theta, double* S) {
+    if (!alpha || !beta || steps < 1 || k < 2 || !converged) return ESPER_E_ARG;
+    if (tol <= 0.0) tol = 1e-10;
+    const int kw = k - 1;
+    std::vector<double> a(alpha, alpha + steps), b(beta, beta + steps), th, Sv;
+    const int guard = 2;
+    const bool ok = ritz_converged(a, b, steps, kw, guard, tol, th, Sv);
+    const int want = (int)th.size();
+    *converged = (ok && want >= kw) ? 1 : 0;
+    if (theta) for (int i = 0; i < kw; ++i) theta[i] = i < want ? th[i] : 0.0;
+    if (S) for (int l = 0; l < steps; ++l) for (int i = 0; i < kw; ++i) S[(size_t)l * kw + i] = i < want ? Sv[(size_t)l * want + i] : 0.0;
+    return ESPER_OK;
+}
+
+int esper_ritz_vectors_d(esper_ctx* c, int n, int steps, int k, const double* V_d, const double* S, double* vec) {
+    ESPER_ENTER(c);
+    if (!V_d || !vec || n < 1 || k < 1 || (k > 1 && (!S || steps < 1))) return fail(c, ESPER_E_ARG, "ritz_vectors_d: bad argument");
+    return run_ritz_vectors(c, n, steps, k, V_d, S, vec);
 }
 
 // ---- stage 4 -----------------------------------------------------------------------------------

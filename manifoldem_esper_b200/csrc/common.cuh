@@ -75,7 +75,8 @@ struct esper_ctx {
 
     // resident data
     esper::DevBuf imgs;     int img_n = 0, img_P = 0;          // raw float32 stack [n, P]
-    esper::DevBuf dist;     int dist_m = 0;                    // float64 [m, m]
+    esper::DevBuf dist;     int dist_m = 0;                    // float64 [m, m] (or the row block [dist_rows, m])
+    int dist_rows = 0, dist_row0 = -1;                         // row-block path: rows held, first global row
     int dist_symmetric = -1;                                   // 1 symmetric, 0 not, -1 unknown (checked lazily)
     // stage-1 workspaces
     esper::DevBuf plane_hi, plane_lo;                          // [rows_pad, ld] float32 (tf32 values)
@@ -149,8 +150,12 @@ inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 // ---- per-stage entry points implemented in the .cu files (host side) ----
 int prep_and_gram(esper_ctx* c, int n, int P, unsigned flags);                 // k0_prep.cu + k1_gram.cu
 int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld);
-int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags);
+int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, int row0 = -1, int nrows = 0);
 int run_sweep(esper_ctx* c, int m, const double* coef_h, int n_eps, double thr, double* logsum_h);
+int run_sweep_rows(esper_ctx* c, int rows, int m, const double* coef_h, int n_eps, double thr, double* out_h, int take_log);
+int run_markov_rows(esper_ctx* c, int rows, int m, int row0, double eps, const double* degree_all_h, double* degree_rows_h, int phase);
+bool ritz_converged(const std::vector<double>& a, const std::vector<double>& b, int n, int kw, int guard, double tol,
+                    std::vector<double>& theta, std::vector<double>& S);
 int check_symmetry(esper_ctx* c, int m);
 int run_markov(esper_ctx* c, int m, double eps);
 int run_lanczos(esper_ctx* c, int m, int k, double tol, int max_iter, double* val_h, double* vec_h, int* iters);
@@ -160,6 +165,10 @@ int run_rot_eval(esper_ctx* c, const double* Uinit, int n_pd, int m, int dim, co
 int run_rot_sweep(esper_ctx* c, const double* Uinit, int n_pd, int m, int dim, const int* combo,
                   const int* n_sub, int max_sub, const int* rij, int n_rij, const double* theta_grid,
                   int n_theta, int bins, double lo, double hi, double* thetas_out, int* counts_out);
+int run_symv_rows(esper_ctx* c, int rows, int m, const double* q_d, double* w_rows_d);
+int run_lanczos_start(esper_ctx* c, int m, const double* degree_all_h, double* V_d);
+int run_lanczos_ortho(esper_ctx* c, int m, int j, double* V_d, double* w_d, double* ab_d);
+int run_ritz_vectors(esper_ctx* c, int m, int steps, int k, const double* V_d, const double* S_h, double* vec_h);
 void nd_rotation_host(int n, const double* theta, double* R);
 void hist_edges_host(int bins, double lo, double hi, double* edges);
 

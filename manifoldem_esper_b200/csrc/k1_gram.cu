@@ -122,6 +122,15 @@ __device__ __forceinline__ void tile_coords(int t, int nt, int& ti, int& tj) {
     while (rem >= nt - i) { rem -= nt - i; ++i; }
     ti = i; tj = i + rem;
 }
+// Work tile t -> canonical upper-triangle tile (ta <= tb) whose Gram block is computed.
+//   rect_ti0 < 0 : the whole upper triangle (single-GPU path)
+//   rect_ti0 >= 0: row-block path, tiles (rect_ti0 + t / nt, t % nt) of a block of tile rows; a tile below the
+//                  diagonal is computed as its mirror image (same operands, same bits) and stored transposed.
+__device__ __forceinline__ void tile_map(int t, int nt, int rect_ti0, int& ta, int& tb, bool& transposed) {
+    if (rect_ti0 < 0) { tile_coords(t, nt, ta, tb); transposed = false; return; }
+    const int ti = rect_ti0 + t / nt, tj = t % nt;
+    if (tj >= ti) { ta = ti; tb = tj; transposed = false; } else { ta = tj; tb = ti; transposed = true; }
+}
 
 // ------------------------------------------------------------------------------------------------
 // The Gram kernel
@@ -130,7 +139,7 @@ __device__ __forceinline__ void tile_coords(int t, int nt, int& ti, int& tj) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gram_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
-            int nt, int n_tiles, int tile0, int nkb, int split_k, float* __restrict__ part) {
+            int nt, int n_tiles, int tile0, int rect_ti0, int nkb, int split_k, float* __restrict__ part) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // 1024-byte aligned operand ring
     const uint32_t bars = base + STAGES * STAGE_BYTES;
@@ -168,7 +177,7 @@ gram_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
             int stage = 0; uint32_t phase = 0;
             for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
                 const int chunk = u / n_tiles, t = tile0 + (u % n_tiles);
-                int ti, tj; tile_coords(t, nt, ti, tj);
+                int ti, tj; bool tr_; tile_map(t, nt, rect_ti0, ti, tj, tr_);
                 const bool diag = (ti == tj);
                 const int kb0 = (int)((long long)nkb * chunk / split_k);
                 const int kb1 = (int)((long long)nkb * (chunk + 1) / split_k);
@@ -194,7 +203,7 @@ gram_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
             int acc = 0; uint32_t acc_phase = 0;
             for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
                 const int chunk = u / n_tiles, t = tile0 + (u % n_tiles);
-                int ti, tj; tile_coords(t, nt, ti, tj);
+                int ti, tj; bool tr_; tile_map(t, nt, rect_ti0, ti, tj, tr_);
                 const bool diag = (ti == tj);
                 const int kb0 = (int)((long long)nkb * chunk / split_k);
                 const int kb1 = (int)((long long)nkb * (chunk + 1) / split_k);
@@ -267,12 +276,14 @@ gram_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
 // One block per tile; thread -> (row r, 4 columns).  FP64 combination in fixed chunk order.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-dist_finalize_kernel(const float* __restrict__ part, int nt, int n_tiles, int tile0, int split_k, int n, int P,
+dist_finalize_kernel(const float* __restrict__ part, int nt, int n_tiles, int tile0, int rect_ti0, int split_k, int n, int P,
                      const RowStat* __restrict__ st, double* __restrict__ D) {
     const int lt = blockIdx.x;
     const int e_per = (BM * (BN / 4)) / gridDim.y;          // slice of the tile handled by this block
-    int ti, tj; tile_coords(tile0 + lt, nt, ti, tj);
+    int ti, tj; bool transposed; tile_map(tile0 + lt, nt, rect_ti0, ti, tj, transposed);
     const bool diag = (ti == tj);
+    const bool rect = rect_ti0 >= 0;
+    const size_t row_off = rect ? (size_t)rect_ti0 * BM : 0;   // first global row held by D in the row-block path
     const double invP = 1.0 / (double)P;
     for (int e = blockIdx.y * e_per + threadIdx.x; e < (blockIdx.y + 1) * e_per; e += blockDim.x) {
         const int r = e & (BM - 1), c4 = e >> 7;
@@ -289,12 +300,18 @@ dist_finalize_kernel(const float* __restrict__ part, int nt, int n_tiles, int ti
             const int c = c4 * 4 + q;
             const int j = tj * BN + c;
             if (j >= n) continue;
-            if (diag && c <= r) { if (c == r) D[(size_t)i * n + i] = 0.0; continue; }
+            if (diag && c <= r) { if (c == r) D[((size_t)i - row_off) * n + i] = 0.0; continue; }
             double d2 = (ni + st[j].norm2 - 2.0 * g[q]) * invP;
             d2 = d2 > 0.0 ? d2 : 0.0;
             const double d = sqrt(d2);
-            D[(size_t)i * n + j] = d;
-            D[(size_t)j * n + i] = d;
+            if (!rect || diag) {                    // both (i, j) and (j, i) live in this D
+                D[((size_t)i - row_off) * n + j] = d;
+                D[((size_t)j - row_off) * n + i] = d;
+            } else if (!transposed) {
+                D[((size_t)i - row_off) * n + j] = d;
+            } else {
+                D[((size_t)j - row_off) * n + i] = d;
+            }
         }
     }
 }
@@ -304,12 +321,13 @@ dist_finalize_kernel(const float* __restrict__ part, int nt, int n_tiles, int ti
 // float64 sum of squared differences of the float32 standardised images).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-flag_pairs_kernel(const double* __restrict__ D, int n, int P, const RowStat* __restrict__ st, double tau,
+flag_pairs_kernel(const double* __restrict__ D, int n, int row0, int nrows, int rect, int P,
+                  const RowStat* __restrict__ st, double tau,
                   int2* __restrict__ pairs, unsigned int* __restrict__ count, unsigned int cap) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)n * n) return;
-    const int i = (int)(idx / n), j = (int)(idx % n);
-    if (j <= i) return;
+    if (idx >= (long long)nrows * n) return;
+    const int i = row0 + (int)(idx / n), j = (int)(idx % n);
+    if (rect ? (j == i) : (j <= i)) return;
     const double d = D[idx];
     if (d * d * (double)P < tau * (st[i].norm2 + st[j].norm2)) {
         const unsigned int k = atomicAdd(count, 1u);
@@ -318,7 +336,7 @@ flag_pairs_kernel(const double* __restrict__ D, int n, int P, const RowStat* __r
 }
 
 __global__ void __launch_bounds__(256)
-refine_pairs_kernel(const float* __restrict__ raw, int n, int P, const RowStat* __restrict__ st,
+refine_pairs_kernel(const float* __restrict__ raw, int n, int row0, int rect, int P, const RowStat* __restrict__ st,
                     const int2* __restrict__ pairs, const unsigned int* __restrict__ count, unsigned int cap,
                     double* __restrict__ D) {
     __shared__ double sh[32];
@@ -337,8 +355,8 @@ refine_pairs_kernel(const float* __restrict__ raw, int n, int P, const RowStat* 
         acc = block_sum(acc, sh);
         if (threadIdx.x == 0) {
             const double d = sqrt(acc / (double)P);
-            D[(size_t)pr.x * n + pr.y] = d;
-            D[(size_t)pr.y * n + pr.x] = d;
+            D[((size_t)pr.x - row0) * n + pr.y] = d;
+            if (!rect) D[(size_t)pr.y * n + pr.x] = d;
         }
     }
 }
@@ -396,10 +414,14 @@ static int choose_split_k(int requested, int nkb, int n_tiles, int sms) {
     return best < 1 ? 1 : best;
 }
 
-int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags) {
+int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, int row0, int nrows) {
     using namespace gram;
+    // row0 < 0: full symmetric matrix (upper triangle of tiles); else the row block [row0, row0+nrows) x [0, n)
     const int nt = rows_pad / BM;
-    const int tiles_total = nt * (nt + 1) / 2;
+    const bool rect = row0 >= 0;
+    const int rect_ti0 = rect ? row0 / BM : -1;
+    const int tiles_total = rect ? ceil_div(nrows, BM) * nt : nt * (nt + 1) / 2;
+    if (!rect) { row0 = 0; nrows = n; }
     const int nkb = ld / BK;
     const int sms = c->sm_count;
     const RowStat* st = c->row_stats.as<RowStat>();
@@ -436,29 +458,30 @@ int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags) {
         const int grid = units < sms ? units : sms;
         {
             LaunchScope ls(c, "gram");
-            gram_kernel<<<grid, NUM_THREADS, SMEM_BYTES, c->stream>>>(map_hi, map_lo, nt, nb, tile0, nkb, sk, part);
+            gram_kernel<<<grid, NUM_THREADS, SMEM_BYTES, c->stream>>>(map_hi, map_lo, nt, nb, tile0, rect_ti0, nkb, sk, part);
         }
         {
             LaunchScope ls(c, "dist_finalize");
-            dist_finalize_kernel<<<dim3(nb, 8), 256, 0, c->stream>>>(part, nt, nb, tile0, sk, n, P, st, D);
+            dist_finalize_kernel<<<dim3(nb, 8), 256, 0, c->stream>>>(part, nt, nb, tile0, rect_ti0, sk, n, P, st, D);
         }
     }
     ESPER_CUDA(c, cudaGetLastError());
 
     if ((flags & ESPER_DIST_REFINE) && c->refine_tau > 0.0 && n > 1) {
-        const unsigned int cap = (unsigned int)(((size_t)n * (n - 1) / 2 < (size_t)1 << 26) ? (size_t)n * (n - 1) / 2 : (size_t)1 << 26);
+        const size_t max_pairs = rect ? (size_t)nrows * n : (size_t)n * (n - 1) / 2;
+        const unsigned int cap = (unsigned int)(max_pairs < ((size_t)1 << 26) ? max_pairs : (size_t)1 << 26);
         ESPER_RESERVE(c, c->pair_list, sizeof(int2) * (size_t)cap + 256);
         unsigned int* count = c->pair_list.as<unsigned int>();
         int2* pairs = reinterpret_cast<int2*>(c->pair_list.as<char>() + 256);
         ESPER_CUDA(c, cudaMemsetAsync(count, 0, sizeof(unsigned int), c->stream));
         {
             LaunchScope ls(c, "refine");
-            const long long tot = (long long)n * n;
-            flag_pairs_kernel<<<ceil_div(tot, 256), 256, 0, c->stream>>>(D, n, P, st, c->refine_tau, pairs, count, cap);
+            const long long tot = (long long)nrows * n;
+            flag_pairs_kernel<<<ceil_div(tot, 256), 256, 0, c->stream>>>(D, n, row0, nrows, rect ? 1 : 0, P, st, c->refine_tau, pairs, count, cap);
         }
         {
             LaunchScope ls(c, "refine");
-            refine_pairs_kernel<<<sms * 8, 256, 0, c->stream>>>(c->imgs.as<float>(), n, P, st, pairs, count, cap, D);
+            refine_pairs_kernel<<<sms * 8, 256, 0, c->stream>>>(c->imgs.as<float>(), n, row0, rect ? 1 : 0, P, st, pairs, count, cap, D);
         }
         ESPER_CUDA(c, cudaGetLastError());
     }

@@ -61,7 +61,7 @@ constexpr int TC = 128;                      // tile columns (a warp reads 32 co
 
 // sym != 0: D is exactly symmetric; only elements j >= i are visited, off-diagonal ones weigh 2.
 __global__ void __launch_bounds__(THREADS)
-sweep_kernel(const double* __restrict__ D, int m, int sym, int mono, const double* __restrict__ coef, int n_eps,
+sweep_kernel(const double* __restrict__ D, int rows, int m, int sym, int mono, const double* __restrict__ coef, int n_eps,
              double thr, const int* __restrict__ row_start /*[tiles_r+1] prefix of valid tiles*/,
              unsigned int* __restrict__ next_tile, double* __restrict__ part /*[gridDim.x][n_eps]*/) {
     extern __shared__ double sm[];
@@ -81,7 +81,7 @@ sweep_kernel(const double* __restrict__ D, int m, int sym, int mono, const doubl
     for (int k = threadIdx.x; k < n_eps; k += THREADS) { acc[k] = 0.0; cf[k] = coef[k]; below[k] = 0.0; above[k] = 0.0; }
     __syncthreads();
 
-    const int tiles_c = (m + TC - 1) / TC, tiles_r = (m + TR - 1) / TR;
+    const int tiles_c = (m + TC - 1) / TC, tiles_r = (rows + TR - 1) / TR;
     const int n_valid = row_start[tiles_r];
     __shared__ int s_tile;
     for (;;) {
@@ -104,7 +104,7 @@ sweep_kernel(const double* __restrict__ D, int m, int sym, int mono, const doubl
             const int i = row0 + (threadIdx.x >> 7) * EPT + e;
             d2[e] = 0.0;                     // excluded (below the diagonal, out of range, NaN): weight 0
             wt[e] = 0.0;
-            if (i < m && j < m && (!sym || j >= i)) {
+            if (i < rows && j < m && (!sym || j >= i)) {
                 const double d = __ldg(D + (size_t)i * m + j);
                 const double q = d * d;
                 if (q == q) {
@@ -236,13 +236,13 @@ __global__ void __launch_bounds__(256) symmetry_kernel(const double* __restrict_
 }
 
 __global__ void __launch_bounds__(256)
-sweep_final_kernel(const double* __restrict__ part, int n_blocks, int n_eps, double* __restrict__ logsum) {
+sweep_final_kernel(const double* __restrict__ part, int n_blocks, int n_eps, int take_log, double* __restrict__ out) {
     __shared__ double sh[32];
     const int k = blockIdx.x;
     double s = 0.0;
     for (int b = threadIdx.x; b < n_blocks; b += blockDim.x) s += part[(size_t)b * n_eps + k];
     s = block_sum(s, sh);
-    if (threadIdx.x == 0) logsum[k] = log(s);
+    if (threadIdx.x == 0) out[k] = take_log ? log(s) : s;
 }
 
 }  // namespace sweep
@@ -264,10 +264,18 @@ int check_symmetry(esper_ctx* c, int m) {
 }
 
 int run_sweep(esper_ctx* c, int m, const double* coef_h, int n_eps, double thr, double* logsum_h) {
+    return run_sweep_rows(c, m, m, coef_h, n_eps, thr, logsum_h, 1);
+}
+
+// rows x m block of D resident in c->dist; take_log = 0 returns the partial sums (row-block path).
+int run_sweep_rows(esper_ctx* c, int rows, int m, const double* coef_h, int n_eps, double thr, double* logsum_h, int take_log) {
     using namespace sweep;
-    if (c->dist_symmetric < 0) { int rc = check_symmetry(c, m); if (rc) return rc; }
-    const int sym = c->dist_symmetric > 0 ? 1 : 0;
-    const int tiles_r = ceil_div(m, TR), tiles_c = ceil_div(m, TC);
+    int sym = 0;
+    if (rows == m && c->dist_row0 < 0) {
+        if (c->dist_symmetric < 0) { int rc = check_symmetry(c, m); if (rc) return rc; }
+        sym = c->dist_symmetric > 0 ? 1 : 0;
+    }
+    const int tiles_r = ceil_div(rows, TR), tiles_c = ceil_div(m, TC);
     std::vector<int> row_start(tiles_r + 2, 0);                   // prefix count of valid tiles per tile row
     for (int tr = 0; tr < tiles_r; ++tr) {
         const int first = sym ? (tr * TR) / TC : 0;               // first tile column touching j >= i
@@ -297,12 +305,12 @@ int run_sweep(esper_ctx* c, int m, const double* coef_h, int n_eps, double thr, 
     }
     {
         LaunchScope ls(c, "sweep");
-        sweep_kernel<<<grid, THREADS, smem, c->stream>>>(c->dist.as<double>(), m, sym, mono, coef_d, n_eps, thr,
+        sweep_kernel<<<grid, THREADS, smem, c->stream>>>(c->dist.as<double>(), rows, m, sym, mono, coef_d, n_eps, thr,
                                                          row_start_d, next_tile_d, c->sweep_part.as<double>());
     }
     {
         LaunchScope ls(c, "sweep");
-        sweep_final_kernel<<<n_eps, 256, 0, c->stream>>>(c->sweep_part.as<double>(), grid, n_eps, logsum_d);
+        sweep_final_kernel<<<n_eps, 256, 0, c->stream>>>(c->sweep_part.as<double>(), grid, n_eps, take_log, logsum_d);
     }
     ESPER_CUDA(c, cudaGetLastError());
     ESPER_CUDA(c, cudaMemcpyAsync(logsum_h, logsum_d, sizeof(double) * n_eps, cudaMemcpyDeviceToHost, c->stream));

@@ -27,12 +27,13 @@ __global__ void __launch_bounds__(256) degree_kernel(const double* __restrict__ 
     if (threadIdx.x == 0) deg[i] = s;
 }
 
-__global__ void __launch_bounds__(256) normalise_kernel(const double* __restrict__ D, int m, double two_eps,
+// Rows [row0, row0 + gridDim.y) of Ms; D and Ms hold those rows only (row0 = 0 for the full matrix).
+__global__ void __launch_bounds__(256) normalise_kernel(const double* __restrict__ D, int m, int row0, double two_eps,
                                                         const double* __restrict__ deg, double* __restrict__ Ms) {
     const int i = blockIdx.y;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
-    const double di = deg[i], dj = __ldg(deg + j);
+    const double di = deg[row0 + i], dj = __ldg(deg + j);
     const double a = kernel_value(__ldg(D + (size_t)i * m + j), two_eps);
     const double mij = __dmul_rn(a, __ddiv_rn(1.0, dj));                       // M = A @ inv(D)
     const double left = __dmul_rn(sqrt(__ddiv_rn(1.0, di)), mij);              // sqrtm(inv(D)) @ M
@@ -53,10 +54,40 @@ int run_markov(esper_ctx* c, int m, double eps) {
     {
         LaunchScope ls(c, "markov");
         dim3 grid(ceil_div(m, 256), m);
-        normalise_kernel<<<grid, 256, 0, c->stream>>>(c->dist.as<double>(), m, two_eps, c->degree.as<double>(),
+        normalise_kernel<<<grid, 256, 0, c->stream>>>(c->dist.as<double>(), m, 0, two_eps, c->degree.as<double>(),
                                                       c->markov.as<double>());
     }
     ESPER_CUDA(c, cudaGetLastError());
+    return ESPER_OK;
+}
+
+// Row-block path.  phase 0: degrees of the owned rows -> degree_rows_h.  phase 1: Ms block from the degrees of
+// ALL rows (gathered by the caller) -> resident c->markov [rows, m]; c->degree holds all m degrees.
+int run_markov_rows(esper_ctx* c, int rows, int m, int row0, double eps, const double* degree_all_h, double* degree_rows_h, int phase) {
+    using namespace markov;
+    const double two_eps = 2.0 * eps;
+    ESPER_RESERVE(c, c->degree, sizeof(double) * (size_t)(m + rows));
+    double* deg_all = c->degree.as<double>();
+    double* deg_rows = deg_all + m;
+    if (phase == 0) {
+        {
+            LaunchScope ls(c, "markov");
+            degree_kernel<<<rows, 256, 0, c->stream>>>(c->dist.as<double>(), m, two_eps, deg_rows);
+        }
+        ESPER_CUDA(c, cudaGetLastError());
+        ESPER_CUDA(c, cudaMemcpyAsync(degree_rows_h, deg_rows, sizeof(double) * (size_t)rows, cudaMemcpyDeviceToHost, c->stream));
+        ESPER_CUDA(c, cudaStreamSynchronize(c->stream));
+        return ESPER_OK;
+    }
+    ESPER_RESERVE(c, c->markov, sizeof(double) * (size_t)rows * m);
+    ESPER_CUDA(c, cudaMemcpyAsync(deg_all, degree_all_h, sizeof(double) * (size_t)m, cudaMemcpyHostToDevice, c->stream));
+    {
+        LaunchScope ls(c, "markov");
+        dim3 grid(ceil_div(m, 256), rows);
+        normalise_kernel<<<grid, 256, 0, c->stream>>>(c->dist.as<double>(), m, row0, two_eps, deg_all, c->markov.as<double>());
+    }
+    ESPER_CUDA(c, cudaGetLastError());
+    ESPER_CUDA(c, cudaStreamSynchronize(c->stream));
     return ESPER_OK;
 }
 

@@ -457,9 +457,12 @@ static void tridiag_eigenvectors(const std::vector<double>& a, const std::vector
     }
 }
 
-// Residual estimates |beta_j s_{j,i}| of the Ritz pairs i in [i0, i1) of T = tridiag(b, a, b); early exit.
-static bool ritz_converged(const std::vector<double>& a, const std::vector<double>& b, int n, int kw, int guard,
-                           double tol, std::vector<double>& theta, std::vector<double>& S) {
+}  // namespace lanczos
+
+// Residual estimates |beta_j s_{j,i}| of the leading Ritz pairs of T = tridiag(b, a, b); early exit.
+bool ritz_converged(const std::vector<double>& a, const std::vector<double>& b, int n, int kw, int guard,
+                    double tol, std::vector<double>& theta, std::vector<double>& S) {
+    using namespace lanczos;
     const int want = std::min(kw + guard, n);
     tridiag_top_eigenvalues(a, b, n, want, theta);
     tridiag_eigenvectors(a, b, n, theta, S);
@@ -472,8 +475,6 @@ static bool ritz_converged(const std::vector<double>& a, const std::vector<doubl
     }
     return true;
 }
-
-}  // namespace lanczos
 
 int run_lanczos(esper_ctx* c, int m, int k, double tol, int max_iter, double* val_h, double* vec_h, int* iters_out) {
     using namespace lanczos;
@@ -603,6 +604,99 @@ int run_lanczos(esper_ctx* c, int m, int k, double tol, int max_iter, double* va
         val_h[0] = 1.0;
         for (int i = 0; i < kw; ++i) val_h[1 + i] = theta[i] * theta[i];
     }
+    return ESPER_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row-block (oversized PD) building blocks: the host layer owns the vectors (device pointers, e.g. torch
+// tensors that NCCL all-gathers) and drives the iteration; every rank orthogonalises the same replicated
+// vector with the same deterministic kernels, so the only collective per step is the all-gather of w.
+// ------------------------------------------------------------------------------------------------
+namespace lanczos {
+
+// w[row] = Ms_rows[row, :] . q   (Ms block streamed from HBM; one warp per row, 8 x 16 B in flight per lane)
+__global__ void __launch_bounds__(256) symv_rows_kernel(const double* __restrict__ Ms, int rows, int m,
+                                                        const double* __restrict__ q, double* __restrict__ w) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const double* a = Ms + (size_t)row * m;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int cidx = lane;
+    for (; cidx + 224 < m; cidx += 256) {
+        const double x0 = __ldcs(a + cidx), x1 = __ldcs(a + cidx + 32), x2 = __ldcs(a + cidx + 64), x3 = __ldcs(a + cidx + 96),
+                     x4 = __ldcs(a + cidx + 128), x5 = __ldcs(a + cidx + 160), x6 = __ldcs(a + cidx + 192), x7 = __ldcs(a + cidx + 224);
+        a0 = fma(x0, __ldg(q + cidx), a0);       a1 = fma(x1, __ldg(q + cidx + 32), a1);
+        a2 = fma(x2, __ldg(q + cidx + 64), a2);  a3 = fma(x3, __ldg(q + cidx + 96), a3);
+        a0 = fma(x4, __ldg(q + cidx + 128), a0); a1 = fma(x5, __ldg(q + cidx + 160), a1);
+        a2 = fma(x6, __ldg(q + cidx + 192), a2); a3 = fma(x7, __ldg(q + cidx + 224), a3);
+    }
+    for (; cidx < m; cidx += 32) a0 = fma(__ldcs(a + cidx), __ldg(q + cidx), a0);
+    const double tot = warp_sum((a0 + a1) + (a2 + a3));
+    if (lane == 0) w[row] = tot;
+}
+
+}  // namespace lanczos
+
+int run_symv_rows(esper_ctx* c, int rows, int m, const double* q_d, double* w_rows_d) {
+    using namespace lanczos;
+    { LaunchScope ls(c, "lanczos"); symv_rows_kernel<<<ceil_div(rows, 8), 256, 0, c->stream>>>(c->markov.as<double>(), rows, m, q_d, w_rows_d); }
+    ESPER_CUDA(c, cudaGetLastError());
+    return ESPER_OK;
+}
+
+// V_d[0] = v0 = sqrt(d)/|sqrt(d)|, V_d[1] = deterministic start vector orthogonal to v0 (unit norm).
+int run_lanczos_start(esper_ctx* c, int m, const double* degree_all_h, double* V_d) {
+    using namespace lanczos;
+    cudaStream_t st = c->stream;
+    ESPER_RESERVE(c, c->degree, sizeof(double) * (size_t)m);
+    ESPER_RESERVE(c, c->lan_w, sizeof(double) * (size_t)m * 2);
+    ESPER_RESERVE(c, c->lan_h, sizeof(double) * 4096);
+    ESPER_CUDA(c, cudaMemcpyAsync(c->degree.p, degree_all_h, sizeof(double) * (size_t)m, cudaMemcpyHostToDevice, st));
+    double* w = c->lan_w.as<double>(); double* w2 = w + m; double* h = c->lan_h.as<double>();
+    { LaunchScope ls(c, "lanczos"); init_kernel<<<ceil_div(m, 256), 256, 0, st>>>(c->degree.as<double>(), m, w, w2); }
+    { LaunchScope ls(c, "lanczos"); normalize_kernel<<<1, 1024, 0, st>>>(w, m, V_d, nullptr); }
+    for (int pass = 0; pass < 2; ++pass) {
+        { LaunchScope ls(c, "lanczos"); dots_kernel<<<1, 256, 0, st>>>(V_d, m, w2, h); }
+        { LaunchScope ls(c, "lanczos"); update_kernel<<<ceil_div(m, 256), 256, 0, st>>>(V_d, m, 1, h, w2, nullptr); }
+    }
+    { LaunchScope ls(c, "lanczos"); normalize_kernel<<<1, 1024, 0, st>>>(w2, m, V_d + m, nullptr); }
+    ESPER_CUDA(c, cudaGetLastError());
+    return ESPER_OK;
+}
+
+// One Lanczos orthogonalisation step on the replicated vectors: w = Ms q_j (gathered, length m) is
+// orthogonalised against V[0..j] by classical Gram-Schmidt applied twice, ab_d[0] = alpha_j, ab_d[1] = beta_j,
+// V[j+1] = w / beta_j.
+int run_lanczos_ortho(esper_ctx* c, int m, int j, double* V_d, double* w_d, double* ab_d) {
+    using namespace lanczos;
+    cudaStream_t st = c->stream;
+    ESPER_RESERVE(c, c->lan_h, sizeof(double) * (size_t)(j + 8 > 4096 ? j + 8 : 4096));
+    double* h = c->lan_h.as<double>();
+    ESPER_CUDA(c, cudaMemsetAsync(ab_d, 0, 2 * sizeof(double), st));
+    for (int pass = 0; pass < 2; ++pass) {
+        { LaunchScope ls(c, "lanczos"); dots_kernel<<<j + 1, 256, 0, st>>>(V_d, m, w_d, h); }
+        { LaunchScope ls(c, "lanczos"); update_kernel<<<ceil_div(m, 256), 256, 0, st>>>(V_d, m, j + 1, h, w_d, ab_d); }
+    }
+    { LaunchScope ls(c, "lanczos"); normalize_kernel<<<1, 1024, 0, st>>>(w_d, m, V_d + (size_t)(j + 1) * m, ab_d + 1); }
+    ESPER_CUDA(c, cudaGetLastError());
+    return ESPER_OK;
+}
+
+// U = [v0, V_1..V_steps S] -> vec_h [m, k] (unit columns, sign fixed).  S_h: [steps, k-1] row-major.
+int run_ritz_vectors(esper_ctx* c, int m, int steps, int k, const double* V_d, const double* S_h, double* vec_h) {
+    using namespace lanczos;
+    cudaStream_t st = c->stream;
+    const int kw = k - 1;
+    ESPER_RESERVE(c, c->lan_small, sizeof(double) * ((size_t)m * k + (size_t)steps * (kw > 0 ? kw : 1) + 8));
+    double* U = c->lan_small.as<double>();
+    double* S_d = U + (size_t)m * k;
+    if (kw > 0) ESPER_CUDA(c, cudaMemcpyAsync(S_d, S_h, sizeof(double) * (size_t)steps * kw, cudaMemcpyHostToDevice, st));
+    { LaunchScope ls(c, "lanczos"); ritz_kernel<<<dim3(ceil_div(m, 128), k), 128, 0, st>>>(V_d, m, kw > 0 ? steps : 0, S_d, kw, U, k); }
+    { LaunchScope ls(c, "lanczos"); fix_columns_kernel<<<k, 256, 0, st>>>(U, m, k); }
+    ESPER_CUDA(c, cudaGetLastError());
+    ESPER_CUDA(c, cudaMemcpyAsync(vec_h, U, sizeof(double) * (size_t)m * k, cudaMemcpyDeviceToHost, st));
+    ESPER_CUDA(c, cudaStreamSynchronize(st));
     return ESPER_OK;
 }
 

@@ -1,0 +1,168 @@
+"""One oversized PD split by distance-matrix row blocks over the GPUs of a node (BASELINE config 4).
+
+The reference cannot run this case (a 50 000 x 50 000 float64 distance matrix and an O(m^3) SVD,
+DiffusionMaps.py:166); the arithmetic per element is the same as in the single-GPU path.  Rank g owns the rows
+[row0, row0 + nrows) of D, A and Ms (128-row aligned).  Data-path collectives (the only ones):
+
+    all-reduce(sum)  of the 1001 partial epsilon-sweep sums           once (twice with the threshold pass)
+    all-gather       of the degrees (n float64)                        once
+    all-gather       of the Lanczos vector w = Ms q (n float64)        once per Lanczos step
+
+After the all-gather every rank orthogonalises the same replicated vector with the same deterministic
+kernels, so no further reduction is needed.  `embed_oversized` is written against a small backend interface
+so that the orchestration is exercised on CPU (gloo, numpy backend in tests/) and on GPUs (NCCL, CudaBackend).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import GaussianBandwidth
+
+TILE = 128
+
+
+def row_partition(n: int, rank: int, world: int):
+    """(row0, nrows, rows_per_rank): contiguous blocks of whole 128-row tiles, equal padded size."""
+    tiles = (n + TILE - 1) // TILE
+    tpr = (tiles + world - 1) // world
+    row0 = rank * tpr * TILE
+    nrows = min(n, (rank + 1) * tpr * TILE) - row0
+    if nrows < 1:
+        raise ValueError('row_partition: %d images over %d ranks leaves rank %d without rows' % (n, world, rank))
+    return row0, nrows, tpr * TILE
+
+
+class TorchComm:
+    """torch.distributed collectives used by the row-block path (backend nccl on GPUs, gloo on CPU)."""
+
+    def __init__(self, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = device if device is not None else torch.device('cpu')
+
+    def allreduce_sum(self, arr):
+        t = self.torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)).to(self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    def allgather_concat(self, arr, chunk):
+        """Gather equal-size (zero padded to `chunk`) float64 blocks from all ranks into one array."""
+        buf = np.zeros(chunk, dtype=np.float64)
+        buf[:len(arr)] = arr
+        t = self.torch.from_numpy(buf).to(self.device)
+        out = self.torch.empty(chunk * self.world, dtype=self.torch.float64, device=self.device)
+        self.dist.all_gather_into_tensor(out, t)
+        return out.cpu().numpy()
+
+    def allgather_vec(self, out_tensor, in_tensor):
+        self.dist.all_gather_into_tensor(out_tensor, in_tensor)
+
+
+class CudaBackend:
+    """Row-block kernels of libesper_b200 on one GPU; vectors are torch CUDA tensors (NCCL-ready)."""
+
+    def __init__(self, ctx, stack, n, P, device):
+        import torch
+        self.torch, self.ctx, self.device = torch, ctx, device
+        self.stack, self.n, self.P = stack, n, P
+
+    def dist_rows(self, row0, nrows):
+        self.row0, self.nrows = row0, nrows
+        self.ctx.dist_rms_rows(self.stack, self.n, self.P, row0, nrows)
+
+    def sweep_rows(self, coef, thr):
+        return self.ctx.eps_sweep_rows(self.nrows, self.n, coef, thr)
+
+    def degree_rows(self, eps):
+        return self.ctx.degree_rows(self.nrows, self.n, eps)
+
+    def markov_rows(self, eps, degree_all):
+        self.ctx.markov_rows(self.nrows, self.n, eps, degree_all)
+
+    def lanczos_alloc(self, max_steps, rows_per, world):
+        t = self.torch
+        self.V = t.zeros((max_steps + 2, self.n), dtype=t.float64, device=self.device)
+        self.w_local = t.zeros(rows_per, dtype=t.float64, device=self.device)
+        self.w_full = t.zeros(rows_per * world, dtype=t.float64, device=self.device)
+        self.ab = t.zeros((max_steps + 2, 2), dtype=t.float64, device=self.device)
+
+    def lanczos_start(self, degree_all):
+        self.ctx.lanczos_start_d(self.n, degree_all, self.V.data_ptr())
+
+    def symv(self, j):
+        self.ctx.symv_rows_d(self.nrows, self.n, self.V[j].data_ptr(), self.w_local.data_ptr())
+
+    def ortho(self, j):
+        self.ctx.lanczos_ortho_d(self.n, j, self.V.data_ptr(), self.w_full.data_ptr(), self.ab[j - 1].data_ptr())
+
+    def read_ab(self, steps):
+        self.ctx.sync()
+        ab = self.ab[:steps].cpu().numpy()
+        return ab[:, 0].copy(), ab[:, 1].copy()
+
+    def ritz_vectors(self, steps, k, S):
+        return self.ctx.ritz_vectors_d(self.n, steps, k, self.V.data_ptr(), S)
+
+    def tridiag_ritz(self, alpha, beta, k, tol):
+        from . import _capi
+        return _capi.tridiag_ritz(alpha, beta, k, tol)
+
+
+def embed_oversized(backend, comm, n, k=16, eps=None, a0=None, tol=0.0, max_steps=1024, check_every=16,
+                    log_eps=None, verbose=False):
+    """Distances -> epsilon -> Markov rows -> leading k eigenpairs of one PD split over comm.world ranks.
+
+    Returns dict(eps, val [k] = lambda^2, vec [n, k], steps, logSumWij, popt) (identical on every rank).
+    `a0` (tanh-fit start, 4 values) must be the same on all ranks; default is a fixed start.
+    """
+    rank, world = comm.rank, comm.world
+    row0, nrows, rows_per = row_partition(n, rank, world)
+    backend.dist_rows(row0, nrows)
+    out = {}
+    if eps is None:
+        log_eps = np.arange(-100, 100.2, 0.2) if log_eps is None else np.asarray(log_eps, dtype=np.float64)
+        e = np.exp(log_eps)
+        # find_threshold (GaussianBandwidth.py:26-32) needs the global sum at the largest epsilon
+        ss = comm.allreduce_sum(backend.sweep_rows(np.array([1. / (2. * np.max(e))]), np.inf))[0]
+        thr = max(-np.log(0.01 * ss / n), 10)
+        sums = comm.allreduce_sum(backend.sweep_rows(1. / (2. * e), thr))
+        logSumWij = np.log(sums)
+        if a0 is None:
+            a0 = np.array([[-0.2], [0.3], [-0.4], [0.1]])
+        state = np.random.get_state()
+        np.random.seed(12345)                     # the retry loop redraws a0 from the global RNG: same on all ranks
+        popt, resnorm, R2 = GaussianBandwidth.fit(log_eps, logSumWij, a0)
+        np.random.set_state(state)
+        eps = float(np.exp(-(popt[1] / popt[0])))
+        out.update(logSumWij=logSumWij, popt=popt, R2=R2)
+    deg_all = comm.allgather_concat(backend.degree_rows(eps), rows_per)[:n]
+    backend.markov_rows(eps, deg_all)
+
+    max_steps = int(min(max_steps, n - 1))
+    kw = k - 1
+    backend.lanczos_alloc(max_steps, rows_per, world)
+    backend.lanczos_start(deg_all)
+    steps, converged, theta, S = 0, kw == 0, np.zeros(0), np.zeros((0, 0))
+    next_check = min(max_steps, max(3 * (kw + 2) + 8, 32))
+    while not converged and steps < max_steps:
+        j = steps + 1
+        backend.symv(j)                                           # w_local = Ms[rows, :] q_j
+        comm.allgather_vec(backend.w_full, backend.w_local)       # the per-step collective
+        backend.ortho(j)                                          # replicated, deterministic
+        steps += 1
+        if steps >= next_check or steps == max_steps:
+            alpha, beta = backend.read_ab(steps)
+            converged, theta, S = backend.tridiag_ritz(alpha, beta, k, tol)
+            breakdown = not (beta[-1] > 1e-14 * max(abs(alpha[0]), 1e-300))
+            converged = converged or breakdown or steps >= n - 1
+            next_check = steps + check_every
+            if verbose and rank == 0:
+                print('lanczos step %d converged=%s' % (steps, converged))
+    if not converged:
+        raise RuntimeError('row-block Lanczos did not converge in %d steps' % steps)
+    vec = backend.ritz_vectors(steps, k, S) if kw > 0 else backend.ritz_vectors(0, 1, np.zeros((0, 0)))
+    val = np.concatenate(([1.0], theta[:kw] ** 2))
+    out.update(eps=eps, val=val, vec=vec, steps=steps, row0=row0, nrows=nrows)
+    return out

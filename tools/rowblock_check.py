@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""GPU check of the row-block (oversized PD) path under torchrun:
+   torchrun --nproc-per-node G tools/rowblock_check.py [small|c4]
+small: N=2000 x 250^2 vs the single-GPU path (bit-equal distance rows, eigenpairs <= 1e-9).
+c4   : N=50000 x 128^2 (BASELINE config 4): timings, residuals |Ms v - lambda v|, orthonormality."""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from manifoldem_esper_b200 import _capi, rowblock, synth  # noqa: E402
+
+mode = sys.argv[1] if len(sys.argv) > 1 else 'small'
+rank, local = int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0))
+torch.cuda.set_device(local)
+dev = torch.device('cuda', local)
+dist.init_process_group('nccl', device_id=dev)
+world = dist.get_world_size()
+stream = torch.cuda.Stream()
+ctx = _capi.Context(local, stream=stream.cuda_stream)
+ctx.dist_config(split_k=37 if mode == 'small' else 8)
+
+if mode == 'small':
+    stack = synth.synthetic_pd(pd=1, box=250, n_side=20, tau=5, snr=0.1)
+    n, P, k = 2000, 62500, 10
+else:
+    t = time.time()
+    stack = synth.synthetic_pd(pd=1, box=128, n_side=20, tau=125, snr=0.1)
+    n, P, k = 50000, 128 * 128, 10
+    if rank == 0:
+        print('generated %s in %.1fs' % (stack.shape, time.time() - t), flush=True)
+stack = stack.reshape(n, P)
+comm = rowblock.TorchComm(dev)
+with torch.cuda.stream(stream):
+    be = rowblock.CudaBackend(ctx, None, n, P, dev)
+    t = time.time(); ctx.upload_images(stack); ctx.sync(); t_up = time.time() - t
+    dist.barrier(); torch.cuda.synchronize()
+    t = time.time()
+    res = rowblock.embed_oversized(be, comm, n, k=k, verbose=(mode != 'small'))
+    torch.cuda.synchronize(); dist.barrier()
+    t_all = time.time() - t
+    if rank == 0:
+        print('mode=%s world=%d n=%d upload %.2fs embed %.3fs steps=%d eps=%.6f lam=%s' % (
+            mode, world, n, t_up, t_all, res['steps'], res['eps'], np.array2string(np.sqrt(res['val']), precision=6)), flush=True)
+    # residuals of the eigenpairs against the resident Ms row block
+    vec = torch.from_numpy(res['vec']).to(dev)
+    w_loc = torch.zeros(be.w_local.shape[0], dtype=torch.float64, device=dev)
+    resid = []
+    lam = np.sqrt(res['val'])
+    for i in range(k):
+        q = vec[:, i].contiguous()
+        ctx.symv_rows_d(be.nrows, n, q.data_ptr(), w_loc.data_ptr()); ctx.sync()
+        r = w_loc[:be.nrows] - lam[i] * q[be.row0:be.row0 + be.nrows]
+        s = (r * r).sum()
+        dist.all_reduce(s)
+        resid.append(float(s.sqrt()))
+    orth = float((vec.T @ vec - torch.eye(k, dtype=torch.float64, device=dev)).abs().max())
+    if rank == 0:
+        print('residuals |Ms v - lam v| = %s  max orth err = %.2e' % (np.array2string(np.array(resid), precision=2), orth), flush=True)
+    if mode == 'small':
+        # single-GPU reference on the same ctx type: bit-equal rows, same eigenpairs
+        ctx1 = _capi.Context(local)
+        ctx1.dist_config(split_k=37)
+        D = ctx1.dist_rms(stack)
+        Drows = ctx.dist_rms_rows(None, n, P, be.row0, be.nrows, download=True)
+        same = np.array_equal(Drows, D[be.row0:be.row0 + be.nrows])
+        val1, vec1, it1 = ctx1.dmap_embed(D, res['eps'], k=k)
+        ev = float(np.max(np.abs(res['val'] - val1) / val1))
+        vv = [float(min(np.abs(res['vec'][:, i] - vec1[:, i]).max(), np.abs(res['vec'][:, i] + vec1[:, i]).max())) for i in range(k)]
+        print('rank %d rows [%d,%d) bit-equal to single-GPU D: %s; val rel diff %.2e; vec diff %s (single-GPU steps %d)' % (
+            rank, be.row0, be.row0 + be.nrows, same, ev, np.array2string(np.array(vv), precision=1), it1), flush=True)
+dist.barrier()
+dist.destroy_process_group()
