@@ -109,6 +109,10 @@ class CudaBackend:
         from . import _capi
         return _capi.tridiag_ritz(alpha, beta, k, tol)
 
+    def sync(self):
+        self.ctx.sync()
+        self.torch.cuda.synchronize()
+
 
 def embed_oversized(backend, comm, n, k=16, eps=None, a0=None, tol=0.0, max_steps=1024, check_every=16,
                     log_eps=None, verbose=False):
@@ -117,9 +121,14 @@ def embed_oversized(backend, comm, n, k=16, eps=None, a0=None, tol=0.0, max_step
     Returns dict(eps, val [k] = lambda^2, vec [n, k], steps, logSumWij, popt) (identical on every rank).
     `a0` (tanh-fit start, 4 values) must be the same on all ranks; default is a fixed start.
     """
+    import time
     rank, world = comm.rank, comm.world
     row0, nrows, rows_per = row_partition(n, rank, world)
+    sync = getattr(backend, 'sync', lambda: None)
+    timings = {}
+    t0 = time.perf_counter()
     backend.dist_rows(row0, nrows)
+    sync(); timings['dist_s'] = time.perf_counter() - t0; t0 = time.perf_counter()
     out = {}
     if eps is None:
         log_eps = np.arange(-100, 100.2, 0.2) if log_eps is None else np.asarray(log_eps, dtype=np.float64)
@@ -137,8 +146,10 @@ def embed_oversized(backend, comm, n, k=16, eps=None, a0=None, tol=0.0, max_step
         np.random.set_state(state)
         eps = float(np.exp(-(popt[1] / popt[0])))
         out.update(logSumWij=logSumWij, popt=popt, R2=R2)
+    sync(); timings['sweep_fit_s'] = time.perf_counter() - t0; t0 = time.perf_counter()
     deg_all = comm.allgather_concat(backend.degree_rows(eps), rows_per)[:n]
     backend.markov_rows(eps, deg_all)
+    sync(); timings['markov_s'] = time.perf_counter() - t0; t0 = time.perf_counter()
 
     max_steps = int(min(max_steps, n - 1))
     kw = k - 1
@@ -163,6 +174,7 @@ def embed_oversized(backend, comm, n, k=16, eps=None, a0=None, tol=0.0, max_step
     if not converged:
         raise RuntimeError('row-block Lanczos did not converge in %d steps' % steps)
     vec = backend.ritz_vectors(steps, k, S) if kw > 0 else backend.ritz_vectors(0, 1, np.zeros((0, 0)))
+    sync(); timings['lanczos_s'] = time.perf_counter() - t0
     val = np.concatenate(([1.0], theta[:kw] ** 2))
-    out.update(eps=eps, val=val, vec=vec, steps=steps, row0=row0, nrows=nrows)
+    out.update(eps=eps, val=val, vec=vec, steps=steps, row0=row0, nrows=nrows, timings=timings)
     return out

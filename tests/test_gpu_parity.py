@@ -78,6 +78,29 @@ def test_distances_full_size_vs_f64_gram(ctx):
     assert np.array_equal(ctx.dist_rms(None, n=2000, P=62500), D)
 
 
+def test_distances_pristine_full_box(ctx):
+    """BASELINE config 1 stand-in: noise-free N=400 stack at the full 250x250 box (small distances, the Gram
+    cancellation regime) against direct float64 differences."""
+    stack = synth.synthetic_pd(pd=4, box=250, n_side=20, tau=1, snr=None)
+    Dr = O.distances_direct(O.standardize_stack(stack))
+    D = ctx.dist_rms(stack)
+    assert Dr[Dr > 0].min() < 0.1 and d_err(D, Dr) < D_TOL
+    assert np.array_equal(D, D.T)
+
+
+def test_distances_row_block_equals_full(ctx):
+    """Row-block path (oversized PD): every block holds the same bits as the rows of the full matrix."""
+    X = np.random.default_rng(11).standard_normal((700, 3000)).astype(np.float32)
+    ctx.dist_config(split_k=4)
+    D = ctx.dist_rms(X)
+    for row0, nrows in [(0, 256), (256, 384), (640, 60)]:
+        Dr = ctx.dist_rms_rows(X, 700, 3000, row0, nrows, download=True)
+        assert np.array_equal(Dr, D[row0:row0 + nrows])
+    with pytest.raises(ValueError):
+        ctx.dist_rms_rows(X, 700, 3000, 100, 200)                             # row0 must be a multiple of 128
+    ctx.dist_config(split_k=0)
+
+
 def test_distances_errors(ctx):
     with pytest.raises(ValueError):
         ctx.dist_rms(None, n=7, P=9)                                          # nothing resident of that shape

@@ -150,6 +150,32 @@ def sec_rot(ctx):
                         print('   counts %s equal=%s' % (k, np.array_equal(c, cnt_ref[k])), flush=True)
 
 
+def sec_rot126(ctx):
+    """BASELINE config 5 shape: 126 manifolds [2000, 15], dim 8, whole theta search in one call."""
+    preps = []
+    t = time.time()
+    for pd in range(126):
+        U0 = synth.random_manifold(m=2000, ncol=15, seed=pd)
+        try:
+            preps.append(RH.prepare(U0, dim=8, PCA=True, CTF=True))
+        except Exception as e:
+            print('prepare failed for', pd, e)
+    groups = {}
+    for p in preps:
+        groups.setdefault(len(p['Rij_final']), []).append(p)
+    print('prepared %d PDs (host conic fits) in %.2fs; groups %s' % (len(preps), time.time() - t, {k: len(v) for k, v in groups.items()}), flush=True)
+    for nr, items in groups.items():
+        RH.sweep_many(items, 8, ctx=ctx)
+        ctx.set_profiling(True); ctx.reset_profiling()
+        t = time.time()
+        th = RH.sweep_many(items, 8, ctx=ctx)
+        tg = time.time() - t
+        rep = kernel_report(ctx); ctx.set_profiling(False)
+        n_eval = sum(len(p['comboList']) for p in items) * nr * 160
+        print('rot126 n_pd=%d n_rij=%d evals=%d wall_ms=%.2f kernel_ms=%.3f evals/s(kernel)=%.3e evals/s(wall)=%.3e' % (
+            len(items), nr, n_eval, tg * 1e3, rep['rot'][0], n_eval / (rep['rot'][0] * 1e-3), n_eval / tg), flush=True)
+
+
 def main():
     secs = sys.argv[1:] or ['smoke', 'shapes', 'sweep', 'eig', 'rot', 'full']
     ctx = _capi.Context(0)
@@ -167,6 +193,7 @@ def main():
             elif s == 'sweep': sec_sweep(ctx)
             elif s == 'eig': sec_eig(ctx)
             elif s == 'rot': sec_rot(ctx)
+            elif s == 'rot126': sec_rot126(ctx)
         except Exception:
             traceback.print_exc()
         print('==== section %s done in %.1fs' % (s, time.time() - t), flush=True)

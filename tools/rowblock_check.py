@@ -41,12 +41,16 @@ with torch.cuda.stream(stream):
     t = time.time(); ctx.upload_images(stack); ctx.sync(); t_up = time.time() - t
     dist.barrier(); torch.cuda.synchronize()
     t = time.time()
-    res = rowblock.embed_oversized(be, comm, n, k=k, verbose=(mode != 'small'))
+    res = rowblock.embed_oversized(be, comm, n, k=k)          # warm-up (allocations, NCCL channels)
+    torch.cuda.synchronize(); dist.barrier()
+    t = time.time()
+    res = rowblock.embed_oversized(be, comm, n, k=k)
     torch.cuda.synchronize(); dist.barrier()
     t_all = time.time() - t
     if rank == 0:
         print('mode=%s world=%d n=%d upload %.2fs embed %.3fs steps=%d eps=%.6f lam=%s' % (
             mode, world, n, t_up, t_all, res['steps'], res['eps'], np.array2string(np.sqrt(res['val']), precision=6)), flush=True)
+        print('timings ' + ' '.join('%s=%.4f' % kv for kv in res['timings'].items()), flush=True)
     # residuals of the eigenpairs against the resident Ms row block
     vec = torch.from_numpy(res['vec']).to(dev)
     w_loc = torch.zeros(be.w_local.shape[0], dtype=torch.float64, device=dev)
