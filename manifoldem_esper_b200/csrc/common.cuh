@@ -71,7 +71,7 @@ struct esper_ctx {
     bool attr_gram = false, attr_sweep = false;
     // stage-1 configuration
     int split_k = 0;
-    double refine_tau = 0.05;
+    double refine_tau = 0.5;
 
     // resident data
     esper::DevBuf imgs;     int img_n = 0, img_P = 0;          // raw float32 stack [n, P]
