@@ -74,15 +74,19 @@ struct GridBarrier {
         if (threadIdx.x == 0) {
             ++epoch;
             int ab = 0;
-            __threadfence();
-            atomicAdd(bar, 1u);
+            // release-arrive / acquire-poll: bar.sync above orders the CTA's writes before the release
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
             const unsigned int target = epoch * gridDim.x;
             const long long t0 = clock64();
-            while (*((volatile unsigned int*)bar) < target) {
-                if (*((volatile unsigned int*)(bar + 1)) != 0u) { ab = 1; break; }
-                if (clock64() - t0 > 4000000000LL) { atomicExch(bar + 1, 1u); ab = 1; break; }
+            for (unsigned int polls = 1;; ++polls) {
+                unsigned int seen;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+                if (seen >= target) break;
+                if ((polls & 255u) == 0u) {                      // watchdog: another CTA gave up, or ~2 s without progress
+                    if (*((volatile unsigned int*)(bar + 1)) != 0u) { ab = 1; break; }
+                    if (clock64() - t0 > 4000000000LL) { atomicExch(bar + 1, 1u); ab = 1; break; }
+                }
             }
-            __threadfence();
             s_abort = ab;
         }
         __syncthreads();
