@@ -58,6 +58,9 @@ int         esper_get_kernel_ms(esper_ctx* ctx, const char* name, double* total_
 int         esper_reset_profiling(esper_ctx* ctx);
 /* Total kernels launched by this ctx since creation (the bench's `gpu_launches` claim). */
 long long   esper_launch_count(esper_ctx* ctx);
+/* Counters: "launches", "lanczos_fallbacks" (partial-reorthogonalisation runs that failed their independent
+ * residual / orthogonality check and were repeated with full reorthogonalisation).  -1 = unknown name. */
+long long   esper_stat(esper_ctx* ctx, const char* name);
 
 /* ---- stage 1: pairwise RMS image distances -------------------------------------------
  * Replaces the non-CTF branch of 1_Embedding/DM/Distances.py:87-104:

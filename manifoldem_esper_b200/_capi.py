@@ -37,6 +37,7 @@ SIGNATURES = {
     'esper_get_kernel_ms': (C.c_int, [C.c_void_p, C.c_char_p, _f64p, _i32p]),
     'esper_reset_profiling': (C.c_int, [C.c_void_p]),
     'esper_launch_count': (C.c_longlong, [C.c_void_p]),
+    'esper_stat': (C.c_longlong, [C.c_void_p, C.c_char_p]),
     'esper_dist_rms': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p]),
     'esper_upload_images': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     'esper_dist_config': (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
@@ -147,6 +148,9 @@ class Context:
 
     def launch_count(self):
         return int(self._lib.esper_launch_count(self._h))
+
+    def stat(self, name):
+        return int(self._lib.esper_stat(self._h, name.encode()))
 
     # -- stage 1 ----------------------------------------------------------------------------
     def dist_config(self, split_k=0, refine_tau=0.5):

@@ -124,6 +124,13 @@ int esper_reset_profiling(esper_ctx* c) {
 
 long long esper_launch_count(esper_ctx* c) { return c ? c->launches : 0; }
 
+long long esper_stat(esper_ctx* c, const char* name) {
+    if (!c || !name) return -1;
+    if (!strcmp(name, "lanczos_fallbacks")) return c->lanczos_fallbacks;
+    if (!strcmp(name, "launches")) return c->launches;
+    return -1;
+}
+
 // ---- stage 1 -----------------------------------------------------------------------------------
 int esper_upload_images(esper_ctx* c, const float* imgs, int n, int P) {
     ESPER_ENTER(c);

@@ -68,7 +68,8 @@ struct esper_ctx {
     std::vector<cudaEvent_t> event_pool;
     long long launches = 0;
 
-    bool attr_gram = false, attr_sweep = false;
+    bool attr_gram = false, attr_sweep = false, attr_lanczos_pro = false;
+    int lanczos_fallbacks = 0;                                 // PRO runs repeated with full reorthogonalisation
     // stage-1 configuration
     int split_k = 0;
     double refine_tau = 0.5;
