@@ -167,17 +167,18 @@ __global__ void __launch_bounds__(LAN_THREADS, 2) lanczos_steps_kernel(StepParam
                 if (r < row1) {
                     const double* a = p.Ms + (size_t)r * m + c0;
                     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                    int cidx = lane;
-                    for (; cidx + 224 < cn; cidx += 256) {            // 8 independent loads in flight per lane
-                        const double x0 = __ldg(a + cidx), x1 = __ldg(a + cidx + 32), x2 = __ldg(a + cidx + 64),
-                                     x3 = __ldg(a + cidx + 96), x4 = __ldg(a + cidx + 128), x5 = __ldg(a + cidx + 160),
-                                     x6 = __ldg(a + cidx + 192), x7 = __ldg(a + cidx + 224);
-                        a0 = fma(x0, s_vec[cidx], a0);       a1 = fma(x1, s_vec[cidx + 32], a1);
-                        a2 = fma(x2, s_vec[cidx + 64], a2);  a3 = fma(x3, s_vec[cidx + 96], a3);
-                        a0 = fma(x4, s_vec[cidx + 128], a0); a1 = fma(x5, s_vec[cidx + 160], a1);
-                        a2 = fma(x6, s_vec[cidx + 192], a2); a3 = fma(x7, s_vec[cidx + 224], a3);
+                    for (int cidx = lane; cidx < cn; cidx += 256) {    // 8 independent (predicated) loads in flight per lane
+                        double x[8], y[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int cc = cidx + 32 * u;
+                            const bool ok = cc < cn;
+                            x[u] = ok ? __ldg(a + cc) : 0.0;
+                            y[u] = ok ? s_vec[cc] : 0.0;
+                        }
+                        a0 = fma(x[0], y[0], a0); a1 = fma(x[1], y[1], a1); a2 = fma(x[2], y[2], a2); a3 = fma(x[3], y[3], a3);
+                        a0 = fma(x[4], y[4], a0); a1 = fma(x[5], y[5], a1); a2 = fma(x[6], y[6], a2); a3 = fma(x[7], y[7], a3);
                     }
-                    for (; cidx < cn; cidx += 32) a0 = fma(__ldg(a + cidx), s_vec[cidx], a0);
                     acc += (a0 + a1) + (a2 + a3);
                 }
             }
@@ -202,13 +203,18 @@ __global__ void __launch_bounds__(LAN_THREADS, 2) lanczos_steps_kernel(StepParam
                 if (i <= i_end) {
                     const double* v = (i <= j) ? p.V + (size_t)i * m : wnew;
                     double a0 = 0.0, a1 = 0.0;
-                    int r = gw * 32 + lane;
-                    for (; r + 768 < m; r += 1024) {                  // 4 independent load pairs per lane
-                        const double v0 = ld_cg(v + r), v1 = ld_cg(v + r + 256), v2 = ld_cg(v + r + 512), v3 = ld_cg(v + r + 768);
-                        const double w0 = ld_cg(wnew + r), w1 = ld_cg(wnew + r + 256), w2 = ld_cg(wnew + r + 512), w3 = ld_cg(wnew + r + 768);
-                        a0 = fma(v0, w0, a0); a1 = fma(v1, w1, a1); a0 = fma(v2, w2, a0); a1 = fma(v3, w3, a1);
+                    for (int r = gw * 32 + lane; r < m; r += 2048) {  // 8 independent (predicated) load pairs per lane
+                        double x[8], y[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int rr = r + 256 * u;
+                            const bool ok = rr < m;
+                            x[u] = ok ? ld_cg(v + rr) : 0.0;
+                            y[u] = ok ? ld_cg(wnew + rr) : 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; u += 2) { a0 = fma(x[u], y[u], a0); a1 = fma(x[u + 1], y[u + 1], a1); }
                     }
-                    for (; r < m; r += 256) a0 = fma(ld_cg(v + r), ld_cg(wnew + r), a0);
                     sacc = warp_sum(a0 + a1);
                 }
                 __syncthreads();
@@ -230,14 +236,18 @@ __global__ void __launch_bounds__(LAN_THREADS, 2) lanczos_steps_kernel(StepParam
                 double sacc = 0.0;
                 if (r < row1) {
                     double a0 = 0.0, a1 = 0.0;
-                    int i = sub;
-                    for (; i + 96 <= j; i += 128) {
-                        const double h0 = ld_cg(p.h + i), h1 = ld_cg(p.h + i + 32), h2 = ld_cg(p.h + i + 64), h3 = ld_cg(p.h + i + 96);
-                        const double v0 = ld_cg(p.V + (size_t)i * m + r), v1 = ld_cg(p.V + (size_t)(i + 32) * m + r),
-                                     v2 = ld_cg(p.V + (size_t)(i + 64) * m + r), v3 = ld_cg(p.V + (size_t)(i + 96) * m + r);
-                        a0 = fma(h0, v0, a0); a1 = fma(h1, v1, a1); a0 = fma(h2, v2, a0); a1 = fma(h3, v3, a1);
+                    for (int i = sub; i <= j; i += 256) {             // 8 independent (predicated) load pairs per thread
+                        double x[8], y[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int ii = i + 32 * u;
+                            const bool ok = ii <= j;
+                            x[u] = ok ? ld_cg(p.h + ii) : 0.0;
+                            y[u] = ok ? ld_cg(p.V + (size_t)ii * m + r) : 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; u += 2) { a0 = fma(x[u], y[u], a0); a1 = fma(x[u + 1], y[u + 1], a1); }
                     }
-                    for (; i <= j; i += 32) a0 = fma(ld_cg(p.h + i), ld_cg(p.V + (size_t)i * m + r), a0);
                     sacc = a0 + a1;
                 }
                 __syncthreads();
