@@ -218,6 +218,7 @@ def run_ours(args):
         ctxs.append(_capi.Context(local_rank, stream=st_.cuda_stream)); streams.append(st_)
     for i, c in enumerate(ctxs):
         c.upload_images(pinned[i % n_stacks].numpy())
+        c.dmap_config(args.eig_mode if args.eig_mode >= 0 else (1 if NF > 1 else 0))
         c.sync()
     iters_used = []
 
@@ -380,6 +381,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--eig-mode', type=int, default=-1, help='esper_dmap_config mode (-1 = throughput when several PDs are in flight)')
     ap.add_argument('--inflight', type=int, default=4, help='PDs in flight per GPU (host threads / ctxs / streams)')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -109,6 +109,11 @@ int esper_markov(esper_ctx* ctx, const double* D, int m, double eps, double* deg
  *              sign fixed so that the entry of largest magnitude is positive
  *   tol: relative residual |Ms v - lambda v| <= tol*lambda_1  (0 = 1e-10)
  *   max_iter: Lanczos steps (0 = min(m-1, 1024));  iters (optional) receives the steps used.  */
+/* Eigensolver scheduling for m <= 2048.  mode 0 (default, lowest latency for one PD): every CTA keeps its rows of
+ * Ms in shared memory / registers for the whole solve (the kernel owns the SMs).  mode 1 (highest throughput with
+ * several ctxs per GPU): rows are streamed from L2 and the kernel fits twice per SM, so the solves of two PDs
+ * overlap and hide each other's grid-barrier latency.  Same arithmetic, same results. */
+int esper_dmap_config(esper_ctx* ctx, int mode);
 int esper_dmap_embed(esper_ctx* ctx, const double* D, int m, double eps, int k, double tol,
                      int max_iter, double* val, double* vec, int* iters);
 

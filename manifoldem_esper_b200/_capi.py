@@ -44,6 +44,7 @@ SIGNATURES = {
     'esper_upload_dist': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     'esper_eps_sweep': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
     'esper_markov': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
+    'esper_dmap_config': (C.c_int, [C.c_void_p, C.c_int]),
     'esper_dmap_embed': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int,
                                    C.c_void_p, C.c_void_p, _i32p]),
     'esper_dist_rms_rows': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int, C.c_void_p]),
@@ -206,6 +207,10 @@ class Context:
         Ms = np.empty((m, m), dtype=np.float64) if want_matrix else None
         self._check(self._lib.esper_markov(self._h, _ptr(D), int(m), float(eps), _ptr(deg), _ptr(Ms)))
         return deg, Ms
+
+    def dmap_config(self, mode=0):
+        """0 = latency (Ms resident on chip), 1 = throughput (two solves share every SM)."""
+        self._check(self._lib.esper_dmap_config(self._h, int(mode)))
 
     def dmap_embed(self, D, eps, k=16, tol=0.0, max_iter=0, m=None):
         """DiffusionMaps.py:109-169 at a given eps -> (val[k] = lambda^2, vec[m, k], lanczos steps)."""

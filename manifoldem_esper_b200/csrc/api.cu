@@ -217,6 +217,13 @@ int esper_markov(esper_ctx* c, const double* D, int m, double eps, double* degre
     return ESPER_OK;
 }
 
+int esper_dmap_config(esper_ctx* c, int mode) {
+    ESPER_ENTER(c);
+    if (mode != 0 && mode != 1) return fail(c, ESPER_E_ARG, "dmap_config: mode must be 0 (latency) or 1 (throughput)");
+    c->lanczos_mode = mode;
+    return ESPER_OK;
+}
+
 int esper_dmap_embed(esper_ctx* c, const double* D, int m, double eps, int k, double tol, int max_iter,
                      double* val, double* vec, int* iters) {
     ESPER_ENTER(c);

@@ -58,6 +58,8 @@ struct StepParams {
     int j_start;          // first Lanczos vector index of this batch (>= 1); V[j_start] is normalised
     int n_steps;
     unsigned int* bar;    // bar[0] arrival counter (zeroed before every launch), bar[1] abort flag
+    int rows_cached;      // resident kernel: owned rows of Ms kept in shared memory (the rest, <= 2, in registers)
+    long long* prof;      // optional [8] cycle counters of CTA 0 per phase (debug), or NULL
 };
 
 // Grid-wide barrier for a co-resident (cooperatively launched) grid: monotone arrival counter, the
@@ -286,6 +288,295 @@ __global__ void __launch_bounds__(LAN_THREADS, 2) lanczos_steps_kernel(StepParam
         const double* src = p.wbuf + (size_t)cur * m;
         if (b == 0 && tid == 0) p.beta[j - 2] = bt;
         for (int r = row0 + tid; r < row1; r += LAN_THREADS) p.V[(size_t)j * m + r] = ld_cg(src + r) * scale;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Resident variant for m <= LAN_CH (the BASELINE shape, m = 2000): Ms never leaves the chip.
+//
+// Ms is the same at every step and a CTA always needs the same rows, so each CTA loads its rows ONCE per launch:
+// up to ~13 rows into shared memory (208 kB) and at most two more into registers.  148 SMs x 13.5 rows x 16 kB
+// is the whole 32 MB matrix.  Per step, the only global traffic is the Lanczos vector (16 kB per CTA), the
+// basis rows for the Gram-Schmidt passes and a few scalars; every phase is arranged so that it waits for at
+// most ONE L2 round trip (measured cycle budget per step in DESIGN.md).  Same arithmetic and the same three
+// grid barriers as lanczos_steps_kernel.
+// ------------------------------------------------------------------------------------------------
+#define RES_PROF(slot)                                                                      \
+    do {                                                                                    \
+        if (p.prof && b == 0 && tid == 0) { const long long t_ = clock64(); p.prof[slot] += t_ - t_prof; t_prof = t_; } \
+    } while (0)
+
+// 16 per-lane values -> 16 warp totals with 16 shuffles (instead of 16 x 5): every round halves the number of values
+// a lane carries by trading the other half with its partner.  Lane l ends with the total of value index
+// ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 + ((l>>1)&1); fixed order, deterministic.
+__device__ __forceinline__ double warp_multi_sum16(double (&v)[16], int lane) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const bool up = lane & 16;
+        const double send = up ? v[i] : v[i + 8];
+        const double keep = up ? v[i + 8] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool up = lane & 8;
+        const double send = up ? v[i] : v[i + 4];
+        const double keep = up ? v[i + 4] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const bool up = lane & 4;
+        const double send = up ? v[i] : v[i + 2];
+        const double keep = up ? v[i + 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    {
+        const bool up = lane & 2;
+        const double send = up ? v[0] : v[1];
+        const double keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// RES = true : rows of Ms resident in shared memory / registers, one CTA per SM (lowest latency for one PD).
+// RES = false: rows streamed from L2 every step, <= 64 registers and 20 kB of shared memory, so that two such grids
+//              (two PDs in flight) share every SM and hide each other's barrier latency (highest throughput).
+template <bool RES>
+__global__ void __launch_bounds__(LAN_THREADS, RES ? 1 : 2) lanczos_resident_kernel(StepParams p) {
+    GridBarrier grid(p.bar);
+    extern __shared__ double res_smem[];
+    double* s_vec = res_smem;                        // [LAN_CH] q_j, normalised, all columns
+    double* s_rows = res_smem + LAN_CH;              // [rows_cached][m]
+    __shared__ double s_red[32 * 16];
+    __shared__ double s_prev[16];                    // q_{j-1} on the owned rows
+    __shared__ double s_nrm[16];
+    __shared__ double s_tmp[LAN_WARPS + 1];
+    const int m = p.m;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nb = gridDim.x, b = blockIdx.x;
+    const int chunk = (m + nb - 1) / nb;
+    const int row0 = min(b * chunk, m), row1 = min(row0 + chunk, m);
+    const int n_own = row1 - row0;                   // <= 16
+    const int n_sm = min(p.rows_cached, n_own);      // rows in shared memory; rows n_sm, n_sm+1 live in registers
+    long long t_prof = clock64();
+
+    // ---- once per launch: rows of Ms -> shared memory / registers; q_j, q_{j-1}, alpha_{j-1}, beta_{j-1} ----
+    int j = p.j_start;
+    double rrow[2][4];
+    if (RES) {
+        for (int rr = 0; rr < n_sm; ++rr) {
+            const double* a = p.Ms + (size_t)(row0 + rr) * m;
+            for (int c = tid; c < m; c += LAN_THREADS) s_rows[(size_t)rr * m + c] = __ldg(a + c);
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = tid + LAN_THREADS * u;
+                rrow[e][u] = (n_sm + e < n_own && c < m) ? __ldg(p.Ms + (size_t)(row0 + n_sm + e) * m + c) : 0.0;
+            }
+    }
+    for (int c = tid; c < m; c += LAN_THREADS) s_vec[c] = ld_cg(p.V + (size_t)j * m + c);
+    if (tid < 16) s_prev[tid] = (j >= 2 && tid < n_own) ? ld_cg(p.V + (size_t)(j - 1) * m + row0 + tid) : 0.0;
+    double sigma = 0.0, beta_prev = 0.0;             // alpha_{j-1} (shift predictor), beta_{j-1}; carried in registers
+    if (j >= 2) { sigma = ld_cg(p.alpha + j - 2); beta_prev = ld_cg(p.beta + j - 2); }
+    __syncthreads();
+    RES_PROF(7);
+
+    int cur = 0;
+    for (int step = 0; step < p.n_steps; ++step, ++j) {
+        double* wnew = p.wbuf + (size_t)cur * m;
+
+        // ---- S0: w = Ms q_j - sigma q_j - beta_{j-1} q_{j-1} on the owned rows ----
+        if (RES) {                                   // on-chip operands only
+            double acc[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) acc[q] = 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = tid + LAN_THREADS * u;
+                if (c < m) {
+                    const double qv = s_vec[c];
+#pragma unroll
+                    for (int q = 0; q < 14; ++q)
+                        if (q < n_sm) acc[q] = fma(s_rows[(size_t)q * m + c], qv, acc[q]);
+                    acc[14] = fma(rrow[0][u], qv, acc[14]);
+                    acc[15] = fma(rrow[1][u], qv, acc[15]);
+                }
+            }
+            const double t = warp_multi_sum16(acc, lane);
+            if ((lane & 1) == 0) s_red[warp * 16 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = t;
+            __syncthreads();
+            if (tid < n_own) {
+                const int slot = tid < n_sm ? tid : 14 + (tid - n_sm);      // register rows sit in slots 14, 15
+                double tot = 0.0;
+#pragma unroll
+                for (int w2 = 0; w2 < LAN_WARPS; ++w2) tot += s_red[w2 * 16 + slot];
+                const int r = row0 + tid;
+                const double qr = s_vec[r];
+                double x = fma(-sigma, qr, tot);
+                x = fma(-beta_prev, s_prev[tid], x);
+                wnew[r] = x;
+                s_prev[tid] = qr;                                           // q_j on the owned rows, for the next step
+            }
+        } else {                                     // rows streamed from L2: one warp per row, 8 loads in flight per lane
+            const int r = row0 + warp;
+            if (warp < n_own) {
+                const double* a = p.Ms + (size_t)r * m;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                for (int cidx = lane; cidx < m; cidx += 256) {
+                    double x[8], y[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int cc = cidx + 32 * u;
+                        const bool ok = cc < m;
+                        x[u] = ok ? __ldg(a + cc) : 0.0;
+                        y[u] = ok ? s_vec[cc] : 0.0;
+                    }
+                    a0 = fma(x[0], y[0], a0); a1 = fma(x[1], y[1], a1); a2 = fma(x[2], y[2], a2); a3 = fma(x[3], y[3], a3);
+                    a0 = fma(x[4], y[4], a0); a1 = fma(x[5], y[5], a1); a2 = fma(x[6], y[6], a2); a3 = fma(x[7], y[7], a3);
+                }
+                const double tot = warp_sum((a0 + a1) + (a2 + a3));
+                if (lane == 0) {
+                    const double qr = s_vec[r];
+                    double x = fma(-sigma, qr, tot);
+                    x = fma(-beta_prev, s_prev[warp], x);
+                    wnew[r] = x;
+                    s_prev[warp] = qr;
+                }
+            }
+        }
+        RES_PROF(0);
+        if (!grid.sync()) return;
+        RES_PROF(1);
+
+        double alpha_j = sigma, s2_last = 0.0;
+        for (int pass = 0; pass < 2; ++pass) {
+            // ---- S1: h[i] = V_i . w for i <= j, and (first pass only) h[j+1] = w . w ----
+            const int i_end = (pass == 0) ? j + 1 : j;
+            const int grp = warp >> 3, gw = warp & 7;
+            for (int i0 = 0; i0 <= i_end; i0 += 2 * nb) {
+                const int i = i0 + grp * nb + b;
+                double sacc = 0.0;
+                if (i <= i_end) {
+                    const double* v = (i <= j) ? p.V + (size_t)i * m : wnew;
+                    double x[8], y[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int rr = gw * 32 + lane + 256 * u;
+                        const bool ok = rr < m;
+                        x[u] = ok ? ld_cg(v + rr) : 0.0;
+                        y[u] = ok ? ld_cg(wnew + rr) : 0.0;
+                    }
+                    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                    for (int u = 0; u < 8; u += 2) { a0 = fma(x[u], y[u], a0); a1 = fma(x[u + 1], y[u + 1], a1); }
+                    sacc = warp_sum(a0 + a1);
+                }
+                __syncthreads();
+                if (lane == 0) s_red[warp] = sacc;
+                __syncthreads();
+                if (gw == 0 && lane == 0 && i <= i_end) {
+                    double tot = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) tot += s_red[grp * 8 + q];
+                    p.h[i] = tot;
+                }
+            }
+            RES_PROF(2);
+            if (!grid.sync()) return;
+            RES_PROF(3);
+
+            // ---- S2: w -= V h on the owned rows; partial |w|^2.  All loads of the phase are issued together. ----
+            const int rloc = tid & 15, sub = tid >> 4;
+            const int r = row0 + rloc;
+            const double hj = ld_cg(p.h + j);
+            const double ww = (pass == 0) ? ld_cg(p.h + j + 1) : 0.0;
+            double wv = 0.0, sacc = 0.0;
+            if (rloc < n_own) {
+                if (sub == 0) wv = ld_cg(wnew + r);
+                double a0 = 0.0, a1 = 0.0;
+                for (int i = sub; i <= j; i += 256) {
+                    double x[8], y[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int ii = i + 32 * u;
+                        const bool ok = ii <= j;
+                        x[u] = ok ? ld_cg(p.h + ii) : 0.0;
+                        y[u] = ok ? ld_cg(p.V + (size_t)ii * m + r) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u += 2) { a0 = fma(x[u], y[u], a0); a1 = fma(x[u + 1], y[u + 1], a1); }
+                }
+                sacc = a0 + a1;
+            }
+            __syncthreads();
+            s_red[sub * 16 + rloc] = sacc;
+            __syncthreads();
+            double nrm = 0.0;
+            if (tid < 16 && tid < n_own) {
+                double tot = 0.0;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) tot += s_red[q * 16 + tid];
+                const double x = wv - tot;
+                wnew[r] = x;
+                nrm = x * x;
+            }
+            if (tid < 16) s_nrm[tid] = nrm;
+            __syncthreads();
+            alpha_j += hj;
+            if (tid == 0) {
+                double tot = 0.0;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) tot += s_nrm[q];
+                p.part[b] = tot;
+                if (b == 0) p.alpha[j - 1] = alpha_j;
+            }
+            RES_PROF(4);
+            if (!grid.sync()) return;
+            RES_PROF(5);
+            // norm of the updated vector; prefetch the new vector elements in the same round trip
+            double nx[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int c = tid + LAN_THREADS * u; nx[u] = c < m ? ld_cg(wnew + c) : 0.0; }
+            s2_last = sum_partials(p.part, nb, s_tmp);
+            // DGKS ("twice is enough"): second pass iff |w_after|^2 < |w_before|^2 / 2
+            if (pass == 0 && !(s2_last < 0.5 * ww)) {
+                const double bt = sqrt(s2_last);
+                const double inv = bt > 0.0 ? 1.0 / bt : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {                               // q_{j+1} for all columns, locally
+                    const int c = tid + LAN_THREADS * u;
+                    if (c < m) {
+                        const double x = nx[u] * inv;
+                        s_vec[c] = x;
+                        if (c >= row0 && c < row1) p.V[(size_t)(j + 1) * m + c] = x;
+                    }
+                }
+                break;
+            }
+            if (pass == 1) {
+                const double bt = sqrt(s2_last);
+                const double inv = bt > 0.0 ? 1.0 / bt : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c = tid + LAN_THREADS * u;
+                    if (c < m) {
+                        const double x = nx[u] * inv;
+                        s_vec[c] = x;
+                        if (c >= row0 && c < row1) p.V[(size_t)(j + 1) * m + c] = x;
+                    }
+                }
+            }
+        }
+        beta_prev = sqrt(s2_last);
+        sigma = alpha_j;
+        if (b == 0 && tid == 0) p.beta[j - 1] = beta_prev;
+        __syncthreads();                                                    // s_vec complete before the next S0
+        cur ^= 1;
+        RES_PROF(6);
     }
 }
 
@@ -796,8 +1087,34 @@ static int lanczos_attempt(esper_ctx* c, int m, int k, double tol, int max_iter,
             c->attr_lanczos_pro = true;
         }
         ESPER_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lanczos_pro_kernel, LAN_THREADS, pro_smem));
-    } else {
-        ESPER_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lanczos_steps_kernel, LAN_THREADS, 0));
+    }
+    // Full reorthogonalisation: the resident kernel when the CTA's rows of Ms fit on chip, else the streaming one.
+    int rows_cached = 0;
+    size_t lan_smem = 0;
+    bool resident = false, small = false;
+    if (!use_pro) {
+        const int chunk_rows = ceil_div(m, c->sm_count);
+        const size_t budget = (size_t)(227 - 7) * 1024 - sizeof(double) * LAN_CH;   // per-CTA limit minus static arrays
+        small = (m <= LAN_CH && chunk_rows <= 16);          // whole vector in shared memory, one warp per owned row
+        if (small && c->lanczos_mode == 0) {
+            rows_cached = (int)std::min<size_t>(std::min(chunk_rows, 14), budget / (sizeof(double) * (size_t)m));
+            resident = chunk_rows <= rows_cached + 2;
+        }
+        if (resident) {
+            lan_smem = sizeof(double) * ((size_t)LAN_CH + (size_t)rows_cached * m);
+            if (!c->attr_lanczos) {
+                ESPER_CUDA(c, cudaFuncSetAttribute(lanczos_resident_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                c->attr_lanczos = true;
+            }
+            ESPER_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lanczos_resident_kernel<true>, LAN_THREADS, lan_smem));
+        } else if (small) {
+            rows_cached = 0;
+            lan_smem = sizeof(double) * (size_t)LAN_CH;
+            ESPER_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lanczos_resident_kernel<false>, LAN_THREADS, lan_smem));
+        } else {
+            rows_cached = 0;
+            ESPER_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lanczos_steps_kernel, LAN_THREADS, 0));
+        }
     }
     if (!coop || per_sm < 1) return fail(c, ESPER_E_CUDA, "cooperative launch unavailable on this device");
     const int grid = c->sm_count;
@@ -805,7 +1122,7 @@ static int lanczos_attempt(esper_ctx* c, int m, int k, double tol, int max_iter,
     const int stride = max_iter + 8;
     ESPER_RESERVE(c, c->lan_V, sizeof(double) * (size_t)(max_iter + 3) * m);
     ESPER_RESERVE(c, c->lan_w, sizeof(double) * (size_t)m * 2);
-    ESPER_RESERVE(c, c->lan_h, sizeof(double) * ((size_t)stride * 3 + 6 * (size_t)grid + 2 * (size_t)ocap + 16));
+    ESPER_RESERVE(c, c->lan_h, sizeof(double) * ((size_t)stride * 3 + 6 * (size_t)grid + 2 * (size_t)ocap + 32));
     if (c->pin.reserve(sizeof(double) * ((size_t)stride * 2 * 2 + 4)) != 0) return fail(c, ESPER_E_NOMEM, "pinned alloc failed");
     double* V = c->lan_V.as<double>();
     double* w = c->lan_w.as<double>();
@@ -817,8 +1134,9 @@ static int lanczos_attempt(esper_ctx* c, int m, int k, double tol, int max_iter,
     double* omega_d = part_d + 6 * (size_t)grid;        // [2 * ocap + 1]
     unsigned int* bar_d = reinterpret_cast<unsigned int*>(omega_d + 2 * (size_t)ocap + 2);
     int* stats_d = reinterpret_cast<int*>(bar_d + 2);
+    long long* prof_d = getenv("ESPER_DEBUG_LANCZOS") ? reinterpret_cast<long long*>(stats_d + 2) : nullptr;   // 8 counters, zeroed below
     ESPER_CUDA(c, cudaMemsetAsync(alpha_d, 0, sizeof(double) * (size_t)stride * 2, st));
-    ESPER_CUDA(c, cudaMemsetAsync(omega_d, 0, sizeof(double) * (2 * (size_t)ocap + 2) + 16, st));
+    ESPER_CUDA(c, cudaMemsetAsync(omega_d, 0, sizeof(double) * (2 * (size_t)ocap + 2) + 16 + 80, st));
     if (use_pro) {
         const double one = 1.0;
         ESPER_CUDA(c, cudaMemcpyAsync(omega_d + 1, &one, sizeof(double), cudaMemcpyHostToDevice, st));   // omega_{1,1} = 1
@@ -856,9 +1174,10 @@ static int lanczos_attempt(esper_ctx* c, int m, int k, double tol, int max_iter,
                 void* args[] = {&sp};
                 e = cudaLaunchCooperativeKernel((void*)lanczos_pro_kernel, dim3(grid), dim3(LAN_THREADS), args, pro_smem, st);
             } else {
-                StepParams sp{Ms, m, V, w, h, part_d, alpha_d, beta_d, steps_issued + 1, n_steps, bar_d};
+                StepParams sp{Ms, m, V, w, h, part_d, alpha_d, beta_d, steps_issued + 1, n_steps, bar_d, rows_cached, prof_d};
                 void* args[] = {&sp};
-                e = cudaLaunchCooperativeKernel((void*)lanczos_steps_kernel, dim3(grid), dim3(LAN_THREADS), args, 0, st);
+                void* fn = resident ? (void*)lanczos_resident_kernel<true> : small ? (void*)lanczos_resident_kernel<false> : (void*)lanczos_steps_kernel;
+                e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(LAN_THREADS), args, lan_smem, st);
             }
         }
         if (e != cudaSuccess) { cudaGetLastError(); return fail(c, ESPER_E_CUDA, "cooperative launch: %s", cudaGetErrorString(e)); }
@@ -872,7 +1191,7 @@ static int lanczos_attempt(esper_ctx* c, int m, int k, double tol, int max_iter,
     int rc = ESPER_OK;
     if (!converged) {
         const int first = std::min(max_iter, std::max(3 * (kw + guard) + 8, 32));
-        const int batch = 16;
+        const int batch = resident ? 24 : 16;                    // resident rows are reloaded per launch: longer batches
         rc = issue_batch(first, slot);
         while (rc == ESPER_OK) {
             const int cur_slot = slot;
@@ -903,7 +1222,14 @@ static int lanczos_attempt(esper_ctx* c, int m, int k, double tol, int max_iter,
         int nre = 0;
         cudaStreamSynchronize(st);
         cudaMemcpy(&nre, stats_d, sizeof(int), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[lanczos] pro=%d converged=%d steps=%d issued=%d explicit_reorth=%d\n", (int)use_pro, (int)converged, steps, steps_issued, nre);
+        fprintf(stderr, "[lanczos] pro=%d resident=%d rows_cached=%d converged=%d steps=%d issued=%d explicit_reorth=%d\n", (int)use_pro, (int)resident, rows_cached, (int)converged, steps, steps_issued, nre);
+        if (prof_d) {
+            long long pr[8];
+            cudaMemcpy(pr, prof_d, sizeof(pr), cudaMemcpyDeviceToHost);
+            const double n = steps_issued > 0 ? (double)steps_issued : 1.0;
+            fprintf(stderr, "[lanczos] CTA0 cycles/step: S0 %.0f | bar1 %.0f | S1 %.0f | bar2 %.0f | S2 %.0f | bar3 %.0f | norm+next %.0f ; per-launch prologue total %lld\n",
+                    pr[0] / n, pr[1] / n, pr[2] / n, pr[3] / n, pr[4] / n, pr[5] / n, pr[6] / n, pr[7]);
+        }
     }
     if (!converged) { cudaStreamSynchronize(st); return fail(c, ESPER_E_NOCONV, "Lanczos did not converge in %d steps", steps); }
 

@@ -215,6 +215,21 @@ def test_embed_end_to_end_matches_reference_run(ctx):
         assert vec_err(res['vec'][:, i], U_r[:, i]) < 1e-3
 
 
+def test_eigensolver_modes_agree(ctx):
+    """Latency mode (Ms resident on chip) and throughput mode (streamed, two grids per SM) run the same algorithm."""
+    g = golden('stage23_medium.npz')
+    ctx.dmap_config(0)
+    v0, U0, it0 = ctx.dmap_embed(g['D'], float(g['eps']), k=10)
+    ctx.dmap_config(1)
+    v1, U1, it1 = ctx.dmap_embed(g['D'], float(g['eps']), k=10)
+    ctx.dmap_config(0)
+    assert it0 == it1 and np.max(np.abs(v0 - v1) / v0) < 1e-12
+    for i in range(10):
+        assert vec_err(U0[:, i], U1[:, i]) < 1e-9
+    with pytest.raises(ValueError):
+        ctx.dmap_config(7)
+
+
 def test_embed_argument_errors(ctx):
     D = golden('stage123_small.npz')['D']
     with pytest.raises(ValueError):
