@@ -101,6 +101,7 @@ struct GridBarrier {
 constexpr int LAN_THREADS = 512;
 constexpr int LAN_WARPS = LAN_THREADS / 32;
 constexpr int LAN_CH = 2048;          // columns of the vector staged in shared memory at a time
+constexpr int LAN_H = 1040;           // Gram-Schmidt coefficients staged in shared memory (max_iter <= 1024)
 
 // Sum of the per-CTA partial norms, identical in every thread of every CTA (fixed reduction tree).
 __device__ __forceinline__ double sum_partials(const double* part, int nb, double* s_tmp /*[LAN_WARPS + 1]*/) {
@@ -351,6 +352,7 @@ __global__ void __launch_bounds__(LAN_THREADS, RES ? 1 : 2) lanczos_resident_ker
     double* s_rows = res_smem + LAN_CH;              // [rows_cached][m]
     __shared__ double s_red[32 * 16];
     __shared__ double s_prev[16];                    // q_{j-1} on the owned rows
+    __shared__ double s_h[LAN_H];                    // Gram-Schmidt coefficients of the step (staged once per CTA)
     __shared__ double s_nrm[16];
     __shared__ double s_tmp[LAN_WARPS + 1];
     const int m = p.m;
@@ -490,26 +492,37 @@ __global__ void __launch_bounds__(LAN_THREADS, RES ? 1 : 2) lanczos_resident_ker
             RES_PROF(3);
 
             // ---- S2: w -= V h on the owned rows; partial |w|^2.  All loads of the phase are issued together. ----
+            // h is read by every thread of every CTA: stage it once per CTA (148 x 512 threads loading the same dozen
+            // cache lines directly made this phase 3x slower -- an L2 slice hot spot).
             const int rloc = tid & 15, sub = tid >> 4;
             const int r = row0 + rloc;
-            const double hj = ld_cg(p.h + j);
-            const double ww = (pass == 0) ? ld_cg(p.h + j + 1) : 0.0;
-            double wv = 0.0, sacc = 0.0;
+            const bool h_sm = (j + 2 <= LAN_H);
+            double wv = 0.0;
+            double yv[8];                                   // basis entries V[ii][r], ii = sub + 32u (first 256 vectors)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int ii = sub + 32 * u;
+                yv[u] = (rloc < n_own && ii <= j) ? ld_cg(p.V + (size_t)ii * m + r) : 0.0;
+            }
+            if (rloc < n_own && sub == 0) wv = ld_cg(wnew + r);
+            if (h_sm) {                                     // same round trip as the loads above
+                for (int i = tid; i <= j + 1; i += LAN_THREADS) s_h[i] = ld_cg(p.h + i);
+                __syncthreads();
+            }
+            const double hj = h_sm ? s_h[j] : ld_cg(p.h + j);
+            const double ww = (pass == 0) ? (h_sm ? s_h[j + 1] : ld_cg(p.h + j + 1)) : 0.0;
+            double sacc = 0.0;
             if (rloc < n_own) {
-                if (sub == 0) wv = ld_cg(wnew + r);
                 double a0 = 0.0, a1 = 0.0;
-                for (int i = sub; i <= j; i += 256) {
-                    double x[8], y[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int ii = i + 32 * u;
-                        const bool ok = ii <= j;
-                        x[u] = ok ? ld_cg(p.h + ii) : 0.0;
-                        y[u] = ok ? ld_cg(p.V + (size_t)ii * m + r) : 0.0;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; u += 2) { a0 = fma(x[u], y[u], a0); a1 = fma(x[u + 1], y[u + 1], a1); }
+                for (int u = 0; u < 8; u += 2) {
+                    const int i0 = sub + 32 * u, i1 = i0 + 32;
+                    const double h0 = i0 <= j ? (h_sm ? s_h[i0] : ld_cg(p.h + i0)) : 0.0;
+                    const double h1 = i1 <= j ? (h_sm ? s_h[i1] : ld_cg(p.h + i1)) : 0.0;
+                    a0 = fma(h0, yv[u], a0); a1 = fma(h1, yv[u + 1], a1);
                 }
+                for (int i = sub + 256; i <= j; i += 32)     // more than 256 basis vectors: the tail, rarely reached
+                    a0 = fma(h_sm ? s_h[i] : ld_cg(p.h + i), ld_cg(p.V + (size_t)i * m + r), a0);
                 sacc = a0 + a1;
             }
             __syncthreads();
@@ -1094,7 +1107,7 @@ static int lanczos_attempt(esper_ctx* c, int m, int k, double tol, int max_iter,
     bool resident = false, small = false;
     if (!use_pro) {
         const int chunk_rows = ceil_div(m, c->sm_count);
-        const size_t budget = (size_t)(227 - 7) * 1024 - sizeof(double) * LAN_CH;   // per-CTA limit minus static arrays
+        const size_t budget = (size_t)(227 - 16) * 1024 - sizeof(double) * LAN_CH;  // per-CTA limit minus static arrays
         small = (m <= LAN_CH && chunk_rows <= 16);          // whole vector in shared memory, one warp per owned row
         if (small && c->lanczos_mode == 0) {
             rows_cached = (int)std::min<size_t>(std::min(chunk_rows, 14), budget / (sizeof(double) * (size_t)m));
@@ -1102,9 +1115,9 @@ static int lanczos_attempt(esper_ctx* c, int m, int k, double tol, int max_iter,
         }
         if (resident) {
             lan_smem = sizeof(double) * ((size_t)LAN_CH + (size_t)rows_cached * m);
-            if (!c->attr_lanczos) {
-                ESPER_CUDA(c, cudaFuncSetAttribute(lanczos_resident_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-                c->attr_lanczos = true;
+            if ((size_t)c->lanczos_smem_set < lan_smem) {
+                ESPER_CUDA(c, cudaFuncSetAttribute(lanczos_resident_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lan_smem));
+                c->lanczos_smem_set = (long long)lan_smem;
             }
             ESPER_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lanczos_resident_kernel<true>, LAN_THREADS, lan_smem));
         } else if (small) {
