@@ -95,7 +95,7 @@ __device__ __forceinline__ float tf32_rna(float x) {
 }
 
 // One block per image: write the hi / lo TF32 planes (row stride ld, zero padded) and |c|^2.
-__global__ void __launch_bounds__(1024) stats_split_kernel(const float* __restrict__ raw, int n, int P, int ld,
+__global__ void __launch_bounds__(512) stats_split_kernel(const float* __restrict__ raw, int n, int P, int ld,
                                                           int standardize, RowStat* __restrict__ st,
                                                           const float* __restrict__ xbar, int center,
                                                           float* __restrict__ hi, float* __restrict__ lo) {
@@ -176,7 +176,7 @@ int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld) {
     }
     {
         LaunchScope ls(c, "prep");
-        stats_split_kernel<<<n, 1024, 0, c->stream>>>(raw, n, P, ld, standardize, st, xbar, center,
+        stats_split_kernel<<<n, 512, 0, c->stream>>>(raw, n, P, ld, standardize, st, xbar, center,
                                                      c->plane_hi.as<float>(), c->plane_lo.as<float>());
     }
     ESPER_CUDA(c, cudaGetLastError());

@@ -11,10 +11,12 @@ sys.path.insert(0, ROOT)
 from manifoldem_esper_b200 import GaussianBandwidth as GB, _capi, synth  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+mode = int(sys.argv[2]) if len(sys.argv) > 2 else 0        # esper_dmap_config: 0 latency (resident), 1 throughput (streamed)
 N, BOX = 2000, 250
 stack = synth.synthetic_pd(pd=1, box=BOX, n_side=20, tau=5, snr=0.1).reshape(N, BOX * BOX)
 ctx = _capi.Context(0)
 ctx.upload_images(stack); ctx.sync()
+ctx.dmap_config(mode)
 logEps = np.arange(-100, 100.2, 0.2)
 coef = 1. / (2. * np.exp(logEps))
 a0 = np.array([[-0.2], [0.3], [-0.4], [0.1]])
