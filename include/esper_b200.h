@@ -83,8 +83,8 @@ int esper_dist_rms(esper_ctx* ctx, const float* imgs, int n, int P, unsigned fla
 int esper_upload_images(esper_ctx* ctx, const float* imgs, int n, int P);
 /* Tuning knobs of stage 1 (defaults in parentheses): split_k = number of K chunks whose FP32
  * partial Grams are combined in FP64 (0 = auto: chunks of ~2048 pixels, rounded so the work
- * units fill the SMs); refine_tau (0.5: pairs with D^2*P < 0.5(|x|^2+|y|^2), i.e. correlated images, where the
- * measured round-toward-zero bias of tensor-core FP32 accumulation would exceed 1e-5). */
+ * units fill the SMs); refine_tau (0.05: pairs with D^2*P < 0.05(|x|^2+|y|^2), i.e. near-duplicate images, where
+ * Gram cancellation would exceed 1e-5; calibrated with tools/calib_gram_error.py). */
 int esper_dist_config(esper_ctx* ctx, int split_k, double refine_tau);
 /* Upload a distance matrix so that stages 2/3 can use it as the resident D. */
 int esper_upload_dist(esper_ctx* ctx, const double* D, int m);

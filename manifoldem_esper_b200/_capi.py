@@ -154,7 +154,7 @@ class Context:
         return int(self._lib.esper_stat(self._h, name.encode()))
 
     # -- stage 1 ----------------------------------------------------------------------------
-    def dist_config(self, split_k=0, refine_tau=0.5):
+    def dist_config(self, split_k=0, refine_tau=0.05):
         self._check(self._lib.esper_dist_config(self._h, int(split_k), float(refine_tau)))
 
     def upload_images(self, imgs):

@@ -74,7 +74,8 @@ struct esper_ctx {
     int lanczos_fallbacks = 0;                                 // PRO runs repeated with full reorthogonalisation
     // stage-1 configuration
     int split_k = 0;
-    double refine_tau = 0.5;
+    int drain_kb = 2;                                          // k-blocks (of 32 pixels) per tensor-core accumulation chain
+    double refine_tau = 0.05;
 
     // resident data
     esper::DevBuf imgs;     int img_n = 0, img_P = 0;          // raw float32 stack [n, P]

@@ -139,7 +139,7 @@ __device__ __forceinline__ void tile_map(int t, int nt, int rect_ti0, int& ta, i
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gram_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
-            int nt, int n_tiles, int tile0, int rect_ti0, int nkb, int split_k, float* __restrict__ part) {
+            int nt, int n_tiles, int tile0, int rect_ti0, int nkb, int split_k, int drain_kb, float* __restrict__ part) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // 1024-byte aligned operand ring
     const uint32_t bars = base + STAGES * STAGE_BYTES;
@@ -207,32 +207,39 @@ gram_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
                 const bool diag = (ti == tj);
                 const int kb0 = (int)((long long)nkb * chunk / split_k);
                 const int kb1 = (int)((long long)nkb * (chunk + 1) / split_k);
-                mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * BN;
-                uint32_t accumulate = 0;
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(full_bar + 8 * stage, phase);
+                // Tensor-core FP32 accumulation rounds toward zero, which biases a long chain in proportion to the
+                // accumulated magnitude (i.e. to the signal).  The chain is therefore cut every `drain_kb` k-blocks:
+                // the accumulator buffer is handed to the epilogue warps, which add it in round-to-nearest FP32 into
+                // register accumulators while the next group runs in the other TMEM buffer.
+                for (int g0 = kb0; g0 < kb1; g0 += drain_kb) {
+                    const int g1 = min(g0 + drain_kb, kb1);
+                    mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
                     tc_fence_after();
-                    const uint32_t sa = base + stage * STAGE_BYTES;
-                    const uint32_t a_hi = sa, a_lo = sa + TILE_BYTES;
-                    const uint32_t b_hi = diag ? a_hi : sa + 2 * TILE_BYTES;
-                    const uint32_t b_lo = diag ? a_lo : sa + 3 * TILE_BYTES;
+                    const uint32_t tmem_d = tmem_base + acc * BN;
+                    uint32_t accumulate = 0;
+                    for (int kb = g0; kb < g1; ++kb) {
+                        mbar_wait(full_bar + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint32_t sa = base + stage * STAGE_BYTES;
+                        const uint32_t a_hi = sa, a_lo = sa + TILE_BYTES;
+                        const uint32_t b_hi = diag ? a_hi : sa + 2 * TILE_BYTES;
+                        const uint32_t b_lo = diag ? a_lo : sa + 3 * TILE_BYTES;
 #pragma unroll
-                    for (int k = 0; k < BK / UK; ++k) {
-                        const uint32_t off = k * UK * 4;   // 32 bytes per UMMA K step inside the swizzle row
-                        const uint64_t dah = make_smem_desc(a_hi + off), dal = make_smem_desc(a_lo + off);
-                        const uint64_t dbh = make_smem_desc(b_hi + off), dbl = make_smem_desc(b_lo + off);
-                        umma_tf32(tmem_d, dal, dbh, accumulate);   // small cross terms first
-                        umma_tf32(tmem_d, dah, dbl, 1);
-                        umma_tf32(tmem_d, dah, dbh, 1);
-                        accumulate = 1;
+                        for (int k = 0; k < BK / UK; ++k) {
+                            const uint32_t off = k * UK * 4;   // 32 bytes per UMMA K step inside the swizzle row
+                            const uint64_t dah = make_smem_desc(a_hi + off), dal = make_smem_desc(a_lo + off);
+                            const uint64_t dbh = make_smem_desc(b_hi + off), dbl = make_smem_desc(b_lo + off);
+                            umma_tf32(tmem_d, dal, dbh, accumulate);   // small cross terms first
+                            umma_tf32(tmem_d, dah, dbl, 1);
+                            umma_tf32(tmem_d, dah, dbh, 1);
+                            accumulate = 1;
+                        }
+                        umma_commit(empty_bar + 8 * stage);            // frees the smem stage when the MMAs retire
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(empty_bar + 8 * stage);            // frees the smem stage when the MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    umma_commit(tfull_bar + 8 * acc);                  // group complete -> epilogue drains it
+                    if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
                 }
-                umma_commit(tfull_bar + 8 * acc);                  // accumulator complete -> epilogue
-                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
@@ -240,26 +247,35 @@ gram_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
         const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
         const int row = quad * 32 + lane;          // tile row held by this thread
         int acc = 0; uint32_t acc_phase = 0;
-        for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-            mbar_wait(tfull_bar + 8 * acc, acc_phase);
-            tc_fence_after();
-            float4* out = reinterpret_cast<float4*>(part + (size_t)u * (BM * BN));
-#pragma unroll 1
-            for (int cc = 0; cc < BN / 32; ++cc) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + cc * 32), r);
-                tmem_ld_wait();
+        float sum[BN];                              // round-to-nearest FP32 accumulators of this thread's tile row
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                           __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-                    out[(size_t)(cc * 8 + q) * BM + row] = v;
+        for (int q = 0; q < BN; ++q) sum[q] = 0.f;
+        for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+            const int chunk = u / n_tiles;
+            const int kb0 = (int)((long long)nkb * chunk / split_k);
+            const int kb1 = (int)((long long)nkb * (chunk + 1) / split_k);
+            for (int g0 = kb0; g0 < kb1; g0 += drain_kb) {
+                mbar_wait(tfull_bar + 8 * acc, acc_phase);
+                tc_fence_after();
+#pragma unroll
+                for (int cc = 0; cc < BN / 32; ++cc) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + cc * 32), r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) sum[cc * 32 + q] = __fadd_rn(sum[cc * 32 + q], __uint_as_float(r[q]));
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
-            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+            float4* out = reinterpret_cast<float4*>(part + (size_t)u * (BM * BN));
+#pragma unroll
+            for (int q4 = 0; q4 < BN / 4; ++q4) {
+                out[(size_t)q4 * BM + row] = make_float4(sum[4 * q4], sum[4 * q4 + 1], sum[4 * q4 + 2], sum[4 * q4 + 3]);
+                sum[4 * q4] = 0.f; sum[4 * q4 + 1] = 0.f; sum[4 * q4 + 2] = 0.f; sum[4 * q4 + 3] = 0.f;
+            }
         }
     }
 
@@ -450,6 +466,8 @@ int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, i
     ESPER_RESERVE(c, c->gram_part, (size_t)batch * split_k * tile_bytes);
     float* part = c->gram_part.as<float>();
 
+    int drain_kb = c->drain_kb > 0 ? c->drain_kb : 2;
+    if (const char* e = getenv("ESPER_DRAIN_KB")) { const int v = atoi(e); if (v > 0) drain_kb = v; }   // experiments only
     for (int tile0 = 0; tile0 < tiles_total; tile0 += batch) {
         const int nb = (tiles_total - tile0 < batch) ? tiles_total - tile0 : batch;
         int sk = choose_split_k(c->split_k, nkb, nb, sms);
@@ -458,7 +476,7 @@ int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, i
         const int grid = units < sms ? units : sms;
         {
             LaunchScope ls(c, "gram");
-            gram_kernel<<<grid, NUM_THREADS, SMEM_BYTES, c->stream>>>(map_hi, map_lo, nt, nb, tile0, rect_ti0, nkb, sk, part);
+            gram_kernel<<<grid, NUM_THREADS, SMEM_BYTES, c->stream>>>(map_hi, map_lo, nt, nb, tile0, rect_ti0, nkb, sk, drain_kb, part);
         }
         {
             LaunchScope ls(c, "dist_finalize");

@@ -215,6 +215,36 @@ def test_embed_end_to_end_matches_reference_run(ctx):
         assert vec_err(res['vec'][:, i], U_r[:, i]) < 1e-3
 
 
+def test_full_size_pipeline_vs_oracle(ctx):
+    """BASELINE config 2 end to end on the GPU (stack -> distances -> sweep -> embedding) against the oracle run on
+    the same stack, at the north-star tolerances: D 1e-5, sweep 1e-9, eigenvalues 1e-6 and eigenvectors 1e-4 at
+    identical epsilon (the separated ones per vector, the bulk-edge cluster as a subspace)."""
+    stack = synth.synthetic_pd(pd=7, box=250, n_side=20, tau=5, snr=0.1)
+    D_ref = O.distances_gram_f64(O.standardize_stack(stack))
+    D = ctx.dist_rms(stack)
+    assert d_err(D, D_ref) < D_TOL
+    L = GaussianBandwidth.sweep(None, LOG_EPS, ctx=ctx, m=2000)               # on the resident GPU matrix
+    L_ref = O.eps_sweep_logsum(D_ref, LOG_EPS, sequential=False)
+    assert np.max(np.abs(L - L_ref)) < 1e-6                                   # carries the 2e-7 distance error
+    a0 = np.array([[-0.2], [0.3], [-0.4], [0.1]])
+    popt, _, _ = GaussianBandwidth.fit(LOG_EPS, L_ref, a0)
+    eps = float(np.exp(-(popt[1] / popt[0])))
+    val_r, U_r = O.dmap_embed(D_ref, eps)
+    k = 10
+    val, vec, iters = ctx.dmap_embed(None, eps, k=k, m=2000)                  # GPU distances -> GPU embedding
+    assert np.max(np.abs(val - val_r[:k]) / val_r[:k]) < VAL_TOL
+    lam = np.sqrt(val_r[:k + 1])
+    for i in range(k):
+        gap = min(abs(lam[i] - lam[i - 1]) if i else 1.0, abs(lam[i] - lam[i + 1]))
+        if gap > 2e-3 * lam[1]:
+            assert vec_err(vec[:, i], U_r[:, i]) < VEC_TOL, i
+    sep = [i for i in range(k) if min(abs(lam[i] - lam[i - 1]) if i else 1.0, abs(lam[i] - lam[i + 1])) > 2e-3 * lam[1]]
+    assert len(sep) >= 5                                                      # steady state + the signal eigenvectors
+    # the whole leading block as a subspace (principal angles) unless the cut falls inside a cluster
+    s_ = np.linalg.svd(vec.T @ U_r[:, :k], compute_uv=False)
+    assert s_.min() > 1 - 1e-6 or lam[k - 1] - lam[k] < 2e-3 * lam[1]
+
+
 def test_eigensolver_modes_agree(ctx):
     """Latency mode (Ms resident on chip) and throughput mode (streamed, two grids per SM) run the same algorithm."""
     g = golden('stage23_medium.npz')
