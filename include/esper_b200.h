@@ -117,6 +117,19 @@ int esper_dmap_config(esper_ctx* ctx, int mode);
 int esper_dmap_embed(esper_ctx* ctx, const double* D, int m, double eps, int k, double tol,
                      int max_iter, double* val, double* vec, int* iters);
 
+/* ---- PCA embedding (1_Embedding/PCA/PCA.py:49-71) ---------------------------------
+ * Y [P, n] = the raw images as columns (PCA.py:49-51, no per-image standardisation), minus the mean image
+ * over the stack (PCA.py:53-55); the reference takes the SVD Y = u s v^T (PCA.py:58) and saves s^2 and the
+ * scores Y^T u[:, :dim] = v[:, :dim] s (PCA.py:66-68).  Here the leading k eigenpairs (s^2, v) of the n x n
+ * Gram matrix Y^T Y are computed with the stage-1 tensor-core Gram kernel and the stage-3 Lanczos solver
+ * (the constant vector, eigenvalue 0 after centring, is locked out), so 1 <= k <= n-1.
+ *   val [k]    = s^2 descending (the reference saves all n)
+ *   U   [n, k] = scores, row-major; column sign: the entry of largest |.| is positive (the reference's sign is
+ *                whatever LAPACK returns)
+ * imgs == NULL: use the resident stack. */
+int esper_pca_embed(esper_ctx* ctx, const float* imgs, int n, int P, int k, double tol, int max_iter,
+                    double* val, double* U, int* iters);
+
 /* ---- oversized PD: distance-matrix row blocks (BASELINE config 4) ------------------
  * One PD too large for one GPU is split by row blocks of D / A / Ms: rank g owns rows [row0, row0+nrows)
  * (row0 a multiple of 128).  The same reference arithmetic as above (Distances.py:87-104,

@@ -47,6 +47,8 @@ SIGNATURES = {
     'esper_dmap_config': (C.c_int, [C.c_void_p, C.c_int]),
     'esper_dmap_embed': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int,
                                    C.c_void_p, C.c_void_p, _i32p]),
+    'esper_pca_embed': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
+                                  C.c_void_p, C.c_void_p, _i32p]),
     'esper_dist_rms_rows': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int, C.c_void_p]),
     'esper_eps_sweep_rows': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
     'esper_degree_rows': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]),
@@ -226,6 +228,21 @@ class Context:
         self._check(self._lib.esper_dmap_embed(self._h, _ptr(D), int(m), float(eps), k, float(tol), int(max_iter),
                                                _ptr(val), _ptr(vec), C.byref(it)))
         return val, vec, it.value
+
+    def pca_embed(self, imgs, k=20, tol=0.0, max_iter=0, n=None, P=None):
+        """PCA.py:49-71 -> (val[k] = s^2 descending, U[n, k] = scores v s, lanczos steps)."""
+        if imgs is not None:
+            imgs = _check_stack(imgs)
+            n, P = imgs.shape
+        if n is None or P is None:
+            raise ValueError('pca_embed: n and P are required when imgs is None')
+        k = int(k)
+        val = np.empty(max(k, 1), dtype=np.float64)
+        U = np.empty((n, max(k, 1)), dtype=np.float64)
+        it = C.c_int(0)
+        self._check(self._lib.esper_pca_embed(self._h, _ptr(imgs), int(n), int(P), k, float(tol), int(max_iter),
+                                              _ptr(val), _ptr(U), C.byref(it)))
+        return val, U, it.value
 
     # -- oversized-PD row-block path (device pointers are plain ints, e.g. torch.Tensor.data_ptr()) ----
     def dist_rms_rows(self, imgs, n, P, row0, nrows, flags=DIST_DEFAULT, download=False):

@@ -239,6 +239,46 @@ int esper_dmap_embed(esper_ctx* c, const double* D, int m, double eps, int k, do
     return run_lanczos(c, m, k, tol, max_iter, val, vec, iters);
 }
 
+// ---- PCA embedding -----------------------------------------------------------------
+__global__ void fill_ones_kernel(double* x, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = 1.0;
+}
+
+int esper_pca_embed(esper_ctx* c, const float* imgs, int n, int P, int k, double tol, int max_iter,
+                    double* val, double* U, int* iters) {
+    ESPER_ENTER(c);
+    if (n < 2 || P < 1) return fail(c, ESPER_E_ARG, "pca_embed: need n >= 2 and P >= 1 (got n=%d, P=%d)", n, P);
+    if (k < 1 || k > n - 1) return fail(c, ESPER_E_ARG, "pca_embed: need 1 <= k <= n-1 (the centred stack has rank <= n-1; k=%d, n=%d)", k, n);
+    if (imgs) {
+        int rc = esper_upload_images(c, imgs, n, P);
+        if (rc) return rc;
+    } else if (c->img_n != n || c->img_P != P || !c->imgs.p) {
+        return fail(c, ESPER_E_STATE, "pca_embed: imgs == NULL but no resident [%d, %d] stack", n, P);
+    }
+    const int rows_pad = (int)round_up((size_t)n, 128);
+    const int ld = (int)round_up((size_t)P, 32);
+    ESPER_RESERVE(c, c->markov, sizeof(double) * (size_t)n * n);
+    ESPER_RESERVE(c, c->degree, sizeof(double) * (size_t)n);
+    c->dist_m = 0;                                         // the plane buffers are reused: no distance matrix is resident
+    int rc = run_prep(c, n, P, ESPER_DIST_CENTER, rows_pad, ld, /*exact_center=*/true);
+    if (rc) return rc;
+    rc = run_gram(c, n, P, rows_pad, ld, 0, -1, 0, c->markov.as<double>());
+    if (rc) return rc;
+    // the mean image was subtracted, so G 1 = 0: lock the constant vector (sqrt of an all-ones "degree")
+    fill_ones_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->degree.as<double>(), n);
+    c->launches++;
+    ESPER_CUDA(c, cudaGetLastError());
+    rc = run_lanczos(c, n, k, tol, max_iter, val, U, iters, /*plain=*/true);
+    if (rc) return rc;
+    if (U && val)                                          // scores Y^T W = V S (PCA.py:68): scale unit eigenvectors by the singular value
+        for (int j = 0; j < k; ++j) {
+            const double sv = val[j] > 0.0 ? sqrt(val[j]) : 0.0;
+            for (int i = 0; i < n; ++i) U[(size_t)i * k + j] *= sv;
+        }
+    return ESPER_OK;
+}
+
 // ---- oversized-PD row-block path ----------------------------------------------------------------
 int esper_dist_rms_rows(esper_ctx* c, const float* imgs, int n, int P, unsigned flags, int row0, int nrows, double* D_rows) {
     ESPER_ENTER(c);

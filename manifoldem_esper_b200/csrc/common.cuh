@@ -153,8 +153,8 @@ inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
 // ---- per-stage entry points implemented in the .cu files (host side) ----
 int prep_and_gram(esper_ctx* c, int n, int P, unsigned flags);                 // k0_prep.cu + k1_gram.cu
-int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld);
-int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, int row0 = -1, int nrows = 0);
+int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld, bool exact_center = false);
+int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, int row0 = -1, int nrows = 0, double* gram_out = nullptr);
 int run_sweep(esper_ctx* c, int m, const double* coef_h, int n_eps, double thr, double* logsum_h);
 int run_sweep_rows(esper_ctx* c, int rows, int m, const double* coef_h, int n_eps, double thr, double* out_h, int take_log);
 int run_markov_rows(esper_ctx* c, int rows, int m, int row0, double eps, const double* degree_all_h, double* degree_rows_h, int phase);
@@ -162,7 +162,7 @@ bool ritz_converged(const std::vector<double>& a, const std::vector<double>& b, 
                     std::vector<double>& theta, std::vector<double>& S);
 int check_symmetry(esper_ctx* c, int m);
 int run_markov(esper_ctx* c, int m, double eps);
-int run_lanczos(esper_ctx* c, int m, int k, double tol, int max_iter, double* val_h, double* vec_h, int* iters);
+int run_lanczos(esper_ctx* c, int m, int k, double tol, int max_iter, double* val_h, double* vec_h, int* iters, bool plain = false);
 int run_rot_eval(esper_ctx* c, const double* Uinit, int n_pd, int m, int dim, const double* R,
                  const int* pd_of_eval, const int* v1, const int* v2, int n_eval, int bins,
                  double lo, double hi, int* nonzero, int* H);

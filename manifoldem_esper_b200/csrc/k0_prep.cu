@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(512) stats_split_kernel(const float* __restric
     if (threadIdx.x == 0) { st[i].mean = m; st[i].stdv = sd; st[i].norm2 = acc; }
 }
 
-int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld) {
+int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld, bool exact_center) {
     const float* raw = c->imgs.as<float>();
     ESPER_RESERVE(c, c->row_stats, sizeof(RowStat) * (size_t)rows_pad);
     ESPER_RESERVE(c, c->plane_hi, sizeof(float) * (size_t)rows_pad * ld);
@@ -148,7 +148,9 @@ int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld) {
     const int center = (flags & ESPER_DIST_CENTER) ? 1 : 0;
     float* xbar = nullptr;
     if (center) {
-        const int stride = n > 256 ? n / 256 : 1;                  // centring subset: images 0, stride, 2*stride, ...
+        // distances: any common image may be subtracted, a subset mean (images 0, stride, 2*stride, ...) serves;
+        // PCA (PCA.py:53-55) needs the mean over all images
+        const int stride = (!exact_center && n > 256) ? n / 256 : 1;
         const int n_sub = (n + stride - 1) / stride;
         const int groups = n_sub >= 16 ? 16 : 1;
         ESPER_RESERVE(c, c->col_part, sizeof(double) * (size_t)(groups + 1) * P);

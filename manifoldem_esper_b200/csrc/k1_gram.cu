@@ -332,6 +332,36 @@ dist_finalize_kernel(const float* __restrict__ part, int nt, int n_tiles, int ti
     }
 }
 
+// Gram epilogue of the PCA path (PCA.py:58: the right singular vectors of Y are the eigenvectors of Y^T Y):
+// G_ij = sum_chunks partial, mirrored; the diagonal is the FP64 |c_i|^2 of the prep pass.
+__global__ void __launch_bounds__(256)
+gram_finalize_kernel(const float* __restrict__ part, int nt, int n_tiles, int tile0, int split_k, int n,
+                     const RowStat* __restrict__ st, double* __restrict__ G) {
+    const int lt = blockIdx.x;
+    const int e_per = (BM * (BN / 4)) / gridDim.y;
+    int ti, tj; bool transposed; tile_map(tile0 + lt, nt, -1, ti, tj, transposed);
+    const bool diag = (ti == tj);
+    for (int e = blockIdx.y * e_per + threadIdx.x; e < (blockIdx.y + 1) * e_per; e += blockDim.x) {
+        const int r = e & (BM - 1), c4 = e >> 7;
+        const int i = ti * BM + r;
+        if (i >= n) continue;
+        double g[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int ch = 0; ch < split_k; ++ch) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(part + (size_t)(ch * n_tiles + lt) * (BM * BN)) + e);
+            g[0] += (double)v.x; g[1] += (double)v.y; g[2] += (double)v.z; g[3] += (double)v.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = c4 * 4 + q;
+            const int j = tj * BN + c;
+            if (j >= n) continue;
+            if (diag && c <= r) { if (c == r) G[(size_t)i * n + i] = st[i].norm2; continue; }
+            G[(size_t)i * n + j] = g[q];
+            G[(size_t)j * n + i] = g[q];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Refinement of cancelling pairs by direct differences (the reference's own arithmetic:
 // float64 sum of squared differences of the float32 standardised images).
@@ -430,7 +460,7 @@ static int choose_split_k(int requested, int nkb, int n_tiles, int sms) {
     return best < 1 ? 1 : best;
 }
 
-int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, int row0, int nrows) {
+int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, int row0, int nrows, double* gram_out) {
     using namespace gram;
     // row0 < 0: full symmetric matrix (upper triangle of tiles); else the row block [row0, row0+nrows) x [0, n)
     const int nt = rows_pad / BM;
@@ -480,12 +510,13 @@ int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, i
         }
         {
             LaunchScope ls(c, "dist_finalize");
-            dist_finalize_kernel<<<dim3(nb, 8), 256, 0, c->stream>>>(part, nt, nb, tile0, rect_ti0, sk, n, P, st, D);
+            if (gram_out) gram_finalize_kernel<<<dim3(nb, 8), 256, 0, c->stream>>>(part, nt, nb, tile0, sk, n, st, gram_out);
+            else dist_finalize_kernel<<<dim3(nb, 8), 256, 0, c->stream>>>(part, nt, nb, tile0, rect_ti0, sk, n, P, st, D);
         }
     }
     ESPER_CUDA(c, cudaGetLastError());
 
-    if ((flags & ESPER_DIST_REFINE) && c->refine_tau > 0.0 && n > 1) {
+    if (!gram_out && (flags & ESPER_DIST_REFINE) && c->refine_tau > 0.0 && n > 1) {
         const size_t max_pairs = rect ? (size_t)nrows * n : (size_t)n * (n - 1) / 2;
         const unsigned int cap = (unsigned int)(max_pairs < ((size_t)1 << 26) ? max_pairs : (size_t)1 << 26);
         ESPER_RESERVE(c, c->pair_list, sizeof(int2) * (size_t)cap + 256);

@@ -1078,7 +1078,7 @@ bool ritz_converged(const std::vector<double>& a, const std::vector<double>& b, 
 }
 
 static int lanczos_attempt(esper_ctx* c, int m, int k, double tol, int max_iter, bool use_pro, double* val_h, double* vec_h,
-                           int* iters_out, bool* suspicious) {
+                           int* iters_out, bool* suspicious, bool plain) {
     using namespace lanczos;
     constexpr int KMAX = 64;
     const int kw = k - 1;                               // non-trivial pairs wanted
@@ -1283,6 +1283,15 @@ static int lanczos_attempt(esper_ctx* c, int m, int k, double tol, int max_iter,
         }
     }
     ESPER_CUDA(c, cudaGetLastError());
+    if (plain) {
+        // general symmetric matrix with a known (locked) eigenvector: return the kw Ritz pairs only
+        if (vec_h && kw > 0)
+            ESPER_CUDA(c, cudaMemcpy2DAsync(vec_h, sizeof(double) * kw, U + 1, sizeof(double) * k, sizeof(double) * kw, m,
+                                            cudaMemcpyDeviceToHost, st));
+        ESPER_CUDA(c, cudaStreamSynchronize(st));
+        if (val_h) for (int i = 0; i < kw; ++i) val_h[i] = theta[i];
+        return ESPER_OK;
+    }
     if (vec_h) ESPER_CUDA(c, cudaMemcpyAsync(vec_h, U, sizeof(double) * (size_t)m * k, cudaMemcpyDeviceToHost, st));
     ESPER_CUDA(c, cudaStreamSynchronize(st));
     if (val_h) {
@@ -1292,9 +1301,15 @@ static int lanczos_attempt(esper_ctx* c, int m, int k, double tol, int max_iter,
     return ESPER_OK;
 }
 
-int run_lanczos(esper_ctx* c, int m, int k, double tol, int max_iter, double* val_h, double* vec_h, int* iters_out) {
+int run_lanczos(esper_ctx* c, int m, int k, double tol, int max_iter, double* val_h, double* vec_h, int* iters_out, bool plain) {
     using namespace lanczos;
     constexpr int KMAX = 64;
+    // plain: c->markov holds any symmetric matrix and sqrt(c->degree) a known eigenvector that is locked out;
+    // k counts the pairs wanted besides it (internally the locked vector is column 0, as in the diffusion-map case)
+    if (plain) {
+        if (k < 1 || k > m - 1 || k + 1 > KMAX) return fail(c, ESPER_E_ARG, "k=%d out of range (1..min(m-1,%d))", k, KMAX - 1);
+        k += 1;
+    }
     if (k < 1 || k > m || k > KMAX) return fail(c, ESPER_E_ARG, "k=%d out of range (1..min(m,%d))", k, KMAX);
     if (tol <= 0.0) tol = 1e-10;
     if (max_iter <= 0) max_iter = 1024;
@@ -1305,10 +1320,11 @@ int run_lanczos(esper_ctx* c, int m, int k, double tol, int max_iter, double* va
     // 20 % shorter solve -- not worth the accuracy.  A PRO run whose independent checks fail is repeated.
     bool use_pro = getenv("ESPER_LANCZOS_PRO") && (m <= PRO_MAX_M) && (max_iter + 4 <= 2048);
     bool suspicious = false;
-    int rc = lanczos_attempt(c, m, k, tol, max_iter, use_pro, val_h, vec_h, iters_out, &suspicious);
+    if (plain) use_pro = false;
+    int rc = lanczos_attempt(c, m, k, tol, max_iter, use_pro, val_h, vec_h, iters_out, &suspicious, plain);
     if (use_pro && (suspicious || rc == ESPER_E_NOCONV)) {
         c->lanczos_fallbacks++;
-        rc = lanczos_attempt(c, m, k, tol, max_iter, false, val_h, vec_h, iters_out, &suspicious);
+        rc = lanczos_attempt(c, m, k, tol, max_iter, false, val_h, vec_h, iters_out, &suspicious, plain);
     }
     return rc;
 }

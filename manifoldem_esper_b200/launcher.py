@@ -76,10 +76,11 @@ def run_sharded(pds, work_fn, rank=0, world=1, gather=None):
 
 
 def _stage_fns(root, stages, dim, pca, k, skip_existing, device):
-    from . import Distances, DiffusionMaps, Rotation_Histograms, _capi
+    from . import PCA, Distances, DiffusionMaps, Rotation_Histograms, _capi
     ctx = _capi.Context(device)
     dm_dir = os.path.join(root, '1_Embedding', 'DM')
     rot_dir = os.path.join(root, '2_Manifold_Rotations')
+    pca_dir = os.path.join(root, '1_Embedding', 'PCA')
 
     def work(pd):
         info = {}
@@ -91,6 +92,10 @@ def _stage_fns(root, stages, dim, pca, k, skip_existing, device):
             out = os.path.join(dm_dir, 'Data_Manifolds', 'PD_%s_vec.npy' % pd)
             if not (skip_existing and os.path.exists(out)):
                 t = time.time(); DiffusionMaps.op(dm_dir, pd, k=k, ctx=ctx); info['dm_s'] = time.time() - t
+        if 'pca' in stages:
+            out = os.path.join(pca_dir, 'Data_Manifolds', 'PD_%s_vec.npy' % pd)
+            if not (skip_existing and os.path.exists(out)):
+                t = time.time(); PCA.op(pca_dir, pd, ctx=ctx); info['pca_s'] = time.time() - t
         if 'rot' in stages:
             out = os.path.join(rot_dir, 'Data_Rotations', 'PD%s' % pd, 'PD%s_RotMatrices.npy' % (pd,))
             if not (skip_existing and os.path.exists(out)):
@@ -103,7 +108,7 @@ def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__.split('\n')[0])
     ap.add_argument('--root', required=True)
     ap.add_argument('--pds', default='1-126')
-    ap.add_argument('--stages', default='dist,dm,rot')
+    ap.add_argument('--stages', default='dist,dm,rot', help='comma list of dist, dm, pca, rot')
     ap.add_argument('--dim', type=int, default=6)
     ap.add_argument('--pca', action='store_true')
     ap.add_argument('-k', type=int, default=16)

@@ -221,6 +221,27 @@ def diffusion_maps_op(Dist: np.ndarray, seed: int | None = None):
                 ln_eps=ln_eps, eps=eps, val=val, vec=U)
 
 
+# ---------------------------------------------------------------------------------------------
+# PCA embedding (1_Embedding/PCA/PCA.py:33-71) -- SURVEY 8f-2
+# ---------------------------------------------------------------------------------------------
+def pca_op(stack_f32: np.ndarray, dim: int = 20):
+    """PCA.py:46-68: Y [P, N] raw pixels as columns, minus the mean image; SVD; returns (eig_vals [N] = s^2,
+    U [N, dim] = Y^T u[:, :dim])."""
+    N = stack_f32.shape[0]
+    P = int(np.prod(stack_f32.shape[1:]))
+    Y = np.ndarray(shape=(P, N), dtype=float)                     # PCA.py:49
+    for i in range(N):
+        Y[:, i] = stack_f32[i].flatten()                          # PCA.py:50-51
+    mean_all = np.mean(Y, axis=1)                                 # PCA.py:53
+    for i in range(N):
+        Y[:, i] -= mean_all                                       # PCA.py:54-55
+    u, s, v = np.linalg.svd(Y, full_matrices=False)               # PCA.py:58
+    eig_vals = s ** 2                                             # PCA.py:60
+    W = np.hstack([u[:, i].reshape(P, 1) for i in range(dim)])    # PCA.py:66
+    U = Y.T.dot(W)                                                # PCA.py:67
+    return eig_vals, U
+
+
 # --------------------------------------------------------------------------------------
 # Stage 4 -- 2_Manifold_Rotations/Generate_Nd_Rot.py, Rotation_Histograms.py
 # --------------------------------------------------------------------------------------

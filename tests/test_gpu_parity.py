@@ -8,8 +8,8 @@ import numpy as np
 import pytest
 
 from conftest import golden
-from manifoldem_esper_b200 import (DiffusionMaps, Distances, GaussianBandwidth, Rotation_Histograms as RH, _capi, mrc,
-                                   synth)
+from manifoldem_esper_b200 import (PCA, DiffusionMaps, Distances, GaussianBandwidth, Rotation_Histograms as RH, _capi,
+                                   mrc, synth)
 from oracle import esper_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -243,6 +243,65 @@ def test_full_size_pipeline_vs_oracle(ctx):
     # the whole leading block as a subspace (principal angles) unless the cut falls inside a cluster
     s_ = np.linalg.svd(vec.T @ U_r[:, :k], compute_uv=False)
     assert s_.min() > 1 - 1e-6 or lam[k - 1] - lam[k] < 2e-3 * lam[1]
+
+
+# ---- PCA embedding ----------------------------------------------------------------
+PCA_FLOOR = 2e-8      # FP32 pixels and 3xTF32 products: absolute accuracy of an eigenvalue ~1e-8 of the largest one
+
+
+def pca_check(val, U, val_r, U_r, k, min_sep=3):
+    """Eigenvalues 1e-6 relative (plus the absolute floor, which only matters for the rank-deficient noise-free
+    stack whose trailing reference eigenvalues are rounding noise); separated eigenvectors 1e-4 up to sign."""
+    assert np.all(np.abs(val - val_r[:k]) <= VAL_TOL * val_r[:k] + PCA_FLOOR * val_r[0])
+    sep = 0
+    for i in range(k):
+        gap = min(val_r[i - 1] - val_r[i] if i else np.inf, val_r[i] - val_r[i + 1])
+        if gap > 1e-2 * val_r[i] and gap > 1e-3 * val_r[0]:
+            sep += 1
+            assert vec_err(U[:, i], U_r[:, i]) < VEC_TOL * np.abs(U_r[:, i]).max(), i
+    assert sep >= min_sep
+    # scores are v s: column norms reproduce the eigenvalues, columns sum to zero (centred data)
+    assert np.allclose(np.linalg.norm(U, axis=0) ** 2, val, rtol=1e-9)
+    assert np.abs(U.sum(axis=0)).max() < 1e-8 * np.abs(U).max()
+    # the significant leading block as a subspace
+    ks = int(np.sum(val_r[:k] > 1e-4 * val_r[0]))
+    while ks > 1 and val_r[ks - 1] - val_r[ks] < 1e-2 * val_r[ks - 1]:
+        ks -= 1
+    s_ = np.linalg.svd((U[:, :ks] / np.linalg.norm(U[:, :ks], axis=0)).T @ (U_r[:, :ks] / np.linalg.norm(U_r[:, :ks], axis=0)),
+                       compute_uv=False)
+    assert s_.min() > 1 - 1e-6
+
+
+@pytest.mark.parametrize('name', ['pca_pristine', 'pca_small'])
+def test_pca_vs_reference_golden(ctx, name):
+    g = golden(name + '.npz')
+    val, U, iters = PCA.embed(g['stack'], dim=20, ctx=ctx)
+    pca_check(val, U, g['val'], g['vec'], 20)
+
+
+def test_pca_medium_vs_oracle(ctx):
+    """N=800 images of 96x96 at SNR 0.1: signal components above a dense noise bulk."""
+    stack = synth.synthetic_pd(pd=4, box=96, n_side=20, tau=2, snr=0.1)
+    val_r, U_r = O.pca_op(stack, dim=21)
+    val, U, iters = PCA.embed(stack, dim=20, ctx=ctx)
+    pca_check(val, U, val_r, U_r, 20, min_sep=2)
+
+
+def test_pca_op_files_and_errors(ctx, tmp_path):
+    g = golden('pca_pristine.npz')
+    pdir = tmp_path / '1_Embedding' / 'PCA'
+    ddir = tmp_path / '0_Data_Inputs' / '_Pristine_2D'
+    pdir.mkdir(parents=True); ddir.mkdir(parents=True)
+    mrc.write_stack(str(ddir / 'PD_005.mrcs'), g['stack'])
+    PCA.op(str(pdir), '005')
+    val = np.load(str(pdir / 'Data_Manifolds' / 'PD_005_val.npy'))
+    vec = np.load(str(pdir / 'Data_Manifolds' / 'PD_005_vec.npy'))
+    assert val.shape == (20,) and vec.shape == (64, 20) and vec.dtype == np.float64
+    assert np.all(np.abs(val - g['val'][:20]) <= VAL_TOL * g['val'][:20] + PCA_FLOOR * g['val'][0])
+    with pytest.raises(ValueError):
+        PCA.embed(g['stack'][:10], dim=20, ctx=ctx)                           # rank of 10 centred images is 9
+    with pytest.raises(ValueError):
+        ctx.pca_embed(None, k=4, n=64, P=77)                                  # no resident stack of that shape
 
 
 def test_eigensolver_modes_agree(ctx):

@@ -73,7 +73,7 @@ def install_stubs():
 
 
 def patched_copy(ref, dst):
-    for d in ['1_Embedding/DM', '2_Manifold_Rotations', '3_Manifold_Binning']:
+    for d in ['1_Embedding/DM', '1_Embedding/PCA', '2_Manifold_Rotations', '3_Manifold_Binning']:
         shutil.copytree(os.path.join(ref, d), os.path.join(dst, d),
                         ignore=shutil.ignore_patterns('*.npy', '*.mp4'))
     os.makedirs(os.path.join(dst, '0_Data_Inputs'), exist_ok=True)
@@ -142,6 +142,20 @@ def stage123(root, mods, stack, pd, seed):
     return out
 
 
+def pca_golden(root, stack, pd):
+    """Reference 1_Embedding/PCA/PCA.py op() on a stack -> dict(stack, val [N], vec [N, 20])."""
+    from manifoldem_esper_b200 import mrc
+    ddir = os.path.join(root, '0_Data_Inputs', '_Pristine_2D')
+    os.makedirs(ddir, exist_ok=True)
+    mrc.write_stack(os.path.join(ddir, 'PD_%s.mrcs' % pd), stack)
+    pdir = os.path.join(root, '1_Embedding', 'PCA')
+    mod = import_from(os.path.join(pdir, 'PCA.py'), 'PCA')
+    run_quiet(mod.op, pdir, pd)
+    return dict(stack=stack,
+                val=np.load(os.path.join(pdir, 'Data_Manifolds', 'PD_%s_val.npy' % pd)),
+                vec=np.load(os.path.join(pdir, 'Data_Manifolds', 'PD_%s_vec.npy' % pd)))
+
+
 def rot_worker(args):
     root, ref, pd, dim, spy = args
     install_stubs()
@@ -185,6 +199,7 @@ def main():
     ap.add_argument('--jobs', type=int, default=8)
     ap.add_argument('--skip-rot', action='store_true')
     ap.add_argument('--only-rot', action='store_true')
+    ap.add_argument('--only-pca', action='store_true')
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     os.environ['PYTHONDONTWRITEBYTECODE'] = '1'
@@ -193,6 +208,16 @@ def main():
     patched_copy(args.ref, root)
     install_stubs()
     from manifoldem_esper_b200 import synth
+
+    if args.only_pca or not args.only_rot:
+        prist = synth.synthetic_pd(pd=5, box=32, n_side=8, tau=1, snr=None)           # N=64, raw pixel values
+        np.savez_compressed(os.path.join(GOLD, 'pca_pristine.npz'), **pca_golden(root, prist, '005'))
+        noisy = synth.synthetic_pd(pd=3, box=32, n_side=6, tau=3, snr=0.1)            # N=108
+        np.savez_compressed(os.path.join(GOLD, 'pca_small.npz'), **pca_golden(root, noisy, '003'))
+        print('pca done')
+    if args.only_pca:
+        shutil.rmtree(root, ignore_errors=True)
+        return
 
     if not args.only_rot:
         dm = os.path.join(root, '1_Embedding', 'DM')
