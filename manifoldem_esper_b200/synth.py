@@ -70,6 +70,34 @@ def synthetic_pd(pd: int = 1, box: int = 250, n_side: int = 20, tau: int = 5, sn
     return noisy_stack(pr, tau, snr, 1000 * pd if seed is None else seed)
 
 
+def ctf_stack(pd: int = 1, box: int = 250, n_side: int = 20, tau: int = 5, snr: float = 0.1, seed: int | None = None,
+              df_range=(5000, 15000), volt: float = 300., Cs: float = 2.7, ampc: float = 0.1, pix: float = 1.0):
+    """CTF-modulated noisy PD stack and its microscope parameters, following
+    0_Data_Inputs/Pristine_AddCtfSNR/GenStackAlign_CtfSnr.py:186-207: per image a random integer defocus in
+    [5000, 15000) A, image <- -ifft2(fft2(image) * CTF).real, Gaussian noise from the "signal" pixels
+    (|pixel| >= 1 std), background normalisation.  Returns (stack float32 [N, box, box],
+    params float64 [N, 5] = pixel size, Cs, defocus, voltage, amplitude contrast)."""
+    from . import Generate_Filters
+    pr = np.repeat(pristine_states(box, n_side, pd), tau, axis=0)
+    n = pr.shape[0]
+    rng = np.random.default_rng(1000 * pd + 7 if seed is None else seed)
+    bg = _background_mask(box)
+    out = np.empty((n, box, box), dtype=np.float32)
+    params = np.empty((n, 5), dtype=np.float64)
+    for i in range(n):
+        df = float(rng.integers(df_range[0], df_range[1]))
+        ctf = Generate_Filters.gen_ctf(box, pix, Cs, df, volt, np.inf, ampc)[0].astype(float)
+        img = -np.fft.ifft2(np.fft.fft2(pr[i].astype(np.float64)) * ctf).real
+        if snr is not None:
+            std = img.std()
+            sig = img[(img <= -std) | (img >= std)]
+            img = img + rng.normal(sig.mean(), np.sqrt(sig.var() / snr), (box, box))
+        b = img[bg]
+        out[i] = (img - b.mean()) / b.std()
+        params[i] = (pix, Cs, df, volt, ampc)
+    return out, params
+
+
 def random_manifold(m: int = 2000, ncol: int = 15, seed: int = 0) -> np.ndarray:
     """float64 [m, ncol] stand-in for a PD_xxx_vec.npy manifold (config 5 throughput shape):
     two parabolic pairs (psi_1, psi_2), (psi_3, psi_4) like a 2-CM diffusion map, mixed by a

@@ -222,6 +222,94 @@ def diffusion_maps_op(Dist: np.ndarray, seed: int | None = None):
 
 
 # ---------------------------------------------------------------------------------------------
+# Stage 1, CTF branch -- 1_Embedding/DM/Distances.py:107-145, Generate_Filters.py -- SURVEY 8f-1
+# ---------------------------------------------------------------------------------------------
+def ctf_grid(N: int) -> np.ndarray:
+    """Generate_Filters.py:25-32 (create_grid): radial frequency in units of Nyquist, centred."""
+    if N % 2 == 1:
+        a = np.arange(-(N - 1) / 2, (N - 1) / 2 + 1)
+    else:
+        a = np.arange(-(N / 2.), N / 2)
+    X, Y = np.meshgrid(a, a)
+    return (1. / (N / 2.)) * np.sqrt(X ** 2 + Y ** 2)
+
+
+def ctf_value(k, Cs_mm, df, kev, ampc):
+    """Generate_Filters.py:41-58 (op) with B = inf as at the call site Distances.py:121 (envelope = 1)."""
+    Cs = Cs_mm * 1.0e7
+    wav = (2 * 511.0) + kev
+    wav = 12.3986 / np.sqrt(wav * kev)
+    w1 = np.pi * Cs * wav * wav * wav
+    w2 = np.pi * wav * df
+    k2 = k * k
+    wr = (0.5 * w1 * k2 - w2) * k2
+    return (np.sin(wr) - ampc * np.cos(wr)) * np.exp(-k2 / np.inf)
+
+
+def ctf_filters(N, px, Cs_mm, df, kev, ampc):
+    """Generate_Filters.py:60-84 (gen_ctf): (CTF, Butterworth G), both ifftshift-ed to FFT order."""
+    Q = ctf_grid(N)
+    CTF = np.fft.ifftshift(ctf_value(Q / (2 * px), Cs_mm, df, kev, ampc))
+    G = np.fft.ifftshift(np.sqrt(1. / (1 + (Q / 0.5) ** (2 * 8))))
+    return CTF, G
+
+
+def distances_ctf_op(stack_f32: np.ndarray, params: np.ndarray):
+    """Distances.py:107-145: defocus-tolerant distances and the Wiener-filtered stack.
+
+    params [nS, 5] = (pixel size, Cs [mm], defocus [A], voltage [keV], amplitude contrast) per image
+    (the star-file columns read at Distances.py:68-72).  Returns (D [nS, nS] float64, wiener [nS, N, N] float32).
+    """
+    from scipy.fftpack import fft2, ifft2
+    nS, N, _ = stack_f32.shape
+    fy = complex(0) * np.ones((nS, N, N))
+    CTF = np.zeros((nS, N, N))
+    imgAll = np.zeros((nS, N, N))
+    for ii in range(nS):
+        tmp = stack_f32[ii]
+        tmp = (tmp - tmp.mean()) / tmp.std()                              # :114-115 (float32 arithmetic)
+        px, Cs, df, volt, ampc = params[ii]
+        CTF[ii], G = ctf_filters(N, px, Cs, df, volt, ampc)               # :118-119
+        image = ifft2(fft2(tmp.astype(np.float64)) * G).real               # :121-122 Butterworth low-pass
+        fy[ii] = fft2(image.T)                                             # :124-125 (column-major flatten = transpose)
+        imgAll[ii] = image                                                 # :126
+    wienerD = 0.
+    for i in range(nS):                                                    # gen_wiener :155-161, SNR = 5
+        wienerD = wienerD + CTF[i] ** 2
+    wienerD = -(wienerD + 1. / 5)                                          # :129
+    wiener = np.zeros((nS, N, N), dtype=np.float32)
+    for ii in range(nS):
+        wiener[ii] = ifft2(fft2(imgAll[ii]) * (CTF[ii] / wienerD)).real   # :130-135
+    fy = fy.reshape(nS, N ** 2)
+    C = CTF.reshape(nS, N ** 2)
+    CTFfy = C.conj() * fy                                                  # :141
+    D = np.dot((abs(C) ** 2), (abs(fy) ** 2).T)                           # :142
+    D = D + D.T - 2 * np.real(np.dot(CTFfy, CTFfy.conj().transpose()))     # :143
+    D -= np.diag(D)                                                        # :144 (row-broadcast of the diagonal)
+    with np.errstate(invalid='ignore'):
+        D = np.sqrt(D)                                                     # :145
+    return D, wiener
+
+
+def distances_ctf_direct(stack_f32: np.ndarray, params: np.ndarray) -> np.ndarray:
+    """The same quantity pair by pair without the Gram expansion: D_ij = |CTF_j fy_i - CTF_i fy_j| (cancellation-free
+    check of the expansion at Distances.py:142-143)."""
+    nS, N, _ = stack_f32.shape
+    F = np.zeros((nS, N, N), dtype=complex)
+    C = np.zeros((nS, N, N))
+    for ii in range(nS):
+        tmp = stack_f32[ii]
+        tmp = (tmp - tmp.mean()) / tmp.std()
+        C[ii], G = ctf_filters(N, *params[ii])
+        F[ii] = np.fft.fft2(tmp.astype(np.float64)) * G
+    D = np.zeros((nS, nS))
+    for i in range(nS):
+        for j in range(i + 1, nS):
+            D[i, j] = D[j, i] = np.sqrt(np.sum(np.abs(C[j] * F[i] - C[i] * F[j]) ** 2))
+    return D
+
+
+# ---------------------------------------------------------------------------------------------
 # PCA embedding (1_Embedding/PCA/PCA.py:33-71) -- SURVEY 8f-2
 # ---------------------------------------------------------------------------------------------
 def pca_op(stack_f32: np.ndarray, dim: int = 20):

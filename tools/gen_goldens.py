@@ -92,6 +92,11 @@ def patched_copy(ref, dst):
     sub('1_Embedding/DM/Distances.py', [
         ('CTF = True #if using', 'CTF = False #if using'),
         ("'0_Data_Inputs/CTF5k15k_SNRpt1_ELS_2D'", "'0_Data_Inputs/Synth'")])
+    # (4) CTF branch: a second copy of Distances.py with the shipped default `CTF = True` left as is (only the data
+    # directory is redirected); Read_Alignment opens the star file with mode 'rU', which Python >= 3.11 rejects
+    shutil.copy(os.path.join(ref, '1_Embedding/DM/Distances.py'), os.path.join(dst, '1_Embedding/DM/Distances_ctf.py'))
+    sub('1_Embedding/DM/Distances_ctf.py', [("'0_Data_Inputs/CTF5k15k_SNRpt1_ELS_2D'", "'0_Data_Inputs/SynthCTF'")])
+    sub('1_Embedding/DM/Read_Alignment.py', [("open(starfile, 'rU')", "open(starfile, 'r')")])
     sub('2_Manifold_Rotations/Rotation_Histograms.py', [
         ('groundTruth = True', 'groundTruth = False'),
         ('PCA = False', 'PCA = True'),
@@ -140,6 +145,26 @@ def stage123(root, mods, stack, pd, seed):
     out.update(seed=seed, a0=a0, popt=popt, logSumWij=logSum, R2=R2,
                eps=np.exp(-(popt[1] / popt[0])), val=val[:32], vec=vec[:, :32])
     return out
+
+
+def ctf_golden(root, stack, params, pd):
+    """Reference Distances.op with CTF = True on (stack, star file) -> dict(stack, params, D, wiener)."""
+    import warnings
+    from manifoldem_esper_b200 import mrc, Read_Alignment
+    ddir = os.path.join(root, '0_Data_Inputs', 'SynthCTF')
+    os.makedirs(ddir, exist_ok=True)
+    name = 'Hsp2D_5k15k_PD_%s' % pd
+    mrc.write_stack(os.path.join(ddir, name + '.mrcs'), stack)
+    Read_Alignment.write_star(os.path.join(ddir, name + '.star'), params[:, 2], volt=params[:, 3], Cs=params[:, 1],
+                              ampc=params[:, 4], pix=params[:, 0], name=name)
+    dm = os.path.join(root, '1_Embedding', 'DM')
+    mod = import_from(os.path.join(dm, 'Distances_ctf.py'), 'Distances_ctf')
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        run_quiet(mod.op, dm, pd)
+    D = np.load(os.path.join(dm, 'Data_Distances', 'PD_%s_dist.npy' % pd))
+    w = np.array(mrc.mmap(os.path.join(ddir, name + '_filtered.mrcs')).data)
+    return dict(stack=stack, params=params, D=D, wiener=w)
 
 
 def pca_golden(root, stack, pd):
@@ -200,6 +225,7 @@ def main():
     ap.add_argument('--skip-rot', action='store_true')
     ap.add_argument('--only-rot', action='store_true')
     ap.add_argument('--only-pca', action='store_true')
+    ap.add_argument('--only-ctf', action='store_true')
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     os.environ['PYTHONDONTWRITEBYTECODE'] = '1'
@@ -209,6 +235,17 @@ def main():
     install_stubs()
     from manifoldem_esper_b200 import synth
 
+    if args.only_ctf or not (args.only_rot or args.only_pca):
+        st, pa = synth.ctf_stack(pd=3, box=32, n_side=6, tau=2, snr=0.1)              # N=72, even box
+        np.savez_compressed(os.path.join(GOLD, 'ctf_small.npz'), **ctf_golden(root, st, pa, '003'))
+        st, pa = synth.ctf_stack(pd=5, box=25, n_side=4, tau=2, snr=0.5)              # N=32, odd box
+        np.savez_compressed(os.path.join(GOLD, 'ctf_odd.npz'), **ctf_golden(root, st, pa, '005'))
+        st, pa = synth.ctf_stack(pd=7, box=24, n_side=5, tau=1, snr=None)             # N=25, noise-free (cancellation)
+        np.savez_compressed(os.path.join(GOLD, 'ctf_pristine.npz'), **ctf_golden(root, st, pa, '007'))
+        print('ctf done')
+    if args.only_ctf:
+        shutil.rmtree(root, ignore_errors=True)
+        return
     if args.only_pca or not args.only_rot:
         prist = synth.synthetic_pd(pd=5, box=32, n_side=8, tau=1, snr=None)           # N=64, raw pixel values
         np.savez_compressed(os.path.join(GOLD, 'pca_pristine.npz'), **pca_golden(root, prist, '005'))
