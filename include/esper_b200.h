@@ -117,6 +117,30 @@ int esper_dmap_config(esper_ctx* ctx, int mode);
 int esper_dmap_embed(esper_ctx* ctx, const double* D, int m, double eps, int k, double tol,
                      int max_iter, double* val, double* vec, int* iters);
 
+/* float32 mean and population standard deviation of each image, bit-identical to numpy's `img.mean()` / `img.std()`
+ * on a float32 array (pairwise summation tree of numpy/_core/src/umath/loops_utils.h.src, two-pass variance of
+ * numpy/_core/_methods.py): the statistics the CTF branch standardises with (Distances.py:114-115).
+ * imgs [n, P] float32 (NULL: resident stack); mean, stdv: [n] float32. */
+int esper_image_stats(esper_ctx* ctx, const float* imgs, int n, int P, float* mean, float* stdv);
+
+/* ---- stage 1, CTF branch (1_Embedding/DM/Distances.py:107-145, the reference's shipped default) ----
+ * imgs [n, box, box] float32; params [n, 5] float64 = pixel size [A], spherical aberration [mm], defocus [A],
+ * voltage [keV], amplitude contrast per image -- the star-file columns read at Distances.py:68-72
+ * (rlnPixelSize, rlnSphericalAberration, rlnDefocusU, rlnVoltage, rlnAmplitudeContrast).  Per image: float32
+ * z-score (Distances.py:114-115), order-8 Butterworth low-pass at 0.5 Nyquist in Fourier space (:118-122,
+ * Generate_Filters.py:34-39,78-80), CTF on the FFT grid with B = inf (Generate_Filters.py:41-58,70-75).
+ *   D [n, n]            defocus-tolerant distances sqrt(sum_k |CTF_j fy_i - CTF_i fy_j|^2) with the reference's
+ *                       unnormalised fft2 (Distances.py:139-145); diagonal exactly 0, symmetric; D == NULL keeps the
+ *                       matrix resident only (chain with esper_eps_sweep / esper_dmap_embed(D = NULL))
+ *   wiener [n, box, box] float32 CTF-corrected stack ifft2(fft2(img) CTF_i / -(sum_i CTF_i^2 + 1/5)).real
+ *                       (Distances.py:128-135,155-161; the file `*_filtered.mrcs` read by Manifold_Binning.py:98);
+ *                       NULL skips it
+ * flags: ESPER_DIST_REFINE recomputes pairs whose D^2 is below refine_tau x the summed Gram terms pair by pair in
+ * FP64.  The reference's `D -= np.diag(D)` (:144, a row-broadcast of a diagonal that is zero up to rounding) is not
+ * reproduced; negative round-off under the square root is clamped to 0 where the reference yields NaN. */
+int esper_ctf_dist(esper_ctx* ctx, const float* imgs, int n, int box, const double* params, unsigned flags,
+                   double* D, float* wiener);
+
 /* ---- PCA embedding (1_Embedding/PCA/PCA.py:49-71) ---------------------------------
  * Y [P, n] = the raw images as columns (PCA.py:49-51, no per-image standardisation), minus the mean image
  * over the stack (PCA.py:53-55); the reference takes the SVD Y = u s v^T (PCA.py:58) and saves s^2 and the

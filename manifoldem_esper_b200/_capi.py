@@ -47,6 +47,8 @@ SIGNATURES = {
     'esper_dmap_config': (C.c_int, [C.c_void_p, C.c_int]),
     'esper_dmap_embed': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int,
                                    C.c_void_p, C.c_void_p, _i32p]),
+    'esper_image_stats': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    'esper_ctf_dist': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p]),
     'esper_pca_embed': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                                   C.c_void_p, C.c_void_p, _i32p]),
     'esper_dist_rms_rows': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int, C.c_void_p]),
@@ -228,6 +230,30 @@ class Context:
         self._check(self._lib.esper_dmap_embed(self._h, _ptr(D), int(m), float(eps), k, float(tol), int(max_iter),
                                                _ptr(val), _ptr(vec), C.byref(it)))
         return val, vec, it.value
+
+    def image_stats(self, imgs):
+        """float32 (mean, std) per image, bit-identical to numpy's float32 `img.mean()`, `img.std()`."""
+        imgs = _check_stack(imgs)
+        n, P = imgs.shape
+        mean = np.empty(n, dtype=np.float32)
+        std = np.empty(n, dtype=np.float32)
+        self._check(self._lib.esper_image_stats(self._h, _ptr(imgs), n, P, _ptr(mean), _ptr(std)))
+        return mean, std
+
+    def ctf_dist(self, stack, params, flags=DIST_DEFAULT, wiener=True, download=True):
+        """Distances.py:107-145 (CTF branch): stack [n, box, box] float32, params [n, 5] float64 =
+        (pixel size, Cs, defocus, voltage, amplitude contrast) -> (D [n, n] or None, wiener [n, box, box] float32 or None)."""
+        stack = np.ascontiguousarray(stack, dtype=np.float32)
+        if stack.ndim != 3 or stack.shape[1] != stack.shape[2]:
+            raise ValueError('ctf_dist: stack must be [n, box, box], got %r' % (stack.shape,))
+        n, box = stack.shape[0], stack.shape[1]
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        if params.shape != (n, 5):
+            raise ValueError('ctf_dist: params must be [%d, 5], got %r' % (n, params.shape))
+        D = np.empty((n, n), dtype=np.float64) if download else None
+        W = np.empty((n, box, box), dtype=np.float32) if wiener else None
+        self._check(self._lib.esper_ctf_dist(self._h, _ptr(stack), n, box, _ptr(params), int(flags), _ptr(D), _ptr(W)))
+        return D, W
 
     def pca_embed(self, imgs, k=20, tol=0.0, max_iter=0, n=None, P=None):
         """PCA.py:49-71 -> (val[k] = s^2 descending, U[n, k] = scores v s, lanczos steps)."""

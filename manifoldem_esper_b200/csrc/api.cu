@@ -1,5 +1,6 @@
 // api.cu -- the extern "C" surface declared in include/esper_b200.h.
 #include "common.cuh"
+#include "devutil.cuh"
 
 using namespace esper;
 
@@ -237,6 +238,51 @@ int esper_dmap_embed(esper_ctx* c, const double* D, int m, double eps, int k, do
     rc = run_markov(c, m, eps);
     if (rc) return rc;
     return run_lanczos(c, m, k, tol, max_iter, val, vec, iters);
+}
+
+// float32 mean and population std per image with numpy's summation order (the statistics of the CTF branch)
+int esper_image_stats(esper_ctx* c, const float* imgs, int n, int P, float* mean, float* stdv) {
+    ESPER_ENTER(c);
+    if (n < 1 || P < 1 || !mean || !stdv) return fail(c, ESPER_E_ARG, "image_stats: need n >= 1, P >= 1 and output arrays");
+    if (imgs) {
+        int rc = esper_upload_images(c, imgs, n, P);
+        if (rc) return rc;
+    } else if (c->img_n != n || c->img_P != P || !c->imgs.p) {
+        return fail(c, ESPER_E_STATE, "image_stats: imgs == NULL but no resident [%d, %d] stack", n, P);
+    }
+    ESPER_RESERVE(c, c->row_stats, sizeof(esper::RowStat) * esper::round_up((size_t)n, 128));
+    c->launches++;
+    int rc = esper::row_stats_numpy(c, n, P, c->row_stats.as<esper::RowStat>());
+    if (rc) return rc;
+    std::vector<esper::RowStat> h((size_t)n);
+    ESPER_CUDA(c, cudaMemcpyAsync(h.data(), c->row_stats.p, sizeof(esper::RowStat) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    ESPER_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; ++i) { mean[i] = h[(size_t)i].mean; stdv[i] = h[(size_t)i].stdv; }
+    return ESPER_OK;
+}
+
+// ---- CTF branch of stage 1 ----------------------------------------------------------
+int esper_ctf_dist(esper_ctx* c, const float* imgs, int n, int box, const double* params, unsigned flags,
+                   double* D, float* wiener) {
+    ESPER_ENTER(c);
+    if (n < 1 || box < 2) return fail(c, ESPER_E_ARG, "ctf_dist: need n >= 1 and box >= 2 (got n=%d, box=%d)", n, box);
+    if (!params) return fail(c, ESPER_E_ARG, "ctf_dist: params == NULL (need [n, 5] = pixel size, Cs, defocus, voltage, amplitude contrast)");
+    const int P = box * box;
+    if (imgs) {
+        int rc = esper_upload_images(c, imgs, n, P);
+        if (rc) return rc;
+    } else if (c->img_n != n || c->img_P != P || !c->imgs.p) {
+        return fail(c, ESPER_E_STATE, "ctf_dist: imgs == NULL but no resident [%d, %d] stack", n, P);
+    }
+    c->dist_m = 0;
+    int rc = run_ctf_dist(c, n, box, params, flags, wiener != nullptr);
+    if (rc) return rc;
+    c->dist_m = n; c->dist_rows = 0; c->dist_row0 = -1;
+    c->dist_symmetric = 1;
+    if (D) ESPER_CUDA(c, cudaMemcpyAsync(D, c->dist.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, c->stream));
+    if (wiener) ESPER_CUDA(c, cudaMemcpyAsync(wiener, c->ctf_wiener.p, sizeof(float) * (size_t)n * P, cudaMemcpyDeviceToHost, c->stream));
+    if (D || wiener) ESPER_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ESPER_OK;
 }
 
 // ---- PCA embedding -----------------------------------------------------------------

@@ -91,6 +91,9 @@ struct esper_ctx {
     // stage-2/3 workspaces
     esper::DevBuf sweep_part, sweep_aux;
     esper::DevBuf markov, degree;                              // Ms [m,m], d [m]
+    esper::DevBuf ctf_par, ctf_T, ctf_fy, ctf_C, ctf_ab, ctf_T12, ctf_wiener;   // CTF branch (k6_ctf.cu)
+    bool attr_ctf = false;
+    esper::DevBuf pw_plan; int pw_P = -1, pw_L = 0, pw_nodes = 0, pw_levels = 0, pw_root = 0;   // numpy pairwise-sum tree (k0_prep.cu)
     esper::DevBuf lan_V, lan_w, lan_h, lan_small;              // Lanczos basis etc.
     // stage-4 workspaces
     esper::DevBuf rot_U, rot_R, rot_idx, rot_out, rot_H, rot_theta, rot_aux;
@@ -151,6 +154,7 @@ struct LaunchScope {
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
+struct RowStat;
 // ---- per-stage entry points implemented in the .cu files (host side) ----
 int prep_and_gram(esper_ctx* c, int n, int P, unsigned flags);                 // k0_prep.cu + k1_gram.cu
 int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld, bool exact_center = false);
@@ -161,6 +165,9 @@ int run_markov_rows(esper_ctx* c, int rows, int m, int row0, double eps, const d
 bool ritz_converged(const std::vector<double>& a, const std::vector<double>& b, int n, int kw, int guard, double tol,
                     std::vector<double>& theta, std::vector<double>& S);
 int check_symmetry(esper_ctx* c, int m);
+int run_product(esper_ctx* c, float* a_hi, float* a_lo, int na, float* b_hi, float* b_lo, int nb, int ld, double* M);
+int run_ctf_dist(esper_ctx* c, int n, int box, const double* params_h, unsigned flags, bool want_wiener);
+int row_stats_numpy(esper_ctx* c, int n, int P, RowStat* st);
 int run_markov(esper_ctx* c, int m, double eps);
 int run_lanczos(esper_ctx* c, int m, int k, double tol, int max_iter, double* val_h, double* vec_h, int* iters, bool plain = false);
 int run_rot_eval(esper_ctx* c, const double* Uinit, int n_pd, int m, int dim, const double* R,

@@ -138,6 +138,128 @@ __global__ void __launch_bounds__(512) stats_split_kernel(const float* __restric
     if (threadIdx.x == 0) { st[i].mean = m; st[i].stdv = sd; st[i].norm2 = acc; }
 }
 
+// ------------------------------------------------------------------------------------------------
+// numpy-exact float32 statistics.  On the CTF branch the reference standardises with `(tmp - tmp.mean()) / tmp.std()`
+// on a float32 array (Distances.py:114-115), i.e. numpy's float32 pairwise summation: blocks of <= 128 elements summed
+// with 8 interleaved accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), halves split at n/2 rounded down
+// to a multiple of 8 (numpy/_core/src/umath/loops_utils.h.src, *_pairwise_sum), mean = sum / n, and the two-pass
+// variance of numpy/_core/_methods.py:_var (x = arr - mean; sum(x*x) / n; sqrt), all in float32.  Reproducing the
+// summation tree makes the z-scores bit-identical to the reference's, which matters for near-duplicate images on
+// that branch (a 1-ulp difference of the float32 std is a 6e-8 rescaling of one image, and the defocus-tolerant
+// distance is not invariant to it the way the plain Euclidean one is).
+// The tree (leaves and combine nodes by level) depends on P only and is built once on the host.
+// ------------------------------------------------------------------------------------------------
+struct PwNode { int left, right, out; };
+
+__device__ __forceinline__ float pw_leaf(const float* __restrict__ a, int len, int lane8, float mean, int squared) {
+    auto elem = [&](int i) -> float {
+        const float x = __ldg(a + i);
+        if (!squared) return x;
+        const float d = __fsub_rn(x, mean);
+        return __fmul_rn(d, d);
+    };
+    if (len < 8) {                                   // only a whole array shorter than 8 elements
+        float res = 0.f;
+        for (int i = 0; i < len; ++i) res = __fadd_rn(res, elem(i));
+        return res;
+    }
+    const int n8 = len - (len % 8);
+    float r = elem(lane8);
+    for (int i = 8; i < n8; i += 8) r = __fadd_rn(r, elem(i + lane8));
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+    for (int i = n8; i < len; ++i) r = __fadd_rn(r, elem(i));
+    return r;
+}
+
+__global__ void __launch_bounds__(256) np_stats_kernel(const float* __restrict__ raw, int P, const int2* __restrict__ leaves,
+                                                       int L, const PwNode* __restrict__ nodes, const int* __restrict__ level_off,
+                                                       int n_levels, int root, RowStat* __restrict__ st) {
+    extern __shared__ float slot[];
+    const int img = blockIdx.x;
+    const float* a = raw + (size_t)img * P;
+    const int group = threadIdx.x >> 3, lane8 = threadIdx.x & 7, n_groups = blockDim.x >> 3;
+    float mean = 0.f, stdv = 1.f;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int lf = group; lf < ((L + n_groups - 1) / n_groups) * n_groups; lf += n_groups) {   // whole warps stay converged
+            const bool live = lf < L;
+            const int2 ol = live ? leaves[lf] : make_int2(0, 8);
+            const float v = pw_leaf(a + ol.x, live ? ol.y : (P < 8 ? P : 8), lane8, mean, pass);
+            if (live && lane8 == 0) slot[lf] = v;
+        }
+        __syncthreads();
+        for (int lv = 0; lv < n_levels; ++lv) {
+            for (int q = level_off[lv] + threadIdx.x; q < level_off[lv + 1]; q += blockDim.x) {
+                const PwNode nd = nodes[q];
+                slot[nd.out] = __fadd_rn(slot[nd.left], slot[nd.right]);
+            }
+            __syncthreads();
+        }
+        const float total = slot[root];
+        __syncthreads();
+        if (pass == 0) mean = __fdiv_rn(total, (float)P);
+        else stdv = __fsqrt_rn(__fdiv_rn(total, (float)P));
+    }
+    if (threadIdx.x == 0) { st[img].mean = mean; st[img].stdv = stdv; st[img].norm2 = 0.0; }
+}
+
+namespace {
+struct PwBuild {
+    std::vector<int2> leaves;
+    struct N { int left, right, height, slot; };
+    std::vector<N> nodes;                 // every tree node; leaves have left = -1
+    int build(int off, int n) {
+        if (n <= 128) {
+            leaves.push_back(make_int2(off, n));
+            nodes.push_back({-1, -1, 0, (int)leaves.size() - 1});
+            return (int)nodes.size() - 1;
+        }
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        const int l = build(off, n2), r = build(off + n2, n - n2);
+        nodes.push_back({l, r, std::max(nodes[l].height, nodes[r].height) + 1, -1});
+        return (int)nodes.size() - 1;
+    }
+};
+}  // namespace
+
+// float32 mean / population std of every image of the resident stack, bit-identical to numpy's (see above)
+int row_stats_numpy(esper_ctx* c, int n, int P, RowStat* st) {
+    if (c->pw_P != P) {
+        PwBuild b;
+        const int root = b.build(0, P);
+        const int L = (int)b.leaves.size();
+        int max_h = b.nodes[root].height, next = L;
+        std::vector<PwNode> prog;
+        std::vector<int> level_off(1, 0);
+        for (int h = 1; h <= max_h; ++h) {
+            for (auto& nd : b.nodes) if (nd.left >= 0 && nd.height == h) nd.slot = next++;
+            for (auto& nd : b.nodes) if (nd.left >= 0 && nd.height == h) prog.push_back({b.nodes[nd.left].slot, b.nodes[nd.right].slot, nd.slot});
+            level_off.push_back((int)prog.size());
+        }
+        const size_t bytes = sizeof(int2) * (size_t)L + sizeof(PwNode) * (prog.size() + 1) + sizeof(int) * level_off.size();
+        ESPER_RESERVE(c, c->pw_plan, bytes + 64);
+        char* base = c->pw_plan.as<char>();
+        ESPER_CUDA(c, cudaMemcpyAsync(base, b.leaves.data(), sizeof(int2) * (size_t)L, cudaMemcpyHostToDevice, c->stream));
+        if (!prog.empty())
+            ESPER_CUDA(c, cudaMemcpyAsync(base + sizeof(int2) * (size_t)L, prog.data(), sizeof(PwNode) * prog.size(), cudaMemcpyHostToDevice, c->stream));
+        ESPER_CUDA(c, cudaMemcpyAsync(base + sizeof(int2) * (size_t)L + sizeof(PwNode) * (prog.size() + 1), level_off.data(),
+                                      sizeof(int) * level_off.size(), cudaMemcpyHostToDevice, c->stream));
+        ESPER_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->pw_P = P; c->pw_L = L; c->pw_nodes = (int)prog.size(); c->pw_levels = max_h; c->pw_root = b.nodes[root].slot;
+    }
+    char* base = c->pw_plan.as<char>();
+    const int2* leaves = reinterpret_cast<const int2*>(base);
+    const PwNode* nodes = reinterpret_cast<const PwNode*>(base + sizeof(int2) * (size_t)c->pw_L);
+    const int* level_off = reinterpret_cast<const int*>(base + sizeof(int2) * (size_t)c->pw_L + sizeof(PwNode) * ((size_t)c->pw_nodes + 1));
+    const size_t smem = sizeof(float) * (size_t)(c->pw_L + c->pw_nodes + 1);
+    if (smem > 48 * 1024) return fail(c, ESPER_E_ARG, "row statistics: %d pixels per image need %zu bytes of shared memory", P, smem);
+    np_stats_kernel<<<n, 256, smem, c->stream>>>(c->imgs.as<float>(), P, leaves, c->pw_L, nodes, level_off, c->pw_levels, c->pw_root, st);
+    ESPER_CUDA(c, cudaGetLastError());
+    return ESPER_OK;
+}
+
 int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld, bool exact_center) {
     const float* raw = c->imgs.as<float>();
     ESPER_RESERVE(c, c->row_stats, sizeof(RowStat) * (size_t)rows_pad);

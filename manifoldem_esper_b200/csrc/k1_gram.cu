@@ -126,7 +126,10 @@ __device__ __forceinline__ void tile_coords(int t, int nt, int& ti, int& tj) {
 //   rect_ti0 < 0 : the whole upper triangle (single-GPU path)
 //   rect_ti0 >= 0: row-block path, tiles (rect_ti0 + t / nt, t % nt) of a block of tile rows; a tile below the
 //                  diagonal is computed as its mirror image (same operands, same bits) and stored transposed.
+//   rect_ti0 == -2: general product A B^T (two operand matrices): tile (t / nt, t % nt), nt = tile columns (B tiles)
+constexpr int FULL_RECT = -2;
 __device__ __forceinline__ void tile_map(int t, int nt, int rect_ti0, int& ta, int& tb, bool& transposed) {
+    if (rect_ti0 == FULL_RECT) { ta = t / nt; tb = t % nt; transposed = false; return; }
     if (rect_ti0 < 0) { tile_coords(t, nt, ta, tb); transposed = false; return; }
     const int ti = rect_ti0 + t / nt, tj = t % nt;
     if (tj >= ti) { ta = ti; tb = tj; transposed = false; } else { ta = tj; tb = ti; transposed = true; }
@@ -139,6 +142,7 @@ __device__ __forceinline__ void tile_map(int t, int nt, int rect_ti0, int& ta, i
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gram_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+            const __grid_constant__ CUtensorMap mapb_hi, const __grid_constant__ CUtensorMap mapb_lo,
             int nt, int n_tiles, int tile0, int rect_ti0, int nkb, int split_k, int drain_kb, float* __restrict__ part) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // 1024-byte aligned operand ring
@@ -158,6 +162,8 @@ gram_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_hi);
         tma_prefetch_desc(&map_lo);
+        tma_prefetch_desc(&mapb_hi);
+        tma_prefetch_desc(&mapb_lo);
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
         for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar + 8 * a, 1); mbar_init(tempty_bar + 8 * a, 4); }
         fence_barrier_init();
@@ -178,7 +184,7 @@ gram_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
             for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
                 const int chunk = u / n_tiles, t = tile0 + (u % n_tiles);
                 int ti, tj; bool tr_; tile_map(t, nt, rect_ti0, ti, tj, tr_);
-                const bool diag = (ti == tj);
+                const bool diag = (ti == tj) && rect_ti0 != FULL_RECT;
                 const int kb0 = (int)((long long)nkb * chunk / split_k);
                 const int kb1 = (int)((long long)nkb * (chunk + 1) / split_k);
                 for (int kb = kb0; kb < kb1; ++kb) {
@@ -189,8 +195,8 @@ gram_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
                     tma_load_2d(sa, &map_hi, fb, kb * BK, ti * BM);
                     tma_load_2d(sa + TILE_BYTES, &map_lo, fb, kb * BK, ti * BM);
                     if (!diag) {
-                        tma_load_2d(sa + 2 * TILE_BYTES, &map_hi, fb, kb * BK, tj * BN);
-                        tma_load_2d(sa + 3 * TILE_BYTES, &map_lo, fb, kb * BK, tj * BN);
+                        tma_load_2d(sa + 2 * TILE_BYTES, &mapb_hi, fb, kb * BK, tj * BN);
+                        tma_load_2d(sa + 3 * TILE_BYTES, &mapb_lo, fb, kb * BK, tj * BN);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -204,7 +210,7 @@ gram_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
             for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
                 const int chunk = u / n_tiles, t = tile0 + (u % n_tiles);
                 int ti, tj; bool tr_; tile_map(t, nt, rect_ti0, ti, tj, tr_);
-                const bool diag = (ti == tj);
+                const bool diag = (ti == tj) && rect_ti0 != FULL_RECT;
                 const int kb0 = (int)((long long)nkb * chunk / split_k);
                 const int kb1 = (int)((long long)nkb * (chunk + 1) / split_k);
                 // Tensor-core FP32 accumulation rounds toward zero, which biases a long chain in proportion to the
@@ -362,6 +368,36 @@ gram_finalize_kernel(const float* __restrict__ part, int nt, int n_tiles, int ti
     }
 }
 
+// General product epilogue (CTF branch): M = sum of the split-K partials, FP64.  sym: upper-triangle tiles of a
+// symmetric product, mirrored, diagonal from the partials; else tile (t / nt, t % nt) of an [na, nb] product.
+__global__ void __launch_bounds__(256)
+product_store_kernel(const float* __restrict__ part, int nt, int n_tiles, int tile0, int sym, int split_k, int na, int nb,
+                     double* __restrict__ M) {
+    const int lt = blockIdx.x;
+    const int e_per = (BM * (BN / 4)) / gridDim.y;
+    int ti, tj; bool transposed; tile_map(tile0 + lt, nt, sym ? -1 : FULL_RECT, ti, tj, transposed);
+    const bool diag = sym && (ti == tj);
+    for (int e = blockIdx.y * e_per + threadIdx.x; e < (blockIdx.y + 1) * e_per; e += blockDim.x) {
+        const int r = e & (BM - 1), c4 = e >> 7;
+        const int i = ti * BM + r;
+        if (i >= na) continue;
+        double g[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int ch = 0; ch < split_k; ++ch) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(part + (size_t)(ch * n_tiles + lt) * (BM * BN)) + e);
+            g[0] += (double)v.x; g[1] += (double)v.y; g[2] += (double)v.z; g[3] += (double)v.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = c4 * 4 + q;
+            const int j = tj * BN + c;
+            if (j >= nb) continue;
+            if (diag && c < r) continue;
+            M[(size_t)i * nb + j] = g[q];
+            if (sym && j != i) M[(size_t)j * nb + i] = g[q];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Refinement of cancelling pairs by direct differences (the reference's own arithmetic:
 // float64 sum of squared differences of the float32 standardised images).
@@ -460,6 +496,58 @@ static int choose_split_k(int requested, int nkb, int n_tiles, int sms) {
     return best < 1 ? 1 : best;
 }
 
+// M [na, nb] (FP64) = A B^T with A, B given as TF32 hi/lo planes of row stride ld (rows padded to 128, zero filled).
+// b_hi == nullptr: symmetric product A A^T (upper-triangle tiles, mirrored).  Used by the CTF branch.
+int run_product(esper_ctx* c, float* a_hi, float* a_lo, int na, float* b_hi, float* b_lo, int nb, int ld, double* M) {
+    using namespace gram;
+    const bool sym = (b_hi == nullptr);
+    if (sym) { b_hi = a_hi; b_lo = a_lo; nb = na; }
+    const int a_pad = (int)round_up((size_t)na, BM), b_pad = (int)round_up((size_t)nb, BN);
+    const int nta = a_pad / BM, ntb = b_pad / BN;
+    const int tiles_total = sym ? nta * (nta + 1) / 2 : nta * ntb;
+    const int nkb = ld / BK;
+    const int sms = c->sm_count;
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    int rc;
+    if ((rc = make_plane_map(c, &ma_hi, a_hi, a_pad, ld))) return rc;
+    if ((rc = make_plane_map(c, &ma_lo, a_lo, a_pad, ld))) return rc;
+    if ((rc = make_plane_map(c, &mb_hi, b_hi, b_pad, ld))) return rc;
+    if ((rc = make_plane_map(c, &mb_lo, b_lo, b_pad, ld))) return rc;
+    if (!c->attr_gram) {
+        ESPER_CUDA(c, cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        c->attr_gram = true;
+    }
+    const size_t tile_bytes = (size_t)BM * BN * sizeof(float);
+    const size_t ws_cap = (size_t)3 << 30;
+    int batch = tiles_total;
+    int split_k = choose_split_k(c->split_k, nkb, batch, sms);
+    while ((size_t)batch * split_k * tile_bytes > ws_cap && batch > sms) {
+        batch = (batch + 1) / 2;
+        split_k = choose_split_k(c->split_k, nkb, batch, sms);
+    }
+    ESPER_RESERVE(c, c->gram_part, (size_t)batch * split_k * tile_bytes);
+    float* part = c->gram_part.as<float>();
+    const int drain_kb = c->drain_kb > 0 ? c->drain_kb : 2;
+    for (int tile0 = 0; tile0 < tiles_total; tile0 += batch) {
+        const int nbt = (tiles_total - tile0 < batch) ? tiles_total - tile0 : batch;
+        int sk = choose_split_k(c->split_k, nkb, nbt, sms);
+        if (sk > split_k) sk = split_k;
+        const int units = nbt * sk;
+        const int grid = units < sms ? units : sms;
+        {
+            LaunchScope ls(c, "gram");
+            gram_kernel<<<grid, NUM_THREADS, SMEM_BYTES, c->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, sym ? nta : ntb, nbt, tile0,
+                                                                       sym ? -1 : FULL_RECT, nkb, sk, drain_kb, part);
+        }
+        {
+            LaunchScope ls(c, "dist_finalize");
+            product_store_kernel<<<dim3(nbt, 8), 256, 0, c->stream>>>(part, sym ? nta : ntb, nbt, tile0, sym ? 1 : 0, sk, na, nb, M);
+        }
+    }
+    ESPER_CUDA(c, cudaGetLastError());
+    return ESPER_OK;
+}
+
 int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, int row0, int nrows, double* gram_out) {
     using namespace gram;
     // row0 < 0: full symmetric matrix (upper triangle of tiles); else the row block [row0, row0+nrows) x [0, n)
@@ -506,7 +594,7 @@ int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, i
         const int grid = units < sms ? units : sms;
         {
             LaunchScope ls(c, "gram");
-            gram_kernel<<<grid, NUM_THREADS, SMEM_BYTES, c->stream>>>(map_hi, map_lo, nt, nb, tile0, rect_ti0, nkb, sk, drain_kb, part);
+            gram_kernel<<<grid, NUM_THREADS, SMEM_BYTES, c->stream>>>(map_hi, map_lo, map_hi, map_lo, nt, nb, tile0, rect_ti0, nkb, sk, drain_kb, part);
         }
         {
             LaunchScope ls(c, "dist_finalize");

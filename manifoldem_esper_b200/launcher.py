@@ -75,7 +75,7 @@ def run_sharded(pds, work_fn, rank=0, world=1, gather=None):
     return records
 
 
-def _stage_fns(root, stages, dim, pca, k, skip_existing, device):
+def _stage_fns(root, stages, dim, pca, k, skip_existing, device, ctf=True):
     from . import PCA, Distances, DiffusionMaps, Rotation_Histograms, _capi
     ctx = _capi.Context(device)
     dm_dir = os.path.join(root, '1_Embedding', 'DM')
@@ -87,7 +87,7 @@ def _stage_fns(root, stages, dim, pca, k, skip_existing, device):
         if 'dist' in stages:
             out = os.path.join(dm_dir, 'Data_Distances', 'PD_%s_dist.npy' % pd)
             if not (skip_existing and os.path.exists(out)):
-                t = time.time(); Distances.op(dm_dir, pd, ctx=ctx); info['dist_s'] = time.time() - t
+                t = time.time(); Distances.op(dm_dir, pd, CTF=ctf, ctx=ctx); info['dist_s'] = time.time() - t
         if 'dm' in stages:
             out = os.path.join(dm_dir, 'Data_Manifolds', 'PD_%s_vec.npy' % pd)
             if not (skip_existing and os.path.exists(out)):
@@ -111,6 +111,7 @@ def main(argv=None):
     ap.add_argument('--stages', default='dist,dm,rot', help='comma list of dist, dm, pca, rot')
     ap.add_argument('--dim', type=int, default=6)
     ap.add_argument('--pca', action='store_true')
+    ap.add_argument('--no-ctf', action='store_true', help='Distances: CTF = False branch (the reference ships CTF = True)')
     ap.add_argument('-k', type=int, default=16)
     ap.add_argument('--skip-existing', action='store_true')
     args = ap.parse_args(argv)
@@ -125,7 +126,7 @@ def main(argv=None):
             out = [None] * world
             dist.all_gather_object(out, local)
             return out
-    work = _stage_fns(args.root, set(args.stages.split(',')), args.dim, args.pca, args.k, args.skip_existing, local_rank)
+    work = _stage_fns(args.root, set(args.stages.split(',')), args.dim, args.pca, args.k, args.skip_existing, local_rank, ctf=not args.no_ctf)
     recs = run_sharded(parse_pds(args.pds), work, rank, world, gather)
     failed = [r for r in recs if not r.get('ok')]
     if rank == 0:

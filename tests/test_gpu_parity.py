@@ -115,7 +115,7 @@ def test_distances_op_files(ctx, tmp_path):
     data = root / '0_Data_Inputs' / 'CTF5k15k_SNRpt1_ELS_2D'
     os.makedirs(dm); os.makedirs(data)
     mrc.write_stack(str(data / 'PD003_SNR_tau5_stack.mrcs'), g['stack'])
-    Distances.op(str(dm), '003', ctx=ctx)
+    Distances.op(str(dm), '003', CTF=False, ctx=ctx)
     D = np.load(str(dm / 'Data_Distances' / 'PD_003_dist.npy'))
     assert D.dtype == np.float64 and D.flags.c_contiguous and d_err(D, g['D']) < D_TOL
     DiffusionMaps.op(str(dm), '003', k=8, ctx=ctx)
@@ -243,6 +243,88 @@ def test_full_size_pipeline_vs_oracle(ctx):
     # the whole leading block as a subspace (principal angles) unless the cut falls inside a cluster
     s_ = np.linalg.svd(vec.T @ U_r[:, :k], compute_uv=False)
     assert s_.min() > 1 - 1e-6 or lam[k - 1] - lam[k] < 2e-3 * lam[1]
+
+
+# ---- stage 1, CTF branch -----------------------------------------------------------
+def offdiag_rel(D, Dr):
+    off = ~np.eye(D.shape[0], dtype=bool)
+    return float(np.max(np.abs(D - Dr)[off] / Dr[off]))
+
+
+@pytest.mark.parametrize('shape', [(5, 250, 250), (9, 32, 32), (7, 25, 25), (4, 7), (3, 129), (6, 1000), (2, 128 * 128)])
+def test_image_stats_bit_identical_to_numpy(ctx, shape):
+    """The float32 statistics of the CTF branch reproduce numpy's pairwise summation bit for bit."""
+    rng = np.random.default_rng(sum(shape))
+    x = (rng.standard_normal(shape) * 3 + 1.5).astype(np.float32)
+    mean, std = ctx.image_stats(x.reshape(shape[0], -1))
+    for i in range(shape[0]):
+        assert mean[i] == x[i].mean() and std[i] == x[i].std(), i
+
+
+@pytest.mark.parametrize('name', ['ctf_small', 'ctf_odd', 'ctf_pristine'])
+def test_ctf_distances_vs_reference_golden(ctx, name):
+    """Defocus-tolerant distances and Wiener-filtered stack against the reference's Distances.op (CTF = True)."""
+    g = golden(name + '.npz')
+    D, W = ctx.ctf_dist(g['stack'], g['params'])
+    assert offdiag_rel(D, g['D']) < D_TOL
+    assert np.array_equal(D, D.T) and np.all(np.diag(D) == 0) and np.all(np.isfinite(D))
+    assert W.dtype == np.float32 and np.max(np.abs(W - g['wiener'])) < 2e-6 * np.abs(g['wiener']).max()
+
+
+def test_ctf_refinement_of_near_duplicates(ctx):
+    """Noise-free images that differ only in defocus, plus exact duplicates: the Gram expansion cancels, the
+    pair-by-pair pass restores 1e-5 and exact zeros."""
+    st, pa = synth.ctf_stack(pd=2, box=48, n_side=4, tau=3, snr=None)
+    st[1], pa[1] = st[0], pa[0]                                               # an exact duplicate
+    Dr = O.distances_ctf_direct(st, pa)
+    D, _ = ctx.ctf_dist(st, pa, wiener=False)
+    off = ~np.eye(len(D), dtype=bool)
+    assert D[0, 1] == 0.0 and D[1, 0] == 0.0
+    m = off & (Dr > 0)
+    assert np.max(np.abs(D - Dr)[m] / Dr[m]) < D_TOL
+    D_raw, _ = ctx.ctf_dist(st, pa, flags=0, wiener=False)                    # without the pass: worse on close pairs
+    assert np.max(np.abs(D_raw - Dr)[m] / Dr[m]) >= np.max(np.abs(D - Dr)[m] / Dr[m])
+
+
+def test_ctf_medium_vs_oracle_and_chain(ctx):
+    """N=400 images of 64x64 at SNR 0.1 with per-image defocus; then the resident matrix feeds stages 2-3."""
+    st, pa = synth.ctf_stack(pd=6, box=64, n_side=10, tau=4, snr=0.1)
+    Dr, Wr = O.distances_ctf_op(st, pa)
+    D, W = ctx.ctf_dist(st, pa)
+    assert offdiag_rel(D, Dr) < D_TOL
+    assert np.max(np.abs(W - Wr)) < 2e-6 * np.abs(Wr).max()
+    L = GaussianBandwidth.sweep(None, LOG_EPS, ctx=ctx, m=400)               # sweep on the resident CTF distances
+    assert np.max(np.abs(L - O.eps_sweep_logsum(Dr, LOG_EPS, sequential=False))) < 1e-4
+    popt, _, _ = GaussianBandwidth.fit(LOG_EPS, L, np.array([[-0.2], [0.3], [-0.4], [0.1]]))
+    eps = float(np.exp(-(popt[1] / popt[0])))
+    val, vec, _ = ctx.dmap_embed(None, eps, k=6, m=400)
+    val_r, U_r = O.dmap_embed(D, eps)
+    assert np.max(np.abs(val - val_r[:6]) / val_r[:6]) < VAL_TOL
+
+
+def test_ctf_op_files_and_errors(ctx, tmp_path):
+    """Distances.op(pyDir, PD) with the reference's default CTF = True: star + stack in, dist.npy + filtered stack out."""
+    from manifoldem_esper_b200 import Read_Alignment
+    g = golden('ctf_odd.npz')
+    dm = tmp_path / '1_Embedding' / 'DM'
+    dd = tmp_path / '0_Data_Inputs' / 'CTF5k15k_SNRpt1_ELS_2D'
+    dm.mkdir(parents=True); dd.mkdir(parents=True)
+    name = 'Hsp2D_5k15k_PD_005'
+    mrc.write_stack(str(dd / (name + '.mrcs')), g['stack'])
+    pa = g['params']
+    Read_Alignment.write_star(str(dd / (name + '.star')), pa[:, 2], volt=pa[:, 3], Cs=pa[:, 1], ampc=pa[:, 4], pix=pa[:, 0], name=name)
+    Distances.op(str(dm), '005', ctx=ctx)
+    D = np.load(str(dm / 'Data_Distances' / 'PD_005_dist.npy'))
+    assert D.dtype == np.float64 and offdiag_rel(D, g['D']) < D_TOL
+    W = np.asarray(mrc.mmap(str(dd / (name + '_filtered.mrcs'))).data)
+    assert W.shape == g['wiener'].shape and np.max(np.abs(W - g['wiener'])) < 2e-6 * np.abs(g['wiener']).max()
+    with pytest.raises(ValueError):
+        ctx.ctf_dist(g['stack'], pa[:-1])                                     # one parameter row per image
+    with pytest.raises(ValueError):
+        ctx.ctf_dist(g['stack'][:, :, :-1], pa)                               # square images only
+    bad = pa.copy(); bad[3, 0] = 0.0
+    with pytest.raises(ValueError):
+        ctx.ctf_dist(g['stack'], bad)                                         # pixel size must be positive
 
 
 # ---- PCA embedding (SURVEY 8f-2) ----------------------------------------------------------------

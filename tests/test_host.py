@@ -108,9 +108,14 @@ def test_mrc_roundtrip(tmp_path):
         mrc.mmap(p)
 
 
-def test_distances_ctf_branch_is_out_of_scope(tmp_path):
-    with pytest.raises(NotImplementedError):
-        Distances.op(str(tmp_path), '001', CTF=True)
+def test_star_params_columns(tmp_path):
+    """Distances.star_params picks the five columns the reference reads (Distances.py:68-72), per image."""
+    from manifoldem_esper_b200 import Read_Alignment
+    df = np.array([5000., 9000.])
+    Read_Alignment.write_star(str(tmp_path / 's.star'), df, volt=200, Cs=2.0, ampc=0.07, pix=1.5)
+    par = Distances.star_params(Read_Alignment.parse_star(str(tmp_path / 's.star')))
+    assert par.shape == (2, 5) and par.dtype == np.float64
+    assert np.array_equal(par, [[1.5, 2.0, 5000., 200., 0.07], [1.5, 2.0, 9000., 200., 0.07]])
 
 
 def test_argument_errors_raise_valueerror():
