@@ -12,8 +12,7 @@
 // Everything is evaluated on the half spectrum kx in [0, N/2] of the real images (weights w = 1 on the self-conjugate
 // columns, 2 elsewhere): all summands are even in k.  The K index of the operand planes is k = kx*N + ky.
 //
-// FFT: hand-written mixed-radix Stockham transform in FP64, one line of N complex values in shared memory per 32..64
-// threads, radices 4/2/3/5/7 in registers, any other prime factor by a direct O(r^2) butterfly.  Two real image rows are
+// FFT: hand-written mixed-radix Stockham transform in FP64, one line of N complex values in shared memory per warp, radices 4/2/3/5/7 in registers, any other prime factor by a direct O(r^2) butterfly.  Two real image rows are
 // packed into one complex transform.  Passes:
 //   rows  : raw rows -> z-score -> FFT along x -> T[img][kx][y]           (ctf_rows_kernel)
 //   cols  : T lines -> FFT along y -> filters, operand planes, fy (FP64) -> Wiener multiply -> inverse FFT along y -> T
@@ -30,6 +29,7 @@ constexpr int MAXF = 16;
 constexpr int LINES = 8;             // complex lines per CTA (= 16 image rows in the row passes)
 constexpr int THREADS = 256;
 struct FftPlan { int N; int nfac; int radix[MAXF]; };
+static_assert(THREADS == 32 * LINES, "one warp per line");
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -42,12 +42,11 @@ __device__ __forceinline__ double2 tw(const double2* W, int e, bool inv) {
 
 // One radix-R Stockham butterfly j of the stage with sub-transform length Ns (Govindaraju et al. formulation):
 //   v_p = in[j + p N/R] W_N^{p (j mod Ns) N/(Ns R)},  out[(j / Ns) Ns R + (j mod Ns) + q Ns] = sum_p v_p W_R^{pq}
+// k = j mod Ns, o = (j / Ns) Ns R + k and step = k N/(Ns R) are supplied by the caller.
 template <int R>
-__device__ __forceinline__ void butterfly(const double2* __restrict__ in, double2* __restrict__ out, int j, int Ns, int N,
-                                          const double2* __restrict__ W, bool inv) {
+__device__ __forceinline__ void butterfly(const double2* __restrict__ in, double2* __restrict__ out, int j, int k, int o,
+                                          int step, int Ns, int N, const double2* __restrict__ W, bool inv) {
     const int stride = N / R;
-    const int k = j % Ns;
-    const int step = k * (N / (Ns * R));
     double2 v[R];
 #pragma unroll
     for (int p = 0; p < R; ++p) {
@@ -58,7 +57,6 @@ __device__ __forceinline__ void butterfly(const double2* __restrict__ in, double
     double2 wr[R];
 #pragma unroll
     for (int m = 0; m < R; ++m) wr[m] = tw(W, m * stride, inv);
-    const int o = (j / Ns) * Ns * R + k;
 #pragma unroll
     for (int q = 0; q < R; ++q) {
         double2 acc = v[0];
@@ -72,12 +70,9 @@ __device__ __forceinline__ void butterfly(const double2* __restrict__ in, double
 }
 
 // Any radix (prime factors > 7): no register arrays, inputs re-read from shared memory.
-__device__ __forceinline__ void butterfly_generic(const double2* __restrict__ in, double2* __restrict__ out, int j, int Ns,
-                                                  int N, int r, const double2* __restrict__ W, bool inv) {
+__device__ __forceinline__ void butterfly_generic(const double2* __restrict__ in, double2* __restrict__ out, int j, int o,
+                                                  int step, int Ns, int N, int r, const double2* __restrict__ W, bool inv) {
     const int stride = N / r;
-    const int k = j % Ns;
-    const int step = k * (N / (Ns * r));
-    const int o = (j / Ns) * Ns * r + k;
     for (int q = 0; q < r; ++q) {
         double2 acc = make_double2(0.0, 0.0);
         for (int p = 0; p < r; ++p) {
@@ -89,29 +84,33 @@ __device__ __forceinline__ void butterfly_generic(const double2* __restrict__ in
     }
 }
 
-// Transform `nlines` lines of length N held in `a` (scratch `b`); returns the buffer holding the result.
-// Unnormalised; inv = conjugate twiddles.  All threads of the CTA must call it.
-__device__ double2* fft_lines(double2* a, double2* b, int nlines, const FftPlan& pl, const double2* W, bool inv) {
+// One warp transforms one line of length N held in `a` (scratch `b`); returns the buffer holding the result.
+// Unnormalised; inv = conjugate twiddles.  Only __syncwarp() between stages: a line never leaves its warp.
+__device__ double2* fft_line(double2* a, double2* b, const FftPlan& pl, const double2* W, bool inv) {
     const int N = pl.N;
+    const int lane = threadIdx.x & 31;
     int Ns = 1;
     double2* in = a; double2* out = b;
     for (int s = 0; s < pl.nfac; ++s) {
         const int r = pl.radix[s];
         const int nb = N / r;
-        for (int item = threadIdx.x; item < nlines * nb; item += blockDim.x) {
-            const int line = item / nb, j = item - line * nb;
-            const double2* li = in + (size_t)line * N;
-            double2* lo = out + (size_t)line * N;
+        const int mul = N / (Ns * r);
+        const float inv_ns = 1.0f / (float)Ns;
+        for (int j = lane; j < nb; j += 32) {
+            const int jq = (int)(((float)j + 0.5f) * inv_ns);          // j / Ns (exact for these sizes)
+            const int k = j - jq * Ns;
+            const int o = jq * Ns * r + k;
+            const int step = k * mul;
             switch (r) {
-                case 2: butterfly<2>(li, lo, j, Ns, N, W, inv); break;
-                case 3: butterfly<3>(li, lo, j, Ns, N, W, inv); break;
-                case 4: butterfly<4>(li, lo, j, Ns, N, W, inv); break;
-                case 5: butterfly<5>(li, lo, j, Ns, N, W, inv); break;
-                case 7: butterfly<7>(li, lo, j, Ns, N, W, inv); break;
-                default: butterfly_generic(li, lo, j, Ns, N, r, W, inv); break;
+                case 2: butterfly<2>(in, out, j, k, o, step, Ns, N, W, inv); break;
+                case 3: butterfly<3>(in, out, j, k, o, step, Ns, N, W, inv); break;
+                case 4: butterfly<4>(in, out, j, k, o, step, Ns, N, W, inv); break;
+                case 5: butterfly<5>(in, out, j, k, o, step, Ns, N, W, inv); break;
+                case 7: butterfly<7>(in, out, j, k, o, step, Ns, N, W, inv); break;
+                default: butterfly_generic(in, out, j, o, step, Ns, N, r, W, inv); break;
             }
         }
-        __syncthreads();
+        __syncwarp();
         Ns *= r;
         double2* t = in; in = out; out = t;
     }
@@ -134,19 +133,30 @@ __device__ __forceinline__ double ctf_eval(double Q, const double* __restrict__ 
     return sn - par[2] * cs;
 }
 
-// C[i][k] for all images and S[k] = sum_i C_i(k)^2 in image order (gen_wiener, Distances.py:155-161).  Thread per k.
+// C[i][k] for all images, Butterworth table Gf[k] and the Wiener denominator sum S[k] = sum_i C_i(k)^2
+// (gen_wiener, Distances.py:155-161).  Thread per (k, image chunk); chunk partial sums are added in chunk order.
+constexpr int GEN_CHUNKS = 8;
 __global__ void __launch_bounds__(256) ctf_gen_kernel(int N, int Kh, int n, const double* __restrict__ par,
-                                                      double* __restrict__ C, double* __restrict__ S) {
+                                                      double* __restrict__ C, double* __restrict__ Spart, double* __restrict__ Gf) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= Kh) return;
     const int kx = k / N, ky = k - kx * N;
     const double Q = grid_q(ky, kx, N);
+    if (blockIdx.y == 0) Gf[k] = sqrt(1.0 / (1.0 + pow(Q / 0.5, 16.0)));   // create_filter('Butter', 8, 0.5, Q)
+    const int i0 = (int)((long long)n * blockIdx.y / gridDim.y), i1 = (int)((long long)n * (blockIdx.y + 1) / gridDim.y);
     double s = 0.0;
-    for (int i = 0; i < n; ++i) {
+    for (int i = i0; i < i1; ++i) {
         const double c = ctf_eval(Q, par + 4 * (size_t)i);
         C[(size_t)i * Kh + k] = c;
         s = s + c * c;
     }
+    Spart[(size_t)blockIdx.y * Kh + k] = s;
+}
+__global__ void __launch_bounds__(256) ctf_sum_kernel(int Kh, int chunks, const double* __restrict__ Spart, double* __restrict__ S) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= Kh) return;
+    double s = 0.0;
+    for (int q = 0; q < chunks; ++q) s += Spart[(size_t)q * Kh + k];
     S[k] = s;
 }
 
@@ -154,32 +164,51 @@ __device__ __forceinline__ void load_twiddles(double2* W, const double2* __restr
     for (int i = threadIdx.x; i < N; i += blockDim.x) W[i] = Wg[i];
 }
 
-// rows: 16 image rows -> 8 packed complex lines -> FFT along x -> half spectra, stored transposed T[img][kx][y].
-__global__ void __launch_bounds__(THREADS) ctf_rows_kernel(const float* __restrict__ raw, const RowStat* __restrict__ st,
+// rows: 16 image rows -> 8 packed complex lines (one per warp) -> FFT along x -> half spectra, stored transposed
+// T[img][kx][y].
+__global__ void __launch_bounds__(THREADS, 3) ctf_rows_kernel(const float* __restrict__ raw, const RowStat* __restrict__ st,
                                                            int N, int Nh, FftPlan pl, const double2* __restrict__ Wg,
                                                            double2* __restrict__ T) {
     extern __shared__ double2 sm[];
     double2* W = sm; double2* A = W + N; double2* B = A + (size_t)LINES * N;
     const int img = blockIdx.y, y0 = blockIdx.x * 2 * LINES;
+    const int l = threadIdx.x >> 5, lane = threadIdx.x & 31;
     load_twiddles(W, Wg, N);
     const float mean = st[img].mean, stdv = st[img].stdv;
     const float* src = raw + (size_t)img * N * N;
-    for (int idx = threadIdx.x; idx < LINES * N; idx += blockDim.x) {
-        const int l = idx / N, x = idx - l * N;
+    {
         const int ya = y0 + 2 * l, yb = ya + 1;
-        const double re = ya < N ? (double)zscore(__ldg(src + (size_t)ya * N + x), mean, stdv) : 0.0;
-        const double im = yb < N ? (double)zscore(__ldg(src + (size_t)yb * N + x), mean, stdv) : 0.0;
-        A[idx] = make_double2(re, im);
+        const float* ra = src + (size_t)(ya < N ? ya : 0) * N;
+        const float* rb = src + (size_t)(yb < N ? yb : 0) * N;
+        for (int x0 = lane; x0 < N; x0 += 128) {                      // 8 independent loads in flight per lane
+            float va[4], vb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int x = x0 + 32 * u;
+                va[u] = x < N ? __ldg(ra + x) : 0.f;
+                vb[u] = x < N ? __ldg(rb + x) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int x = x0 + 32 * u;
+                if (x < N)
+                    A[(size_t)l * N + x] = make_double2(ya < N ? (double)zscore(va[u], mean, stdv) : 0.0,
+                                                        yb < N ? (double)zscore(vb[u], mean, stdv) : 0.0);
+            }
+        }
     }
+    __syncthreads();                                                   // twiddles
+    const double2* Rl = fft_line(A + (size_t)l * N, B + (size_t)l * N, pl, W, false);
+    const bool in_a = (Rl == A + (size_t)l * N);                       // same for every warp
     __syncthreads();
-    const double2* R = fft_lines(A, B, LINES, pl, W, false);
+    const double2* R = in_a ? A : B;
     for (int idx = threadIdx.x; idx < Nh * 2 * LINES; idx += blockDim.x) {
-        const int kx = idx / (2 * LINES), r = idx - kx * 2 * LINES;
+        const int kx = idx >> 4, r = idx & 15;
         const int y = y0 + r;
         if (y >= N) continue;
-        const int l = r >> 1;
-        const double2 zk = R[(size_t)l * N + kx];
-        double2 zm = R[(size_t)l * N + (kx ? N - kx : 0)];
+        const int ll = r >> 1;
+        const double2 zk = R[(size_t)ll * N + kx];
+        double2 zm = R[(size_t)ll * N + (kx ? N - kx : 0)];
         zm.y = -zm.y;
         double2 o;
         if ((r & 1) == 0) o = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y + zm.y));
@@ -201,78 +230,96 @@ __device__ __forceinline__ void split_store(float* __restrict__ hi, float* __res
 }
 
 // cols: 8 kx lines of one image: FFT along y, Butterworth, operand planes + fy; Wiener multiply and inverse FFT along y.
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 3)
 ctf_cols_kernel(double2* __restrict__ T, int N, int Nh, FftPlan pl, const double2* __restrict__ Wg,
-                const double* __restrict__ C, const double* __restrict__ S, double2* __restrict__ fy_out,
+                const double* __restrict__ C, const double* __restrict__ S, const double* __restrict__ Gf, double2* __restrict__ fy_out,
                 float* __restrict__ q_hi, float* __restrict__ q_lo, int ldq,
                 float* __restrict__ a_hi, float* __restrict__ a_lo, float* __restrict__ b_hi, float* __restrict__ b_lo, int lda,
                 int do_wiener) {
     extern __shared__ double2 sm[];
     double2* W = sm; double2* A = W + N; double2* B = A + (size_t)LINES * N;
     const int img = blockIdx.y, kx0 = blockIdx.x * LINES;
+    const int l = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nl = min(LINES, Nh - kx0);
     const int Kh = Nh * N;
     load_twiddles(W, Wg, N);
-    double2* lines = T + ((size_t)img * Nh + kx0) * N;
-    for (int idx = threadIdx.x; idx < nl * N; idx += blockDim.x) A[idx] = lines[idx];
     __syncthreads();
-    double2* R = fft_lines(A, B, nl, pl, W, false);
-    double2* other = (R == A) ? B : A;
-    for (int idx = threadIdx.x; idx < nl * N; idx += blockDim.x) {
-        const int l = idx / N, ky = idx - l * N;
-        const int kx = kx0 + l;
+    if (l >= nl) return;                                               // no CTA-wide barrier below
+    const int kx = kx0 + l;
+    double2* line = T + ((size_t)img * Nh + kx) * N;
+    double2* a = A + (size_t)l * N; double2* b = B + (size_t)l * N;
+    for (int y0 = lane; y0 < N; y0 += 128) {
+        double2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = (y0 + 32 * u < N) ? line[y0 + 32 * u] : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (y0 + 32 * u < N) a[y0 + 32 * u] = v[u];
+    }
+    __syncwarp();
+    double2* R = fft_line(a, b, pl, W, false);
+    double2* other = (R == a) ? b : a;
+    const bool self = (kx == 0) || (2 * kx == N);
+    const double w = self ? 1.0 : 2.0, sw = self ? 1.0 : 1.4142135623730951;
+#pragma unroll 2
+    for (int ky = lane; ky < N; ky += 32) {
         const int k = kx * N + ky;
-        const double Q = grid_q(ky, kx, N);
-        const double G = sqrt(1.0 / (1.0 + pow(Q / 0.5, 16.0)));       // create_filter('Butter', 8, 0.5, Q)
+        const double G = Gf[k];
         const double c = C[(size_t)img * Kh + k];
-        const double2 F = R[idx];
+        const double2 F = R[ky];
         const double2 f = make_double2(G * F.x, G * F.y);
-        fy_out[(size_t)img * Kh + k] = f;
-        const bool self = (kx == 0) || (2 * kx == N);
-        const double w = self ? 1.0 : 2.0, sw = self ? 1.0 : 1.4142135623730951;
+        if (fy_out) fy_out[(size_t)img * Kh + k] = f;
         split_store(q_hi, q_lo, (size_t)img * ldq + k, sw * c * f.x);
         split_store(q_hi, q_lo, (size_t)img * ldq + Kh + k, sw * c * f.y);
         split_store(a_hi, a_lo, (size_t)img * lda + k, f.x * f.x + f.y * f.y);
         split_store(b_hi, b_lo, (size_t)img * lda + k, w * c * c);
         if (do_wiener) {
             const double t = c / (-(S[k] + 1.0 / 5.0));                // Distances.py:129,133 (gen_wiener SNR = 5)
-            other[idx] = make_double2(f.x * t, f.y * t);
+            other[ky] = make_double2(f.x * t, f.y * t);
         }
     }
     if (!do_wiener) return;
-    __syncthreads();
-    const double2* R2 = fft_lines(other, R, nl, pl, W, true);
-    for (int idx = threadIdx.x; idx < nl * N; idx += blockDim.x) lines[idx] = R2[idx];
+    __syncwarp();
+    const double2* R2 = fft_line(other, R, pl, W, true);
+    for (int y = lane; y < N; y += 32) line[y] = R2[y];
 }
 
 // irows: inverse FFT along x of 16 rows (two real rows per complex line) -> float32 Wiener image rows.
-__global__ void __launch_bounds__(THREADS) ctf_irows_kernel(const double2* __restrict__ T, int N, int Nh, FftPlan pl,
+__global__ void __launch_bounds__(THREADS, 3) ctf_irows_kernel(const double2* __restrict__ T, int N, int Nh, FftPlan pl,
                                                             const double2* __restrict__ Wg, float* __restrict__ wiener) {
     extern __shared__ double2 sm[];
     double2* W = sm; double2* A = W + N; double2* B = A + (size_t)LINES * N; double2* Hs = B + (size_t)LINES * N;
     const int img = blockIdx.y, y0 = blockIdx.x * 2 * LINES;
     load_twiddles(W, Wg, N);
-    for (int idx = threadIdx.x; idx < Nh * 2 * LINES; idx += blockDim.x) {
-        const int kx = idx / (2 * LINES), r = idx - kx * 2 * LINES;
-        const int y = y0 + r;
-        Hs[(size_t)r * Nh + kx] = y < N ? T[((size_t)img * Nh + kx) * N + y] : make_double2(0.0, 0.0);
+    for (int idx0 = threadIdx.x; idx0 < Nh * 2 * LINES; idx0 += 4 * THREADS) {     // 4 independent loads in flight per thread
+        double2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = idx0 + u * THREADS;
+            const int kx = idx >> 4, y = y0 + (idx & 15);
+            v[u] = (idx < Nh * 2 * LINES && y < N) ? T[((size_t)img * Nh + kx) * N + y] : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = idx0 + u * THREADS;
+            if (idx < Nh * 2 * LINES) Hs[(size_t)(idx & 15) * Nh + (idx >> 4)] = v[u];
+        }
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < LINES * N; idx += blockDim.x) {
-        const int l = idx / N, k = idx - l * N;
+    const int l = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double2* a = A + (size_t)l * N; double2* b = B + (size_t)l * N;
+    for (int k = lane; k < N; k += 32) {
         double2 ha, hb;
         if (k < Nh) { ha = Hs[(size_t)(2 * l) * Nh + k]; hb = Hs[(size_t)(2 * l + 1) * Nh + k]; }
         else { ha = Hs[(size_t)(2 * l) * Nh + (N - k)]; hb = Hs[(size_t)(2 * l + 1) * Nh + (N - k)]; ha.y = -ha.y; hb.y = -hb.y; }
-        A[idx] = make_double2(ha.x - hb.y, ha.y + hb.x);
+        a[k] = make_double2(ha.x - hb.y, ha.y + hb.x);
     }
-    __syncthreads();
-    const double2* R = fft_lines(A, B, LINES, pl, W, true);
+    __syncwarp();
+    const double2* R = fft_line(a, b, pl, W, true);
     const double inv = 1.0 / ((double)N * (double)N);
     float* dst = wiener + (size_t)img * N * N;
-    for (int idx = threadIdx.x; idx < LINES * N; idx += blockDim.x) {
-        const int l = idx / N, x = idx - l * N;
-        const int ya = y0 + 2 * l, yb = ya + 1;
-        const double2 v = R[idx];
+    const int ya = y0 + 2 * l, yb = ya + 1;
+    for (int x = lane; x < N; x += 32) {
+        const double2 v = R[x];
         if (ya < N) dst[(size_t)ya * N + x] = (float)(v.x * inv);
         if (yb < N) dst[(size_t)yb * N + x] = (float)(v.y * inv);
     }
@@ -389,8 +436,9 @@ int run_ctf_dist(esper_ctx* c, int n, int N, const double* params_h, unsigned fl
 
     ESPER_RESERVE(c, c->row_stats, sizeof(RowStat) * (size_t)n_pad);
     ESPER_RESERVE(c, c->ctf_T, sizeof(double2) * (size_t)n * Kh);
-    ESPER_RESERVE(c, c->ctf_fy, sizeof(double2) * (size_t)n * Kh);
-    ESPER_RESERVE(c, c->ctf_C, sizeof(double) * ((size_t)n * Kh + Kh));
+    const bool refine = (flags & ESPER_DIST_REFINE) && c->refine_tau > 0.0 && n > 1;
+    if (refine) ESPER_RESERVE(c, c->ctf_fy, sizeof(double2) * (size_t)n * Kh);
+    ESPER_RESERVE(c, c->ctf_C, sizeof(double) * ((size_t)n * Kh + (2 + (size_t)GEN_CHUNKS) * Kh));
     ESPER_RESERVE(c, c->plane_hi, sizeof(float) * (size_t)n_pad * ldq);
     ESPER_RESERVE(c, c->plane_lo, sizeof(float) * (size_t)n_pad * ldq);
     ESPER_RESERVE(c, c->ctf_ab, sizeof(float) * (size_t)4 * n_pad * lda);
@@ -399,16 +447,29 @@ int run_ctf_dist(esper_ctx* c, int n, int N, const double* params_h, unsigned fl
     if (want_wiener) ESPER_RESERVE(c, c->ctf_wiener, sizeof(float) * (size_t)n * P);
     RowStat* rs = c->row_stats.as<RowStat>();
     double2* T = c->ctf_T.as<double2>();
-    double2* fy = c->ctf_fy.as<double2>();
+    double2* fy = refine ? c->ctf_fy.as<double2>() : nullptr;
     double* C = c->ctf_C.as<double>();
     double* S = C + (size_t)n * Kh;
+    double* Gf = S + Kh;
+    double* Spart = Gf + Kh;
     float* q_hi = c->plane_hi.as<float>(); float* q_lo = c->plane_lo.as<float>();
     float* a_hi = c->ctf_ab.as<float>(); float* a_lo = a_hi + (size_t)n_pad * lda;
     float* b_hi = a_lo + (size_t)n_pad * lda; float* b_lo = b_hi + (size_t)n_pad * lda;
     double* T1 = c->ctf_T12.as<double>(); double* T2 = T1 + (size_t)n * n;
-    ESPER_CUDA(c, cudaMemsetAsync(q_hi, 0, sizeof(float) * (size_t)n_pad * ldq, st));     // padding rows / columns must be zero
-    ESPER_CUDA(c, cudaMemsetAsync(q_lo, 0, sizeof(float) * (size_t)n_pad * ldq, st));
-    ESPER_CUDA(c, cudaMemsetAsync(a_hi, 0, sizeof(float) * (size_t)4 * n_pad * lda, st));
+    // the padding (rows n..n_pad, columns K..ld) of the operand planes must be zero; the rest is overwritten
+    auto zero_pad = [&](float* plane, int K, int ld) -> cudaError_t {
+        cudaError_t e = cudaSuccess;
+        if (n_pad > n) e = cudaMemsetAsync(plane + (size_t)n * ld, 0, sizeof(float) * (size_t)(n_pad - n) * ld, st);
+        if (e == cudaSuccess && ld > K)
+            e = cudaMemset2DAsync(plane + K, sizeof(float) * (size_t)ld, 0, sizeof(float) * (size_t)(ld - K), (size_t)n, st);
+        return e;
+    };
+    ESPER_CUDA(c, zero_pad(q_hi, 2 * Kh, ldq));
+    ESPER_CUDA(c, zero_pad(q_lo, 2 * Kh, ldq));
+    ESPER_CUDA(c, zero_pad(a_hi, Kh, lda));
+    ESPER_CUDA(c, zero_pad(a_lo, Kh, lda));
+    ESPER_CUDA(c, zero_pad(b_hi, Kh, lda));
+    ESPER_CUDA(c, zero_pad(b_lo, Kh, lda));
 
     if (!c->attr_ctf) {
         ESPER_CUDA(c, cudaFuncSetAttribute(ctf_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -417,22 +478,23 @@ int run_ctf_dist(esper_ctx* c, int n, int N, const double* params_h, unsigned fl
         c->attr_ctf = true;
     }
     {
-        LaunchScope ls(c, "ctf_fft");
+        LaunchScope ls(c, "ctf_stats");
         const int rc_st = row_stats_numpy(c, n, P, rs);
         if (rc_st) return rc_st;
     }
-    { LaunchScope ls(c, "ctf_fft"); ctf_gen_kernel<<<ceil_div(Kh, 256), 256, 0, st>>>(N, Kh, n, par_d, C, S); }
+    { LaunchScope ls(c, "ctf_gen"); ctf_gen_kernel<<<dim3(ceil_div(Kh, 256), GEN_CHUNKS), 256, 0, st>>>(N, Kh, n, par_d, C, Spart, Gf); }
+    { LaunchScope ls(c, "ctf_gen"); ctf_sum_kernel<<<ceil_div(Kh, 256), 256, 0, st>>>(Kh, GEN_CHUNKS, Spart, S); }
     {
-        LaunchScope ls(c, "ctf_fft");
+        LaunchScope ls(c, "ctf_rows");
         ctf_rows_kernel<<<dim3(ceil_div(N, 2 * LINES), n), THREADS, smem_fft, st>>>(c->imgs.as<float>(), rs, N, Nh, pl, W_d, T);
     }
     {
-        LaunchScope ls(c, "ctf_fft");
-        ctf_cols_kernel<<<dim3(ceil_div(Nh, LINES), n), THREADS, smem_fft, st>>>(T, N, Nh, pl, W_d, C, S, fy, q_hi, q_lo, ldq,
+        LaunchScope ls(c, "ctf_cols");
+        ctf_cols_kernel<<<dim3(ceil_div(Nh, LINES), n), THREADS, smem_fft, st>>>(T, N, Nh, pl, W_d, C, S, Gf, fy, q_hi, q_lo, ldq,
                                                                                  a_hi, a_lo, b_hi, b_lo, lda, want_wiener ? 1 : 0);
     }
     if (want_wiener) {
-        LaunchScope ls(c, "ctf_fft");
+        LaunchScope ls(c, "ctf_irows");
         ctf_irows_kernel<<<dim3(ceil_div(N, 2 * LINES), n), THREADS, smem_irows, st>>>(T, N, Nh, pl, W_d, c->ctf_wiener.as<float>());
     }
     ESPER_CUDA(c, cudaGetLastError());
@@ -442,7 +504,6 @@ int run_ctf_dist(esper_ctx* c, int n, int N, const double* params_h, unsigned fl
     rc = run_product(c, b_hi, b_lo, n, a_hi, a_lo, n, lda, T1);
     if (rc) return rc;
 
-    const bool refine = (flags & ESPER_DIST_REFINE) && c->refine_tau > 0.0 && n > 1;
     int2* pairs = nullptr; unsigned int* count = nullptr; unsigned int cap = 0;
     if (refine) {
         const size_t max_pairs = (size_t)n * (n - 1) / 2;
