@@ -169,9 +169,9 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def embed_step(ctx, GB, coef, a0, n, p, imgs=None, download=False):
-    """One PD through stages 1-3 on `ctx`.  imgs=None -> the ctx-resident stack."""
-    D = ctx.dist_rms(imgs, n=n, P=p, download=download)
+def embed_step(ctx, GB, coef, a0, n, p, imgs=None, download=False, out=None):
+    """One PD through stages 1-3 on `ctx`.  imgs=None -> the ctx-resident stack; out = caller buffer for D."""
+    D = ctx.dist_rms(imgs, n=n, P=p, download=download, out=out)
     L = ctx.eps_sweep(None, coef, 10.0, m=n)
     popt, resnorm, R2 = GB.fit(LOG_EPS, L, a0)
     eps = float(np.exp(-(popt[1] / popt[0])))
@@ -231,7 +231,8 @@ def run_ours(args):
                 torch.cuda.set_device(local_rank)
                 for s in range(t, n_steps, NF):
                     if e2e:
-                        embed_step(ctxs[t], GB, coef, a0, N_IMG, P, imgs=pinned[t % n_stacks].numpy(), download=True)
+                        embed_step(ctxs[t], GB, coef, a0, N_IMG, P, imgs=pinned[t % n_stacks].numpy(), download=True,
+                                   out=d_out[t].numpy())
                     else:
                         out = embed_step(ctxs[t], GB, coef, a0, N_IMG, P)
                         iters_used.append(out[4])
@@ -291,9 +292,24 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     launches = sum(c.launch_count() for c in ctxs) - launches0
 
-    # ---- end-to-end arm: host stacks -> H2D -> stages -> D2H of D, sweep, eigenpairs (two in flight) ----
+    # ---- end-to-end arm: host stacks -> H2D -> stages -> D2H of D, sweep, eigenpairs (NF in flight) ----
+    # The caller owns the output buffers; here they are page-locked like the input stacks.
+    d_out = [torch.empty((N_IMG, N_IMG), dtype=torch.float64).pin_memory() for _ in range(NF)]
     pipelined(NF, True)
     ms_e2e = pipelined(args.steps, True)
+
+    # raw host->device rate of this box for one 500 MB stack (what bounds the e2e figure)
+    probe = torch.empty((N_IMG, P), dtype=torch.float32, device='cuda')
+    probe.copy_(pinned[0], non_blocking=True)
+    torch.cuda.synchronize()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(4):
+        probe.copy_(pinned[0], non_blocking=True)
+    p1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 4 * N_IMG * P * 4 / (p0.elapsed_time(p1) * 1e-3) / 1e9
+    del probe
 
     tms = torch.tensor([ms, ms_e2e, float(launches), ms_serial], dtype=torch.float64, device='cuda')
     if world > 1:
@@ -342,7 +358,9 @@ def run_ours(args):
                    'lanczos_steps': iters_used[-1] if iters_used else None},
         'e2e': {'value': pds / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(N_IMG * P * 4),
                 'd2h_bytes_per_step': int(N_IMG * N_IMG * 8 + len(LOG_EPS) * 8 + K_EIG * 8 + N_IMG * K_EIG * 8),
-                'ms_per_step': ms_e2e / args.steps},
+                'ms_per_step': ms_e2e / args.steps, 'h2d_probe_gbs': round(h2d_gbs, 2),
+                'h2d_floor_ms_per_step': round(N_IMG * P * 4 / (h2d_gbs * 1e9) * 1e3, 3),
+                'note': 'bounded by the host->device copy of the 500 MB stack (probe: bare pinned cudaMemcpyAsync rate on this box)'},
         'gpu_launches': launches,
         'clocks': clocks,
         'roofline': {'bound': 'tensor', 'kernel': 'gram_kernel (tcgen05 kind::tf32, 3xTF32, upper triangle)',

@@ -53,7 +53,7 @@ int         esper_sync(esper_ctx* ctx);                 /* cudaStreamSynchronize
 /* Per-kernel CUDA-event timing of the calls that follow (off by default). */
 int         esper_set_profiling(esper_ctx* ctx, int on);
 /* Sum / count of the kernel launches recorded under `name` since the last reset.
- * names: "prep", "gram", "dist_finalize", "refine", "sweep", "markov", "lanczos", "rot".    */
+ * names: "prep", "gram", "dist_finalize", "refine", "sweep", "markov", "lanczos", "rot", "conic".    */
 int         esper_get_kernel_ms(esper_ctx* ctx, const char* name, double* total_ms, int* launches);
 int         esper_reset_profiling(esper_ctx* ctx);
 /* Total kernels launched by this ctx since creation (the bench's `gpu_launches` claim). */
@@ -203,12 +203,27 @@ int esper_rot_hist_eval(esper_ctx* ctx, const double* Uinit, int n_pd, int m, in
  * n_theta angles, keep the FIRST argmax of the empty-bin score, move on to the next Rij.
  *   combo:  [n_pd, max_sub, 2] int (v1, v2), n_sub: [n_pd];  rij: [n_pd, n_rij] int
  *   theta_grid: [n_theta] radians (np.arange(start,stop,step)*pi/180 computed by the caller)
+ *   Uinit == NULL: the [n_pd, m, dim] manifolds left on the device by esper_manifold_prepare
  *   thetas_out: [n_pd, max_sub, T] radians (rows >= n_sub[p] are zero)
  *   counts_out (optional): [n_pd, max_sub, n_rij, n_theta] non-zero-bin counts               */
 int esper_rot_sweep(esper_ctx* ctx, const double* Uinit, int n_pd, int m, int dim,
                     const int* combo, const int* n_sub, int max_sub, const int* rij, int n_rij,
                     const double* theta_grid, int n_theta, int bins, double lo, double hi,
                     double* thetas_out, int* counts_out);
+
+/* ---- stage-4 preparation on the device ---------------------------------------
+ * esper_manifold_prepare: Rotation_Histograms.py:100-112 -- `normalize` (every column of U0 to [0,1], then the whole
+ * matrix to [-1,1]; bit-identical to numpy) and the slice U[:, first:first+dim] (first = 1 for diffusion maps, 0 for
+ * PCA); then, when kind != 0, the conic fits of findParabolas (:153-212) for every column pair v1 < v2:
+ * kind 2 = 3_Manifold_Binning/ConicFit.py:205-264 (`fit2`), kind 3 = ConicFit.py:267-283 (`fit3`).
+ *   U0: [n_pd, m, ncol]; Uinit (optional out): [n_pd, m, dim] -- it also stays resident on the device, and a following
+ *   esper_rot_sweep / esper_conic_fit_batch with Uinit == NULL uses that copy;
+ *   R2: [n_pd, dim(dim-1)/2] coefficient of determination per pair in lexicographic order (0,1),(0,2),...;
+ *   coef (optional): [n_pd, pairs, 5] fit coefficients (fit2: B, C, D, E, F of x^2+Bxy+Cy^2+Dx+Ey+F; fit3: a, b, c, 0, 0). */
+int esper_manifold_prepare(esper_ctx* ctx, const double* U0, int n_pd, int m, int ncol, int first, int dim, int kind,
+                           double* Uinit, double* R2, double* coef);
+/* The conic fits alone on caller-supplied (already normalised / pre-rotated) manifolds Uinit [n_pd, m, dim]. */
+int esper_conic_fit_batch(esper_ctx* ctx, const double* Uinit, int n_pd, int m, int dim, int kind, double* R2, double* coef);
 
 #ifdef __cplusplus
 }

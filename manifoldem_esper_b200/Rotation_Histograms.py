@@ -1,10 +1,12 @@
 """Optimal Nd eigen-rotations per PD by 2-D histogram sweeps (interface of
 2_Manifold_Rotations/Rotation_Histograms.py).
 
-Host side (this file): manifold normalisation (:100-112), parabola detection with conic fits
-(:153-212) and the comboList / Rij bookkeeping (:217-281).  Device side (K5, esper_rot_sweep):
-the whole theta search (:283-365) for any number of PDs in one call.  `op(pyDir, PD)` reads and
-writes the same files as the reference; `sweep_many` is the batched entry the launcher uses.
+Device side: manifold normalisation (:100-112) and the conic fits of the parabola detection (:153-212) for
+every column pair of any number of PDs (esper_manifold_prepare, k7_conic.cu); the whole theta search
+(:283-365) for any number of PDs (K5, esper_rot_sweep).  Host side (this file): the partner selection
+from the R^2 table, the comboList / Rij bookkeeping (:217-281) and the files.  `op(pyDir, PD)` reads and
+writes the same files as the reference; `prepare_many` + `sweep_many` (or `run_many`) are the batched entries
+the launcher uses.  `prepare` / `findParabolas` are the host-only (numpy) statement of the same preparation.
 """
 import os
 import sys
@@ -88,6 +90,64 @@ def prepare(U0, dim=6, PCA=False, CTF=True):
                 comboFinal=comboFinal, Rij_final=Rij_final, itIdx=itIdx)
 
 
+def select_partners(dim, R2_pairs):
+    """Partner selection of findParabolas (:159-177) given R^2 of every pair v1 < v2 in lexicographic order."""
+    R2_best_vals = np.zeros(dim - 1, dtype=float)
+    R2_best_psi = np.zeros(dim - 1, dtype=int)
+    q = 0
+    for v1 in range(dim - 1):
+        R2_best = 0
+        for v2 in range(v1 + 1, dim):
+            R2 = R2_pairs[q]
+            q += 1
+            if R2 > R2_best and v2 != R2_best_psi[0]:
+                R2_best = R2
+                R2_best_vals[v1] = R2
+                R2_best_psi[v1] = v2
+    return R2_best_psi, R2_best_vals
+
+
+def prepare_many(U0s, dim=6, PCA=False, CTF=True, ctx=None):
+    """`prepare` for a batch of equally shaped manifolds with the normalisation and all dim(dim-1)/2 conic fits
+    per PD on the GPU (one esper_manifold_prepare call).  Returns the list of prep dicts; `preps[0]['resident']`
+    is the token `sweep_many` compares with the ctx to know that the device still holds exactly these U_init."""
+    ctx = ctx or _capi.default_context()
+    U0 = np.stack([np.asarray(u, dtype=np.float64) for u in U0s])
+    kind = 2 if CTF else 3
+    Ui, R2 = ctx.manifold_prepare(U0, dim, first=0 if PCA else 1, kind=kind)
+    n_pd = U0.shape[0]
+    psi, itIdx = [None] * n_pd, [1] * n_pd
+    retry = []
+    for i in range(n_pd):
+        psi[i], vals = select_partners(dim, R2[i])
+        if vals[0] < 0.2:                                   # rare pre-rotation retry (:202-209)
+            retry.append(i)
+    if retry:
+        thetas = np.zeros(shape=(int(dim * (dim - 1) / 2), 1), dtype=float)
+        thetas[0] = 45 * np.pi / 180
+        R = Generate_Nd_Rot.genNdRotations(dim, thetas)
+        for i in retry:
+            Ui[i] = np.matmul(R, Ui[i].T).T
+            itIdx[i] = 2
+        R2r = ctx.conic_fit_batch(np.ascontiguousarray(Ui[retry]), kind=kind)
+        for j, i in enumerate(retry):
+            psi[i], _ = select_partners(dim, R2r[j])
+    token = None if retry else ctx.rot_token           # a retry changed U_init on the host: upload again for the sweep
+    preps = []
+    for i in range(n_pd):
+        comboList, saveEigs, comboFinal, Rij_final = plan(dim, psi[i])
+        preps.append(dict(U_init=Ui[i], comboList=comboList, saveEigs=saveEigs, comboFinal=comboFinal,
+                          Rij_final=Rij_final, itIdx=itIdx[i], R2=R2[i], resident=token))
+    return preps
+
+
+def run_many(U0s, dim=6, PCA=False, CTF=True, ctx=None):
+    """Normalise, fit, plan and sweep a batch of manifolds -> (preps, list of thetas_all)."""
+    ctx = ctx or _capi.default_context()
+    preps = prepare_many(U0s, dim=dim, PCA=PCA, CTF=CTF, ctx=ctx)
+    return preps, sweep_many(preps, dim, ctx=ctx)
+
+
 def theta_grid():
     return np.arange(THETA_START, THETA_STOP, THETA_STEP) * np.pi / 180
 
@@ -105,7 +165,9 @@ def sweep_many(preps, dim, ctx=None, want_counts=False):
     if any(len(p['Rij_final']) != n_rij for p in preps):
         raise ValueError('all PDs of one batch must have the same number of Rij operators')
     m = preps[0]['U_init'].shape[0]
-    U = np.stack([p['U_init'] for p in preps]).astype(np.float64)
+    tok = getattr(ctx, 'rot_token', None)                          # device copy left by prepare_many, still current?
+    resident = tok is not None and all(p.get('resident') is tok for p in preps)
+    U = None if resident else np.stack([p['U_init'] for p in preps]).astype(np.float64)
     combo = np.zeros((n_pd, max_sub, 2), dtype=np.int32)
     n_sub = np.zeros(n_pd, dtype=np.int32)
     rij = np.zeros((n_pd, max(n_rij, 1)), dtype=np.int32)
@@ -115,7 +177,8 @@ def sweep_many(preps, dim, ctx=None, want_counts=False):
         n_sub[i] = len(p['comboList'])
         combo[i, :n_sub[i]] = np.array(p['comboList'], dtype=np.int32)
         rij[i, :n_rij] = p['Rij_final']
-    res = ctx.rot_sweep(U, combo, n_sub, rij[:, :n_rij], theta_grid(), BINS, HIST_LO, HIST_HI, want_counts=want_counts)
+    res = ctx.rot_sweep(U, combo, n_sub, rij[:, :n_rij], theta_grid(), BINS, HIST_LO, HIST_HI, want_counts=want_counts,
+                        shape=(n_pd, m, dim))
     thetas, counts = res if want_counts else (res, None)
     out = []
     for i, p in enumerate(preps):
@@ -141,7 +204,7 @@ def op(pyDir, PD, dim=6, PCA=False, CTF=True, maniPath=None, ctx=None):
             maniPath = os.path.join(parDir, '1_Embedding/DM/Data_Manifolds/PD_%s_vec.npy' % PD)
     U0 = np.load(maniPath)
     print('Manifold Info:', np.shape(U0))
-    prep = prepare(U0, dim=dim, PCA=PCA, CTF=CTF)
+    prep = prepare_many([U0], dim=dim, PCA=PCA, CTF=CTF, ctx=ctx)[0]
     print('Parabolic subspaces:', prep['comboList'])
     print('Rij:', prep['comboFinal'])
     print('Rij indices:', prep['Rij_final'])

@@ -68,6 +68,9 @@ SIGNATURES = {
     'esper_rot_sweep': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                   C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
                                   C.c_void_p, C.c_void_p]),
+    'esper_manifold_prepare': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    'esper_conic_fit_batch': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }
 
 
@@ -114,6 +117,7 @@ class Context:
         if not self._h:
             raise EsperError(self._lib.esper_last_error(None).decode())
         self.device = int(device)
+        self.rot_token = None          # identifies the batch of normalised manifolds resident on the device
 
     def close(self):
         if getattr(self, '_h', None):
@@ -325,13 +329,52 @@ class Context:
             raise ValueError('rot_hist_eval: R, pd_of_eval, v1, v2 must have one entry per evaluation')
         nz = np.empty(ne, dtype=np.int32)
         H = np.empty((ne, bins, bins), dtype=np.int32) if want_hist else None
+        self.rot_token = None
         self._check(self._lib.esper_rot_hist_eval(self._h, _ptr(Uinit), n_pd, m, dim, _ptr(R), _ptr(pd_of_eval), _ptr(v1),
                                                   _ptr(v2), ne, int(bins), float(lo), float(hi), _ptr(nz), _ptr(H)))
         return (nz, H) if want_hist else nz
 
-    def rot_sweep(self, Uinit, combo, n_sub, rij, theta_grid, bins=51, lo=-1.5, hi=1.5, want_counts=False):
-        Uinit = _as(Uinit, np.float64)
-        n_pd, m, dim = Uinit.shape
+    def manifold_prepare(self, U0, dim, first, kind=2, want_coef=False):
+        """Rotation_Histograms.py:100-112 (normalize + slice) and the conic fits of findParabolas (:153-212) for a
+        batch of manifolds U0 [n_pd, m, ncol] -> (Uinit [n_pd, m, dim], R2 [n_pd, pairs] or None[, coef]).  The
+        normalised manifolds stay resident for rot_sweep(None, ..., shape=...) / conic_fit_batch(None, ...)."""
+        U0 = _as(U0, np.float64)
+        if U0.ndim == 2:
+            U0 = U0[None]
+        n_pd, m, ncol = U0.shape
+        dim = int(dim)
+        n_pairs = dim * (dim - 1) // 2
+        Ui = np.empty((n_pd, m, dim), dtype=np.float64)
+        R2 = np.empty((n_pd, n_pairs), dtype=np.float64) if kind else None
+        coef = np.empty((n_pd, n_pairs, 5), dtype=np.float64) if (kind and want_coef) else None
+        self.rot_token = None
+        self._check(self._lib.esper_manifold_prepare(self._h, _ptr(U0), n_pd, m, ncol, int(first), dim, int(kind),
+                                                     _ptr(Ui), _ptr(R2), _ptr(coef)))
+        self.rot_token = object()
+        return (Ui, R2, coef) if want_coef else (Ui, R2)
+
+    def conic_fit_batch(self, Uinit, kind=2, shape=None, want_coef=False):
+        """ConicFit.fit2 (kind 2) / fit3 (kind 3) for every column pair of every manifold -> R2 [n_pd, pairs]."""
+        if Uinit is not None:
+            Uinit = _as(Uinit, np.float64)
+            if Uinit.ndim == 2:
+                Uinit = Uinit[None]
+            shape = Uinit.shape
+            self.rot_token = None
+        n_pd, m, dim = (int(x) for x in shape)
+        n_pairs = dim * (dim - 1) // 2
+        R2 = np.empty((n_pd, n_pairs), dtype=np.float64)
+        coef = np.empty((n_pd, n_pairs, 5), dtype=np.float64) if want_coef else None
+        self._check(self._lib.esper_conic_fit_batch(self._h, _ptr(Uinit), n_pd, m, dim, int(kind), _ptr(R2), _ptr(coef)))
+        return (R2, coef) if want_coef else R2
+
+    def rot_sweep(self, Uinit, combo, n_sub, rij, theta_grid, bins=51, lo=-1.5, hi=1.5, want_counts=False, shape=None):
+        """Uinit=None with shape=(n_pd, m, dim): the manifolds left resident by manifold_prepare."""
+        if Uinit is not None:
+            Uinit = _as(Uinit, np.float64)
+            shape = Uinit.shape
+            self.rot_token = None
+        n_pd, m, dim = (int(x) for x in shape)
         combo = _as(combo, np.int32)
         max_sub = combo.shape[1]
         n_sub = _as(n_sub, np.int32).reshape(-1)

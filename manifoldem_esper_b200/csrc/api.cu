@@ -449,10 +449,33 @@ int esper_rot_sweep(esper_ctx* c, const double* Uinit, int n_pd, int m, int dim,
                     const int* n_sub, int max_sub, const int* rij, int n_rij, const double* theta_grid,
                     int n_theta, int bins, double lo, double hi, double* thetas_out, int* counts_out) {
     ESPER_ENTER(c);
-    if (!Uinit || !combo || !n_sub || (!rij && n_rij > 0) || !theta_grid || !thetas_out || n_pd < 1 || m < 1)
+    if (!combo || !n_sub || (!rij && n_rij > 0) || !theta_grid || !thetas_out || n_pd < 1 || m < 1)
         return fail(c, ESPER_E_ARG, "rot_sweep: NULL argument or empty batch");
+    if (!Uinit && (c->rot_n_pd != n_pd || c->rot_m != m || c->rot_dim != dim))
+        return fail(c, ESPER_E_STATE, "rot_sweep: Uinit == NULL but no resident [%d, %d, %d] manifolds (resident: [%d, %d, %d])",
+                    n_pd, m, dim, c->rot_n_pd, c->rot_m, c->rot_dim);
     return run_rot_sweep(c, Uinit, n_pd, m, dim, combo, n_sub, max_sub, rij, n_rij, theta_grid, n_theta, bins, lo,
                          hi, thetas_out, counts_out);
+}
+
+int esper_manifold_prepare(esper_ctx* c, const double* U0, int n_pd, int m, int ncol, int first, int dim, int kind,
+                           double* Uinit, double* R2, double* coef) {
+    ESPER_ENTER(c);
+    if (!U0 || (kind != 0 && !R2)) return fail(c, ESPER_E_ARG, "manifold_prepare: U0 (and R2 when kind != 0) must not be NULL");
+    c->rot_n_pd = 0;
+    int rc = run_manifold_prepare(c, U0, n_pd, m, ncol, first, dim, kind, Uinit, R2, coef);
+    if (rc == ESPER_OK) { c->rot_n_pd = n_pd; c->rot_m = m; c->rot_dim = dim; }
+    return rc;
+}
+
+int esper_conic_fit_batch(esper_ctx* c, const double* Uinit, int n_pd, int m, int dim, int kind, double* R2, double* coef) {
+    ESPER_ENTER(c);
+    if (!Uinit && (c->rot_n_pd != n_pd || c->rot_m != m || c->rot_dim != dim))
+        return fail(c, ESPER_E_STATE, "conic_fit_batch: Uinit == NULL but no resident [%d, %d, %d] manifolds", n_pd, m, dim);
+    if (Uinit) c->rot_n_pd = 0;
+    int rc = run_conic_fits(c, Uinit, n_pd, m, dim, kind, R2, coef);
+    if (rc == ESPER_OK && Uinit) { c->rot_n_pd = n_pd; c->rot_m = m; c->rot_dim = dim; }
+    return rc;
 }
 
 }  // extern "C"

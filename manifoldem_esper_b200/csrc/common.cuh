@@ -97,6 +97,7 @@ struct esper_ctx {
     esper::DevBuf lan_V, lan_w, lan_h, lan_small;              // Lanczos basis etc.
     // stage-4 workspaces
     esper::DevBuf rot_U, rot_R, rot_idx, rot_out, rot_H, rot_theta, rot_aux;
+    int rot_n_pd = 0, rot_m = 0, rot_dim = 0;                  // shape of the normalised manifolds resident in rot_U
     esper::PinBuf pin;                                         // small pinned staging area
 };
 
@@ -180,6 +181,9 @@ int run_symv_rows(esper_ctx* c, int rows, int m, const double* q_d, double* w_ro
 int run_lanczos_start(esper_ctx* c, int m, const double* degree_all_h, double* V_d);
 int run_lanczos_ortho(esper_ctx* c, int m, int j, double* V_d, double* w_d, double* ab_d);
 int run_ritz_vectors(esper_ctx* c, int m, int steps, int k, const double* V_d, const double* S_h, double* vec_h);
+int run_manifold_prepare(esper_ctx* c, const double* U0, int n_pd, int m, int ncol, int first, int dim, int kind,
+                         double* Uinit_h, double* R2_h, double* coef_h);
+int run_conic_fits(esper_ctx* c, const double* Uinit, int n_pd, int m, int dim, int kind, double* R2_h, double* coef_h);
 void nd_rotation_host(int n, const double* theta, double* R);
 void hist_edges_host(int bins, double lo, double hi, double* edges);
 

@@ -11,12 +11,13 @@
 //   over its chunk in TMEM and writes an FP32 partial tile; chains are kept short (<= ~2048 pixels)
 //   because tensor-core FP32 accumulation is not round-to-nearest; partials are summed in FP64.
 //
-// Kernel structure (one CTA per SM, persistent over units, 192 threads):
+// Kernel structure (one CTA per SM, persistent over units, 320 threads):
 //   warp 0     TMA producer   (cp.async.bulk.tensor.2d, 128B swizzle, mbarrier complete_tx)
 //   warp 1     MMA issuer     (tcgen05.mma.cta_group::1.kind::tf32, one elected lane) + TMEM alloc
-//   warps 2-5  epilogue       (tcgen05.ld 32x32b -> registers -> coalesced FP32 partial tile)
+//   warps 2-9  epilogue       (tcgen05.ld 32x32b -> registers -> coalesced FP32 partial tile); warps w and
+//                             w+4 share a TMEM lane quadrant and take 64 of the 128 columns each
 //   smem ring: 3 stages x {A_hi, A_lo, B_hi, B_lo} x (128 rows x 32 fp32) = 3 x 64 KB
-//   TMEM: 2 accumulator buffers x 128 columns (double buffered against the epilogue)
+//   TMEM: 4 accumulator buffers x 128 columns (the MMA warp runs up to 3 groups ahead of the drains)
 #include <cuda.h>
 #include "common.cuh"
 #include "devutil.cuh"
@@ -31,9 +32,10 @@ constexpr int UK = 8;                   // UMMA K for kind::tf32 (32 bytes)
 constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4; // 16 KB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;
-constexpr int ACC_STAGES = 2;
-constexpr int TMEM_COLS = ACC_STAGES * BN;  // 256
-constexpr int NUM_THREADS = 192;
+constexpr int ACC_STAGES = 4;
+constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512: the whole tensor memory of the SM (one CTA per SM)
+constexpr int EPI_WARPS = 8;                // two warps per TMEM lane quadrant, 64 columns each
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
 // ------------------------------------------------------------------------------------------------
@@ -143,8 +145,10 @@ __device__ __forceinline__ void tile_map(int t, int nt, int rect_ti0, int& ta, i
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gram_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
             const __grid_constant__ CUtensorMap mapb_hi, const __grid_constant__ CUtensorMap mapb_lo,
-            int nt, int n_tiles, int tile0, int rect_ti0, int nkb, int split_k, int drain_kb, float* __restrict__ part) {
+            int nt, int n_tiles, int tile0, int rect_ti0, int nkb, int split_k, int drain_kb_arg, float* __restrict__ part) {
     extern __shared__ uint8_t smem_raw[];
+    const bool skip_drain_loads = drain_kb_arg < 0;      // diagnostics only (ESPER_DRAIN_KB=-d): groups without TMEM reads
+    const int drain_kb = drain_kb_arg < 0 ? -drain_kb_arg : drain_kb_arg;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // 1024-byte aligned operand ring
     const uint32_t bars = base + STAGES * STAGE_BYTES;
     const uint32_t full_bar = bars;                                     // STAGES x 8 B
@@ -165,7 +169,7 @@ gram_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
         tma_prefetch_desc(&mapb_hi);
         tma_prefetch_desc(&mapb_lo);
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
-        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar + 8 * a, 1); mbar_init(tempty_bar + 8 * a, 4); }
+        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar + 8 * a, 1); mbar_init(tempty_bar + 8 * a, EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -249,13 +253,15 @@ gram_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..9) =====================
         const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+        const int half = (warp - 2) >> 2;          // which 64 of the 128 accumulator columns
         const int row = quad * 32 + lane;          // tile row held by this thread
+        constexpr int HC = BN / 2;
         int acc = 0; uint32_t acc_phase = 0;
-        float sum[BN];                              // round-to-nearest FP32 accumulators of this thread's tile row
+        float sum[HC];                              // round-to-nearest FP32 accumulators of this thread's half row
 #pragma unroll
-        for (int q = 0; q < BN; ++q) sum[q] = 0.f;
+        for (int q = 0; q < HC; ++q) sum[q] = 0.f;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
             const int chunk = u / n_tiles;
             const int kb0 = (int)((long long)nkb * chunk / split_k);
@@ -263,22 +269,29 @@ gram_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
             for (int g0 = kb0; g0 < kb1; g0 += drain_kb) {
                 mbar_wait(tfull_bar + 8 * acc, acc_phase);
                 tc_fence_after();
-#pragma unroll
-                for (int cc = 0; cc < BN / 32; ++cc) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + cc * 32), r);
+                uint32_t r0[32], r1[32];
+                const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * HC);
+                if (!skip_drain_loads) {
+                    tmem_ld32(ta, r0);              // both loads in flight before the wait
+                    tmem_ld32(ta + 32, r1);
                     tmem_ld_wait();
+                } else {
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) sum[cc * 32 + q] = __fadd_rn(sum[cc * 32 + q], __uint_as_float(r[q]));
+                    for (int q = 0; q < 32; ++q) { r0[q] = 0u; r1[q] = 0u; }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+                if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);     // values are in registers: release the buffer
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    sum[q] = __fadd_rn(sum[q], __uint_as_float(r0[q]));
+                    sum[32 + q] = __fadd_rn(sum[32 + q], __uint_as_float(r1[q]));
+                }
                 if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             }
-            float4* out = reinterpret_cast<float4*>(part + (size_t)u * (BM * BN));
+            float4* out = reinterpret_cast<float4*>(part + (size_t)u * (BM * BN)) + (size_t)half * (HC / 4) * BM;
 #pragma unroll
-            for (int q4 = 0; q4 < BN / 4; ++q4) {
+            for (int q4 = 0; q4 < HC / 4; ++q4) {
                 out[(size_t)q4 * BM + row] = make_float4(sum[4 * q4], sum[4 * q4 + 1], sum[4 * q4 + 2], sum[4 * q4 + 3]);
                 sum[4 * q4] = 0.f; sum[4 * q4 + 1] = 0.f; sum[4 * q4 + 2] = 0.f; sum[4 * q4 + 3] = 0.f;
             }
@@ -585,7 +598,7 @@ int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, i
     float* part = c->gram_part.as<float>();
 
     int drain_kb = c->drain_kb > 0 ? c->drain_kb : 2;
-    if (const char* e = getenv("ESPER_DRAIN_KB")) { const int v = atoi(e); if (v > 0) drain_kb = v; }   // experiments only
+    if (const char* e = getenv("ESPER_DRAIN_KB")) { const int v = atoi(e); if (v != 0) drain_kb = v; }   // experiments only
     for (int tile0 = 0; tile0 < tiles_total; tile0 += batch) {
         const int nb = (tiles_total - tile0 < batch) ? tiles_total - tile0 : batch;
         int sk = choose_split_k(c->split_k, nkb, nb, sms);

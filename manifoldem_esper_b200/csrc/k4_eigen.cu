@@ -1115,10 +1115,19 @@ static int lanczos_attempt(esper_ctx* c, int m, int k, double tol, int max_iter,
         }
         if (resident) {
             lan_smem = sizeof(double) * ((size_t)LAN_CH + (size_t)rows_cached * m);
-            if ((size_t)c->lanczos_smem_set < lan_smem) {
-                ESPER_CUDA(c, cudaFuncSetAttribute(lanczos_resident_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lan_smem));
-                c->lanczos_smem_set = (long long)lan_smem;
+            // The opt-in is a property of the function in this process (not of the ctx): a smaller value set through
+            // another ctx would LOWER the limit and make this launch fail.  Opt in to the device maximum, once per ctx.
+            if (!c->lanczos_smem_set) {
+                int optin = 0;
+                cudaFuncAttributes fa;
+                ESPER_CUDA(c, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+                ESPER_CUDA(c, cudaFuncGetAttributes(&fa, lanczos_resident_kernel<true>));
+                ESPER_CUDA(c, cudaFuncSetAttribute(lanczos_resident_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   optin - (int)fa.sharedSizeBytes));
+                c->lanczos_smem_set = optin - (long long)fa.sharedSizeBytes;
             }
+            if ((long long)lan_smem > c->lanczos_smem_set)
+                return fail(c, ESPER_E_STATE, "lanczos: %zu bytes of shared memory requested, %lld available", lan_smem, c->lanczos_smem_set);
             ESPER_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lanczos_resident_kernel<true>, LAN_THREADS, lan_smem));
         } else if (small) {
             rows_cached = 0;

@@ -197,6 +197,7 @@ int run_rot_eval(esper_ctx* c, const double* Uinit, int n_pd, int m, int dim, co
     std::vector<double> edges(bins + 1);
     hist_edges_host(bins, lo, hi, edges.data());
     int rc;
+    c->rot_n_pd = 0;                                   // rot_U no longer holds esper_manifold_prepare's output
     if ((rc = upload(c, c->rot_U, Uinit, sizeof(double) * (size_t)n_pd * m * dim))) return rc;
     if ((rc = upload(c, c->rot_R, R, sizeof(double) * (size_t)n_eval * dim * dim))) return rc;
     std::vector<int> idx((size_t)3 * n_eval);
@@ -247,7 +248,11 @@ int run_rot_sweep(esper_ctx* c, const double* Uinit, int n_pd, int m, int dim, c
     double* cg = tab.data() + bins + 1; double* sg = cg + n_theta; double* tg = sg + n_theta;
     for (int t = 0; t < n_theta; ++t) { cg[t] = cos(theta_grid[t]); sg[t] = sin(theta_grid[t]); tg[t] = theta_grid[t]; }
     int rc;
-    if ((rc = upload(c, c->rot_U, Uinit, sizeof(double) * (size_t)n_pd * m * dim))) return rc;
+    if (Uinit) {                                       // NULL: manifolds left resident by esper_manifold_prepare
+        c->rot_n_pd = 0;
+        if ((rc = upload(c, c->rot_U, Uinit, sizeof(double) * (size_t)n_pd * m * dim))) return rc;
+        c->rot_n_pd = n_pd; c->rot_m = m; c->rot_dim = dim;
+    }
     if ((rc = upload(c, c->rot_theta, tab.data(), sizeof(double) * tab.size()))) return rc;
     std::vector<int> idx((size_t)n_pd * max_sub * 2 + n_pd + (size_t)n_pd * (n_rij > 0 ? n_rij : 1));
     memcpy(idx.data(), combo, sizeof(int) * (size_t)n_pd * max_sub * 2);

@@ -453,6 +453,77 @@ def test_rotation_sweep_vs_reference_run(ctx, dim):
             assert np.array_equal(counts[i, :len(preps[i]['comboList'])].reshape(-1), cnt[k])
 
 
+@pytest.mark.parametrize('dim', [6, 8])
+def test_device_prepare_and_sweep_vs_reference_run(ctx, dim):
+    """normalisation + all conic fits on the device (esper_manifold_prepare), partner selection on the
+    host, sweep on the manifolds left resident: outputs equal the reference run's files bit for bit."""
+    fx, ref = golden('rot_inputs.npz'), golden('rot_ref_dim%d.npz' % dim)
+    keys = list(fx.keys())
+    preps, thetas = RH.run_many([fx[k] for k in keys], dim=dim, PCA=True, CTF=True, ctx=ctx)
+    assert preps[0]['resident'] is not None                 # no retry: the sweep used the device-resident manifolds
+    for i, k in enumerate(keys):
+        host = RH.prepare(fx[k], dim=dim, PCA=True, CTF=True)
+        assert np.array_equal(preps[i]['U_init'], host['U_init']), k          # normalisation is bit-identical
+        assert preps[i]['comboList'] == host['comboList'] and preps[i]['Rij_final'] == host['Rij_final']
+        assert np.array_equal(thetas[i], ref['RotMatrices_' + k[2:]]), k
+        assert np.array_equal(preps[i]['saveEigs'], ref['RotEigenfunctions_' + k[2:]])
+
+
+@pytest.mark.parametrize('kind', [2, 3])
+def test_conic_fits_vs_host_rref(ctx, kind):
+    """R^2 and coefficients of every pair equal the oracle's (the reference's sympy `rref` solve) to rounding."""
+    fx = golden('rot_inputs.npz')
+    keys = list(fx.keys())[:3]
+    dim = 7
+    Ui, R2, coef = ctx.manifold_prepare(np.stack([fx[k][:, :8] for k in keys]), dim, first=1, kind=kind, want_coef=True)
+    for i, k in enumerate(keys):
+        U = O.normalize_manifold(fx[k][:, :8])[:, 1:dim + 1]
+        assert np.array_equal(Ui[i], U)
+        q = 0
+        for v1 in range(dim - 1):
+            for v2 in range(v1 + 1, dim):
+                if kind == 2:
+                    cF1, r2 = O.conic_fit2(U, v1, v2)
+                    cF = cF1[1:]
+                else:
+                    cF, r2 = O.conic_fit3(U, v1, v2)
+                assert abs(R2[i, q] - r2) < 1e-11, (k, v1, v2)
+                assert np.allclose(coef[i, q, :len(cF)], cF, rtol=1e-8, atol=1e-10), (k, v1, v2)
+                q += 1
+    # the fits alone on caller-supplied manifolds, and on the resident copy
+    R2b = ctx.conic_fit_batch(Ui, kind=kind)
+    assert np.array_equal(R2b, R2)
+    assert np.array_equal(ctx.conic_fit_batch(None, kind=kind, shape=Ui.shape), R2)
+
+
+def test_device_prepare_retry_path(ctx):
+    """A manifold without any parabolic pair (R^2 < 0.2 in row 0) takes the 45-degree pre-rotation (:202-209)."""
+    rng = np.random.default_rng(5)
+    blob = rng.standard_normal((600, 8))
+    good = golden('rot_inputs.npz')['PD001'][:600, :8]
+    preps = RH.prepare_many([blob, good], dim=6, PCA=False, CTF=True, ctx=ctx)
+    for p, U0 in zip(preps, (blob, good)):
+        host = RH.prepare(U0, dim=6, PCA=False, CTF=True)
+        assert p['itIdx'] == host['itIdx'] and p['comboList'] == host['comboList'] and p['Rij_final'] == host['Rij_final']
+        assert np.array_equal(p['U_init'], host['U_init'])
+    assert preps[0]['itIdx'] == 2 and preps[0]['resident'] is None
+    th = RH.sweep_many(preps, 6, ctx=ctx)
+    th_host = RH.sweep_many([RH.prepare(U0, dim=6, PCA=False, CTF=True) for U0 in (blob, good)], 6, ctx=ctx)
+    assert all(np.array_equal(a, b) for a, b in zip(th, th_host))
+
+
+def test_manifold_prepare_argument_errors(ctx):
+    U = np.zeros((1, 10, 6))
+    with pytest.raises(ValueError):
+        ctx.manifold_prepare(U, 6, first=1)                      # first + dim > ncol
+    with pytest.raises(ValueError):
+        ctx.manifold_prepare(U, 4, first=0, kind=7)
+    with pytest.raises(ValueError):
+        ctx.conic_fit_batch(None, kind=2, shape=(3, 10, 4))      # nothing resident of that shape
+    with pytest.raises(ValueError):
+        ctx.rot_sweep(None, np.array([[[0, 1]]]), [1], [[0]], RH.theta_grid(), shape=(2, 10, 4))
+
+
 def test_rotation_op_files(ctx, tmp_path):
     fx, ref = golden('rot_inputs.npz'), golden('rot_ref_dim6.npz')
     root = tmp_path / 'tree'

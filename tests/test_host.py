@@ -80,6 +80,18 @@ def test_conic_fits_equal_sympy_rref():
 
 
 @pytest.mark.parametrize('dim', [6, 8])
+def test_select_partners_equals_find_parabolas(dim):
+    """The partner selection used with the device R^2 table takes the decisions of findParabolas (:159-177)."""
+    fx = golden('rot_inputs.npz')
+    for key in ['PD002', 'PD064']:
+        Ui = O.initial_subspace(fx[key], dim, True)
+        R2 = [ConicFit.fit2(Ui, v1, v2)[3] for v1 in range(dim - 1) for v2 in range(v1 + 1, dim)]
+        psi, vals = RH.select_partners(dim, R2)
+        psi_ref, _, it = O.find_parabolas(dim, Ui, 1, True)
+        assert it == 1 and np.array_equal(psi, psi_ref) and vals[0] >= 0.2
+
+
+@pytest.mark.parametrize('dim', [6, 8])
 def test_rotation_plan_equals_oracle(dim):
     fx = golden('rot_inputs.npz')
     for key in ['PD001', 'PD048', 'PD126']:
