@@ -53,7 +53,7 @@ int         esper_sync(esper_ctx* ctx);                 /* cudaStreamSynchronize
 /* Per-kernel CUDA-event timing of the calls that follow (off by default). */
 int         esper_set_profiling(esper_ctx* ctx, int on);
 /* Sum / count of the kernel launches recorded under `name` since the last reset.
- * names: "prep", "gram", "dist_finalize", "refine", "sweep", "markov", "lanczos", "rot", "conic".    */
+ * names: "prep", "gram", "dist_finalize", "refine", "sweep", "markov", "lanczos", "rot", "conic", "dataprep".    */
 int         esper_get_kernel_ms(esper_ctx* ctx, const char* name, double* total_ms, int* launches);
 int         esper_reset_profiling(esper_ctx* ctx);
 /* Total kernels launched by this ctx since creation (the bench's `gpu_launches` claim). */
@@ -224,6 +224,33 @@ int esper_manifold_prepare(esper_ctx* ctx, const double* U0, int n_pd, int m, in
                            double* Uinit, double* R2, double* coef);
 /* The conic fits alone on caller-supplied (already normalised / pre-rotated) manifolds Uinit [n_pd, m, dim]. */
 int esper_conic_fit_batch(esper_ctx* ctx, const double* Uinit, int n_pd, int m, int dim, int kind, double* R2, double* coef);
+
+/* ---- data preparation and formats either side of the path ---------------------
+ * esper_tau_snr_stack: 0_Data_Inputs/Pristine_AddTauSNR/Generate_TauSNR.py:56-64 with AddNoise.py:17-86 per image:
+ * every pristine state -> tau copies with additive Gaussian noise N(signal mean, sqrt(var(signal)/snr)) (signal =
+ * pixels outside +-0.25 std), each standardised by the mean/std of its pixels outside the inscribed circle.
+ *   pristine: [ss, box, box] float32 (host); image s*tau + t of the result is copy t of state s;
+ *   snr == 0: tau exact copies without noise or standardisation (apply_noise = False, :62-63);
+ *   seed: Philox4x32-10 key (the reference uses numpy's unseeded global generator);
+ *   params (optional out): [ss, 2] = (signal mean, noise std) per state -- AddNoise.find_SNR;
+ *   stack (optional out): [ss*tau, box, box] float32.  The stack also stays resident: a following
+ *   esper_dist_rms(imgs = NULL, n = ss*tau, P = box*box) embeds it without any host round trip.                */
+int esper_tau_snr_stack(esper_ctx* ctx, const float* pristine, int ss, int box, int tau, double snr,
+                        unsigned long long seed, double* params, float* stack);
+/* D2H copy of the resident image stack [n, P] (e.g. to write a generated stack as .mrcs). */
+int esper_download_images(esper_ctx* ctx, float* imgs, int n, int P);
+/* MRC2014 header of `path` (host only): dims = (nx, ny, nz), mode, byte offset of the first image
+ * (1024 + extended header).  Replaces what mrcfile.mmap reports (Distances.py:75-76).  Error text: esper_last_error(NULL). */
+int esper_mrc_info(const char* path, int* dims, int* mode, long long* data_offset);
+/* Stream images [first, first+count) (count <= 0: to the end) of a mode-2 MRC stack from disk into the resident image
+ * buffer through two page-locked staging buffers (disk read of chunk i+1 overlaps the H2D copy of chunk i).
+ * dims (optional out) = (images, ny, nx).  Follow with esper_dist_rms(imgs = NULL, ...).                            */
+int esper_upload_mrc(esper_ctx* ctx, const char* path, int first, int count, int* dims);
+/* 3_Manifold_Binning/Manifold_Binning.py:940-974: sums[b] = sum of the float32 images order[offsets[b] .. offsets[b+1])
+ * in float64, added in that order (bit-identical to the reference's `finalStackBin[b] += image` loop).
+ *   imgs: [n, P] float32 or NULL = resident stack; order: image indices; offsets: [n_bins+1]; sums: [n_bins, P].   */
+int esper_bin_accumulate(esper_ctx* ctx, const float* imgs, int n, int P, const int* order, const int* offsets,
+                         int n_bins, double* sums);
 
 #ifdef __cplusplus
 }

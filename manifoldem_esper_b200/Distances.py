@@ -53,13 +53,12 @@ def op(pyDir, PD, CTF=True, dataDir=None, stackPath=None, outDir=None, ctx=None)
             alt = os.path.join(dataDir, 'PD_%s.mrcs' % PD)
             stackPath = alt if os.path.exists(alt) else stackPath
     print('CTF mode disabled.')
-    PD_stack = mrc.mmap(stackPath, 'r')
-    nS, N, N2 = PD_stack.data.shape
+    ctx = ctx or _capi.default_context()
+    nS, N, N2 = ctx.upload_mrc(stackPath)        # disk -> page-locked double buffer -> HBM (the reference: mrcfile.mmap, :75)
     print('Computing distances...')
-    D = distances(np.asarray(PD_stack.data).reshape(nS, N * N2), ctx=ctx)
+    D = ctx.dist_rms(None, n=nS, P=N * N2)
     np.save(os.path.join(outDir, 'PD_%s_dist.npy' % PD), D)
     print('Distances complete.')
-    PD_stack.close()
 
 
 def _op_ctf(PD, dataDir, outDir, ctx):

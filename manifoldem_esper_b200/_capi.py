@@ -70,6 +70,12 @@ SIGNATURES = {
                                   C.c_void_p, C.c_void_p]),
     'esper_manifold_prepare': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    'esper_tau_snr_stack': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_ulonglong,
+                                      C.c_void_p, C.c_void_p]),
+    'esper_download_images': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    'esper_mrc_info': (C.c_int, [C.c_char_p, _i32p, _i32p, C.POINTER(C.c_longlong)]),
+    'esper_upload_mrc': (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, _i32p]),
+    'esper_bin_accumulate': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     'esper_conic_fit_batch': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }
 
@@ -334,6 +340,49 @@ class Context:
                                                   _ptr(v2), ne, int(bins), float(lo), float(hi), _ptr(nz), _ptr(H)))
         return (nz, H) if want_hist else nz
 
+    # -- data preparation / formats ---------------------------------------------
+    def tau_snr_stack(self, pristine, tau, snr, seed=0, download=True):
+        """Generate_TauSNR.py:56-64 + AddNoise.py:17-86 on the device: float32 [ss, box, box] pristine states ->
+        (stack float32 [ss*tau, box, box] or None, params float64 [ss, 2] = (signal mean, noise std)).
+        snr=None/0 -> tau exact copies.  The stack stays resident for dist_rms(None, n=ss*tau, P=box*box)."""
+        pristine = np.ascontiguousarray(pristine, dtype=np.float32)
+        if pristine.ndim != 3 or pristine.shape[1] != pristine.shape[2]:
+            raise ValueError('tau_snr_stack: pristine must be [ss, box, box]')
+        ss, box, _ = pristine.shape
+        tau = int(tau)
+        params = np.empty((ss, 2), dtype=np.float64)
+        stack = np.empty((ss * max(tau, 0), box, box), dtype=np.float32) if download else None
+        self._check(self._lib.esper_tau_snr_stack(self._h, _ptr(pristine), ss, box, tau, float(snr or 0.0),
+                                                  C.c_ulonglong(int(seed) & 0xFFFFFFFFFFFFFFFF), _ptr(params), _ptr(stack)))
+        return stack, params
+
+    def download_images(self, n, P):
+        out = np.empty((int(n), int(P)), dtype=np.float32)
+        self._check(self._lib.esper_download_images(self._h, _ptr(out), int(n), int(P)))
+        return out
+
+    def upload_mrc(self, path, first=0, count=0):
+        """Stream a mode-2 MRC stack from disk into the resident image buffer -> (images, ny, nx)."""
+        dims = (C.c_int32 * 3)()
+        self._check(self._lib.esper_upload_mrc(self._h, os.fsencode(path), int(first), int(count), dims))
+        return int(dims[0]), int(dims[1]), int(dims[2])
+
+    def bin_accumulate(self, imgs, order, offsets, n=None, P=None):
+        """Manifold_Binning.py:940-974: float64 sums [n_bins, P] of the images order[offsets[b]:offsets[b+1]], in order."""
+        if imgs is not None:
+            imgs = _check_stack(imgs)
+            n, P = imgs.shape
+        if n is None or P is None:
+            raise ValueError('bin_accumulate: n and P are required when imgs is None')
+        order = _as(order, np.int32).reshape(-1)
+        offsets = _as(offsets, np.int32).reshape(-1)
+        if offsets.shape[0] < 2 or offsets[-1] != order.shape[0]:
+            raise ValueError('bin_accumulate: offsets must be [n_bins + 1] with offsets[-1] == len(order)')
+        sums = np.empty((offsets.shape[0] - 1, int(P)), dtype=np.float64)
+        self._check(self._lib.esper_bin_accumulate(self._h, _ptr(imgs), int(n), int(P), _ptr(order), _ptr(offsets),
+                                                   offsets.shape[0] - 1, _ptr(sums)))
+        return sums
+
     def manifold_prepare(self, U0, dim, first, kind=2, want_coef=False):
         """Rotation_Histograms.py:100-112 (normalize + slice) and the conic fits of findParabolas (:153-212) for a
         batch of manifolds U0 [n_pd, m, ncol] -> (Uinit [n_pd, m, dim], R2 [n_pd, pairs] or None[, coef]).  The
@@ -431,6 +480,18 @@ def nd_rotation(n, theta):
     if rc != ESPER_OK:
         raise ValueError('%s angles required' % (int(n * (n - 1) / 2)))
     return R
+
+
+def mrc_info(path):
+    """(nx, ny, nz), mode, data offset of an MRC2014 file (host only; what mrcfile.mmap reports)."""
+    lib = load_library()
+    dims = (C.c_int32 * 3)()
+    mode = C.c_int32(0)
+    off = C.c_longlong(0)
+    rc = lib.esper_mrc_info(os.fsencode(path), dims, C.byref(mode), C.byref(off))
+    if rc != ESPER_OK:
+        raise ValueError(lib.esper_last_error(None).decode())
+    return (int(dims[0]), int(dims[1]), int(dims[2])), int(mode.value), int(off.value)
 
 
 def hist_edges(bins, lo, hi):

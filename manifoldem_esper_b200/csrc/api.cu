@@ -69,9 +69,11 @@ void esper_destroy(esper_ctx* c) {
     DevBuf* bufs[] = {&c->imgs, &c->dist, &c->plane_hi, &c->plane_lo, &c->row_stats, &c->col_part, &c->gram_part,
                       &c->pair_list, &c->sweep_part, &c->sweep_aux, &c->markov, &c->degree, &c->lan_V, &c->lan_w,
                       &c->lan_h, &c->lan_small, &c->rot_U, &c->rot_R, &c->rot_idx, &c->rot_out, &c->rot_H,
-                      &c->rot_theta, &c->rot_aux};
+                      &c->rot_theta, &c->rot_aux, &c->prep_src, &c->prep_out,
+                      &c->ctf_par, &c->ctf_T, &c->ctf_fy, &c->ctf_C, &c->ctf_ab, &c->ctf_T12, &c->ctf_wiener, &c->pw_plan};
     for (DevBuf* b : bufs) b->release();
     c->pin.release();
+    c->pin_stream[0].release(); c->pin_stream[1].release();
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -476,6 +478,50 @@ int esper_conic_fit_batch(esper_ctx* c, const double* Uinit, int n_pd, int m, in
     int rc = run_conic_fits(c, Uinit, n_pd, m, dim, kind, R2, coef);
     if (rc == ESPER_OK && Uinit) { c->rot_n_pd = n_pd; c->rot_m = m; c->rot_dim = dim; }
     return rc;
+}
+
+// ---- data preparation and formats ---------------------------------------------------
+int esper_tau_snr_stack(esper_ctx* c, const float* pristine, int ss, int box, int tau, double snr, unsigned long long seed,
+                        double* params, float* stack) {
+    ESPER_ENTER(c);
+    if (!pristine) return fail(c, ESPER_E_ARG, "tau_snr_stack: pristine is NULL");
+    return run_tau_snr_stack(c, pristine, ss, box, tau, snr, seed, params, stack);
+}
+
+int esper_download_images(esper_ctx* c, float* imgs, int n, int P) {
+    ESPER_ENTER(c);
+    if (!imgs) return fail(c, ESPER_E_ARG, "download_images: imgs is NULL");
+    if (c->img_n != n || c->img_P != P || !c->imgs.p)
+        return fail(c, ESPER_E_STATE, "download_images: no resident [%d, %d] stack (resident: [%d, %d])", n, P, c->img_n, c->img_P);
+    ESPER_CUDA(c, cudaMemcpyAsync(imgs, c->imgs.p, sizeof(float) * (size_t)n * P, cudaMemcpyDeviceToHost, c->stream));
+    ESPER_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ESPER_OK;
+}
+
+int esper_mrc_info(const char* path, int* dims, int* mode, long long* data_offset) {
+    if (!path || !dims || !mode || !data_offset) { g_create_error = "mrc_info: NULL argument"; return ESPER_E_ARG; }
+    char err[400];
+    int rc = mrc_info_host(path, dims, mode, data_offset, err, sizeof err);
+    if (rc) g_create_error = err;
+    return rc;
+}
+
+int esper_upload_mrc(esper_ctx* c, const char* path, int first, int count, int* dims) {
+    ESPER_ENTER(c);
+    if (!path) return fail(c, ESPER_E_ARG, "upload_mrc: path is NULL");
+    return run_upload_mrc(c, path, first, count, dims);
+}
+
+int esper_bin_accumulate(esper_ctx* c, const float* imgs, int n, int P, const int* order, const int* offsets, int n_bins, double* sums) {
+    ESPER_ENTER(c);
+    if (!order || !offsets || !sums || n < 1 || P < 1) return fail(c, ESPER_E_ARG, "bin_accumulate: NULL argument or empty stack");
+    if (imgs) {
+        int rc = esper_upload_images(c, imgs, n, P);
+        if (rc) return rc;
+    } else if (c->img_n != n || c->img_P != P || !c->imgs.p) {
+        return fail(c, ESPER_E_STATE, "bin_accumulate: imgs == NULL but no resident [%d, %d] stack (resident: [%d, %d])", n, P, c->img_n, c->img_P);
+    }
+    return run_bin_accumulate(c, n, P, order, offsets, n_bins, sums);
 }
 
 }  // extern "C"

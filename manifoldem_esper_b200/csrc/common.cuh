@@ -98,6 +98,9 @@ struct esper_ctx {
     // stage-4 workspaces
     esper::DevBuf rot_U, rot_R, rot_idx, rot_out, rot_H, rot_theta, rot_aux;
     int rot_n_pd = 0, rot_m = 0, rot_dim = 0;                  // shape of the normalised manifolds resident in rot_U
+    // data preparation / formats (k8_dataprep.cu)
+    esper::DevBuf prep_src, prep_out;                          // pristine states + SNR table; bin sums
+    esper::PinBuf pin_stream[2];                               // page-locked double buffer of the MRC reader
     esper::PinBuf pin;                                         // small pinned staging area
 };
 
@@ -184,6 +187,11 @@ int run_ritz_vectors(esper_ctx* c, int m, int steps, int k, const double* V_d, c
 int run_manifold_prepare(esper_ctx* c, const double* U0, int n_pd, int m, int ncol, int first, int dim, int kind,
                          double* Uinit_h, double* R2_h, double* coef_h);
 int run_conic_fits(esper_ctx* c, const double* Uinit, int n_pd, int m, int dim, int kind, double* R2_h, double* coef_h);
+int run_tau_snr_stack(esper_ctx* c, const float* pristine_h, int ss, int box, int tau, double snr, unsigned long long seed,
+                      double* params_h, float* stack_h);
+int mrc_info_host(const char* path, int* dims, int* mode, long long* data_offset, char* err, size_t err_len);
+int run_upload_mrc(esper_ctx* c, const char* path, int first, int count, int* dims_out);
+int run_bin_accumulate(esper_ctx* c, int n, int P, const int* order_h, const int* offsets_h, int n_bins, double* sums_h);
 void nd_rotation_host(int n, const double* theta, double* R);
 void hist_edges_host(int bins, double lo, double hi, double* edges);
 

@@ -12,8 +12,8 @@
 //   because tensor-core FP32 accumulation is not round-to-nearest; partials are summed in FP64.
 //
 // Kernel structure (one CTA per SM, persistent over units, 320 threads):
-//   warp 0     TMA producer   (cp.async.bulk.tensor.2d, 128B swizzle, mbarrier complete_tx)
-//   warp 1     MMA issuer     (tcgen05.mma.cta_group::1.kind::tf32, one elected lane) + TMEM alloc
+//   warp 0     TMA producer   (cp.async.bulk.tensor.2d, 128B swizzle, mbarrier complete_tx; elect.sync lane)
+//   warp 1     MMA issuer     (tcgen05.mma.cta_group::1.kind::tf32, elect.sync lane, warp-uniform loop) + TMEM alloc
 //   warps 2-9  epilogue       (tcgen05.ld 32x32b -> registers -> coalesced FP32 partial tile); warps w and
 //                             w+4 share a TMEM lane quadrant and take 64 of the 128 columns each
 //   smem ring: 3 stages x {A_hi, A_lo, B_hi, B_lo} x (128 rows x 32 fp32) = 3 x 64 KB
@@ -63,6 +63,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t"
         "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// One elected lane of a converged warp (warp-uniform predicate: the tensor-core / TMA instructions guarded by it take
+// their operands from uniform registers; under an `if (lane == 0)` branch ptxas emits a per-instruction
+// ELECT / R2UR waterfall instead, ~12 instructions per tcgen05.mma, and the issuing thread becomes the bottleneck).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 rx;\n\t"
+        ".reg .pred px;\n\t"
+        "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+        "@px mov.s32 %0, 1;\n\t"
+        "}" : "+r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -182,17 +196,17 @@ gram_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-                const int chunk = u / n_tiles, t = tile0 + (u % n_tiles);
-                int ti, tj; bool tr_; tile_map(t, nt, rect_ti0, ti, tj, tr_);
-                const bool diag = (ti == tj) && rect_ti0 != FULL_RECT;
-                const int kb0 = (int)((long long)nkb * chunk / split_k);
-                const int kb1 = (int)((long long)nkb * (chunk + 1) / split_k);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+        // ===================== TMA producer (whole warp in the loop, one elected lane issues) =====================
+        int stage = 0; uint32_t phase = 0;
+        for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+            const int chunk = u / n_tiles, t = tile0 + (u % n_tiles);
+            int ti, tj; bool tr_; tile_map(t, nt, rect_ti0, ti, tj, tr_);
+            const bool diag = (ti == tj) && rect_ti0 != FULL_RECT;
+            const int kb0 = (int)((long long)nkb * chunk / split_k);
+            const int kb1 = (int)((long long)nkb * (chunk + 1) / split_k);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                if (elect_one_sync()) {
                     const uint32_t sa = base + stage * STAGE_BYTES;
                     const uint32_t fb = full_bar + 8 * stage;
                     mbar_expect_tx(fb, diag ? 2 * TILE_BYTES : 4 * TILE_BYTES);
@@ -202,54 +216,53 @@ gram_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
                         tma_load_2d(sa + 2 * TILE_BYTES, &mapb_hi, fb, kb * BK, tj * BN);
                         tma_load_2d(sa + 3 * TILE_BYTES, &mapb_lo, fb, kb * BK, tj * BN);
                     }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-                const int chunk = u / n_tiles, t = tile0 + (u % n_tiles);
-                int ti, tj; bool tr_; tile_map(t, nt, rect_ti0, ti, tj, tr_);
-                const bool diag = (ti == tj) && rect_ti0 != FULL_RECT;
-                const int kb0 = (int)((long long)nkb * chunk / split_k);
-                const int kb1 = (int)((long long)nkb * (chunk + 1) / split_k);
-                // Tensor-core FP32 accumulation rounds toward zero, which biases a long chain in proportion to the
-                // accumulated magnitude (i.e. to the signal).  The chain is therefore cut every `drain_kb` k-blocks:
-                // the accumulator buffer is handed to the epilogue warps, which add it in round-to-nearest FP32 into
-                // register accumulators while the next group runs in the other TMEM buffer.
-                for (int g0 = kb0; g0 < kb1; g0 += drain_kb) {
-                    const int g1 = min(g0 + drain_kb, kb1);
-                    mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+        // ===================== MMA issuer (whole warp in the loop, one elected lane issues) =====================
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+            const int chunk = u / n_tiles, t = tile0 + (u % n_tiles);
+            int ti, tj; bool tr_; tile_map(t, nt, rect_ti0, ti, tj, tr_);
+            const bool diag = (ti == tj) && rect_ti0 != FULL_RECT;
+            const int kb0 = (int)((long long)nkb * chunk / split_k);
+            const int kb1 = (int)((long long)nkb * (chunk + 1) / split_k);
+            // Tensor-core FP32 accumulation rounds toward zero, which biases a long chain in proportion to the
+            // accumulated magnitude (i.e. to the signal).  The chain is therefore cut every `drain_kb` k-blocks:
+            // the accumulator buffer is handed to the epilogue warps, which add it in round-to-nearest FP32 into
+            // register accumulators while the next groups run in the other TMEM buffers.
+            for (int g0 = kb0; g0 < kb1; g0 += drain_kb) {
+                const int g1 = min(g0 + drain_kb, kb1);
+                mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = g0; kb < g1; ++kb) {
+                    mbar_wait(full_bar + 8 * stage, phase);
                     tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + acc * BN;
-                    uint32_t accumulate = 0;
-                    for (int kb = g0; kb < g1; ++kb) {
-                        mbar_wait(full_bar + 8 * stage, phase);
-                        tc_fence_after();
-                        const uint32_t sa = base + stage * STAGE_BYTES;
-                        const uint32_t a_hi = sa, a_lo = sa + TILE_BYTES;
-                        const uint32_t b_hi = diag ? a_hi : sa + 2 * TILE_BYTES;
-                        const uint32_t b_lo = diag ? a_lo : sa + 3 * TILE_BYTES;
+                    const uint32_t sa = base + stage * STAGE_BYTES;
+                    const uint32_t a_hi = sa, a_lo = sa + TILE_BYTES;
+                    const uint32_t b_hi = diag ? a_hi : sa + 2 * TILE_BYTES;
+                    const uint32_t b_lo = diag ? a_lo : sa + 3 * TILE_BYTES;
+                    const uint64_t dah0 = make_smem_desc(a_hi), dal0 = make_smem_desc(a_lo);
+                    const uint64_t dbh0 = make_smem_desc(b_hi), dbl0 = make_smem_desc(b_lo);
+                    if (elect_one_sync()) {
 #pragma unroll
                         for (int k = 0; k < BK / UK; ++k) {
-                            const uint32_t off = k * UK * 4;   // 32 bytes per UMMA K step inside the swizzle row
-                            const uint64_t dah = make_smem_desc(a_hi + off), dal = make_smem_desc(a_lo + off);
-                            const uint64_t dbh = make_smem_desc(b_hi + off), dbl = make_smem_desc(b_lo + off);
-                            umma_tf32(tmem_d, dal, dbh, accumulate);   // small cross terms first
-                            umma_tf32(tmem_d, dah, dbl, 1);
-                            umma_tf32(tmem_d, dah, dbh, 1);
-                            accumulate = 1;
+                            const uint64_t off = (uint64_t)((k * UK * 4) >> 4);   // 32 bytes per UMMA K step, in 16-byte units
+                            umma_tf32(tmem_d, dal0 + off, dbh0 + off, (kb > g0 || k > 0) ? 1u : 0u);   // small cross terms first
+                            umma_tf32(tmem_d, dah0 + off, dbl0 + off, 1);
+                            umma_tf32(tmem_d, dah0 + off, dbh0 + off, 1);
                         }
                         umma_commit(empty_bar + 8 * stage);            // frees the smem stage when the MMAs retire
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        if (kb == g1 - 1) umma_commit(tfull_bar + 8 * acc);   // group complete -> epilogue drains it
                     }
-                    umma_commit(tfull_bar + 8 * acc);                  // group complete -> epilogue drains it
-                    if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {

@@ -113,3 +113,33 @@ def random_manifold(m: int = 2000, ncol: int = 15, seed: int = 0) -> np.ndarray:
     Q, _ = np.linalg.qr(np.eye(k) + 0.15 * rng.standard_normal((k, k)))
     U[:, :k] = U[:, :k] @ Q
     return np.ascontiguousarray(U * (1.0 / np.sqrt(m)))
+
+
+# ---- the device noise generator of esper_tau_snr_stack, restated in numpy (tests compare the two) -------------
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 (Salmon et al., SC'11) on uint32 arrays -> four uint32 arrays."""
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), 0x9E3779B9, 0xBB67AE85
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) for c in np.broadcast_arrays(c0, c1, c2, c3))
+    k0, k1 = int(k0) & 0xFFFFFFFF, int(k1) & 0xFFFFFFFF
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c0, c1, c2, c3 = hi1 ^ c1 ^ np.uint64(k0), lo1, hi0 ^ c3 ^ np.uint64(k1), lo0
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def philox_normal(seed: int, image: int, n_pixels: int) -> np.ndarray:
+    """float64 [n_pixels] N(0,1) field of image `image` exactly as k8_dataprep.cu draws it: counter = (pixel pair,
+    image, 0, 0), key = seed; two 53-bit uniforms per counter; Box-Muller (pixel 2k <- r cos, pixel 2k+1 <- r sin)."""
+    pairs = (n_pixels + 1) // 2
+    x0, x1, x2, x3 = philox4x32_10(np.arange(pairs, dtype=np.uint64), np.uint64(image), np.uint64(0), np.uint64(0),
+                                   seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    u0 = ((x0 >> np.uint64(5)).astype(np.float64) * 67108864.0 + (x1 >> np.uint64(6)).astype(np.float64)) / 9007199254740992.0
+    u1 = ((x2 >> np.uint64(5)).astype(np.float64) * 67108864.0 + (x3 >> np.uint64(6)).astype(np.float64)) / 9007199254740992.0
+    r = np.sqrt(-2.0 * np.log(1.0 - u0))
+    z = np.empty(2 * pairs, dtype=np.float64)
+    z[0::2] = r * np.cos(2.0 * np.pi * u1)
+    z[1::2] = r * np.sin(2.0 * np.pi * u1)
+    return z[:n_pixels]

@@ -535,3 +535,76 @@ def rotation_histograms_op(U0, dim=6, PCA=False, CTF=True, collect=None):
     return dict(RotMatrices=thetas_all, RotEigenfunctions=saveEigs,
                 RotParameters=np.array([dim]), comboList=comboList, Rij_final=Rij_final,
                 U_init=U_init, itIdx=itIdx)
+
+
+# --------------------------------------------------------------------------------------
+# Data preparation either side of the path
+#   0_Data_Inputs/Pristine_AddTauSNR/AddNoise.py, Generate_TauSNR.py; Manifold_Binning.py:940-974
+# --------------------------------------------------------------------------------------
+def find_snr(image: np.ndarray, SNR: float):
+    """AddNoise.py:17-39 -> (sig_mean, noise_std).  The reference flattens the float32 image into a Python list of
+    numpy float32 scalars; `np.mean` / `np.var` of that list are float32 pairwise reductions over the same
+    contiguous values, which is what the array calls below compute (bit-identical, see the golden test)."""
+    img_1d = np.asarray(image).reshape(-1)
+    img_std = np.sqrt(np.var(img_1d))
+    keep = ~((-img_std * .25 < img_1d) & (img_1d < img_std * .25))
+    sig = img_1d[keep]
+    sig_mean = np.mean(sig)
+    noise_std = np.sqrt(np.var(sig) / SNR)
+    return sig_mean, noise_std
+
+
+def background_mask(h: int, w: int) -> np.ndarray:
+    """AddNoise.py:54-59: True inside the circle of radius int(h/2) around (int(w/2), int(h/2))."""
+    center = [int(w / 2), int(h / 2)]
+    radius = int(h / 2)
+    Y, X = np.ogrid[:h, :w]
+    return np.sqrt((X - center[0]) ** 2 + (Y - center[1]) ** 2) <= radius
+
+
+def standardize_background(image: np.ndarray):
+    """AddNoise.py:52-75: (image - mean(bg)) / std(bg), bg = pixels outside the inscribed circle; 0 if std(bg) == 0."""
+    mask = background_mask(*image.shape[:2])
+    bg = image[~mask]
+    bg_mean, bg_std = np.mean(bg), np.std(bg)
+    if bg_std == 0:
+        return 0
+    return (image - bg_mean) / bg_std
+
+
+def add_noise_op(img_orig: np.ndarray, SNR: float, gauss: np.ndarray | None = None) -> np.ndarray:
+    """AddNoise.op (:77-86).  gauss=None draws `np.random.normal(mean, std, shape)` from numpy's global generator like
+    the reference (:45); otherwise `gauss` is a field of N(0,1) values and the noise is mean + std * gauss."""
+    sig_mean, noise_std = find_snr(img_orig, SNR)
+    row, col = img_orig.shape
+    if gauss is None:
+        noise = np.random.normal(sig_mean, noise_std, (row, col))
+    else:
+        noise = sig_mean + noise_std * np.asarray(gauss, dtype=np.float64)
+    return standardize_background(img_orig + noise)
+
+
+def tau_snr_stack(pristine: np.ndarray, tau: int, SNR: float | None, gauss: np.ndarray | None = None) -> np.ndarray:
+    """Generate_TauSNR.py:56-64: float32 [ss*tau, box, box], image s*tau + t = copy t of state s (mode-2 MRC cast)."""
+    ss, box, _ = pristine.shape
+    out = np.empty((ss * tau, box, box), dtype=np.float32)
+    k = 0
+    for i in range(ss):
+        for j in range(tau):
+            if SNR:
+                out[k] = add_noise_op(pristine[i], SNR, None if gauss is None else gauss[k])
+            else:
+                out[k] = pristine[i]
+            k += 1
+    return out
+
+
+def bin_accumulate(stack: np.ndarray, order, offsets) -> np.ndarray:
+    """3_Manifold_Binning/Manifold_Binning.py:338,940-974: `finalStackBin[b] += init_stack.data[img]` (float64
+    accumulator, float32 images) for the images order[offsets[b]:offsets[b+1]] of every bin, in that order."""
+    n_bins = len(offsets) - 1
+    out = np.zeros((n_bins,) + stack.shape[1:])
+    for b in range(n_bins):
+        for k in range(offsets[b], offsets[b + 1]):
+            out[b] += stack[order[k]]
+    return out

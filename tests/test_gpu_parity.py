@@ -8,8 +8,8 @@ import numpy as np
 import pytest
 
 from conftest import golden
-from manifoldem_esper_b200 import (PCA, DiffusionMaps, Distances, GaussianBandwidth, Rotation_Histograms as RH, _capi,
-                                   mrc, synth)
+from manifoldem_esper_b200 import (PCA, AddNoise, DiffusionMaps, Distances, GaussianBandwidth, Generate_TauSNR,
+                                   Rotation_Histograms as RH, _capi, mrc, synth)
 from oracle import esper_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -542,3 +542,120 @@ def test_rotation_sweep_argument_errors(ctx):
         ctx.rot_sweep(U, np.array([[[0, 9]]]), [1], [[0]], RH.theta_grid())   # v2 out of range
     with pytest.raises(ValueError):
         ctx.rot_sweep(U, np.array([[[0, 1]]]), [1], [[15]], RH.theta_grid())  # Rij out of range
+
+
+# ---- data preparation and formats --------------------------------------------------
+def test_snr_params_vs_reference_golden(ctx):
+    """AddNoise.find_SNR per state: the reference computes it in float32, the device in float64."""
+    g = golden('tau_snr.npz')
+    _, params = ctx.tau_snr_stack(g['pristine'], 2, float(g['snr']), seed=1, download=False)
+    assert np.max(np.abs(params - g['params']) / np.abs(g['params'])) < 1e-5
+    sm, ns = AddNoise.find_SNR(g['pristine'][3], float(g['snr']), ctx=ctx)
+    assert sm == params[3, 0] and ns == params[3, 1]
+
+
+@pytest.mark.parametrize('box,ns,tau', [(24, 6, 10), (25, 4, 3), (250, 3, 2)])
+def test_tau_snr_stack_vs_oracle_on_the_same_noise_field(ctx, box, ns, tau):
+    """The device stack equals the oracle's AddNoise.op applied with the SAME N(0,1) field (the numpy restatement of the
+    device's Philox + Box-Muller stream); every image is standardised on its background ring."""
+    pr = golden('tau_snr.npz')['pristine'] if box == 24 else synth.pristine_states(box=box, n_side=2, pd=4)[:ns]
+    seed = 0x1234567890ABCDEF + box
+    stack, params = ctx.tau_snr_stack(pr, tau, 0.1, seed=seed)
+    gauss = np.stack([synth.philox_normal(seed, k, box * box).reshape(box, box) for k in range(pr.shape[0] * tau)])
+    ref = O.tau_snr_stack(pr, tau, 0.1, gauss=gauss)
+    assert stack.shape == ref.shape and stack.dtype == np.float32
+    assert np.max(np.abs(stack - ref)) < 2e-5
+    bg = ~O.background_mask(box, box)
+    for img in stack:
+        assert abs(img[bg].astype(np.float64).mean()) < 1e-5 and abs(img[bg].astype(np.float64).std() - 1) < 1e-5
+    again, _ = ctx.tau_snr_stack(pr, tau, 0.1, seed=seed)
+    other, _ = ctx.tau_snr_stack(pr, tau, 0.1, seed=seed + 1)
+    assert np.array_equal(again, stack) and not np.array_equal(other, stack)
+    # copies of one state carry independent noise
+    a, b = stack[0].astype(np.float64).ravel(), stack[1].astype(np.float64).ravel()
+    assert abs(np.corrcoef(a - a.mean(), b - b.mean())[0, 1]) < 0.5
+
+
+def test_tau_snr_resident_chain_and_duplicates(ctx):
+    pr = synth.pristine_states(box=32, n_side=4, pd=9)
+    stack, _ = ctx.tau_snr_stack(pr, 3, 0.5, seed=77)
+    D_res = ctx.dist_rms(None, n=48, P=1024)                      # embeds the stack where it was generated
+    assert np.array_equal(ctx.download_images(48, 1024), stack.reshape(48, 1024))
+    assert np.array_equal(D_res, ctx.dist_rms(stack))
+    dup, params = ctx.tau_snr_stack(pr, 3, None)
+    assert np.array_equal(dup, np.repeat(pr, 3, axis=0)) and not params.any()
+    odd = synth.pristine_states(box=25, n_side=2, pd=1)            # P not a multiple of 4
+    assert np.array_equal(ctx.tau_snr_stack(odd, 2, 0)[0], np.repeat(odd, 2, axis=0))
+    with pytest.raises(ValueError):
+        ctx.tau_snr_stack(pr[:, :, :16], 2, 0.1)
+    with pytest.raises(ValueError):
+        ctx.tau_snr_stack(pr, 0, 0.1)
+
+
+def test_generate_tau_snr_op_files(ctx, tmp_path):
+    g = golden('tau_snr.npz')
+    root = tmp_path / '0_Data_Inputs'
+    os.makedirs(root / 'Pristine_2D'); os.makedirs(root / 'Pristine_AddTauSNR')
+    mrc.write_stack(str(root / 'Pristine_2D' / 'PD_001.mrcs'), g['pristine'])
+    Generate_TauSNR.op(str(root / 'Pristine_AddTauSNR'), '001', seed=5, ctx=ctx)
+    out = mrc.mmap(str(root / 'Pristine_AddTauSNR' / 'Modified_Stacks' / 'PD001_SNR_tau10_stack.mrcs'))
+    assert out.data.shape == g['stack'].shape
+    ref, _ = ctx.tau_snr_stack(g['pristine'], 10, 0.1, seed=5)
+    assert np.array_equal(np.asarray(out.data), ref)
+    # same statistics as the reference run's stack (different noise stream): per-image spread of the whole image
+    assert abs(np.asarray(out.data).std() / g['stack'].std() - 1) < 0.05
+    out.close()
+    Generate_TauSNR.op(str(root / 'Pristine_AddTauSNR'), '001', apply_noise=False, tau=2, ctx=ctx)
+    dup = mrc.mmap(str(root / 'Pristine_AddTauSNR' / 'Modified_Stacks' / 'PD001_tau2_stack.mrcs'))
+    assert np.array_equal(np.asarray(dup.data), np.repeat(g['pristine'], 2, axis=0))
+    dup.close()
+
+
+def test_upload_mrc_streams_the_stack(ctx, tmp_path):
+    rng = np.random.default_rng(11)
+    stack = rng.standard_normal((300, 250, 250)).astype(np.float32)          # 75 MB: three staging chunks
+    path = str(tmp_path / 'PD_009.mrcs')
+    mrc.write_stack(path, stack)
+    assert ctx.upload_mrc(path) == (300, 250, 250)
+    assert np.array_equal(ctx.download_images(300, 62500), stack.reshape(300, -1))
+    assert ctx.upload_mrc(path, first=290, count=50) == (10, 250, 250)        # clipped at the end of the file
+    assert np.array_equal(ctx.download_images(10, 62500), stack[290:].reshape(10, -1))
+    D = ctx.dist_rms(None, n=10, P=62500)
+    assert np.array_equal(D, ctx.dist_rms(stack[290:]))
+    # extended header (nsymbt) and the error paths
+    raw = bytearray(open(path, 'rb').read(1024))
+    small = stack[:4, :8, :8].copy()
+    hdr = np.frombuffer(bytes(raw), dtype='<i4').copy()
+    hdr[0:3] = (8, 8, 4); hdr[23] = 80
+    p2 = str(tmp_path / 'ext.mrcs')
+    with open(p2, 'wb') as f:
+        f.write(hdr.tobytes()); f.write(b'x' * 80); f.write(small.tobytes())
+    assert ctx.upload_mrc(p2) == (4, 8, 8)
+    assert np.array_equal(ctx.download_images(4, 64), small.reshape(4, 64))
+    hdr[3] = 1
+    p3 = str(tmp_path / 'mode1.mrcs')
+    with open(p3, 'wb') as f:
+        f.write(hdr.tobytes()); f.write(b'x' * 80); f.write(small.tobytes())
+    with pytest.raises(ValueError):
+        ctx.upload_mrc(p3)
+    with pytest.raises(ValueError):
+        ctx.upload_mrc(str(tmp_path / 'missing.mrcs'))
+    with pytest.raises(ValueError):
+        ctx.upload_mrc(path, first=300)
+
+
+def test_bin_accumulate_bit_exact(ctx):
+    """Manifold_Binning.py:940-974: float64 bin sums in the caller's order equal the reference loop bit for bit."""
+    rng = np.random.default_rng(2)
+    stack = (rng.standard_normal((400, 33, 33)) * np.exp(rng.uniform(-8, 8, (400, 1, 1)))).astype(np.float32)
+    order = rng.permutation(400)[:371].astype(np.int32)
+    cuts = np.sort(rng.choice(372, 19, replace=False))
+    offsets = np.concatenate([[0], cuts[:7], [cuts[7]], cuts[7:], [371]]).astype(np.int32)     # 21 bins, one of them empty
+    ref = O.bin_accumulate(stack, order, offsets)
+    sums = ctx.bin_accumulate(stack, order, offsets)
+    assert np.array_equal(sums, ref.reshape(ref.shape[0], -1))
+    assert np.array_equal(ctx.bin_accumulate(None, order, offsets, n=400, P=33 * 33), sums)    # resident stack
+    with pytest.raises(ValueError):
+        ctx.bin_accumulate(stack, [400], [0, 1])
+    with pytest.raises(ValueError):
+        ctx.bin_accumulate(stack, [1, 2], [0, 2, 1])

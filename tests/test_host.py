@@ -160,3 +160,28 @@ def test_pd_parsing_and_sharding():
     recs = launcher.run_sharded(pds, work, 0, 1)
     assert [r['ok'] for r in recs] == [True, True, False, True, True, True, True, True]
     assert 'boom' in recs[2]['error']
+
+
+def test_philox_restatement_known_answers():
+    """Random123 known-answer vectors for Philox4x32-10 (the generator of esper_tau_snr_stack)."""
+    def kat(c, k):
+        r = synth.philox4x32_10(*[np.array([x], dtype=np.uint64) for x in c], k[0], k[1])
+        return [int(x[0]) for x in r]
+    assert kat((0, 0, 0, 0), (0, 0)) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert kat((0xffffffff,) * 4, (0xffffffff, 0xffffffff)) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert kat((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    z = synth.philox_normal(99, 3, 200001)
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01 and z.shape == (200001,)
+
+
+def test_mrc_info_host_entry(lib_built, tmp_path):
+    st = np.arange(3 * 5 * 7, dtype=np.float32).reshape(3, 5, 7)
+    p = str(tmp_path / 'a.mrcs')
+    mrc.write_stack(p, st)
+    assert _capi.mrc_info(p) == ((7, 5, 3), 2, 1024)
+    with pytest.raises(ValueError):
+        _capi.mrc_info(str(tmp_path / 'missing.mrcs'))
+    with open(str(tmp_path / 'short.mrcs'), 'wb') as f:
+        f.write(open(p, 'rb').read()[:1100])
+    with pytest.raises(ValueError):
+        _capi.mrc_info(str(tmp_path / 'short.mrcs'))

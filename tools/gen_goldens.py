@@ -17,6 +17,8 @@ Outputs (all under tests/golden/):
   rot_inputs.npz        first 9 columns of 12 shipped Data_Manifolds_126 fixtures
   rot_ref_dim{6,8}.npz  Rotation_Histograms.op outputs for all 126 fixtures     (P5)
   rot_counts_dim8.npz   per-evaluation non-zero-bin counts for 3 PDs (histogramdd spy)
+  tau_snr.npz           0_Data_Inputs/Pristine_AddTauSNR: AddNoise.find_SNR per state and Generate_TauSNR.op
+                        (tau = 10, SNR = 0.1 as shipped) on a 6-state pristine stack under np.random.seed
 """
 from __future__ import annotations
 
@@ -62,7 +64,7 @@ class _Null(types.ModuleType):
 def install_stubs():
     null = _Null('matplotlib')
     for name in ['matplotlib', 'matplotlib.figure', 'matplotlib.pyplot', 'matplotlib.cm',
-                 'matplotlib.gridspec', 'matplotlib.ticker', 'pylab', 'mpl_toolkits',
+                 'matplotlib.gridspec', 'matplotlib.ticker', 'pylab', 'mpl_toolkits', 'imageio',
                  'mpl_toolkits.mplot3d']:
         sys.modules[name] = null
     from manifoldem_esper_b200 import mrc
@@ -218,6 +220,28 @@ def rot_worker(args):
             np.load(os.path.join(o, 'PD%s_RotParameters.npy' % pds)), np.array(counts, dtype=np.int32))
 
 
+def tau_snr_golden(ref):
+    """Run the reference's Generate_TauSNR.op / AddNoise from a scratch copy of 0_Data_Inputs (it writes next to itself)."""
+    from manifoldem_esper_b200 import mrc, synth
+    root = tempfile.mkdtemp(prefix='esper_prep_')
+    shutil.copytree(os.path.join(ref, '0_Data_Inputs/Pristine_AddTauSNR'), os.path.join(root, 'Pristine_AddTauSNR'))
+    os.makedirs(os.path.join(root, 'Pristine_2D'))
+    pristine = synth.pristine_states(box=24, n_side=3, pd=2)[:6]
+    mrc.write_stack(os.path.join(root, 'Pristine_2D', 'PD_001.mrcs'), pristine)
+    d = os.path.join(root, 'Pristine_AddTauSNR')
+    AN = import_from(os.path.join(d, 'AddNoise.py'), 'AddNoise')
+    GT = import_from(os.path.join(d, 'Generate_TauSNR.py'), 'Generate_TauSNR')
+    params = np.array([AN.find_SNR(img, 0.1) for img in pristine])            # float32 (sig_mean, noise_std)
+    seed = 20201
+    np.random.seed(seed)
+    run_quiet(GT.op, d, '001')
+    mm = mrc.mmap(os.path.join(d, "Modified_Stacks", "PD001_SNR_tau10_stack.mrcs"))
+    out = np.array(mm.data)
+    mm.close()
+    shutil.rmtree(root, ignore_errors=True)
+    return dict(pristine=pristine, params=params, seed=np.array(seed), tau=np.array(10), snr=np.array(0.1), stack=np.array(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--ref', default='/root/reference')
@@ -226,6 +250,7 @@ def main():
     ap.add_argument('--only-rot', action='store_true')
     ap.add_argument('--only-pca', action='store_true')
     ap.add_argument('--only-ctf', action='store_true')
+    ap.add_argument('--only-prep', action='store_true')
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     os.environ['PYTHONDONTWRITEBYTECODE'] = '1'
@@ -235,6 +260,12 @@ def main():
     install_stubs()
     from manifoldem_esper_b200 import synth
 
+    if args.only_prep or not (args.only_rot or args.only_pca or args.only_ctf):
+        np.savez_compressed(os.path.join(GOLD, 'tau_snr.npz'), **tau_snr_golden(args.ref))
+        print('data prep done')
+    if args.only_prep:
+        shutil.rmtree(root, ignore_errors=True)
+        return
     if args.only_ctf or not (args.only_rot or args.only_pca):
         st, pa = synth.ctf_stack(pd=3, box=32, n_side=6, tau=2, snr=0.1)              # N=72, even box
         np.savez_compressed(os.path.join(GOLD, 'ctf_small.npz'), **ctf_golden(root, st, pa, '003'))
