@@ -70,6 +70,12 @@ SIGNATURES = {
                                   C.c_void_p, C.c_void_p]),
     'esper_manifold_prepare': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    'esper_comm_alloc': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    'esper_comm_open': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    'esper_comm_close': (C.c_int, [C.c_void_p]),
+    'esper_symv_allgather_d': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    'esper_comm_wait_d': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    'esper_comm_status': (C.c_int, [C.c_void_p, C.POINTER(C.c_uint)]),
     'esper_tau_snr_stack': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_ulonglong,
                                       C.c_void_p, C.c_void_p]),
     'esper_download_images': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
@@ -308,6 +314,38 @@ class Context:
 
     def symv_rows_d(self, nrows, n, q_ptr, w_ptr):
         self._check(self._lib.esper_symv_rows_d(self._h, int(nrows), int(n), C.c_void_p(q_ptr), C.c_void_p(w_ptr)))
+
+    # -- fused SYMV + all-gather over peer memory (row-block path) ---------------------------
+    def comm_alloc(self, n_pad, world):
+        """Allocate this rank's gather buffer; returns its 64-byte CUDA IPC handle (bytes) for the peers."""
+        h = (C.c_char * 64)()
+        self._check(self._lib.esper_comm_alloc(self._h, int(n_pad), int(world), h))
+        return bytes(h.raw)
+
+    def comm_open(self, handles, rank, world):
+        """handles: list of `world` 64-byte IPC handles in rank order."""
+        blob = b''.join(handles)
+        if len(blob) != 64 * int(world):
+            raise ValueError('comm_open: need one 64-byte handle per rank')
+        buf = C.create_string_buffer(blob, len(blob))
+        self._check(self._lib.esper_comm_open(self._h, buf, int(rank), int(world)))
+
+    def comm_close(self):
+        self._check(self._lib.esper_comm_close(self._h))
+
+    def symv_allgather_d(self, nrows, n, row0, q_ptr, step):
+        self._check(self._lib.esper_symv_allgather_d(self._h, int(nrows), int(n), int(row0), C.c_void_p(q_ptr), int(step)))
+
+    def comm_wait_d(self, step):
+        """Enqueue the wait for `step`; returns the device address of the gathered vector on this rank."""
+        p = C.c_void_p(0)
+        self._check(self._lib.esper_comm_wait_d(self._h, int(step), C.byref(p)))
+        return int(p.value)
+
+    def comm_status(self):
+        st = C.c_uint(0)
+        self._check(self._lib.esper_comm_status(self._h, C.byref(st)))
+        return int(st.value)
 
     def lanczos_start_d(self, n, degree_all, V_ptr):
         degree_all = _as(degree_all, np.float64).reshape(-1)

@@ -71,6 +71,8 @@ void esper_destroy(esper_ctx* c) {
                       &c->lan_h, &c->lan_small, &c->rot_U, &c->rot_R, &c->rot_idx, &c->rot_out, &c->rot_H,
                       &c->rot_theta, &c->rot_aux, &c->prep_src, &c->prep_out,
                       &c->ctf_par, &c->ctf_T, &c->ctf_fy, &c->ctf_C, &c->ctf_ab, &c->ctf_T12, &c->ctf_wiener, &c->pw_plan};
+    run_comm_close(c);
+    c->comm_buf.release();
     for (DevBuf* b : bufs) b->release();
     c->pin.release();
     c->pin_stream[0].release(); c->pin_stream[1].release();
@@ -389,6 +391,43 @@ int esper_symv_rows_d(esper_ctx* c, int nrows, int n, const double* q_d, double*
     ESPER_ENTER(c);
     if (!q_d || !w_rows_d || nrows < 1 || n < 1 || !c->markov.p) return fail(c, ESPER_E_ARG, "symv_rows_d: bad argument or no resident Ms block");
     return run_symv_rows(c, nrows, n, q_d, w_rows_d);
+}
+
+// ---- fused SYMV + all-gather over peer memory ---------------------------------------------------------------------
+int esper_comm_alloc(esper_ctx* c, int n_pad, int world, void* ipc_handle) {
+    ESPER_ENTER(c);
+    if (!ipc_handle) return fail(c, ESPER_E_ARG, "comm_alloc: ipc_handle is NULL");
+    run_comm_close(c);
+    return run_comm_alloc(c, n_pad, world, ipc_handle);
+}
+
+int esper_comm_open(esper_ctx* c, const void* ipc_handles, int rank, int world) {
+    ESPER_ENTER(c);
+    if (!ipc_handles) return fail(c, ESPER_E_ARG, "comm_open: ipc_handles is NULL");
+    return run_comm_open(c, ipc_handles, rank, world);
+}
+
+int esper_comm_close(esper_ctx* c) {
+    ESPER_ENTER(c);
+    ESPER_CUDA(c, cudaStreamSynchronize(c->stream));
+    return run_comm_close(c);
+}
+
+int esper_symv_allgather_d(esper_ctx* c, int nrows, int n, int row0, const double* q_d, int step) {
+    ESPER_ENTER(c);
+    if (!q_d || nrows < 1 || n < 1 || !c->markov.p) return fail(c, ESPER_E_ARG, "symv_allgather_d: bad argument or no resident Ms block");
+    return run_symv_allgather(c, nrows, n, row0, q_d, step);
+}
+
+int esper_comm_wait_d(esper_ctx* c, int step, double** w_full_d) {
+    ESPER_ENTER(c);
+    return run_comm_wait(c, step, w_full_d);
+}
+
+int esper_comm_status(esper_ctx* c, unsigned int* status) {
+    ESPER_ENTER(c);
+    if (!status) return fail(c, ESPER_E_ARG, "comm_status: status is NULL");
+    return run_comm_status(c, status);
 }
 
 int esper_lanczos_start_d(esper_ctx* c, int n, const double* degree_all, double* V_d) {

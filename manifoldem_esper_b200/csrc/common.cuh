@@ -98,6 +98,11 @@ struct esper_ctx {
     // stage-4 workspaces
     esper::DevBuf rot_U, rot_R, rot_idx, rot_out, rot_H, rot_theta, rot_aux;
     int rot_n_pd = 0, rot_m = 0, rot_dim = 0;                  // shape of the normalised manifolds resident in rot_U
+    // row-block path: peer-memory communicator (k4_eigen.cu)
+    esper::DevBuf comm_buf;
+    void* comm_peer[16] = {nullptr};
+    int comm_n_pad = 0, comm_world = 0, comm_rank = 0;
+    bool comm_open = false;
     // data preparation / formats (k8_dataprep.cu)
     esper::DevBuf prep_src, prep_out;                          // pristine states + SNR table; bin sums
     esper::PinBuf pin_stream[2];                               // page-locked double buffer of the MRC reader
@@ -181,6 +186,12 @@ int run_rot_sweep(esper_ctx* c, const double* Uinit, int n_pd, int m, int dim, c
                   const int* n_sub, int max_sub, const int* rij, int n_rij, const double* theta_grid,
                   int n_theta, int bins, double lo, double hi, double* thetas_out, int* counts_out);
 int run_symv_rows(esper_ctx* c, int rows, int m, const double* q_d, double* w_rows_d);
+int run_comm_alloc(esper_ctx* c, int n_pad, int world, void* handle_out);
+int run_comm_open(esper_ctx* c, const void* handles, int rank, int world);
+int run_comm_close(esper_ctx* c);
+int run_symv_allgather(esper_ctx* c, int rows, int m, int row0, const double* q_d, int step);
+int run_comm_wait(esper_ctx* c, int step, double** w_full_d);
+int run_comm_status(esper_ctx* c, unsigned int* status);
 int run_lanczos_start(esper_ctx* c, int m, const double* degree_all_h, double* V_d);
 int run_lanczos_ortho(esper_ctx* c, int m, int j, double* V_d, double* w_d, double* ab_d);
 int run_ritz_vectors(esper_ctx* c, int m, int steps, int k, const double* V_d, const double* S_h, double* vec_h);

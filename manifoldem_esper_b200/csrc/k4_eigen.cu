@@ -1367,7 +1367,193 @@ __global__ void __launch_bounds__(256) symv_rows_kernel(const double* __restrict
     if (lane == 0) w[row] = tot;
 }
 
+// ---- fused SYMV + all-gather over NVLink peer memory (row-block path, one process per GPU) -------------------------
+// Every rank owns a communication buffer that its peers map through CUDA IPC:
+//     w[2][n_pad] doubles (two slots, step parity) | flags[2][MAX_PEERS] u32 | counter[2] u32 | error u32
+// symv_allgather_kernel computes the rank's rows of w = Ms q exactly like symv_rows_kernel, directly into slot
+// (step & 1) of its own buffer; the last CTA to finish (device-scope arrival counter) copies the finished block into the
+// same slot of every peer's buffer with 16-byte NVLink stores and publishes `step` in this rank's flag word on every
+// peer (release, system scope) -- one system-scope fence per launch.  (A first version stored every CTA's rows to all
+// peers and fenced at system scope per CTA: the per-CTA membar.sys halved the SYMV's HBM bandwidth.)  The consumer
+// (comm_wait_kernel, stream-ordered before the orthogonalisation) spins until all `world` flags of the slot show the
+// step.  Slot reuse two steps later is safe: a rank reaches step j+2 only after its wait for step j+1, i.e. after every
+// peer launched its SYMV of step j+1, which is stream-ordered after that peer's orthogonalisation of step j.
+constexpr int MAX_PEERS = 16;
+struct PeerTable { double* w[MAX_PEERS]; unsigned int* flags[MAX_PEERS]; };
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+symv_allgather_kernel(const double* __restrict__ Ms, int rows, int m, const double* __restrict__ q, PeerTable peers, int world,
+                      int rank, int n_pad, int row0, unsigned int step, unsigned int* __restrict__ counter) {
+    const int wrp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + wrp;
+    const int slot = (int)(step & 1u);
+    double* mine = peers.w[rank] + (size_t)slot * n_pad + row0;        // this rank's rows inside its own gather buffer
+    if (row < rows) {
+        const double* a = Ms + (size_t)row * m;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int cidx = lane;
+        for (; cidx + 224 < m; cidx += 256) {
+            const double x0 = __ldcs(a + cidx), x1 = __ldcs(a + cidx + 32), x2 = __ldcs(a + cidx + 64), x3 = __ldcs(a + cidx + 96),
+                         x4 = __ldcs(a + cidx + 128), x5 = __ldcs(a + cidx + 160), x6 = __ldcs(a + cidx + 192), x7 = __ldcs(a + cidx + 224);
+            a0 = fma(x0, __ldg(q + cidx), a0);       a1 = fma(x1, __ldg(q + cidx + 32), a1);
+            a2 = fma(x2, __ldg(q + cidx + 64), a2);  a3 = fma(x3, __ldg(q + cidx + 96), a3);
+            a0 = fma(x4, __ldg(q + cidx + 128), a0); a1 = fma(x5, __ldg(q + cidx + 160), a1);
+            a2 = fma(x6, __ldg(q + cidx + 192), a2); a3 = fma(x7, __ldg(q + cidx + 224), a3);
+        }
+        for (; cidx < m; cidx += 32) a0 = fma(__ldcs(a + cidx), __ldg(q + cidx), a0);
+        const double tot = warp_sum((a0 + a1) + (a2 + a3));
+        if (lane == 0) mine[row] = tot;
+    }
+    // last-CTA detection (device scope): the CTA that completes the block pushes it to every peer over NVLink
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(counter + slot, 1u);
+        last = (prev == gridDim.x - 1);
+        if (last) counter[slot] = 0u;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const int n2 = rows >> 1;                                            // 16-byte stores; row0 and n_pad are even
+    const double2* src2 = reinterpret_cast<const double2*>(mine);
+    for (int p = 0; p < world; ++p) {
+        if (p == rank) continue;
+        double* dst = peers.w[p] + (size_t)slot * n_pad + row0;
+        double2* dst2 = reinterpret_cast<double2*>(dst);
+        for (int i = threadIdx.x; i < n2; i += blockDim.x) dst2[i] = __ldcg(src2 + i);
+        if ((rows & 1) && threadIdx.x == 0) dst[rows - 1] = __ldcg(mine + rows - 1);
+    }
+    __threadfence_system();                                              // the peer stores are performed before the flags
+    __syncthreads();
+    if (threadIdx.x < world) st_release_sys(peers.flags[threadIdx.x] + slot * MAX_PEERS + rank, step);
+}
+
+// Waits until every rank's flag of the slot shows `step`; on timeout raises the error word instead of hanging.
+__global__ void comm_wait_kernel(const unsigned int* __restrict__ flags, int world, unsigned int step, long long timeout_cycles,
+                                 unsigned int* __restrict__ error) {
+    const int r = threadIdx.x;
+    if (r < world) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys(flags + (step & 1u) * MAX_PEERS + r) != step) {
+            if (clock64() - t0 > timeout_cycles) { atomicExch(error, 0x100u + (unsigned int)r); break; }
+            __nanosleep(100);
+        }
+    }
+    __threadfence_system();
+}
+
 }  // namespace lanczos
+
+// Communication buffer of this rank (see above) and its IPC handle.
+int run_comm_alloc(esper_ctx* c, int n_pad, int world, void* handle_out) {
+    using namespace lanczos;
+    if (n_pad < 1 || world < 1 || world > MAX_PEERS) return fail(c, ESPER_E_ARG, "comm_alloc: need n_pad >= 1 and 1 <= world <= %d", MAX_PEERS);
+    const size_t w_bytes = sizeof(double) * 2 * (size_t)n_pad;
+    const size_t bytes = w_bytes + sizeof(unsigned int) * (2 * MAX_PEERS + 2 + 1 + 29);
+    c->comm_buf.release();                                   // a fresh allocation: its handle is exported below
+    ESPER_RESERVE(c, c->comm_buf, bytes);
+    ESPER_CUDA(c, cudaMemsetAsync(c->comm_buf.p, 0, bytes, c->stream));
+    ESPER_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->comm_n_pad = n_pad; c->comm_world = world; c->comm_open = false;
+    cudaIpcMemHandle_t h;
+    ESPER_CUDA(c, cudaIpcGetMemHandle(&h, c->comm_buf.p));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handle_out, &h, sizeof h);
+    return ESPER_OK;
+}
+
+int run_comm_open(esper_ctx* c, const void* handles, int rank, int world) {
+    using namespace lanczos;
+    if (!c->comm_buf.p || world != c->comm_world || rank < 0 || rank >= world)
+        return fail(c, ESPER_E_STATE, "comm_open: call comm_alloc with the same world size first");
+    const size_t w_bytes = sizeof(double) * 2 * (size_t)c->comm_n_pad;
+    for (int p = 0; p < world; ++p) {
+        void* base = nullptr;
+        if (p == rank) base = c->comm_buf.p;
+        else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const char*)handles + 64 * (size_t)p, sizeof h);
+            cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                for (int q = 0; q < p; ++q) if (q != rank && c->comm_peer[q]) { cudaIpcCloseMemHandle(c->comm_peer[q]); c->comm_peer[q] = nullptr; }
+                return fail(c, ESPER_E_CUDA, "comm_open: cudaIpcOpenMemHandle for rank %d: %s", p, cudaGetErrorString(e));
+            }
+        }
+        c->comm_peer[p] = base;
+    }
+    (void)w_bytes;
+    c->comm_rank = rank; c->comm_open = true;
+    return ESPER_OK;
+}
+
+int run_comm_close(esper_ctx* c) {
+    if (c->comm_open)
+        for (int p = 0; p < c->comm_world; ++p)
+            if (p != c->comm_rank && c->comm_peer[p]) cudaIpcCloseMemHandle(c->comm_peer[p]);
+    for (auto& p : c->comm_peer) p = nullptr;
+    c->comm_open = false;
+    return ESPER_OK;
+}
+
+int run_symv_allgather(esper_ctx* c, int rows, int m, int row0, const double* q_d, int step) {
+    using namespace lanczos;
+    if (!c->comm_open) return fail(c, ESPER_E_STATE, "symv_allgather_d: no open communicator (comm_alloc + comm_open)");
+    if (step < 1 || row0 < 0 || row0 + rows > c->comm_n_pad) return fail(c, ESPER_E_ARG, "symv_allgather_d: step >= 1 and row0 + rows <= n_pad required");
+    PeerTable pt;
+    const size_t w_bytes = sizeof(double) * 2 * (size_t)c->comm_n_pad;
+    for (int p = 0; p < MAX_PEERS; ++p) {
+        char* base = (char*)c->comm_peer[p < c->comm_world ? p : c->comm_rank];
+        pt.w[p] = reinterpret_cast<double*>(base);
+        pt.flags[p] = reinterpret_cast<unsigned int*>(base + w_bytes);
+    }
+    unsigned int* counter = reinterpret_cast<unsigned int*>(c->comm_buf.as<char>() + w_bytes) + 2 * MAX_PEERS;
+    {
+        LaunchScope ls(c, "lanczos");
+        symv_allgather_kernel<<<ceil_div(rows, 8), 256, 0, c->stream>>>(c->markov.as<double>(), rows, m, q_d, pt, c->comm_world,
+                                                                        c->comm_rank, c->comm_n_pad, row0, (unsigned int)step, counter);
+    }
+    ESPER_CUDA(c, cudaGetLastError());
+    return ESPER_OK;
+}
+
+// Enqueue the wait for step `step`; *w_full_d = this rank's gathered vector (slot step & 1), valid after the wait.
+int run_comm_wait(esper_ctx* c, int step, double** w_full_d) {
+    using namespace lanczos;
+    if (!c->comm_open) return fail(c, ESPER_E_STATE, "comm_wait_d: no open communicator");
+    const size_t w_bytes = sizeof(double) * 2 * (size_t)c->comm_n_pad;
+    unsigned int* flags = reinterpret_cast<unsigned int*>(c->comm_buf.as<char>() + w_bytes);
+    unsigned int* error = flags + 2 * MAX_PEERS + 2;
+    {
+        LaunchScope ls(c, "lanczos");
+        comm_wait_kernel<<<1, 32, 0, c->stream>>>(flags, c->comm_world, (unsigned int)step, 20000000000LL, error);   // ~10 s
+    }
+    ESPER_CUDA(c, cudaGetLastError());
+    if (w_full_d) *w_full_d = c->comm_buf.as<double>() + (size_t)(step & 1) * c->comm_n_pad;
+    return ESPER_OK;
+}
+
+// 0 = healthy; 0x100 + r = the wait for rank r timed out (synchronises the stream).
+int run_comm_status(esper_ctx* c, unsigned int* status) {
+    using namespace lanczos;
+    if (!c->comm_buf.p) return fail(c, ESPER_E_STATE, "comm_status: no communicator");
+    const size_t w_bytes = sizeof(double) * 2 * (size_t)c->comm_n_pad;
+    const unsigned int* error = reinterpret_cast<unsigned int*>(c->comm_buf.as<char>() + w_bytes) + 2 * MAX_PEERS + 2;
+    ESPER_CUDA(c, cudaMemcpyAsync(status, error, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    ESPER_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ESPER_OK;
+}
 
 int run_symv_rows(esper_ctx* c, int rows, int m, const double* q_d, double* w_rows_d) {
     using namespace lanczos;

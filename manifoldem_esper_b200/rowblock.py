@@ -9,7 +9,10 @@ DiffusionMaps.py:166); the arithmetic per element is the same as in the single-G
     all-gather       of the Lanczos vector w = Ms q (n float64)        once per Lanczos step
 
 After the all-gather every rank orthogonalises the same replicated vector with the same deterministic
-kernels, so no further reduction is needed.  `embed_oversized` is written against a small backend interface
+kernels, so no further reduction is needed.  On GPUs the per-step SYMV and its all-gather are ONE kernel
+(`esper_symv_allgather_d`): every rank stores its rows of w straight into all peers' buffers over NVLink (CUDA IPC
+peer memory) and publishes a flag; `CudaBackend(fused=True)` selects it, the NCCL all-gather remains as the
+reference implementation of the same exchange (`fused=False`; identical bits).  `embed_oversized` is written against a small backend interface
 so that the orchestration is exercised on CPU (gloo, numpy backend in tests/) and on GPUs (NCCL, CudaBackend).
 """
 from __future__ import annotations
@@ -63,10 +66,11 @@ class TorchComm:
 class CudaBackend:
     """Row-block kernels of libesper_b200 on one GPU; vectors are torch CUDA tensors (NCCL-ready)."""
 
-    def __init__(self, ctx, stack, n, P, device):
+    def __init__(self, ctx, stack, n, P, device, fused=False):
         import torch
         self.torch, self.ctx, self.device = torch, ctx, device
         self.stack, self.n, self.P = stack, n, P
+        self.fused = bool(fused)
 
     def dist_rows(self, row0, nrows):
         self.row0, self.nrows = row0, nrows
@@ -87,6 +91,14 @@ class CudaBackend:
         self.w_local = t.zeros(rows_per, dtype=t.float64, device=self.device)
         self.w_full = t.zeros(rows_per * world, dtype=t.float64, device=self.device)
         self.ab = t.zeros((max_steps + 2, 2), dtype=t.float64, device=self.device)
+        if self.fused:
+            # one gather buffer per rank, mapped by every peer through CUDA IPC
+            import torch.distributed as dist
+            handle = self.ctx.comm_alloc(rows_per * world, world)
+            handles = [None] * world
+            dist.all_gather_object(handles, handle)
+            self.ctx.comm_open(handles, dist.get_rank(), world)
+            dist.barrier()                                  # nobody stores into a buffer that is not mapped everywhere yet
 
     def lanczos_start(self, degree_all):
         self.ctx.lanczos_start_d(self.n, degree_all, self.V.data_ptr())
@@ -94,8 +106,27 @@ class CudaBackend:
     def symv(self, j):
         self.ctx.symv_rows_d(self.nrows, self.n, self.V[j].data_ptr(), self.w_local.data_ptr())
 
+    def symv_allgather(self, j):
+        """Fused: w = Ms[rows, :] q_j stored into every rank's gather buffer; returns after enqueueing the wait."""
+        self.ctx.symv_allgather_d(self.nrows, self.n, self.row0, self.V[j].data_ptr(), j)
+        self._w_ptr = self.ctx.comm_wait_d(j)
+
     def ortho(self, j):
-        self.ctx.lanczos_ortho_d(self.n, j, self.V.data_ptr(), self.w_full.data_ptr(), self.ab[j - 1].data_ptr())
+        w_ptr = self._w_ptr if self.fused else self.w_full.data_ptr()
+        self.ctx.lanczos_ortho_d(self.n, j, self.V.data_ptr(), w_ptr, self.ab[j - 1].data_ptr())
+
+    def comm_check(self):
+        if self.fused:
+            st = self.ctx.comm_status()
+            if st:
+                raise RuntimeError('peer-memory all-gather: wait for rank %d timed out' % (st - 0x100))
+
+    def lanczos_free(self):
+        if self.fused:
+            import torch.distributed as dist
+            self.ctx.sync()
+            dist.barrier()                                  # every rank is done storing into its peers
+            self.ctx.comm_close()
 
     def read_ab(self, steps):
         self.ctx.sync()
@@ -159,12 +190,16 @@ def embed_oversized(backend, comm, n, k=16, eps=None, a0=None, tol=0.0, max_step
     next_check = min(max_steps, max(3 * (kw + 2) + 8, 32))
     while not converged and steps < max_steps:
         j = steps + 1
-        backend.symv(j)                                           # w_local = Ms[rows, :] q_j
-        comm.allgather_vec(backend.w_full, backend.w_local)       # the per-step collective
+        if getattr(backend, 'fused', False):
+            backend.symv_allgather(j)                             # ONE kernel: SYMV + stores into all peers + flag
+        else:
+            backend.symv(j)                                       # w_local = Ms[rows, :] q_j
+            comm.allgather_vec(backend.w_full, backend.w_local)   # the per-step collective
         backend.ortho(j)                                          # replicated, deterministic
         steps += 1
         if steps >= next_check or steps == max_steps:
             alpha, beta = backend.read_ab(steps)
+            getattr(backend, 'comm_check', lambda: None)()
             converged, theta, S = backend.tridiag_ritz(alpha, beta, k, tol)
             breakdown = not (beta[-1] > 1e-14 * max(abs(alpha[0]), 1e-300))
             converged = converged or breakdown or steps >= n - 1
@@ -174,6 +209,7 @@ def embed_oversized(backend, comm, n, k=16, eps=None, a0=None, tol=0.0, max_step
     if not converged:
         raise RuntimeError('row-block Lanczos did not converge in %d steps' % steps)
     vec = backend.ritz_vectors(steps, k, S) if kw > 0 else backend.ritz_vectors(0, 1, np.zeros((0, 0)))
+    getattr(backend, 'lanczos_free', lambda: None)()
     sync(); timings['lanczos_s'] = time.perf_counter() - t0
     val = np.concatenate(([1.0], theta[:kw] ** 2))
     out.update(eps=eps, val=val, vec=vec, steps=steps, row0=row0, nrows=nrows, timings=timings)

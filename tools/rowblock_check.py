@@ -2,7 +2,9 @@
 """GPU check of the row-block (oversized PD) path under torchrun:
    torchrun --nproc-per-node G tools/rowblock_check.py [small|c4]
 small: N=2000 x 250^2 vs the single-GPU path (bit-equal distance rows, eigenpairs <= 1e-9).
-c4   : N=50000 x 128^2 (BASELINE config 4): timings, residuals |Ms v - lambda v|, orthonormality."""
+c4   : N=50000 x 128^2 (BASELINE config 4): timings, residuals |Ms v - lambda v|, orthonormality.  The stack is
+       generated on every GPU by esper_tau_snr_stack (same seed -> same bits), no 3.3 GB host stack.
+Both run the per-step exchange twice: NCCL all-gather, then the fused SYMV + peer-memory all-gather kernel."""
 import os
 import sys
 import time
@@ -28,17 +30,19 @@ ctx.dist_config(split_k=37 if mode == 'small' else 8)
 if mode == 'small':
     stack = synth.synthetic_pd(pd=1, box=250, n_side=20, tau=5, snr=0.1)
     n, P, k = 2000, 62500, 10
+    stack = stack.reshape(n, P)
 else:
-    t = time.time()
-    stack = synth.synthetic_pd(pd=1, box=128, n_side=20, tau=125, snr=0.1)
     n, P, k = 50000, 128 * 128, 10
-    if rank == 0:
-        print('generated %s in %.1fs' % (stack.shape, time.time() - t), flush=True)
-stack = stack.reshape(n, P)
+    stack = None
 comm = rowblock.TorchComm(dev)
 with torch.cuda.stream(stream):
     be = rowblock.CudaBackend(ctx, None, n, P, dev)
-    t = time.time(); ctx.upload_images(stack); ctx.sync(); t_up = time.time() - t
+    t = time.time()
+    if stack is not None:
+        ctx.upload_images(stack)
+    else:
+        ctx.tau_snr_stack(synth.pristine_states(box=128, n_side=20, pd=1), 125, 0.1, seed=1000, download=False)
+    ctx.sync(); t_up = time.time() - t
     dist.barrier(); torch.cuda.synchronize()
     t = time.time()
     res = rowblock.embed_oversized(be, comm, n, k=k)          # warm-up (allocations, NCCL channels)
@@ -51,6 +55,23 @@ with torch.cuda.stream(stream):
         print('mode=%s world=%d n=%d upload %.2fs embed %.3fs steps=%d eps=%.6f lam=%s' % (
             mode, world, n, t_up, t_all, res['steps'], res['eps'], np.array2string(np.sqrt(res['val']), precision=6)), flush=True)
         print('timings ' + ' '.join('%s=%.4f' % kv for kv in res['timings'].items()), flush=True)
+    # the same embedding with the fused SYMV + peer-memory all-gather kernel instead of symv + NCCL all-gather
+    bf = rowblock.CudaBackend(ctx, None, n, P, dev, fused=True)
+    rowblock.embed_oversized(bf, comm, n, k=k)                 # warm-up (IPC mappings)
+    torch.cuda.synchronize(); dist.barrier()
+    t = time.time()
+    resf = rowblock.embed_oversized(bf, comm, n, k=k)
+    torch.cuda.synchronize(); dist.barrier()
+    t_f = time.time() - t
+    # bit-identity of the two exchanges at a FIXED epsilon (the epsilon sweep's dynamic tile order makes the fitted
+    # epsilon vary in its last bits from run to run, whatever the exchange)
+    rn = rowblock.embed_oversized(be, comm, n, k=k, eps=res['eps'])
+    rf = rowblock.embed_oversized(bf, comm, n, k=k, eps=res['eps'])
+    same_f = rf['steps'] == rn['steps'] and np.array_equal(rf['val'], rn['val']) and np.array_equal(rf['vec'], rn['vec'])
+    print('rank %d fused embed %.3fs (nccl %.3fs) lanczos fused %.4fs vs nccl %.4fs, %d steps; fused == NCCL bit for bit at fixed eps: %s '
+          '(max |dval| %.2e, max |dvec| %.2e)' % (
+              rank, t_f, t_all, resf['timings']['lanczos_s'], res['timings']['lanczos_s'], resf['steps'], same_f,
+              np.max(np.abs(rf['val'] - rn['val'])), np.max(np.abs(rf['vec'] - rn['vec']))), flush=True)
     # residuals of the eigenpairs against the resident Ms row block
     vec = torch.from_numpy(res['vec']).to(dev)
     w_loc = torch.zeros(be.w_local.shape[0], dtype=torch.float64, device=dev)
