@@ -173,18 +173,19 @@ int esper_markov_rows(esper_ctx* ctx, int nrows, int n, double eps, const double
 /* w_rows_d[nrows] = Ms_rows . q_d[n]   (device pointers; asynchronous on the ctx stream). */
 int esper_symv_rows_d(esper_ctx* ctx, int nrows, int n, const double* q_d, double* w_rows_d);
 /* Fused SYMV + all-gather over NVLink peer memory (one process per GPU, CUDA IPC; replaces symv_rows_d followed by an
- * NCCL all-gather).  comm_alloc: this rank's buffer for gathered vectors of n_pad = rows_per_rank * world doubles
- * (two slots) + flags; ipc_handle: 64 bytes to exchange with the peers (e.g. torch.distributed all_gather).
- * comm_open: ipc_handles = [world][64] in rank order.  symv_allgather_d (step = 1, 2, ...): w = Ms_rows . q_d, stored
- * directly at [row0, row0 + nrows) of slot step & 1 of EVERY rank's buffer, then this rank's flag is published on every
- * peer.  comm_wait_d: enqueues the wait for all ranks' flags of `step` on the ctx stream; *w_full_d = the gathered
- * vector on this rank (valid for kernels enqueued after the wait; pass it to lanczos_ortho_d).  Steps must be
- * consecutive on all ranks.  comm_status: 0, or 0x100 + r if a wait for rank r timed out (10 s watchdog, no hang). */
+ * NCCL all-gather).  comm_alloc: this rank's receive buffer for gathered vectors of n_pad = rows_per_rank * world
+ * elements; ipc_handle: 64 bytes to exchange with the peers (e.g. torch.distributed all_gather).
+ * comm_open: ipc_handles = [world][64] in rank order.  symv_allgather_d (step = 1, 2, ...): w = Ms_rows . q_d, every
+ * element stored as a 16-byte {value, step} packet at [row0, row0 + nrows) of slot step & 1 of EVERY rank's buffer as
+ * soon as its CTA has it (flag-in-data, no fences).  comm_wait_d: enqueues on the ctx stream the unpack of elements
+ * [0, n) of `step` (spins per element until its flags show the step); *w_full_d = the dense gathered vector on this
+ * rank (valid for kernels enqueued afterwards; pass it to lanczos_ortho_d).  Steps must be consecutive on all ranks,
+ * each rank on a GPU of its own.  comm_status: 0, or non-zero if an unpack timed out (10 s watchdog, no hang). */
 int esper_comm_alloc(esper_ctx* ctx, int n_pad, int world, void* ipc_handle);
 int esper_comm_open(esper_ctx* ctx, const void* ipc_handles, int rank, int world);
 int esper_comm_close(esper_ctx* ctx);
 int esper_symv_allgather_d(esper_ctx* ctx, int nrows, int n, int row0, const double* q_d, int step);
-int esper_comm_wait_d(esper_ctx* ctx, int step, double** w_full_d);
+int esper_comm_wait_d(esper_ctx* ctx, int step, int n, double** w_full_d);
 int esper_comm_status(esper_ctx* ctx, unsigned int* status);
 /* Replicated Lanczos state, vectors owned by the caller on the device: V_d is [max_steps+2, n].
  * start: V_d[0] = sqrt(degree)/|.| (locked), V_d[1] = start vector.  ortho (step j >= 1, w_d = gathered

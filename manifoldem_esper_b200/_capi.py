@@ -74,7 +74,7 @@ SIGNATURES = {
     'esper_comm_open': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     'esper_comm_close': (C.c_int, [C.c_void_p]),
     'esper_symv_allgather_d': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
-    'esper_comm_wait_d': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    'esper_comm_wait_d': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     'esper_comm_status': (C.c_int, [C.c_void_p, C.POINTER(C.c_uint)]),
     'esper_tau_snr_stack': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_ulonglong,
                                       C.c_void_p, C.c_void_p]),
@@ -336,10 +336,10 @@ class Context:
     def symv_allgather_d(self, nrows, n, row0, q_ptr, step):
         self._check(self._lib.esper_symv_allgather_d(self._h, int(nrows), int(n), int(row0), C.c_void_p(q_ptr), int(step)))
 
-    def comm_wait_d(self, step):
-        """Enqueue the wait for `step`; returns the device address of the gathered vector on this rank."""
+    def comm_wait_d(self, step, n):
+        """Enqueue the unpack of elements [0, n) of `step`; returns the device address of the dense gathered vector."""
         p = C.c_void_p(0)
-        self._check(self._lib.esper_comm_wait_d(self._h, int(step), C.byref(p)))
+        self._check(self._lib.esper_comm_wait_d(self._h, int(step), int(n), C.byref(p)))
         return int(p.value)
 
     def comm_status(self):

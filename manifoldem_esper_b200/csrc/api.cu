@@ -419,9 +419,9 @@ int esper_symv_allgather_d(esper_ctx* c, int nrows, int n, int row0, const doubl
     return run_symv_allgather(c, nrows, n, row0, q_d, step);
 }
 
-int esper_comm_wait_d(esper_ctx* c, int step, double** w_full_d) {
+int esper_comm_wait_d(esper_ctx* c, int step, int n, double** w_full_d) {
     ESPER_ENTER(c);
-    return run_comm_wait(c, step, w_full_d);
+    return run_comm_wait(c, step, n, w_full_d);
 }
 
 int esper_comm_status(esper_ctx* c, unsigned int* status) {

@@ -190,7 +190,7 @@ int run_comm_alloc(esper_ctx* c, int n_pad, int world, void* handle_out);
 int run_comm_open(esper_ctx* c, const void* handles, int rank, int world);
 int run_comm_close(esper_ctx* c);
 int run_symv_allgather(esper_ctx* c, int rows, int m, int row0, const double* q_d, int step);
-int run_comm_wait(esper_ctx* c, int step, double** w_full_d);
+int run_comm_wait(esper_ctx* c, int step, int n, double** w_full_d);
 int run_comm_status(esper_ctx* c, unsigned int* status);
 int run_lanczos_start(esper_ctx* c, int m, const double* degree_all_h, double* V_d);
 int run_lanczos_ortho(esper_ctx* c, int m, int j, double* V_d, double* w_d, double* ab_d);

@@ -1369,34 +1369,40 @@ __global__ void __launch_bounds__(256) symv_rows_kernel(const double* __restrict
 
 // ---- fused SYMV + all-gather over NVLink peer memory (row-block path, one process per GPU) -------------------------
 // Every rank owns a communication buffer that its peers map through CUDA IPC:
-//     w[2][n_pad] doubles (two slots, step parity) | flags[2][MAX_PEERS] u32 | counter[2] u32 | error u32
-// symv_allgather_kernel computes the rank's rows of w = Ms q exactly like symv_rows_kernel, directly into slot
-// (step & 1) of its own buffer; the last CTA to finish (device-scope arrival counter) copies the finished block into the
-// same slot of every peer's buffer with 16-byte NVLink stores and publishes `step` in this rank's flag word on every
-// peer (release, system scope) -- one system-scope fence per launch.  (A first version stored every CTA's rows to all
-// peers and fenced at system scope per CTA: the per-CTA membar.sys halved the SYMV's HBM bandwidth.)  The consumer
-// (comm_wait_kernel, stream-ordered before the orthogonalisation) spins until all `world` flags of the slot show the
-// step.  Slot reuse two steps later is safe: a rank reaches step j+2 only after its wait for step j+1, i.e. after every
-// peer launched its SYMV of step j+1, which is stream-ordered after that peer's orthogonalisation of step j.
+//     ll[2][n_pad] 16-byte packets (two slots, step parity) | w[n_pad] doubles (the unpacked vector) | error u32
+// symv_allgather_kernel computes the rank's rows of w = Ms q exactly like symv_rows_kernel and writes them in wire
+// format, CTA by CTA as the rows finish, into slot (step & 1) of its OWN buffer: each double is one 16-byte packet
+// {lo, step, hi, step} whose 8-byte halves carry their own flag (the low-latency protocol NCCL calls LL) -- no staging
+// copy, no NCCL call, no memory fence, no remote store.  ll_gather_kernel on every rank (stream-ordered before the
+// orthogonalisation) PULLS all n packets, its own from local memory and the others over NVLink, spinning per element
+// until both flags show the step, so the transfer of the finished rows overlaps the rest of the peers' SYMV; a watchdog
+// raises the error word instead of hanging.  Slot reuse two steps later is safe: a rank overwrites its slot for step
+// j+2 only after its gather of step j+1 completed, i.e. after every peer produced step j+1, which each peer does
+// (stream order) after its gather of step j.
+// Three push-based versions were measured first (profiles/r1_fused_allgather.md): (1) every CTA stores its rows to all
+// peers + a system-scope fence per CTA: SYMV bandwidth halved; (2) the last CTA pushes the block, one fence.sys: 6 %
+// faster than NCCL at 2 GPUs, 11 % slower at 8 (a fence.sys behind stores to 7 peers costs tens of microseconds; with
+// 16 segment pushes, 80 % slower); (3) LL packets stored to all peers by every CTA, no fence: bit-correct but 2.5x
+// slower at N = 50 000 -- remote stores issued from all SMs while they stream Ms from HBM stall the SYMV.
 constexpr int MAX_PEERS = 16;
-struct PeerTable { double* w[MAX_PEERS]; unsigned int* flags[MAX_PEERS]; };
+struct PeerTable { uint4* ll[MAX_PEERS]; };
 
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_ll(uint4* p, double v, unsigned int flag) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned int)__double2loint(v)), "r"(flag),
+                 "r"((unsigned int)__double2hiint(v)), "r"(flag) : "memory");
 }
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ uint4 ld_ll(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
 
 __global__ void __launch_bounds__(256)
-symv_allgather_kernel(const double* __restrict__ Ms, int rows, int m, const double* __restrict__ q, PeerTable peers, int world,
-                      int rank, int n_pad, int row0, unsigned int step, unsigned int* __restrict__ counter) {
+symv_allgather_kernel(const double* __restrict__ Ms, int rows, int m, const double* __restrict__ q, uint4* __restrict__ mine_ll,
+                      int n_pad, int row0, unsigned int step) {
+    __shared__ double res[8];
     const int wrp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + wrp;
-    const int slot = (int)(step & 1u);
-    double* mine = peers.w[rank] + (size_t)slot * n_pad + row0;        // this rank's rows inside its own gather buffer
     if (row < rows) {
         const double* a = Ms + (size_t)row * m;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -1411,56 +1417,44 @@ symv_allgather_kernel(const double* __restrict__ Ms, int rows, int m, const doub
         }
         for (; cidx < m; cidx += 32) a0 = fma(__ldcs(a + cidx), __ldg(q + cidx), a0);
         const double tot = warp_sum((a0 + a1) + (a2 + a3));
-        if (lane == 0) mine[row] = tot;
-    }
-    // last-CTA detection (device scope): the CTA that completes the block pushes it to every peer over NVLink
-    __shared__ bool last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int prev = atomicAdd(counter + slot, 1u);
-        last = (prev == gridDim.x - 1);
-        if (last) counter[slot] = 0u;
+        if (lane == 0) res[wrp] = tot;
     }
     __syncthreads();
-    if (!last) return;
-    __threadfence();
-    const int n2 = rows >> 1;                                            // 16-byte stores; row0 and n_pad are even
-    const double2* src2 = reinterpret_cast<const double2*>(mine);
-    for (int p = 0; p < world; ++p) {
-        if (p == rank) continue;
-        double* dst = peers.w[p] + (size_t)slot * n_pad + row0;
-        double2* dst2 = reinterpret_cast<double2*>(dst);
-        for (int i = threadIdx.x; i < n2; i += blockDim.x) dst2[i] = __ldcg(src2 + i);
-        if ((rows & 1) && threadIdx.x == 0) dst[rows - 1] = __ldcg(mine + rows - 1);
-    }
-    __threadfence_system();                                              // the peer stores are performed before the flags
-    __syncthreads();
-    if (threadIdx.x < world) st_release_sys(peers.flags[threadIdx.x] + slot * MAX_PEERS + rank, step);
+    // this CTA's 8 rows as 8 packets (128 contiguous bytes) in the rank's OWN buffer; the peers pull them over NVLink
+    if (threadIdx.x < 8 && blockIdx.x * 8 + threadIdx.x < rows)
+        st_ll(mine_ll + (size_t)(step & 1u) * n_pad + row0 + blockIdx.x * 8 + threadIdx.x, res[threadIdx.x], step);
 }
 
-// Waits until every rank's flag of the slot shows `step`; on timeout raises the error word instead of hanging.
-__global__ void comm_wait_kernel(const unsigned int* __restrict__ flags, int world, unsigned int step, long long timeout_cycles,
-                                 unsigned int* __restrict__ error) {
-    const int r = threadIdx.x;
-    if (r < world) {
-        const long long t0 = clock64();
-        while (ld_acquire_sys(flags + (step & 1u) * MAX_PEERS + r) != step) {
-            if (clock64() - t0 > timeout_cycles) { atomicExch(error, 0x100u + (unsigned int)r); break; }
-            __nanosleep(100);
+// Receiver: element i lives in the buffer of rank i / rows_per (local memory for this rank's own rows, NVLink peer memory
+// otherwise); w[i] = its double once both flags of the packet show `step`.  On timeout the error word is raised.
+__global__ void __launch_bounds__(256)
+ll_gather_kernel(PeerTable peers, int rows_per, int n_pad, int n, unsigned int step, long long timeout_cycles,
+                 double* __restrict__ w, unsigned int* __restrict__ error) {
+    const long long t0 = clock64();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4* src = peers.ll[i / rows_per] + (size_t)(step & 1u) * n_pad + i;
+        uint4 v = ld_ll(src);
+        while (v.y != step || v.w != step) {
+            if (clock64() - t0 > timeout_cycles) { atomicExch(error, 0x100u); return; }
+            __nanosleep(200);
+            v = ld_ll(src);
         }
+        w[i] = __hiloint2double((int)v.z, (int)v.x);
     }
-    __threadfence_system();
 }
 
 }  // namespace lanczos
+
+namespace {
+inline size_t comm_ll_bytes(int n_pad) { return sizeof(uint4) * 2 * (size_t)n_pad; }
+inline size_t comm_w_bytes(int n_pad) { return sizeof(double) * (size_t)n_pad; }
+}
 
 // Communication buffer of this rank (see above) and its IPC handle.
 int run_comm_alloc(esper_ctx* c, int n_pad, int world, void* handle_out) {
     using namespace lanczos;
     if (n_pad < 1 || world < 1 || world > MAX_PEERS) return fail(c, ESPER_E_ARG, "comm_alloc: need n_pad >= 1 and 1 <= world <= %d", MAX_PEERS);
-    const size_t w_bytes = sizeof(double) * 2 * (size_t)n_pad;
-    const size_t bytes = w_bytes + sizeof(unsigned int) * (2 * MAX_PEERS + 2 + 1 + 29);
+    const size_t bytes = comm_ll_bytes(n_pad) + comm_w_bytes(n_pad) + 128;
     c->comm_buf.release();                                   // a fresh allocation: its handle is exported below
     ESPER_RESERVE(c, c->comm_buf, bytes);
     ESPER_CUDA(c, cudaMemsetAsync(c->comm_buf.p, 0, bytes, c->stream));
@@ -1477,7 +1471,6 @@ int run_comm_open(esper_ctx* c, const void* handles, int rank, int world) {
     using namespace lanczos;
     if (!c->comm_buf.p || world != c->comm_world || rank < 0 || rank >= world)
         return fail(c, ESPER_E_STATE, "comm_open: call comm_alloc with the same world size first");
-    const size_t w_bytes = sizeof(double) * 2 * (size_t)c->comm_n_pad;
     for (int p = 0; p < world; ++p) {
         void* base = nullptr;
         if (p == rank) base = c->comm_buf.p;
@@ -1493,7 +1486,6 @@ int run_comm_open(esper_ctx* c, const void* handles, int rank, int world) {
         }
         c->comm_peer[p] = base;
     }
-    (void)w_bytes;
     c->comm_rank = rank; c->comm_open = true;
     return ESPER_OK;
 }
@@ -1511,45 +1503,42 @@ int run_symv_allgather(esper_ctx* c, int rows, int m, int row0, const double* q_
     using namespace lanczos;
     if (!c->comm_open) return fail(c, ESPER_E_STATE, "symv_allgather_d: no open communicator (comm_alloc + comm_open)");
     if (step < 1 || row0 < 0 || row0 + rows > c->comm_n_pad) return fail(c, ESPER_E_ARG, "symv_allgather_d: step >= 1 and row0 + rows <= n_pad required");
-    PeerTable pt;
-    const size_t w_bytes = sizeof(double) * 2 * (size_t)c->comm_n_pad;
-    for (int p = 0; p < MAX_PEERS; ++p) {
-        char* base = (char*)c->comm_peer[p < c->comm_world ? p : c->comm_rank];
-        pt.w[p] = reinterpret_cast<double*>(base);
-        pt.flags[p] = reinterpret_cast<unsigned int*>(base + w_bytes);
-    }
-    unsigned int* counter = reinterpret_cast<unsigned int*>(c->comm_buf.as<char>() + w_bytes) + 2 * MAX_PEERS;
+    if (row0 != c->comm_rank * (c->comm_n_pad / c->comm_world))
+        return fail(c, ESPER_E_ARG, "symv_allgather_d: row0 must be rank * rows_per_rank (%d)", c->comm_rank * (c->comm_n_pad / c->comm_world));
     {
         LaunchScope ls(c, "lanczos");
-        symv_allgather_kernel<<<ceil_div(rows, 8), 256, 0, c->stream>>>(c->markov.as<double>(), rows, m, q_d, pt, c->comm_world,
-                                                                        c->comm_rank, c->comm_n_pad, row0, (unsigned int)step, counter);
+        symv_allgather_kernel<<<ceil_div(rows, 8), 256, 0, c->stream>>>(c->markov.as<double>(), rows, m, q_d, c->comm_buf.as<uint4>(),
+                                                                        c->comm_n_pad, row0, (unsigned int)step);
     }
     ESPER_CUDA(c, cudaGetLastError());
     return ESPER_OK;
 }
 
-// Enqueue the wait for step `step`; *w_full_d = this rank's gathered vector (slot step & 1), valid after the wait.
-int run_comm_wait(esper_ctx* c, int step, double** w_full_d) {
+// Enqueue the unpack of step `step` (waits per element for its flags); *w_full_d = the gathered dense vector on this rank.
+int run_comm_wait(esper_ctx* c, int step, int n, double** w_full_d) {
     using namespace lanczos;
     if (!c->comm_open) return fail(c, ESPER_E_STATE, "comm_wait_d: no open communicator");
-    const size_t w_bytes = sizeof(double) * 2 * (size_t)c->comm_n_pad;
-    unsigned int* flags = reinterpret_cast<unsigned int*>(c->comm_buf.as<char>() + w_bytes);
-    unsigned int* error = flags + 2 * MAX_PEERS + 2;
+    if (n < 1 || n > c->comm_n_pad) return fail(c, ESPER_E_ARG, "comm_wait_d: need 1 <= n <= n_pad");
+    PeerTable pt;
+    for (int p = 0; p < MAX_PEERS; ++p) pt.ll[p] = reinterpret_cast<uint4*>(c->comm_peer[p < c->comm_world ? p : c->comm_rank]);
+    double* w = reinterpret_cast<double*>(c->comm_buf.as<char>() + comm_ll_bytes(c->comm_n_pad));
+    unsigned int* error = reinterpret_cast<unsigned int*>(c->comm_buf.as<char>() + comm_ll_bytes(c->comm_n_pad) + comm_w_bytes(c->comm_n_pad));
     {
         LaunchScope ls(c, "lanczos");
-        comm_wait_kernel<<<1, 32, 0, c->stream>>>(flags, c->comm_world, (unsigned int)step, 20000000000LL, error);   // ~10 s
+        const int grid = std::max(1, std::min(ceil_div(n, 256), c->sm_count));
+        ll_gather_kernel<<<grid, 256, 0, c->stream>>>(pt, c->comm_n_pad / c->comm_world, c->comm_n_pad, n, (unsigned int)step,
+                                                      20000000000LL, w, error);                                  // ~10 s watchdog
     }
     ESPER_CUDA(c, cudaGetLastError());
-    if (w_full_d) *w_full_d = c->comm_buf.as<double>() + (size_t)(step & 1) * c->comm_n_pad;
+    if (w_full_d) *w_full_d = w;
     return ESPER_OK;
 }
 
-// 0 = healthy; 0x100 + r = the wait for rank r timed out (synchronises the stream).
+// 0 = healthy; non-zero = an unpack timed out (synchronises the stream).
 int run_comm_status(esper_ctx* c, unsigned int* status) {
     using namespace lanczos;
     if (!c->comm_buf.p) return fail(c, ESPER_E_STATE, "comm_status: no communicator");
-    const size_t w_bytes = sizeof(double) * 2 * (size_t)c->comm_n_pad;
-    const unsigned int* error = reinterpret_cast<unsigned int*>(c->comm_buf.as<char>() + w_bytes) + 2 * MAX_PEERS + 2;
+    const unsigned int* error = reinterpret_cast<unsigned int*>(c->comm_buf.as<char>() + comm_ll_bytes(c->comm_n_pad) + comm_w_bytes(c->comm_n_pad));
     ESPER_CUDA(c, cudaMemcpyAsync(status, error, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
     ESPER_CUDA(c, cudaStreamSynchronize(c->stream));
     return ESPER_OK;

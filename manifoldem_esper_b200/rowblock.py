@@ -11,7 +11,7 @@ DiffusionMaps.py:166); the arithmetic per element is the same as in the single-G
 After the all-gather every rank orthogonalises the same replicated vector with the same deterministic
 kernels, so no further reduction is needed.  On GPUs the per-step SYMV and its all-gather are ONE kernel
 (`esper_symv_allgather_d`): every rank stores its rows of w straight into all peers' buffers over NVLink (CUDA IPC
-peer memory) and publishes a flag; `CudaBackend(fused=True)` selects it, the NCCL all-gather remains as the
+peer memory) as {value, step} packets, flag in the data, no fences; `CudaBackend(fused=True)` selects it, the NCCL all-gather remains as the
 reference implementation of the same exchange (`fused=False`; identical bits).  `embed_oversized` is written against a small backend interface
 so that the orchestration is exercised on CPU (gloo, numpy backend in tests/) and on GPUs (NCCL, CudaBackend).
 """
@@ -94,6 +94,12 @@ class CudaBackend:
         if self.fused:
             # one gather buffer per rank, mapped by every peer through CUDA IPC
             import torch.distributed as dist
+            # the exchange spins on flags written by the peers: every rank needs a GPU of its own (ranks sharing one
+            # GPU are not guaranteed to run at the same time)
+            devs = [None] * world
+            dist.all_gather_object(devs, int(self.ctx.device))
+            if len(set(devs)) != world or world > t.cuda.device_count():
+                raise RuntimeError('fused SYMV + all-gather needs one GPU per rank (devices of the ranks: %s)' % devs)
             handle = self.ctx.comm_alloc(rows_per * world, world)
             handles = [None] * world
             dist.all_gather_object(handles, handle)
@@ -109,7 +115,7 @@ class CudaBackend:
     def symv_allgather(self, j):
         """Fused: w = Ms[rows, :] q_j stored into every rank's gather buffer; returns after enqueueing the wait."""
         self.ctx.symv_allgather_d(self.nrows, self.n, self.row0, self.V[j].data_ptr(), j)
-        self._w_ptr = self.ctx.comm_wait_d(j)
+        self._w_ptr = self.ctx.comm_wait_d(j, self.n)
 
     def ortho(self, j):
         w_ptr = self._w_ptr if self.fused else self.w_full.data_ptr()
@@ -119,7 +125,7 @@ class CudaBackend:
         if self.fused:
             st = self.ctx.comm_status()
             if st:
-                raise RuntimeError('peer-memory all-gather: wait for rank %d timed out' % (st - 0x100))
+                raise RuntimeError('peer-memory all-gather: an element of the gathered vector never arrived (watchdog)')
 
     def lanczos_free(self):
         if self.fused:
