@@ -91,8 +91,9 @@ class CudaBackend:
         self.w_local = t.zeros(rows_per, dtype=t.float64, device=self.device)
         self.w_full = t.zeros(rows_per * world, dtype=t.float64, device=self.device)
         self.ab = t.zeros((max_steps + 2, 2), dtype=t.float64, device=self.device)
-        if self.fused:
-            # one gather buffer per rank, mapped by every peer through CUDA IPC
+        if self.fused and getattr(self, '_comm_key', None) != (rows_per, world):
+            # one gather buffer per rank, mapped by every peer through CUDA IPC; set up once per backend and reused by
+            # later embeddings (IPC mapping costs milliseconds per peer)
             import torch.distributed as dist
             # the exchange spins on flags written by the peers: every rank needs a GPU of its own (ranks sharing one
             # GPU are not guaranteed to run at the same time)
@@ -100,11 +101,13 @@ class CudaBackend:
             dist.all_gather_object(devs, int(self.ctx.device))
             if len(set(devs)) != world or world > t.cuda.device_count():
                 raise RuntimeError('fused SYMV + all-gather needs one GPU per rank (devices of the ranks: %s)' % devs)
+            self.comm_close()
             handle = self.ctx.comm_alloc(rows_per * world, world)
             handles = [None] * world
             dist.all_gather_object(handles, handle)
             self.ctx.comm_open(handles, dist.get_rank(), world)
-            dist.barrier()                                  # nobody stores into a buffer that is not mapped everywhere yet
+            dist.barrier()                                  # nobody reads a buffer that is not mapped everywhere yet
+            self._comm_key, self._step0 = (rows_per, world), 0
 
     def lanczos_start(self, degree_all):
         self.ctx.lanczos_start_d(self.n, degree_all, self.V.data_ptr())
@@ -114,8 +117,10 @@ class CudaBackend:
 
     def symv_allgather(self, j):
         """Fused: w = Ms[rows, :] q_j stored into every rank's gather buffer; returns after enqueueing the wait."""
-        self.ctx.symv_allgather_d(self.nrows, self.n, self.row0, self.V[j].data_ptr(), j)
-        self._w_ptr = self.ctx.comm_wait_d(j, self.n)
+        step = self._step0 + j                            # packet flags never repeat over the life of the communicator
+        self.ctx.symv_allgather_d(self.nrows, self.n, self.row0, self.V[j].data_ptr(), step)
+        self._w_ptr = self.ctx.comm_wait_d(step, self.n)
+        self._steps_used = j
 
     def ortho(self, j):
         w_ptr = self._w_ptr if self.fused else self.w_full.data_ptr()
@@ -129,10 +134,17 @@ class CudaBackend:
 
     def lanczos_free(self):
         if self.fused:
+            self._step0 += getattr(self, '_steps_used', 0)  # the same on every rank (replicated recurrence)
+            self._steps_used = 0
+
+    def comm_close(self):
+        """Unmap the peers' buffers (collective: every rank must call it)."""
+        if getattr(self, '_comm_key', None) is not None:
             import torch.distributed as dist
             self.ctx.sync()
-            dist.barrier()                                  # every rank is done storing into its peers
+            dist.barrier()                                  # every rank is done reading its peers
             self.ctx.comm_close()
+            self._comm_key = None
 
     def read_ab(self, steps):
         self.ctx.sync()

@@ -141,3 +141,12 @@ def test_two_rank_rowblock_embedding(tmp_path, lib_built):
     # replicated state: both ranks end with the same numbers
     assert outs[0]['val_hash'] == outs[1]['val_hash'] and outs[0]['steps'] == outs[1]['steps']
     assert abs(outs[0]['vec_hash'] - outs[1]['vec_hash']) < 1e-9
+
+
+def test_cuda_backend_implements_the_backend_interface():
+    """Every method embed_oversized calls on the numpy test backend exists on the GPU backend (no GPU needed to check)."""
+    import re
+    names = set(re.findall(r'^    def ([a-z][a-z_]*)\(', WORKER.split('class NumpyBackend')[1].split('\ndef ')[0], flags=re.M))
+    assert {'dist_rows', 'symv', 'ortho', 'read_ab', 'ritz_vectors'} <= names
+    for name in sorted(names) + ['symv_allgather', 'comm_check', 'lanczos_free', 'comm_close', 'sync']:
+        assert callable(getattr(rowblock.CudaBackend, name, None)), name

@@ -99,5 +99,6 @@ with torch.cuda.stream(stream):
         vv = [float(min(np.abs(res['vec'][:, i] - vec1[:, i]).max(), np.abs(res['vec'][:, i] + vec1[:, i]).max())) for i in range(k)]
         print('rank %d rows [%d,%d) bit-equal to single-GPU D: %s; val rel diff %.2e; vec diff %s (single-GPU steps %d)' % (
             rank, be.row0, be.row0 + be.nrows, same, ev, np.array2string(np.array(vv), precision=1), it1), flush=True)
+bf.comm_close()
 dist.barrier()
 dist.destroy_process_group()
