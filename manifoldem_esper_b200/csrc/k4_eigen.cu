@@ -45,6 +45,56 @@ __global__ void __launch_bounds__(256) update_kernel(const double* __restrict__ 
     if (alpha_slot && blockIdx.x == 0 && threadIdx.x == 0) *alpha_slot += h[nb - 1];
 }
 
+// Row-block (replicated) orthogonalisation at large m: the same two operations with enough loads in flight to stream V
+// from HBM.  dots: grid (basis vector, DOT_SPLIT row ranges), four independent accumulators per thread, partial sums
+// h_part[i][s]; update: every CTA first adds the DOT_SPLIT partials of every coefficient in a fixed order (shared
+// memory; every rank computes the same bits), then w -= sum_i h[i] V_i with four independent accumulators.
+constexpr int DOT_SPLIT = 8;
+__global__ void __launch_bounds__(256) dots_split_kernel(const double* __restrict__ V, int m, const double* __restrict__ w,
+                                                         double* __restrict__ h_part) {
+    __shared__ double sh[32];
+    const double* v = V + (size_t)blockIdx.x * m;
+    const int chunk = (m + DOT_SPLIT - 1) / DOT_SPLIT;
+    const int r0 = blockIdx.y * chunk, r1 = min(m, r0 + chunk);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int r = r0 + threadIdx.x;
+    for (; r + 768 < r1; r += 1024) {
+        const double x0 = __ldg(v + r), x1 = __ldg(v + r + 256), x2 = __ldg(v + r + 512), x3 = __ldg(v + r + 768);
+        s0 = fma(x0, __ldg(w + r), s0);       s1 = fma(x1, __ldg(w + r + 256), s1);
+        s2 = fma(x2, __ldg(w + r + 512), s2); s3 = fma(x3, __ldg(w + r + 768), s3);
+    }
+    for (; r < r1; r += 256) s0 = fma(__ldg(v + r), __ldg(w + r), s0);
+    const double s = block_sum((s0 + s1) + (s2 + s3), sh);
+    if (threadIdx.x == 0) h_part[(size_t)blockIdx.x * DOT_SPLIT + blockIdx.y] = s;
+}
+
+__global__ void __launch_bounds__(256) update_split_kernel(const double* __restrict__ V, int m, int nb,
+                                                           const double* __restrict__ h_part, double* __restrict__ w,
+                                                           double* __restrict__ alpha_slot) {
+    extern __shared__ double hs[];                     // [nb] summed coefficients
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        double t = h_part[(size_t)i * DOT_SPLIT];
+#pragma unroll
+        for (int q = 1; q < DOT_SPLIT; ++q) t += h_part[(size_t)i * DOT_SPLIT + q];
+        hs[i] = t;
+    }
+    __syncthreads();
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < m) {
+        double a0 = w[r], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int i = 0;
+        for (; i + 3 < nb; i += 4) {
+            const double x0 = __ldg(V + (size_t)i * m + r), x1 = __ldg(V + (size_t)(i + 1) * m + r),
+                         x2 = __ldg(V + (size_t)(i + 2) * m + r), x3 = __ldg(V + (size_t)(i + 3) * m + r);
+            a0 = fma(-hs[i], x0, a0);     a1 = fma(-hs[i + 1], x1, a1);
+            a2 = fma(-hs[i + 2], x2, a2); a3 = fma(-hs[i + 3], x3, a3);
+        }
+        for (; i < nb; ++i) a0 = fma(-hs[i], __ldg(V + (size_t)i * m + r), a0);
+        w[r] = (a0 + a1) + (a2 + a3);
+    }
+    if (alpha_slot && blockIdx.x == 0 && threadIdx.x == 0) *alpha_slot += hs[nb - 1];
+}
+
 __device__ __forceinline__ double ld_cg(const double* p) { return __ldcg(p); }
 
 struct StepParams {
@@ -1577,12 +1627,13 @@ int run_lanczos_start(esper_ctx* c, int m, const double* degree_all_h, double* V
 int run_lanczos_ortho(esper_ctx* c, int m, int j, double* V_d, double* w_d, double* ab_d) {
     using namespace lanczos;
     cudaStream_t st = c->stream;
-    ESPER_RESERVE(c, c->lan_h, sizeof(double) * (size_t)(j + 8 > 4096 ? j + 8 : 4096));
+    if (j + 1 > 5000) return fail(c, ESPER_E_ARG, "lanczos_ortho_d: at most 5000 basis vectors");
+    ESPER_RESERVE(c, c->lan_h, sizeof(double) * round_up((size_t)(j + 8) * DOT_SPLIT, 16384));   // grows in 128 kB steps
     double* h = c->lan_h.as<double>();
     ESPER_CUDA(c, cudaMemsetAsync(ab_d, 0, 2 * sizeof(double), st));
     for (int pass = 0; pass < 2; ++pass) {
-        { LaunchScope ls(c, "lanczos"); dots_kernel<<<j + 1, 256, 0, st>>>(V_d, m, w_d, h); }
-        { LaunchScope ls(c, "lanczos"); update_kernel<<<ceil_div(m, 256), 256, 0, st>>>(V_d, m, j + 1, h, w_d, ab_d); }
+        { LaunchScope ls(c, "lanczos"); dots_split_kernel<<<dim3(j + 1, DOT_SPLIT), 256, 0, st>>>(V_d, m, w_d, h); }
+        { LaunchScope ls(c, "lanczos"); update_split_kernel<<<ceil_div(m, 256), 256, sizeof(double) * (size_t)(j + 1), st>>>(V_d, m, j + 1, h, w_d, ab_d); }
     }
     { LaunchScope ls(c, "lanczos"); normalize_kernel<<<1, 1024, 0, st>>>(w_d, m, V_d + (size_t)(j + 1) * m, ab_d + 1); }
     ESPER_CUDA(c, cudaGetLastError());

@@ -209,7 +209,7 @@ def embed_oversized(backend, comm, n, k=16, eps=None, a0=None, tol=0.0, max_step
     while not converged and steps < max_steps:
         j = steps + 1
         if getattr(backend, 'fused', False):
-            backend.symv_allgather(j)                             # ONE kernel: SYMV + stores into all peers + flag
+            backend.symv_allgather(j)                             # SYMV writing wire-format packets + the pull
         else:
             backend.symv(j)                                       # w_local = Ms[rows, :] q_j
             comm.allgather_vec(backend.w_full, backend.w_local)   # the per-step collective
