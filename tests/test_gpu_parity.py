@@ -659,3 +659,42 @@ def test_bin_accumulate_bit_exact(ctx):
         ctx.bin_accumulate(stack, [400], [0, 1])
     with pytest.raises(ValueError):
         ctx.bin_accumulate(stack, [1, 2], [0, 2, 1])
+
+
+def test_whole_chain_through_files_with_the_launcher(ctx, tmp_path):
+    """Generate_TauSNR.op -> launcher (Distances.op non-CTF, DiffusionMaps.op, Rotation_Histograms.op) on a tree laid out
+    like the reference's, every stage reading the previous stage's files; each output checked against the oracle applied to
+    the same input file."""
+    from manifoldem_esper_b200 import launcher
+    root = tmp_path / 'tree'
+    dm = root / '1_Embedding' / 'DM'
+    rot = root / '2_Manifold_Rotations'
+    prep = root / '0_Data_Inputs' / 'Pristine_AddTauSNR'
+    data = root / '0_Data_Inputs' / 'CTF5k15k_SNRpt1_ELS_2D'          # the data directory Distances.op reads (:50)
+    for d in (dm, rot, prep, root / '0_Data_Inputs' / 'Pristine_2D', data):
+        os.makedirs(d)
+    pds = ['001', '002']
+    for pd in pds:
+        mrc.write_stack(str(root / '0_Data_Inputs' / 'Pristine_2D' / ('PD_%s.mrcs' % pd)),
+                        synth.pristine_states(box=32, n_side=8, pd=int(pd)))
+        Generate_TauSNR.op(str(prep), pd, SNR=2.0, tau=5, seed=int(pd), ctx=ctx)
+        os.replace(str(prep / 'Modified_Stacks' / ('PD%s_SNR_tau5_stack.mrcs' % pd)), str(data / ('PD%s_SNR_tau5_stack.mrcs' % pd)))
+    work = launcher._stage_fns(str(root), {'dist', 'dm', 'rot'}, 4, False, 8, False, ctx.device, ctf=False)
+    recs = launcher.run_sharded(pds, work, 0, 1)
+    for pd, rec in zip(pds, recs):
+        stack = np.asarray(mrc.mmap(str(data / ('PD%s_SNR_tau5_stack.mrcs' % pd))).data)
+        assert stack.shape == (320, 32, 32)
+        D = np.load(str(dm / 'Data_Distances' / ('PD_%s_dist.npy' % pd)))
+        assert d_err(D, O.distances_gram_f64(O.standardize_stack(stack))) < D_TOL
+        val = np.load(str(dm / 'Data_Manifolds' / ('PD_%s_val.npy' % pd)))
+        vec = np.load(str(dm / 'Data_Manifolds' / ('PD_%s_vec.npy' % pd)))
+        assert val.shape == (8,) and vec.shape == (320, 8) and val[0] == 1.0 and np.all(np.diff(val) <= 0)
+        try:
+            ref = O.rotation_histograms_op(vec, dim=4, PCA=False, CTF=True)
+        except IndexError:                      # no mixed pair of parabolic subspaces: the reference fails too (:266)
+            assert not rec['ok'] and 'IndexError' in rec['error']
+            continue
+        assert rec['ok'], rec
+        out = rot / 'Data_Rotations' / ('PD%s' % pd)
+        assert np.array_equal(np.load(str(out / ('PD%s_RotMatrices.npy' % pd))), ref['RotMatrices'])
+        assert np.array_equal(np.load(str(out / ('PD%s_RotEigenfunctions.npy' % pd))), ref['RotEigenfunctions'])
