@@ -188,6 +188,9 @@ def run_ours(args):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     torch.cuda.set_device(local_rank)
+    # pinned stacks and host threads on the NUMA node of this rank's GPU (matters for the e2e figure at 8 GPUs)
+    from manifoldem_esper_b200 import hostbind
+    numa = hostbind.bind_to_gpu_numa_node(local_rank) if world > 1 and not args.no_numa_bind else {'bound': False}
     stream = torch.cuda.Stream()
     ctx = _capi.Context(local_rank, stream=stream.cuda_stream)
 
@@ -355,7 +358,7 @@ def run_ours(args):
         'config': {'workload': WORKLOAD, 'pd_per_rank_per_step': 1, 'sharding': 'independent PDs per rank, no data-path collective',
                    'pipelining': '%d PDs in flight per GPU (one host thread / ctx / stream each)' % NF, 'serial_ms_per_step': ms_serial / args.steps,
                    'l2': 'inputs larger than L2 (500 MB stack per PD, two alternating stacks per rank)',
-                   'lanczos_steps': iters_used[-1] if iters_used else None},
+                   'lanczos_steps': iters_used[-1] if iters_used else None, 'numa_bind_rank0': numa},
         'e2e': {'value': pds / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(N_IMG * P * 4),
                 'd2h_bytes_per_step': int(N_IMG * N_IMG * 8 + len(LOG_EPS) * 8 + K_EIG * 8 + N_IMG * K_EIG * 8),
                 'ms_per_step': ms_e2e / args.steps, 'h2d_probe_gbs': round(h2d_gbs, 2),
@@ -399,6 +402,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-numa-bind', action='store_true', help='do not restrict ranks to the CPUs of their GPU\'s NUMA node')
     ap.add_argument('--eig-mode', type=int, default=-1, help='esper_dmap_config mode (-1 = throughput when several PDs are in flight)')
     ap.add_argument('--inflight', type=int, default=4, help='PDs in flight per GPU (host threads / ctxs / streams)')
     args = ap.parse_args()

@@ -126,6 +126,9 @@ def main(argv=None):
             out = [None] * world
             dist.all_gather_object(out, local)
             return out
+    if world > 1:
+        from . import hostbind
+        hostbind.bind_to_gpu_numa_node(local_rank)      # host buffers of this rank next to its GPU (best effort)
     work = _stage_fns(args.root, set(args.stages.split(',')), args.dim, args.pca, args.k, args.skip_existing, local_rank, ctf=not args.no_ctf)
     recs = run_sharded(parse_pds(args.pds), work, rank, world, gather)
     failed = [r for r in recs if not r.get('ok')]

@@ -185,3 +185,11 @@ def test_mrc_info_host_entry(lib_built, tmp_path):
         f.write(open(p, 'rb').read()[:1100])
     with pytest.raises(ValueError):
         _capi.mrc_info(str(tmp_path / 'short.mrcs'))
+
+
+def test_hostbind_is_best_effort_without_a_gpu():
+    from manifoldem_esper_b200 import hostbind
+    assert hostbind._parse_cpulist('0-3,8,10-11\n') == {0, 1, 2, 3, 8, 10, 11}
+    before = os.sched_getaffinity(0)
+    info = hostbind.bind_to_gpu_numa_node(0)               # no CUDA device here: nothing is changed, nothing raises
+    assert info['bound'] is False and os.sched_getaffinity(0) == before
