@@ -68,7 +68,7 @@ struct esper_ctx {
     std::vector<cudaEvent_t> event_pool;
     long long launches = 0;
 
-    bool attr_gram = false, attr_sweep = false, attr_lanczos_pro = false, attr_lanczos = false;
+    bool attr_gram_wide = false, attr_gram = false, attr_sweep = false, attr_lanczos_pro = false, attr_lanczos = false;
     long long lanczos_smem_set = 0;                            // dynamic shared memory opted in for the resident kernel
     int lanczos_mode = 0;                                      // 0 latency (Ms resident on chip), 1 throughput (streamed, two grids per SM)
     int lanczos_fallbacks = 0;                                 // PRO runs repeated with full reorthogonalisation

@@ -146,9 +146,191 @@ __device__ __forceinline__ void tile_coords(int t, int nt, int& ti, int& tj) {
 constexpr int FULL_RECT = -2;
 __device__ __forceinline__ void tile_map(int t, int nt, int rect_ti0, int& ta, int& tb, bool& transposed) {
     if (rect_ti0 == FULL_RECT) { ta = t / nt; tb = t % nt; transposed = false; return; }
+    if (rect_ti0 == -3) {                      // WIDE_TRI: t = virtual 128x128 tile 2 w + h of wide tile w (see gram_wide_kernel)
+        const int nt2 = (nt + 1) / 2;
+        int i = 0, rem = t >> 1;
+        while (rem >= nt2 - i / 2) { rem -= nt2 - i / 2; ++i; }
+        ta = i; tb = 2 * (i / 2 + rem) + (t & 1); transposed = false;
+        if (tb < ta || tb >= nt) ta = -1;       // redundant (below the diagonal) or beyond the matrix: nothing to store
+        return;
+    }
     if (rect_ti0 < 0) { tile_coords(t, nt, ta, tb); transposed = false; return; }
     const int ti = rect_ti0 + t / nt, tj = t % nt;
     if (tj >= ti) { ta = ti; tb = tj; transposed = false; } else { ta = tj; tb = ti; transposed = true; }
+}
+
+// ---- wide (128 x 256) tiles: EXPERIMENTAL, opt-in with ESPER_GRAM_WIDE=1, not yet validated on hardware --------------
+// Motivation (profiles/r1_gram_chain_cut_cost.md): the 128x128 kernel is bound by operand feed from L2 (60 kB per k-block
+// per SM) and pays ~330 cycles per accumulation-chain cut.  A 128x256 tile reads 96 kB for twice the MMA work (25 % fewer
+// operand bytes per flop) and halves the cuts per flop.  The upper triangle is covered by tiles (ti, tc): rows
+// [128 ti, 128 ti + 128), columns [256 tc, 256 tc + 256), tc >= ti / 2; a wide tile is stored as two 128x128 partial tiles
+// ("virtual tiles" 2 t and 2 t + 1, columns tj = 2 tc + h), so the epilogue kernels keep their layout; virtual tiles below
+// the diagonal (odd ti, h = 0: computed but redundant, +6 % work) or beyond the matrix are skipped there.
+constexpr int BN_W = 256;
+constexpr int STAGES_W = 2;
+constexpr int STAGE_W_BYTES = 2 * TILE_BYTES + 2 * (2 * TILE_BYTES);     // A hi, lo (16 kB each) + B hi, lo (32 kB each) = 96 kB
+constexpr int ACC_W = 2;                                                  // 2 x 256 TMEM columns
+constexpr int SMEM_W_BYTES = STAGES_W * STAGE_W_BYTES + 1024 + 256;
+constexpr uint32_t IDESC_W = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN_W >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr int WIDE_TRI = -3;
+
+__host__ __device__ inline int wide_tile_count(int nt) {
+    const int nt2 = (nt + 1) / 2;
+    int tot = 0;
+    for (int i = 0; i < nt; ++i) tot += nt2 - i / 2;
+    return tot;
+}
+__device__ __forceinline__ void wide_coords(int t, int nt, int& ti, int& tc) {
+    const int nt2 = (nt + 1) / 2;
+    int i = 0, rem = t;
+    while (rem >= nt2 - i / 2) { rem -= nt2 - i / 2; ++i; }
+    ti = i; tc = i / 2 + rem;
+}
+
+__device__ __forceinline__ void umma_tf32_w(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC_W), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gram_wide_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                 const __grid_constant__ CUtensorMap mapw_hi, const __grid_constant__ CUtensorMap mapw_lo,
+                 int nt, int n_tiles, int tile0, int nkb, int split_k, int drain_kb, float* __restrict__ part) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + STAGES_W * STAGE_W_BYTES;
+    const uint32_t full_bar = bars;                                     // STAGES_W x 8 B
+    const uint32_t empty_bar = bars + 8 * STAGES_W;
+    const uint32_t tfull_bar = bars + 16 * STAGES_W;                    // ACC_W x 8 B
+    const uint32_t tempty_bar = tfull_bar + 8 * ACC_W;
+    const uint32_t tmem_slot = tempty_bar + 8 * ACC_W;
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_units = n_tiles * split_k;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_hi); tma_prefetch_desc(&map_lo); tma_prefetch_desc(&mapw_hi); tma_prefetch_desc(&mapw_lo);
+        for (int s = 0; s < STAGES_W; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+        for (int a = 0; a < ACC_W; ++a) { mbar_init(tfull_bar + 8 * a, 1); mbar_init(tempty_bar + 8 * a, EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(ACC_W * BN_W));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        int stage = 0; uint32_t phase = 0;
+        for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+            const int chunk = u / n_tiles;
+            int ti, tc; wide_coords(tile0 + (u % n_tiles), nt, ti, tc);
+            const int kb0 = (int)((long long)nkb * chunk / split_k);
+            const int kb1 = (int)((long long)nkb * (chunk + 1) / split_k);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                if (elect_one_sync()) {
+                    const uint32_t sa = base + stage * STAGE_W_BYTES;
+                    const uint32_t fb = full_bar + 8 * stage;
+                    mbar_expect_tx(fb, STAGE_W_BYTES);
+                    tma_load_2d(sa, &map_hi, fb, kb * BK, ti * BM);
+                    tma_load_2d(sa + TILE_BYTES, &map_lo, fb, kb * BK, ti * BM);
+                    tma_load_2d(sa + 2 * TILE_BYTES, &mapw_hi, fb, kb * BK, tc * BN_W);
+                    tma_load_2d(sa + 4 * TILE_BYTES, &mapw_lo, fb, kb * BK, tc * BN_W);
+                }
+                __syncwarp();
+                if (++stage == STAGES_W) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+            const int chunk = u / n_tiles;
+            const int kb0 = (int)((long long)nkb * chunk / split_k);
+            const int kb1 = (int)((long long)nkb * (chunk + 1) / split_k);
+            for (int g0 = kb0; g0 < kb1; g0 += drain_kb) {
+                const int g1 = min(g0 + drain_kb, kb1);
+                mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+                const uint32_t tmem_d = tmem_base + acc * BN_W;
+                for (int kb = g0; kb < g1; ++kb) {
+                    mbar_wait(full_bar + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * STAGE_W_BYTES;
+                    const uint64_t dah0 = make_smem_desc(sa), dal0 = make_smem_desc(sa + TILE_BYTES);
+                    const uint64_t dbh0 = make_smem_desc(sa + 2 * TILE_BYTES), dbl0 = make_smem_desc(sa + 4 * TILE_BYTES);
+                    if (elect_one_sync()) {
+#pragma unroll
+                        for (int k = 0; k < BK / UK; ++k) {
+                            const uint64_t off = (uint64_t)((k * UK * 4) >> 4);
+                            umma_tf32_w(tmem_d, dal0 + off, dbh0 + off, (kb > g0 || k > 0) ? 1u : 0u);
+                            umma_tf32_w(tmem_d, dah0 + off, dbl0 + off, 1);
+                            umma_tf32_w(tmem_d, dah0 + off, dbh0 + off, 1);
+                        }
+                        umma_commit(empty_bar + 8 * stage);
+                        if (kb == g1 - 1) umma_commit(tfull_bar + 8 * acc);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES_W) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == ACC_W) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // epilogue warps 2..9: quadrant = warp & 3 (TMEM lanes), half = which 128 of the 256 accumulator columns
+        const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row = quad * 32 + lane;
+        int acc = 0; uint32_t acc_phase = 0;
+        float sum[BN];
+#pragma unroll
+        for (int q = 0; q < BN; ++q) sum[q] = 0.f;
+        for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+            const int chunk = u / n_tiles;
+            const int kb0 = (int)((long long)nkb * chunk / split_k);
+            const int kb1 = (int)((long long)nkb * (chunk + 1) / split_k);
+            for (int g0 = kb0; g0 < kb1; g0 += drain_kb) {
+                mbar_wait(tfull_bar + 8 * acc, acc_phase);
+                tc_fence_after();
+                const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN_W + half * BN);
+#pragma unroll
+                for (int cc = 0; cc < BN / 32; ++cc) {
+                    uint32_t r[32];
+                    tmem_ld32(ta + cc * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) sum[cc * 32 + q] = __fadd_rn(sum[cc * 32 + q], __uint_as_float(r[q]));
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+                if (++acc == ACC_W) { acc = 0; acc_phase ^= 1; }
+            }
+            float4* out = reinterpret_cast<float4*>(part + ((size_t)u * 2 + half) * (BM * BN));
+#pragma unroll
+            for (int q4 = 0; q4 < BN / 4; ++q4) {
+                out[(size_t)q4 * BM + row] = make_float4(sum[4 * q4], sum[4 * q4 + 1], sum[4 * q4 + 2], sum[4 * q4 + 3]);
+                sum[4 * q4] = 0.f; sum[4 * q4 + 1] = 0.f; sum[4 * q4 + 2] = 0.f; sum[4 * q4 + 3] = 0.f;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ACC_W * BN_W));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -329,6 +511,7 @@ dist_finalize_kernel(const float* __restrict__ part, int nt, int n_tiles, int ti
     const int lt = blockIdx.x;
     const int e_per = (BM * (BN / 4)) / gridDim.y;          // slice of the tile handled by this block
     int ti, tj; bool transposed; tile_map(tile0 + lt, nt, rect_ti0, ti, tj, transposed);
+    if (ti < 0) return;                                     // wide-tile mode: redundant / out-of-range virtual tile
     const bool diag = (ti == tj);
     const bool rect = rect_ti0 >= 0;
     const size_t row_off = rect ? (size_t)rect_ti0 * BM : 0;   // first global row held by D in the row-block path
@@ -367,11 +550,12 @@ dist_finalize_kernel(const float* __restrict__ part, int nt, int n_tiles, int ti
 // Gram epilogue of the PCA path (PCA.py:58: the right singular vectors of Y are the eigenvectors of Y^T Y):
 // G_ij = sum_chunks partial, mirrored; the diagonal is the FP64 |c_i|^2 of the prep pass.
 __global__ void __launch_bounds__(256)
-gram_finalize_kernel(const float* __restrict__ part, int nt, int n_tiles, int tile0, int split_k, int n,
+gram_finalize_kernel(const float* __restrict__ part, int nt, int n_tiles, int tile0, int mode, int split_k, int n,
                      const RowStat* __restrict__ st, double* __restrict__ G) {
     const int lt = blockIdx.x;
     const int e_per = (BM * (BN / 4)) / gridDim.y;
-    int ti, tj; bool transposed; tile_map(tile0 + lt, nt, -1, ti, tj, transposed);
+    int ti, tj; bool transposed; tile_map(tile0 + lt, nt, mode, ti, tj, transposed);
+    if (ti < 0) return;
     const bool diag = (ti == tj);
     for (int e = blockIdx.y * e_per + threadIdx.x; e < (blockIdx.y + 1) * e_per; e += blockDim.x) {
         const int r = e & (BM - 1), c4 = e >> 7;
@@ -490,12 +674,12 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-static int make_plane_map(esper_ctx* c, CUtensorMap* map, float* plane, int rows_pad, int ld) {
+static int make_plane_map(esper_ctx* c, CUtensorMap* map, float* plane, int rows_pad, int ld, int box_rows = gram::BM) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(c, ESPER_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows_pad};
     cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)gram::BK, (cuuint32_t)gram::BM};
+    cuuint32_t box[2] = {(cuuint32_t)gram::BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, plane, gdim, gstride, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -598,9 +782,50 @@ int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, i
         c->attr_gram = true;
     }
 
+    int drain_kb = c->drain_kb > 0 ? c->drain_kb : 2;
+    if (const char* e = getenv("ESPER_DRAIN_KB")) { const int v = atoi(e); if (v != 0) drain_kb = v; }   // experiments only
+    const char* wide_env = getenv("ESPER_GRAM_WIDE");
+    const bool wide = !rect && nt >= 2 && wide_env && atoi(wide_env) != 0 && drain_kb > 0;   // EXPERIMENTAL 128x256 tiles (see gram_wide_kernel)
+
     // Bound the split-K workspace: process the triangle in batches of tiles.
-    const size_t tile_bytes = (size_t)BM * BN * sizeof(float);
     const size_t ws_cap = (size_t)3 << 30;   // 3 GiB
+    if (wide) {
+        CUtensorMap mapw_hi, mapw_lo;
+        if ((rc = make_plane_map(c, &mapw_hi, c->plane_hi.as<float>(), rows_pad, ld, BN_W))) return rc;
+        if ((rc = make_plane_map(c, &mapw_lo, c->plane_lo.as<float>(), rows_pad, ld, BN_W))) return rc;
+        if (!c->attr_gram_wide) {
+            ESPER_CUDA(c, cudaFuncSetAttribute(gram_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_W_BYTES));
+            c->attr_gram_wide = true;
+        }
+        const int n_wide = wide_tile_count(nt);
+        const size_t wtile_bytes = (size_t)2 * BM * BN * sizeof(float);
+        int batch = n_wide;
+        int split_k = choose_split_k(c->split_k, nkb, batch, sms);
+        while ((size_t)batch * split_k * wtile_bytes > ws_cap && batch > sms) {
+            batch = (batch + 1) / 2;
+            split_k = choose_split_k(c->split_k, nkb, batch, sms);
+        }
+        ESPER_RESERVE(c, c->gram_part, (size_t)batch * split_k * wtile_bytes);
+        float* part = c->gram_part.as<float>();
+        for (int tile0 = 0; tile0 < n_wide; tile0 += batch) {
+            const int nb = (n_wide - tile0 < batch) ? n_wide - tile0 : batch;
+            int sk = choose_split_k(c->split_k, nkb, nb, sms);
+            if (sk > split_k) sk = split_k;
+            const int units = nb * sk;
+            {
+                LaunchScope ls(c, "gram");
+                gram_wide_kernel<<<units < sms ? units : sms, NUM_THREADS, SMEM_W_BYTES, c->stream>>>(map_hi, map_lo, mapw_hi, mapw_lo, nt, nb, tile0,
+                                                                                                    nkb, sk, drain_kb, part);
+            }
+            {
+                LaunchScope ls(c, "dist_finalize");
+                if (gram_out) gram_finalize_kernel<<<dim3(2 * nb, 8), 256, 0, c->stream>>>(part, nt, 2 * nb, 2 * tile0, WIDE_TRI, sk, n, st, gram_out);
+                else dist_finalize_kernel<<<dim3(2 * nb, 8), 256, 0, c->stream>>>(part, nt, 2 * nb, 2 * tile0, WIDE_TRI, sk, n, P, st, D);
+            }
+        }
+        ESPER_CUDA(c, cudaGetLastError());
+    } else {
+    const size_t tile_bytes = (size_t)BM * BN * sizeof(float);
     int batch = tiles_total;
     int split_k = choose_split_k(c->split_k, nkb, batch, sms);
     while ((size_t)batch * split_k * tile_bytes > ws_cap && batch > sms) {
@@ -610,8 +835,6 @@ int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, i
     ESPER_RESERVE(c, c->gram_part, (size_t)batch * split_k * tile_bytes);
     float* part = c->gram_part.as<float>();
 
-    int drain_kb = c->drain_kb > 0 ? c->drain_kb : 2;
-    if (const char* e = getenv("ESPER_DRAIN_KB")) { const int v = atoi(e); if (v != 0) drain_kb = v; }   // experiments only
     for (int tile0 = 0; tile0 < tiles_total; tile0 += batch) {
         const int nb = (tiles_total - tile0 < batch) ? tiles_total - tile0 : batch;
         int sk = choose_split_k(c->split_k, nkb, nb, sms);
@@ -624,11 +847,12 @@ int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, i
         }
         {
             LaunchScope ls(c, "dist_finalize");
-            if (gram_out) gram_finalize_kernel<<<dim3(nb, 8), 256, 0, c->stream>>>(part, nt, nb, tile0, sk, n, st, gram_out);
+            if (gram_out) gram_finalize_kernel<<<dim3(nb, 8), 256, 0, c->stream>>>(part, nt, nb, tile0, -1, sk, n, st, gram_out);
             else dist_finalize_kernel<<<dim3(nb, 8), 256, 0, c->stream>>>(part, nt, nb, tile0, rect_ti0, sk, n, P, st, D);
         }
     }
     ESPER_CUDA(c, cudaGetLastError());
+    }
 
     if (!gram_out && (flags & ESPER_DIST_REFINE) && c->refine_tau > 0.0 && n > 1) {
         const size_t max_pairs = rect ? (size_t)nrows * n : (size_t)n * (n - 1) / 2;
