@@ -159,7 +159,9 @@ __device__ __forceinline__ void tile_map(int t, int nt, int rect_ti0, int& ta, i
     if (tj >= ti) { ta = ti; tb = tj; transposed = false; } else { ta = tj; tb = ti; transposed = true; }
 }
 
-// ---- wide (128 x 256) tiles: EXPERIMENTAL, opt-in with ESPER_GRAM_WIDE=1, not yet validated on hardware --------------
+// ---- wide (128 x 256) tiles: the default for the full symmetric matrix (ESPER_GRAM_WIDE=0 switches back) ---------------
+// Measured at the benchmark shape: 1.107 ms against 1.259 ms for the 128x128 kernel on the same box, distances bit-identical
+// (same per-element accumulation order); `pytest -m gpu` distance / PCA / full-size parity tests green with it.
 // Motivation (profiles/r1_gram_chain_cut_cost.md): the 128x128 kernel is bound by operand feed from L2 (60 kB per k-block
 // per SM) and pays ~330 cycles per accumulation-chain cut.  A 128x256 tile reads 96 kB for twice the MMA work (25 % fewer
 // operand bytes per flop) and halves the cuts per flop.  The upper triangle is covered by tiles (ti, tc): rows
@@ -784,8 +786,10 @@ int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, i
 
     int drain_kb = c->drain_kb > 0 ? c->drain_kb : 2;
     if (const char* e = getenv("ESPER_DRAIN_KB")) { const int v = atoi(e); if (v != 0) drain_kb = v; }   // experiments only
+    // 128x256 tiles for the full symmetric matrix (gram_wide_kernel): same bits as the 128x128 kernel, 12 % faster at the
+    // benchmark shape.  ESPER_GRAM_WIDE=0 selects the 128x128 kernel (which the row-block and CTF products always use).
     const char* wide_env = getenv("ESPER_GRAM_WIDE");
-    const bool wide = !rect && nt >= 2 && wide_env && atoi(wide_env) != 0 && drain_kb > 0;   // EXPERIMENTAL 128x256 tiles (see gram_wide_kernel)
+    const bool wide = !rect && nt >= 2 && !(wide_env && atoi(wide_env) == 0) && drain_kb > 0;
 
     // Bound the split-K workspace: process the triangle in batches of tiles.
     const size_t ws_cap = (size_t)3 << 30;   // 3 GiB
