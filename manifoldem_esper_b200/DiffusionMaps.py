@@ -53,6 +53,9 @@ def op(pyDir, PD, k=16, eps=None, ctx=None):
     res = embed(Dist, k=k, eps=eps, ctx=ctx)
     np.save(os.path.join(outDir, 'PD_%s_val.npy' % PD), res['val'])
     np.save(os.path.join(outDir, 'PD_%s_vec.npy' % PD), res['vec'])
+    # the reference returns None; the summary below is what its prints show (:94-96) plus the solver's step count
+    return {'eps': float(res['eps']), 'R2': float(res['R2']) if 'R2' in res else None,
+            'slope': float(res['slope']) if 'slope' in res else None, 'lanczos_steps': int(res['iters'])}
 
 
 if __name__ == '__main__':

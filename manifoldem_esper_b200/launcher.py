@@ -91,7 +91,7 @@ def _stage_fns(root, stages, dim, pca, k, skip_existing, device, ctf=True):
         if 'dm' in stages:
             out = os.path.join(dm_dir, 'Data_Manifolds', 'PD_%s_vec.npy' % pd)
             if not (skip_existing and os.path.exists(out)):
-                t = time.time(); DiffusionMaps.op(dm_dir, pd, k=k, ctx=ctx); info['dm_s'] = time.time() - t
+                t = time.time(); info.update(DiffusionMaps.op(dm_dir, pd, k=k, ctx=ctx) or {}); info['dm_s'] = time.time() - t
         if 'pca' in stages:
             out = os.path.join(pca_dir, 'Data_Manifolds', 'PD_%s_vec.npy' % pd)
             if not (skip_existing and os.path.exists(out)):
