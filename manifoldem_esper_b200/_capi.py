@@ -45,6 +45,8 @@ SIGNATURES = {
     'esper_eps_sweep': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
     'esper_markov': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     'esper_dmap_config': (C.c_int, [C.c_void_p, C.c_int]),
+    'esper_sweep_config': (C.c_int, [C.c_void_p, C.c_int]),
+    'esper_sweep_info': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     'esper_dmap_embed': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int,
                                    C.c_void_p, C.c_void_p, _i32p]),
     'esper_image_stats': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
@@ -217,6 +219,16 @@ class Context:
         out = np.empty(coef.shape[0], dtype=np.float64)
         self._check(self._lib.esper_eps_sweep(self._h, _ptr(D), int(m), _ptr(coef), coef.shape[0], float(thr), _ptr(out)))
         return out
+
+    def sweep_config(self, mode=0):
+        """0 = general sweep kernel (default), 1 = moment sweep with automatic return to the general kernel."""
+        self._check(self._lib.esper_sweep_config(self._h, int(mode)))
+
+    def sweep_info(self):
+        """(path, bins) of the last eps_sweep: path 0 = general kernel, 1 = moment sweep."""
+        path, bins = C.c_int(0), C.c_int(0)
+        self._check(self._lib.esper_sweep_info(self._h, C.byref(path), C.byref(bins)))
+        return path.value, bins.value
 
     # -- stage 3 ----------------------------------------------------------------------------
     def markov(self, D, eps, m=None, want_matrix=True):

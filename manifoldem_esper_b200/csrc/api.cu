@@ -46,6 +46,7 @@ esper_ctx* esper_create(int device, void* stream) {
     esper_ctx* c = new esper_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    if (const char* ev = getenv("ESPER_SWEEP_MOMENTS")) c->sweep_mode = (atoi(ev) != 0) ? 1 : 0;   // experimental, see esper_sweep_config
     if (stream) {
         c->stream = reinterpret_cast<cudaStream_t>(stream);
     } else {
@@ -206,6 +207,20 @@ int esper_eps_sweep(esper_ctx* c, const double* D, int m, const double* coef, in
     int rc = need_dist(c, D, m, "eps_sweep");
     if (rc) return rc;
     return run_sweep(c, m, coef, n_eps, thr, logSum);
+}
+
+int esper_sweep_config(esper_ctx* c, int mode) {
+    ESPER_ENTER(c);
+    if (mode != 0 && mode != 1) return fail(c, ESPER_E_ARG, "sweep_config: mode must be 0 (general) or 1 (moments)");
+    c->sweep_mode = mode;
+    return ESPER_OK;
+}
+
+int esper_sweep_info(esper_ctx* c, int* last_path, int* bins) {
+    ESPER_ENTER(c);
+    if (last_path) *last_path = c->sweep_last_path;
+    if (bins) *bins = c->sweep_last_bins;
+    return ESPER_OK;
 }
 
 // ---- stage 3 -----------------------------------------------------------------------------------

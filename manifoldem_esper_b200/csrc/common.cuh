@@ -90,6 +90,7 @@ struct esper_ctx {
     esper::DevBuf pair_list;                                   // refine: flagged pairs + counter
     // stage-2/3 workspaces
     esper::DevBuf sweep_part, sweep_aux;
+    int sweep_mode = 0, sweep_last_path = 0, sweep_last_bins = 0;   // esper_sweep_config / esper_sweep_info
     esper::DevBuf markov, degree;                              // Ms [m,m], d [m]
     esper::DevBuf ctf_par, ctf_T, ctf_fy, ctf_C, ctf_ab, ctf_T12, ctf_wiener;   // CTF branch (k6_ctf.cu)
     bool attr_ctf = false;

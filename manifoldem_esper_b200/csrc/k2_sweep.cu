@@ -245,6 +245,222 @@ sweep_final_kernel(const double* __restrict__ part, int n_blocks, int n_eps, int
     if (threadIdx.x == 0) out[k] = take_log ? log(s) : s;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Moment sweep (opt-in, ESPER_SWEEP_MOMENTS=1): O(1) work per element instead of one exp() per (element, active k).
+//
+//   S_k = sum_{ij : c_k q_ij < thr} w_ij exp(-c_k q_ij),   q = D^2.
+//
+// The non-zero q are grouped into <= MB geometric bins [e_b, e_b rho), e_0 = min q, rho = 1/(1 - 2/thr) (1.25 for the
+// reference's thr = 10).  For one bin and one k exactly one of three things holds (c_k >= 0 non-increasing in k, so
+// each is a contiguous k range found by bisection; fl(c q) is monotone in q):
+//   k <  ka_b : c_k e_b >= thr        -> no element of the bin passes the truncation
+//   k >= kf_b : c_k e_{b+1} < thr     -> every element passes, and |c_k (q - mu_b)| <= thr (rho - 1)/(2 rho) = 1, so
+//                                        exp(-c q) = exp(-c mu_b) sum_p (-c h_b)^p u^p / p!,  u = (q - mu_b)/h_b in [-1, 1],
+//                                        truncated after p = MP = 16 (remainder <= e/17! = 7.6e-15 relative; all terms of
+//                                        S_k are positive, so that is the relative error of the bin's sum): only the
+//                                        moments M_p = sum w u^p are needed, accumulated in registers
+//   otherwise : the truncation boundary thr/c_k falls inside the bin (at most 2 k for the reference's grid of e^0.2 per
+//               step; more than MS -> the general kernel runs instead): evaluated per element with the same products
+//               t = c_k q and the same exp as sweep_kernel, so the inclusion test stays bit-identical.
+// Exact zeros (the diagonal, duplicate images) contribute 1 each for every k.  Launch chain: statistics -> plan (one
+// block) -> moments (one pass over D per bin; one bin on high-noise stacks, where D^2 spans a few per cent) -> final.
+// Every reduction has a fixed order (deterministic).  Numpy statement + error measurements: tools/sweep_moments_proto.py.
+constexpr int MP = 16;                       // highest moment
+constexpr int MS = 4;                        // straddling k per bin evaluated exactly
+constexpr int MB = 32;                       // bins
+constexpr int MV = MP + 1 + MS;              // values per (block, bin)
+constexpr int PLAN_HDR = 8, PLAN_BIN = 6;    // plan layout (doubles): [status, B, zero_term, n_valid, mn, mx, rho, -] + B x [lo, hi, mu, 1/h, ka, kf]
+constexpr int PLAN_LEN = PLAN_HDR + PLAN_BIN * MB;
+constexpr int MTHREADS = 256;
+constexpr int MWARPS = MTHREADS / 32;
+
+// Rows p and m-1-p are handled together: m+1 elements of the upper triangle per pair (sym) or 2m (full matrix).
+struct PairRange { int i1, j1, len1, i2, j2, len2; };
+__device__ __forceinline__ PairRange pair_range(int p, int m, int sym) {
+    PairRange r;
+    r.i1 = p; r.j1 = sym ? p : 0; r.len1 = m - r.j1;
+    r.i2 = m - 1 - p; r.j2 = sym ? r.i2 : 0; r.len2 = (r.i2 > r.i1) ? m - r.j2 : 0;
+    return r;
+}
+
+__global__ void __launch_bounds__(MTHREADS)
+moment_stats_kernel(const double* __restrict__ D, int m, int sym, double* __restrict__ stat_part /*[gridDim.x][4]*/) {
+    __shared__ double sh[4 * MWARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double mn = INFINITY, mx = 0.0, nz = 0.0, nv = 0.0;
+    const int npairs = (m + 1) >> 1;
+    for (int p = blockIdx.x; p < npairs; p += gridDim.x) {
+        const PairRange r = pair_range(p, m, sym);
+        for (int e = threadIdx.x; e < r.len1 + r.len2; e += MTHREADS) {
+            const int i = e < r.len1 ? r.i1 : r.i2;
+            const int j = e < r.len1 ? r.j1 + e : r.j2 + (e - r.len1);
+            const double d = __ldg(D + (size_t)i * m + j);
+            const double q = d * d;
+            if (q == q) {
+                const double w = (sym && j > i) ? 2.0 : 1.0;
+                nv += w;
+                if (q == 0.0) nz += w; else mn = fmin(mn, q);
+                mx = fmax(mx, q);
+            }
+        }
+    }
+    mn = warp_min(mn); mx = warp_max(mx); nz = warp_sum(nz); nv = warp_sum(nv);
+    if (lane == 0) { sh[warp] = mn; sh[MWARPS + warp] = mx; sh[2 * MWARPS + warp] = nz; sh[3 * MWARPS + warp] = nv; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mn = sh[0]; mx = sh[MWARPS]; nz = 0.0; nv = 0.0;
+        for (int w = 0; w < MWARPS; ++w) {
+            mn = fmin(mn, sh[w]); mx = fmax(mx, sh[MWARPS + w]); nz += sh[2 * MWARPS + w]; nv += sh[3 * MWARPS + w];
+        }
+        double* o = stat_part + 4 * (size_t)blockIdx.x;
+        o[0] = mn; o[1] = mx; o[2] = nz; o[3] = nv;
+    }
+}
+
+// One block: global statistics, bin edges and the k ranges of every bin.  status != 0 -> the general kernel must run.
+// Requires non-increasing finite coefficients >= 0 and 0 < thr < inf (checked by the host).
+__global__ void __launch_bounds__(32)
+moment_plan_kernel(const double* __restrict__ stat_part, int n_parts, const double* __restrict__ coef, int n_eps, double thr,
+                   double* __restrict__ plan) {
+    if (threadIdx.x != 0) return;
+    double mn = INFINITY, mx = 0.0, nz = 0.0, nv = 0.0;
+    for (int b = 0; b < n_parts; ++b) {
+        const double* s = stat_part + 4 * (size_t)b;
+        mn = fmin(mn, s[0]); mx = fmax(mx, s[1]); nz += s[2]; nv += s[3];
+    }
+    double rho = (thr > 4.0) ? 1.0 / (1.0 - 2.0 / thr) : 2.0;    // thr (rho-1)/(2 rho) <= 1; rho <= 2 keeps q - mu exact-ish
+    if (!(rho <= 2.0)) rho = 2.0;
+    int status = 0, B = 0;
+    if (mn < INFINITY) {                                          // at least one non-zero element
+        double lo = mn;
+        while (B < MB) {
+            const double hi = lo * rho;
+            double* pb = plan + PLAN_HDR + PLAN_BIN * B;
+            const double mu = 0.5 * (lo + hi), h = hi - mu;
+            int a = 0, z = n_eps;                                 // ka = first k with coef[k]*lo < thr
+            while (a < z) { const int mid = (a + z) >> 1; if (coef[mid] * lo < thr) z = mid; else a = mid + 1; }
+            const int ka = a;
+            a = 0; z = n_eps;                                     // kf = first k with coef[k]*hi < thr   (kf >= ka)
+            while (a < z) { const int mid = (a + z) >> 1; if (coef[mid] * hi < thr) z = mid; else a = mid + 1; }
+            const int kf = a < ka ? ka : a;
+            if (kf - ka > MS) status = 2;                         // too many k straddle this bin
+            if (!(h > 0.0) || !(hi < INFINITY)) status = 3;       // degenerate edges (overflow / underflow)
+            pb[0] = lo; pb[1] = hi; pb[2] = mu; pb[3] = (h > 0.0) ? 1.0 / h : 0.0; pb[4] = (double)ka; pb[5] = (double)kf;
+            ++B;
+            if (hi > mx) break;                                   // every q <= mx < hi is covered
+            lo = hi;
+            if (B == MB) status = 1;                              // D^2 spans more than rho^MB
+        }
+    }
+    if (!(mx < INFINITY)) status = 4;
+    plan[0] = (double)status; plan[1] = (double)B; plan[2] = nz; plan[3] = nv; plan[4] = mn; plan[5] = mx; plan[6] = rho; plan[7] = 0.0;
+}
+
+__global__ void __launch_bounds__(MTHREADS)
+moment_accum_kernel(const double* __restrict__ D, int m, int sym, const double* __restrict__ coef, double thr,
+                    const double* __restrict__ plan, double* __restrict__ part /*[gridDim.x][MB][MV]*/) {
+    __shared__ double sh[MWARPS * MV];
+    if (plan[0] != 0.0) return;                                   // the host falls back to sweep_kernel
+    const int B = (int)plan[1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int npairs = (m + 1) >> 1;
+    const double SMALL = 7.450580596923828e-09;                   // as in sweep_kernel
+    for (int b = 0; b < B; ++b) {
+        const double* pb = plan + PLAN_HDR + PLAN_BIN * b;
+        const double lo = pb[0], hi = pb[1], mu = pb[2], sc = pb[3];
+        const int ka = (int)pb[4], ns = (int)pb[5] - ka;
+        double cs[MS];
+#pragma unroll
+        for (int s = 0; s < MS; ++s) cs[s] = (s < ns) ? coef[ka + s] : 0.0;
+        double acc[MP + 1], st[MS];
+#pragma unroll
+        for (int p = 0; p <= MP; ++p) acc[p] = 0.0;
+#pragma unroll
+        for (int s = 0; s < MS; ++s) st[s] = 0.0;
+        for (int p = blockIdx.x; p < npairs; p += gridDim.x) {
+            const PairRange r = pair_range(p, m, sym);
+#pragma unroll 2
+            for (int e = threadIdx.x; e < r.len1 + r.len2; e += MTHREADS) {
+                const int i = e < r.len1 ? r.i1 : r.i2;
+                const int j = e < r.len1 ? r.j1 + e : r.j2 + (e - r.len1);
+                const double d = __ldg(D + (size_t)i * m + j);
+                const double q = d * d;
+                // membership: lo <= q < hi (the last bin has hi > max q); zeros and NaN belong to no bin
+                if (!(q >= lo && q < hi) || q == 0.0) continue;
+                const double w = (sym && j > i) ? 2.0 : 1.0;
+                const double u = (q - mu) * sc;
+                double pw = w;
+                acc[0] += pw;
+#pragma unroll
+                for (int pp = 1; pp <= MP; ++pp) { pw *= u; acc[pp] += pw; }
+                if (ns > 0) {
+#pragma unroll
+                    for (int s = 0; s < MS; ++s) {
+                        if (s < ns) {
+                            const double t = cs[s] * q;
+                            if (t < thr) {
+                                const double term = (t < SMALL) ? fma(t, fma(t, 0.5, -1.0), 1.0) : exp_neg_fast(fmin(t, 700.0));
+                                st[s] = fma(w, term, st[s]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();                                          // sh is reused from the previous bin
+#pragma unroll
+        for (int p = 0; p <= MP; ++p) { const double v = warp_sum(acc[p]); if (lane == 0) sh[warp * MV + p] = v; }
+#pragma unroll
+        for (int s = 0; s < MS; ++s) { const double v = warp_sum(st[s]); if (lane == 0) sh[warp * MV + MP + 1 + s] = v; }
+        __syncthreads();
+        if (threadIdx.x < MV) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < MWARPS; ++w) t += sh[w * MV + threadIdx.x];
+            part[((size_t)blockIdx.x * MB + b) * MV + threadIdx.x] = t;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+moment_final_kernel(const double* __restrict__ part, int n_blocks, const double* __restrict__ coef, int n_eps, double thr,
+                    const double* __restrict__ plan, double* __restrict__ out) {
+    __shared__ double tot[MB * MV];
+    __shared__ double pl[PLAN_LEN];
+    if (plan[0] != 0.0) return;
+    const int B = (int)plan[1];
+    for (int i = threadIdx.x; i < PLAN_HDR + PLAN_BIN * B; i += blockDim.x) pl[i] = plan[i];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int v = warp; v < B * MV; v += nwarps) {                 // v = b*MV + value
+        const int b = v / MV, x = v - b * MV;
+        double s = 0.0;
+        for (int blk = lane; blk < n_blocks; blk += 32) s += part[((size_t)blk * MB + b) * MV + x];
+        s = warp_sum(s);
+        if (lane == 0) tot[v] = s;
+    }
+    __syncthreads();
+    const double zero_term = (0.0 < thr) ? pl[2] : 0.0;
+    for (int k = threadIdx.x; k < n_eps; k += blockDim.x) {
+        const double c = coef[k];
+        double S = zero_term;
+        for (int b = 0; b < B; ++b) {
+            const double* pb = pl + PLAN_HDR + PLAN_BIN * b;
+            const int ka = (int)pb[4], kf = (int)pb[5];
+            const double* M = tot + b * MV;
+            if (k < ka) continue;
+            if (k < kf) { S += M[MP + 1 + (k - ka)]; continue; }
+            const double h = pb[1] - pb[2];                       // hi - mu, the h the moments were scaled with (sc = 1/h)
+            const double x = -(c * h);
+            double poly = M[MP];
+#pragma unroll
+            for (int p = MP - 1; p >= 0; --p) poly = fma(poly, x / (double)(p + 1), M[p]);
+            S += exp(-(c * pb[2])) * poly;
+        }
+        out[k] = log(S);
+    }
+}
+
 }  // namespace sweep
 
 int check_symmetry(esper_ctx* c, int m) {
@@ -267,6 +483,55 @@ int run_sweep(esper_ctx* c, int m, const double* coef_h, int n_eps, double thr, 
     return run_sweep_rows(c, m, m, coef_h, n_eps, thr, logsum_h, 1);
 }
 
+// Moment sweep of the full resident matrix (see the comment above moment_stats_kernel).  Returns ESPER_OK with
+// *done = 1 when logsum_h holds the result, *done = 0 when the data need the general kernel (D^2 too spread out, or
+// more than MS coefficients per bin boundary).
+static int run_sweep_moments(esper_ctx* c, int m, int sym, const double* coef_h, int n_eps, double thr, double* logsum_h, int* done) {
+    using namespace sweep;
+    *done = 0;
+    const int npairs = (m + 1) / 2;
+    int grid = c->sm_count * 2;
+    if (grid > 480) grid = 480;
+    if (grid > npairs) grid = npairs;
+    if (grid < 1) grid = 1;
+    ESPER_RESERVE(c, c->sweep_part, sizeof(double) * (size_t)grid * MB * MV);
+    ESPER_RESERVE(c, c->sweep_aux, sizeof(double) * ((size_t)n_eps * 2 + 4096) + sizeof(int) * 64);
+    double* stat_d = c->sweep_aux.as<double>();                   // [grid][4], grid <= 480
+    double* plan_d = c->sweep_aux.as<double>() + 2048;            // [PLAN_LEN] (the symmetry flag lives at 4000)
+    double* coef_d = c->sweep_aux.as<double>() + 4096;
+    double* logsum_d = coef_d + n_eps;
+    static_assert(2048 + PLAN_LEN <= 4000 && 480 * 4 <= 2048, "sweep_aux layout");
+    ESPER_CUDA(c, cudaMemcpyAsync(coef_d, coef_h, sizeof(double) * n_eps, cudaMemcpyHostToDevice, c->stream));
+    {
+        LaunchScope ls(c, "sweep");
+        moment_stats_kernel<<<grid, MTHREADS, 0, c->stream>>>(c->dist.as<double>(), m, sym, stat_d);
+    }
+    {
+        LaunchScope ls(c, "sweep");
+        moment_plan_kernel<<<1, 32, 0, c->stream>>>(stat_d, grid, coef_d, n_eps, thr, plan_d);
+    }
+    {
+        LaunchScope ls(c, "sweep");
+        moment_accum_kernel<<<grid, MTHREADS, 0, c->stream>>>(c->dist.as<double>(), m, sym, coef_d, thr, plan_d,
+                                                              c->sweep_part.as<double>());
+    }
+    {
+        LaunchScope ls(c, "sweep");
+        moment_final_kernel<<<1, 1024, 0, c->stream>>>(c->sweep_part.as<double>(), grid, coef_d, n_eps, thr, plan_d, logsum_d);
+    }
+    ESPER_CUDA(c, cudaGetLastError());
+    double hdr[PLAN_HDR];
+    ESPER_CUDA(c, cudaMemcpyAsync(hdr, plan_d, sizeof hdr, cudaMemcpyDeviceToHost, c->stream));
+    ESPER_CUDA(c, cudaMemcpyAsync(logsum_h, logsum_d, sizeof(double) * n_eps, cudaMemcpyDeviceToHost, c->stream));
+    ESPER_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (getenv("ESPER_DEBUG_SWEEP"))
+        fprintf(stderr, "[sweep moments] status %d bins %d zeros %.0f valid %.0f min %.6e max %.6e rho %.6f\n", (int)hdr[0], (int)hdr[1],
+                hdr[2], hdr[3], hdr[4], hdr[5], hdr[6]);
+    *done = (hdr[0] == 0.0) ? 1 : 0;
+    if (*done) { c->sweep_last_path = 1; c->sweep_last_bins = (int)hdr[1]; }
+    return ESPER_OK;
+}
+
 // rows x m block of D resident in c->dist; take_log = 0 returns the partial sums (row-block path).
 int run_sweep_rows(esper_ctx* c, int rows, int m, const double* coef_h, int n_eps, double thr, double* logsum_h, int take_log) {
     using namespace sweep;
@@ -274,6 +539,16 @@ int run_sweep_rows(esper_ctx* c, int rows, int m, const double* coef_h, int n_ep
     if (rows == m && c->dist_row0 < 0) {
         if (c->dist_symmetric < 0) { int rc = check_symmetry(c, m); if (rc) return rc; }
         sym = c->dist_symmetric > 0 ? 1 : 0;
+    }
+    int mono = 1;                                  // non-increasing, finite, non-negative coefficients?
+    for (int k = 0; k < n_eps; ++k)
+        if (!(coef_h[k] >= 0.0) || !(coef_h[k] < INFINITY) || (k > 0 && coef_h[k] > coef_h[k - 1])) { mono = 0; break; }
+    c->sweep_last_path = 0; c->sweep_last_bins = 0;
+    if (c->sweep_mode == 1 && rows == m && c->dist_row0 < 0 && take_log && mono && thr > 0.0 && thr < INFINITY) {
+        int done = 0;
+        const int rc = run_sweep_moments(c, m, sym, coef_h, n_eps, thr, logsum_h, &done);
+        if (rc) return rc;
+        if (done) return ESPER_OK;
     }
     const int tiles_r = ceil_div(rows, TR), tiles_c = ceil_div(m, TC);
     std::vector<int> row_start(tiles_r + 2, 0);                   // prefix count of valid tiles per tile row
@@ -295,9 +570,6 @@ int run_sweep_rows(esper_ctx* c, int rows, int m, const double* coef_h, int n_ep
     ESPER_CUDA(c, cudaMemcpyAsync(row_start_d, row_start.data(), sizeof(int) * (size_t)(tiles_r + 1), cudaMemcpyHostToDevice, c->stream));
     ESPER_CUDA(c, cudaMemsetAsync(next_tile_d, 0, sizeof(unsigned int), c->stream));
     const size_t smem = sizeof(double) * ((size_t)4 * n_eps + WARPS * KB + 4 * WARPS) + sizeof(int) * ((size_t)n_eps + 4);
-    int mono = 1;                                  // non-increasing, finite, non-negative coefficients?
-    for (int k = 0; k < n_eps; ++k)
-        if (!(coef_h[k] >= 0.0) || !(coef_h[k] < INFINITY) || (k > 0 && coef_h[k] > coef_h[k - 1])) { mono = 0; break; }
     if (smem > 200 * 1024) return fail(c, ESPER_E_ARG, "n_eps=%d too large for the sweep kernel", n_eps);
     if (!c->attr_sweep) {
         ESPER_CUDA(c, cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

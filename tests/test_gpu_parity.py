@@ -172,6 +172,90 @@ def test_eps_sweep_nonsymmetric_input(ctx):
         ctx.dmap_embed(D, 0.3, k=4)                                           # the eigensolver needs symmetry
 
 
+# Kernels written after the round's GPU budget was spent have never run on hardware: their tests are opt-in
+# (ESPER_TEST_EXPERIMENTAL=1) until a GPU session has seen them pass, so that the default suite only holds verified code.
+experimental = pytest.mark.skipif(os.environ.get('ESPER_TEST_EXPERIMENTAL', '0') == '0',
+                                  reason='not yet run on hardware; set ESPER_TEST_EXPERIMENTAL=1')
+
+
+@experimental
+@pytest.mark.parametrize('name', ['stage123_small', 'stage123_pristine', 'stage23_medium', 'stage1_dupes'])
+def test_moment_sweep_vs_reference_golden(ctx, name):
+    """esper_sweep_config(1): the moment sweep against the reference run's logSumWij and against the general kernel."""
+    g = golden(name + '.npz')
+    D = g['D']
+    Lr = g['logSumWij'] if 'logSumWij' in g else O.eps_sweep_logsum(D, LOG_EPS)
+    L0 = GaussianBandwidth.sweep(D, LOG_EPS, ctx=ctx)
+    assert ctx.sweep_info()[0] == 0
+    ctx.sweep_config(1)
+    try:
+        L1 = GaussianBandwidth.sweep(D, LOG_EPS, ctx=ctx)
+        path, bins = ctx.sweep_info()
+    finally:
+        ctx.sweep_config(0)
+    assert path == 1 and 1 <= bins <= 32
+    assert np.array_equal(np.isfinite(L1), np.isfinite(Lr))
+    fin = np.isfinite(Lr)
+    assert np.max(np.abs(L1[fin] - Lr[fin])) < 1e-9
+    assert np.max(np.abs(L1[fin] - L0[fin])) < 1e-12
+
+
+@experimental
+def test_moment_sweep_nonsymmetric_thresholds_and_fallbacks(ctx):
+    rng = np.random.default_rng(5)
+    D = np.sqrt(1.9 + 0.1 * rng.random((300, 300)))                           # concentrated like a high-noise stack
+    np.fill_diagonal(D, 0.0)
+    D[3, 7] = 0.0                                                             # an off-diagonal zero, non-symmetric matrix
+    coef = 1. / (2. * np.exp(LOG_EPS))
+    ctx.sweep_config(1)
+    try:
+        for thr in (10.0, 3.0, 25.0):
+            L = ctx.eps_sweep(D, coef, thr)
+            assert ctx.sweep_info() == (1, 1)
+            ref = []
+            for c in coef:
+                t = c * (D * D)
+                ref.append(np.log(np.sum(np.exp(-t[t < thr]))))
+            assert np.allclose(L, ref, rtol=0, atol=1e-12), thr
+        # returns to the general kernel: spread of more than 32 bins, unsorted coefficients, no truncation
+        W = np.exp(rng.uniform(-12, 12, (120, 120)))
+        L = ctx.eps_sweep(W, coef, 10.0)
+        assert ctx.sweep_info()[0] == 0
+        ref = [np.log(np.sum(np.exp(-(c * W * W)[(c * W * W) < 10.0]))) for c in coef]
+        assert np.allclose(L, ref, rtol=0, atol=1e-12)
+        ctx.eps_sweep(D, coef[::-1].copy(), 10.0)
+        assert ctx.sweep_info()[0] == 0
+        ctx.eps_sweep(D, coef, np.inf)
+        assert ctx.sweep_info()[0] == 0
+        with pytest.raises(ValueError):
+            ctx.sweep_config(5)
+    finally:
+        ctx.sweep_config(0)
+
+
+@experimental
+def test_moment_sweep_full_size(ctx):
+    """BASELINE config 2 shape: D^2 spans 5 %, one bin; both kernels on the same resident matrix."""
+    rng = np.random.default_rng(11)
+    X = rng.standard_normal((2000, 8192))
+    G = X @ X.T
+    nrm = np.diag(G)
+    D = np.sqrt(np.maximum(nrm[:, None] + nrm[None, :] - 2 * G, 0) / 8192) * (1.38 / np.sqrt(2))
+    D = 0.5 * (D + D.T)
+    np.fill_diagonal(D, 0.0)
+    coef = 1. / (2. * np.exp(LOG_EPS))
+    L0 = ctx.eps_sweep(D, coef, 10.0)
+    ctx.sweep_config(1)
+    try:
+        L1 = ctx.eps_sweep(None, coef, 10.0, m=2000)
+        path, bins = ctx.sweep_info()
+    finally:
+        ctx.sweep_config(0)
+    assert path == 1 and bins <= 2
+    assert np.max(np.abs(L1 - L0)) < 1e-12
+    assert np.max(np.abs(L1 - O.eps_sweep_logsum(D, LOG_EPS, sequential=False))) < 1e-10
+
+
 # ---- stage 3 ----------------------------------------------------------------------------------
 @pytest.mark.parametrize('name', ['stage123_pristine', 'stage23_medium'])
 def test_markov_matrix_vs_oracle(ctx, name):
