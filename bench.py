@@ -222,6 +222,10 @@ def run_ours(args):
     for i, c in enumerate(ctxs):
         c.upload_images(pinned[i % n_stacks].numpy())
         c.dmap_config(args.eig_mode if args.eig_mode >= 0 else (1 if NF > 1 else 0))
+        if args.gram_f16:
+            c.gram_config(1)               # experimental 3xFP16 operand planes (off by default)
+        if args.sweep_moments:
+            c.sweep_config(1)              # experimental moment sweep (off by default)
         c.sync()
     iters_used = []
 
@@ -336,6 +340,13 @@ def run_ours(args):
     if not bf16_sus:
         bf16_sus, peak_src = 1400.0, 'fallback (B200_PROFILING.md sustained 1.4 PFLOP/s bf16 / 2)'
     tf32_peak = bf16_sus / 2.0
+    gram_kernel_name = 'gram_wide_kernel (tcgen05 kind::tf32, 3xTF32, 128x256 tiles on the upper triangle)'
+    gram_peak = tf32_peak
+    if args.gram_f16:
+        gram_kernel_name = 'gram_wide_kernel<F16> (tcgen05 kind::f16, 3xFP16 split of the same 22 bits, 128x256 tiles on the upper triangle)'
+        gram_peak = bf16_sus
+        peak_src = peak_src.replace(' / 2: dense TF32 is half the bf16 rate on tcgen05', ': kind::f16 runs at the bf16 rate')
+    tf32_peak = gram_peak
     gram_ms = kern['gram'][0] / max(kern['gram'][1], 1)
     alg_flops = 2.0 * N_IMG * N_IMG * P                           # GEMM convention, SURVEY 8(d)
     n_tiles = (N_IMG + 127) // 128
@@ -354,12 +365,13 @@ def run_ours(args):
     pds = world * args.steps
     line = {
         'metric': METRIC, 'value': pds / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32x3+f64',
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16x3+f64' if args.gram_f16 else 'tf32x3+f64',
         'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'pd_per_rank_per_step': 1, 'sharding': 'independent PDs per rank, no data-path collective',
                    'pipelining': '%d PDs in flight per GPU (one host thread / ctx / stream each)' % NF, 'serial_ms_per_step': ms_serial / args.steps,
                    'l2': 'inputs larger than L2 (500 MB stack per PD, two alternating stacks per rank)',
-                   'lanczos_steps': iters_used[-1] if iters_used else None, 'numa_bind_rank0': numa},
+                   'lanczos_steps': iters_used[-1] if iters_used else None, 'numa_bind_rank0': numa,
+                   'experimental': {'gram_f16': bool(args.gram_f16), 'sweep_moments': bool(args.sweep_moments)}},
         'e2e': {'value': pds / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(N_IMG * P * 4),
                 'd2h_bytes_per_step': int(N_IMG * N_IMG * 8 + len(LOG_EPS) * 8 + K_EIG * 8 + N_IMG * K_EIG * 8),
                 'ms_per_step': ms_e2e / args.steps, 'h2d_probe_gbs': round(h2d_gbs, 2),
@@ -367,7 +379,7 @@ def run_ours(args):
                 'note': 'bounded by the host->device copy of the 500 MB stack (probe: bare pinned cudaMemcpyAsync rate on this box)'},
         'gpu_launches': launches,
         'clocks': clocks,
-        'roofline': {'bound': 'tensor', 'kernel': 'gram_wide_kernel (tcgen05 kind::tf32, 3xTF32, 128x256 tiles on the upper triangle)',
+        'roofline': {'bound': 'tensor', 'kernel': gram_kernel_name,
                      'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': achieved / tf32_peak if tf32_peak else None,
                      'traffic': traffic, 'peak_source': peak_src, 'flops_per_launch': alg_flops,
                      'flops_convention': '2*N^2*P (full GEMM); the kernel issues 3 TF32 MMAs per product on 72 tiles of 128x256 covering the upper triangle',
@@ -406,6 +418,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-numa-bind', action='store_true', help='do not restrict ranks to the CPUs of their GPU\'s NUMA node')
     ap.add_argument('--eig-mode', type=int, default=-1, help='esper_dmap_config mode (-1 = throughput when several PDs are in flight)')
+    ap.add_argument('--gram-f16', action='store_true', help='experimental: 3xFP16 operand planes for the Gram kernel (esper_gram_config 1)')
+    ap.add_argument('--sweep-moments', action='store_true', help='experimental: moment sweep (esper_sweep_config 1)')
     ap.add_argument('--inflight', type=int, default=4, help='PDs in flight per GPU (host threads / ctxs / streams)')
     args = ap.parse_args()
     if args.impl == 'reference':

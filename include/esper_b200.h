@@ -86,6 +86,15 @@ int esper_upload_images(esper_ctx* ctx, const float* imgs, int n, int P);
  * units fill the SMs); refine_tau (0.05: pairs with D^2*P < 0.05(|x|^2+|y|^2), i.e. near-duplicate images, where
  * Gram cancellation would exceed 1e-5; calibrated with tools/calib_gram_error.py). */
 int esper_dist_config(esper_ctx* ctx, int split_k, double refine_tau);
+/* Operand format of the stage-1 tensor-core contraction.  mode 0 (default): 3xTF32 -- every centred z-score c is split into
+ * two TF32 values, hi*hi + hi*lo + lo*hi accumulate in FP32.  mode 1: 3xFP16 -- the same split into two FP16 values of
+ * c * 2^s (an FP16 significand has the same 11 bits as a TF32 one; s is chosen from P so that |c| <= 2 sqrt(P) stays in
+ * range), tcgen05 kind::f16 at twice the TF32 rate with half the operand bytes; used for esper_dist_rms with
+ * ESPER_DIST_STANDARDIZE on stacks of more than 128 images, the 3xTF32 path otherwise (unstandardised input, PCA, CTF
+ * branch, row blocks).  Experimental this round: ESPER_GRAM_F16=1 sets the initial mode of new contexts.
+ * esper_gram_info: operand format the last esper_dist_rms used (0 TF32, 1 FP16). */
+int esper_gram_config(esper_ctx* ctx, int mode);
+int esper_gram_info(esper_ctx* ctx, int* last_operands);
 /* Upload a distance matrix so that stages 2/3 can use it as the resident D. */
 int esper_upload_dist(esper_ctx* ctx, const double* D, int m);
 

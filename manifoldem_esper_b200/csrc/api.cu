@@ -46,6 +46,7 @@ esper_ctx* esper_create(int device, void* stream) {
     esper_ctx* c = new esper_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    if (const char* ev = getenv("ESPER_GRAM_F16")) c->gram_mode = (atoi(ev) != 0) ? 1 : 0;           // experimental, see esper_gram_config
     if (const char* ev = getenv("ESPER_SWEEP_MOMENTS")) c->sweep_mode = (atoi(ev) != 0) ? 1 : 0;   // experimental, see esper_sweep_config
     if (stream) {
         c->stream = reinterpret_cast<cudaStream_t>(stream);
@@ -155,6 +156,19 @@ int esper_dist_config(esper_ctx* c, int split_k, double refine_tau) {
     return ESPER_OK;
 }
 
+int esper_gram_config(esper_ctx* c, int mode) {
+    ESPER_ENTER(c);
+    if (mode != 0 && mode != 1) return fail(c, ESPER_E_ARG, "gram_config: mode must be 0 (3xTF32) or 1 (3xFP16)");
+    c->gram_mode = mode;
+    return ESPER_OK;
+}
+
+int esper_gram_info(esper_ctx* c, int* last_operands) {
+    ESPER_ENTER(c);
+    if (last_operands) *last_operands = c->gram_last_f16;
+    return ESPER_OK;
+}
+
 int esper_dist_rms(esper_ctx* c, const float* imgs, int n, int P, unsigned flags, double* D) {
     ESPER_ENTER(c);
     if (n < 1 || P < 1) return fail(c, ESPER_E_ARG, "dist_rms: need n >= 1 and P >= 1 (got n=%d, P=%d)", n, P);
@@ -166,13 +180,18 @@ int esper_dist_rms(esper_ctx* c, const float* imgs, int n, int P, unsigned flags
                     n, P, c->img_n, c->img_P);
     }
     const int rows_pad = (int)round_up((size_t)n, 128);
-    const int ld = (int)round_up((size_t)P, 32);
+    // operand planes: TF32 pairs (default) or, opted in through esper_gram_config, FP16 pairs for z-scored stacks of at least
+    // two 128-row tiles (the bound on |c| that makes FP16's range sufficient needs the standardisation)
+    int hs = -1;
+    if (c->gram_mode == 1 && (flags & ESPER_DIST_STANDARDIZE) && rows_pad >= 256) hs = gram_f16_scale_log2(P);
+    const int ld = (int)round_up((size_t)P, hs >= 0 ? 64 : 32);
     ESPER_RESERVE(c, c->dist, sizeof(double) * (size_t)n * n);
     c->dist_m = 0;
-    int rc = run_prep(c, n, P, flags, rows_pad, ld);
+    int rc = run_prep(c, n, P, flags, rows_pad, ld, false, hs);
     if (rc) return rc;
-    rc = run_gram(c, n, P, rows_pad, ld, flags);
+    rc = run_gram(c, n, P, rows_pad, ld, flags, -1, 0, nullptr, hs);
     if (rc) return rc;
+    c->gram_last_f16 = hs >= 0 ? 1 : 0;
     c->dist_m = n; c->dist_rows = 0; c->dist_row0 = -1;
     c->dist_symmetric = 1;                  // mirrored writes: symmetric by construction
     if (D) {

@@ -76,6 +76,7 @@ struct esper_ctx {
     int split_k = 0;
     int drain_kb = 2;                                          // k-blocks (of 32 pixels) per tensor-core accumulation chain
     double refine_tau = 0.05;
+    int gram_mode = 0, gram_last_f16 = 0;                      // esper_gram_config: 0 = 3xTF32 operand planes, 1 = 3xFP16 (opt-in)
 
     // resident data
     esper::DevBuf imgs;     int img_n = 0, img_P = 0;          // raw float32 stack [n, P]
@@ -167,8 +168,10 @@ inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 struct RowStat;
 // ---- per-stage entry points implemented in the .cu files (host side) ----
 int prep_and_gram(esper_ctx* c, int n, int P, unsigned flags);                 // k0_prep.cu + k1_gram.cu
-int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld, bool exact_center = false);
-int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, int row0 = -1, int nrows = 0, double* gram_out = nullptr);
+int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld, bool exact_center = false, int half_scale_log2 = -1);
+int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, int row0 = -1, int nrows = 0, double* gram_out = nullptr,
+             int half_scale_log2 = -1);
+int gram_f16_scale_log2(int P);
 int run_sweep(esper_ctx* c, int m, const double* coef_h, int n_eps, double thr, double* logsum_h);
 int run_sweep_rows(esper_ctx* c, int rows, int m, const double* coef_h, int n_eps, double thr, double* out_h, int take_log);
 int run_markov_rows(esper_ctx* c, int rows, int m, int row0, double eps, const double* degree_all_h, double* degree_rows_h, int phase);

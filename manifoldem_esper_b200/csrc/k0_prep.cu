@@ -9,6 +9,7 @@
 //                               c = fl32(z - xbar); hi = tf32(c); lo = tf32(c - hi); |c|^2 in FP64
 //
 // Algorithmic bytes per PD (n images, P pixels): read 4nP once from HBM (+4nP from L2), write 8nP.
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "devutil.cuh"
 
@@ -94,16 +95,19 @@ __device__ __forceinline__ float tf32_rna(float x) {
     return __uint_as_float(r);
 }
 
-// One block per image: write the hi / lo TF32 planes (row stride ld, zero padded) and |c|^2.
+// One block per image: write the hi / lo operand planes (row stride ld elements, zero padded) and |c|^2.
+//   HALF = false: TF32 values in float32 storage (3xTF32 Gram, tcgen05 kind::tf32)
+//   HALF = true : FP16 values, c scaled by the exact power of two `scale` first (3xFP16 Gram, kind::f16, opt-in).  An FP16
+//                 significand has the 11 bits of a TF32 one, so hi + lo carries the same 22 bits; the scale keeps lo out
+//                 of the FP16 subnormal range, |c| <= 2 sqrt(P) for z-scores bounds the top (host: gram_f16_scale_log2).
+template <bool HALF>
 __global__ void __launch_bounds__(512) stats_split_kernel(const float* __restrict__ raw, int n, int P, int ld,
                                                           int standardize, RowStat* __restrict__ st,
-                                                          const float* __restrict__ xbar, int center,
-                                                          float* __restrict__ hi, float* __restrict__ lo) {
+                                                          const float* __restrict__ xbar, int center, float scale,
+                                                          void* __restrict__ hi_v, void* __restrict__ lo_v) {
     __shared__ double sh[32];
     int i = blockIdx.x;
     const float* row = raw + (size_t)i * P;
-    float4* hrow = reinterpret_cast<float4*>(hi + (size_t)i * ld);
-    float4* lrow = reinterpret_cast<float4*>(lo + (size_t)i * ld);
     float m = 0.f, sd = 1.f;
     if (standardize) row_stats(row, P, sh, m, sd);
     const bool vec = ((P & 3) == 0);
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(512) stats_split_kernel(const float* __restric
 #pragma unroll
             for (int e = 0; e < 4; ++e) v[e] = (p0 + e < P) ? __ldg(row + p0 + e) : 0.f;
         }
-        float h[4], l[4];
+        float cv[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             float c = 0.f;
@@ -127,12 +131,34 @@ __global__ void __launch_bounds__(512) stats_split_kernel(const float* __restric
                 c = zscore(v[e], m, sd);
                 if (center) c = __fsub_rn(c, __ldg(xbar + p0 + e));
             }
-            h[e] = tf32_rna(c);
-            l[e] = tf32_rna(__fsub_rn(c, h[e]));
+            cv[e] = c;
             acc += (double)c * (double)c;
         }
-        hrow[q] = make_float4(h[0], h[1], h[2], h[3]);
-        lrow[q] = make_float4(l[0], l[1], l[2], l[3]);
+        if (!HALF) {
+            float h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                h[e] = tf32_rna(cv[e]);
+                l[e] = tf32_rna(__fsub_rn(cv[e], h[e]));
+            }
+            reinterpret_cast<float4*>(reinterpret_cast<float*>(hi_v) + (size_t)i * ld)[q] = make_float4(h[0], h[1], h[2], h[3]);
+            reinterpret_cast<float4*>(reinterpret_cast<float*>(lo_v) + (size_t)i * ld)[q] = make_float4(l[0], l[1], l[2], l[3]);
+        } else {
+            __half h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float cs = __fmul_rn(cv[e], scale);             // exact: scale is a power of two
+                h[e] = __float2half_rn(cs);
+                l[e] = __float2half_rn(__fsub_rn(cs, __half2float(h[e])));
+            }
+            uint2 hv, lv;
+            hv.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+            hv.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+            lv.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
+            lv.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+            reinterpret_cast<uint2*>(reinterpret_cast<__half*>(hi_v) + (size_t)i * ld)[q] = hv;
+            reinterpret_cast<uint2*>(reinterpret_cast<__half*>(lo_v) + (size_t)i * ld)[q] = lv;
+        }
     }
     acc = block_sum(acc, sh);
     if (threadIdx.x == 0) { st[i].mean = m; st[i].stdv = sd; st[i].norm2 = acc; }
@@ -260,11 +286,15 @@ int row_stats_numpy(esper_ctx* c, int n, int P, RowStat* st) {
     return ESPER_OK;
 }
 
-int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld, bool exact_center) {
+// half_scale_log2 < 0: TF32 planes (float32 storage, ld a multiple of 32); >= 0: FP16 planes scaled by 2^half_scale_log2
+// (ld a multiple of 64).
+int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld, bool exact_center, int half_scale_log2) {
     const float* raw = c->imgs.as<float>();
     ESPER_RESERVE(c, c->row_stats, sizeof(RowStat) * (size_t)rows_pad);
-    ESPER_RESERVE(c, c->plane_hi, sizeof(float) * (size_t)rows_pad * ld);
-    ESPER_RESERVE(c, c->plane_lo, sizeof(float) * (size_t)rows_pad * ld);
+    const bool half = half_scale_log2 >= 0;
+    const size_t esz = half ? sizeof(__half) : sizeof(float);
+    ESPER_RESERVE(c, c->plane_hi, esz * (size_t)rows_pad * ld);
+    ESPER_RESERVE(c, c->plane_lo, esz * (size_t)rows_pad * ld);
     RowStat* st = c->row_stats.as<RowStat>();
     const int standardize = (flags & ESPER_DIST_STANDARDIZE) ? 1 : 0;
     const int center = (flags & ESPER_DIST_CENTER) ? 1 : 0;
@@ -293,15 +323,17 @@ int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld, b
         }
     }
     if (rows_pad > n) {
-        ESPER_CUDA(c, cudaMemsetAsync(c->plane_hi.as<float>() + (size_t)n * ld, 0,
-                                      sizeof(float) * (size_t)(rows_pad - n) * ld, c->stream));
-        ESPER_CUDA(c, cudaMemsetAsync(c->plane_lo.as<float>() + (size_t)n * ld, 0,
-                                      sizeof(float) * (size_t)(rows_pad - n) * ld, c->stream));
+        ESPER_CUDA(c, cudaMemsetAsync(c->plane_hi.as<char>() + esz * (size_t)n * ld, 0, esz * (size_t)(rows_pad - n) * ld, c->stream));
+        ESPER_CUDA(c, cudaMemsetAsync(c->plane_lo.as<char>() + esz * (size_t)n * ld, 0, esz * (size_t)(rows_pad - n) * ld, c->stream));
     }
     {
         LaunchScope ls(c, "prep");
-        stats_split_kernel<<<n, 512, 0, c->stream>>>(raw, n, P, ld, standardize, st, xbar, center,
-                                                     c->plane_hi.as<float>(), c->plane_lo.as<float>());
+        if (half)
+            stats_split_kernel<true><<<n, 512, 0, c->stream>>>(raw, n, P, ld, standardize, st, xbar, center,
+                                                               ldexpf(1.0f, half_scale_log2), c->plane_hi.p, c->plane_lo.p);
+        else
+            stats_split_kernel<false><<<n, 512, 0, c->stream>>>(raw, n, P, ld, standardize, st, xbar, center, 1.0f,
+                                                                c->plane_hi.p, c->plane_lo.p);
     }
     ESPER_CUDA(c, cudaGetLastError());
     return ESPER_OK;

@@ -198,7 +198,27 @@ __device__ __forceinline__ void umma_tf32_w(uint32_t tmem_d, uint64_t adesc, uin
         "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC_W), "r"(accumulate)
         : "memory");
 }
+// 3xFP16 variant (opt-in, esper_gram_config(ctx, 1) / ESPER_GRAM_F16=1): operands are FP16 hi/lo planes (same 11-bit
+// significands as TF32, see stats_split_kernel<true>), D = F32, A = B = F16 (format 0), K = 16 per instruction: the same
+// 32 bytes per operand row per MMA as kind::tf32, so descriptors, swizzle and the k-step offsets are unchanged while a
+// 128-byte row now holds 64 pixels -- half the MMA issue slots and half the operand bytes per pixel.
+constexpr uint32_t IDESC_WH = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN_W >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr int BK_H = 64;                    // FP16 elements per 128-byte swizzle row
+__device__ __forceinline__ void umma_f16_w(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC_WH), "r"(accumulate)
+        : "memory");
+}
+template <bool F16>
+__device__ __forceinline__ void umma_w(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    if (F16) umma_f16_w(tmem_d, adesc, bdesc, accumulate); else umma_tf32_w(tmem_d, adesc, bdesc, accumulate);
+}
 
+template <bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gram_wide_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                  const __grid_constant__ CUtensorMap mapw_hi, const __grid_constant__ CUtensorMap mapw_lo,
@@ -216,6 +236,7 @@ gram_wide_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int total_units = n_tiles * split_k;
+    constexpr int BKE = F16 ? BK_H : BK;                                // elements per k-block (one 128-byte row)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_hi); tma_prefetch_desc(&map_lo); tma_prefetch_desc(&mapw_hi); tma_prefetch_desc(&mapw_lo);
@@ -245,10 +266,10 @@ gram_wide_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
                     const uint32_t sa = base + stage * STAGE_W_BYTES;
                     const uint32_t fb = full_bar + 8 * stage;
                     mbar_expect_tx(fb, STAGE_W_BYTES);
-                    tma_load_2d(sa, &map_hi, fb, kb * BK, ti * BM);
-                    tma_load_2d(sa + TILE_BYTES, &map_lo, fb, kb * BK, ti * BM);
-                    tma_load_2d(sa + 2 * TILE_BYTES, &mapw_hi, fb, kb * BK, tc * BN_W);
-                    tma_load_2d(sa + 4 * TILE_BYTES, &mapw_lo, fb, kb * BK, tc * BN_W);
+                    tma_load_2d(sa, &map_hi, fb, kb * BKE, ti * BM);
+                    tma_load_2d(sa + TILE_BYTES, &map_lo, fb, kb * BKE, ti * BM);
+                    tma_load_2d(sa + 2 * TILE_BYTES, &mapw_hi, fb, kb * BKE, tc * BN_W);
+                    tma_load_2d(sa + 4 * TILE_BYTES, &mapw_lo, fb, kb * BKE, tc * BN_W);
                 }
                 __syncwarp();
                 if (++stage == STAGES_W) { stage = 0; phase ^= 1; }
@@ -275,9 +296,9 @@ gram_wide_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
 #pragma unroll
                         for (int k = 0; k < BK / UK; ++k) {
                             const uint64_t off = (uint64_t)((k * UK * 4) >> 4);
-                            umma_tf32_w(tmem_d, dal0 + off, dbh0 + off, (kb > g0 || k > 0) ? 1u : 0u);
-                            umma_tf32_w(tmem_d, dah0 + off, dbl0 + off, 1);
-                            umma_tf32_w(tmem_d, dah0 + off, dbh0 + off, 1);
+                            umma_w<F16>(tmem_d, dal0 + off, dbh0 + off, (kb > g0 || k > 0) ? 1u : 0u);
+                            umma_w<F16>(tmem_d, dah0 + off, dbl0 + off, 1);
+                            umma_w<F16>(tmem_d, dah0 + off, dbh0 + off, 1);
                         }
                         umma_commit(empty_bar + 8 * stage);
                         if (kb == g1 - 1) umma_commit(tfull_bar + 8 * acc);
@@ -509,7 +530,8 @@ gram_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 dist_finalize_kernel(const float* __restrict__ part, int nt, int n_tiles, int tile0, int rect_ti0, int split_k, int n, int P,
-                     const RowStat* __restrict__ st, double* __restrict__ D) {
+                     const RowStat* __restrict__ st, double gscale /*exact power of two; 1 unless the operands were scaled*/,
+                     double* __restrict__ D) {
     const int lt = blockIdx.x;
     const int e_per = (BM * (BN / 4)) / gridDim.y;          // slice of the tile handled by this block
     int ti, tj; bool transposed; tile_map(tile0 + lt, nt, rect_ti0, ti, tj, transposed);
@@ -534,7 +556,7 @@ dist_finalize_kernel(const float* __restrict__ part, int nt, int n_tiles, int ti
             const int j = tj * BN + c;
             if (j >= n) continue;
             if (diag && c <= r) { if (c == r) D[((size_t)i - row_off) * n + i] = 0.0; continue; }
-            double d2 = (ni + st[j].norm2 - 2.0 * g[q]) * invP;
+            double d2 = (ni + st[j].norm2 - 2.0 * (g[q] * gscale)) * invP;
             d2 = d2 > 0.0 ? d2 : 0.0;
             const double d = sqrt(d2);
             if (!rect || diag) {                    // both (i, j) and (j, i) live in this D
@@ -690,6 +712,30 @@ static int make_plane_map(esper_ctx* c, CUtensorMap* map, float* plane, int rows
     return ESPER_OK;
 }
 
+static int make_plane_map_h(esper_ctx* c, CUtensorMap* map, void* plane, int rows_pad, int ldh, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(c, ESPER_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[2] = {(cuuint64_t)ldh, (cuuint64_t)rows_pad};
+    cuuint64_t gstride[1] = {(cuuint64_t)ldh * 2};
+    cuuint32_t box[2] = {(cuuint32_t)gram::BK_H, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, plane, gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(c, ESPER_E_CUDA, "cuTensorMapEncodeTiled (FP16 planes) failed (%d)", (int)r);
+    return ESPER_OK;
+}
+
+// Power-of-two scale of the FP16 operand planes for z-scored images of P pixels: |c| <= 2 sqrt(P) (a z-score is at most
+// sqrt(P - 1), so is the common image subtracted from it), scaled values stay below 2^15 < 65504, and the lo parts of
+// all but the smallest pixels leave the FP16 subnormal range.  -1: P too large for the FP16 path.
+int gram_f16_scale_log2(int P) {
+    const double top = 2.0 * sqrt((double)P);
+    int s = (int)floor(log2(32768.0 / top));
+    if (s < 0) return -1;
+    return s > 8 ? 8 : s;
+}
+
 // Choose the number of K chunks: chains of <= ~2048 pixels, and a unit count that fills the SMs.
 static int choose_split_k(int requested, int nkb, int n_tiles, int sms) {
     if (requested > 0) return requested < nkb ? requested : nkb;
@@ -760,7 +806,8 @@ int run_product(esper_ctx* c, float* a_hi, float* a_lo, int na, float* b_hi, flo
     return ESPER_OK;
 }
 
-int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, int row0, int nrows, double* gram_out) {
+int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, int row0, int nrows, double* gram_out,
+             int half_scale_log2) {
     using namespace gram;
     // row0 < 0: full symmetric matrix (upper triangle of tiles); else the row block [row0, row0+nrows) x [0, n)
     const int nt = rows_pad / BM;
@@ -768,15 +815,19 @@ int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, i
     const int rect_ti0 = rect ? row0 / BM : -1;
     const int tiles_total = rect ? ceil_div(nrows, BM) * nt : nt * (nt + 1) / 2;
     if (!rect) { row0 = 0; nrows = n; }
-    const int nkb = ld / BK;
+    const bool f16 = half_scale_log2 >= 0;            // FP16 planes (ld a multiple of 64 halves), see run_prep
+    const int nkb = f16 ? ld / BK_H : ld / BK;
     const int sms = c->sm_count;
     const RowStat* st = c->row_stats.as<RowStat>();
     double* D = c->dist.as<double>();
+    const double gscale = f16 ? ldexp(1.0, -2 * half_scale_log2) : 1.0;
+    if (f16 && (rect || gram_out || nt < 2))
+        return fail(c, ESPER_E_STATE, "gram: the FP16 operand path covers the full symmetric distance matrix only");
 
     CUtensorMap map_hi, map_lo;
-    int rc = make_plane_map(c, &map_hi, c->plane_hi.as<float>(), rows_pad, ld);
+    int rc = f16 ? make_plane_map_h(c, &map_hi, c->plane_hi.p, rows_pad, ld, BM) : make_plane_map(c, &map_hi, c->plane_hi.as<float>(), rows_pad, ld);
     if (rc) return rc;
-    rc = make_plane_map(c, &map_lo, c->plane_lo.as<float>(), rows_pad, ld);
+    rc = f16 ? make_plane_map_h(c, &map_lo, c->plane_lo.p, rows_pad, ld, BM) : make_plane_map(c, &map_lo, c->plane_lo.as<float>(), rows_pad, ld);
     if (rc) return rc;
 
     if (!c->attr_gram) {
@@ -789,16 +840,23 @@ int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, i
     // 128x256 tiles for the full symmetric matrix (gram_wide_kernel): same bits as the 128x128 kernel, 12 % faster at the
     // benchmark shape.  ESPER_GRAM_WIDE=0 selects the 128x128 kernel (which the row-block and CTF products always use).
     const char* wide_env = getenv("ESPER_GRAM_WIDE");
-    const bool wide = !rect && nt >= 2 && !(wide_env && atoi(wide_env) == 0) && drain_kb > 0;
+    const bool wide = f16 || (!rect && nt >= 2 && !(wide_env && atoi(wide_env) == 0) && drain_kb > 0);
+    if (f16 && drain_kb < 1) drain_kb = 2;
 
     // Bound the split-K workspace: process the triangle in batches of tiles.
     const size_t ws_cap = (size_t)3 << 30;   // 3 GiB
     if (wide) {
         CUtensorMap mapw_hi, mapw_lo;
-        if ((rc = make_plane_map(c, &mapw_hi, c->plane_hi.as<float>(), rows_pad, ld, BN_W))) return rc;
-        if ((rc = make_plane_map(c, &mapw_lo, c->plane_lo.as<float>(), rows_pad, ld, BN_W))) return rc;
+        if (f16) {
+            if ((rc = make_plane_map_h(c, &mapw_hi, c->plane_hi.p, rows_pad, ld, BN_W))) return rc;
+            if ((rc = make_plane_map_h(c, &mapw_lo, c->plane_lo.p, rows_pad, ld, BN_W))) return rc;
+        } else {
+            if ((rc = make_plane_map(c, &mapw_hi, c->plane_hi.as<float>(), rows_pad, ld, BN_W))) return rc;
+            if ((rc = make_plane_map(c, &mapw_lo, c->plane_lo.as<float>(), rows_pad, ld, BN_W))) return rc;
+        }
         if (!c->attr_gram_wide) {
-            ESPER_CUDA(c, cudaFuncSetAttribute(gram_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_W_BYTES));
+            ESPER_CUDA(c, cudaFuncSetAttribute(gram_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_W_BYTES));
+            ESPER_CUDA(c, cudaFuncSetAttribute(gram_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_W_BYTES));
             c->attr_gram_wide = true;
         }
         const int n_wide = wide_tile_count(nt);
@@ -818,13 +876,17 @@ int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, i
             const int units = nb * sk;
             {
                 LaunchScope ls(c, "gram");
-                gram_wide_kernel<<<units < sms ? units : sms, NUM_THREADS, SMEM_W_BYTES, c->stream>>>(map_hi, map_lo, mapw_hi, mapw_lo, nt, nb, tile0,
-                                                                                                    nkb, sk, drain_kb, part);
+                if (f16)
+                    gram_wide_kernel<true><<<units < sms ? units : sms, NUM_THREADS, SMEM_W_BYTES, c->stream>>>(map_hi, map_lo, mapw_hi, mapw_lo, nt, nb,
+                                                                                                              tile0, nkb, sk, drain_kb, part);
+                else
+                    gram_wide_kernel<false><<<units < sms ? units : sms, NUM_THREADS, SMEM_W_BYTES, c->stream>>>(map_hi, map_lo, mapw_hi, mapw_lo, nt, nb,
+                                                                                                               tile0, nkb, sk, drain_kb, part);
             }
             {
                 LaunchScope ls(c, "dist_finalize");
                 if (gram_out) gram_finalize_kernel<<<dim3(2 * nb, 8), 256, 0, c->stream>>>(part, nt, 2 * nb, 2 * tile0, WIDE_TRI, sk, n, st, gram_out);
-                else dist_finalize_kernel<<<dim3(2 * nb, 8), 256, 0, c->stream>>>(part, nt, 2 * nb, 2 * tile0, WIDE_TRI, sk, n, P, st, D);
+                else dist_finalize_kernel<<<dim3(2 * nb, 8), 256, 0, c->stream>>>(part, nt, 2 * nb, 2 * tile0, WIDE_TRI, sk, n, P, st, gscale, D);
             }
         }
         ESPER_CUDA(c, cudaGetLastError());
@@ -852,7 +914,7 @@ int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, i
         {
             LaunchScope ls(c, "dist_finalize");
             if (gram_out) gram_finalize_kernel<<<dim3(nb, 8), 256, 0, c->stream>>>(part, nt, nb, tile0, -1, sk, n, st, gram_out);
-            else dist_finalize_kernel<<<dim3(nb, 8), 256, 0, c->stream>>>(part, nt, nb, tile0, rect_ti0, sk, n, P, st, D);
+            else dist_finalize_kernel<<<dim3(nb, 8), 256, 0, c->stream>>>(part, nt, nb, tile0, rect_ti0, sk, n, P, st, 1.0, D);
         }
     }
     ESPER_CUDA(c, cudaGetLastError());

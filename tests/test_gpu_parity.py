@@ -178,6 +178,86 @@ experimental = pytest.mark.skipif(os.environ.get('ESPER_TEST_EXPERIMENTAL', '0')
                                   reason='not yet run on hardware; set ESPER_TEST_EXPERIMENTAL=1')
 
 
+@pytest.fixture
+def f16_operands(ctx):
+    ctx.gram_config(1)
+    yield ctx
+    ctx.gram_config(0)
+
+
+@experimental
+@pytest.mark.parametrize('n,P', [(129, 1000), (257, 16), (300, 4096), (640, 16384), (700, 3000)])
+def test_f16_operands_tile_and_k_tails(f16_operands, n, P):
+    """esper_gram_config(1): 3xFP16 operand planes (kind::f16) against the float64 oracle and the 3xTF32 path."""
+    ctx = f16_operands
+    X = np.random.default_rng(n * 7 + P).standard_normal((n, P)).astype(np.float32)
+    D = ctx.dist_rms(X)
+    assert ctx.gram_info() == 1
+    Dr = O.distances_gram_f64(O.standardize_stack(X.reshape(n, 1, P)))
+    assert D.shape == (n, n) and d_err(D, Dr) < D_TOL
+    assert np.array_equal(D, D.T) and np.all(np.diag(D) == 0)
+    ctx.gram_config(0)
+    D0 = ctx.dist_rms(X)
+    assert ctx.gram_info() == 0 and d_err(D, D0) < 2e-6
+
+
+@experimental
+def test_f16_operands_fall_back_where_the_range_is_not_bounded(f16_operands):
+    ctx = f16_operands
+    X = np.random.default_rng(5).standard_normal((300, 999)).astype(np.float32) * 3e6 + 1
+    D = ctx.dist_rms(X, flags=_capi.DIST_CENTER)                             # no z-score: 3xTF32 planes
+    assert ctx.gram_info() == 0
+    Dr = O.distances_gram_f64(X.astype(np.float64).reshape(300, 1, 999))
+    assert d_err(D, Dr) < D_TOL
+    ctx.dist_rms(X[:100])                                                    # a single 128-row tile
+    assert ctx.gram_info() == 0
+    with pytest.raises(ValueError):
+        ctx.gram_config(3)
+
+
+@experimental
+def test_f16_operands_outlier_pixels(f16_operands):
+    """A hot pixel makes one z-score ~ sqrt(P): the largest value the FP16 planes must hold."""
+    ctx = f16_operands
+    X = np.random.default_rng(21).standard_normal((260, 4096)).astype(np.float32) * 1e-3
+    X[7, 100] = 5e4
+    X[9, 4000] = -7e4
+    D = ctx.dist_rms(X)
+    assert ctx.gram_info() == 1 and np.all(np.isfinite(D))
+    assert d_err(D, O.distances_gram_f64(O.standardize_stack(X.reshape(260, 1, 4096)))) < D_TOL
+
+
+@experimental
+def test_f16_operands_pristine_and_duplicates(f16_operands):
+    """Noise-free stack (Gram cancellation regime) with every image duplicated: exact zeros, refinement, symmetry."""
+    ctx = f16_operands
+    stack = synth.synthetic_pd(pd=4, box=250, n_side=14, tau=2, snr=None)
+    Dr = O.distances_direct(O.standardize_stack(stack))
+    D = ctx.dist_rms(stack)
+    assert ctx.gram_info() == 1
+    assert Dr[Dr > 0].min() < 0.1 and d_err(D, Dr) < D_TOL
+    assert np.array_equal(D, D.T)
+    n = D.shape[0]
+    assert np.all(D[np.arange(0, n, 2), np.arange(1, n, 2)] == 0)
+
+
+@experimental
+def test_f16_operands_full_size_pipeline(f16_operands):
+    """BASELINE config 2 with FP16 operand planes: distances, no accumulation bias, eigenvalues at fixed epsilon."""
+    ctx = f16_operands
+    stack = synth.synthetic_pd(pd=1, box=250, n_side=20, tau=5, snr=0.1)
+    Dr = O.distances_gram_f64(O.standardize_stack(stack))
+    D = ctx.dist_rms(stack)
+    assert ctx.gram_info() == 1 and d_err(D, Dr) < D_TOL
+    d2, d2r = D * D, Dr * Dr
+    off = ~np.eye(D.shape[0], dtype=bool)
+    assert abs(np.mean((d2 - d2r)[off] / d2r[off])) < 1e-7
+    eps = 0.2834
+    val_r, _ = O.dmap_embed(Dr, eps)
+    val, vec, _ = ctx.dmap_embed(None, eps, k=10, m=2000)
+    assert np.max(np.abs(val - val_r[:10]) / val_r[:10]) < VAL_TOL
+
+
 @experimental
 @pytest.mark.parametrize('name', ['stage123_small', 'stage123_pristine', 'stage23_medium', 'stage1_dupes'])
 def test_moment_sweep_vs_reference_golden(ctx, name):
