@@ -224,6 +224,8 @@ def run_ours(args):
         c.dmap_config(args.eig_mode if args.eig_mode >= 0 else (1 if NF > 1 else 0))
         if args.gram_f16:
             c.gram_config(1)               # experimental 3xFP16 operand planes (off by default)
+        if args.prep_cluster:
+            c.prep_config(1)               # experimental cluster standardise-and-split pass (off by default)
         if args.sweep_moments:
             c.sweep_config(1)              # experimental moment sweep (off by default)
         c.sync()
@@ -371,7 +373,7 @@ def run_ours(args):
                    'pipelining': '%d PDs in flight per GPU (one host thread / ctx / stream each)' % NF, 'serial_ms_per_step': ms_serial / args.steps,
                    'l2': 'inputs larger than L2 (500 MB stack per PD, two alternating stacks per rank)',
                    'lanczos_steps': iters_used[-1] if iters_used else None, 'numa_bind_rank0': numa,
-                   'experimental': {'gram_f16': bool(args.gram_f16), 'sweep_moments': bool(args.sweep_moments)}},
+                   'experimental': {'gram_f16': bool(args.gram_f16), 'sweep_moments': bool(args.sweep_moments), 'prep_cluster': bool(args.prep_cluster)}},
         'e2e': {'value': pds / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(N_IMG * P * 4),
                 'd2h_bytes_per_step': int(N_IMG * N_IMG * 8 + len(LOG_EPS) * 8 + K_EIG * 8 + N_IMG * K_EIG * 8),
                 'ms_per_step': ms_e2e / args.steps, 'h2d_probe_gbs': round(h2d_gbs, 2),
@@ -419,6 +421,7 @@ def main():
     ap.add_argument('--no-numa-bind', action='store_true', help='do not restrict ranks to the CPUs of their GPU\'s NUMA node')
     ap.add_argument('--eig-mode', type=int, default=-1, help='esper_dmap_config mode (-1 = throughput when several PDs are in flight)')
     ap.add_argument('--gram-f16', action='store_true', help='experimental: 3xFP16 operand planes for the Gram kernel (esper_gram_config 1)')
+    ap.add_argument('--prep-cluster', action='store_true', help='experimental: cluster standardise-and-split pass (esper_prep_config 1)')
     ap.add_argument('--sweep-moments', action='store_true', help='experimental: moment sweep (esper_sweep_config 1)')
     ap.add_argument('--inflight', type=int, default=4, help='PDs in flight per GPU (host threads / ctxs / streams)')
     args = ap.parse_args()

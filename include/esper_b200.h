@@ -95,6 +95,12 @@ int esper_dist_config(esper_ctx* ctx, int split_k, double refine_tau);
  * esper_gram_info: operand format the last esper_dist_rms used (0 TF32, 1 FP16). */
 int esper_gram_config(esper_ctx* ctx, int mode);
 int esper_gram_info(esper_ctx* ctx, int* last_operands);
+/* Standardise-and-split pass that writes the operand planes.  mode 0 (default): one CTA per image, the row is read twice
+ * (statistics, then split).  mode 1: a thread-block cluster per image keeps the row in (distributed) shared memory between
+ * the two sweeps, so the stack is read from HBM once.  Experimental this round: ESPER_PREP_CLUSTER=1 sets the initial mode.
+ * esper_prep_info: cluster size the last pass used (0 = mode-0 kernel, also when a row does not fit 8 x 64 kB). */
+int esper_prep_config(esper_ctx* ctx, int mode);
+int esper_prep_info(esper_ctx* ctx, int* last_cluster);
 /* Upload a distance matrix so that stages 2/3 can use it as the resident D. */
 int esper_upload_dist(esper_ctx* ctx, const double* D, int m);
 

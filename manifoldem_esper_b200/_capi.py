@@ -45,6 +45,8 @@ SIGNATURES = {
     'esper_eps_sweep': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
     'esper_markov': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     'esper_dmap_config': (C.c_int, [C.c_void_p, C.c_int]),
+    'esper_prep_config': (C.c_int, [C.c_void_p, C.c_int]),
+    'esper_prep_info': (C.c_int, [C.c_void_p, C.c_void_p]),
     'esper_gram_config': (C.c_int, [C.c_void_p, C.c_int]),
     'esper_gram_info': (C.c_int, [C.c_void_p, C.c_void_p]),
     'esper_sweep_config': (C.c_int, [C.c_void_p, C.c_int]),
@@ -202,6 +204,16 @@ class Context:
                 raise ValueError('dist_rms: out must be a C-contiguous float64 [n, n] array')
         self._check(self._lib.esper_dist_rms(self._h, _ptr(imgs), int(n), int(P), int(flags), _ptr(D)))
         return D
+
+    def prep_config(self, mode=0):
+        """0 = one CTA per image (row read twice), 1 = cluster per image (row kept in shared memory between the sweeps)."""
+        self._check(self._lib.esper_prep_config(self._h, int(mode)))
+
+    def prep_info(self):
+        """Cluster size the last standardise-and-split pass used (0 = the one-CTA-per-image kernel)."""
+        v = C.c_int(0)
+        self._check(self._lib.esper_prep_info(self._h, C.byref(v)))
+        return v.value
 
     def gram_config(self, mode=0):
         """0 = 3xTF32 operand planes (default), 1 = 3xFP16 (z-scored stacks of more than 128 images)."""

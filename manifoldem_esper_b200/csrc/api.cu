@@ -46,6 +46,7 @@ esper_ctx* esper_create(int device, void* stream) {
     esper_ctx* c = new esper_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    if (const char* ev = getenv("ESPER_PREP_CLUSTER")) c->prep_mode = (atoi(ev) != 0) ? 1 : 0;        // experimental, see esper_prep_config
     if (const char* ev = getenv("ESPER_GRAM_F16")) c->gram_mode = (atoi(ev) != 0) ? 1 : 0;           // experimental, see esper_gram_config
     if (const char* ev = getenv("ESPER_SWEEP_MOMENTS")) c->sweep_mode = (atoi(ev) != 0) ? 1 : 0;   // experimental, see esper_sweep_config
     if (stream) {
@@ -160,6 +161,19 @@ int esper_gram_config(esper_ctx* c, int mode) {
     ESPER_ENTER(c);
     if (mode != 0 && mode != 1) return fail(c, ESPER_E_ARG, "gram_config: mode must be 0 (3xTF32) or 1 (3xFP16)");
     c->gram_mode = mode;
+    return ESPER_OK;
+}
+
+int esper_prep_config(esper_ctx* c, int mode) {
+    ESPER_ENTER(c);
+    if (mode != 0 && mode != 1) return fail(c, ESPER_E_ARG, "prep_config: mode must be 0 (one CTA per image) or 1 (cluster per image)");
+    c->prep_mode = mode;
+    return ESPER_OK;
+}
+
+int esper_prep_info(esper_ctx* c, int* last_cluster) {
+    ESPER_ENTER(c);
+    if (last_cluster) *last_cluster = c->prep_last_cluster;
     return ESPER_OK;
 }
 

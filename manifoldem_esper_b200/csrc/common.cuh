@@ -76,6 +76,7 @@ struct esper_ctx {
     int split_k = 0;
     int drain_kb = 2;                                          // k-blocks (of 32 pixels) per tensor-core accumulation chain
     double refine_tau = 0.05;
+    int prep_mode = 0, prep_last_cluster = 0; bool attr_prep_cluster = false;   // esper_prep_config: 1 = cluster split kernel (opt-in)
     int gram_mode = 0, gram_last_f16 = 0;                      // esper_gram_config: 0 = 3xTF32 operand planes, 1 = 3xFP16 (opt-in)
 
     // resident data

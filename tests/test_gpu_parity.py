@@ -259,6 +259,29 @@ def test_f16_operands_full_size_pipeline(f16_operands):
 
 
 @experimental
+@pytest.mark.parametrize('f16', [0, 1])
+@pytest.mark.parametrize('n,P,cluster', [(70, 999, 1), (300, 16384, 1), (260, 20000, 2), (300, 62500, 4), (130, 250000, 0)])
+def test_cluster_prep_matches_the_one_cta_kernel(ctx, n, P, cluster, f16):
+    """esper_prep_config(1): the row stays in (distributed) shared memory between the statistics and the split sweep."""
+    X = (np.random.default_rng(n + P).standard_normal((n, P)) * 2.5 + 0.7).astype(np.float32)
+    ctx.gram_config(f16)
+    try:
+        D0 = ctx.dist_rms(X)
+        assert ctx.prep_info() == 0
+        ctx.prep_config(1)
+        D1 = ctx.dist_rms(X)
+        assert ctx.prep_info() == cluster
+        Du = ctx.dist_rms(X, flags=_capi.DIST_CENTER)                        # no standardisation: no statistics exchange
+    finally:
+        ctx.prep_config(0)
+        ctx.gram_config(0)
+    Du0 = ctx.dist_rms(X, flags=_capi.DIST_CENTER)
+    assert d_err(D1, D0) < 1e-6 and np.array_equal(D1, D1.T)                 # mean32 / std32 may differ in the last bit
+    assert d_err(Du, Du0) < 1e-6
+    assert d_err(D1, O.distances_gram_f64(O.standardize_stack(X.reshape(n, 1, P)))) < D_TOL
+
+
+@experimental
 @pytest.mark.parametrize('name', ['stage123_small', 'stage123_pristine', 'stage23_medium', 'stage1_dupes'])
 def test_moment_sweep_vs_reference_golden(ctx, name):
     """esper_sweep_config(1): the moment sweep against the reference run's logSumWij and against the general kernel."""

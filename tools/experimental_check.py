@@ -2,14 +2,15 @@
 """First hardware run of the kernels written after round 1's GPU budget was spent (never executed so far):
 
   * 3xFP16 operand planes for the Gram kernel     esper_gram_config(ctx, 1)    gram_wide_kernel<true>, stats_split_kernel<true>
+  * cluster standardise-and-split pass            esper_prep_config(ctx, 1)    stats_split_cluster_kernel<HALF>
   * moment sweep                                  esper_sweep_config(ctx, 1)   moment_{stats,plan,accum,final}_kernel
 
     gpurun --timeout 400 -- 'timeout 300 python tools/experimental_check.py [gram|sweep]'
 
 Every stage prints before the next starts (flush), small shapes first, so a hang or fault is attributable.  Then:
 
-    ESPER_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -q -k "f16_operands or moment_sweep"
-    python bench.py --gram-f16 --sweep-moments
+    ESPER_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -q -k "f16_operands or moment_sweep or cluster_prep"
+    python bench.py --gram-f16 --sweep-moments --prep-cluster
 
 When both are green and faster, make them the defaults (ctx->gram_mode / sweep_mode = 1 in esper_create), drop the
 `experimental` marker in tests/test_gpu_parity.py and re-capture profiles/ (launch list + ncu --set full of the Gram kernel).
@@ -75,6 +76,28 @@ if what in ('all', 'gram'):
                                                                    ctx.kernel_ms('gram')[0] / 5, ctx.kernel_ms('dist_finalize')[0] / 5), flush=True)
     ctx.set_profiling(False)
     ctx.gram_config(0)
+    print('== cluster standardise-and-split pass ==', flush=True)
+    for n, P in [(70, 999), (300, 16384), (2000, 62500)]:
+        Xc = X if n == 2000 else rng.standard_normal((n, P), dtype=np.float32)
+        ctx.prep_config(0)
+        D0 = ctx.dist_rms(Xc)
+        ctx.prep_config(1)
+        D1 = ctx.dist_rms(Xc)
+        good = rel(D1, D0) < 1e-6
+        ok &= good
+        print('n=%4d P=%5d  cluster size %d  |cluster - default| %.2e  %s' % (n, P, ctx.prep_info(), rel(D1, D0), 'ok' if good else 'FAILED'), flush=True)
+    ctx.set_profiling(True)
+    for gm in (0, 1):
+        for pm in (0, 1):
+            ctx.gram_config(gm); ctx.prep_config(pm)
+            ctx.dist_rms(X)
+            ctx.reset_profiling()
+            for _ in range(5):
+                ctx.dist_rms(None, n=2000, P=62500, download=False)
+            ctx.sync()
+            print('%s planes, %s prep: %.3f ms' % ('FP16' if gm else 'TF32', 'cluster' if pm else 'one-CTA', ctx.kernel_ms('prep')[0] / 5), flush=True)
+    ctx.set_profiling(False)
+    ctx.gram_config(0); ctx.prep_config(0)
 
 if what in ('all', 'sweep'):
     print('== moment sweep ==', flush=True)
