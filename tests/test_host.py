@@ -193,3 +193,68 @@ def test_hostbind_is_best_effort_without_a_gpu():
     before = os.sched_getaffinity(0)
     info = hostbind.bind_to_gpu_numa_node(0)               # no CUDA device here: nothing is changed, nothing raises
     assert info['bound'] is False and os.sched_getaffinity(0) == before
+
+
+# ---- numpy statements of the opt-in kernels: the algorithms the CUDA code follows, pinned on the CPU ----
+def _tool(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, 'tools', name + '.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize('name', ['stage123_small', 'stage123_pristine', 'stage23_medium', 'stage1_dupes'])
+def test_moment_sweep_statement_vs_reference_golden(name):
+    """The plan of moment_plan_kernel / moment_accum_kernel / moment_final_kernel (k2_sweep.cu), restated in numpy,
+    reproduces the reference run's logSumWij (GaussianBandwidth.py:36-44) on every golden matrix."""
+    proto = _tool('sweep_moments_proto')
+    g = golden(name + '.npz')
+    log_eps = np.arange(-100, 100.2, 0.2)
+    coef = 1. / (2. * np.exp(log_eps))
+    ref = g['logSumWij'] if 'logSumWij' in g else O.eps_sweep_logsum(g['D'], log_eps)
+    L, bins = proto.moment_sweep(g['D'], coef, 10.0)
+    assert L is not None and 1 <= bins <= proto.MB
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(L), fin)
+    assert np.max(np.abs(L[fin] - ref[fin])) < 1e-9                           # the GPU tests' tolerance
+
+
+def test_moment_sweep_statement_plan_limits():
+    proto = _tool('sweep_moments_proto')
+    coef = 1. / (2. * np.exp(np.arange(-100, 100.2, 0.2)))
+    rng = np.random.default_rng(3)
+    W = np.exp(rng.uniform(-12, 12, (40, 40)))                                # D^2 spans e^48: more than 32 bins
+    assert proto.moment_sweep(W, coef, 10.0, symmetric=False) == (None, 1)
+    fine = 1. / (2. * np.exp(np.arange(-3, 3, 0.01)))                         # 22 coefficients per bin boundary
+    D = np.sqrt(1.9 + 0.1 * rng.random((30, 30)))
+    np.fill_diagonal(D, 0.0)
+    assert proto.moment_sweep(D, fine, 10.0, symmetric=False) == (None, 2)
+    for thr in (3.0, 10.0, 25.0):                                             # rho = 2, 1.25, 1.087
+        L, bins = proto.moment_sweep(D, coef, thr, symmetric=False)
+        ref = []
+        for c in coef:
+            t = c * (D * D)
+            ref.append(np.log(np.sum(np.exp(-t[t < thr]))))
+        assert bins == 1 and np.max(np.abs(L - np.array(ref))) < 1e-12
+
+
+def test_f16_split_statement_matches_the_tf32_split():
+    """3xFP16 operand planes (stats_split_kernel<true>) carry the same 22 bits as the 3xTF32 planes: equal Gram and
+    distance errors on a noisy and on a noise-free (cancellation regime) stack; the scale keeps FP16 in range."""
+    proto = _tool('f16_split_proto')
+    assert [proto.f16_scale_log2(P) for P in (16, 4096, 16384, 62500, 250000, 10 ** 9)] == [8, 8, 7, 6, 5, -1]
+    for snr, n_side, tau in ((0.1, 6, 3), (None, 9, 1)):
+        stack = synth.synthetic_pd(pd=2, box=64, n_side=n_side, tau=tau, snr=snr)
+        X = O.standardize_stack(stack).reshape(stack.shape[0], -1)
+        c = (X - X[:16].mean(axis=0)).astype(np.float32)
+        err = proto.split_errors(c)
+        assert err['f16x3'][0] < 1.5e-7 and err['tf32x3'][0] < 1.5e-7         # 2^-22-level Gram error for both
+        assert err['f16x3'][1] < 1.5 * err['tf32x3'][1] + 1e-9
+        assert err['f16x3'][1] < 1e-5
+    # a hot pixel: the largest z-score a row of P pixels can hold stays finite after scaling
+    P = 4096
+    x = np.full((1, P), -1.0 / np.sqrt(P - 1), dtype=np.float32)
+    x[0, 7] = np.sqrt(P - 1)
+    hi, lo = proto.split_f16(np.repeat(x, 2, axis=0))
+    assert np.all(np.isfinite(hi)) and abs(hi[0, 7] + lo[0, 7] - float(x[0, 7])) < 1e-5
