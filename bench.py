@@ -169,11 +169,14 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+NATIVE_FIT = True      # stage 2b through esper_tanh_fit (MINPACK lmdif restated in C, no interpreter lock); --scipy-fit: curve_fit
+
+
 def embed_step(ctx, GB, coef, a0, n, p, imgs=None, download=False, out=None):
     """One PD through stages 1-3 on `ctx`.  imgs=None -> the ctx-resident stack; out = caller buffer for D."""
     D = ctx.dist_rms(imgs, n=n, P=p, download=download, out=out)
     L = ctx.eps_sweep(None, coef, 10.0, m=n)
-    popt, resnorm, R2 = GB.fit(LOG_EPS, L, a0)
+    popt, resnorm, R2 = GB.fit(LOG_EPS, L, a0, native=NATIVE_FIT)
     eps = float(np.exp(-(popt[1] / popt[0])))
     val, vec, iters = ctx.dmap_embed(None, eps, k=K_EIG, m=n)
     return D, eps, val, vec, iters
@@ -373,6 +376,7 @@ def run_ours(args):
                    'pipelining': '%d PDs in flight per GPU (one host thread / ctx / stream each)' % NF, 'serial_ms_per_step': ms_serial / args.steps,
                    'l2': 'inputs larger than L2 (500 MB stack per PD, two alternating stacks per rank)',
                    'lanczos_steps': iters_used[-1] if iters_used else None, 'numa_bind_rank0': numa,
+                   'tanh_fit': 'esper_tanh_fit (MINPACK lmdif in C)' if NATIVE_FIT else 'scipy.optimize.curve_fit',
                    'experimental': {'gram_f16': bool(args.gram_f16), 'sweep_moments': bool(args.sweep_moments), 'prep_cluster': bool(args.prep_cluster)}},
         'e2e': {'value': pds / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(N_IMG * P * 4),
                 'd2h_bytes_per_step': int(N_IMG * N_IMG * 8 + len(LOG_EPS) * 8 + K_EIG * 8 + N_IMG * K_EIG * 8),
@@ -421,10 +425,13 @@ def main():
     ap.add_argument('--no-numa-bind', action='store_true', help='do not restrict ranks to the CPUs of their GPU\'s NUMA node')
     ap.add_argument('--eig-mode', type=int, default=-1, help='esper_dmap_config mode (-1 = throughput when several PDs are in flight)')
     ap.add_argument('--gram-f16', action='store_true', help='experimental: 3xFP16 operand planes for the Gram kernel (esper_gram_config 1)')
+    ap.add_argument('--scipy-fit', action='store_true', help='tanh fit with scipy.optimize.curve_fit (the reference\'s call) instead of esper_tanh_fit')
     ap.add_argument('--prep-cluster', action='store_true', help='experimental: cluster standardise-and-split pass (esper_prep_config 1)')
     ap.add_argument('--sweep-moments', action='store_true', help='experimental: moment sweep (esper_sweep_config 1)')
     ap.add_argument('--inflight', type=int, default=4, help='PDs in flight per GPU (host threads / ctxs / streams)')
     args = ap.parse_args()
+    global NATIVE_FIT
+    NATIVE_FIT = not args.scipy_fit
     if args.impl == 'reference':
         return run_reference(args)
     return run_ours(args)

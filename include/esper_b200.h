@@ -112,6 +112,18 @@ int esper_upload_dist(esper_ctx* ctx, const double* D, int m);
  * thr: GaussianBandwidth.find_threshold (:26-32); pass +inf for "no truncation".          */
 int esper_eps_sweep(esper_ctx* ctx, const double* D, int m, const double* coef, int n_eps,
                     double thr, double* logSum);
+/* ---- stage 2b: the tanh fit (host code, no ctx, no device) ---------------------------------
+ * Replaces the body of the retry loop of 1_Embedding/DM/GaussianBandwidth.py:47-57 for one start vector:
+ *     popt, pcov = curve_fit(fun, logEps, logSumWij, p0=a0);  resnorm = sum(sqrt(abs(diag(pcov))));  R_squared
+ * with fun(x) = a3 + a2 tanh(a0 x + a1) (:18-24).  curve_fit is MINPACK's lmdif behind scipy.optimize.leastsq; this is a
+ * restatement of that algorithm with scipy's default tolerances (k9_fit.cu), so that a whole PD can run without the
+ * Python interpreter; popt agrees with scipy's to ~1e-12 relative on the golden sweeps (tests/test_host.py).
+ * x, y: [n] finite values (ESPER_E_ARG otherwise -- curve_fit raises ValueError there); a0, popt: [4];
+ * info: MINPACK termination code (1..4 = converged); resnorm = +inf when the covariance cannot be estimated (curve_fit
+ * returns an infinite pcov there), which makes the caller's `while resnorm > 100` loop draw a new start as in the reference. */
+int esper_tanh_fit(const double* x, const double* y, int n, const double* a0, double* popt, double* resnorm,
+                   double* r_squared, int* info, int* nfev);
+
 /* Sweep algorithm: mode 0 (default) evaluates exp() for every (element, k) between the plateaus; mode 1 is the
  * moment sweep -- D^2 grouped into geometric bins, 17 moments per bin give every fully included k at once, only the
  * k whose truncation boundary falls inside a bin are evaluated per element (the inclusion test stays bit-identical) --

@@ -32,12 +32,24 @@ def sweep(D, logEps, ctx=None, m=None):
     return ctx.eps_sweep(None, coef, thr, m=m)
 
 
-def fit(logEps, logSumWij, a0):
-    """The curve-fit retry loop of GaussianBandwidth.py:47-57 (host side)."""
+def fit(logEps, logSumWij, a0, native=False):
+    """The curve-fit retry loop of GaussianBandwidth.py:47-57 (host side).
+
+    native=False: scipy's `curve_fit`, the reference's own call.  native=True: `esper_tanh_fit`, the same MINPACK lmdif
+    algorithm with scipy's default tolerances restated in C (csrc/k9_fit.cu) -- identical to scipy's result bit for bit
+    when scipy is given a libm-tanh model, 4e-9 relative from it with numpy's SIMD tanh (the forward-difference Jacobian
+    amplifies one-ulp differences), and callable without the interpreter lock, so the fits of several PDs in flight
+    run in parallel."""
     resnorm = np.inf
+    logEps = np.asarray(logEps, dtype=np.float64)
+    logSumWij = np.asarray(logSumWij, dtype=np.float64)
     with warnings.catch_warnings():
         warnings.simplefilter(action='ignore', category=OptimizeWarning)
         while resnorm > 100:
+            if native:
+                popt, resnorm, R_squared, _, _ = _capi.tanh_fit(logEps, logSumWij, a0)
+                a0 = 1 * (np.random.rand(4, 1) - .5)
+                continue
             popt, pcov = curve_fit(fun, logEps, logSumWij, p0=a0)
             resnorm = sum(np.sqrt(np.fabs(np.diag(pcov))))
             a0 = 1 * (np.random.rand(4, 1) - .5)
@@ -48,8 +60,8 @@ def fit(logEps, logSumWij, a0):
     return popt, resnorm, R_squared
 
 
-def op(D, logEps, a0, ctx=None, m=None):
+def op(D, logEps, a0, ctx=None, m=None, native=False):
     """Same call and return tuple as the reference: (popt, logSumWij, resnorm, R_squared)."""
     logSumWij = sweep(D, logEps, ctx=ctx, m=m)
-    popt, resnorm, R_squared = fit(logEps, logSumWij, a0)
+    popt, resnorm, R_squared = fit(logEps, logSumWij, a0, native=native)
     return (popt, logSumWij, resnorm, R_squared)

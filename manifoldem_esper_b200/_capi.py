@@ -49,6 +49,7 @@ SIGNATURES = {
     'esper_prep_info': (C.c_int, [C.c_void_p, C.c_void_p]),
     'esper_gram_config': (C.c_int, [C.c_void_p, C.c_int]),
     'esper_gram_info': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'esper_tanh_fit': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'esper_sweep_config': (C.c_int, [C.c_void_p, C.c_int]),
     'esper_sweep_info': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     'esper_dmap_embed': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int,
@@ -543,6 +544,22 @@ def tridiag_ritz(alpha, beta, k, tol=0.0):
     if rc != ESPER_OK:
         raise ValueError('tridiag_ritz: bad argument')
     return bool(conv.value), theta, S
+
+
+def tanh_fit(x, y, a0):
+    """Host only: esper_tanh_fit, one curve_fit(fun, x, y, p0=a0) of GaussianBandwidth.py:47-57 ->
+    (popt[4], resnorm, R_squared, info, nfev)."""
+    lib = load_library()
+    x, y = _as(x, np.float64).reshape(-1), _as(y, np.float64).reshape(-1)
+    a0 = _as(a0, np.float64).reshape(-1)
+    if x.shape != y.shape or a0.shape[0] != 4:
+        raise ValueError('tanh_fit: x and y must have the same length and a0 four entries')
+    popt = np.empty(4)
+    rn, r2, info, nfev = C.c_double(0), C.c_double(0), C.c_int(0), C.c_int(0)
+    rc = lib.esper_tanh_fit(_ptr(x), _ptr(y), x.shape[0], _ptr(a0), _ptr(popt), C.byref(rn), C.byref(r2), C.byref(info), C.byref(nfev))
+    if rc != ESPER_OK:
+        raise ValueError('tanh_fit: array must not contain infs or NaNs (and needs at least 4 points)')
+    return popt, rn.value, r2.value, info.value, nfev.value
 
 
 def nd_rotation(n, theta):

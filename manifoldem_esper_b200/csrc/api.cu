@@ -242,6 +242,11 @@ int esper_eps_sweep(esper_ctx* c, const double* D, int m, const double* coef, in
     return run_sweep(c, m, coef, n_eps, thr, logSum);
 }
 
+int esper_tanh_fit(const double* x, const double* y, int n, const double* a0, double* popt, double* resnorm,
+                   double* r_squared, int* info, int* nfev) {
+    return tanh_fit_host(x, y, n, a0, popt, resnorm, r_squared, info, nfev);
+}
+
 int esper_sweep_config(esper_ctx* c, int mode) {
     ESPER_ENTER(c);
     if (mode != 0 && mode != 1) return fail(c, ESPER_E_ARG, "sweep_config: mode must be 0 (general) or 1 (moments)");

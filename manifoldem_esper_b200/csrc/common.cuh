@@ -208,6 +208,8 @@ int run_tau_snr_stack(esper_ctx* c, const float* pristine_h, int ss, int box, in
 int mrc_info_host(const char* path, int* dims, int* mode, long long* data_offset, char* err, size_t err_len);
 int run_upload_mrc(esper_ctx* c, const char* path, int first, int count, int* dims_out);
 int run_bin_accumulate(esper_ctx* c, int n, int P, const int* order_h, const int* offsets_h, int n_bins, double* sums_h);
+int tanh_fit_host(const double* x, const double* y, int m, const double* a0, double* popt, double* resnorm, double* r_squared,
+                  int* info_out, int* nfev_out);                        // k9_fit.cu
 void nd_rotation_host(int n, const double* theta, double* R);
 void hist_edges_host(int bins, double lo, double hi, double* edges);
 

@@ -258,3 +258,62 @@ def test_f16_split_statement_matches_the_tf32_split():
     x[0, 7] = np.sqrt(P - 1)
     hi, lo = proto.split_f16(np.repeat(x, 2, axis=0))
     assert np.all(np.isfinite(hi)) and abs(hi[0, 7] + lo[0, 7] - float(x[0, 7])) < 1e-5
+
+
+# ---- stage 2b in C: esper_tanh_fit against scipy's curve_fit (the reference's call, GaussianBandwidth.py:47-57) ----
+@pytest.mark.parametrize('name', ['stage123_small', 'stage123_pristine', 'stage23_medium'])
+def test_tanh_fit_vs_scipy_curve_fit(lib_built, name):
+    from scipy.optimize import curve_fit
+    from manifoldem_esper_b200 import GaussianBandwidth as GB
+    g = golden(name + '.npz')
+    log_eps = np.arange(-100, 100.2, 0.2)
+    L = g['logSumWij']
+    rng = np.random.RandomState(int(g['seed']) if 'seed' in g else 0)
+    for trial in range(4):
+        a0 = rng.rand(4, 1) - .5                                   # the reference's start (DiffusionMaps.py:74)
+        try:
+            popt, pcov = curve_fit(GB.fun, log_eps, L, p0=a0)
+        except RuntimeError:
+            continue
+        resnorm = sum(np.sqrt(np.fabs(np.diag(pcov))))
+        p, rn, r2, info, nfev = _capi.tanh_fit(log_eps, L, a0)
+        if not np.isfinite(resnorm) or resnorm > 100:
+            assert rn > 100                                           # both ask for another start
+            continue
+        assert 1 <= info <= 4 and nfev > 4
+        assert np.max(np.abs(p - popt) / np.maximum(np.abs(popt), 1e-3)) < 1e-7
+        assert abs(np.exp(-(p[1] / p[0])) - np.exp(-(popt[1] / popt[0]))) / np.exp(-(popt[1] / popt[0])) < 1e-7   # epsilon
+        assert abs(rn - resnorm) / resnorm < 1e-5
+        res = L - GB.fun(log_eps, *popt)
+        assert abs(r2 - (1 - np.sum(res ** 2) / np.sum((L - np.mean(L)) ** 2))) < 1e-10
+    if 'eps' in g and 'seed' in g:                                     # the epsilon of the reference run itself
+        np.random.seed(int(g['seed']))
+        a0 = 1 * (np.random.rand(4, 1) - .5)
+        p, _, _ = GB.fit(log_eps, L, a0, native=True)
+        assert abs(np.exp(-(p[1] / p[0])) - float(g['eps'])) / float(g['eps']) < 1e-7
+
+
+def test_tanh_fit_is_minpack_lmdif_bit_for_bit(lib_built):
+    """With the same libm tanh inside the model, scipy's MINPACK and the C restatement walk the same trajectory."""
+    import math
+    from scipy.optimize import leastsq
+    g = golden('stage23_medium.npz')
+    log_eps = np.arange(-100, 100.2, 0.2)
+    L = g['logSumWij']
+
+    def resid(a):
+        return np.array([a[3] + a[2] * math.tanh(a[0] * x + a[1]) - y for x, y in zip(log_eps, L)])
+    for a0 in ([-0.2, 0.3, -0.4, 0.1], [0.4, -0.1, 0.3, 0.45]):
+        ref = leastsq(resid, np.array(a0), full_output=1)
+        p, rn, r2, info, nfev = _capi.tanh_fit(log_eps, L, a0)
+        assert np.array_equal(p, ref[0]) and nfev == ref[2]['nfev'] and info == ref[4]
+
+
+def test_tanh_fit_argument_errors(lib_built):
+    x = np.arange(10.0)
+    with pytest.raises(ValueError):
+        _capi.tanh_fit(x, np.full(10, -np.inf), [0.1, 0.1, 0.1, 0.1])   # curve_fit: "array must not contain infs or NaNs"
+    with pytest.raises(ValueError):
+        _capi.tanh_fit(x, x[:5], [0.1, 0.1, 0.1, 0.1])
+    with pytest.raises(ValueError):
+        _capi.tanh_fit(x[:3], x[:3], [0.1, 0.1, 0.1, 0.1])
