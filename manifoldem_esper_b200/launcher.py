@@ -46,26 +46,59 @@ def dist_env():
     return int(os.environ.get('RANK', '0')), int(os.environ.get('LOCAL_RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
 
 
-def run_sharded(pds, work_fn, rank=0, world=1, gather=None):
+def _run_one(pd, work_fn, rank):
+    t0 = time.time()
+    rec = {'PD': pd, 'rank': rank}
+    try:
+        extra = work_fn(pd)
+        rec['ok'] = True
+        if isinstance(extra, dict):
+            rec.update(extra)
+    except Exception as e:                      # noqa: BLE001 -- isolate one PD's failure
+        rec.update(ok=False, error='%s: %s' % (type(e).__name__, e), trace=traceback.format_exc(limit=4))
+    rec['seconds'] = time.time() - t0
+    return rec
+
+
+def run_sharded(pds, work_fn, rank=0, world=1, gather=None, inflight=1):
     """Run work_fn(pd) for this rank's PDs with per-PD error isolation.
+
+    `work_fn` is a callable, or -- with `inflight` > 1 -- a list of `inflight` callables (one per host thread, each
+    with its own GPU context and stream): the threads take this rank's PDs from a shared queue, so the file I/O,
+    host-to-device copy and host-side fit of one PD overlap the kernels of the others (the library calls release the
+    interpreter lock).  Records come back in PD order either way.
 
     Returns this rank's records, or on rank 0 all ranks' records when `gather` (a callable
     taking the local list and returning the list of all ranks' lists, e.g. built on
     torch.distributed.all_gather_object) is given.
     """
-    records = []
-    for pd in shard(pds, rank, world):
-        t0 = time.time()
-        rec = {'PD': pd, 'rank': rank}
-        try:
-            extra = work_fn(pd)
-            rec['ok'] = True
-            if isinstance(extra, dict):
-                rec.update(extra)
-        except Exception as e:                      # noqa: BLE001 -- isolate one PD's failure
-            rec.update(ok=False, error='%s: %s' % (type(e).__name__, e), trace=traceback.format_exc(limit=4))
-        rec['seconds'] = time.time() - t0
-        records.append(rec)
+    mine = shard(pds, rank, world)
+    fns = list(work_fn) if isinstance(work_fn, (list, tuple)) else [work_fn]
+    if inflight < 1 or (inflight > 1 and len(fns) != inflight):
+        raise ValueError('run_sharded: inflight=%s needs that many work functions (got %d)' % (inflight, len(fns)))
+    if inflight == 1:
+        records = [_run_one(pd, fns[0], rank) for pd in mine]
+    else:
+        import queue
+        import threading
+        todo = queue.Queue()
+        for i, pd in enumerate(mine):
+            todo.put((i, pd))
+        slots = [None] * len(mine)
+
+        def worker(fn):
+            while True:
+                try:
+                    i, pd = todo.get_nowait()
+                except queue.Empty:
+                    return
+                slots[i] = _run_one(pd, fn, rank)
+        threads = [threading.Thread(target=worker, args=(fn,)) for fn in fns]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        records = slots
     if gather is not None:
         all_lists = gather(records)
         if rank == 0:
@@ -114,6 +147,7 @@ def main(argv=None):
     ap.add_argument('--no-ctf', action='store_true', help='Distances: CTF = False branch (the reference ships CTF = True)')
     ap.add_argument('-k', type=int, default=16)
     ap.add_argument('--skip-existing', action='store_true')
+    ap.add_argument('--inflight', type=int, default=1, help='PDs in flight per GPU (host threads, each with its own context and stream)')
     args = ap.parse_args(argv)
     rank, local_rank, world = dist_env()
     gather = None
@@ -129,8 +163,9 @@ def main(argv=None):
     if world > 1:
         from . import hostbind
         hostbind.bind_to_gpu_numa_node(local_rank)      # host buffers of this rank next to its GPU (best effort)
-    work = _stage_fns(args.root, set(args.stages.split(',')), args.dim, args.pca, args.k, args.skip_existing, local_rank, ctf=not args.no_ctf)
-    recs = run_sharded(parse_pds(args.pds), work, rank, world, gather)
+    works = [_stage_fns(args.root, set(args.stages.split(',')), args.dim, args.pca, args.k, args.skip_existing, local_rank, ctf=not args.no_ctf)
+             for _ in range(max(1, args.inflight))]
+    recs = run_sharded(parse_pds(args.pds), works if len(works) > 1 else works[0], rank, world, gather, inflight=len(works))
     failed = [r for r in recs if not r.get('ok')]
     if rank == 0:
         for r in recs:

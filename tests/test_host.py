@@ -160,6 +160,23 @@ def test_pd_parsing_and_sharding():
     recs = launcher.run_sharded(pds, work, 0, 1)
     assert [r['ok'] for r in recs] == [True, True, False, True, True, True, True, True]
     assert 'boom' in recs[2]['error']
+    # several PDs in flight: one work function per host thread, records still in PD order, failures isolated
+    import threading
+    import time as _time
+    seen = {}
+
+    def make(tag):
+        def w(pd):
+            seen.setdefault(tag, []).append((pd, threading.get_ident()))
+            _time.sleep(0.01)
+            return work(pd)
+        return w
+    recs3 = launcher.run_sharded(pds, [make(t) for t in range(3)], 0, 1, inflight=3)
+    assert [r['PD'] for r in recs3] == pds and [r['ok'] for r in recs3] == [r['ok'] for r in recs]
+    assert sorted(pd for v in seen.values() for pd, _ in v) == pds and len(seen) == 3
+    assert all(len({tid for _, tid in v}) == 1 for v in seen.values())          # a work function stays on its thread
+    with pytest.raises(ValueError):
+        launcher.run_sharded(pds, work, 0, 1, inflight=2)
 
 
 def test_philox_restatement_known_answers():
