@@ -191,6 +191,7 @@ def run_ours(args):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     torch.cuda.set_device(local_rank)
+    sys.setswitchinterval(2e-4)          # pipeline threads hand the interpreter lock over quickly (default 5 ms)
     # pinned stacks and host threads on the NUMA node of this rank's GPU (matters for the e2e figure at 8 GPUs)
     from manifoldem_esper_b200 import hostbind
     numa = hostbind.bind_to_gpu_numa_node(local_rank) if world > 1 and not args.no_numa_bind else {'bound': False}
