@@ -148,7 +148,9 @@ int esper_markov(esper_ctx* ctx, const double* D, int m, double eps, double* deg
 /* Eigensolver scheduling for m <= 2048.  mode 0 (default, lowest latency for one PD): every CTA keeps its rows of
  * Ms in shared memory / registers for the whole solve (the kernel owns the SMs).  mode 1 (highest throughput with
  * several ctxs per GPU): rows are streamed from L2 and the kernel fits twice per SM, so the solves of two PDs
- * overlap and hide each other's grid-barrier latency.  Same arithmetic, same results. */
+ * overlap and hide each other's grid-barrier latency.  Same arithmetic, same results.  mode 2 (opt-in, not yet run on
+ * hardware): mode 1 without the speculatively launched batch -- batches of 8 steps issued after each failed convergence
+ * test, ~20 fewer steps executed per PD when other streams fill the gaps. */
 int esper_dmap_config(esper_ctx* ctx, int mode);
 int esper_dmap_embed(esper_ctx* ctx, const double* D, int m, double eps, int k, double tol,
                      int max_iter, double* val, double* vec, int* iters);

@@ -266,7 +266,8 @@ class Context:
         return deg, Ms
 
     def dmap_config(self, mode=0):
-        """0 = latency (Ms resident on chip), 1 = throughput (two solves share every SM)."""
+        """0 = latency (Ms resident on chip), 1 = throughput (two solves share every SM), 2 = throughput without the
+        speculative batch (opt-in)."""
         self._check(self._lib.esper_dmap_config(self._h, int(mode)))
 
     def dmap_embed(self, D, eps, k=16, tol=0.0, max_iter=0, m=None):

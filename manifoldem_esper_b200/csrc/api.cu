@@ -277,7 +277,7 @@ int esper_markov(esper_ctx* c, const double* D, int m, double eps, double* degre
 
 int esper_dmap_config(esper_ctx* c, int mode) {
     ESPER_ENTER(c);
-    if (mode != 0 && mode != 1) return fail(c, ESPER_E_ARG, "dmap_config: mode must be 0 (latency) or 1 (throughput)");
+    if (mode < 0 || mode > 2) return fail(c, ESPER_E_ARG, "dmap_config: mode must be 0 (latency), 1 (throughput) or 2 (throughput, no speculative batch)");
     c->lanczos_mode = mode;
     return ESPER_OK;
 }

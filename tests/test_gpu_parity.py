@@ -588,6 +588,23 @@ def test_eigensolver_modes_agree(ctx):
         ctx.dmap_config(7)
 
 
+@experimental
+def test_eigensolver_without_speculative_batch(ctx):
+    """esper_dmap_config(2): batches of 8 steps issued after each failed convergence test; same pairs, no more steps."""
+    for name, k in (('stage23_medium', 10), ('stage123_pristine', 12)):
+        g = golden(name + '.npz')
+        ctx.dmap_config(1)
+        v1, U1, it1 = ctx.dmap_embed(g['D'], float(g['eps']), k=k)
+        ctx.dmap_config(2)
+        try:
+            v2, U2, it2 = ctx.dmap_embed(g['D'], float(g['eps']), k=k)
+        finally:
+            ctx.dmap_config(0)
+        assert it2 <= it1 and np.max(np.abs(v1 - v2) / v1) < 1e-10
+        for i in range(k):
+            assert vec_err(U1[:, i], U2[:, i]) < 1e-7 or i >= 7       # bulk-edge vectors: subspace only
+
+
 def test_embed_argument_errors(ctx):
     D = golden('stage123_small.npz')['D']
     with pytest.raises(ValueError):

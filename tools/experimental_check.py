@@ -4,13 +4,14 @@
   * 3xFP16 operand planes for the Gram kernel     esper_gram_config(ctx, 1)    gram_wide_kernel<true>, stats_split_kernel<true>
   * cluster standardise-and-split pass            esper_prep_config(ctx, 1)    stats_split_cluster_kernel<HALF>
   * moment sweep                                  esper_sweep_config(ctx, 1)   moment_{stats,plan,accum,final}_kernel
+  * eigensolver schedule without speculation      esper_dmap_config(ctx, 2)    host control flow of lanczos_attempt only
 
-    gpurun --timeout 400 -- 'timeout 300 python tools/experimental_check.py [gram|sweep]'
+    gpurun --timeout 400 -- 'timeout 300 python tools/experimental_check.py [gram|sweep|eig]'
 
 Every stage prints before the next starts (flush), small shapes first, so a hang or fault is attributable.  Then:
 
     ESPER_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -q -k "f16_operands or moment_sweep or cluster_prep"
-    python bench.py --gram-f16 --sweep-moments --prep-cluster
+    python bench.py --gram-f16 --sweep-moments --prep-cluster --eig-mode 2
 
 When both are green and faster, make them the defaults (ctx->gram_mode / sweep_mode = 1 in esper_create), drop the
 `experimental` marker in tests/test_gpu_parity.py and re-capture profiles/ (launch list + ncu --set full of the Gram kernel).
@@ -136,5 +137,27 @@ if what in ('all', 'sweep'):
         print('%s sweep: %.3f ms of kernels' % ('moment' if mode else 'general', ctx.kernel_ms('sweep')[0] / 5), flush=True)
     ctx.set_profiling(False)
     ctx.sweep_config(0)
+
+if what in ('all', 'eig'):
+    print('== eigensolver schedule without the speculative batch (esper_dmap_config 2) ==', flush=True)
+    Xe = synth.synthetic_pd(pd=3, box=250, n_side=20, tau=5, snr=0.1).reshape(2000, 62500)
+    ctx.dist_rms(Xe, download=False)
+    ctx.set_profiling(True)
+    res = {}
+    for mode in (1, 2):
+        ctx.dmap_config(mode)
+        ctx.dmap_embed(None, 0.2834, k=10, m=2000)
+        ctx.reset_profiling()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            val, vec, steps = ctx.dmap_embed(None, 0.2834, k=10, m=2000)
+        wall = (time.perf_counter() - t0) / 5 * 1e3
+        res[mode] = val
+        print('mode %d: %d steps reported, %.3f ms of kernels, %.3f ms wall per solve' % (mode, steps, ctx.kernel_ms('lanczos')[0] / 5, wall), flush=True)
+    good = float(np.max(np.abs(res[1] - res[2]) / res[1])) < 1e-10
+    ok &= good
+    print('eigenvalues of both schedules agree: %s' % ('ok' if good else 'FAILED'), flush=True)
+    ctx.set_profiling(False)
+    ctx.dmap_config(0)
 
 print('EXPERIMENTAL KERNELS OK' if ok else 'EXPERIMENTAL KERNELS FAILED')
