@@ -840,7 +840,11 @@ int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, i
     // 128x256 tiles for the full symmetric matrix (gram_wide_kernel): same bits as the 128x128 kernel, 12 % faster at the
     // benchmark shape.  ESPER_GRAM_WIDE=0 selects the 128x128 kernel (which the row-block and CTF products always use).
     const char* wide_env = getenv("ESPER_GRAM_WIDE");
-    const bool wide = f16 || (!rect && nt >= 2 && !(wide_env && atoi(wide_env) == 0) && drain_kb > 0);
+    // The PCA Gram output (gram_out) keeps the 128x128 kernel until gram_finalize_kernel has run with wide tiles on hardware
+    // (the wide kernel became the default in the last GPU minutes of round 1; only the distance epilogue was exercised);
+    // ESPER_GRAM_WIDE=2 enables it there too.
+    const bool wide_gram_ok = !gram_out || (wide_env && atoi(wide_env) == 2);
+    const bool wide = f16 || (!rect && nt >= 2 && !(wide_env && atoi(wide_env) == 0) && drain_kb > 0 && wide_gram_ok);
     if (f16 && drain_kb < 1) drain_kb = 2;
 
     // Bound the split-K workspace: process the triangle in batches of tiles.
