@@ -50,7 +50,8 @@ esper_ctx*  esper_create(int device, void* stream);
 void        esper_destroy(esper_ctx* ctx);
 const char* esper_last_error(esper_ctx* ctx);          /* ctx may be NULL: last create error */
 int         esper_sync(esper_ctx* ctx);                 /* cudaStreamSynchronize              */
-/* Per-kernel CUDA-event timing of the calls that follow (off by default). */
+/* Per-kernel CUDA-event timing of the calls that follow (off by default).  on: 0 off, 1 every launch, 2 the stage-1 Gram
+ * launches only (two events per PD: cheap enough to leave on inside a timed region). */
 int         esper_set_profiling(esper_ctx* ctx, int on);
 /* Sum / count of the kernel launches recorded under `name` since the last reset.
  * names: "prep", "gram", "dist_finalize", "refine", "sweep", "markov", "lanczos", "rot", "conic", "dataprep".    */

@@ -164,7 +164,7 @@ class Context:
         self._check(self._lib.esper_sync(self._h))
 
     def set_profiling(self, on=True):
-        self._check(self._lib.esper_set_profiling(self._h, int(bool(on))))
+        self._check(self._lib.esper_set_profiling(self._h, int(on)))       # 0 off, 1 every launch, 2 the Gram launches only
 
     def reset_profiling(self):
         self._check(self._lib.esper_reset_profiling(self._h))

@@ -94,6 +94,7 @@ int esper_sync(esper_ctx* c) {
 int esper_set_profiling(esper_ctx* c, int on) {
     ESPER_ENTER(c);
     c->profiling = on != 0;
+    c->profiling_gram_only = (on == 2);
     return ESPER_OK;
 }
 

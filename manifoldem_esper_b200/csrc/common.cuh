@@ -64,6 +64,7 @@ struct esper_ctx {
 
     // profiling
     bool profiling = false;
+    bool profiling_gram_only = false;                          // esper_set_profiling(ctx, 2): time the stage-1 Gram launches only
     std::map<std::string, esper::KernelTimer> timers;
     std::vector<cudaEvent_t> event_pool;
     long long launches = 0;
@@ -149,6 +150,7 @@ struct LaunchScope {
     LaunchScope(esper_ctx* ctx, const char* nm) : c(ctx), name(nm) {
         c->launches++;
         if (!c->profiling) return;
+        if (c->profiling_gram_only && strcmp(nm, "gram") != 0) return;
         a = get(); b = get();
         cudaEventRecord(a, c->stream);
     }
