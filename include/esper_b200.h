@@ -205,6 +205,16 @@ int esper_dist_rms_rows(esper_ctx* ctx, const float* imgs /*[n,P] or NULL=reside
                         int row0, int nrows, double* D_rows /*[nrows,n] or NULL*/);
 /* sums[k] = sum over the resident block of exp(-t) with t < thr (NOT the logarithm: ranks add these). */
 int esper_eps_sweep_rows(esper_ctx* ctx, int nrows, int n, const double* coef, int n_eps, double thr, double* sums);
+/* Moment sweep over row blocks (opt-in, not yet run on hardware; DESIGN.md 6f, manifoldem_esper_b200/moment_sweep.py).
+ * stats4 = {min non-zero D^2, max D^2, number of exact zeros, number of valid elements} of the resident block; the ranks
+ * all-reduce them (min, max, sum, sum) and build ONE plan (moment_sweep.plan: geometric bins, k ranges per bin).
+ * moment_accum_rows: table [32][21] = per bin 17 moments + 4 boundary sums of the block against that plan; the ranks
+ * all-reduce(sum) the tables and moment_sweep.finalize evaluates every epsilon.  esper_moment_layout: {MP, MS, MB, plan
+ * header, plan entries per bin} the library was built with (host only). */
+int esper_moment_layout(int* out5);
+int esper_moment_stats_rows(esper_ctx* ctx, int nrows, int n, double* stats4);
+int esper_moment_accum_rows(esper_ctx* ctx, int nrows, int n, const double* coef, int n_eps, double thr,
+                            const double* plan, double* table);
 /* degree of the owned rows (DiffusionMaps.py:131-137): degree_rows [nrows]. */
 int esper_degree_rows(esper_ctx* ctx, int nrows, int n, double eps, double* degree_rows);
 /* Ms rows from the gathered degrees of all n rows (DiffusionMaps.py:139-152); block stays resident. */

@@ -59,6 +59,9 @@ SIGNATURES = {
     'esper_pca_embed': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                                   C.c_void_p, C.c_void_p, _i32p]),
     'esper_dist_rms_rows': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int, C.c_void_p]),
+    'esper_moment_layout': (C.c_int, [C.c_void_p]),
+    'esper_moment_stats_rows': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    'esper_moment_accum_rows': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     'esper_eps_sweep_rows': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
     'esper_degree_rows': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]),
     'esper_markov_rows': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]),
@@ -332,6 +335,23 @@ class Context:
         D = np.empty((nrows, n), dtype=np.float64) if download else None
         self._check(self._lib.esper_dist_rms_rows(self._h, _ptr(imgs), int(n), int(P), int(flags), int(row0), int(nrows), _ptr(D)))
         return D
+
+    def moment_stats_rows(self, nrows, n):
+        """[min non-zero D^2, max D^2, zeros, valid elements] of the resident row block (moment sweep, step 1)."""
+        out = np.empty(4, dtype=np.float64)
+        self._check(self._lib.esper_moment_stats_rows(self._h, int(nrows), int(n), _ptr(out)))
+        return out
+
+    def moment_accum_rows(self, nrows, n, coef, thr, plan):
+        """Moments and boundary sums [MB, MV] of the resident row block against `plan` (moment_sweep.plan)."""
+        from . import moment_sweep
+        coef = _as(coef, np.float64).reshape(-1)
+        plan = _as(plan, np.float64).reshape(-1)
+        if plan.shape[0] != moment_sweep.PLAN_LEN:
+            raise ValueError('moment_accum_rows: plan must have %d entries' % moment_sweep.PLAN_LEN)
+        out = np.empty((moment_sweep.MB, moment_sweep.MV), dtype=np.float64)
+        self._check(self._lib.esper_moment_accum_rows(self._h, int(nrows), int(n), _ptr(coef), coef.shape[0], float(thr), _ptr(plan), _ptr(out)))
+        return out
 
     def eps_sweep_rows(self, nrows, n, coef, thr):
         coef = _as(coef, np.float64).reshape(-1)

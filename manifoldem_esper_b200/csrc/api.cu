@@ -417,6 +417,28 @@ static int need_rows(esper_ctx* c, int nrows, int n, const char* who) {
     return ESPER_OK;
 }
 
+int esper_moment_layout(int* out5) {
+    if (!out5) return ESPER_E_ARG;
+    moment_layout_host(out5);
+    return ESPER_OK;
+}
+
+int esper_moment_stats_rows(esper_ctx* c, int nrows, int n, double* stats4) {
+    ESPER_ENTER(c);
+    if (!stats4) return fail(c, ESPER_E_ARG, "moment_stats_rows: stats4 is NULL");
+    int rc = need_rows(c, nrows, n, "moment_stats_rows");
+    if (rc) return rc;
+    return run_moment_stats_rows(c, nrows, n, stats4);
+}
+
+int esper_moment_accum_rows(esper_ctx* c, int nrows, int n, const double* coef, int n_eps, double thr, const double* plan, double* table) {
+    ESPER_ENTER(c);
+    if (!coef || !plan || !table || n_eps < 1) return fail(c, ESPER_E_ARG, "moment_accum_rows: need coef, plan, table != NULL and n_eps >= 1");
+    int rc = need_rows(c, nrows, n, "moment_accum_rows");
+    if (rc) return rc;
+    return run_moment_accum_rows(c, nrows, n, coef, n_eps, thr, plan, table);
+}
+
 int esper_eps_sweep_rows(esper_ctx* c, int nrows, int n, const double* coef, int n_eps, double thr, double* sums) {
     ESPER_ENTER(c);
     if (!coef || !sums || n_eps < 1) return fail(c, ESPER_E_ARG, "eps_sweep_rows: need coef, sums != NULL and n_eps >= 1");

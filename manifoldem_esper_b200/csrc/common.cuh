@@ -181,6 +181,9 @@ int run_markov_rows(esper_ctx* c, int rows, int m, int row0, double eps, const d
 bool ritz_converged(const std::vector<double>& a, const std::vector<double>& b, int n, int kw, int guard, double tol,
                     std::vector<double>& theta, std::vector<double>& S);
 int check_symmetry(esper_ctx* c, int m);
+int run_moment_stats_rows(esper_ctx* c, int rows, int m, double* out4_h);
+int run_moment_accum_rows(esper_ctx* c, int rows, int m, const double* coef_h, int n_eps, double thr, const double* plan_h, double* table_h);
+void moment_layout_host(int* out5);
 int run_product(esper_ctx* c, float* a_hi, float* a_lo, int na, float* b_hi, float* b_lo, int nb, int ld, double* M);
 int run_ctf_dist(esper_ctx* c, int n, int box, const double* params_h, unsigned flags, bool want_wiener);
 int row_stats_numpy(esper_ctx* c, int n, int P, RowStat* st);

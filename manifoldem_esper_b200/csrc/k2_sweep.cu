@@ -275,23 +275,24 @@ constexpr int PLAN_LEN = PLAN_HDR + PLAN_BIN * MB;
 constexpr int MTHREADS = 256;
 constexpr int MWARPS = MTHREADS / 32;
 
-// Rows p and m-1-p are handled together: m+1 elements of the upper triangle per pair (sym) or 2m (full matrix).
+// Rows p and rows-1-p of a [rows, m] block are handled together: m+1 elements of the upper triangle per pair (sym, square
+// matrix only) or 2m (all elements: full matrix or the row block of the oversized-PD path).
 struct PairRange { int i1, j1, len1, i2, j2, len2; };
-__device__ __forceinline__ PairRange pair_range(int p, int m, int sym) {
+__device__ __forceinline__ PairRange pair_range(int p, int rows, int m, int sym) {
     PairRange r;
     r.i1 = p; r.j1 = sym ? p : 0; r.len1 = m - r.j1;
-    r.i2 = m - 1 - p; r.j2 = sym ? r.i2 : 0; r.len2 = (r.i2 > r.i1) ? m - r.j2 : 0;
+    r.i2 = rows - 1 - p; r.j2 = sym ? r.i2 : 0; r.len2 = (r.i2 > r.i1) ? m - r.j2 : 0;
     return r;
 }
 
 __global__ void __launch_bounds__(MTHREADS)
-moment_stats_kernel(const double* __restrict__ D, int m, int sym, double* __restrict__ stat_part /*[gridDim.x][4]*/) {
+moment_stats_kernel(const double* __restrict__ D, int rows, int m, int sym, double* __restrict__ stat_part /*[gridDim.x][4]*/) {
     __shared__ double sh[4 * MWARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double mn = INFINITY, mx = 0.0, nz = 0.0, nv = 0.0;
-    const int npairs = (m + 1) >> 1;
+    const int npairs = (rows + 1) >> 1;
     for (int p = blockIdx.x; p < npairs; p += gridDim.x) {
-        const PairRange r = pair_range(p, m, sym);
+        const PairRange r = pair_range(p, rows, m, sym);
         for (int e = threadIdx.x; e < r.len1 + r.len2; e += MTHREADS) {
             const int i = e < r.len1 ? r.i1 : r.i2;
             const int j = e < r.len1 ? r.j1 + e : r.j2 + (e - r.len1);
@@ -358,13 +359,13 @@ moment_plan_kernel(const double* __restrict__ stat_part, int n_parts, const doub
 }
 
 __global__ void __launch_bounds__(MTHREADS)
-moment_accum_kernel(const double* __restrict__ D, int m, int sym, const double* __restrict__ coef, double thr,
+moment_accum_kernel(const double* __restrict__ D, int rows, int m, int sym, const double* __restrict__ coef, double thr,
                     const double* __restrict__ plan, double* __restrict__ part /*[gridDim.x][MB][MV]*/) {
     __shared__ double sh[MWARPS * MV];
     if (plan[0] != 0.0) return;                                   // the host falls back to sweep_kernel
     const int B = (int)plan[1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int npairs = (m + 1) >> 1;
+    const int npairs = (rows + 1) >> 1;
     const double SMALL = 7.450580596923828e-09;                   // as in sweep_kernel
     for (int b = 0; b < B; ++b) {
         const double* pb = plan + PLAN_HDR + PLAN_BIN * b;
@@ -379,7 +380,7 @@ moment_accum_kernel(const double* __restrict__ D, int m, int sym, const double* 
 #pragma unroll
         for (int s = 0; s < MS; ++s) st[s] = 0.0;
         for (int p = blockIdx.x; p < npairs; p += gridDim.x) {
-            const PairRange r = pair_range(p, m, sym);
+            const PairRange r = pair_range(p, rows, m, sym);
 #pragma unroll 2
             for (int e = threadIdx.x; e < r.len1 + r.len2; e += MTHREADS) {
                 const int i = e < r.len1 ? r.i1 : r.i2;
@@ -461,7 +462,90 @@ moment_final_kernel(const double* __restrict__ part, int n_blocks, const double*
     }
 }
 
+
+// Row-block path: tot[b][v] = sum over blocks of part[blk][b][v] (fixed order), the table a rank contributes to the all-reduce.
+__global__ void __launch_bounds__(1024)
+moment_table_kernel(const double* __restrict__ part, int n_blocks, int B, double* __restrict__ tot /*[MB][MV]*/) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int v = warp; v < MB * MV; v += nwarps) {
+        const int b = v / MV, x = v - b * MV;
+        double s = 0.0;
+        if (b < B) {
+            for (int blk = lane; blk < n_blocks; blk += 32) s += part[((size_t)blk * MB + b) * MV + x];
+            s = warp_sum(s);
+        }
+        if (lane == 0) tot[v] = s;
+    }
+}
+
 }  // namespace sweep
+
+// Oversized-PD path, step 1 of the moment sweep: {min non-zero q, max q, weight of exact zeros, weight of valid elements} of the
+// resident [rows, m] block (every element weighs 1).  The ranks all-reduce these (min, max, sum, sum).
+int run_moment_stats_rows(esper_ctx* c, int rows, int m, double* out4_h) {
+    using namespace sweep;
+    int grid = c->sm_count * 2;
+    if (grid > 480) grid = 480;
+    if (grid > (rows + 1) / 2) grid = (rows + 1) / 2;
+    if (grid < 1) grid = 1;
+    ESPER_RESERVE(c, c->sweep_aux, sizeof(double) * 8192);
+    double* stat_d = c->sweep_aux.as<double>();
+    {
+        LaunchScope ls(c, "sweep");
+        moment_stats_kernel<<<grid, MTHREADS, 0, c->stream>>>(c->dist.as<double>(), rows, m, 0, stat_d);
+    }
+    ESPER_CUDA(c, cudaGetLastError());
+    std::vector<double> st((size_t)4 * grid);
+    ESPER_CUDA(c, cudaMemcpyAsync(st.data(), stat_d, sizeof(double) * st.size(), cudaMemcpyDeviceToHost, c->stream));
+    ESPER_CUDA(c, cudaStreamSynchronize(c->stream));
+    double mn = INFINITY, mx = 0.0, nz = 0.0, nv = 0.0;
+    for (int b = 0; b < grid; ++b) { mn = fmin(mn, st[4 * b]); mx = fmax(mx, st[4 * b + 1]); nz += st[4 * b + 2]; nv += st[4 * b + 3]; }
+    out4_h[0] = mn; out4_h[1] = mx; out4_h[2] = nz; out4_h[3] = nv;
+    return ESPER_OK;
+}
+
+// Step 2: moments and boundary sums of the resident block against the caller's plan (manifoldem_esper_b200/moment_sweep.py:
+// made from the all-reduced statistics, so every rank uses the same bins).  table_h [MB][MV].
+int run_moment_accum_rows(esper_ctx* c, int rows, int m, const double* coef_h, int n_eps, double thr, const double* plan_h,
+                          double* table_h) {
+    using namespace sweep;
+    if (plan_h[0] != 0.0) return fail(c, ESPER_E_ARG, "moment_accum_rows: the plan is not usable (status %d)", (int)plan_h[0]);
+    const int B = (int)plan_h[1];
+    if (B < 0 || B > MB) return fail(c, ESPER_E_ARG, "moment_accum_rows: %d bins", B);
+    for (int b = 0; b < B; ++b) {
+        const int ka = (int)plan_h[PLAN_HDR + PLAN_BIN * b + 4], kf = (int)plan_h[PLAN_HDR + PLAN_BIN * b + 5];
+        if (ka < 0 || kf < ka || kf - ka > MS || kf > n_eps) return fail(c, ESPER_E_ARG, "moment_accum_rows: bad k range in bin %d", b);
+    }
+    int grid = c->sm_count * 2;
+    if (grid > 480) grid = 480;
+    if (grid > (rows + 1) / 2) grid = (rows + 1) / 2;
+    if (grid < 1) grid = 1;
+    ESPER_RESERVE(c, c->sweep_part, sizeof(double) * (size_t)grid * MB * MV);
+    ESPER_RESERVE(c, c->sweep_aux, sizeof(double) * ((size_t)n_eps + 8192));
+    double* plan_d = c->sweep_aux.as<double>() + 2048;
+    double* table_d = c->sweep_aux.as<double>() + 4096;            // [MB * MV] = 672 doubles
+    double* coef_d = c->sweep_aux.as<double>() + 8192;
+    static_assert(MB * MV <= 4000, "sweep_aux layout");
+    ESPER_CUDA(c, cudaMemcpyAsync(coef_d, coef_h, sizeof(double) * n_eps, cudaMemcpyHostToDevice, c->stream));
+    ESPER_CUDA(c, cudaMemcpyAsync(plan_d, plan_h, sizeof(double) * PLAN_LEN, cudaMemcpyHostToDevice, c->stream));
+    {
+        LaunchScope ls(c, "sweep");
+        moment_accum_kernel<<<grid, MTHREADS, 0, c->stream>>>(c->dist.as<double>(), rows, m, 0, coef_d, thr, plan_d,
+                                                              c->sweep_part.as<double>());
+    }
+    {
+        LaunchScope ls(c, "sweep");
+        moment_table_kernel<<<1, 1024, 0, c->stream>>>(c->sweep_part.as<double>(), grid, B, table_d);
+    }
+    ESPER_CUDA(c, cudaGetLastError());
+    ESPER_CUDA(c, cudaMemcpyAsync(table_h, table_d, sizeof(double) * MB * MV, cudaMemcpyDeviceToHost, c->stream));
+    ESPER_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ESPER_OK;
+}
+
+void moment_layout_host(int* out5) {
+    out5[0] = sweep::MP; out5[1] = sweep::MS; out5[2] = sweep::MB; out5[3] = sweep::PLAN_HDR; out5[4] = sweep::PLAN_BIN;
+}
 
 int check_symmetry(esper_ctx* c, int m) {
     ESPER_RESERVE(c, c->sweep_aux, sizeof(double) * 4096);
@@ -504,7 +588,7 @@ static int run_sweep_moments(esper_ctx* c, int m, int sym, const double* coef_h,
     ESPER_CUDA(c, cudaMemcpyAsync(coef_d, coef_h, sizeof(double) * n_eps, cudaMemcpyHostToDevice, c->stream));
     {
         LaunchScope ls(c, "sweep");
-        moment_stats_kernel<<<grid, MTHREADS, 0, c->stream>>>(c->dist.as<double>(), m, sym, stat_d);
+        moment_stats_kernel<<<grid, MTHREADS, 0, c->stream>>>(c->dist.as<double>(), m, m, sym, stat_d);
     }
     {
         LaunchScope ls(c, "sweep");
@@ -512,7 +596,7 @@ static int run_sweep_moments(esper_ctx* c, int m, int sym, const double* coef_h,
     }
     {
         LaunchScope ls(c, "sweep");
-        moment_accum_kernel<<<grid, MTHREADS, 0, c->stream>>>(c->dist.as<double>(), m, sym, coef_d, thr, plan_d,
+        moment_accum_kernel<<<grid, MTHREADS, 0, c->stream>>>(c->dist.as<double>(), m, m, sym, coef_d, thr, plan_d,
                                                               c->sweep_part.as<double>());
     }
     {

@@ -50,6 +50,13 @@ class TorchComm:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return t.cpu().numpy()
 
+    def allreduce_minmax(self, lo, hi):
+        """(global min of lo, global max of hi) of two scalars."""
+        t = self.torch.tensor([-float(lo), float(hi)], dtype=self.torch.float64, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        t = t.cpu().numpy()
+        return -float(t[0]), float(t[1])
+
     def allgather_concat(self, arr, chunk):
         """Gather equal-size (zero padded to `chunk`) float64 blocks from all ranks into one array."""
         buf = np.zeros(chunk, dtype=np.float64)
@@ -78,6 +85,12 @@ class CudaBackend:
 
     def sweep_rows(self, coef, thr):
         return self.ctx.eps_sweep_rows(self.nrows, self.n, coef, thr)
+
+    def moment_stats_rows(self):
+        return self.ctx.moment_stats_rows(self.nrows, self.n)
+
+    def moment_accum_rows(self, coef, thr, plan):
+        return self.ctx.moment_accum_rows(self.nrows, self.n, coef, thr, plan)
 
     def degree_rows(self, eps):
         return self.ctx.degree_rows(self.nrows, self.n, eps)
@@ -163,12 +176,32 @@ class CudaBackend:
         self.torch.cuda.synchronize()
 
 
+def sweep_sums(backend, comm, coef, thr, moments=False):
+    """sum_{ij : t < thr} exp(-t), t = coef[k] D_ij^2, over all ranks' row blocks -> (sums[k], 'general' | 'moments').
+
+    General: every rank evaluates its block (`esper_eps_sweep_rows`), one all-reduce of the 1001 sums.  `moments=True`
+    (opt-in; moment_sweep.py): all-reduce of the block statistics (min / max of the non-zero D^2, number of zeros), one
+    plan for all ranks, all-reduce of the [32, 21] moment tables, evaluation on the host; falls back to the general sweep
+    when D^2 spans more than 32 bins or the coefficients are not a non-increasing grid."""
+    from . import moment_sweep as MSW
+    if moments and hasattr(backend, 'moment_stats_rows') and MSW.usable(coef, thr):
+        st = np.asarray(backend.moment_stats_rows(), dtype=np.float64)
+        mn, mx = comm.allreduce_minmax(st[0], st[1])
+        nz, nv = comm.allreduce_sum(st[2:4])
+        status, pl = MSW.plan(mn, mx, nz, nv, coef, thr)
+        if status == 0:
+            tot = comm.allreduce_sum(np.asarray(backend.moment_accum_rows(coef, thr, pl), dtype=np.float64).reshape(-1))
+            return MSW.finalize(pl, tot, coef, thr), 'moments'
+    return comm.allreduce_sum(backend.sweep_rows(coef, thr)), 'general'
+
+
 def embed_oversized(backend, comm, n, k=16, eps=None, a0=None, tol=0.0, max_steps=1024, check_every=16,
-                    log_eps=None, verbose=False):
+                    log_eps=None, verbose=False, moments=False):
     """Distances -> epsilon -> Markov rows -> leading k eigenpairs of one PD split over comm.world ranks.
 
     Returns dict(eps, val [k] = lambda^2, vec [n, k], steps, logSumWij, popt) (identical on every rank).
     `a0` (tanh-fit start, 4 values) must be the same on all ranks; default is a fixed start.
+    `moments=True` selects the moment sweep (see sweep_sums).
     """
     import time
     rank, world = comm.rank, comm.world
@@ -185,8 +218,10 @@ def embed_oversized(backend, comm, n, k=16, eps=None, a0=None, tol=0.0, max_step
         # find_threshold (GaussianBandwidth.py:26-32) needs the global sum at the largest epsilon
         ss = comm.allreduce_sum(backend.sweep_rows(np.array([1. / (2. * np.max(e))]), np.inf))[0]
         thr = max(-np.log(0.01 * ss / n), 10)
-        sums = comm.allreduce_sum(backend.sweep_rows(1. / (2. * e), thr))
-        logSumWij = np.log(sums)
+        sums, sweep_path = sweep_sums(backend, comm, 1. / (2. * e), thr, moments=moments)
+        with np.errstate(divide='ignore'):
+            logSumWij = np.log(sums)
+        out['sweep_path'] = sweep_path
         if a0 is None:
             a0 = np.array([[-0.2], [0.3], [-0.4], [0.1]])
         state = np.random.get_state()

@@ -334,3 +334,13 @@ def test_tanh_fit_argument_errors(lib_built):
         _capi.tanh_fit(x, x[:5], [0.1, 0.1, 0.1, 0.1])
     with pytest.raises(ValueError):
         _capi.tanh_fit(x[:3], x[:3], [0.1, 0.1, 0.1, 0.1])
+
+
+def test_moment_sweep_layout_matches_the_library(lib_built):
+    """moment_sweep.py builds the plan the device kernels read: its constants must be the library's."""
+    from manifoldem_esper_b200 import moment_sweep
+    moment_sweep.check_layout(_capi.load_library())
+    coef = 1. / (2. * np.exp(np.arange(-100, 100.2, 0.2)))
+    assert moment_sweep.usable(coef, 10.0) and not moment_sweep.usable(coef[::-1], 10.0) and not moment_sweep.usable(coef, np.inf)
+    status, pl = moment_sweep.plan(1.85, 1.95, 2000.0, 4e6, coef, 10.0)
+    assert status == 0 and pl.shape == (moment_sweep.PLAN_LEN,) and pl[1] == 1 and 0 <= pl[13] - pl[12] <= moment_sweep.MS

@@ -33,6 +33,14 @@ class NumpyBackend:
     def sweep_rows(self, coef, thr):
         D2 = self.D * self.D
         return np.array([np.sum(np.exp(-(c * D2)[(c * D2) < thr])) for c in coef])
+    def moment_stats_rows(self):
+        q = (self.D * self.D).ravel()
+        nzm = q == 0
+        return np.array([q[~nzm].min() if np.any(~nzm) else np.inf, q.max(), float(nzm.sum()), float(q.size)])
+    def moment_accum_rows(self, coef, thr, plan):
+        from manifoldem_esper_b200 import moment_sweep as MSW
+        q = (self.D * self.D).ravel()
+        return MSW.accumulate_numpy(q, np.ones_like(q), plan, coef, thr)
     def degree_rows(self, eps):
         self.A = np.exp(-1. * ((self.D ** 2.) / (2. * eps)))
         return self.A.sum(axis=1)
@@ -80,13 +88,20 @@ g = np.load(os.path.join(%(root)r, 'tests', 'golden', 'stage23_medium.npz'))
 D = g['D']
 comm = rowblock.TorchComm()
 res = rowblock.embed_oversized(NumpyBackend(D), comm, D.shape[0], k=8)
+res_m = rowblock.embed_oversized(NumpyBackend(D), comm, D.shape[0], k=8, moments=True)
+wide = np.exp(np.random.default_rng(4).uniform(-12, 12, D.shape))          # more than 32 bins: returns to the general sweep
+bk = NumpyBackend(wide); bk.dist_rows(*rowblock.row_partition(D.shape[0], comm.rank, comm.world)[:2])
+_, path_wide = rowblock.sweep_sums(bk, comm, 1. / (2. * np.exp(np.arange(-100, 100.2, 0.2))), 10.0, moments=True)
 val_r, U_r = O.dmap_embed(D, res['eps'])
 err_val = float(np.max(np.abs(res['val'] - val_r[:8]) / val_r[:8]))
 err_vec = [float(min(np.abs(res['vec'][:, i] - U_r[:, i]).max(), np.abs(res['vec'][:, i] + U_r[:, i]).max())) for i in range(5)]
 L_r = O.eps_sweep_logsum(D, np.arange(-100, 100.2, 0.2), sequential=False)
 out = dict(rank=comm.rank, row0=res['row0'], nrows=res['nrows'], eps=res['eps'], eps_ref=float(g['eps']), steps=res['steps'],
            err_val=err_val, err_vec=err_vec, err_log=float(np.max(np.abs(res['logSumWij'] - L_r))),
-           val_hash=float(np.sum(res['val'])), vec_hash=float(np.sum(np.abs(res['vec']))))
+           val_hash=float(np.sum(res['val'])), vec_hash=float(np.sum(np.abs(res['vec']))),
+           sweep_path=res['sweep_path'], sweep_path_m=res_m['sweep_path'], path_wide=path_wide,
+           err_log_m=float(np.max(np.abs(res_m['logSumWij'] - L_r))), eps_m=res_m['eps'],
+           err_val_m=float(np.max(np.abs(res_m['val'] - res['val']) / res['val'])))
 print('RESULT ' + json.dumps(out), flush=True)
 dist.barrier()
 dist.destroy_process_group()
@@ -138,6 +153,10 @@ def test_two_rank_rowblock_embedding(tmp_path, lib_built):
     for o in outs:
         assert abs(o['eps'] - o['eps_ref']) / o['eps_ref'] < 2e-5      # different tanh-fit start than the golden run
         assert o['err_log'] < 1e-9 and o['err_val'] < 1e-9 and max(o['err_vec']) < 1e-6
+        # the moment sweep over row blocks (plan from all-reduced statistics, all-reduced tables) gives the same curve
+        assert o['sweep_path'] == 'general' and o['sweep_path_m'] == 'moments' and o['path_wide'] == 'general'
+        assert o['err_log_m'] < 1e-12                                  # the curve itself: 2e-15
+        assert abs(o['eps_m'] - o['eps']) / o['eps'] < 1e-7 and o['err_val_m'] < 1e-7   # the fit amplifies 1e-15 to ~1e-9
     # replicated state: both ranks end with the same numbers
     assert outs[0]['val_hash'] == outs[1]['val_hash'] and outs[0]['steps'] == outs[1]['steps']
     assert abs(outs[0]['vec_hash'] - outs[1]['vec_hash']) < 1e-9

@@ -55,6 +55,18 @@ with torch.cuda.stream(stream):
         print('mode=%s world=%d n=%d upload %.2fs embed %.3fs steps=%d eps=%.6f lam=%s' % (
             mode, world, n, t_up, t_all, res['steps'], res['eps'], np.array2string(np.sqrt(res['val']), precision=6)), flush=True)
         print('timings ' + ' '.join('%s=%.4f' % kv for kv in res['timings'].items()), flush=True)
+    if os.environ.get('ESPER_ROWBLOCK_MOMENTS', '0') != '0':
+        # opt-in (not yet run on hardware): the moment sweep over row blocks against the general sweep of the run above
+        rowblock.embed_oversized(be, comm, n, k=k, moments=True)
+        torch.cuda.synchronize(); dist.barrier()
+        t = time.time()
+        resm = rowblock.embed_oversized(be, comm, n, k=k, moments=True)
+        torch.cuda.synchronize(); dist.barrier()
+        if rank == 0:
+            fin = np.isfinite(res['logSumWij'])
+            print('moment sweep (%s): embed %.3fs sweep+fit %.4fs (general %.4fs); max |dlogSum| %.2e, eps %.9f vs %.9f' % (
+                resm['sweep_path'], time.time() - t, resm['timings']['sweep_fit_s'], res['timings']['sweep_fit_s'],
+                np.max(np.abs(resm['logSumWij'][fin] - res['logSumWij'][fin])), resm['eps'], res['eps']), flush=True)
     # the same embedding with the fused SYMV + peer-memory all-gather kernel instead of symv + NCCL all-gather
     bf = rowblock.CudaBackend(ctx, None, n, P, dev, fused=True)
     rowblock.embed_oversized(bf, comm, n, k=k)                 # warm-up (IPC mappings)
