@@ -396,13 +396,16 @@ int esper_dist_rms_rows(esper_ctx* c, const float* imgs, int n, int P, unsigned 
         return fail(c, ESPER_E_STATE, "dist_rms_rows: imgs == NULL but no resident [%d, %d] stack", n, P);
     }
     const int rows_pad = (int)round_up((size_t)n, 128);
-    const int ld = (int)round_up((size_t)P, 32);
+    int hs = -1;                                           // FP16 operand planes: opt-in, z-scored stacks only (see esper_dist_rms)
+    if (c->gram_mode == 1 && (flags & ESPER_DIST_STANDARDIZE)) hs = gram_f16_scale_log2(P);
+    const int ld = (int)round_up((size_t)P, hs >= 0 ? 64 : 32);
     ESPER_RESERVE(c, c->dist, sizeof(double) * (size_t)nrows * n);
     c->dist_m = 0;
-    int rc = run_prep(c, n, P, flags, rows_pad, ld);
+    int rc = run_prep(c, n, P, flags, rows_pad, ld, false, hs);
     if (rc) return rc;
-    rc = run_gram(c, n, P, rows_pad, ld, flags, row0, nrows);
+    rc = run_gram(c, n, P, rows_pad, ld, flags, row0, nrows, nullptr, hs);
     if (rc) return rc;
+    c->gram_last_f16 = hs >= 0 ? 1 : 0;
     c->dist_m = n; c->dist_rows = nrows; c->dist_row0 = row0; c->dist_symmetric = 0;
     if (D_rows) {
         ESPER_CUDA(c, cudaMemcpyAsync(D_rows, c->dist.p, sizeof(double) * (size_t)nrows * n, cudaMemcpyDeviceToHost, c->stream));

@@ -361,6 +361,23 @@ gram_wide_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
 //   part: [split_k * n_tiles] tiles of 128x128 FP32 in "tile-native" order: element (r, c) of a
 //         tile lives at ((c>>2)*128 + r)*4 + (c&3)  (so that a warp's 32 rows store 512 contiguous B)
 // ------------------------------------------------------------------------------------------------
+constexpr uint32_t IDESC_H = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC_H), "r"(accumulate)
+        : "memory");
+}
+template <bool F16>
+__device__ __forceinline__ void umma_sq(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    if (F16) umma_f16(tmem_d, adesc, bdesc, accumulate); else umma_tf32(tmem_d, adesc, bdesc, accumulate);
+}
+
+// F16 = true: FP16 operand planes (see gram_wide_kernel<true>); used by the row-block path when esper_gram_config(ctx, 1).
+template <bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gram_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
             const __grid_constant__ CUtensorMap mapb_hi, const __grid_constant__ CUtensorMap mapb_lo,
@@ -381,6 +398,7 @@ gram_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int total_units = n_tiles * split_k;
+    constexpr int BKE = F16 ? BK_H : BK;                                // elements per k-block (one 128-byte row)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_hi);
@@ -415,11 +433,11 @@ gram_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
                     const uint32_t sa = base + stage * STAGE_BYTES;
                     const uint32_t fb = full_bar + 8 * stage;
                     mbar_expect_tx(fb, diag ? 2 * TILE_BYTES : 4 * TILE_BYTES);
-                    tma_load_2d(sa, &map_hi, fb, kb * BK, ti * BM);
-                    tma_load_2d(sa + TILE_BYTES, &map_lo, fb, kb * BK, ti * BM);
+                    tma_load_2d(sa, &map_hi, fb, kb * BKE, ti * BM);
+                    tma_load_2d(sa + TILE_BYTES, &map_lo, fb, kb * BKE, ti * BM);
                     if (!diag) {
-                        tma_load_2d(sa + 2 * TILE_BYTES, &mapb_hi, fb, kb * BK, tj * BN);
-                        tma_load_2d(sa + 3 * TILE_BYTES, &mapb_lo, fb, kb * BK, tj * BN);
+                        tma_load_2d(sa + 2 * TILE_BYTES, &mapb_hi, fb, kb * BKE, tj * BN);
+                        tma_load_2d(sa + 3 * TILE_BYTES, &mapb_lo, fb, kb * BKE, tj * BN);
                     }
                 }
                 __syncwarp();
@@ -457,9 +475,9 @@ gram_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
 #pragma unroll
                         for (int k = 0; k < BK / UK; ++k) {
                             const uint64_t off = (uint64_t)((k * UK * 4) >> 4);   // 32 bytes per UMMA K step, in 16-byte units
-                            umma_tf32(tmem_d, dal0 + off, dbh0 + off, (kb > g0 || k > 0) ? 1u : 0u);   // small cross terms first
-                            umma_tf32(tmem_d, dah0 + off, dbl0 + off, 1);
-                            umma_tf32(tmem_d, dah0 + off, dbh0 + off, 1);
+                            umma_sq<F16>(tmem_d, dal0 + off, dbh0 + off, (kb > g0 || k > 0) ? 1u : 0u);   // small cross terms first
+                            umma_sq<F16>(tmem_d, dah0 + off, dbl0 + off, 1);
+                            umma_sq<F16>(tmem_d, dah0 + off, dbh0 + off, 1);
                         }
                         umma_commit(empty_bar + 8 * stage);            // frees the smem stage when the MMAs retire
                         if (kb == g1 - 1) umma_commit(tfull_bar + 8 * acc);   // group complete -> epilogue drains it
@@ -772,7 +790,8 @@ int run_product(esper_ctx* c, float* a_hi, float* a_lo, int na, float* b_hi, flo
     if ((rc = make_plane_map(c, &mb_hi, b_hi, b_pad, ld))) return rc;
     if ((rc = make_plane_map(c, &mb_lo, b_lo, b_pad, ld))) return rc;
     if (!c->attr_gram) {
-        ESPER_CUDA(c, cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        ESPER_CUDA(c, cudaFuncSetAttribute(gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        ESPER_CUDA(c, cudaFuncSetAttribute(gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         c->attr_gram = true;
     }
     const size_t tile_bytes = (size_t)BM * BN * sizeof(float);
@@ -794,7 +813,7 @@ int run_product(esper_ctx* c, float* a_hi, float* a_lo, int na, float* b_hi, flo
         const int grid = units < sms ? units : sms;
         {
             LaunchScope ls(c, "gram");
-            gram_kernel<<<grid, NUM_THREADS, SMEM_BYTES, c->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, sym ? nta : ntb, nbt, tile0,
+            gram_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, c->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, sym ? nta : ntb, nbt, tile0,
                                                                        sym ? -1 : FULL_RECT, nkb, sk, drain_kb, part);
         }
         {
@@ -821,8 +840,8 @@ int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, i
     const RowStat* st = c->row_stats.as<RowStat>();
     double* D = c->dist.as<double>();
     const double gscale = f16 ? ldexp(1.0, -2 * half_scale_log2) : 1.0;
-    if (f16 && (rect || gram_out || nt < 2))
-        return fail(c, ESPER_E_STATE, "gram: the FP16 operand path covers the full symmetric distance matrix only");
+    if (f16 && (gram_out || (!rect && nt < 2)))
+        return fail(c, ESPER_E_STATE, "gram: the FP16 operand path covers distance matrices (full symmetric, or row blocks) only");
 
     CUtensorMap map_hi, map_lo;
     int rc = f16 ? make_plane_map_h(c, &map_hi, c->plane_hi.p, rows_pad, ld, BM) : make_plane_map(c, &map_hi, c->plane_hi.as<float>(), rows_pad, ld);
@@ -831,7 +850,8 @@ int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, i
     if (rc) return rc;
 
     if (!c->attr_gram) {
-        ESPER_CUDA(c, cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        ESPER_CUDA(c, cudaFuncSetAttribute(gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        ESPER_CUDA(c, cudaFuncSetAttribute(gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         c->attr_gram = true;
     }
 
@@ -844,7 +864,7 @@ int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, i
     // (the wide kernel became the default in the last GPU minutes of round 1; only the distance epilogue was exercised);
     // ESPER_GRAM_WIDE=2 enables it there too.
     const bool wide_gram_ok = !gram_out || (wide_env && atoi(wide_env) == 2);
-    const bool wide = f16 || (!rect && nt >= 2 && !(wide_env && atoi(wide_env) == 0) && drain_kb > 0 && wide_gram_ok);
+    const bool wide = (f16 && !rect) || (!rect && nt >= 2 && !(wide_env && atoi(wide_env) == 0) && drain_kb > 0 && wide_gram_ok);
     if (f16 && drain_kb < 1) drain_kb = 2;
 
     // Bound the split-K workspace: process the triangle in batches of tiles.
@@ -913,12 +933,13 @@ int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, i
         const int grid = units < sms ? units : sms;
         {
             LaunchScope ls(c, "gram");
-            gram_kernel<<<grid, NUM_THREADS, SMEM_BYTES, c->stream>>>(map_hi, map_lo, map_hi, map_lo, nt, nb, tile0, rect_ti0, nkb, sk, drain_kb, part);
+            if (f16) gram_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, c->stream>>>(map_hi, map_lo, map_hi, map_lo, nt, nb, tile0, rect_ti0, nkb, sk, drain_kb, part);
+            else gram_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, c->stream>>>(map_hi, map_lo, map_hi, map_lo, nt, nb, tile0, rect_ti0, nkb, sk, drain_kb, part);
         }
         {
             LaunchScope ls(c, "dist_finalize");
             if (gram_out) gram_finalize_kernel<<<dim3(nb, 8), 256, 0, c->stream>>>(part, nt, nb, tile0, -1, sk, n, st, gram_out);
-            else dist_finalize_kernel<<<dim3(nb, 8), 256, 0, c->stream>>>(part, nt, nb, tile0, rect_ti0, sk, n, P, st, 1.0, D);
+            else dist_finalize_kernel<<<dim3(nb, 8), 256, 0, c->stream>>>(part, nt, nb, tile0, rect_ti0, sk, n, P, st, gscale, D);
         }
     }
     ESPER_CUDA(c, cudaGetLastError());

@@ -202,6 +202,23 @@ def test_f16_operands_tile_and_k_tails(f16_operands, n, P):
 
 
 @experimental
+def test_f16_operands_row_block_equals_full(f16_operands):
+    """Row-block path with FP16 planes (gram_kernel<true>): every block holds the same bits as the rows of the full matrix."""
+    ctx = f16_operands
+    X = np.random.default_rng(11).standard_normal((700, 3000)).astype(np.float32)
+    ctx.dist_config(split_k=4)
+    try:
+        D = ctx.dist_rms(X)
+        assert ctx.gram_info() == 1
+        for row0, nrows in [(0, 256), (256, 384), (640, 60)]:
+            Dr = ctx.dist_rms_rows(X, 700, 3000, row0, nrows, download=True)
+            assert ctx.gram_info() == 1 and np.array_equal(Dr, D[row0:row0 + nrows])
+    finally:
+        ctx.dist_config(split_k=0)
+    assert d_err(D, O.distances_gram_f64(O.standardize_stack(X.reshape(700, 1, 3000)))) < D_TOL
+
+
+@experimental
 def test_f16_operands_fall_back_where_the_range_is_not_bounded(f16_operands):
     ctx = f16_operands
     X = np.random.default_rng(5).standard_normal((300, 999)).astype(np.float32) * 3e6 + 1
