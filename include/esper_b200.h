@@ -90,9 +90,9 @@ int esper_dist_config(esper_ctx* ctx, int split_k, double refine_tau);
 /* Operand format of the stage-1 tensor-core contraction.  mode 0 (default): 3xTF32 -- every centred z-score c is split into
  * two TF32 values, hi*hi + hi*lo + lo*hi accumulate in FP32.  mode 1: 3xFP16 -- the same split into two FP16 values of
  * c * 2^s (an FP16 significand has the same 11 bits as a TF32 one; s is chosen from P so that |c| <= 2 sqrt(P) stays in
- * range), tcgen05 kind::f16 at twice the TF32 rate with half the operand bytes; used for esper_dist_rms with
- * ESPER_DIST_STANDARDIZE on stacks of more than 128 images, the 3xTF32 path otherwise (unstandardised input, PCA, CTF
- * branch, row blocks).  Experimental this round: ESPER_GRAM_F16=1 sets the initial mode of new contexts.
+ * range), tcgen05 kind::f16 at twice the TF32 rate with half the operand bytes; used for esper_dist_rms (stacks of more
+ * than 128 images) and esper_dist_rms_rows with ESPER_DIST_STANDARDIZE, the 3xTF32 path otherwise (unstandardised input,
+ * PCA, CTF branch).  Experimental this round: ESPER_GRAM_F16=1 sets the initial mode of new contexts.
  * esper_gram_info: operand format the last esper_dist_rms used (0 TF32, 1 FP16). */
 int esper_gram_config(esper_ctx* ctx, int mode);
 int esper_gram_info(esper_ctx* ctx, int* last_operands);
