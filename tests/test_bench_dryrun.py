@@ -140,6 +140,7 @@ def test_bench_gpu_arm_dry_run(monkeypatch, flags):
     for key in ('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'):
         assert key in d['roofline'], key
     assert d['roofline']['bound'] == 'tensor' and d['roofline']['launches_timed'] == 4 and abs(d['roofline']['avg_launch_ms'] - 1.1) < 1e-9
+    assert d['roofline']['launches_pipelined'] == 4 and abs(d['roofline']['avg_launch_ms_pipelined'] - 1.1) < 1e-9
     assert abs(d['roofline']['frac'] - d['roofline']['achieved'] / d['roofline']['peak']) < 1e-12
     for key in ('value', 'unit', 'cores', 'kind', 'sample'):
         assert key in d['cpu_baseline'], key
