@@ -6,7 +6,9 @@
   * moment sweep                                  esper_sweep_config(ctx, 1)   moment_{stats,plan,accum,final}_kernel
   * eigensolver schedule without speculation      esper_dmap_config(ctx, 2)    host control flow of lanczos_attempt only
 
-    gpurun --timeout 400 -- 'timeout 300 python tools/experimental_check.py [gram|sweep|eig]'
+    gpurun --timeout 900 -- 'for w in gram prep sweep eig; do timeout 200 python tools/experimental_check.py $w; done'
+
+(one process per stage: a device fault in one kernel does not take the later stages with it)
 
 Every stage prints before the next starts (flush), small shapes first, so a hang or fault is attributable.  Then:
 
@@ -77,7 +79,9 @@ if what in ('all', 'gram'):
                                                                    ctx.kernel_ms('gram')[0] / 5, ctx.kernel_ms('dist_finalize')[0] / 5), flush=True)
     ctx.set_profiling(False)
     ctx.gram_config(0)
+if what in ('all', 'prep'):
     print('== cluster standardise-and-split pass ==', flush=True)
+    X = synth.synthetic_pd(pd=3, box=250, n_side=20, tau=5, snr=0.1).reshape(2000, 62500)
     for n, P in [(70, 999), (300, 16384), (2000, 62500)]:
         Xc = X if n == 2000 else rng.standard_normal((n, P), dtype=np.float32)
         ctx.prep_config(0)
