@@ -25,12 +25,15 @@ static EmuDim blockDim, gridDim;
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
-#define __shared__ static
+#ifndef EMU_ARENA_SHARED
+#define __shared__ static       // one block at a time: a function-local static is the block's shared variable
+#endif
 
 static std::unique_ptr<std::barrier<>> emu_block_bar;
 static std::vector<std::unique_ptr<std::barrier<>>> emu_warp_bar;
 static double emu_slots[32][32];
 
+#ifndef EMU_ARENA_SHARED
 inline void __syncthreads() { emu_block_bar->arrive_and_wait(); }
 inline double __shfl_xor_sync(unsigned, double v, int o) {
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -40,17 +43,149 @@ inline double __shfl_xor_sync(unsigned, double v, int o) {
     emu_warp_bar[w]->arrive_and_wait();
     return r;
 }
+#else
+namespace emu2 { inline void syncthreads(); inline double shfl_xor(double v, int o); }
+inline void __syncthreads() { emu2::syncthreads(); }
+inline double __shfl_xor_sync(unsigned, double v, int o) { return emu2::shfl_xor(v, o); }
+#endif
 inline double __ldg(const double* p) { return *p; }
+inline float __ldg(const float* p) { return *p; }
+struct float4 { float x, y, z, w; };
+struct uint2 { uint32_t x, y; };
+inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
+inline float4 __ldg(const float4* p) { return *p; }
+inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+inline uint32_t emu_f2u(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+inline float emu_u2f(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+// IEEE binary16, round to nearest even (what __float2half_rn does), subnormals and overflow to infinity included
+struct __half { uint16_t bits; };
+inline __half __float2half_rn(float f) {
+    const uint32_t u = emu_f2u(f), sign = (u >> 16) & 0x8000u;
+    const int32_t e = (int32_t)((u >> 23) & 0xFF) - 127;
+    uint32_t man = u & 0x7FFFFFu;
+    __half h;
+    if (((u >> 23) & 0xFF) == 0xFF) { h.bits = (uint16_t)(sign | 0x7C00u | (man ? 0x200u : 0)); return h; }
+    if (e > 15) { h.bits = (uint16_t)(sign | 0x7C00u); return h; }
+    if (e >= -14) {                                        // normal half
+        uint32_t m10 = man >> 13, rest = man & 0x1FFFu, he = (uint32_t)(e + 15);
+        uint32_t v = (he << 10) | m10;
+        if (rest > 0x1000u || (rest == 0x1000u && (m10 & 1))) ++v;       // carries into the exponent correctly
+        h.bits = (uint16_t)(sign | v);
+        return h;
+    }
+    if (e < -25) { h.bits = (uint16_t)sign; return h; }      // below half the smallest subnormal
+    man |= 0x800000u;                                        // subnormal: shift the 24-bit significand
+    const int shift = -14 - e + 13;
+    uint32_t m = man >> shift, rest = man & ((1u << shift) - 1), half = 1u << (shift - 1);
+    if (rest > half || (rest == half && (m & 1))) ++m;
+    h.bits = (uint16_t)(sign | m);
+    return h;
+}
+inline float __half2float(__half h) {
+    const uint32_t sign = (uint32_t)(h.bits & 0x8000u) << 16, e = (h.bits >> 10) & 0x1Fu, m = h.bits & 0x3FFu;
+    if (e == 0x1F) return emu_u2f(sign | 0x7F800000u | (m << 13));
+    if (e == 0) { const float v = std::ldexp((float)m, -24); return sign ? -v : v; }
+    return emu_u2f(sign | ((e + 112) << 23) | (m << 13));
+}
+inline unsigned short __half_as_ushort(__half h) { return h.bits; }
 inline long long __double_as_longlong(double d) { long long r; std::memcpy(&r, &d, 8); return r; }
 inline double __longlong_as_double(long long v) { double r; std::memcpy(&r, &v, 8); return r; }
 inline int min(int a, int b) { return a < b ? a : b; }
 
+#ifndef EMU_NO_WARP_SUM
 namespace esper {
 inline double warp_sum(double v) {                 // devutil.cuh: xor-shuffle tree, 16 down to 1
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 }  // namespace esper
+#endif
+
+// ---- second model (EMU_ARENA_SHARED): blocks of a thread-block cluster run CONCURRENTLY, so shared memory is a per-block
+// arena; the test rewrites `__shared__ T name[N];` into `T* name = emu_smem<T>(N);` (same allocation order in every thread ->
+// same offsets) and `extern __shared__ T name[];` into `T* name = emu_dyn<T>();`.  map_shared_rank translates an address of
+// this block's arena into the peer's, which is what distributed shared memory does.
+constexpr size_t EMU_STATIC_BYTES = 16 * 1024;
+static thread_local char* emu_arena = nullptr;
+static thread_local size_t emu_off = 0;
+static std::vector<std::vector<char>> emu_arenas;          // one per block of the running cluster
+static thread_local unsigned emu_cluster_rank = 0;
+static unsigned emu_cluster_size = 1;
+static std::unique_ptr<std::barrier<>> emu_cluster_bar;
+static std::vector<std::unique_ptr<std::barrier<>>> emu_block_bars;
+static thread_local std::barrier<>* emu_my_block_bar = nullptr;
+static thread_local std::barrier<>* emu_my_warp_bar = nullptr;
+static thread_local double* emu_my_slots = nullptr;
+
+template <class T> T* emu_smem(size_t n) {
+    emu_off = (emu_off + 15) & ~size_t(15);
+    T* p = reinterpret_cast<T*>(emu_arena + emu_off);
+    emu_off += n * sizeof(T);
+    if (emu_off > EMU_STATIC_BYTES) { fprintf(stderr, "emu: static shared memory exhausted\n"); abort(); }
+    return p;
+}
+template <class T> T* emu_dyn() { return reinterpret_cast<T*>(emu_arena + EMU_STATIC_BYTES); }
+
+#ifdef EMU_ARENA_SHARED
+#undef EMU_SYNC_DEFINED
+namespace emu2 {
+inline void syncthreads() { emu_my_block_bar->arrive_and_wait(); }
+inline double shfl_xor(double v, int o) {
+    const int l = threadIdx.x & 31;
+    emu_my_slots[l] = v;
+    emu_my_warp_bar->arrive_and_wait();
+    const double r = emu_my_slots[l ^ o];
+    emu_my_warp_bar->arrive_and_wait();
+    return r;
+}
+}  // namespace emu2
+namespace cooperative_groups {
+struct cluster_group {
+    unsigned num_blocks() const { return emu_cluster_size; }
+    unsigned block_rank() const { return emu_cluster_rank; }
+    void sync() const { emu_cluster_bar->arrive_and_wait(); }
+    template <class T> T* map_shared_rank(T* p, unsigned r) const {
+        return reinterpret_cast<T*>(emu_arenas[r].data() + (reinterpret_cast<char*>(p) - emu_arena));
+    }
+};
+inline cluster_group this_cluster() { return cluster_group(); }
+}  // namespace cooperative_groups
+
+// grid blocks of `threads` threads in clusters of `cs` consecutive blocks (cs = 1: plain launch); dyn = dynamic shared bytes.
+template <class K, class... A>
+void emu_launch_cluster(int grid, int threads, int cs, size_t dyn, K kernel, A... args) {
+    gridDim.x = (unsigned)grid; blockDim.x = (unsigned)threads;
+    emu_cluster_size = (unsigned)cs;
+    const int warps = (threads + 31) / 32;
+    static std::vector<double> slots;
+    for (int c0 = 0; c0 < grid; c0 += cs) {
+        emu_arenas.assign(cs, std::vector<char>(EMU_STATIC_BYTES + dyn + 64, 0));
+        emu_cluster_bar = std::make_unique<std::barrier<>>(cs * threads);
+        emu_block_bars.clear();
+        std::vector<std::unique_ptr<std::barrier<>>> wbars;
+        slots.assign((size_t)cs * warps * 32, 0.0);
+        for (int r = 0; r < cs; ++r) {
+            emu_block_bars.push_back(std::make_unique<std::barrier<>>(threads));
+            for (int w = 0; w < warps; ++w) wbars.push_back(std::make_unique<std::barrier<>>(std::min(32, threads - 32 * w)));
+        }
+        std::vector<std::thread> th;
+        for (int r = 0; r < cs; ++r)
+            for (int t = 0; t < threads; ++t)
+                th.emplace_back([=, &wbars]() {
+                    threadIdx.x = (unsigned)t; blockIdx.x = (unsigned)(c0 + r);
+                    emu_cluster_rank = (unsigned)r;
+                    emu_arena = emu_arenas[r].data(); emu_off = 0;
+                    emu_my_block_bar = emu_block_bars[r].get();
+                    emu_my_warp_bar = wbars[(size_t)r * warps + (t >> 5)].get();
+                    emu_my_slots = slots.data() + ((size_t)r * warps + (t >> 5)) * 32;
+                    kernel(args...);
+                });
+        for (auto& x : th) x.join();
+    }
+}
+#endif
 
 // Run kernel(args...) on a grid of `grid` blocks of `threads` threads, one block after the other.
 template <class K, class... A>

@@ -103,3 +103,105 @@ def test_moment_kernels_on_the_cpu_full_matrix_row_block_and_limits(emu_bin):
         r = run_emu(emu_bin, Dm, coef, 10.0, sym=True)
         L_np, _ = MSW.sweep_numpy(Dm, coef, 10.0)
         assert r['status'] == 0 and np.allclose(r['logsum'], L_np, rtol=0, atol=1e-12), m
+
+
+# ---- K0: stats_split_kernel<HALF> and the cluster variant ---------------------------------------------------------------
+K0 = os.path.join(ROOT, 'manifoldem_esper_b200', 'csrc', 'k0_prep.cu')
+DEVUTIL = os.path.join(ROOT, 'manifoldem_esper_b200', 'csrc', 'devutil.cuh')
+
+
+def arena_shared(text):
+    import re
+    text = re.sub(r'extern\s+__shared__\s+(\w+)\s+(\w+)\[\];', r'\1* \2 = emu_dyn<\1>();', text)
+    return re.sub(r'__shared__\s+(\w+)\s+(\w+)\[([^\]]+)\];', r'\1* \2 = emu_smem<\1>(\3);', text)
+
+
+@pytest.fixture(scope='module')
+def prep_bin(tmp_path_factory):
+    d = tmp_path_factory.mktemp('emu_prep')
+    dev = open(DEVUTIL).read()
+    (d / 'devutil_body.inc').write_text(cut(dev, 'struct RowStat', '}  // namespace esper'))
+    src = open(K0).read()
+    parts = [cut(src, '__device__ __forceinline__ void row_stats(', '// Statistics of the images i = blockIdx.x * stride'),
+             cut(src, 'template <bool HALF>\n__global__ void __launch_bounds__(512) stats_split_kernel', '// Cluster variant of stats_split_kernel'),
+             cut(src, 'namespace cg = cooperative_groups;', '// ------------------------------------------------------------------------------------------------\n// numpy-exact float32 statistics.')]
+    text = arena_shared('\n'.join(parts))
+    assert '__shared__' not in text and 'stats_split_cluster_kernel' in text and 'emu_dyn<float4>' in text
+    (d / 'prep_kernels.inc').write_text(text)
+    exe = str(d / 'prep_emu')
+    cmd = ['g++', '-O1', '-std=c++20', '-pthread', '-ffp-contract=off', '-Wno-unknown-pragmas', '-I', EMU, '-I', str(d),
+           os.path.join(EMU, 'prep_emu.cpp'), '-o', exe]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-4000:]
+    return exe, d
+
+
+def tf32_rna(x):
+    b = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    return ((b + 0x1000) & 0xFFFFE000).astype(np.uint32).view(np.float32)
+
+
+def run_prep(prep_bin, raw, ld, standardize, xbar, half, scale_log2, cs):
+    exe, d = prep_bin
+    n, P = raw.shape
+    raw.astype(np.float32).tofile(str(d / 'raw.bin'))
+    xb = '-'
+    if xbar is not None:
+        xbar.astype(np.float32).tofile(str(d / 'xbar.bin'))
+        xb = str(d / 'xbar.bin')
+    res = subprocess.run([exe, str(d / 'raw.bin'), str(n), str(P), str(ld), str(int(standardize)), xb, str(int(half)),
+                          repr(float(2.0 ** scale_log2)), str(cs), str(d / 'hi.bin'), str(d / 'lo.bin'), str(d / 'st.bin')],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stderr[-2000:]
+    dt = np.float16 if half else np.float32
+    hi = np.fromfile(str(d / 'hi.bin'), dtype=dt).reshape(n, ld)
+    lo = np.fromfile(str(d / 'lo.bin'), dtype=dt).reshape(n, ld)
+    st = np.fromfile(str(d / 'st.bin')).reshape(n, 3)
+    return hi, lo, st
+
+
+def expected_planes(raw, st, xbar, standardize, half, scale_log2, ld):
+    """The kernel's arithmetic from ITS mean32 / std32: z = fl32(fl32(x - mean) / std), c = fl32(z - xbar), split."""
+    n, P = raw.shape
+    mean, std = st[:, 0].astype(np.float32)[:, None], st[:, 1].astype(np.float32)[:, None]
+    z = ((raw - mean).astype(np.float32) / std).astype(np.float32) if standardize else raw.astype(np.float32)
+    c = (z - xbar[None, :]).astype(np.float32) if xbar is not None else z
+    if half:
+        cs_ = (c * np.float32(2.0 ** scale_log2)).astype(np.float32)
+        h = cs_.astype(np.float16)
+        l = (cs_ - h.astype(np.float32)).astype(np.float32).astype(np.float16)
+    else:
+        h = tf32_rna(c)
+        l = tf32_rna((c - h).astype(np.float32))
+    H = np.zeros((n, ld), dtype=h.dtype); L = np.zeros((n, ld), dtype=h.dtype)
+    H[:, :P] = h; L[:, :P] = l
+    return H, L, np.sum(c.astype(np.float64) ** 2, axis=1)
+
+
+@pytest.mark.parametrize('half', [0, 1])
+@pytest.mark.parametrize('P,cs', [(1000, 0), (1000, 1), (999, 2), (1000, 4), (250, 8), (7, 4)])
+def test_split_kernels_on_the_cpu(prep_bin, P, cs, half):
+    rng = np.random.default_rng(P + 10 * cs + half)
+    n = 5
+    raw = (rng.standard_normal((n, P)) * 2.5 + 0.7).astype(np.float32)
+    raw[1, 3] = 400.0                                                         # an outlier pixel: a large z-score
+    xbar = (rng.standard_normal(P) * 0.1).astype(np.float32)
+    ld = -(-P // (64 if half else 32)) * (64 if half else 32)
+    s = 6
+    for standardize, xb in ((1, xbar), (1, None), (0, xbar)):
+        hi, lo, st = run_prep(prep_bin, raw, ld, standardize, xb, half, s, cs)
+        if standardize:
+            m64, s64 = raw.astype(np.float64).mean(axis=1), raw.astype(np.float64).std(axis=1)
+            assert np.all(np.abs(st[:, 0] - m64) <= 2e-7 * np.abs(m64) + 1e-9) and np.all(np.abs(st[:, 1] - s64) <= 2e-7 * s64)
+        else:
+            assert np.all(st[:, 0] == 0) and np.all(st[:, 1] == 1)
+        H, L, nrm = expected_planes(raw, st, xb, standardize, half, s, ld)
+        assert np.array_equal(hi.view(np.uint16 if half else np.uint32), H.view(np.uint16 if half else np.uint32))
+        assert np.array_equal(lo.view(np.uint16 if half else np.uint32), L.view(np.uint16 if half else np.uint32))
+        assert np.allclose(st[:, 2], nrm, rtol=1e-13, atol=0)
+        # hi + lo carries 22 bits of the centred z-score
+        c = (H.astype(np.float64) + L.astype(np.float64))[:, :P] / (2.0 ** s if half else 1.0)
+        z = ((raw - st[:, 0].astype(np.float32)[:, None]).astype(np.float32) / st[:, 1].astype(np.float32)[:, None]).astype(np.float32) if standardize else raw
+        cref = (z - xb[None, :]).astype(np.float32) if xb is not None else z
+        floor = 2.0 ** -25 / 2.0 ** s if half else 0.0                        # half the FP16 subnormal spacing, unscaled
+        assert np.all(np.abs(c - cref) <= 2.0 ** -22 * np.abs(cref) + floor)
