@@ -6,8 +6,9 @@ On one GPU the plan and the final evaluation run on the device (moment_plan_kern
 distance matrix is split by row blocks over several ranks, the bins must be the same everywhere, so the plan is made
 here from the all-reduced statistics (min / max of the non-zero q, weight of the exact zeros), every rank accumulates
 the moments and boundary sums of its rows against that plan (`esper_moment_accum_rows`), the [bins, values] table is
-all-reduced and `finalize` evaluates the 1001 sums.  `plan` / `finalize` follow the two kernels statement by statement;
-`accumulate_numpy` is the numpy statement of moment_accum_kernel (CPU tests, tools/sweep_moments_proto.py).
+all-reduced and `finalize` evaluates the 1001 sums.  `plan` / `finalize` follow the two kernels statement by statement.
+There is no CPU path for the per-element work here: the numpy statement of moment_accum_kernel used by the CPU tests lives
+in tools/sweep_moments_proto.py (test infrastructure).
 """
 from __future__ import annotations
 
@@ -71,29 +72,6 @@ def plan(mn, mx, zero_weight, valid_weight, coef, thr):
     return status, out
 
 
-def accumulate_numpy(q, w, plan_arr, coef, thr):
-    """numpy statement of moment_accum_kernel: q, w flat arrays of D^2 values and weights -> table [MB, MV]."""
-    coef = np.asarray(coef, dtype=np.float64)
-    tot = np.zeros((MB, MV))
-    ok = (q == q) & (q != 0)
-    q, w = q[ok], w[ok]
-    for b in range(int(plan_arr[1])):
-        lo, hi, mu, sc, ka, kf = plan_arr[PLAN_HDR + PLAN_BIN * b: PLAN_HDR + PLAN_BIN * (b + 1)]
-        sel = (q >= lo) & (q < hi)
-        qb, wb = q[sel], w[sel]
-        u = (qb - mu) * sc
-        pw = wb.copy()
-        tot[b, 0] = pw.sum()
-        for p in range(1, MP + 1):
-            pw = pw * u
-            tot[b, p] = pw.sum()
-        for s in range(int(kf) - int(ka)):
-            t = coef[int(ka) + s] * qb
-            keep = t < thr
-            tot[b, MP + 1 + s] = np.sum(wb[keep] * np.exp(-t[keep]))
-    return tot
-
-
 def finalize(plan_arr, tot, coef, thr):
     """moment_final_kernel: plan + (all-reduced) table [MB, MV] -> S[k] for every coefficient (not the logarithm)."""
     coef = np.asarray(coef, dtype=np.float64)
@@ -113,30 +91,6 @@ def finalize(plan_arr, tot, coef, thr):
                 poly = poly * (x / (p + 1)) + M[p]
             S[kf:] += np.exp(-(c * mu)) * poly
     return S
-
-
-def sweep_numpy(D, coef, thr, symmetric=True):
-    """The whole moment sweep on the host (CPU tests): -> (logSum[k] or None, status or number of bins)."""
-    D = np.asarray(D, dtype=np.float64)
-    m = D.shape[0]
-    if symmetric:
-        iu = np.triu_indices(m)
-        q = (D * D)[iu]
-        w = np.where(iu[0] == iu[1], 1.0, 2.0)
-    else:
-        q = (D * D).ravel()
-        w = np.ones_like(q)
-    ok = q == q
-    q, w = q[ok], w[ok]
-    nzm = q == 0
-    mn = q[~nzm].min() if np.any(~nzm) else np.inf
-    mx = q.max() if q.size else 0.0
-    status, pl = plan(mn, mx, w[nzm].sum(), w.sum(), coef, thr)
-    if status:
-        return None, status
-    S = finalize(pl, accumulate_numpy(q, w, pl, coef, thr), coef, thr)
-    with np.errstate(divide='ignore'):
-        return np.log(S), int(pl[1])
 
 
 def check_layout(lib):

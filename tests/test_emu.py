@@ -10,6 +10,17 @@ import pytest
 
 from conftest import ROOT, golden
 from manifoldem_esper_b200 import moment_sweep as MSW
+
+
+def _proto():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('sweep_moments_proto', os.path.join(ROOT, 'tools', 'sweep_moments_proto.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+PROTO = _proto()
 from oracle import esper_oracle as O
 
 SRC = os.path.join(ROOT, 'manifoldem_esper_b200', 'csrc', 'k2_sweep.cu')
@@ -60,7 +71,7 @@ def test_moment_kernels_on_the_cpu_vs_reference_golden(emu_bin, name):
     coef = 1. / (2. * np.exp(LOG_EPS))
     ref = g['logSumWij'] if 'logSumWij' in g else O.eps_sweep_logsum(D, LOG_EPS)
     r = run_emu(emu_bin, D, coef, 10.0, sym=True)
-    L_np, bins_np = MSW.sweep_numpy(D, coef, 10.0)
+    L_np, bins_np = PROTO.sweep_numpy(D, coef, 10.0)
     assert r['status'] == 0 and r['bins'] == bins_np
     fin = np.isfinite(ref)
     assert np.array_equal(np.isfinite(r['logsum']), fin)
@@ -88,7 +99,7 @@ def test_moment_kernels_on_the_cpu_full_matrix_row_block_and_limits(emu_bin):
     q = (blk * blk).ravel()
     st, pl = MSW.plan(q[q != 0].min(), q.max(), float((q == 0).sum()), float(q.size), coef, 10.0)
     assert st == 0 and np.array_equal(r['plan'][:8 + 6], pl[:8 + 6])
-    tab = MSW.accumulate_numpy(q, np.ones_like(q), pl, coef, 10.0)
+    tab = PROTO.accumulate_numpy(q, np.ones_like(q), pl, coef, 10.0)
     assert np.allclose(r['table'], tab, rtol=1e-13, atol=1e-13)
     # more than 32 bins / too many coefficients per bin: status tells the host to run the general kernel
     W = np.exp(rng.uniform(-12, 12, (40, 40)))
@@ -101,7 +112,7 @@ def test_moment_kernels_on_the_cpu_full_matrix_row_block_and_limits(emu_bin):
         Dm = 0.5 * (Dm + Dm.T)
         np.fill_diagonal(Dm, 0.0)
         r = run_emu(emu_bin, Dm, coef, 10.0, sym=True)
-        L_np, _ = MSW.sweep_numpy(Dm, coef, 10.0)
+        L_np, _ = PROTO.sweep_numpy(Dm, coef, 10.0)
         assert r['status'] == 0 and np.allclose(r['logsum'], L_np, rtol=0, atol=1e-12), m
 
 

@@ -38,9 +38,11 @@ class NumpyBackend:
         nzm = q == 0
         return np.array([q[~nzm].min() if np.any(~nzm) else np.inf, q.max(), float(nzm.sum()), float(q.size)])
     def moment_accum_rows(self, coef, thr, plan):
-        from manifoldem_esper_b200 import moment_sweep as MSW
+        import importlib.util
+        spec = importlib.util.spec_from_file_location('sweep_moments_proto', os.path.join(%(root)r, 'tools', 'sweep_moments_proto.py'))
+        proto = importlib.util.module_from_spec(spec); spec.loader.exec_module(proto)
         q = (self.D * self.D).ravel()
-        return MSW.accumulate_numpy(q, np.ones_like(q), plan, coef, thr)
+        return proto.accumulate_numpy(q, np.ones_like(q), plan, coef, thr)
     def degree_rows(self, eps):
         self.A = np.exp(-1. * ((self.D ** 2.) / (2. * eps)))
         return self.A.sum(axis=1)

@@ -7,9 +7,8 @@ ESPER_SWEEP_MOMENTS=1) and its error against the reference sweep (GaussianBandwi
 Non-zero q are grouped into geometric bins [e_b, e_b rho), rho = 1/(1 - 2/thr).  Per bin and k: nothing passes
 (c_k e_b >= thr), everything passes (c_k e_{b+1} < thr: 17 scaled moments about the bin centre give the sum, Taylor
 remainder <= e/17!), or the truncation boundary falls inside the bin (exact per-element evaluation; <= MS such k).
-The statement itself is manifoldem_esper_b200/moment_sweep.py (`plan`, `accumulate_numpy`, `finalize` follow
-moment_plan_kernel, moment_accum_kernel and moment_final_kernel line by line; the row-block path uses `plan` and `finalize`
-on the host).
+`accumulate_numpy` below follows moment_accum_kernel line by line; `plan` and `finalize` (moment_plan_kernel,
+moment_final_kernel) are the host functions of manifoldem_esper_b200/moment_sweep.py that the row-block path uses.
 
 Run: python tools/sweep_moments_proto.py [D.npy ...]   -> max |log S - reference| (tolerance of the tests: 1e-9)
 """
@@ -24,12 +23,60 @@ sys.path.insert(0, ROOT)
 
 from manifoldem_esper_b200 import moment_sweep as MSW  # noqa: E402  (the numpy statement lives with the host code that uses it)
 
-MP, MS, MB = MSW.MP, MSW.MS, MSW.MB
+MP, MS, MB, MV = MSW.MP, MSW.MS, MSW.MB, MSW.MV
+PLAN_HDR, PLAN_BIN = MSW.PLAN_HDR, MSW.PLAN_BIN
+
+
+def accumulate_numpy(q, w, plan_arr, coef, thr):
+    """numpy statement of moment_accum_kernel: q, w flat arrays of D^2 values and weights -> table [MB, MV]."""
+    coef = np.asarray(coef, dtype=np.float64)
+    tot = np.zeros((MB, MV))
+    ok = (q == q) & (q != 0)
+    q, w = q[ok], w[ok]
+    for b in range(int(plan_arr[1])):
+        lo, hi, mu, sc, ka, kf = plan_arr[PLAN_HDR + PLAN_BIN * b: PLAN_HDR + PLAN_BIN * (b + 1)]
+        sel = (q >= lo) & (q < hi)
+        qb, wb = q[sel], w[sel]
+        u = (qb - mu) * sc
+        pw = wb.copy()
+        tot[b, 0] = pw.sum()
+        for p in range(1, MP + 1):
+            pw = pw * u
+            tot[b, p] = pw.sum()
+        for s in range(int(kf) - int(ka)):
+            t = coef[int(ka) + s] * qb
+            keep = t < thr
+            tot[b, MP + 1 + s] = np.sum(wb[keep] * np.exp(-t[keep]))
+    return tot
+
+
+def sweep_numpy(D, coef, thr, symmetric=True):
+    """The whole moment sweep on the host (CPU tests): -> (logSum[k] or None, status or number of bins)."""
+    D = np.asarray(D, dtype=np.float64)
+    m = D.shape[0]
+    if symmetric:
+        iu = np.triu_indices(m)
+        q = (D * D)[iu]
+        w = np.where(iu[0] == iu[1], 1.0, 2.0)
+    else:
+        q = (D * D).ravel()
+        w = np.ones_like(q)
+    ok = q == q
+    q, w = q[ok], w[ok]
+    nzm = q == 0
+    mn = q[~nzm].min() if np.any(~nzm) else np.inf
+    mx = q.max() if q.size else 0.0
+    status, pl = MSW.plan(mn, mx, w[nzm].sum(), w.sum(), coef, thr)
+    if status:
+        return None, status
+    S = MSW.finalize(pl, accumulate_numpy(q, w, pl, coef, thr), coef, thr)
+    with np.errstate(divide='ignore'):
+        return np.log(S), int(pl[1])
 
 
 def moment_sweep(D, coef, thr, symmetric=True):
     """-> (logSum[k], bins) or (None, status): plan -> per-bin moments and boundary sums -> final evaluation."""
-    return MSW.sweep_numpy(D, coef, thr, symmetric=symmetric)
+    return sweep_numpy(D, coef, thr, symmetric=symmetric)
 
 
 if __name__ == '__main__':
