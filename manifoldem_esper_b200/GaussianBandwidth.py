@@ -40,15 +40,18 @@ def fit(logEps, logSumWij, a0, native=False):
     when scipy is given a libm-tanh model, 4e-9 relative from it with numpy's SIMD tanh (the forward-difference Jacobian
     amplifies one-ulp differences), and callable without the interpreter lock, so the fits of several PDs in flight
     run in parallel."""
-    resnorm = np.inf
+    resnorm, tries = np.inf, 0
     logEps = np.asarray(logEps, dtype=np.float64)
     logSumWij = np.asarray(logSumWij, dtype=np.float64)
     with warnings.catch_warnings():
         warnings.simplefilter(action='ignore', category=OptimizeWarning)
         while resnorm > 100:
             if native:
-                popt, resnorm, R_squared, _, _ = _capi.tanh_fit(logEps, logSumWij, a0)
+                popt, resnorm, R_squared, info, _ = _capi.tanh_fit(logEps, logSumWij, a0)
                 a0 = 1 * (np.random.rand(4, 1) - .5)
+                tries += 1
+                if tries >= 200 and resnorm > 100:        # curve_fit raises when MINPACK gives up; never spin forever
+                    raise RuntimeError('Optimal parameters not found: %d starts without a usable tanh fit (last MINPACK code %d)' % (tries, info))
                 continue
             popt, pcov = curve_fit(fun, logEps, logSumWij, p0=a0)
             resnorm = sum(np.sqrt(np.fabs(np.diag(pcov))))
