@@ -216,3 +216,19 @@ def test_split_kernels_on_the_cpu(prep_bin, P, cs, half):
         cref = (z - xb[None, :]).astype(np.float32) if xb is not None else z
         floor = 2.0 ** -25 / 2.0 ** s if half else 0.0                        # half the FP16 subnormal spacing, unscaled
         assert np.all(np.abs(c - cref) <= 2.0 ** -22 * np.abs(cref) + floor)
+
+
+def test_gram_tile_maps_exhaustively(tmp_path):
+    """tile_coords / tile_map / wide_coords / wide_tile_count of k1_gram.cu on the host for every tile count up to 80
+    (N = 10 240 images): the wide enumeration covers the upper triangle exactly once, the row-block map its rectangle."""
+    src = open(os.path.join(ROOT, 'manifoldem_esper_b200', 'csrc', 'k1_gram.cu')).read()
+    text = cut(src, '// Upper-triangular tile index t -> (ta, tb)'.replace('(ta, tb)', '(ti, tj)'), '// ---- wide (128 x 256) tiles')
+    text += cut(src, 'constexpr int WIDE_TRI = -3;', '__device__ __forceinline__ void umma_tf32_w(')
+    assert 'tile_map' in text and 'wide_coords' in text and 'wide_tile_count' in text
+    (tmp_path / 'tilemap.inc').write_text(text)
+    exe = str(tmp_path / 'tilemap_emu')
+    res = subprocess.run(['g++', '-O1', '-std=c++17', '-I', str(tmp_path), os.path.join(EMU, 'tilemap_emu.cpp'), '-o', exe],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-3000:]
+    res = subprocess.run([exe, '80'], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and res.stdout.strip() == 'ok 80', res.stdout[-500:]
