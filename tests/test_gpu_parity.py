@@ -354,6 +354,33 @@ def test_moment_sweep_nonsymmetric_thresholds_and_fallbacks(ctx):
 
 
 @experimental
+def test_moment_sweep_row_block_entry_points(ctx):
+    """esper_moment_stats_rows / esper_moment_accum_rows on a resident row block against the host plan and the numpy
+    statement of the accumulation (tools/sweep_moments_proto.py); finalize reproduces the general row-block sweep."""
+    import importlib.util
+    from manifoldem_esper_b200 import moment_sweep as MSW
+    spec = importlib.util.spec_from_file_location('sweep_moments_proto', os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools', 'sweep_moments_proto.py'))
+    proto = importlib.util.module_from_spec(spec); spec.loader.exec_module(proto)
+    X = np.random.default_rng(31).standard_normal((600, 4096)).astype(np.float32)
+    row0, nrows = 256, 300
+    Dr = ctx.dist_rms_rows(X, 600, 4096, row0, nrows, download=True)
+    coef = 1. / (2. * np.exp(LOG_EPS))
+    st = ctx.moment_stats_rows(nrows, 600)
+    q = (Dr * Dr).ravel()
+    assert st[0] == q[q != 0].min() and st[1] == q.max() and st[2] == (q == 0).sum() and st[3] == q.size
+    status, pl = MSW.plan(st[0], st[1], st[2], st[3], coef, 10.0)
+    assert status == 0
+    tab = ctx.moment_accum_rows(nrows, 600, coef, 10.0, pl)
+    assert np.allclose(tab, proto.accumulate_numpy(q, np.ones_like(q), pl, coef, 10.0), rtol=1e-12, atol=1e-12)
+    sums = MSW.finalize(pl, tab, coef, 10.0)
+    ref = ctx.eps_sweep_rows(nrows, 600, coef, 10.0)
+    assert np.allclose(sums, ref, rtol=1e-12, atol=0)
+    bad = pl.copy(); bad[0] = 1.0
+    with pytest.raises(ValueError):
+        ctx.moment_accum_rows(nrows, 600, coef, 10.0, bad)
+
+
+@experimental
 def test_moment_sweep_full_size(ctx):
     """BASELINE config 2 shape: D^2 spans 5 %, one bin; both kernels on the same resident matrix."""
     rng = np.random.default_rng(11)
