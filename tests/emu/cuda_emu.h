@@ -187,6 +187,18 @@ void emu_launch_cluster(int grid, int threads, int cs, size_t dyn, K kernel, A..
 }
 #endif
 
+#ifndef EMU_ARENA_SHARED
+// 2-D grid of kernels without __syncthreads / shuffles (epilogue kernels): the threads of a block run one after the other.
+template <class K, class... A>
+void emu_launch_serial(int gx, int gy, int threads, K kernel, A... args) {
+    gridDim.x = (unsigned)gx; gridDim.y = (unsigned)gy; blockDim.x = (unsigned)threads;
+    for (int by = 0; by < gy; ++by)
+        for (int bx = 0; bx < gx; ++bx)
+            for (int t = 0; t < threads; ++t) { threadIdx.x = (unsigned)t; blockIdx.x = (unsigned)bx; blockIdx.y = (unsigned)by; kernel(args...); }
+    gridDim.y = 1;
+}
+#endif
+
 // Run kernel(args...) on a grid of `grid` blocks of `threads` threads, one block after the other.
 template <class K, class... A>
 void emu_launch(int grid, int threads, K kernel, A... args) {

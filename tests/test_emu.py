@@ -232,3 +232,80 @@ def test_gram_tile_maps_exhaustively(tmp_path):
     assert res.returncode == 0, res.stderr[-3000:]
     res = subprocess.run([exe, '80'], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and res.stdout.strip() == 'ok 80', res.stdout[-500:]
+
+
+# ---- K1 epilogues: split-K partial tiles -> distances / Gram matrix, plain and wide tile enumeration ------------------
+@pytest.fixture(scope='module')
+def finalize_bin(tmp_path_factory):
+    d = tmp_path_factory.mktemp('emu_fin')
+    src = open(os.path.join(ROOT, 'manifoldem_esper_b200', 'csrc', 'k1_gram.cu')).read()
+    text = cut(src, '// Upper-triangular tile index t -> (ti, tj)', '// ---- wide (128 x 256) tiles')
+    text += cut(src, '// Distance epilogue: D_ij = sqrt(', '// General product epilogue (CTF branch)')
+    assert 'dist_finalize_kernel' in text and 'gram_finalize_kernel' in text and 'gscale' in text
+    (d / 'finalize.inc').write_text(text)
+    exe = str(d / 'finalize_emu')
+    res = subprocess.run(['g++', '-O1', '-std=c++20', '-pthread', '-ffp-contract=off', '-Wno-unknown-pragmas', '-I', EMU, '-I', str(d),
+                          os.path.join(EMU, 'finalize_emu.cpp'), '-o', exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-4000:]
+    return exe, d
+
+
+def tile_native(T):
+    """[128, 128] tile -> the layout the Gram kernels store: element (r, c) at ((c >> 2) * 128 + r) * 4 + (c & 3)."""
+    return T.reshape(128, 32, 4).transpose(1, 0, 2).reshape(-1)
+
+
+@pytest.mark.parametrize('n,wide', [(300, False), (300, True), (640, True), (129, True)])
+@pytest.mark.parametrize('gram', [0, 1])
+def test_gram_epilogues_on_the_cpu(finalize_bin, n, wide, gram):
+    exe, d = finalize_bin
+    rng = np.random.default_rng(n + wide)
+    P, split_k, s_log2 = 777, 3, 5
+    C = rng.standard_normal((n, P)).astype(np.float32)
+    G = C.astype(np.float64) @ C.astype(np.float64).T
+    nrm = np.diag(G).copy()
+    nt = -(-n // 128)
+    Gp = np.zeros((nt * 128, nt * 128))
+    Gp[:n, :n] = G
+    gscale = 2.0 ** (-2 * s_log2) if (wide and not gram) else 1.0              # the FP16 path hands scaled sums to the epilogue
+    if wide:
+        nt2 = (nt + 1) // 2
+        tiles = [(i, 2 * tc + h) for i in range(nt) for tc in range(i // 2, nt2) for h in (0, 1)]   # virtual tiles 2w + h
+    else:
+        tiles = [(i, j) for i in range(nt) for j in range(i, nt)]
+    part = np.zeros((split_k, len(tiles), 128 * 128), dtype=np.float32)
+    wts = rng.dirichlet(np.ones(split_k))
+    for t, (ti, tj) in enumerate(tiles):
+        if tj >= nt or tj < ti:
+            part[:, t] = np.nan                                                    # redundant / out-of-range virtual tile: never read
+            continue
+        T = Gp[ti * 128:(ti + 1) * 128, tj * 128:(tj + 1) * 128] / gscale
+        for ch in range(split_k):
+            part[ch, t] = tile_native((T * wts[ch]).astype(np.float32))
+    part.tofile(str(d / 'part.bin')); nrm.tofile(str(d / 'nrm.bin'))
+    res = subprocess.run([exe, str(d / 'part.bin'), str(d / 'nrm.bin'), str(n), str(P), str(nt), str(len(tiles)), str(-3 if wide else -1),
+                          str(split_k), repr(gscale), str(gram), str(d / 'out.bin')], capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stderr[-2000:]
+    out = np.fromfile(str(d / 'out.bin')).reshape(n, n)
+    assert np.array_equal(out, out.T) and not np.any(out == -7.0)
+    Gs = np.zeros((nt * 128, nt * 128))                                            # what the kernel sums: float32 partials, FP64 adds
+    for t, (ti, tj) in enumerate(tiles):
+        if tj < nt and tj >= ti:
+            tot = np.zeros(128 * 128)
+            for ch in range(split_k):
+                tot += part[ch, t].astype(np.float64)
+            Gs[ti * 128:(ti + 1) * 128, tj * 128:(tj + 1) * 128] = tot.reshape(32, 128, 4).transpose(1, 0, 2).reshape(128, 128)
+    Gs = np.triu(Gs) + np.triu(Gs, 1).T
+    Gs = Gs[:n, :n]
+    if gram:
+        ref = Gs.copy()
+        np.fill_diagonal(ref, nrm)
+        assert np.array_equal(out, ref)
+    else:
+        d2 = (nrm[:, None] + nrm[None, :] - 2.0 * (Gs * gscale)) * (1.0 / P)
+        ref = np.sqrt(np.maximum(d2, 0.0))
+        np.fill_diagonal(ref, 0.0)
+        assert np.allclose(out, ref, rtol=1e-15, atol=0) and np.all(np.diag(out) == 0)
+        true = np.sqrt(np.maximum(nrm[:, None] + nrm[None, :] - 2 * G, 0) / P)
+        off = ~np.eye(n, dtype=bool)
+        assert np.max(np.abs(out - true)[off] / true[off]) < 1e-5
