@@ -28,6 +28,13 @@ EMU = os.path.join(ROOT, 'tests', 'emu')
 LOG_EPS = np.arange(-100, 100.2, 0.2)
 
 
+def check_run(res):
+    """The stand-in needs up to ~2000 OS threads; an environment that refuses them skips instead of failing."""
+    if res.returncode != 0 and 'Resource temporarily unavailable' in (res.stderr or ''):
+        pytest.skip('cannot create the threads of the execution-model stand-in here')
+    assert res.returncode == 0, (res.stderr or '')[-2000:]
+
+
 def cut(text, start, stop):
     a = text.index(start)
     return text[a:text.index(stop, a)]
@@ -57,7 +64,7 @@ def run_emu(emu_bin, D, coef, thr, sym, sms=3):
     np.ascontiguousarray(coef, dtype=np.float64).tofile(str(d / 'coef.bin'))
     res = subprocess.run([exe, str(d / 'D.bin'), str(m), str(rows), str(int(sym)), str(d / 'coef.bin'), str(len(coef)), repr(float(thr)),
                           str(d / 'out.bin'), str(sms)], capture_output=True, text=True, timeout=600)
-    assert res.returncode == 0, res.stderr[-2000:]
+    check_run(res)
     out = np.fromfile(str(d / 'out.bin'))
     n = len(coef)
     return dict(status=int(out[0]), bins=int(out[1]), logsum=out[2:2 + n], table=out[2 + n:2 + n + MSW.MB * MSW.MV].reshape(MSW.MB, MSW.MV),
@@ -163,7 +170,7 @@ def run_prep(prep_bin, raw, ld, standardize, xbar, half, scale_log2, cs):
     res = subprocess.run([exe, str(d / 'raw.bin'), str(n), str(P), str(ld), str(int(standardize)), xb, str(int(half)),
                           repr(float(2.0 ** scale_log2)), str(cs), str(d / 'hi.bin'), str(d / 'lo.bin'), str(d / 'st.bin')],
                          capture_output=True, text=True, timeout=900)
-    assert res.returncode == 0, res.stderr[-2000:]
+    check_run(res)
     dt = np.float16 if half else np.float32
     hi = np.fromfile(str(d / 'hi.bin'), dtype=dt).reshape(n, ld)
     lo = np.fromfile(str(d / 'lo.bin'), dtype=dt).reshape(n, ld)
@@ -285,7 +292,7 @@ def test_gram_epilogues_on_the_cpu(finalize_bin, n, wide, gram):
     part.tofile(str(d / 'part.bin')); nrm.tofile(str(d / 'nrm.bin'))
     res = subprocess.run([exe, str(d / 'part.bin'), str(d / 'nrm.bin'), str(n), str(P), str(nt), str(len(tiles)), str(-3 if wide else -1),
                           str(split_k), repr(gscale), str(gram), str(d / 'out.bin')], capture_output=True, text=True, timeout=900)
-    assert res.returncode == 0, res.stderr[-2000:]
+    check_run(res)
     out = np.fromfile(str(d / 'out.bin')).reshape(n, n)
     assert np.array_equal(out, out.T) and not np.any(out == -7.0)
     Gs = np.zeros((nt * 128, nt * 128))                                            # what the kernel sums: float32 partials, FP64 adds
