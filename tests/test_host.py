@@ -344,3 +344,13 @@ def test_moment_sweep_layout_matches_the_library(lib_built):
     assert moment_sweep.usable(coef, 10.0) and not moment_sweep.usable(coef[::-1], 10.0) and not moment_sweep.usable(coef, np.inf)
     status, pl = moment_sweep.plan(1.85, 1.95, 2000.0, 4e6, coef, 10.0)
     assert status == 0 and pl.shape == (moment_sweep.PLAN_LEN,) and pl[1] == 1 and 0 <= pl[13] - pl[12] <= moment_sweep.MS
+
+
+def test_product_package_never_touches_the_oracle_or_the_test_tools():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU arms may use oracle/; tools/ holds test statements only."""
+    pkg = os.path.join(ROOT, 'manifoldem_esper_b200')
+    for fn in sorted(os.listdir(pkg)):
+        if fn.endswith('.py'):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r'^\s*(from|import)\s+(oracle|tools)\b', src, flags=re.M), fn
+            assert 'esper_oracle' not in src and 'sweep_moments_proto' not in src, fn
