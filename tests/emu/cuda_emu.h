@@ -93,6 +93,11 @@ inline unsigned short __half_as_ushort(__half h) { return h.bits; }
 inline long long __double_as_longlong(double d) { long long r; std::memcpy(&r, &d, 8); return r; }
 inline double __longlong_as_double(long long v) { double r; std::memcpy(&r, &v, 8); return r; }
 inline int min(int a, int b) { return a < b ? a : b; }
+inline double __ldcg(const double* p) { return *reinterpret_cast<const volatile double*>(p); }
+inline long long clock64() { return 0; }                                  // no watchdog in the stand-in
+inline unsigned int atomicExch(unsigned int* p, unsigned int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+inline void emu_red_release_add(unsigned int* p) { __atomic_fetch_add(p, 1u, __ATOMIC_RELEASE); }
+inline unsigned int emu_ld_acquire(const unsigned int* p) { std::this_thread::yield(); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 
 #ifndef EMU_NO_WARP_SUM
 namespace esper {
@@ -107,7 +112,10 @@ inline double warp_sum(double v) {                 // devutil.cuh: xor-shuffle t
 // arena; the test rewrites `__shared__ T name[N];` into `T* name = emu_smem<T>(N);` (same allocation order in every thread ->
 // same offsets) and `extern __shared__ T name[];` into `T* name = emu_dyn<T>();`.  map_shared_rank translates an address of
 // this block's arena into the peer's, which is what distributed shared memory does.
-constexpr size_t EMU_STATIC_BYTES = 16 * 1024;
+#ifndef EMU_STATIC_BYTES_DEF
+#define EMU_STATIC_BYTES_DEF (16 * 1024)
+#endif
+constexpr size_t EMU_STATIC_BYTES = EMU_STATIC_BYTES_DEF;
 static thread_local char* emu_arena = nullptr;
 static thread_local size_t emu_off = 0;
 static std::vector<std::vector<char>> emu_arenas;          // one per block of the running cluster

@@ -316,3 +316,67 @@ def test_gram_epilogues_on_the_cpu(finalize_bin, n, wide, gram):
         true = np.sqrt(np.maximum(nrm[:, None] + nrm[None, :] - 2 * G, 0) / P)
         off = ~np.eye(n, dtype=bool)
         assert np.max(np.abs(out - true)[off] / true[off]) < 1e-5
+
+
+# ---- K4: the persistent cooperative Lanczos kernels (grid barriers between concurrently running blocks) -----------------
+def scalar_shared(text):
+    import re
+    return re.sub(r'__shared__\s+(\w+)\s+(\w+);', r'\1& \2 = *emu_smem<\1>(1);', text)
+
+
+@pytest.fixture(scope='module')
+def lanczos_bin(tmp_path_factory):
+    d = tmp_path_factory.mktemp('emu_lan')
+    src = open(os.path.join(ROOT, 'manifoldem_esper_b200', 'csrc', 'k4_eigen.cu')).read()
+    text = cut(src, '__device__ __forceinline__ double ld_cg(const double* p)', '// ------------------------------------------------------------------------------------------------\n// Small-m variant (the whole Lanczos vector fits in shared memory): ONE grid barrier per step.')
+    text = text.replace('asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");', 'emu_red_release_add(bar);')
+    text = text.replace('asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");', 'seen = emu_ld_acquire(bar);')
+    assert 'asm' not in text and 'lanczos_resident_kernel' in text and 'lanczos_steps_kernel' in text
+    text = scalar_shared(arena_shared(text))
+    assert '__shared__' not in text
+    (d / 'lanczos.inc').write_text(text)
+    exe = str(d / 'lanczos_emu')
+    res = subprocess.run(['g++', '-O1', '-std=c++20', '-pthread', '-Wno-unknown-pragmas', '-I', EMU, '-I', str(d),
+                          os.path.join(EMU, 'lanczos_emu.cpp'), '-o', exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-4000:]
+    return exe, d
+
+
+@pytest.mark.parametrize('variant,m,grid', [(0, 45, 3), (1, 45, 4), (2, 45, 4), (1, 29, 3)])
+def test_lanczos_kernels_on_the_cpu(lanczos_bin, variant, m, grid):
+    """Full-reorthogonalisation Lanczos on a small Markov matrix: alpha / beta against a numpy Lanczos with the same start,
+    orthonormal basis, Ritz values equal to the leading eigenvalues; batches as the host issues them (state carried over)."""
+    exe, d = lanczos_bin
+    g = golden('stage123_pristine.npz')
+    D = g['D'][:m, :m]
+    Ms = O.markov_symmetric_dense(D, float(g['eps']) if 'eps' in g else 0.0128)
+    lam, U = np.linalg.eigh(Ms)
+    v0 = U[:, -1] * np.sign(U[:, -1].sum())
+    q = np.cos(np.arange(m) * 0.7 + 0.3)
+    for _ in range(2):
+        q -= v0 * (v0 @ q)
+    q /= np.linalg.norm(q)
+    steps = 14
+    Ms.tofile(str(d / 'Ms.bin')); np.stack([v0, q]).tofile(str(d / 'V0.bin'))
+    res = subprocess.run([exe, str(d / 'Ms.bin'), str(m), str(d / 'V0.bin'), str(steps), str(variant), str(grid), '5', str(d / 'out.bin')],
+                         capture_output=True, text=True, timeout=900)
+    check_run(res)
+    out = np.fromfile(str(d / 'out.bin'))
+    alpha, beta, V = out[:steps], out[steps:2 * steps], out[2 * steps:].reshape(steps + 2, m)
+    # numpy Lanczos with full (two-pass) reorthogonalisation against [v0, q1, ...]
+    Vn = [v0, q]; an, bn = [], []
+    for j in range(steps):
+        w = Ms @ Vn[-1]
+        B = np.array(Vn)
+        a = 0.0
+        for _ in range(2):
+            hh = B @ w
+            w = w - B.T @ hh
+            a += hh[-1]
+        b = np.linalg.norm(w)
+        an.append(a); bn.append(b); Vn.append(w / b)
+    assert np.allclose(alpha, an, rtol=1e-9, atol=1e-13) and np.allclose(beta, bn, rtol=1e-9, atol=1e-13)
+    assert np.max(np.abs(V[:steps + 1] @ V[:steps + 1].T - np.eye(steps + 1))) < 1e-12
+    T = np.diag(alpha) + np.diag(beta[:-1], 1) + np.diag(beta[:-1], -1)
+    th = np.linalg.eigvalsh(T)[::-1]
+    assert abs(th[0] - lam[-2]) / lam[-2] < 1e-8                          # leading non-trivial eigenvalue
