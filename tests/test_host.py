@@ -354,3 +354,37 @@ def test_product_package_never_touches_the_oracle_or_the_test_tools():
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r'^\s*(from|import)\s+(oracle|tools)\b', src, flags=re.M), fn
             assert not re.search(r'importlib[^\n]*(oracle|tools)', src), fn
+
+
+def test_moment_sweep_statement_random_spreads_and_thresholds():
+    """Random orders, spreads (0.1 % to 16 decades), zeros, grids and thresholds: wherever the plan is usable the sums agree
+    with the brute-force sweep to 1e-13, everything else is sent to the general kernel."""
+    proto = _tool('sweep_moments_proto')
+    rng = np.random.default_rng(0)
+    used = 0
+    for trial in range(80):
+        m = int(rng.integers(2, 30))
+        spread = 10 ** rng.uniform(-3, 1.2)
+        base = 10 ** rng.uniform(-6, 6)
+        D = np.sqrt(base * np.exp(rng.uniform(0, spread * np.log(10), (m, m))))
+        D = 0.5 * (D + D.T)
+        if rng.random() < 0.7:
+            np.fill_diagonal(D, 0)
+        step = rng.choice([0.2, 0.1, 0.5, 1.0])
+        log_eps = np.arange(-40, 40 + step / 2, step) + np.log(base)
+        coef = 1. / (2. * np.exp(log_eps))
+        thr = float(rng.choice([10, 10, 3, 25, 6.5, 100]))
+        L, info = proto.sweep_numpy(D, coef, thr, symmetric=True)
+        if L is None:
+            assert info in (1, 2)
+            continue
+        ref = []
+        with np.errstate(divide='ignore'):
+            for c in coef:
+                t = c * (D * D)
+                ref.append(np.log(np.sum(np.exp(-t[t < thr]))))
+        ref = np.array(ref)
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(L), fin) and (not fin.any() or np.max(np.abs(L[fin] - ref[fin])) < 1e-13)
+        used += 1
+    assert used >= 40
