@@ -380,3 +380,31 @@ def test_lanczos_kernels_on_the_cpu(lanczos_bin, variant, m, grid):
     T = np.diag(alpha) + np.diag(beta[:-1], 1) + np.diag(beta[:-1], -1)
     th = np.linalg.eigvalsh(T)[::-1]
     assert abs(th[0] - lam[-2]) / lam[-2] < 1e-8                          # leading non-trivial eigenvalue
+
+
+def test_moment_kernels_on_the_cpu_random_cases(emu_bin):
+    """The kernel text against its numpy statement on random spreads, zero patterns, grids and thresholds (plan status,
+    bin count and every sum)."""
+    rng = np.random.default_rng(1)
+    agree = 0
+    for trial in range(14):
+        m = int(rng.integers(2, 70))
+        spread = 10 ** rng.uniform(-3, 1.0)
+        base = 10 ** rng.uniform(-4, 4)
+        D = np.sqrt(base * np.exp(rng.uniform(0, spread * np.log(10), (m, m))))
+        D = 0.5 * (D + D.T)
+        if trial % 3:
+            np.fill_diagonal(D, 0)
+        step = [0.2, 0.1, 0.5][trial % 3]
+        coef = 1. / (2. * np.exp(np.arange(-30, 30 + step / 2, step) + np.log(base)))
+        thr = [10.0, 3.0, 25.0, 6.5][trial % 4]
+        r = run_emu(emu_bin, D, coef, thr, sym=True, sms=1 + trial % 4)
+        L, info = PROTO.sweep_numpy(D, coef, thr, symmetric=True)
+        if L is None:
+            assert r['status'] == info
+            continue
+        assert r['status'] == 0 and r['bins'] == info
+        fin = np.isfinite(L)
+        assert np.array_equal(np.isfinite(r['logsum']), fin) and (not fin.any() or np.max(np.abs(r['logsum'][fin] - L[fin])) < 1e-12)
+        agree += 1
+    assert agree >= 6
