@@ -330,6 +330,31 @@ def run_ours(args):
     h2d_gbs = 4 * N_IMG * P * 4 / (p0.elapsed_time(p1) * 1e-3) / 1e9
     del probe
 
+    # dense TF32 library GEMM on this box (the peak the Gram kernel is compared with; reported next to the
+    # MEASURED_PEAKS-based denominator, never instead of it)
+    tf32_probe = None
+    if rank == 0:
+        prev = torch.backends.cuda.matmul.allow_tf32
+        try:
+            torch.backends.cuda.matmul.allow_tf32 = True
+            a_ = torch.randn((8192, 8192), dtype=torch.float32, device='cuda')
+            b_ = torch.randn((8192, 8192), dtype=torch.float32, device='cuda')
+            for _ in range(3):
+                torch.matmul(a_, b_)
+            torch.cuda.synchronize()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            for _ in range(10):
+                torch.matmul(a_, b_)
+            q1.record()
+            torch.cuda.synchronize()
+            tf32_probe = 10 * 2.0 * 8192 ** 3 / (q0.elapsed_time(q1) * 1e-3) / 1e12
+            del a_, b_
+        except Exception:                                  # noqa: BLE001 -- the probe is informational
+            tf32_probe = None
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+
     tms = torch.tensor([ms, ms_e2e, float(launches), ms_serial], dtype=torch.float64, device='cuda')
     if world > 1:
         import torch.distributed as dist
@@ -399,6 +424,7 @@ def run_ours(args):
                      'traffic_note': 'ncu capture of the 128x128 kernel this kernel replaced on the last GPU minutes of round 1 (same operand planes; partial tiles 349 instead of 330 MB); to be re-captured',
                      'issued_tflops': issued_flops / (gram_ms * 1e-3) / 1e12 if gram_ms > 0 else 0.0,
                      'avg_launch_ms': gram_ms, 'launches_timed': kern['gram'][1],
+                     'tf32_gemm_probe_tflops': tf32_probe,
                      'avg_launch_ms_pipelined': gram_live_ms, 'launches_pipelined': sum(b_ for _, b_ in gram_live),
                      'timing': 'avg_launch_ms: CUDA events on the launching stream in a serial pass of the same K steps (one PD at a time); '
                                'avg_launch_ms_pipelined: the same events inside the timed region with several PDs in flight -- an event pair '
