@@ -408,3 +408,33 @@ def test_moment_kernels_on_the_cpu_random_cases(emu_bin):
         assert np.array_equal(np.isfinite(r['logsum']), fin) and (not fin.any() or np.max(np.abs(r['logsum'][fin] - L[fin])) < 1e-12)
         agree += 1
     assert agree >= 6
+
+
+def test_umma_instruction_descriptors_match_the_cutlass_encoder(tmp_path):
+    """The four tcgen05 instruction descriptors of k1_gram.cu (TF32 / FP16 operands, N = 128 / 256) against
+    cute::UMMA::make_instr_desc of the CUTLASS headers vendored in the image (library code used as a checker only)."""
+    import glob
+    import re
+    inc = [p for p in glob.glob('/opt/prime-rl/.venv/lib/python3*/site-packages/*/data/cutlass/include') +
+           glob.glob('/opt/prime-rl/.venv/lib/python3*/site-packages/*/3rdparty/cutlass/include')
+           if os.path.exists(os.path.join(p, 'cute', 'arch', 'mma_sm100_desc.hpp'))]
+    if not inc:
+        pytest.skip('no CUTLASS headers with mma_sm100_desc.hpp in this image')
+    src = open(os.path.join(ROOT, 'manifoldem_esper_b200', 'csrc', 'k1_gram.cu')).read()
+    defs = re.findall(r'^constexpr (?:int|uint32_t) (?:BM|BN|BN_W|IDESC|IDESC_W|IDESC_WH|IDESC_H) = [^;]+;', src, flags=re.M)
+    assert len(defs) == 7, defs
+    prog = '#include <cstdint>\n#include <cute/arch/mma_sm100_desc.hpp>\n#include <cutlass/half.h>\n#include <cutlass/tfloat32.h>\n' + '\n'.join(defs) + '''
+template <class T, int N> constexpr uint32_t ref() {
+    return uint32_t(cute::UMMA::make_instr_desc<T, T, float, 128, N, cute::UMMA::Major::K, cute::UMMA::Major::K>());
+}
+int main() {
+    return (ref<cutlass::tfloat32_t, 128>() == IDESC ? 0 : 1) + (ref<cutlass::tfloat32_t, 256>() == IDESC_W ? 0 : 2)
+         + (ref<cutlass::half_t, 256>() == IDESC_WH ? 0 : 4) + (ref<cutlass::half_t, 128>() == IDESC_H ? 0 : 8);
+}
+'''
+    (tmp_path / 'idesc.cu').write_text(prog)
+    exe = str(tmp_path / 'idesc')
+    res = subprocess.run(['nvcc', '-std=c++17', '-Wno-deprecated-gpu-targets', '-I', inc[0], '-o', exe, str(tmp_path / 'idesc.cu')],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-3000:]
+    assert subprocess.run([exe]).returncode == 0
