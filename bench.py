@@ -445,6 +445,21 @@ def run_ours(args):
                       'count, eps sweep on 250 of 1001 eps scaled x4.0, kernel+degree+full SVD at full size; %.0f s of CPU work' % (time.time() - t0),
             'detail_s_per_pd': detail, 'vectorised_value': 1.0 / detail['vectorised_total_s'],
             'vectorised_note': 'same math restated with a float64 dgemm Gram instead of the pair loop (not the reference)'}
+    if world == 1 and not args.no_probe:
+        # Opt-in kernels that have never run on hardware: one subprocess per stage, after every measurement
+        # above is taken and with a time-out, so a fault cannot touch this line's numbers; nothing from here enters `value`.
+        probe = {}
+        for st_name in ('sweep', 'prep', 'eig'):
+            try:
+                pr = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'experimental_probe.py'), st_name],
+                                    capture_output=True, text=True, timeout=90)
+                js = [ln for ln in pr.stdout.splitlines() if ln.startswith('{')]
+                probe[st_name] = json.loads(js[-1]) if js else {'ok': False, 'error': 'no output (rc %d): %s' % (pr.returncode, pr.stderr[-200:])}
+            except subprocess.TimeoutExpired:
+                probe[st_name] = {'ok': False, 'error': 'timeout'}
+            except Exception as e:                     # noqa: BLE001
+                probe[st_name] = {'ok': False, 'error': '%s: %s' % (type(e).__name__, str(e)[:200])}
+        line['experimental_probe'] = probe
     print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
@@ -462,6 +477,7 @@ def main():
     ap.add_argument('--no-numa-bind', action='store_true', help='do not restrict ranks to the CPUs of their GPU\'s NUMA node')
     ap.add_argument('--eig-mode', type=int, default=-1, help='esper_dmap_config mode (-1 = throughput when several PDs are in flight)')
     ap.add_argument('--gram-f16', action='store_true', help='experimental: 3xFP16 operand planes for the Gram kernel (esper_gram_config 1)')
+    ap.add_argument('--no-probe', action='store_true', help='skip the post-measurement subprocess probes of the opt-in kernels')
     ap.add_argument('--scipy-fit', action='store_true', help='tanh fit with scipy.optimize.curve_fit (the reference\'s call) instead of esper_tanh_fit')
     ap.add_argument('--prep-cluster', action='store_true', help='experimental: cluster standardise-and-split pass (esper_prep_config 1)')
     ap.add_argument('--sweep-moments', action='store_true', help='experimental: moment sweep (esper_sweep_config 1)')

@@ -121,7 +121,7 @@ def test_bench_gpu_arm_dry_run(monkeypatch, flags):
                                                                          'vectorised_dist_s': 0.8, 'vectorised_total_s': 25.0}))
     for var in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE'):
         monkeypatch.delenv(var, raising=False)
-    monkeypatch.setattr(sys, 'argv', ['bench.py', '--steps', '4', '--warmup', '3', '--inflight', '2'] + flags)
+    monkeypatch.setattr(sys, 'argv', ['bench.py', '--steps', '4', '--warmup', '3', '--inflight', '2'] + flags + ([] if flags else ['--no-probe']))
     buf = io.StringIO()
     with redirect_stdout(buf):
         assert bench.main() == 0
@@ -149,3 +149,8 @@ def test_bench_gpu_arm_dry_run(monkeypatch, flags):
     assert exp == {'gram_f16': bool(flags), 'sweep_moments': bool(flags), 'prep_cluster': bool(flags)}
     assert d['dtype'] == ('f16x3+f64' if flags else 'tf32x3+f64')
     assert ('curve_fit' in d['config']['tanh_fit']) == bool(flags)
+    if flags:                                                        # the probes ran as subprocesses; without a GPU each reports an error
+        assert set(d['experimental_probe']) == {'sweep', 'prep', 'eig'}
+        assert all(v['ok'] is False and 'error' in v for v in d['experimental_probe'].values())
+    else:
+        assert 'experimental_probe' not in d
