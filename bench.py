@@ -449,7 +449,7 @@ def run_ours(args):
         # Opt-in kernels that have never run on hardware: one subprocess per stage, after every measurement
         # above is taken and with a time-out, so a fault cannot touch this line's numbers; nothing from here enters `value`.
         probe = {}
-        for st_name in ('sweep', 'prep', 'eig'):
+        for st_name in ('sweep', 'prep', 'eig', 'gram'):           # the tensor-core kernel last: it is the one that can fault
             try:
                 pr = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'experimental_probe.py'), st_name],
                                     capture_output=True, text=True, timeout=90)

@@ -150,7 +150,7 @@ def test_bench_gpu_arm_dry_run(monkeypatch, flags):
     assert d['dtype'] == ('f16x3+f64' if flags else 'tf32x3+f64')
     assert ('curve_fit' in d['config']['tanh_fit']) == bool(flags)
     if flags:                                                        # the probes ran as subprocesses; without a GPU each reports an error
-        assert set(d['experimental_probe']) == {'sweep', 'prep', 'eig'}
+        assert set(d['experimental_probe']) == {'sweep', 'prep', 'eig', 'gram'}
         assert all(v['ok'] is False and 'error' in v for v in d['experimental_probe'].values())
     else:
         assert 'experimental_probe' not in d

@@ -1,10 +1,9 @@
 #!/usr/bin/env python
 """One stage of the opt-in kernels against the default kernels on this GPU, at the benchmark shape, as ONE
-JSON line.  bench.py runs the stages `sweep`, `prep` and `eig` in separate subprocesses AFTER its measurements (a fault or a
-time-out in a probe cannot touch the numbers already taken, and nothing measured here enters `value`): it records whether
-kernels that have never run on hardware work on this box and what they would gain.  The FP16 Gram kernel is not probed from
-the bench: a tensor-core / TMA kernel that has never run can wait on an mbarrier forever; run tools/experimental_check.py
-for it under a time-out of its own.
+JSON line.  bench.py runs the stages `sweep`, `prep`, `eig` and -- last, because a tensor-core / TMA kernel that has never
+run is the one that can fault or wait on an mbarrier -- `gram` in separate subprocesses AFTER its measurements, each under a
+time-out: a fault in a probe cannot touch the numbers already taken, and nothing measured here enters `value`.  It records
+whether kernels that have never run on hardware work on this box and what they would gain.
 
     python tools/experimental_probe.py sweep|prep|eig|gram
 """
