@@ -226,12 +226,8 @@ def run_ours(args):
     for i, c in enumerate(ctxs):
         c.upload_images(pinned[i % n_stacks].numpy())
         c.dmap_config(args.eig_mode if args.eig_mode >= 0 else (1 if NF > 1 else 0))
-        if args.gram_f16:
-            c.gram_config(1)               # experimental 3xFP16 operand planes (off by default)
-        if args.prep_cluster:
-            c.prep_config(1)               # experimental cluster standardise-and-split pass (off by default)
-        if args.sweep_moments:
-            c.sweep_config(1)              # experimental moment sweep (off by default)
+        c.gram_config(1 if args.gram_f16 else 0)       # 3xFP16 operand planes (library default) / --gram-tf32: 3xTF32
+        c.sweep_config(1 if args.sweep_moments else 0) # moment sweep (library default) / --sweep-general
         c.sync()
     iters_used = []
 
@@ -409,7 +405,7 @@ def run_ours(args):
                    'l2': 'inputs larger than L2 (500 MB stack per PD, two alternating stacks per rank)',
                    'lanczos_steps': iters_used[-1] if iters_used else None, 'numa_bind_rank0': numa,
                    'tanh_fit': 'esper_tanh_fit (MINPACK lmdif in C)' if NATIVE_FIT else 'scipy.optimize.curve_fit',
-                   'experimental': {'gram_f16': bool(args.gram_f16), 'sweep_moments': bool(args.sweep_moments), 'prep_cluster': bool(args.prep_cluster)}},
+                   'kernels': {'gram_f16': bool(args.gram_f16), 'sweep_moments': bool(args.sweep_moments)}},
         'e2e': {'value': pds / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(N_IMG * P * 4),
                 'd2h_bytes_per_step': int(N_IMG * N_IMG * 8 + len(LOG_EPS) * 8 + K_EIG * 8 + N_IMG * K_EIG * 8),
                 'ms_per_step': ms_e2e / args.steps, 'h2d_probe_gbs': round(h2d_gbs, 2),
@@ -445,21 +441,6 @@ def run_ours(args):
                       'count, eps sweep on 250 of 1001 eps scaled x4.0, kernel+degree+full SVD at full size; %.0f s of CPU work' % (time.time() - t0),
             'detail_s_per_pd': detail, 'vectorised_value': 1.0 / detail['vectorised_total_s'],
             'vectorised_note': 'same math restated with a float64 dgemm Gram instead of the pair loop (not the reference)'}
-    if world == 1 and not args.no_probe:
-        # Opt-in kernels that have never run on hardware: one subprocess per stage, after every measurement
-        # above is taken and with a time-out, so a fault cannot touch this line's numbers; nothing from here enters `value`.
-        probe = {}
-        for st_name in ('sweep', 'prep', 'eig', 'gram'):           # the tensor-core kernel last: it is the one that can fault
-            try:
-                pr = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'experimental_probe.py'), st_name],
-                                    capture_output=True, text=True, timeout=90)
-                js = [ln for ln in pr.stdout.splitlines() if ln.startswith('{')]
-                probe[st_name] = json.loads(js[-1]) if js else {'ok': False, 'error': 'no output (rc %d): %s' % (pr.returncode, pr.stderr[-200:])}
-            except subprocess.TimeoutExpired:
-                probe[st_name] = {'ok': False, 'error': 'timeout'}
-            except Exception as e:                     # noqa: BLE001
-                probe[st_name] = {'ok': False, 'error': '%s: %s' % (type(e).__name__, str(e)[:200])}
-        line['experimental_probe'] = probe
     print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
@@ -476,13 +457,12 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-numa-bind', action='store_true', help='do not restrict ranks to the CPUs of their GPU\'s NUMA node')
     ap.add_argument('--eig-mode', type=int, default=-1, help='esper_dmap_config mode (-1 = throughput when several PDs are in flight)')
-    ap.add_argument('--gram-f16', action='store_true', help='experimental: 3xFP16 operand planes for the Gram kernel (esper_gram_config 1)')
-    ap.add_argument('--no-probe', action='store_true', help='skip the post-measurement subprocess probes of the opt-in kernels')
+    ap.add_argument('--gram-tf32', action='store_true', help='3xTF32 operand planes for the Gram kernel (esper_gram_config 0) instead of the default 3xFP16')
     ap.add_argument('--scipy-fit', action='store_true', help='tanh fit with scipy.optimize.curve_fit (the reference\'s call) instead of esper_tanh_fit')
-    ap.add_argument('--prep-cluster', action='store_true', help='experimental: cluster standardise-and-split pass (esper_prep_config 1)')
-    ap.add_argument('--sweep-moments', action='store_true', help='experimental: moment sweep (esper_sweep_config 1)')
+    ap.add_argument('--sweep-general', action='store_true', help='general sweep kernel (esper_sweep_config 0) instead of the default moment sweep')
     ap.add_argument('--inflight', type=int, default=4, help='PDs in flight per GPU (host threads / ctxs / streams)')
     args = ap.parse_args()
+    args.gram_f16, args.sweep_moments = not args.gram_tf32, not args.sweep_general
     global NATIVE_FIT
     NATIVE_FIT = not args.scipy_fit
     if args.impl == 'reference':

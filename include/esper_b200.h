@@ -50,6 +50,7 @@ esper_ctx*  esper_create(int device, void* stream);
 void        esper_destroy(esper_ctx* ctx);
 const char* esper_last_error(esper_ctx* ctx);          /* ctx may be NULL: last create error */
 int         esper_sync(esper_ctx* ctx);                 /* cudaStreamSynchronize              */
+void*       esper_stream(esper_ctx* ctx);               /* the cudaStream_t every call is enqueued on (callers order their own work against it) */
 /* Per-kernel CUDA-event timing of the calls that follow (off by default).  on: 0 off, 1 every launch, 2 the stage-1 Gram
  * launches only (two events per PD: cheap enough to leave on inside a timed region). */
 int         esper_set_profiling(esper_ctx* ctx, int on);
@@ -87,21 +88,15 @@ int esper_upload_images(esper_ctx* ctx, const float* imgs, int n, int P);
  * units fill the SMs); refine_tau (0.05: pairs with D^2*P < 0.05(|x|^2+|y|^2), i.e. near-duplicate images, where
  * Gram cancellation would exceed 1e-5; calibrated with tools/calib_gram_error.py). */
 int esper_dist_config(esper_ctx* ctx, int split_k, double refine_tau);
-/* Operand format of the stage-1 tensor-core contraction.  mode 0 (default): 3xTF32 -- every centred z-score c is split into
- * two TF32 values, hi*hi + hi*lo + lo*hi accumulate in FP32.  mode 1: 3xFP16 -- the same split into two FP16 values of
+/* Operand format of the stage-1 tensor-core contraction.  mode 0: 3xTF32 -- every centred z-score c is split into
+ * two TF32 values, hi*hi + hi*lo + lo*hi accumulate in FP32.  mode 1 (default): 3xFP16 -- the same split into two FP16 values of
  * c * 2^s (an FP16 significand has the same 11 bits as a TF32 one; s is chosen from P so that |c| <= 2 sqrt(P) stays in
  * range), tcgen05 kind::f16 at twice the TF32 rate with half the operand bytes; used for esper_dist_rms (stacks of more
  * than 128 images) and esper_dist_rms_rows with ESPER_DIST_STANDARDIZE, the 3xTF32 path otherwise (unstandardised input,
- * PCA, CTF branch).  Experimental this round: ESPER_GRAM_F16=1 sets the initial mode of new contexts.
+ * PCA, CTF branch).  ESPER_GRAM_F16=0/1 sets the initial mode of new contexts.
  * esper_gram_info: operand format the last esper_dist_rms used (0 TF32, 1 FP16). */
 int esper_gram_config(esper_ctx* ctx, int mode);
 int esper_gram_info(esper_ctx* ctx, int* last_operands);
-/* Standardise-and-split pass that writes the operand planes.  mode 0 (default): one CTA per image, the row is read twice
- * (statistics, then split).  mode 1: a thread-block cluster per image keeps the row in (distributed) shared memory between
- * the two sweeps, so the stack is read from HBM once.  Experimental this round: ESPER_PREP_CLUSTER=1 sets the initial mode.
- * esper_prep_info: cluster size the last pass used (0 = mode-0 kernel, also when a row does not fit 8 x 64 kB). */
-int esper_prep_config(esper_ctx* ctx, int mode);
-int esper_prep_info(esper_ctx* ctx, int* last_cluster);
 /* Upload a distance matrix so that stages 2/3 can use it as the resident D. */
 int esper_upload_dist(esper_ctx* ctx, const double* D, int m);
 
@@ -125,12 +120,12 @@ int esper_eps_sweep(esper_ctx* ctx, const double* D, int m, const double* coef, 
 int esper_tanh_fit(const double* x, const double* y, int n, const double* a0, double* popt, double* resnorm,
                    double* r_squared, int* info, int* nfev);
 
-/* Sweep algorithm: mode 0 (default) evaluates exp() for every (element, k) between the plateaus; mode 1 is the
+/* Sweep algorithm: mode 0 evaluates exp() for every (element, k) between the plateaus; mode 1 (default) is the
  * moment sweep -- D^2 grouped into geometric bins, 17 moments per bin give every fully included k at once, only the
  * k whose truncation boundary falls inside a bin are evaluated per element (the inclusion test stays bit-identical) --
  * with an automatic return to mode 0's kernel when D^2 spans more than 32 bins or the coefficients are not a
- * non-increasing grid.  Results agree to ~1e-14 in logSum.  Experimental this round: the environment variable
- * ESPER_SWEEP_MOMENTS=1 sets the initial mode of new contexts.
+ * non-increasing grid.  Results agree to ~1e-14 in logSum.  The environment variable
+ * ESPER_SWEEP_MOMENTS=0/1 sets the initial mode of new contexts.
  * esper_sweep_info: which kernel produced the last esper_eps_sweep result (0 general, 1 moments) and its bin count. */
 int esper_sweep_config(esper_ctx* ctx, int mode);
 int esper_sweep_info(esper_ctx* ctx, int* last_path, int* bins);
@@ -195,7 +190,7 @@ int esper_pca_embed(esper_ctx* ctx, const float* imgs, int n, int P, int k, doub
 
 /* ---- oversized PD: distance-matrix row blocks (BASELINE config 4) ------------------
  * One PD too large for one GPU is split by row blocks of D / A / Ms: rank g owns rows [row0, row0+nrows)
- * (row0 a multiple of 128).  The same reference arithmetic as above (Distances.py:87-104,
+ * (row0 a multiple of 128; nrows a multiple of 128 unless the block ends at row n).  The same reference arithmetic as above (Distances.py:87-104,
  * GaussianBandwidth.py:36-44, DiffusionMaps.py:109-169) is evaluated on the block; the collectives
  * (sum of the sweep partials, all-gather of the degrees and of the Lanczos vector) are done by the host
  * layer between these calls (manifoldem_esper_b200/rowblock.py, torch.distributed over NCCL).

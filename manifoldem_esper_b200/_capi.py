@@ -33,6 +33,7 @@ SIGNATURES = {
     'esper_destroy': (None, [C.c_void_p]),
     'esper_last_error': (C.c_char_p, [C.c_void_p]),
     'esper_sync': (C.c_int, [C.c_void_p]),
+    'esper_stream': (C.c_void_p, [C.c_void_p]),
     'esper_set_profiling': (C.c_int, [C.c_void_p, C.c_int]),
     'esper_get_kernel_ms': (C.c_int, [C.c_void_p, C.c_char_p, _f64p, _i32p]),
     'esper_reset_profiling': (C.c_int, [C.c_void_p]),
@@ -45,8 +46,6 @@ SIGNATURES = {
     'esper_eps_sweep': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
     'esper_markov': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     'esper_dmap_config': (C.c_int, [C.c_void_p, C.c_int]),
-    'esper_prep_config': (C.c_int, [C.c_void_p, C.c_int]),
-    'esper_prep_info': (C.c_int, [C.c_void_p, C.c_void_p]),
     'esper_gram_config': (C.c_int, [C.c_void_p, C.c_int]),
     'esper_gram_info': (C.c_int, [C.c_void_p, C.c_void_p]),
     'esper_tanh_fit': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -166,6 +165,11 @@ class Context:
     def sync(self):
         self._check(self._lib.esper_sync(self._h))
 
+    @property
+    def stream_ptr(self):
+        """cudaStream_t (as an integer) every call of this ctx is enqueued on."""
+        return int(self._lib.esper_stream(self._h) or 0)
+
     def set_profiling(self, on=True):
         self._check(self._lib.esper_set_profiling(self._h, int(on)))       # 0 off, 1 every launch, 2 the Gram launches only
 
@@ -209,18 +213,8 @@ class Context:
         self._check(self._lib.esper_dist_rms(self._h, _ptr(imgs), int(n), int(P), int(flags), _ptr(D)))
         return D
 
-    def prep_config(self, mode=0):
-        """0 = one CTA per image (row read twice), 1 = cluster per image (row kept in shared memory between the sweeps)."""
-        self._check(self._lib.esper_prep_config(self._h, int(mode)))
-
-    def prep_info(self):
-        """Cluster size the last standardise-and-split pass used (0 = the one-CTA-per-image kernel)."""
-        v = C.c_int(0)
-        self._check(self._lib.esper_prep_info(self._h, C.byref(v)))
-        return v.value
-
-    def gram_config(self, mode=0):
-        """0 = 3xTF32 operand planes (default), 1 = 3xFP16 (z-scored stacks of more than 128 images)."""
+    def gram_config(self, mode=1):
+        """0 = 3xTF32 operand planes, 1 = 3xFP16 (default; used for z-scored stacks of more than 128 images)."""
         self._check(self._lib.esper_gram_config(self._h, int(mode)))
 
     def gram_info(self):
@@ -248,8 +242,8 @@ class Context:
         self._check(self._lib.esper_eps_sweep(self._h, _ptr(D), int(m), _ptr(coef), coef.shape[0], float(thr), _ptr(out)))
         return out
 
-    def sweep_config(self, mode=0):
-        """0 = general sweep kernel (default), 1 = moment sweep with automatic return to the general kernel."""
+    def sweep_config(self, mode=1):
+        """0 = general sweep kernel, 1 = moment sweep (default) with automatic return to the general kernel."""
         self._check(self._lib.esper_sweep_config(self._h, int(mode)))
 
     def sweep_info(self):

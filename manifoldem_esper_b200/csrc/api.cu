@@ -46,9 +46,8 @@ esper_ctx* esper_create(int device, void* stream) {
     esper_ctx* c = new esper_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    if (const char* ev = getenv("ESPER_PREP_CLUSTER")) c->prep_mode = (atoi(ev) != 0) ? 1 : 0;        // experimental, see esper_prep_config
-    if (const char* ev = getenv("ESPER_GRAM_F16")) c->gram_mode = (atoi(ev) != 0) ? 1 : 0;           // experimental, see esper_gram_config
-    if (const char* ev = getenv("ESPER_SWEEP_MOMENTS")) c->sweep_mode = (atoi(ev) != 0) ? 1 : 0;   // experimental, see esper_sweep_config
+    if (const char* ev = getenv("ESPER_GRAM_F16")) c->gram_mode = (atoi(ev) != 0) ? 1 : 0;           // see esper_gram_config
+    if (const char* ev = getenv("ESPER_SWEEP_MOMENTS")) c->sweep_mode = (atoi(ev) != 0) ? 1 : 0;   // see esper_sweep_config
     if (stream) {
         c->stream = reinterpret_cast<cudaStream_t>(stream);
     } else {
@@ -73,17 +72,19 @@ void esper_destroy(esper_ctx* c) {
                       &c->pair_list, &c->sweep_part, &c->sweep_aux, &c->markov, &c->degree, &c->lan_V, &c->lan_w,
                       &c->lan_h, &c->lan_small, &c->rot_U, &c->rot_R, &c->rot_idx, &c->rot_out, &c->rot_H,
                       &c->rot_theta, &c->rot_aux, &c->prep_src, &c->prep_out,
-                      &c->ctf_par, &c->ctf_T, &c->ctf_fy, &c->ctf_C, &c->ctf_ab, &c->ctf_T12, &c->ctf_wiener, &c->pw_plan};
+                      &c->ctf_par, &c->ctf_T, &c->ctf_fy, &c->ctf_C, &c->ctf_ab, &c->ctf_T12, &c->ctf_wiener, &c->pw_plan, &c->chain_ws};
     run_comm_close(c);
     c->comm_buf.release();
     for (DevBuf* b : bufs) b->release();
-    c->pin.release();
+    c->pin.release(); c->pin_chain.release();
     c->pin_stream[0].release(); c->pin_stream[1].release();
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
 const char* esper_last_error(esper_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+void* esper_stream(esper_ctx* c) { return c ? reinterpret_cast<void*>(c->stream) : nullptr; }
 
 int esper_sync(esper_ctx* c) {
     ESPER_ENTER(c);
@@ -165,19 +166,6 @@ int esper_gram_config(esper_ctx* c, int mode) {
     return ESPER_OK;
 }
 
-int esper_prep_config(esper_ctx* c, int mode) {
-    ESPER_ENTER(c);
-    if (mode != 0 && mode != 1) return fail(c, ESPER_E_ARG, "prep_config: mode must be 0 (one CTA per image) or 1 (cluster per image)");
-    c->prep_mode = mode;
-    return ESPER_OK;
-}
-
-int esper_prep_info(esper_ctx* c, int* last_cluster) {
-    ESPER_ENTER(c);
-    if (last_cluster) *last_cluster = c->prep_last_cluster;
-    return ESPER_OK;
-}
-
 int esper_gram_info(esper_ctx* c, int* last_operands) {
     ESPER_ENTER(c);
     if (last_operands) *last_operands = c->gram_last_f16;
@@ -195,8 +183,8 @@ int esper_dist_rms(esper_ctx* c, const float* imgs, int n, int P, unsigned flags
                     n, P, c->img_n, c->img_P);
     }
     const int rows_pad = (int)round_up((size_t)n, 128);
-    // operand planes: TF32 pairs (default) or, opted in through esper_gram_config, FP16 pairs for z-scored stacks of at least
-    // two 128-row tiles (the bound on |c| that makes FP16's range sufficient needs the standardisation)
+    // operand planes: FP16 pairs (esper_gram_config 1, the default) for z-scored stacks of at least
+    // two 128-row tiles (the bound on |c| that makes FP16's range sufficient needs the standardisation), TF32 pairs otherwise
     int hs = -1;
     if (c->gram_mode == 1 && (flags & ESPER_DIST_STANDARDIZE) && rows_pad >= 256) hs = gram_f16_scale_log2(P);
     const int ld = (int)round_up((size_t)P, hs >= 0 ? 64 : 32);
@@ -278,7 +266,7 @@ int esper_markov(esper_ctx* c, const double* D, int m, double eps, double* degre
 
 int esper_dmap_config(esper_ctx* c, int mode) {
     ESPER_ENTER(c);
-    if (mode < 0 || mode > 2) return fail(c, ESPER_E_ARG, "dmap_config: mode must be 0 (latency), 1 (throughput) or 2 (throughput, no speculative batch)");
+    if (mode < 0 || mode > 3) return fail(c, ESPER_E_ARG, "dmap_config: mode must be 0 (barrier-free chain kernel), 1 (streamed barrier kernel, two grids per SM), 2 (the same without the speculative batch) or 3 (resident barrier kernel)");
     c->lanczos_mode = mode;
     return ESPER_OK;
 }
@@ -389,6 +377,10 @@ int esper_dist_rms_rows(esper_ctx* c, const float* imgs, int n, int P, unsigned 
     if (n < 1 || P < 1) return fail(c, ESPER_E_ARG, "dist_rms_rows: need n >= 1 and P >= 1");
     if (row0 < 0 || nrows < 1 || row0 + nrows > n || (row0 % 128) != 0)
         return fail(c, ESPER_E_ARG, "dist_rms_rows: need 0 <= row0 (multiple of 128), nrows >= 1, row0 + nrows <= n");
+    // the epilogue stores whole 128-row tiles guarded by the matrix order only: a short block must be the last one
+    if ((nrows % 128) != 0 && row0 + nrows != n)
+        return fail(c, ESPER_E_ARG, "dist_rms_rows: nrows must be a multiple of 128 unless the block ends at row n (row0=%d, nrows=%d, n=%d)",
+                    row0, nrows, n);
     if (imgs) {
         int rc = esper_upload_images(c, imgs, n, P);
         if (rc) return rc;
@@ -396,7 +388,7 @@ int esper_dist_rms_rows(esper_ctx* c, const float* imgs, int n, int P, unsigned 
         return fail(c, ESPER_E_STATE, "dist_rms_rows: imgs == NULL but no resident [%d, %d] stack", n, P);
     }
     const int rows_pad = (int)round_up((size_t)n, 128);
-    int hs = -1;                                           // FP16 operand planes: opt-in, z-scored stacks only (see esper_dist_rms)
+    int hs = -1;                                           // FP16 operand planes: z-scored stacks only (see esper_dist_rms)
     if (c->gram_mode == 1 && (flags & ESPER_DIST_STANDARDIZE)) hs = gram_f16_scale_log2(P);
     const int ld = (int)round_up((size_t)P, hs >= 0 ? 64 : 32);
     ESPER_RESERVE(c, c->dist, sizeof(double) * (size_t)nrows * n);

@@ -77,8 +77,7 @@ struct esper_ctx {
     int split_k = 0;
     int drain_kb = 2;                                          // k-blocks (of 32 pixels) per tensor-core accumulation chain
     double refine_tau = 0.05;
-    int prep_mode = 0, prep_last_cluster = 0; bool attr_prep_cluster = false;   // esper_prep_config: 1 = cluster split kernel (opt-in)
-    int gram_mode = 0, gram_last_f16 = 0;                      // esper_gram_config: 0 = 3xTF32 operand planes, 1 = 3xFP16 (opt-in)
+    int gram_mode = 1, gram_last_f16 = 0;                      // esper_gram_config: 0 = 3xTF32 operand planes, 1 = 3xFP16 (default)
 
     // resident data
     esper::DevBuf imgs;     int img_n = 0, img_P = 0;          // raw float32 stack [n, P]
@@ -93,12 +92,13 @@ struct esper_ctx {
     esper::DevBuf pair_list;                                   // refine: flagged pairs + counter
     // stage-2/3 workspaces
     esper::DevBuf sweep_part, sweep_aux;
-    int sweep_mode = 0, sweep_last_path = 0, sweep_last_bins = 0;   // esper_sweep_config / esper_sweep_info
+    int sweep_mode = 1, sweep_last_path = 0, sweep_last_bins = 0;   // esper_sweep_config / esper_sweep_info
     esper::DevBuf markov, degree;                              // Ms [m,m], d [m]
     esper::DevBuf ctf_par, ctf_T, ctf_fy, ctf_C, ctf_ab, ctf_T12, ctf_wiener;   // CTF branch (k6_ctf.cu)
     bool attr_ctf = false;
     esper::DevBuf pw_plan; int pw_P = -1, pw_L = 0, pw_nodes = 0, pw_levels = 0, pw_root = 0;   // numpy pairwise-sum tree (k0_prep.cu)
     esper::DevBuf lan_V, lan_w, lan_h, lan_small;              // Lanczos basis etc.
+    esper::DevBuf chain_ws; esper::PinBuf pin_chain; long long chain_smem_set = 0;   // barrier-free schedule (k4_chain.cu)
     // stage-4 workspaces
     esper::DevBuf rot_U, rot_R, rot_idx, rot_out, rot_H, rot_theta, rot_aux;
     int rot_n_pd = 0, rot_m = 0, rot_dim = 0;                  // shape of the normalised manifolds resident in rot_U
@@ -195,6 +195,8 @@ int run_rot_eval(esper_ctx* c, const double* Uinit, int n_pd, int m, int dim, co
 int run_rot_sweep(esper_ctx* c, const double* Uinit, int n_pd, int m, int dim, const int* combo,
                   const int* n_sub, int max_sub, const int* rij, int n_rij, const double* theta_grid,
                   int n_theta, int bins, double lo, double hi, double* thetas_out, int* counts_out);
+int run_lanczos_chain(esper_ctx* c, int m, int k, int guard, double tol, int max_iter, double* V, double* U_d);
+int chain_result(esper_ctx* c, int k, double* theta_out, int* iters_out);
 int run_symv_rows(esper_ctx* c, int rows, int m, const double* q_d, double* w_rows_d);
 int run_comm_alloc(esper_ctx* c, int n_pad, int world, void* handle_out);
 int run_comm_open(esper_ctx* c, const void* handles, int rank, int world);

@@ -9,7 +9,6 @@
 //                               c = fl32(z - xbar); hi = tf32(c); lo = tf32(c - hi); |c|^2 in FP64
 //
 // Algorithmic bytes per PD (n images, P pixels): read 4nP once from HBM (+4nP from L2), write 8nP.
-#include <cooperative_groups.h>
 #include <cuda_fp16.h>
 #include "common.cuh"
 #include "devutil.cuh"
@@ -163,128 +162,6 @@ __global__ void __launch_bounds__(512) stats_split_kernel(const float* __restric
     }
     acc = block_sum(acc, sh);
     if (threadIdx.x == 0) { st[i].mean = m; st[i].stdv = sd; st[i].norm2 = acc; }
-}
-
-// Cluster variant of stats_split_kernel (opt-in, esper_prep_config(ctx, 1) / ESPER_PREP_CLUSTER=1): a thread-block cluster
-// of CS CTAs takes one image, every CTA keeps its 1/CS slice of the row in shared memory between the statistics sweep and
-// the split sweep, so the stack is read from HBM exactly once (stats_split_kernel re-reads every row: 0.5 GB more at the
-// benchmark shape, the L2 does not hold the ~300 rows in flight).  The sums of the slices are exchanged through
-// distributed shared memory and added in rank order by every CTA (deterministic, identical in all CTAs).  Three 64 kB
-// CTAs share an SM, so loads of one image overlap the stores of another.  Same arithmetic per element as
-// stats_split_kernel; the FP64 sums are associated differently (slices), so mean32 / std32 may differ in the last bit.
-namespace cg = cooperative_groups;
-
-template <bool HALF>
-__global__ void __launch_bounds__(256) stats_split_cluster_kernel(const float* __restrict__ raw, int n, int P, int ld,
-                                                                  int standardize, RowStat* __restrict__ st,
-                                                                  const float* __restrict__ xbar, int center, float scale,
-                                                                  void* __restrict__ hi_v, void* __restrict__ lo_v,
-                                                                  int quads_per_cta) {
-    extern __shared__ float4 s_row[];                     // [quads_per_cta] this CTA's slice of the raw row
-    __shared__ double sh[32];
-    __shared__ double s_part[4];                          // sum, sum of squares, |c|^2 of this slice (read by the peers)
-    __shared__ double bc[2];
-    cg::cluster_group cl = cg::this_cluster();
-    const int cs = (int)cl.num_blocks(), rank = (int)cl.block_rank();
-    const int i = blockIdx.x / cs;                        // image (1-D clusters of consecutive CTAs)
-    const float* row = raw + (size_t)i * P;
-    const int nq = ld >> 2;                               // quads per plane row (zero padded beyond P)
-    const int q0 = min(rank * quads_per_cta, nq), q1 = min(q0 + quads_per_cta, nq);
-    const bool vec = ((P & 3) == 0);
-
-    // sweep 1: HBM -> shared memory, FP64 sum and sum of squares of the slice
-    double s = 0.0, s2 = 0.0;
-    for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
-        const int p0 = q << 2;
-        float4 t;
-        if (vec && p0 + 3 < P) {
-            t = __ldg(reinterpret_cast<const float4*>(row) + q);
-        } else {
-            t.x = (p0 < P) ? __ldg(row + p0) : 0.f;
-            t.y = (p0 + 1 < P) ? __ldg(row + p0 + 1) : 0.f;
-            t.z = (p0 + 2 < P) ? __ldg(row + p0 + 2) : 0.f;
-            t.w = (p0 + 3 < P) ? __ldg(row + p0 + 3) : 0.f;
-        }
-        s_row[q - q0] = t;
-        const double a = t.x, b = t.y, c = t.z, d = t.w;  // padding contributes exact zeros
-        s += (a + b) + (c + d);
-        s2 += (a * a + b * b) + (c * c + d * d);
-    }
-    float m = 0.f, sd = 1.f;
-    if (standardize) {
-        s = block_sum(s, sh);
-        s2 = block_sum(s2, sh);
-        if (threadIdx.x == 0) { s_part[0] = s; s_part[1] = s2; }
-        cl.sync();                                        // every slice's sums are visible cluster-wide
-        if (threadIdx.x == 0) {
-            double ts = 0.0, ts2 = 0.0;
-            for (int r = 0; r < cs; ++r) {
-                const double* pp = cl.map_shared_rank(s_part, r);
-                ts += pp[0]; ts2 += pp[1];
-            }
-            const double mean = ts / P;
-            double var = ts2 / P - mean * mean;
-            if (var < 0.0) var = 0.0;
-            bc[0] = (double)(float)mean;
-            bc[1] = (double)(float)sqrt(var);
-        }
-        __syncthreads();
-        m = (float)bc[0];
-        sd = (float)bc[1];
-    }
-
-    // sweep 2: shared memory -> operand planes
-    double acc = 0.0;
-    for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
-        const int p0 = q << 2;
-        const float4 t = s_row[q - q0];
-        const float v[4] = {t.x, t.y, t.z, t.w};
-        float cv[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float c = 0.f;
-            if (p0 + e < P) {
-                c = zscore(v[e], m, sd);
-                if (center) c = __fsub_rn(c, __ldg(xbar + p0 + e));
-            }
-            cv[e] = c;
-            acc += (double)c * (double)c;
-        }
-        if (!HALF) {
-            float h[4], l[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                h[e] = tf32_rna(cv[e]);
-                l[e] = tf32_rna(__fsub_rn(cv[e], h[e]));
-            }
-            reinterpret_cast<float4*>(reinterpret_cast<float*>(hi_v) + (size_t)i * ld)[q] = make_float4(h[0], h[1], h[2], h[3]);
-            reinterpret_cast<float4*>(reinterpret_cast<float*>(lo_v) + (size_t)i * ld)[q] = make_float4(l[0], l[1], l[2], l[3]);
-        } else {
-            __half h[4], l[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float cs_ = __fmul_rn(cv[e], scale);
-                h[e] = __float2half_rn(cs_);
-                l[e] = __float2half_rn(__fsub_rn(cs_, __half2float(h[e])));
-            }
-            uint2 hv, lv;
-            hv.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
-            hv.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
-            lv.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
-            lv.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
-            reinterpret_cast<uint2*>(reinterpret_cast<__half*>(hi_v) + (size_t)i * ld)[q] = hv;
-            reinterpret_cast<uint2*>(reinterpret_cast<__half*>(lo_v) + (size_t)i * ld)[q] = lv;
-        }
-    }
-    acc = block_sum(acc, sh);
-    if (threadIdx.x == 0) s_part[2] = acc;
-    cl.sync();
-    if (rank == 0 && threadIdx.x == 0) {
-        double tot = 0.0;
-        for (int r = 0; r < cs; ++r) tot += cl.map_shared_rank(s_part, r)[2];
-        st[i].mean = m; st[i].stdv = sd; st[i].norm2 = tot;
-    }
-    cl.sync();                                            // no CTA leaves while rank 0 still reads its shared memory
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -451,36 +328,7 @@ int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld, b
     }
     {
         LaunchScope ls(c, "prep");
-        // cluster variant: smallest cluster whose slices fit three CTAs per SM (<= 64 kB each)
-        int cs = 0;
-        if (c->prep_mode == 1) {
-            for (int cand = 1; cand <= 8; cand *= 2)
-                if ((size_t)ceil_div(ld / 4, cand) * sizeof(float4) <= 64 * 1024) { cs = cand; break; }
-        }
-        c->prep_last_cluster = cs;
-        if (cs > 0) {
-            const int quads_per_cta = ceil_div(ld / 4, cs);
-            const size_t smem = (size_t)quads_per_cta * sizeof(float4);
-            void (*kern)(const float*, int, int, int, int, RowStat*, const float*, int, float, void*, void*, int) =
-                half ? stats_split_cluster_kernel<true> : stats_split_cluster_kernel<false>;
-            if (!c->attr_prep_cluster) {
-                ESPER_CUDA(c, cudaFuncSetAttribute(stats_split_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-                ESPER_CUDA(c, cudaFuncSetAttribute(stats_split_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-                c->attr_prep_cluster = true;
-            }
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)n * cs);
-            cfg.blockDim = dim3(256);
-            cfg.dynamicSmemBytes = smem;
-            cfg.stream = c->stream;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            const float scale = half ? ldexpf(1.0f, half_scale_log2) : 1.0f;
-            ESPER_CUDA(c, cudaLaunchKernelEx(&cfg, kern, raw, n, P, ld, standardize, st, (const float*)xbar, center, scale,
-                                             c->plane_hi.p, c->plane_lo.p, quads_per_cta));
-        } else if (half)
+        if (half)
             stats_split_kernel<true><<<n, 512, 0, c->stream>>>(raw, n, P, ld, standardize, st, xbar, center,
                                                                ldexpf(1.0f, half_scale_log2), c->plane_hi.p, c->plane_lo.p);
         else

@@ -1,0 +1,792 @@
+// k4_chain.cu -- K4, default schedule for m <= 2048: Lanczos with full reorthogonalisation as ONE persistent kernel
+// WITHOUT grid barriers.  Replaces the full SVD of 1_Embedding/DM/DiffusionMaps.py:166-169 (leading pairs only).
+//
+// The three-barrier kernel of k4_eigen.cu spent 40 % of every step inside grid barriers and the rest waiting for one L2
+// round trip per phase (profiles/r1_bench_lines.md).  Here every hand-over between CTAs is a flag-carrying 16-byte packet
+// {lo, tag, hi, tag} (the protocol NCCL calls LL; already used by the row-block all-gather): the consumer polls the data
+// itself, so a hand-over costs one store and one load instead of arrive + poll + load.
+//
+//   worker CTA b (owns rows R_b of Ms on chip: shared memory + registers, and the same rows of every basis vector in shared
+//   memory, Vs[r][i]); the whole current Lanczos vector q_j is in its shared memory:
+//     S0   w_r = Ms[r,:] q_j - sigma q_j[r] - beta_{j-1} q_{j-1}[r]          r in R_b          (on-chip operands only)
+//     P1   partial coefficients  p_b[s] = sum_{r in R_b} Vs[r][s-1] w_r  (s >= 1),  p_b[0] = sum_r w_r^2   -> packets pbuf[s][b]
+//     P2   the CTA that owns slot s (s mod workers) adds the partials of all workers in a fixed order     -> packet  hbuf[s]
+//     P3   every CTA reads all h; w_r -= sum_i Vs[r][i] h_i;  beta^2 = |w|^2 - sum h^2 (exact for an orthonormal basis; the
+//          DGKS test beta^2 < |w|^2 / 2 asks for a second P1-P3 pass, in which |w'|^2 is summed again);
+//          q_{j+1}[r] = w_r / beta  -> Vs, global V (for the Ritz vectors) and packets qbuf[r]
+//     P4   every CTA reads q_{j+1} (m packets) into shared memory
+//   Three dependent hand-overs per step, no barrier, every reduction in a fixed order (deterministic, identical in all CTAs).
+//
+//   checker CTAs (the CTAs that own no rows): follow alpha_j / beta_j (packets abuf[j] from CTA 0) and test convergence of
+//   the leading Ritz pairs on the device: multisection Sturm counts with all threads (division-free scaled recurrence),
+//   inverse iteration with a stored pivoted LU (one thread per Ritz vector), residual |beta_n s_{n,i}|.  The first checker
+//   whose test passes publishes theta, S and n and raises the stop word; CTA 0 forwards it to all workers inside the control
+//   packet of the next P2, so that all of them leave at the same step.  The host is not involved until the final copy.
+//
+// A failure of any spin wait (~2 s) raises the abort word and ends the kernel; the host then falls back to the
+// barrier kernels of k4_eigen.cu, as it does for sizes this schedule does not cover.
+#include "common.cuh"
+#include "devutil.cuh"
+#include <algorithm>
+
+namespace esper {
+namespace chain {
+
+constexpr int CH_THREADS = 512;
+constexpr int CH_WARPS = CH_THREADS / 32;
+constexpr int CH_MAXROWS = 14;          // rows of Ms per worker CTA
+constexpr int CH_REGROWS = 4;           // of which in registers (the rest in shared memory)
+constexpr int CH_MAXM = 2048;
+constexpr int CH_MAXWANT = 24;          // Ritz pairs followed by a checker (kw + guard)
+constexpr int CH_MAXCHK = 4;
+constexpr long long CH_TIMEOUT = 4000000000LL;     // ~2 s
+
+struct Ctl {
+    unsigned int stop;                  // 0, or 0x80000000 | checker << 16 | n  (first passing check)
+    unsigned int abort;                 // a spin wait timed out
+    unsigned int final_n;               // workers ended without a stop: 0x80000000 | breakdown << 30 | steps
+    unsigned int progress;              // steps completed (alpha/beta published)
+    int status;                         // 1 converged, 2 not converged at max_steps
+    int n_final, winner, steps_run;
+    long long prof[16];
+};
+
+struct Params {
+    const double* Ms; int m;
+    double* V;                          // [max_steps + 2][m]: V[0] locked vector, V[1] start vector (both set by the host side)
+    double* alpha; double* beta;        // plain copies for the host (alpha[j-1], beta[j-1] of step j)
+    int chunk, n_workers, n_checkers;
+    int max_steps;                      // <= vs_cap - 2
+    int vs_cap;                         // basis vectors per owned row held in shared memory
+    int kw, guard, cap_steps;           // pairs wanted (without the locked one), guard pairs, Krylov dimension m - 1
+    double tol;
+    int first_check;
+    uint4* pbuf;                        // [slots][n_workers]
+    uint4* hbuf;                        // [slots + 1]; the last packet is the control word
+    uint4* qbuf;                        // [m]
+    uint4* abuf;                        // [max_steps + 1][2]
+    Ctl* ctl;
+    double* theta_out;                  // [n_checkers][CH_MAXWANT]
+    double* S_out;                      // [n_checkers][max_steps * kw]
+    int s_stride;                       // doubles per checker in S_out
+    int prof_on;
+};
+
+// ---- packet and flag primitives (the CPU stand-in of tests/emu replaces exactly these) ----------------------------------
+#ifndef ESPER_CHAIN_EMU
+__device__ __forceinline__ void st_ll(uint4* p, double v, unsigned int tag) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned int)__double2loint(v)), "r"(tag),
+                 "r"((unsigned int)__double2hiint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ bool ld_ll(const uint4* p, unsigned int tag, double& v) {
+    uint4 x;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "l"(p) : "memory");
+    v = __hiloint2double((int)x.z, (int)x.x);
+    return x.y == tag && x.w == tag;
+}
+__device__ __forceinline__ unsigned int ld_word(const unsigned int* p) { return *((const volatile unsigned int*)p); }
+__device__ __forceinline__ void st_word(unsigned int* p, unsigned int v) { *((volatile unsigned int*)p) = v; }
+__device__ __forceinline__ unsigned int cas_word(unsigned int* p, unsigned int cmp, unsigned int v) { return atomicCAS(p, cmp, v); }
+__device__ __forceinline__ void publish_fence() { __threadfence(); }
+__device__ __forceinline__ long long now() { return clock64(); }
+__device__ __forceinline__ void relax() { __nanosleep(40); }
+#endif
+
+// ---- begin chain kernel text (tests/test_emu.py cuts from here) ----
+// Spin until the packet carries `tag`; false after the watchdog or when another CTA raised the abort word.
+__device__ __forceinline__ bool wait_ll(const uint4* p, unsigned int tag, double& v, Ctl* ctl) {
+    if (ld_ll(p, tag, v)) return true;
+    const long long t0 = now();
+    for (unsigned int polls = 1;; ++polls) {
+        if (ld_ll(p, tag, v)) return true;
+        if ((polls & 63u) == 0u) {
+            if (ld_word(&ctl->abort) != 0u) return false;
+            if (now() - t0 > CH_TIMEOUT) { st_word(&ctl->abort, 1u); return false; }
+        }
+    }
+}
+
+// 16 per-lane values -> 16 warp totals with 16 shuffles; lane l ends with the total of value index
+// ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 + ((l>>1)&1); fixed order.
+__device__ __forceinline__ double multi_sum16(double (&v)[16], int lane) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const bool up = lane & 16;
+        const double send = up ? v[i] : v[i + 8];
+        const double keep = up ? v[i + 8] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool up = lane & 8;
+        const double send = up ? v[i] : v[i + 4];
+        const double keep = up ? v[i + 4] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const bool up = lane & 4;
+        const double send = up ? v[i] : v[i + 2];
+        const double keep = up ? v[i + 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    {
+        const bool up = lane & 2;
+        const double send = up ? v[0] : v[1];
+        const double keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Checker: convergence test of the leading Ritz pairs of T_n = tridiag(b, a, b) by one CTA.
+// ---------------------------------------------------------------------------------------------------------------------
+// Number of eigenvalues of T_n below x: sign changes of the Sturm sequence p_i = (a_i - x) p_{i-1} - b_{i-1}^2 p_{i-2},
+// evaluated without divisions and rescaled by exact powers of two (a zero takes the sign opposite to its predecessor).
+__device__ __forceinline__ int sturm_below(const double* a, const double* b2, int n, double x) {
+    double pm = 1.0, pc = a[0] - x;
+    int cnt = 0;
+    bool neg = (pc < 0.0) || (pc == 0.0);
+    if (neg) ++cnt;                                             // sign(p_1) != sign(p_0 = 1)
+    for (int i = 1; i < n; ++i) {
+        const double pn = (a[i] - x) * pc - b2[i - 1] * pm;
+        const bool nneg = (pn < 0.0) || (pn == 0.0 && !neg);
+        if (nneg != neg) ++cnt;
+        neg = nneg;
+        pm = pc; pc = pn;
+        if ((i & 7) == 7) {                                     // keep |p| near 1: both by the same power of two
+            const double mag = fmax(fabs(pc), fabs(pm));
+            if (mag > 0.0 && (mag < 1e-100 || mag > 1e100)) {
+                int e;
+                frexp(mag, &e);
+                pc = ldexp(pc, -e); pm = ldexp(pm, -e);
+            }
+        }
+    }
+    return cnt;
+}
+
+struct CheckSmem {
+    double* a; double* b; double* b2;       // [cap] each
+    double* theta;                          // [CH_MAXWANT]
+    double* lo; double* hi;                 // [CH_MAXWANT]
+    double* y; double* di; double* du; double* ff;   // [want][cap]: vector, 1/pivot, super-diagonal, multiplier (sign bit of swp = row swap)
+    unsigned char* swp;                     // [want][cap]
+    int* cnt;                               // [CH_THREADS]
+    double* xs;                             // [CH_THREADS] section points of the current round
+    double* red;                            // [3][CH_WARPS]
+};
+
+// Shared-memory doubles a checker needs for `want` Ritz pairs and a Krylov dimension of at most cap (host and device).
+__host__ __device__ inline size_t checker_doubles(int want, int cap) {
+    return 3 * (size_t)cap + 3 * CH_MAXWANT + 3 * CH_WARPS + 4 * (size_t)want * cap + CH_THREADS + CH_THREADS / 2 + ((size_t)want * cap + 7) / 8 + 8;
+}
+
+// Factor T - x I = P L U (partial pivoting, as LAPACK dgttrf) once, keep it, and run `iters` inverse-iteration solves.
+// One thread per Ritz vector.  du2[i] (second super-diagonal of U) is b[i+1] where rows were swapped, else 0.
+__device__ void inverse_iteration_thread(const CheckSmem& cs, int n, int cap, int col, double x, double tiny) {
+    double* di = cs.di + (size_t)col * cap;
+    double* du = cs.du + (size_t)col * cap; double* ff = cs.ff + (size_t)col * cap;
+    unsigned char* swp = cs.swp + (size_t)col * cap;
+    const double* a = cs.a; const double* b = cs.b;
+    // factorisation
+    double d = a[0] - x;                    // current pivot candidate d[i]
+    double dui = n > 1 ? b[0] : 0.0;        // du[i] as modified by the previous step
+    for (int i = 0; i < n - 1; ++i) {
+        const double dl = b[i];
+        const double dn = a[i + 1] - x;     // unmodified d[i+1]
+        const double dun = (i < n - 2) ? b[i + 1] : 0.0;   // unmodified du[i+1]
+        if (fabs(d) >= fabs(dl)) {
+            if (d == 0.0) d = tiny;
+            const double f = dl / d;
+            ff[i] = f; swp[i] = 0;
+            di[i] = 1.0 / d; du[i] = dui;
+            d = dn - f * dui;
+            dui = dun;
+        } else {                            // swap rows i and i+1
+            const double f = d / dl;
+            ff[i] = f; swp[i] = 1;
+            di[i] = 1.0 / dl; du[i] = dn;   // U[i][i] = dl, U[i][i+1] = old d[i+1], U[i][i+2] = old du[i+1]
+            d = dui - f * dn;
+            dui = -f * dun;
+        }
+    }
+    if (d == 0.0) d = tiny;
+    di[n - 1] = 1.0 / d; du[n - 1] = 0.0;
+}
+
+__device__ void inverse_solve_thread(const CheckSmem& cs, int n, int cap, int col) {
+    double* y = cs.y + (size_t)col * cap; const double* di = cs.di + (size_t)col * cap;
+    const double* du = cs.du + (size_t)col * cap; const double* ff = cs.ff + (size_t)col * cap;
+    const unsigned char* swp = cs.swp + (size_t)col * cap;
+    const double* b = cs.b;
+    // forward: apply P L^-1
+    double yi = y[0];
+    for (int i = 0; i < n - 1; ++i) {
+        const double yn = y[i + 1];
+        if (!swp[i]) { y[i] = yi; yi = yn - ff[i] * yi; }
+        else { y[i] = yn; yi = yi - ff[i] * yn; }
+    }
+    y[n - 1] = yi;
+    // backward: U z = y
+    double z1 = y[n - 1] * di[n - 1], z2 = 0.0;
+    y[n - 1] = z1;
+    for (int i = n - 2; i >= 0; --i) {
+        const double du2 = (swp[i] && i < n - 2) ? b[i + 1] : 0.0;
+        const double z = (y[i] - du[i] * z1 - du2 * z2) * di[i];
+        y[i] = z;
+        z2 = z1; z1 = z;
+    }
+}
+
+// Runs by all threads of a checker CTA.  Returns (in every thread) whether the kw leading pairs (and the guard pairs at
+// 1e-5) have converged for T_n; theta / y hold the `want` leading Ritz values and unit Ritz vectors of T_n afterwards.
+__device__ bool check_converged(const CheckSmem& cs, int n, int cap, int kw, int guard, double tol, int* want_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int want = min(kw + guard, n);
+    *want_out = want;
+    // Gershgorin interval and norm
+    double glo = 1e300, ghi = -1e300, tn = 0.0;
+    for (int i = tid; i < n; i += CH_THREADS) {
+        const double r = (i > 0 ? fabs(cs.b[i - 1]) : 0.0) + (i < n - 1 ? fabs(cs.b[i]) : 0.0);
+        glo = fmin(glo, cs.a[i] - r); ghi = fmax(ghi, cs.a[i] + r); tn = fmax(tn, fabs(cs.a[i]) + r);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        glo = fmin(glo, __shfl_xor_sync(0xffffffffu, glo, o));
+        ghi = fmax(ghi, __shfl_xor_sync(0xffffffffu, ghi, o));
+        tn = fmax(tn, __shfl_xor_sync(0xffffffffu, tn, o));
+    }
+    __syncthreads();
+    if (lane == 0) { cs.red[warp] = glo; cs.red[CH_WARPS + warp] = ghi; cs.red[2 * CH_WARPS + warp] = tn; }
+    __syncthreads();
+    glo = cs.red[0]; ghi = cs.red[CH_WARPS]; tn = cs.red[2 * CH_WARPS];
+    for (int w = 1; w < CH_WARPS; ++w) { glo = fmin(glo, cs.red[w]); ghi = fmax(ghi, cs.red[CH_WARPS + w]); tn = fmax(tn, cs.red[2 * CH_WARPS + w]); }
+    __syncthreads();
+    const double span = ghi - glo;
+    glo -= 1e-12 * span + 1e-300; ghi += 1e-12 * span + 1e-300;
+
+    // ---- multisection: round 0 places CH_THREADS points over the whole interval, later rounds P points per eigenvalue ----
+    // eigenvalue i (descending) = smallest x with below(x) >= n - i
+    if (tid < want) { cs.lo[tid] = glo; cs.hi[tid] = ghi; }
+    __syncthreads();
+    const int P = CH_THREADS / want;                            // points per eigenvalue
+    for (int round = 0; round < 64; ++round) {
+        double x; int e = -1;
+        if (round == 0) {
+            x = glo + (ghi - glo) * ((double)(tid + 1) / (double)(CH_THREADS + 1));
+        } else {
+            e = tid / P;
+            const int q = tid - e * P;
+            if (e < want) { const double l = cs.lo[e], h = cs.hi[e]; x = l + (h - l) * ((double)(q + 1) / (double)(P + 1)); }
+            else x = 0.0;
+        }
+        int c = 0;
+        if (round == 0 || e < want) c = sturm_below(cs.a, cs.b2, n, x);
+        cs.cnt[tid] = c;
+        cs.xs[tid] = x;
+        __syncthreads();
+        // narrowing: thread e (< want) scans its points (monotone counts)
+        bool moved = false;
+        if (tid < want) {
+            const int target = n - tid;
+            double l = cs.lo[tid], h = cs.hi[tid];
+            const int p0 = (round == 0) ? 0 : tid * P, p1 = (round == 0) ? CH_THREADS : p0 + P;
+            for (int q = p0; q < p1; ++q) {
+                const double xq = cs.xs[q];
+                if (!(xq > l && xq < h)) continue;
+                if (cs.cnt[q] >= target) { h = xq; break; }
+                l = xq;
+            }
+            moved = (l != cs.lo[tid]) || (h != cs.hi[tid]);
+            cs.lo[tid] = l; cs.hi[tid] = h;
+        }
+        const int any = __syncthreads_or(moved ? 1 : 0);
+        if (!any) break;
+    }
+    if (tid < want) cs.theta[tid] = 0.5 * (cs.lo[tid] + cs.hi[tid]);
+    __syncthreads();
+
+    // ---- inverse iteration, one thread per Ritz vector; vectors of a cluster are orthogonalised in index order ----
+    const double tiny = fmax(tn * 2.2e-16, 1e-300);
+    const double cluster_tol = 1e-3 * tn;
+    if (tid < want) {
+        int cstart = tid;
+        while (cstart > 0 && fabs(cs.theta[cstart] - cs.theta[cstart - 1]) <= cluster_tol) --cstart;
+        double x = cs.theta[tid];
+        if (tid > cstart && fabs(x - cs.theta[tid - 1]) < 10.0 * tiny) x = cs.theta[tid - 1] - 10.0 * tiny * (tid - cstart);
+        inverse_iteration_thread(cs, n, cap, tid, x, tiny);
+        double* y = cs.y + (size_t)tid * cap;
+        unsigned int seed = 12345u + 7919u * (unsigned int)tid;
+        for (int r = 0; r < n; ++r) { seed = seed * 1664525u + 1013904223u; y[r] = ((double)(seed >> 8) / 16777216.0) - 0.5; }
+    }
+    __syncthreads();
+    for (int it = 0; it < 4; ++it) {
+        if (tid < want) inverse_solve_thread(cs, n, cap, tid);
+        __syncthreads();
+        // warp 0: normalise; orthogonalise vector i against the earlier vectors of its cluster (two passes), in index order
+        if (warp == 0) {
+            int cstart = 0;
+            for (int i = 0; i < want; ++i) {
+                if (i > 0 && fabs(cs.theta[i] - cs.theta[i - 1]) > cluster_tol) cstart = i;
+                double* yi = cs.y + (size_t)i * cap;
+                for (int pass = 0; pass < 2; ++pass)
+                    for (int pp = cstart; pp < i; ++pp) {
+                        const double* yp = cs.y + (size_t)pp * cap;
+                        double dot = 0.0;
+                        for (int r = lane; r < n; r += 32) dot = fma(yp[r], yi[r], dot);
+                        dot = wsum(dot);
+                        for (int r = lane; r < n; r += 32) yi[r] -= dot * yp[r];
+                        __syncwarp();
+                    }
+                double nrm = 0.0;
+                for (int r = lane; r < n; r += 32) nrm = fma(yi[r], yi[r], nrm);
+                nrm = sqrt(wsum(nrm));
+                if (!(nrm > 0.0) || !(nrm < 1e300)) {
+                    for (int r = lane; r < n; r += 32) yi[r] = (r == (i % n)) ? 1.0 : 0.0;
+                } else {
+                    const double inv = 1.0 / nrm;
+                    for (int r = lane; r < n; r += 32) yi[r] *= inv;
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    }
+    // ---- residual estimates |beta_n s_{n,i}| ----
+    const double scale = fmax(fabs(cs.theta[0]), 1e-300);
+    const double beta_last = cs.b[n - 1];
+    bool ok = (n >= kw);
+    for (int i = 0; i < want; ++i) {
+        const double res = fabs(beta_last * cs.y[(size_t)i * cap + (n - 1)]);
+        if (!(res <= (i < kw ? tol : 1e-5) * scale)) ok = false;
+    }
+    return ok;
+}
+
+__device__ void checker_main(const Params& p, double* smem, int c) {
+    const int tid = threadIdx.x;
+    const int cap = p.max_steps + 2;
+    CheckSmem cs;
+    double* q = smem;
+    cs.a = q; q += cap; cs.b = q; q += cap; cs.b2 = q; q += cap;
+    cs.theta = q; q += CH_MAXWANT; cs.lo = q; q += CH_MAXWANT; cs.hi = q; q += CH_MAXWANT;
+    cs.red = q; q += 3 * CH_WARPS;
+    const int wmax = min(p.kw + p.guard, CH_MAXWANT);
+    cs.y = q; q += (size_t)wmax * cap; cs.di = q; q += (size_t)wmax * cap; cs.du = q; q += (size_t)wmax * cap; cs.ff = q; q += (size_t)wmax * cap;
+    cs.xs = q; q += CH_THREADS;
+    cs.cnt = reinterpret_cast<int*>(q); q += CH_THREADS / 2;
+    cs.swp = reinterpret_cast<unsigned char*>(q);
+    __shared__ int s_n;
+    __shared__ int s_mode;
+    int have = 0;                                              // alpha/beta of steps 1..have are in shared memory
+    int next_n = p.first_check + c;
+    for (;;) {
+        // ---- wait for the next size to test (thread 0 decides) ----
+        if (tid == 0) {
+            int mode = 0, n = 0;                               // mode 1 = test T_n, 2 = final forced/unforced test, 3 = leave
+            const long long t0 = now();
+            for (;;) {
+                if (ld_word(&p.ctl->stop) != 0u || ld_word(&p.ctl->abort) != 0u) { mode = 3; break; }
+                const unsigned int fin = ld_word(&p.ctl->final_n);
+                if (fin != 0u) {
+                    if (c != 0) { mode = 3; break; }
+                    n = (int)(fin & 0xffffu); mode = ((fin >> 30) & 1u) ? 4 : 2;       // 4 = breakdown: accept
+                    if (n >= p.cap_steps) mode = 4;                                     // Krylov space exhausted: T_n is exact
+                    break;
+                }
+                const int prog = (int)ld_word(&p.ctl->progress);
+                if (prog >= next_n) { n = prog; mode = 1; break; }
+                if (now() - t0 > CH_TIMEOUT) { st_word(&p.ctl->abort, 1u); mode = 3; break; }
+                relax();
+            }
+            s_n = n; s_mode = mode;
+        }
+        __syncthreads();
+        const int n = s_n, mode = s_mode;
+        if (mode == 3 || n < 1) return;
+        // ---- fetch alpha/beta of the steps not yet seen ----
+        int bad = 0;
+        for (int jj = have + 1 + tid; jj <= n; jj += CH_THREADS) {
+            double av, bv;
+            if (!wait_ll(p.abuf + 2 * (size_t)jj, 1u, av, p.ctl) || !wait_ll(p.abuf + 2 * (size_t)jj + 1, 1u, bv, p.ctl)) { bad = 1; break; }
+            cs.a[jj - 1] = av; cs.b[jj - 1] = bv; cs.b2[jj - 1] = bv * bv;
+        }
+        if (__syncthreads_or(bad)) return;
+        have = n;
+        int want = 0;
+        const bool ok = check_converged(cs, n, cap, p.kw, p.guard, p.tol, &want);
+        if (ok || mode == 4 || mode == 2) {
+            if (ok || mode == 4) {
+                // publish theta and S [n][kw] of this checker, then try to win the stop word
+                double* th = p.theta_out + (size_t)c * CH_MAXWANT;
+                double* S = p.S_out + (size_t)c * p.s_stride;
+                if (tid < CH_MAXWANT) th[tid] = tid < want ? cs.theta[tid] : 0.0;
+                for (int idx = tid; idx < n * p.kw; idx += CH_THREADS) {
+                    const int l = idx / p.kw, i = idx - l * p.kw;
+                    S[idx] = i < want ? cs.y[(size_t)i * cap + l] : 0.0;
+                }
+                publish_fence();
+                __syncthreads();
+                if (tid == 0) {
+                    const unsigned int word = 0x80000000u | ((unsigned int)c << 16) | (unsigned int)n;
+                    if (cas_word(&p.ctl->stop, 0u, word) == 0u) {
+                        p.ctl->n_final = n; p.ctl->winner = c; p.ctl->status = (want >= p.kw) ? 1 : 2;
+                    }
+                }
+            } else if (tid == 0) {
+                if (cas_word(&p.ctl->stop, 0u, 0x80000000u) == 0u) { p.ctl->n_final = n; p.ctl->winner = -1; p.ctl->status = 2; }
+            }
+            return;
+        }
+        next_n = n + 1;
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CH_THREADS, 1) lanczos_chain_kernel(Params p) {
+    extern __shared__ double ch_smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.x;
+    if (b >= p.n_workers) {
+        if (b - p.n_workers < p.n_checkers) checker_main(p, ch_smem, b - p.n_workers);
+        return;
+    }
+    const int m = p.m, nW = p.n_workers, cap = p.vs_cap;
+    const int row0 = b * p.chunk, n_own = min(p.chunk, m - row0);           // 1 .. CH_MAXROWS
+    const int n_sm = max(0, n_own - CH_REGROWS);                             // rows in shared memory; the rest in registers
+    double* s_vec = ch_smem;                                                 // [m]   q_j
+    double* s_rows = s_vec + m;                                              // [n_sm][m]
+    double* Vs = s_rows + (size_t)n_sm * m;                                  // [n_own][cap]
+    __shared__ double s_red[CH_WARPS * 16];
+    __shared__ double s_w[16];
+    __shared__ double s_upd[16];
+    __shared__ double s_h[CH_THREADS + 8];
+    __shared__ double s_sc[4];
+    __shared__ unsigned int s_stop;
+    Ctl* ctl = p.ctl;
+    long long t_prof = now();
+#define CH_PROF(slot) do { if (p.prof_on && b == 0 && tid == 0) { const long long t_ = now(); ctl->prof[slot] += t_ - t_prof; t_prof = t_; } } while (0)
+
+    // ---- once: rows of Ms on chip, v0 / q1 on the owned rows, q1 everywhere ----
+    for (int rr = 0; rr < n_sm; ++rr) {
+        const double* a = p.Ms + (size_t)(row0 + rr) * m;
+        for (int c = tid; c < m; c += CH_THREADS) s_rows[(size_t)rr * m + c] = __ldg(a + c);
+    }
+    double rrow[CH_REGROWS][4];
+#pragma unroll
+    for (int e = 0; e < CH_REGROWS; ++e)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = tid + CH_THREADS * u;
+            rrow[e][u] = (n_sm + e < n_own && c < m) ? __ldg(p.Ms + (size_t)(row0 + n_sm + e) * m + c) : 0.0;
+        }
+    for (int c = tid; c < m; c += CH_THREADS) s_vec[c] = p.V[(size_t)m + c];
+    if (tid < 2 * n_own) { const int r = tid >> 1, i = tid & 1; Vs[(size_t)r * cap + i] = p.V[(size_t)i * m + row0 + r]; }
+    double sigma = 0.0, beta_prev = 0.0, alpha1 = 0.0;
+    __syncthreads();
+    CH_PROF(0);
+
+    int j = 1;
+    int end_reason = 0;                                                      // 1 stop word, 2 breakdown, 3 max_steps, 4 abort
+    for (; j <= p.max_steps; ++j) {
+        // ---- S0: w = Ms q_j - sigma q_j - beta_{j-1} q_{j-1} on the owned rows ----
+        {
+            double acc[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) acc[q] = 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = tid + CH_THREADS * u;
+                if (c < m) {
+                    const double qv = s_vec[c];
+#pragma unroll
+                    for (int q = 0; q < CH_MAXROWS - CH_REGROWS; ++q)
+                        if (q < n_sm) acc[q] = fma(s_rows[(size_t)q * m + c], qv, acc[q]);
+#pragma unroll
+                    for (int e = 0; e < CH_REGROWS; ++e) acc[CH_MAXROWS - CH_REGROWS + e] = fma(rrow[e][u], qv, acc[CH_MAXROWS - CH_REGROWS + e]);
+                }
+            }
+            const double t = multi_sum16(acc, lane);
+            if ((lane & 1) == 0) s_red[warp * 16 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = t;
+            __syncthreads();
+            if (tid < n_own) {
+                const int slot = tid < n_sm ? tid : (CH_MAXROWS - CH_REGROWS) + (tid - n_sm);
+                double tot = 0.0;
+#pragma unroll
+                for (int w2 = 0; w2 < CH_WARPS; ++w2) tot += s_red[w2 * 16 + slot];
+                const double qr = Vs[(size_t)tid * cap + j];
+                double x = fma(-sigma, qr, tot);
+                if (j >= 2) x = fma(-beta_prev, Vs[(size_t)tid * cap + j - 1], x);
+                s_w[tid] = x;
+            }
+            __syncthreads();
+        }
+        CH_PROF(1);
+
+        double alpha_j = sigma, beta_j = 0.0;
+        bool leave = false;
+        for (int pass = 0; pass < 2; ++pass) {
+            const unsigned int tag = 2u * (unsigned int)j + (unsigned int)pass;
+            const int n_slots = j + 2;                                       // slot 0: |w|^2, slot 1 + i: V_i . w, i = 0..j
+            // ---- P1: partial coefficients of the owned rows ----
+            for (int s = tid; s < n_slots; s += CH_THREADS) {
+                double v = 0.0;
+                if (s == 0) { for (int r = 0; r < n_own; ++r) v = fma(s_w[r], s_w[r], v); }
+                else { for (int r = 0; r < n_own; ++r) v = fma(Vs[(size_t)r * cap + (s - 1)], s_w[r], v); }
+                st_ll(p.pbuf + (size_t)s * nW + b, v, tag);
+            }
+            // ---- P2: slots owned by this CTA: fixed-order sum of all workers' partials ----
+            int bad = 0;
+            for (int s = b + warp * nW; s < n_slots; s += CH_WARPS * nW) {
+                double v = 0.0;
+                for (int c = lane; c < nW; c += 32) {
+                    double x;
+                    if (!wait_ll(p.pbuf + (size_t)s * nW + c, tag, x, ctl)) { bad = 1; break; }
+                    v += x;
+                }
+                v = wsum(v);
+                if (lane == 0) {
+                    st_ll(p.hbuf + s, v, tag);
+                    if (s == 0) {                                            // CTA 0 forwards the stop word with slot 0
+                        const unsigned int stop = ld_word(&ctl->stop) != 0u ? 1u : 0u;
+                        st_ll(p.hbuf + (p.max_steps + 2), (double)stop, tag);
+                    }
+                }
+            }
+            // ---- P3: all coefficients ----
+            for (int s = tid; s < n_slots; s += CH_THREADS) {
+                double x;
+                if (!wait_ll(p.hbuf + s, tag, x, ctl)) { bad = 1; break; }
+                s_h[s] = x;
+            }
+            if (tid == CH_THREADS - 1) {
+                double x = 0.0;
+                if (!wait_ll(p.hbuf + (p.max_steps + 2), tag, x, ctl)) bad = 1;
+                s_stop = x != 0.0 ? 1u : 0u;
+            }
+            if (__syncthreads_or(bad)) { end_reason = 4; leave = true; break; }
+            if (s_stop) { end_reason = 1; leave = true; break; }
+            CH_PROF(2 + pass * 4);
+            // update of the owned rows (warp r) and sum of squares of the coefficients (last warp)
+            if (warp < n_own) {
+                const double* vr = Vs + (size_t)warp * cap;
+                double a0 = 0.0, a1 = 0.0;
+                int i = lane;
+                for (; i + 32 <= j; i += 64) { a0 = fma(vr[i], s_h[1 + i], a0); a1 = fma(vr[i + 32], s_h[1 + i + 32], a1); }
+                if (i <= j) a0 = fma(vr[i], s_h[1 + i], a0);
+                const double tot = wsum(a0 + a1);
+                if (lane == 0) s_upd[warp] = s_w[warp] - tot;
+            } else if (warp == CH_WARPS - 1) {
+                double a0 = 0.0;
+                for (int i = lane; i <= j; i += 32) a0 = fma(s_h[1 + i], s_h[1 + i], a0);
+                a0 = wsum(a0);
+                if (lane == 0) s_sc[0] = a0;
+            }
+            __syncthreads();
+            const double ww = s_h[0], after = ww - s_sc[0];
+            alpha_j += s_h[1 + j];
+            if (tid < n_own) s_w[tid] = s_upd[tid];
+            if (pass == 0 && after < 0.5 * ww) { __syncthreads(); continue; }   // DGKS: orthogonalise once more
+            beta_j = after > 0.0 ? sqrt(after) : 0.0;
+            break;
+        }
+        if (leave) break;
+        if (j == 1) alpha1 = alpha_j;
+        // ---- q_{j+1} on the owned rows -> Vs, global V, packets; alpha/beta for the checkers and the host ----
+        const bool breakdown = !(beta_j > 1e-14 * fmax(fabs(alpha1), 1e-300));
+        const double inv = beta_j > 0.0 ? 1.0 / beta_j : 0.0;
+        __syncthreads();
+        if (tid < n_own) {
+            const double x = s_w[tid] * inv;
+            Vs[(size_t)tid * cap + j + 1] = x;
+            p.V[(size_t)(j + 1) * m + row0 + tid] = x;
+            st_ll(p.qbuf + row0 + tid, x, 2u * (unsigned int)j);
+        }
+        if (b == 0 && tid == 32) {
+            p.alpha[j - 1] = alpha_j; p.beta[j - 1] = beta_j;
+            st_ll(p.abuf + 2 * (size_t)j, alpha_j, 1u);
+            st_ll(p.abuf + 2 * (size_t)j + 1, beta_j, 1u);
+            publish_fence();
+            st_word(&ctl->progress, (unsigned int)j);
+        }
+        CH_PROF(3);
+        if (breakdown) { end_reason = 2; ++j; break; }
+        if (j == p.max_steps) { end_reason = 3; ++j; break; }
+        // ---- P4: the whole next vector ----
+        int bad = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = tid + CH_THREADS * u;
+            if (c < m) {
+                double x;
+                if (!wait_ll(p.qbuf + c, 2u * (unsigned int)j, x, ctl)) { bad = 1; break; }
+                s_vec[c] = x;
+            }
+        }
+        if (__syncthreads_or(bad)) { end_reason = 4; ++j; break; }
+        sigma = alpha_j; beta_prev = beta_j;
+        CH_PROF(4);
+    }
+    // j - 1 = steps completed
+    if (b == 0 && tid == 0) {
+        ctl->steps_run = j - 1;
+        if (end_reason == 2 || end_reason == 3) {
+            publish_fence();
+            st_word(&ctl->final_n, 0x80000000u | (end_reason == 2 ? 0x40000000u : 0u) | (unsigned int)(j - 1));
+        }
+    }
+#undef CH_PROF
+}
+
+// U[r][1+i] = sum_l V_{1+l}[r] S[l][i] with the step count and S of the winning checker read on the device; U[r][0] = V_0[r].
+__global__ void __launch_bounds__(128) ritz_chain_kernel(const double* __restrict__ V, int m, const Ctl* __restrict__ ctl,
+                                                         const double* __restrict__ S_base, int s_stride, int kw,
+                                                         double* __restrict__ U, int k) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (r >= m) return;
+    if (i == 0) { U[(size_t)r * k] = V[r]; return; }
+    const int steps = ctl->n_final, win = ctl->winner;
+    if (win < 0 || steps < 1) { U[(size_t)r * k + i] = 0.0; return; }
+    const double* S = S_base + (size_t)win * s_stride;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int l = 0;
+    for (; l + 3 < steps; l += 4) {
+        a0 = fma(V[(size_t)(1 + l) * m + r], S[(size_t)l * kw + (i - 1)], a0);
+        a1 = fma(V[(size_t)(2 + l) * m + r], S[(size_t)(l + 1) * kw + (i - 1)], a1);
+        a2 = fma(V[(size_t)(3 + l) * m + r], S[(size_t)(l + 2) * kw + (i - 1)], a2);
+        a3 = fma(V[(size_t)(4 + l) * m + r], S[(size_t)(l + 3) * kw + (i - 1)], a3);
+    }
+    for (; l < steps; ++l) a0 = fma(V[(size_t)(1 + l) * m + r], S[(size_t)l * kw + (i - 1)], a0);
+    U[(size_t)r * k + i] = (a0 + a1) + (a2 + a3);
+}
+// ---- end chain kernel text ----
+
+}  // namespace chain
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Host side.  Preconditions (checked by chain_plan): 32 <= m <= 2048, ceil(m / (SMs - 1)) <= 14, kw + guard <= 16.
+// V[0] (locked vector) and V[1] (start vector) are already on the device.  On success U_d [m, k] holds the unnormalised Ritz
+// vectors (column 0 = V[0]) and the result block is on its way to the host; the caller synchronises.
+// Returns ESPER_OK, an error, or +1 = "not handled / not converged here: use the barrier kernels".
+// ---------------------------------------------------------------------------------------------------------------------
+struct ChainPlan {
+    bool ok = false;
+    int chunk = 0, n_workers = 0, n_checkers = 0, n_sm = 0, vs_cap = 0, max_steps = 0;
+    size_t smem = 0;
+};
+
+static ChainPlan chain_plan(esper_ctx* c, int m, int kw, int guard, int max_iter, long long smem_limit) {
+    using namespace chain;
+    ChainPlan pl;
+    if (m < 32 || m > CH_MAXM || kw < 1 || kw + guard > CH_MAXWANT || c->sm_count < 2) return pl;
+    pl.chunk = ceil_div(m, c->sm_count - 1);
+    if (pl.chunk > CH_MAXROWS) return pl;
+    pl.n_workers = ceil_div(m, pl.chunk);
+    pl.n_checkers = std::min(c->sm_count - pl.n_workers, CH_MAXCHK);
+    if (pl.n_checkers < 1) return pl;
+    pl.n_sm = std::max(0, pl.chunk - CH_REGROWS);
+    const size_t fixed = sizeof(double) * ((size_t)m + (size_t)pl.n_sm * m);
+    if ((long long)fixed + 4096 > smem_limit) return pl;
+    // workers: Vs [chunk][vs_cap]; checkers: 3 cap + 3*16 + 18 + 4 want cap doubles + counters + swap flags
+    const int want = kw + guard;
+    int steps = std::min(max_iter, CH_THREADS - 2);                            // all coefficients of a step: one packet per thread
+    while (steps >= 32 && (fixed + sizeof(double) * (size_t)pl.chunk * (steps + 2) > (size_t)smem_limit ||
+                           sizeof(double) * checker_doubles(want, steps + 2) > (size_t)smem_limit)) steps -= 2;
+    if (steps < std::min(max_iter, 96)) return pl;
+    pl.max_steps = steps;
+    pl.vs_cap = steps + 2;
+    pl.smem = std::max(fixed + sizeof(double) * (size_t)pl.chunk * pl.vs_cap, sizeof(double) * checker_doubles(want, steps + 2));
+    pl.ok = (long long)pl.smem <= smem_limit;
+    return pl;
+}
+
+int run_lanczos_chain(esper_ctx* c, int m, int k, int guard, double tol, int max_iter, double* V, double* U_d) {
+    using namespace chain;
+    const int kw = k - 1;
+    cudaStream_t st = c->stream;
+    if (!c->chain_smem_set) {
+        int optin = 0;
+        cudaFuncAttributes fa;
+        ESPER_CUDA(c, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+        ESPER_CUDA(c, cudaFuncGetAttributes(&fa, lanczos_chain_kernel));
+        ESPER_CUDA(c, cudaFuncSetAttribute(lanczos_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+        c->chain_smem_set = optin - (long long)fa.sharedSizeBytes;
+    }
+    const ChainPlan pl = chain_plan(c, m, kw, guard, max_iter, c->chain_smem_set);
+    if (!pl.ok) return 1;
+    int per_sm = 0;
+    ESPER_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lanczos_chain_kernel, CH_THREADS, pl.smem));
+    if (per_sm < 1) return 1;
+
+    // workspace: packets | ctl | theta | S | alpha, beta
+    const int slots = pl.max_steps + 3;
+    const size_t n_p = (size_t)slots * pl.n_workers, n_h = (size_t)slots + 1, n_q = (size_t)m, n_a = 2 * ((size_t)pl.max_steps + 2);
+    const size_t pk_bytes = sizeof(uint4) * (n_p + n_h + n_q + n_a);
+    const int s_stride = pl.max_steps * kw;
+    const size_t bytes = pk_bytes + sizeof(Ctl) + 64 + sizeof(double) * ((size_t)CH_MAXCHK * CH_MAXWANT + (size_t)CH_MAXCHK * s_stride + 2 * ((size_t)pl.max_steps + 8));
+    ESPER_RESERVE(c, c->chain_ws, bytes);
+    char* base = c->chain_ws.as<char>();
+    uint4* pbuf = reinterpret_cast<uint4*>(base);
+    uint4* hbuf = pbuf + n_p; uint4* qbuf = hbuf + n_h; uint4* abuf = qbuf + n_q;
+    Ctl* ctl = reinterpret_cast<Ctl*>(base + pk_bytes);
+    double* theta_d = reinterpret_cast<double*>(base + pk_bytes + ((sizeof(Ctl) + 63) / 64) * 64);
+    double* S_d = theta_d + (size_t)CH_MAXCHK * CH_MAXWANT;
+    double* alpha_d = S_d + (size_t)CH_MAXCHK * s_stride;
+    double* beta_d = alpha_d + pl.max_steps + 4;
+    // tags repeat from one solve to the next: the packet buffers and the control block start from zero every time
+    ESPER_CUDA(c, cudaMemsetAsync(base, 0, pk_bytes + sizeof(Ctl), st));
+
+    Params p;
+    p.Ms = c->markov.as<double>(); p.m = m; p.V = V; p.alpha = alpha_d; p.beta = beta_d;
+    p.chunk = pl.chunk; p.n_workers = pl.n_workers; p.n_checkers = pl.n_checkers;
+    p.max_steps = pl.max_steps; p.vs_cap = pl.vs_cap;
+    p.kw = kw; p.guard = guard; p.cap_steps = m - 1; p.tol = tol;
+    p.first_check = std::min(pl.max_steps, std::max(3 * (kw + guard) + 8, 32));
+    p.pbuf = pbuf; p.hbuf = hbuf; p.qbuf = qbuf; p.abuf = abuf; p.ctl = ctl;
+    p.theta_out = theta_d; p.S_out = S_d; p.s_stride = s_stride;
+    p.prof_on = getenv("ESPER_DEBUG_LANCZOS") ? 1 : 0;
+    {
+        LaunchScope ls(c, "lanczos");
+        void* args[] = {&p};
+        cudaError_t e = cudaLaunchCooperativeKernel((void*)lanczos_chain_kernel, dim3(c->sm_count), dim3(CH_THREADS), args, pl.smem, st);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(c, ESPER_E_CUDA, "cooperative launch (chain): %s", cudaGetErrorString(e)); }
+    }
+    { LaunchScope ls(c, "lanczos"); ritz_chain_kernel<<<dim3(ceil_div(m, 128), k), 128, 0, st>>>(V, m, ctl, S_d, s_stride, kw, U_d, k); }
+    ESPER_CUDA(c, cudaGetLastError());
+    // result block -> pinned host memory (same stream; the caller's final synchronise covers it)
+    if (c->pin_chain.reserve(sizeof(Ctl) + sizeof(double) * CH_MAXCHK * CH_MAXWANT) != 0) return fail(c, ESPER_E_NOMEM, "pinned alloc failed");
+    ESPER_CUDA(c, cudaMemcpyAsync(c->pin_chain.p, ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+    ESPER_CUDA(c, cudaMemcpyAsync(c->pin_chain.as<char>() + sizeof(Ctl), theta_d, sizeof(double) * CH_MAXCHK * CH_MAXWANT, cudaMemcpyDeviceToHost, st));
+    return ESPER_OK;
+}
+
+// After the stream has been synchronised: decode the result block.  Returns ESPER_OK, +1 (fall back) or an error.
+int chain_result(esper_ctx* c, int k, double* theta_out, int* iters_out) {
+    using namespace chain;
+    const Ctl* h = c->pin_chain.as<Ctl>();
+    const double* th = reinterpret_cast<const double*>(c->pin_chain.as<char>() + sizeof(Ctl));
+    if (getenv("ESPER_DEBUG_LANCZOS")) {
+        fprintf(stderr, "[chain] status=%d n_final=%d winner=%d steps_run=%d abort=%u stop=%08x\n", h->status, h->n_final, h->winner, h->steps_run, h->abort, h->stop);
+        const double n = h->steps_run > 0 ? (double)h->steps_run : 1.0;
+        fprintf(stderr, "[chain] CTA0 cycles/step: S0 %.0f | P1-P3 %.0f | norm+publish %.0f | P4 %.0f | second pass %.0f ; prologue %lld\n",
+                h->prof[1] / n, h->prof[2] / n, h->prof[3] / n, h->prof[4] / n, h->prof[6] / n, h->prof[0]);
+    }
+    if (h->abort != 0u) return fail(c, ESPER_E_CUDA, "lanczos (chain): a packet wait timed out (CTAs not co-resident?)");
+    if (h->status != 1 || h->winner < 0) return 1;
+    const int kw = k - 1;
+    for (int i = 0; i < kw; ++i) theta_out[i] = th[(size_t)h->winner * CH_MAXWANT + i];
+    if (iters_out) *iters_out = h->n_final;
+    return ESPER_OK;
+}
+
+}  // namespace esper

@@ -1159,7 +1159,7 @@ static int lanczos_attempt(esper_ctx* c, int m, int k, double tol, int max_iter,
         const int chunk_rows = ceil_div(m, c->sm_count);
         const size_t budget = (size_t)(227 - 16) * 1024 - sizeof(double) * LAN_CH;  // per-CTA limit minus static arrays
         small = (m <= LAN_CH && chunk_rows <= 16);          // whole vector in shared memory, one warp per owned row
-        if (small && c->lanczos_mode == 0) {
+        if (small && (c->lanczos_mode == 0 || c->lanczos_mode == 3)) {
             rows_cached = (int)std::min<size_t>(std::min(chunk_rows, 14), budget / (sizeof(double) * (size_t)m));
             resident = chunk_rows <= rows_cached + 2;
         }
@@ -1223,6 +1223,36 @@ static int lanczos_attempt(esper_ctx* c, int m, int k, double tol, int max_iter,
             { LaunchScope ls(c, "lanczos"); update_kernel<<<ceil_div(m, 256), 256, 0, st>>>(V, m, 1, h, w2, nullptr); }
         }
         { LaunchScope ls(c, "lanczos"); normalize_kernel<<<1, 1024, 0, st>>>(w2, m, V + m, nullptr); }
+    }
+
+    // Default schedule (esper_dmap_config 0): the barrier-free chain kernel with on-device convergence tests (k4_chain.cu).
+    // It returns +1 for shapes it does not cover or when it did not converge within its shared-memory basis capacity;
+    // the barrier kernels below then run the whole iteration from the same start vector.
+    if (!use_pro && kw > 0 && c->lanczos_mode == 0 && !getenv("ESPER_LANCZOS_NO_CHAIN")) {
+        ESPER_RESERVE(c, c->lan_small, sizeof(double) * ((size_t)m * k + (size_t)(max_iter + 8) * KMAX + 2 * KMAX * KMAX + 4096 + (size_t)ceil_div(m, 8) * 2));
+        double* Uc = c->lan_small.as<double>();
+        int rcc = run_lanczos_chain(c, m, k, guard, tol, max_iter, V, Uc);
+        if (rcc < 0) return rcc;
+        if (rcc == 0) {
+            { LaunchScope ls(c, "lanczos"); fix_columns_kernel<<<k, 256, 0, st>>>(Uc, m, k); }
+            ESPER_CUDA(c, cudaGetLastError());
+            if (vec_h) {
+                if (plain) ESPER_CUDA(c, cudaMemcpy2DAsync(vec_h, sizeof(double) * kw, Uc + 1, sizeof(double) * k, sizeof(double) * kw, m, cudaMemcpyDeviceToHost, st));
+                else ESPER_CUDA(c, cudaMemcpyAsync(vec_h, Uc, sizeof(double) * (size_t)m * k, cudaMemcpyDeviceToHost, st));
+            }
+            ESPER_CUDA(c, cudaStreamSynchronize(st));
+            std::vector<double> th((size_t)kw);
+            rcc = chain_result(c, k, th.data(), iters_out);
+            if (rcc < 0) return rcc;
+            if (rcc == 0) {
+                if (val_h) {
+                    if (plain) for (int i = 0; i < kw; ++i) val_h[i] = th[i];
+                    else { val_h[0] = 1.0; for (int i = 0; i < kw; ++i) val_h[1 + i] = th[i] * th[i]; }
+                }
+                return ESPER_OK;
+            }
+            c->lanczos_fallbacks++;
+        }
     }
 
     // Batches of steps; the host tests batch n while batch n+1 already runs (speculatively).

@@ -9,10 +9,15 @@ DiffusionMaps.py:166); the arithmetic per element is the same as in the single-G
     all-gather       of the Lanczos vector w = Ms q (n float64)        once per Lanczos step
 
 After the all-gather every rank orthogonalises the same replicated vector with the same deterministic
-kernels, so no further reduction is needed.  On GPUs the per-step SYMV and its all-gather are ONE kernel
-(`esper_symv_allgather_d`): every rank stores its rows of w straight into all peers' buffers over NVLink (CUDA IPC
-peer memory) as {value, step} packets, flag in the data, no fences; `CudaBackend(fused=True)` selects it, the NCCL all-gather remains as the
-reference implementation of the same exchange (`fused=False`; identical bits).  `embed_oversized` is written against a small backend interface
+kernels, so no further reduction is needed.  On GPUs the per-step SYMV and its all-gather can run as ONE exchange
+(`esper_symv_allgather_d` + `esper_comm_wait_d`): the SYMV kernel writes its rows of w as {value, step} packets (flag in the
+data, no fences) into the rank's OWN buffer, CTA by CTA as they finish, and a gather kernel on every rank PULLS all n
+packets -- its own from local memory, the others over NVLink through CUDA IPC peer mappings; `CudaBackend(fused=True)` selects
+it, the NCCL all-gather remains as the reference implementation of the same exchange (`fused=False`; identical bits).
+
+Stream contract: `CudaBackend` allocates its torch tensors and runs the NCCL collectives on the ctx's own stream
+(`esper_stream`, wrapped as a `torch.cuda.ExternalStream`), so library kernels, torch fills and collectives are ordered
+by stream order alone; `TorchComm(device, stream=backend.stream)` must be given the same stream.  `embed_oversized` is written against a small backend interface
 so that the orchestration is exercised on CPU (gloo, numpy backend in tests/) and on GPUs (NCCL, CudaBackend).
 """
 from __future__ import annotations
@@ -38,46 +43,58 @@ def row_partition(n: int, rank: int, world: int):
 class TorchComm:
     """torch.distributed collectives used by the row-block path (backend nccl on GPUs, gloo on CPU)."""
 
-    def __init__(self, device=None):
+    def __init__(self, device=None, stream=None):
+        import contextlib
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.device = device if device is not None else torch.device('cpu')
+        # GPU: every collective and staging copy is enqueued under the backend's stream (see the stream contract above)
+        self._on = (lambda: torch.cuda.stream(stream)) if stream is not None else contextlib.nullcontext
 
     def allreduce_sum(self, arr):
-        t = self.torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)).to(self.device)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
-        return t.cpu().numpy()
+        with self._on():
+            t = self.torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)).to(self.device)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+            return t.cpu().numpy()
 
     def allreduce_minmax(self, lo, hi):
         """(global min of lo, global max of hi) of two scalars."""
-        t = self.torch.tensor([-float(lo), float(hi)], dtype=self.torch.float64, device=self.device)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
-        t = t.cpu().numpy()
+        with self._on():
+            t = self.torch.tensor([-float(lo), float(hi)], dtype=self.torch.float64, device=self.device)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            t = t.cpu().numpy()
         return -float(t[0]), float(t[1])
 
     def allgather_concat(self, arr, chunk):
         """Gather equal-size (zero padded to `chunk`) float64 blocks from all ranks into one array."""
         buf = np.zeros(chunk, dtype=np.float64)
         buf[:len(arr)] = arr
-        t = self.torch.from_numpy(buf).to(self.device)
-        out = self.torch.empty(chunk * self.world, dtype=self.torch.float64, device=self.device)
-        self.dist.all_gather_into_tensor(out, t)
-        return out.cpu().numpy()
+        with self._on():
+            t = self.torch.from_numpy(buf).to(self.device)
+            out = self.torch.empty(chunk * self.world, dtype=self.torch.float64, device=self.device)
+            self.dist.all_gather_into_tensor(out, t)
+            return out.cpu().numpy()
 
     def allgather_vec(self, out_tensor, in_tensor):
-        self.dist.all_gather_into_tensor(out_tensor, in_tensor)
+        with self._on():
+            self.dist.all_gather_into_tensor(out_tensor, in_tensor)
 
 
 class CudaBackend:
-    """Row-block kernels of libesper_b200 on one GPU; vectors are torch CUDA tensors (NCCL-ready)."""
+    """Row-block kernels of libesper_b200 on one GPU; vectors are torch CUDA tensors (NCCL-ready).
+
+    All torch work of the backend (allocations, fills, collectives) is enqueued on `self.stream`, the ctx's own stream, so it
+    is ordered with the library kernels; pass `stream=backend.stream` to `TorchComm`."""
 
     def __init__(self, ctx, stack, n, P, device, fused=False):
         import torch
         self.torch, self.ctx, self.device = torch, ctx, device
         self.stack, self.n, self.P = stack, n, P
         self.fused = bool(fused)
+        self.stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=device)
+        self._step = 0                                      # packet flags: monotone over the life of the backend
 
     def dist_rows(self, row0, nrows):
         self.row0, self.nrows = row0, nrows
@@ -100,10 +117,11 @@ class CudaBackend:
 
     def lanczos_alloc(self, max_steps, rows_per, world):
         t = self.torch
-        self.V = t.zeros((max_steps + 2, self.n), dtype=t.float64, device=self.device)
-        self.w_local = t.zeros(rows_per, dtype=t.float64, device=self.device)
-        self.w_full = t.zeros(rows_per * world, dtype=t.float64, device=self.device)
-        self.ab = t.zeros((max_steps + 2, 2), dtype=t.float64, device=self.device)
+        with t.cuda.stream(self.stream):
+            self.V = t.zeros((max_steps + 2, self.n), dtype=t.float64, device=self.device)
+            self.w_local = t.zeros(rows_per, dtype=t.float64, device=self.device)
+            self.w_full = t.zeros(rows_per * world, dtype=t.float64, device=self.device)
+            self.ab = t.zeros((max_steps + 2, 2), dtype=t.float64, device=self.device)
         if self.fused and getattr(self, '_comm_key', None) != (rows_per, world):
             # one gather buffer per rank, mapped by every peer through CUDA IPC; set up once per backend and reused by
             # later embeddings (IPC mapping costs milliseconds per peer)
@@ -120,7 +138,7 @@ class CudaBackend:
             dist.all_gather_object(handles, handle)
             self.ctx.comm_open(handles, dist.get_rank(), world)
             dist.barrier()                                  # nobody reads a buffer that is not mapped everywhere yet
-            self._comm_key, self._step0 = (rows_per, world), 0
+            self._comm_key = (rows_per, world)               # a fresh buffer is zeroed; flags stay monotone anyway
 
     def lanczos_start(self, degree_all):
         self.ctx.lanczos_start_d(self.n, degree_all, self.V.data_ptr())
@@ -130,10 +148,10 @@ class CudaBackend:
 
     def symv_allgather(self, j):
         """Fused: w = Ms[rows, :] q_j stored into every rank's gather buffer; returns after enqueueing the wait."""
-        step = self._step0 + j                            # packet flags never repeat over the life of the communicator
+        self._step += 1                                   # advanced at the point of use: flags never repeat, also after a
+        step = self._step                                 # failed embedding (the same sequence on every rank)
         self.ctx.symv_allgather_d(self.nrows, self.n, self.row0, self.V[j].data_ptr(), step)
         self._w_ptr = self.ctx.comm_wait_d(step, self.n)
-        self._steps_used = j
 
     def ortho(self, j):
         w_ptr = self._w_ptr if self.fused else self.w_full.data_ptr()
@@ -145,11 +163,6 @@ class CudaBackend:
             if st:
                 raise RuntimeError('peer-memory all-gather: an element of the gathered vector never arrived (watchdog)')
 
-    def lanczos_free(self):
-        if self.fused:
-            self._step0 += getattr(self, '_steps_used', 0)  # the same on every rank (replicated recurrence)
-            self._steps_used = 0
-
     def comm_close(self):
         """Unmap the peers' buffers (collective: every rank must call it)."""
         if getattr(self, '_comm_key', None) is not None:
@@ -160,8 +173,8 @@ class CudaBackend:
             self._comm_key = None
 
     def read_ab(self, steps):
-        self.ctx.sync()
-        ab = self.ab[:steps].cpu().numpy()
+        with self.torch.cuda.stream(self.stream):
+            ab = self.ab[:steps].cpu().numpy()
         return ab[:, 0].copy(), ab[:, 1].copy()
 
     def ritz_vectors(self, steps, k, S):
@@ -262,7 +275,6 @@ def embed_oversized(backend, comm, n, k=16, eps=None, a0=None, tol=0.0, max_step
     if not converged:
         raise RuntimeError('row-block Lanczos did not converge in %d steps' % steps)
     vec = backend.ritz_vectors(steps, k, S) if kw > 0 else backend.ritz_vectors(0, 1, np.zeros((0, 0)))
-    getattr(backend, 'lanczos_free', lambda: None)()
     sync(); timings['lanczos_s'] = time.perf_counter() - t0
     val = np.concatenate(([1.0], theta[:kw] ** 2))
     out.update(eps=eps, val=val, vec=vec, steps=steps, row0=row0, nrows=nrows, timings=timings)

@@ -5,6 +5,7 @@
 // __shared__ variables become function-local statics (valid because blocks run one after the other).
 // Nothing in the product includes this file; the kernels under test are cut from the .cu sources by tests/test_emu.py.
 #pragma once
+#include <atomic>
 #include <barrier>
 #include <cmath>
 #include <cstdint>
@@ -44,8 +45,10 @@ inline double __shfl_xor_sync(unsigned, double v, int o) {
     return r;
 }
 #else
-namespace emu2 { inline void syncthreads(); inline double shfl_xor(double v, int o); }
+namespace emu2 { inline void syncthreads(); inline double shfl_xor(double v, int o); inline int syncthreads_or(int v); inline void syncwarp(); }
 inline void __syncthreads() { emu2::syncthreads(); }
+inline int __syncthreads_or(int v);
+inline void __syncwarp();
 inline double __shfl_xor_sync(unsigned, double v, int o) { return emu2::shfl_xor(v, o); }
 #endif
 inline double __ldg(const double* p) { return *p; }
@@ -93,6 +96,8 @@ inline unsigned short __half_as_ushort(__half h) { return h.bits; }
 inline long long __double_as_longlong(double d) { long long r; std::memcpy(&r, &d, 8); return r; }
 inline double __longlong_as_double(long long v) { double r; std::memcpy(&r, &v, 8); return r; }
 inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
+struct uint4 { uint32_t x, y, z, w; };
 inline double __ldcg(const double* p) { return *reinterpret_cast<const volatile double*>(p); }
 inline long long clock64() { return 0; }                                  // no watchdog in the stand-in
 inline unsigned int atomicExch(unsigned int* p, unsigned int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
@@ -124,6 +129,8 @@ static unsigned emu_cluster_size = 1;
 static std::unique_ptr<std::barrier<>> emu_cluster_bar;
 static std::vector<std::unique_ptr<std::barrier<>>> emu_block_bars;
 static thread_local std::barrier<>* emu_my_block_bar = nullptr;
+static thread_local std::atomic<int>* emu_my_or = nullptr;     // [2] per block: __syncthreads_or
+static thread_local int emu_or_parity = 0;
 static thread_local std::barrier<>* emu_my_warp_bar = nullptr;
 static thread_local double* emu_my_slots = nullptr;
 
@@ -140,6 +147,16 @@ template <class T> T* emu_dyn() { return reinterpret_cast<T*>(emu_arena + EMU_ST
 #undef EMU_SYNC_DEFINED
 namespace emu2 {
 inline void syncthreads() { emu_my_block_bar->arrive_and_wait(); }
+inline int syncthreads_or(int v) {
+    const int p = emu_or_parity; emu_or_parity ^= 1;
+    if (v) emu_my_or[p].store(1);
+    emu_my_block_bar->arrive_and_wait();
+    const int r = emu_my_or[p].load();
+    emu_my_block_bar->arrive_and_wait();
+    if (threadIdx.x == 0) emu_my_or[p].store(0);
+    return r;
+}
+inline void syncwarp() { emu_my_warp_bar->arrive_and_wait(); }
 inline double shfl_xor(double v, int o) {
     const int l = threadIdx.x & 31;
     emu_my_slots[l] = v;
@@ -149,6 +166,8 @@ inline double shfl_xor(double v, int o) {
     return r;
 }
 }  // namespace emu2
+inline int __syncthreads_or(int v) { return emu2::syncthreads_or(v); }
+inline void __syncwarp() { emu2::syncwarp(); }
 namespace cooperative_groups {
 struct cluster_group {
     unsigned num_blocks() const { return emu_cluster_size; }
@@ -173,6 +192,8 @@ void emu_launch_cluster(int grid, int threads, int cs, size_t dyn, K kernel, A..
         emu_cluster_bar = std::make_unique<std::barrier<>>(cs * threads);
         emu_block_bars.clear();
         std::vector<std::unique_ptr<std::barrier<>>> wbars;
+        std::vector<std::atomic<int>> orflags(2 * (size_t)cs);
+        for (auto& f : orflags) f.store(0);
         slots.assign((size_t)cs * warps * 32, 0.0);
         for (int r = 0; r < cs; ++r) {
             emu_block_bars.push_back(std::make_unique<std::barrier<>>(threads));
@@ -181,8 +202,9 @@ void emu_launch_cluster(int grid, int threads, int cs, size_t dyn, K kernel, A..
         std::vector<std::thread> th;
         for (int r = 0; r < cs; ++r)
             for (int t = 0; t < threads; ++t)
-                th.emplace_back([=, &wbars]() {
+                th.emplace_back([=, &wbars, &orflags]() {
                     threadIdx.x = (unsigned)t; blockIdx.x = (unsigned)(c0 + r);
+                    emu_my_or = orflags.data() + 2 * (size_t)r; emu_or_parity = 0;
                     emu_cluster_rank = (unsigned)r;
                     emu_arena = emu_arenas[r].data(); emu_off = 0;
                     emu_my_block_bar = emu_block_bars[r].get();

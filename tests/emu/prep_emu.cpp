@@ -1,6 +1,6 @@
 // prep_emu.cpp -- TEST INFRASTRUCTURE ONLY: runs the standardise-and-split kernels of csrc/k0_prep.cu (cut into
 // prep_kernels.inc by tests/test_emu.py, `__shared__` declarations rewritten to the per-block arena) on the CPU:
-// stats_split_kernel<HALF> (one CTA per image) and stats_split_cluster_kernel<HALF> (a cluster of cs CTAs per image).
+// stats_split_kernel<HALF> (one CTA per image).
 //   prep_emu raw.bin n P ld standardize xbar.bin|- half scale cs hi.bin lo.bin stat.bin
 #define EMU_ARENA_SHARED
 #define EMU_NO_WARP_SUM
@@ -42,10 +42,8 @@ int main(int argc, char** argv) {
         if (half) emu_launch_cluster(n, 512, 1, 0, stats_split_kernel<true>, (const float*)raw.data(), n, P, ld, standardize, st.data(), xb, (int)center, scale, (void*)hi.data(), (void*)lo.data());
         else emu_launch_cluster(n, 512, 1, 0, stats_split_kernel<false>, (const float*)raw.data(), n, P, ld, standardize, st.data(), xb, (int)center, scale, (void*)hi.data(), (void*)lo.data());
     } else {
-        const int qpc = (ld / 4 + cs - 1) / cs;
-        const size_t dyn = (size_t)qpc * sizeof(float4);
-        if (half) emu_launch_cluster(n * cs, 256, cs, dyn, stats_split_cluster_kernel<true>, (const float*)raw.data(), n, P, ld, standardize, st.data(), xb, (int)center, scale, (void*)hi.data(), (void*)lo.data(), qpc);
-        else emu_launch_cluster(n * cs, 256, cs, dyn, stats_split_cluster_kernel<false>, (const float*)raw.data(), n, P, ld, standardize, st.data(), xb, (int)center, scale, (void*)hi.data(), (void*)lo.data(), qpc);
+        fprintf(stderr, "prep_emu: cs must be 0 (the cluster kernel was removed)\n");
+        return 2;
     }
     write_bin(argv[10], hi.data(), hi.size());
     write_bin(argv[11], lo.data(), lo.size());

@@ -172,20 +172,14 @@ def test_eps_sweep_nonsymmetric_input(ctx):
         ctx.dmap_embed(D, 0.3, k=4)                                           # the eigensolver needs symmetry
 
 
-# Kernels written after the round's GPU budget was spent have never run on hardware: their tests are opt-in
-# (ESPER_TEST_EXPERIMENTAL=1) until a GPU session has seen them pass, so that the default suite only holds verified code.
-experimental = pytest.mark.skipif(os.environ.get('ESPER_TEST_EXPERIMENTAL', '0') == '0',
-                                  reason='not yet run on hardware; set ESPER_TEST_EXPERIMENTAL=1')
-
-
 @pytest.fixture
 def f16_operands(ctx):
+    """3xFP16 operand planes are the default; the fixture pins the mode so these tests also hold under ESPER_GRAM_F16=0."""
     ctx.gram_config(1)
     yield ctx
-    ctx.gram_config(0)
+    ctx.gram_config(1)
 
 
-@experimental
 @pytest.mark.parametrize('n,P', [(129, 1000), (257, 16), (300, 4096), (640, 16384), (700, 3000)])
 def test_f16_operands_tile_and_k_tails(f16_operands, n, P):
     """esper_gram_config(1): 3xFP16 operand planes (kind::f16) against the float64 oracle and the 3xTF32 path."""
@@ -201,7 +195,6 @@ def test_f16_operands_tile_and_k_tails(f16_operands, n, P):
     assert ctx.gram_info() == 0 and d_err(D, D0) < 2e-6
 
 
-@experimental
 def test_f16_operands_row_block_equals_full(f16_operands):
     """Row-block path with FP16 planes (gram_kernel<true>): every block holds the same bits as the rows of the full matrix."""
     ctx = f16_operands
@@ -218,7 +211,6 @@ def test_f16_operands_row_block_equals_full(f16_operands):
     assert d_err(D, O.distances_gram_f64(O.standardize_stack(X.reshape(700, 1, 3000)))) < D_TOL
 
 
-@experimental
 def test_f16_operands_fall_back_where_the_range_is_not_bounded(f16_operands):
     ctx = f16_operands
     X = np.random.default_rng(5).standard_normal((300, 999)).astype(np.float32) * 3e6 + 1
@@ -232,7 +224,6 @@ def test_f16_operands_fall_back_where_the_range_is_not_bounded(f16_operands):
         ctx.gram_config(3)
 
 
-@experimental
 def test_f16_operands_outlier_pixels(f16_operands):
     """A hot pixel makes one z-score ~ sqrt(P): the largest value the FP16 planes must hold."""
     ctx = f16_operands
@@ -244,7 +235,6 @@ def test_f16_operands_outlier_pixels(f16_operands):
     assert d_err(D, O.distances_gram_f64(O.standardize_stack(X.reshape(260, 1, 4096)))) < D_TOL
 
 
-@experimental
 def test_f16_operands_pristine_and_duplicates(f16_operands):
     """Noise-free stack (Gram cancellation regime) with every image duplicated: exact zeros, refinement, symmetry."""
     ctx = f16_operands
@@ -258,7 +248,6 @@ def test_f16_operands_pristine_and_duplicates(f16_operands):
     assert np.all(D[np.arange(0, n, 2), np.arange(1, n, 2)] == 0)
 
 
-@experimental
 def test_f16_operands_full_size_pipeline(f16_operands):
     """BASELINE config 2 with FP16 operand planes: distances, no accumulation bias, eigenvalues at fixed epsilon."""
     ctx = f16_operands
@@ -275,44 +264,20 @@ def test_f16_operands_full_size_pipeline(f16_operands):
     assert np.max(np.abs(val - val_r[:10]) / val_r[:10]) < VAL_TOL
 
 
-@experimental
-@pytest.mark.parametrize('f16', [0, 1])
-@pytest.mark.parametrize('n,P,cluster', [(70, 999, 1), (300, 16384, 1), (260, 20000, 2), (300, 62500, 4), (130, 250000, 0)])
-def test_cluster_prep_matches_the_one_cta_kernel(ctx, n, P, cluster, f16):
-    """esper_prep_config(1): the row stays in (distributed) shared memory between the statistics and the split sweep."""
-    X = (np.random.default_rng(n + P).standard_normal((n, P)) * 2.5 + 0.7).astype(np.float32)
-    ctx.gram_config(f16)
-    try:
-        D0 = ctx.dist_rms(X)
-        assert ctx.prep_info() == 0
-        ctx.prep_config(1)
-        D1 = ctx.dist_rms(X)
-        assert ctx.prep_info() == cluster
-        Du = ctx.dist_rms(X, flags=_capi.DIST_CENTER)                        # no standardisation: no statistics exchange
-    finally:
-        ctx.prep_config(0)
-        ctx.gram_config(0)
-    Du0 = ctx.dist_rms(X, flags=_capi.DIST_CENTER)
-    assert d_err(D1, D0) < 1e-6 and np.array_equal(D1, D1.T)                 # mean32 / std32 may differ in the last bit
-    assert d_err(Du, Du0) < 1e-6
-    assert d_err(D1, O.distances_gram_f64(O.standardize_stack(X.reshape(n, 1, P)))) < D_TOL
-
-
-@experimental
 @pytest.mark.parametrize('name', ['stage123_small', 'stage123_pristine', 'stage23_medium', 'stage1_dupes'])
 def test_moment_sweep_vs_reference_golden(ctx, name):
     """esper_sweep_config(1): the moment sweep against the reference run's logSumWij and against the general kernel."""
     g = golden(name + '.npz')
     D = g['D']
     Lr = g['logSumWij'] if 'logSumWij' in g else O.eps_sweep_logsum(D, LOG_EPS)
-    L0 = GaussianBandwidth.sweep(D, LOG_EPS, ctx=ctx)
-    assert ctx.sweep_info()[0] == 0
-    ctx.sweep_config(1)
+    ctx.sweep_config(0)
     try:
-        L1 = GaussianBandwidth.sweep(D, LOG_EPS, ctx=ctx)
-        path, bins = ctx.sweep_info()
+        L0 = GaussianBandwidth.sweep(D, LOG_EPS, ctx=ctx)
+        assert ctx.sweep_info()[0] == 0
     finally:
-        ctx.sweep_config(0)
+        ctx.sweep_config(1)
+    L1 = GaussianBandwidth.sweep(D, LOG_EPS, ctx=ctx)
+    path, bins = ctx.sweep_info()
     assert path == 1 and 1 <= bins <= 32
     assert np.array_equal(np.isfinite(L1), np.isfinite(Lr))
     fin = np.isfinite(Lr)
@@ -320,7 +285,6 @@ def test_moment_sweep_vs_reference_golden(ctx, name):
     assert np.max(np.abs(L1[fin] - L0[fin])) < 1e-12
 
 
-@experimental
 def test_moment_sweep_nonsymmetric_thresholds_and_fallbacks(ctx):
     rng = np.random.default_rng(5)
     D = np.sqrt(1.9 + 0.1 * rng.random((300, 300)))                           # concentrated like a high-noise stack
@@ -350,10 +314,9 @@ def test_moment_sweep_nonsymmetric_thresholds_and_fallbacks(ctx):
         with pytest.raises(ValueError):
             ctx.sweep_config(5)
     finally:
-        ctx.sweep_config(0)
+        ctx.sweep_config(1)
 
 
-@experimental
 def test_moment_sweep_row_block_entry_points(ctx):
     """esper_moment_stats_rows / esper_moment_accum_rows on a resident row block against the host plan and the numpy
     statement of the accumulation (tools/sweep_moments_proto.py); finalize reproduces the general row-block sweep."""
@@ -380,7 +343,6 @@ def test_moment_sweep_row_block_entry_points(ctx):
         ctx.moment_accum_rows(nrows, 600, coef, 10.0, bad)
 
 
-@experimental
 def test_moment_sweep_full_size(ctx):
     """BASELINE config 2 shape: D^2 spans 5 %, one bin; both kernels on the same resident matrix."""
     rng = np.random.default_rng(11)
@@ -391,13 +353,13 @@ def test_moment_sweep_full_size(ctx):
     D = 0.5 * (D + D.T)
     np.fill_diagonal(D, 0.0)
     coef = 1. / (2. * np.exp(LOG_EPS))
-    L0 = ctx.eps_sweep(D, coef, 10.0)
-    ctx.sweep_config(1)
+    ctx.sweep_config(0)
     try:
-        L1 = ctx.eps_sweep(None, coef, 10.0, m=2000)
-        path, bins = ctx.sweep_info()
+        L0 = ctx.eps_sweep(D, coef, 10.0)
     finally:
-        ctx.sweep_config(0)
+        ctx.sweep_config(1)
+    L1 = ctx.eps_sweep(None, coef, 10.0, m=2000)
+    path, bins = ctx.sweep_info()
     assert path == 1 and bins <= 2
     assert np.max(np.abs(L1 - L0)) < 1e-12
     assert np.max(np.abs(L1 - O.eps_sweep_logsum(D, LOG_EPS, sequential=False))) < 1e-10
@@ -632,7 +594,6 @@ def test_eigensolver_modes_agree(ctx):
         ctx.dmap_config(7)
 
 
-@experimental
 def test_eigensolver_without_speculative_batch(ctx):
     """esper_dmap_config(2): batches of 8 steps issued after each failed convergence test; same pairs, no more steps."""
     for name, k in (('stage23_medium', 10), ('stage123_pristine', 12)):
