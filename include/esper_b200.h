@@ -39,6 +39,7 @@ extern "C" {
 #define ESPER_E_NOCONV       -4   /* eigensolver did not converge within max_iter          */
 #define ESPER_E_STATE        -5   /* a NULL "use resident copy" argument with nothing resident */
 #define ESPER_E_ARCH         -6   /* device is not sm_100 (no fallback path exists)        */
+#define ESPER_E_NOFIT        -7   /* esper_pd_embed_fused: the tanh fit from this start is unusable (resnorm > 100); stages 1-2 are done */
 
 typedef struct esper_ctx esper_ctx;
 
@@ -150,6 +151,21 @@ int esper_markov(esper_ctx* ctx, const double* D, int m, double eps, double* deg
 int esper_dmap_config(esper_ctx* ctx, int mode);
 int esper_dmap_embed(esper_ctx* ctx, const double* D, int m, double eps, int k, double tol,
                      int max_iter, double* val, double* vec, int* iters);
+
+/* ---- stages 1-3 in one call (SURVEY 8b `esper_pd_embed_fused`; the throughput harness and launcher.py use it) --------
+ * One PD from the image stack to its leading eigenpairs without returning to the caller in between:
+ *   esper_dist_rms (Distances.py:87-104)  ->  threshold 10 (GaussianBandwidth.py:26-32: the diagonal of this D is exactly 0,
+ *   so find_threshold's first term is <= 4.6)  ->  esper_eps_sweep (:36-44)  ->  esper_tanh_fit from the start a0 (:47-57, one
+ *   curve_fit)  ->  eps = exp(-a1/a0) (DiffusionMaps.py:91-93)  ->  esper_dmap_embed (:109-169).
+ * imgs [n, P] float32 or NULL = the resident stack.  logEps / coef [n_eps]: the grid and the caller's 1./(2.*exp(logEps))
+ * (same convention as esper_eps_sweep).  a0 [4].  Outputs are caller-allocated; D [n, n] may be NULL (when given, its
+ * device-to-host copy runs on a second stream behind stages 2-3); logSum [n_eps]; fit [8] = popt[0..3], resnorm, R_squared,
+ * eps, slope = popt[0]*popt[2]; val [k]; vec [n, k]; iters optional.
+ * Returns ESPER_E_NOFIT when the fit from a0 fails the reference's `resnorm > 100` retry test: D stays resident, logSum and
+ * fit[0..5] are filled, and the caller continues with a new start (esper_tanh_fit) and esper_dmap_embed(D = NULL). */
+int esper_pd_embed_fused(esper_ctx* ctx, const float* imgs, int n, int P, unsigned flags, const double* logEps,
+                         const double* coef, int n_eps, const double* a0, int k, double tol, int max_iter,
+                         double* D, double* logSum, double* fit, double* val, double* vec, int* iters);
 
 /* float32 mean and population standard deviation of each image, bit-identical to numpy's `img.mean()` / `img.std()`
  * on a float32 array (pairwise summation tree of numpy/_core/src/umath/loops_utils.h.src, two-pass variance of

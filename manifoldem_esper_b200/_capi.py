@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libesper_b200.so')
 
 ESPER_OK = 0
-E_ARG, E_CUDA, E_NOMEM, E_NOCONV, E_STATE, E_ARCH = -1, -2, -3, -4, -5, -6
+E_ARG, E_CUDA, E_NOMEM, E_NOCONV, E_STATE, E_ARCH, E_NOFIT = -1, -2, -3, -4, -5, -6, -7
 DIST_STANDARDIZE, DIST_CENTER, DIST_REFINE = 1, 2, 4
 DIST_DEFAULT = DIST_STANDARDIZE | DIST_CENTER | DIST_REFINE
 
@@ -41,6 +41,8 @@ SIGNATURES = {
     'esper_stat': (C.c_longlong, [C.c_void_p, C.c_char_p]),
     'esper_dist_rms': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p]),
     'esper_upload_images': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    'esper_pd_embed_fused': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                       C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'esper_dist_config': (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     'esper_upload_dist': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     'esper_eps_sweep': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
@@ -281,6 +283,49 @@ class Context:
         self._check(self._lib.esper_dmap_embed(self._h, _ptr(D), int(m), float(eps), k, float(tol), int(max_iter),
                                                _ptr(val), _ptr(vec), C.byref(it)))
         return val, vec, it.value
+
+    def pd_embed_fused(self, imgs, logEps, a0, k=16, n=None, P=None, flags=DIST_DEFAULT, tol=0.0, max_iter=0, want_D=False, out=None):
+        """Stages 1-3 in ONE library call (esper_pd_embed_fused): stack -> distances -> eps sweep -> tanh fit from a0 ->
+        Markov matrix -> leading k eigenpairs.  imgs=None -> the resident stack of shape (n, P).
+        Returns dict(logSumWij, popt, resnorm, R2, eps, slope, val, vec, iters[, D]).  When the fit from a0 fails the reference's
+        `resnorm > 100` test, the retry loop of GaussianBandwidth.py:47-57 continues here (new random starts, esper_tanh_fit)
+        and the embedding finishes on the resident matrix."""
+        if imgs is not None:
+            imgs = _check_stack(imgs)
+            n, P = imgs.shape
+        if n is None or P is None:
+            raise ValueError('pd_embed_fused: n and P are required when imgs is None')
+        logEps = _as(logEps, np.float64).reshape(-1)
+        coef = 1. / (2. * np.exp(logEps))
+        a0 = _as(a0, np.float64).reshape(-1)
+        if a0.shape[0] != 4:
+            raise ValueError('pd_embed_fused: a0 must have four entries')
+        k = int(k)
+        D = None
+        if want_D or out is not None:
+            D = out if out is not None else np.empty((n, n), dtype=np.float64)
+            if D.shape != (n, n) or D.dtype != np.float64 or not D.flags.c_contiguous:
+                raise ValueError('pd_embed_fused: out must be a C-contiguous float64 [n, n] array')
+        L = np.empty(logEps.shape[0], dtype=np.float64)
+        fit = np.zeros(8, dtype=np.float64)
+        val = np.empty(max(k, 1), dtype=np.float64)
+        vec = np.empty((n, max(k, 1)), dtype=np.float64)
+        it = C.c_int(0)
+        rc = self._lib.esper_pd_embed_fused(self._h, _ptr(imgs), int(n), int(P), int(flags), _ptr(logEps), _ptr(coef), logEps.shape[0],
+                                            _ptr(a0), k, float(tol), int(max_iter), _ptr(D), _ptr(L), _ptr(fit), _ptr(val), _ptr(vec), C.byref(it))
+        if rc == E_NOFIT:
+            from . import GaussianBandwidth
+            popt, resnorm, R2 = GaussianBandwidth.fit(logEps, L, 1 * (np.random.rand(4, 1) - .5), native=True)
+            eps = float(np.exp(-(popt[1] / popt[0])))
+            val, vec, iters = self.dmap_embed(None, eps, k=k, tol=tol, max_iter=max_iter, m=n)
+            res = dict(logSumWij=L, popt=np.asarray(popt), resnorm=resnorm, R2=R2, eps=eps, slope=popt[0] * popt[2], val=val, vec=vec, iters=iters)
+        else:
+            self._check(rc)
+            res = dict(logSumWij=L, popt=fit[:4].copy(), resnorm=float(fit[4]), R2=float(fit[5]), eps=float(fit[6]), slope=float(fit[7]),
+                       val=val, vec=vec, iters=it.value)
+        if D is not None:
+            res['D'] = D
+        return res
 
     def image_stats(self, imgs):
         """float32 (mean, std) per image, bit-identical to numpy's float32 `img.mean()`, `img.std()`."""

@@ -78,6 +78,8 @@ void esper_destroy(esper_ctx* c) {
     for (DevBuf* b : bufs) b->release();
     c->pin.release(); c->pin_chain.release();
     c->pin_stream[0].release(); c->pin_stream[1].release();
+    if (c->copy_event) cudaEventDestroy(c->copy_event);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -284,6 +286,50 @@ int esper_dmap_embed(esper_ctx* c, const double* D, int m, double eps, int k, do
     rc = run_markov(c, m, eps);
     if (rc) return rc;
     return run_lanczos(c, m, k, tol, max_iter, val, vec, iters);
+}
+
+// ---- stages 1-3 in one call -------------------------------------------------------------------------
+int esper_pd_embed_fused(esper_ctx* c, const float* imgs, int n, int P, unsigned flags, const double* logEps,
+                         const double* coef, int n_eps, const double* a0, int k, double tol, int max_iter,
+                         double* D, double* logSum, double* fit, double* val, double* vec, int* iters) {
+    ESPER_ENTER(c);
+    if (!logEps || !coef || !a0 || !logSum || !fit || !val || !vec || n_eps < 4)
+        return fail(c, ESPER_E_ARG, "pd_embed_fused: logEps, coef, a0, logSum, fit, val, vec must not be NULL and n_eps >= 4");
+    if (k < 1 || k > n) return fail(c, ESPER_E_ARG, "pd_embed_fused: need 1 <= k <= n (k=%d, n=%d)", k, n);
+    int rc = esper_dist_rms(c, imgs, n, P, flags, nullptr);
+    if (rc) return rc;
+    if (D) {                                               // 8 n^2 bytes leave on a second stream while stages 2-3 run
+        if (!c->copy_stream) {
+            ESPER_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+            ESPER_CUDA(c, cudaEventCreateWithFlags(&c->copy_event, cudaEventDisableTiming));
+        }
+        ESPER_CUDA(c, cudaEventRecord(c->copy_event, c->stream));
+        ESPER_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->copy_event, 0));
+        ESPER_CUDA(c, cudaMemcpyAsync(D, c->dist.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+    auto finish_copy = [&]() -> int {
+        if (D) ESPER_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+        return ESPER_OK;
+    };
+    rc = run_sweep(c, n, coef, n_eps, 10.0, logSum);
+    if (rc) { finish_copy(); return rc; }
+    double resnorm = INFINITY, r2 = 0.0;
+    int info = 0, nfev = 0;
+    rc = tanh_fit_host(logEps, logSum, n_eps, a0, fit, &resnorm, &r2, &info, &nfev);
+    if (rc) { finish_copy(); return fail(c, ESPER_E_ARG, "pd_embed_fused: the sweep produced non-finite values (tanh fit impossible)"); }
+    fit[4] = resnorm; fit[5] = r2; fit[6] = 0.0; fit[7] = fit[0] * fit[2];
+    if (!(resnorm <= 100.0)) {
+        rc = finish_copy();
+        if (rc) return rc;
+        return fail(c, ESPER_E_NOFIT, "pd_embed_fused: tanh fit from this start has resnorm %g > 100 (MINPACK code %d); retry with a new start", resnorm, info);
+    }
+    const double eps = exp(-(fit[1] / fit[0]));
+    fit[6] = eps;
+    if (!(eps > 0.0) || !(eps < INFINITY)) { finish_copy(); return fail(c, ESPER_E_NOFIT, "pd_embed_fused: epsilon %g from the fit is unusable", eps); }
+    rc = run_markov(c, n, eps);
+    if (!rc) rc = run_lanczos(c, n, k, tol, max_iter, val, vec, iters);
+    const int rc2 = finish_copy();
+    return rc ? rc : rc2;
 }
 
 // float32 mean and population std per image with numpy's summation order (the statistics of the CTF branch)

@@ -60,6 +60,8 @@ struct esper_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;                        // device-to-host copies that overlap later stages (esper_pd_embed_fused)
+    cudaEvent_t copy_event = nullptr;
     std::string err;
 
     // profiling

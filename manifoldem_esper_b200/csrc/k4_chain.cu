@@ -39,6 +39,8 @@ constexpr int CH_REGROWS = 4;           // of which in registers (the rest in sh
 constexpr int CH_MAXM = 2048;
 constexpr int CH_MAXWANT = 24;          // Ritz pairs followed by a checker (kw + guard)
 constexpr int CH_MAXCHK = 4;
+constexpr int CH_HWARP = 8;             // warps 0..7 may own coefficient slots (P2); warps 8..11 fetch the coefficients (P3)
+constexpr int CH_PK = 8;                // partial packets per lane and slot: workers <= 32 * CH_PK
 constexpr long long CH_TIMEOUT = 4000000000LL;     // ~2 s
 
 struct Ctl {
@@ -98,6 +100,7 @@ __device__ __forceinline__ bool wait_ll(const uint4* p, unsigned int tag, double
     if (ld_ll(p, tag, v)) return true;
     const long long t0 = now();
     for (unsigned int polls = 1;; ++polls) {
+        relax();
         if (ld_ll(p, tag, v)) return true;
         if ((polls & 63u) == 0u) {
             if (ld_word(&ctl->abort) != 0u) return false;
@@ -182,11 +185,13 @@ struct CheckSmem {
     int* cnt;                               // [CH_THREADS]
     double* xs;                             // [CH_THREADS] section points of the current round
     double* red;                            // [3][CH_WARPS]
+    double* prev;                           // [CH_MAXWANT] eigenvalues of this checker's previous test
+    double* dots;                           // [CH_MAXWANT] orthogonalisation coefficients
 };
 
 // Shared-memory doubles a checker needs for `want` Ritz pairs and a Krylov dimension of at most cap (host and device).
 __host__ __device__ inline size_t checker_doubles(int want, int cap) {
-    return 3 * (size_t)cap + 3 * CH_MAXWANT + 3 * CH_WARPS + 4 * (size_t)want * cap + CH_THREADS + CH_THREADS / 2 + ((size_t)want * cap + 7) / 8 + 8;
+    return 3 * (size_t)cap + 5 * CH_MAXWANT + 3 * CH_WARPS + 4 * (size_t)want * cap + CH_THREADS + CH_THREADS / 2 + ((size_t)want * cap + 7) / 8 + 8;
 }
 
 // Factor T - x I = P L U (partial pivoting, as LAPACK dgttrf) once, keep it, and run `iters` inverse-iteration solves.
@@ -246,13 +251,13 @@ __device__ void inverse_solve_thread(const CheckSmem& cs, int n, int cap, int co
     }
 }
 
-// Runs by all threads of a checker CTA.  Returns (in every thread) whether the kw leading pairs (and the guard pairs at
-// 1e-5) have converged for T_n; theta / y hold the `want` leading Ritz values and unit Ritz vectors of T_n afterwards.
-__device__ bool check_converged(const CheckSmem& cs, int n, int cap, int kw, int guard, double tol, int* want_out) {
+// Leading `want` eigenvalues of T_n (descending) by multisection, all threads of the CTA.  eigenvalue i = smallest x with
+// below(x) >= n - i.  With the values of an earlier, smaller T (have_prev) the search starts from them: by interlacing a
+// leading eigenvalue can only grow with n, so round 0 places its points geometrically above the old value (a converged
+// value is bracketed to a few ulps at once); otherwise round 0 spreads CH_THREADS points over the Gershgorin interval.
+// Later rounds: P uniformly spaced points per eigenvalue, until no bracket moves.  Returns the norm bound tn.
+__device__ double leading_eigenvalues(const CheckSmem& cs, int n, int want, bool have_prev) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int want = min(kw + guard, n);
-    *want_out = want;
-    // Gershgorin interval and norm
     double glo = 1e300, ghi = -1e300, tn = 0.0;
     for (int i = tid; i < n; i += CH_THREADS) {
         const double r = (i > 0 ? fabs(cs.b[i - 1]) : 0.0) + (i < n - 1 ? fabs(cs.b[i]) : 0.0);
@@ -272,33 +277,34 @@ __device__ bool check_converged(const CheckSmem& cs, int n, int cap, int kw, int
     __syncthreads();
     const double span = ghi - glo;
     glo -= 1e-12 * span + 1e-300; ghi += 1e-12 * span + 1e-300;
-
-    // ---- multisection: round 0 places CH_THREADS points over the whole interval, later rounds P points per eigenvalue ----
-    // eigenvalue i (descending) = smallest x with below(x) >= n - i
-    if (tid < want) { cs.lo[tid] = glo; cs.hi[tid] = ghi; }
+    const double d0 = 4.0 * 2.220446049250313e-16 * tn;          // first geometric offset above an old eigenvalue
+    if (tid < want) { cs.lo[tid] = have_prev ? fmax(glo, cs.prev[tid] - d0) : glo; cs.hi[tid] = ghi; }
     __syncthreads();
-    const int P = CH_THREADS / want;                            // points per eigenvalue
-    for (int round = 0; round < 64; ++round) {
-        double x; int e = -1;
-        if (round == 0) {
+    const int P = CH_THREADS / want;                                // points per eigenvalue
+    for (int round = 0; round < 80; ++round) {
+        const bool global_scan = (round == 0 && !have_prev);
+        double x = 0.0; int e = -1;
+        if (global_scan) {
             x = glo + (ghi - glo) * ((double)(tid + 1) / (double)(CH_THREADS + 1));
         } else {
             e = tid / P;
             const int q = tid - e * P;
-            if (e < want) { const double l = cs.lo[e], h = cs.hi[e]; x = l + (h - l) * ((double)(q + 1) / (double)(P + 1)); }
-            else x = 0.0;
+            if (e < want) {
+                const double l = cs.lo[e], h = cs.hi[e];
+                if (round == 0) x = fmin(l + ldexp(d0, 2 * q + 1), h);                       // lo + 2 d0 4^q
+                else x = l + (h - l) * ((double)(q + 1) / (double)(P + 1));
+            }
         }
         int c = 0;
-        if (round == 0 || e < want) c = sturm_below(cs.a, cs.b2, n, x);
+        if (global_scan || e < want) c = sturm_below(cs.a, cs.b2, n, x);
         cs.cnt[tid] = c;
         cs.xs[tid] = x;
         __syncthreads();
-        // narrowing: thread e (< want) scans its points (monotone counts)
         bool moved = false;
-        if (tid < want) {
+        if (tid < want) {                                            // thread e narrows bracket e (ascending points, monotone counts)
             const int target = n - tid;
             double l = cs.lo[tid], h = cs.hi[tid];
-            const int p0 = (round == 0) ? 0 : tid * P, p1 = (round == 0) ? CH_THREADS : p0 + P;
+            const int p0 = global_scan ? 0 : tid * P, p1 = global_scan ? CH_THREADS : p0 + P;
             for (int q = p0; q < p1; ++q) {
                 const double xq = cs.xs[q];
                 if (!(xq > l && xq < h)) continue;
@@ -309,12 +315,19 @@ __device__ bool check_converged(const CheckSmem& cs, int n, int cap, int kw, int
             cs.lo[tid] = l; cs.hi[tid] = h;
         }
         const int any = __syncthreads_or(moved ? 1 : 0);
-        if (!any) break;
+        if (!any && round > 0) break;
     }
     if (tid < want) cs.theta[tid] = 0.5 * (cs.lo[tid] + cs.hi[tid]);
     __syncthreads();
+    return tn;
+}
 
-    // ---- inverse iteration, one thread per Ritz vector; vectors of a cluster are orthogonalised in index order ----
+// Unit eigenvectors of T_n for cs.theta[0..want) in cs.y (inverse iteration, one thread per vector; the vectors of a
+// cluster |theta_i - theta_{i-1}| <= 1e-3 |T| are orthogonalised against each other in index order, LAPACK dstein's rule,
+// by all threads: coefficients by one warp per earlier vector, then the update).  Returns (in every thread) whether
+// the kw leading pairs (and the guard pairs at 1e-5) have converged: |beta_n s_{n,i}| <= tol |theta_0|.
+__device__ bool ritz_vectors_converged(const CheckSmem& cs, int n, int cap, int kw, int want, double tol, double tn) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double tiny = fmax(tn * 2.2e-16, 1e-300);
     const double cluster_tol = 1e-3 * tn;
     if (tid < want) {
@@ -328,39 +341,49 @@ __device__ bool check_converged(const CheckSmem& cs, int n, int cap, int kw, int
         for (int r = 0; r < n; ++r) { seed = seed * 1664525u + 1013904223u; y[r] = ((double)(seed >> 8) / 16777216.0) - 0.5; }
     }
     __syncthreads();
-    for (int it = 0; it < 4; ++it) {
+    for (int it = 0; it < 3; ++it) {
         if (tid < want) inverse_solve_thread(cs, n, cap, tid);
         __syncthreads();
-        // warp 0: normalise; orthogonalise vector i against the earlier vectors of its cluster (two passes), in index order
-        if (warp == 0) {
-            int cstart = 0;
-            for (int i = 0; i < want; ++i) {
-                if (i > 0 && fabs(cs.theta[i] - cs.theta[i - 1]) > cluster_tol) cstart = i;
-                double* yi = cs.y + (size_t)i * cap;
-                for (int pass = 0; pass < 2; ++pass)
-                    for (int pp = cstart; pp < i; ++pp) {
+        int cstart = 0;
+        for (int i = 0; i < want; ++i) {
+            if (i > 0 && fabs(cs.theta[i] - cs.theta[i - 1]) > cluster_tol) cstart = i;
+            double* yi = cs.y + (size_t)i * cap;
+            if (i > cstart) {
+                for (int pass = 0; pass < 2; ++pass) {
+                    for (int pp = cstart + warp; pp < i; pp += CH_WARPS) {
                         const double* yp = cs.y + (size_t)pp * cap;
                         double dot = 0.0;
                         for (int r = lane; r < n; r += 32) dot = fma(yp[r], yi[r], dot);
                         dot = wsum(dot);
-                        for (int r = lane; r < n; r += 32) yi[r] -= dot * yp[r];
-                        __syncwarp();
+                        if (lane == 0) cs.dots[pp] = dot;
                     }
-                double nrm = 0.0;
-                for (int r = lane; r < n; r += 32) nrm = fma(yi[r], yi[r], nrm);
-                nrm = sqrt(wsum(nrm));
-                if (!(nrm > 0.0) || !(nrm < 1e300)) {
-                    for (int r = lane; r < n; r += 32) yi[r] = (r == (i % n)) ? 1.0 : 0.0;
-                } else {
-                    const double inv = 1.0 / nrm;
-                    for (int r = lane; r < n; r += 32) yi[r] *= inv;
+                    __syncthreads();
+                    for (int r = tid; r < n; r += CH_THREADS) {
+                        double acc = yi[r];
+                        for (int pp = cstart; pp < i; ++pp) acc = fma(-cs.dots[pp], cs.y[(size_t)pp * cap + r], acc);
+                        yi[r] = acc;
+                    }
+                    __syncthreads();
                 }
-                __syncwarp();
             }
+            // normalise (fixed-order block sum)
+            double nrm = 0.0;
+            for (int r = tid; r < n; r += CH_THREADS) nrm = fma(yi[r], yi[r], nrm);
+            nrm = wsum(nrm);
+            if (lane == 0) cs.red[warp] = nrm;
+            __syncthreads();
+            double tot = 0.0;
+            for (int w = 0; w < CH_WARPS; ++w) tot += cs.red[w];
+            tot = sqrt(tot);
+            if (!(tot > 0.0) || !(tot < 1e300)) {
+                for (int r = tid; r < n; r += CH_THREADS) yi[r] = (r == (i % n)) ? 1.0 : 0.0;
+            } else {
+                const double inv = 1.0 / tot;
+                for (int r = tid; r < n; r += CH_THREADS) yi[r] *= inv;
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
-    // ---- residual estimates |beta_n s_{n,i}| ----
     const double scale = fmax(fabs(cs.theta[0]), 1e-300);
     const double beta_last = cs.b[n - 1];
     bool ok = (n >= kw);
@@ -378,6 +401,7 @@ __device__ void checker_main(const Params& p, double* smem, int c) {
     double* q = smem;
     cs.a = q; q += cap; cs.b = q; q += cap; cs.b2 = q; q += cap;
     cs.theta = q; q += CH_MAXWANT; cs.lo = q; q += CH_MAXWANT; cs.hi = q; q += CH_MAXWANT;
+    cs.prev = q; q += CH_MAXWANT; cs.dots = q; q += CH_MAXWANT;
     cs.red = q; q += 3 * CH_WARPS;
     const int wmax = min(p.kw + p.guard, CH_MAXWANT);
     cs.y = q; q += (size_t)wmax * cap; cs.di = q; q += (size_t)wmax * cap; cs.du = q; q += (size_t)wmax * cap; cs.ff = q; q += (size_t)wmax * cap;
@@ -387,11 +411,12 @@ __device__ void checker_main(const Params& p, double* smem, int c) {
     __shared__ int s_n;
     __shared__ int s_mode;
     int have = 0;                                              // alpha/beta of steps 1..have are in shared memory
-    int next_n = p.first_check + c;
+    int next_n = p.first_check + c;                            // checker c follows the sizes first_check + c + i n_checkers
+    int prev_want = 0;                                         // eigenvalues of this checker's previous test in cs.prev
     for (;;) {
         // ---- wait for the next size to test (thread 0 decides) ----
         if (tid == 0) {
-            int mode = 0, n = 0;                               // mode 1 = test T_n, 2 = final forced/unforced test, 3 = leave
+            int mode = 0, n = 0;                               // 1 = test T_n, 2 = last test at max_steps, 4 = accept T_n, 3 = leave
             const long long t0 = now();
             for (;;) {
                 if (ld_word(&p.ctl->stop) != 0u || ld_word(&p.ctl->abort) != 0u) { mode = 3; break; }
@@ -403,7 +428,7 @@ __device__ void checker_main(const Params& p, double* smem, int c) {
                     break;
                 }
                 const int prog = (int)ld_word(&p.ctl->progress);
-                if (prog >= next_n) { n = prog; mode = 1; break; }
+                if (prog >= next_n) { n = prog - ((prog - next_n) % p.n_checkers); mode = 1; break; }
                 if (now() - t0 > CH_TIMEOUT) { st_word(&p.ctl->abort, 1u); mode = 3; break; }
                 relax();
             }
@@ -421,9 +446,23 @@ __device__ void checker_main(const Params& p, double* smem, int c) {
         }
         if (__syncthreads_or(bad)) return;
         have = n;
-        int want = 0;
-        const bool ok = check_converged(cs, n, cap, p.kw, p.guard, p.tol, &want);
-        if (ok || mode == 4 || mode == 2) {
+        const int want = min(p.kw + p.guard, n);
+        const double tn = leading_eigenvalues(cs, n, want, prev_want >= want);
+        // A converged Ritz value no longer moves (its error is residual^2 / gap): the eigenvectors are only worth computing
+        // once the kw leading values have stopped moving since this checker's previous test.
+        bool stagnant = (prev_want >= want) && n >= p.kw;
+        if (stagnant) {
+            const double thr = fmax(64.0 * 2.220446049250313e-16 * tn, 1e3 * p.tol * p.tol * tn);
+            for (int i = 0; i < min(p.kw, want); ++i)
+                if (!(fabs(cs.theta[i] - cs.prev[i]) <= thr)) stagnant = false;
+        }
+        __syncthreads();
+        if (tid < want) cs.prev[tid] = cs.theta[tid];
+        prev_want = want;
+        __syncthreads();
+        bool ok = false;
+        if (stagnant || mode != 1) ok = ritz_vectors_converged(cs, n, cap, p.kw, want, p.tol, tn);
+        if (ok || mode != 1) {
             if (ok || mode == 4) {
                 // publish theta and S [n][kw] of this checker, then try to win the stop word
                 double* th = p.theta_out + (size_t)c * CH_MAXWANT;
@@ -446,7 +485,7 @@ __device__ void checker_main(const Params& p, double* smem, int c) {
             }
             return;
         }
-        next_n = n + 1;
+        next_n = n + p.n_checkers;
         __syncthreads();
     }
 }
@@ -544,15 +583,31 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_chain_kernel(Params p) 
                 else { for (int r = 0; r < n_own; ++r) v = fma(Vs[(size_t)r * cap + (s - 1)], s_w[r], v); }
                 st_ll(p.pbuf + (size_t)s * nW + b, v, tag);
             }
-            // ---- P2: slots owned by this CTA: fixed-order sum of all workers' partials ----
+            // Polling discipline (measured: with every thread of every CTA spinning on the same few lines the hand-overs cost
+            // ~5k cycles each -- an L2 slice hot spot that also delays the stores being waited for): only the warps that need
+            // a packet poll, with all their loads of a round in flight together and a pause between rounds.
+            // ---- P2: slots owned by this CTA (warps 0..): fixed-order sum of all workers' partials ----
             int bad = 0;
-            for (int s = b + warp * nW; s < n_slots; s += CH_WARPS * nW) {
-                double v = 0.0;
-                for (int c = lane; c < nW; c += 32) {
-                    double x;
-                    if (!wait_ll(p.pbuf + (size_t)s * nW + c, tag, x, ctl)) { bad = 1; break; }
-                    v += x;
+            for (int s = b + warp * nW; s < n_slots && warp < CH_HWARP; s += CH_HWARP * nW) {
+                double x[CH_PK];
+                unsigned int pend = 0u;
+#pragma unroll
+                for (int q = 0; q < CH_PK; ++q) { x[q] = 0.0; if (lane + 32 * q < nW) pend |= 1u << q; }
+                const uint4* src = p.pbuf + (size_t)s * nW + lane;
+                const long long t0 = now();
+                for (unsigned int rounds = 1; pend != 0u; ++rounds) {
+                    const unsigned int cur = pend;
+#pragma unroll
+                    for (int q = 0; q < CH_PK; ++q)
+                        if ((cur >> q) & 1u) { double v; if (ld_ll(src + 32 * q, tag, v)) { x[q] = v; pend &= ~(1u << q); } }
+                    if (pend != 0u) {
+                        relax();
+                        if ((rounds & 63u) == 0u && (ld_word(&ctl->abort) != 0u || now() - t0 > CH_TIMEOUT)) { st_word(&ctl->abort, 1u); bad = 1; break; }
+                    }
                 }
+                double v = x[0];
+#pragma unroll
+                for (int q = 1; q < CH_PK; ++q) v += x[q];
                 v = wsum(v);
                 if (lane == 0) {
                     st_ll(p.hbuf + s, v, tag);
@@ -562,16 +617,25 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_chain_kernel(Params p) 
                     }
                 }
             }
-            // ---- P3: all coefficients ----
-            for (int s = tid; s < n_slots; s += CH_THREADS) {
-                double x;
-                if (!wait_ll(p.hbuf + s, tag, x, ctl)) { bad = 1; break; }
-                s_h[s] = x;
-            }
-            if (tid == CH_THREADS - 1) {
-                double x = 0.0;
-                if (!wait_ll(p.hbuf + (p.max_steps + 2), tag, x, ctl)) bad = 1;
-                s_stop = x != 0.0 ? 1u : 0u;
+            // ---- P3: all coefficients, fetched by four warps (up to four packets per lane in flight) ----
+            if (warp >= CH_HWARP && warp < CH_HWARP + 4) {
+                const int t = tid - 32 * CH_HWARP;                           // 0..127
+                unsigned int pend = 0u;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (t + 128 * q < n_slots) pend |= 1u << q;
+                if (t == 127) pend |= 1u << 4;                               // the control packet
+                const long long t0 = now();
+                for (unsigned int rounds = 1; pend != 0u; ++rounds) {
+                    const unsigned int cur = pend;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if ((cur >> q) & 1u) { double v; if (ld_ll(p.hbuf + t + 128 * q, tag, v)) { s_h[t + 128 * q] = v; pend &= ~(1u << q); } }
+                    if ((cur >> 4) & 1u) { double v; if (ld_ll(p.hbuf + (p.max_steps + 2), tag, v)) { s_stop = v != 0.0 ? 1u : 0u; pend &= ~(1u << 4); } }
+                    if (pend != 0u) {
+                        relax();
+                        if ((rounds & 63u) == 0u && (ld_word(&ctl->abort) != 0u || now() - t0 > CH_TIMEOUT)) { st_word(&ctl->abort, 1u); bad = 1; break; }
+                    }
+                }
             }
             if (__syncthreads_or(bad)) { end_reason = 4; leave = true; break; }
             if (s_stop) { end_reason = 1; leave = true; break; }
@@ -609,7 +673,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_chain_kernel(Params p) 
             const double x = s_w[tid] * inv;
             Vs[(size_t)tid * cap + j + 1] = x;
             p.V[(size_t)(j + 1) * m + row0 + tid] = x;
-            st_ll(p.qbuf + row0 + tid, x, 2u * (unsigned int)j);
+            st_ll(p.qbuf + row0 + tid, x, 2u * (unsigned int)j);                 // lanes 0..n_own-1 of warp 0: one store instruction
         }
         if (b == 0 && tid == 32) {
             p.alpha[j - 1] = alpha_j; p.beta[j - 1] = beta_j;
@@ -621,15 +685,31 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_chain_kernel(Params p) 
         CH_PROF(3);
         if (breakdown) { end_reason = 2; ++j; break; }
         if (j == p.max_steps) { end_reason = 3; ++j; break; }
-        // ---- P4: the whole next vector ----
+        // ---- P4: the whole next vector.  First one sentinel packet per producer (its last row; a producer stores all its
+        // rows with one instruction), then every packet once; a packet that is still missing is waited for individually. ----
         int bad = 0;
+        const unsigned int qtag = 2u * (unsigned int)j;
+        for (int c = tid; c < nW; c += CH_THREADS) {
+            double x;
+            if (!wait_ll(p.qbuf + min(c * p.chunk + p.chunk - 1, m - 1), qtag, x, ctl)) bad = 1;
+        }
+        if (__syncthreads_or(bad)) { end_reason = 4; ++j; break; }
+        {
+            double x[4];
+            bool ok[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int c = tid + CH_THREADS * u;
-            if (c < m) {
-                double x;
-                if (!wait_ll(p.qbuf + c, 2u * (unsigned int)j, x, ctl)) { bad = 1; break; }
-                s_vec[c] = x;
+            for (int u = 0; u < 4; ++u) {
+                const int c = tid + CH_THREADS * u;
+                ok[u] = true; x[u] = 0.0;
+                if (c < m) ok[u] = ld_ll(p.qbuf + c, qtag, x[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = tid + CH_THREADS * u;
+                if (c < m) {
+                    if (!ok[u] && !wait_ll(p.qbuf + c, qtag, x[u], ctl)) bad = 1;
+                    s_vec[c] = x[u];
+                }
             }
         }
         if (__syncthreads_or(bad)) { end_reason = 4; ++j; break; }
@@ -688,7 +768,7 @@ struct ChainPlan {
 static ChainPlan chain_plan(esper_ctx* c, int m, int kw, int guard, int max_iter, long long smem_limit) {
     using namespace chain;
     ChainPlan pl;
-    if (m < 32 || m > CH_MAXM || kw < 1 || kw + guard > CH_MAXWANT || c->sm_count < 2) return pl;
+    if (m < 32 || m > CH_MAXM || kw < 1 || kw + guard > CH_MAXWANT || c->sm_count < 2 || c->sm_count > 32 * CH_PK) return pl;
     pl.chunk = ceil_div(m, c->sm_count - 1);
     if (pl.chunk > CH_MAXROWS) return pl;
     pl.n_workers = ceil_div(m, pl.chunk);

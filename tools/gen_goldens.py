@@ -17,6 +17,10 @@ Outputs (all under tests/golden/):
   rot_inputs.npz        first 9 columns of 12 shipped Data_Manifolds_126 fixtures
   rot_ref_dim{6,8}.npz  Rotation_Histograms.op outputs for all 126 fixtures     (P5)
   rot_counts_dim8.npz   per-evaluation non-zero-bin counts for 3 PDs (histogramdd spy)
+  stage1_p2.npz         Distances.op on the config-1 stand-in at full box: pristine N=400, 250x250 (--only-big)
+  stage1_c2_rows.npz    Distances.op at BASELINE config 2 (N=2000, 250x250, SNR 0.1; ~20 min): every 25th row of D (--only-big)
+  stage23_c2.npz        DiffusionMaps.op at BASELINE config 2 on the float64-Gram distance matrix of the same stack:
+                        logSumWij, popt, eps, R2, val[:16], vec[:, :16] under np.random.seed (--only-big)
   tau_snr.npz           0_Data_Inputs/Pristine_AddTauSNR: AddNoise.find_SNR per state and Generate_TauSNR.op
                         (tau = 10, SNR = 0.1 as shipped) on a 6-state pristine stack under np.random.seed
 """
@@ -242,6 +246,45 @@ def tau_snr_golden(ref):
     return dict(pristine=pristine, params=params, seed=np.array(seed), tau=np.array(10), snr=np.array(0.1), stack=np.array(out))
 
 
+def big_goldens(root, parts):
+    """Reference runs at the BASELINE sizes.  The stacks are regenerated from synth's seeds by the tests, only outputs are stored."""
+    from manifoldem_esper_b200 import synth
+    from oracle import esper_oracle as O
+    dm = os.path.join(root, '1_Embedding', 'DM')
+    mods = {n: import_from(os.path.join(dm, n + '.py'), n) for n in ['GaussianBandwidth', 'Distances', 'DiffusionMaps']}
+    if 'p2' in parts:
+        prist = synth.synthetic_pd(pd=4, box=250, n_side=20, tau=1, snr=None)         # N=400, the config-1 stand-in
+        o = stage123(root, mods, prist, '004', 5)
+        o.pop('stack')
+        o['synth'] = np.array([4, 250, 20, 1, -1])                                    # pd, box, n_side, tau, snr (-1 = none)
+        np.savez_compressed(os.path.join(GOLD, 'stage1_p2.npz'), **o)
+        print('stage1_p2 done', flush=True)
+    if 'c2dm' in parts:
+        stack = synth.synthetic_pd(pd=1, box=250, n_side=20, tau=5, snr=0.1)          # N=2000, config 2
+        D = O.distances_gram_f64(O.standardize_stack(stack))
+        os.makedirs(os.path.join(dm, 'Data_Distances'), exist_ok=True)
+        np.save(os.path.join(dm, 'Data_Distances', 'PD_001_dist.npy'), D)
+        logEps = np.arange(-100, 100.2, 0.2)
+        seed = 17
+        np.random.seed(seed)
+        a0 = 1 * (np.random.rand(4, 1) - .5)
+        popt, logSum, resnorm, R2 = mods['GaussianBandwidth'].op(D, logEps, a0)
+        np.random.seed(seed)
+        run_quiet(mods['DiffusionMaps'].op, dm, '001')
+        val = np.load(os.path.join(dm, 'Data_Manifolds', 'PD_001_val.npy'))
+        vec = np.load(os.path.join(dm, 'Data_Manifolds', 'PD_001_vec.npy'))
+        np.savez_compressed(os.path.join(GOLD, 'stage23_c2.npz'), seed=seed, a0=a0, popt=popt, logSumWij=logSum, R2=R2,
+                            eps=np.exp(-(popt[1] / popt[0])), val=val[:16], vec=vec[:, :16], D_rows=D[::100],
+                            synth=np.array([1, 250, 20, 5, 0.1]))
+        print('stage23_c2 done', flush=True)
+    if 'c2dist' in parts:
+        stack = synth.synthetic_pd(pd=1, box=250, n_side=20, tau=5, snr=0.1)
+        o = stage123(root, mods, stack, '011', None)
+        np.savez_compressed(os.path.join(GOLD, 'stage1_c2_rows.npz'), D_rows=o['D'][::25], step=np.array(25),
+                            synth=np.array([1, 250, 20, 5, 0.1]))
+        print('stage1_c2_rows done', flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--ref', default='/root/reference')
@@ -251,6 +294,8 @@ def main():
     ap.add_argument('--only-pca', action='store_true')
     ap.add_argument('--only-ctf', action='store_true')
     ap.add_argument('--only-prep', action='store_true')
+    ap.add_argument('--only-big', action='store_true', help='the BASELINE-size goldens only (about half an hour of CPU)')
+    ap.add_argument('--big-part', default='p2,c2dm,c2dist', help='which BASELINE-size goldens: p2, c2dm, c2dist')
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     os.environ['PYTHONDONTWRITEBYTECODE'] = '1'
@@ -260,6 +305,10 @@ def main():
     install_stubs()
     from manifoldem_esper_b200 import synth
 
+    if args.only_big:
+        big_goldens(root, args.big_part.split(','))
+        shutil.rmtree(root, ignore_errors=True)
+        return
     if args.only_prep or not (args.only_rot or args.only_pca or args.only_ctf):
         np.savez_compressed(os.path.join(GOLD, 'tau_snr.npz'), **tau_snr_golden(args.ref))
         print('data prep done')
