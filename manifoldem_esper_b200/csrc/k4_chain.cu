@@ -39,6 +39,7 @@ constexpr int CH_REGROWS = 4;           // of which in registers (the rest in sh
 constexpr int CH_MAXM = 2048;
 constexpr int CH_MAXWANT = 24;          // Ritz pairs followed by a checker (kw + guard)
 constexpr int CH_MAXCHK = 4;
+constexpr int CH_POINTS = 16;           // multisection points per eigenvalue and round
 constexpr int CH_HWARP = 8;             // warps 0..7 may own coefficient slots (P2); warps 8..11 fetch the coefficients (P3)
 constexpr int CH_PK = 8;                // partial packets per lane and slot: workers <= 32 * CH_PK
 constexpr long long CH_TIMEOUT = 4000000000LL;     // ~2 s
@@ -210,15 +211,17 @@ __device__ void inverse_iteration_thread(const CheckSmem& cs, int n, int cap, in
         const double dun = (i < n - 2) ? b[i + 1] : 0.0;   // unmodified du[i+1]
         if (fabs(d) >= fabs(dl)) {
             if (d == 0.0) d = tiny;
-            const double f = dl / d;
+            const double r = 1.0 / d;       // the only division of the step (the multiplier is a product with it)
+            const double f = dl * r;
             ff[i] = f; swp[i] = 0;
-            di[i] = 1.0 / d; du[i] = dui;
+            di[i] = r; du[i] = dui;
             d = dn - f * dui;
             dui = dun;
         } else {                            // swap rows i and i+1
-            const double f = d / dl;
+            const double r = 1.0 / dl;
+            const double f = d * r;
             ff[i] = f; swp[i] = 1;
-            di[i] = 1.0 / dl; du[i] = dn;   // U[i][i] = dl, U[i][i+1] = old d[i+1], U[i][i+2] = old du[i+1]
+            di[i] = r; du[i] = dn;          // U[i][i] = dl, U[i][i+1] = old d[i+1], U[i][i+2] = old du[i+1]
             d = dui - f * dn;
             dui = -f * dun;
         }
@@ -255,8 +258,10 @@ __device__ void inverse_solve_thread(const CheckSmem& cs, int n, int cap, int co
 // below(x) >= n - i.  With the values of an earlier, smaller T (have_prev) the search starts from them: by interlacing a
 // leading eigenvalue can only grow with n, so round 0 places its points geometrically above the old value (a converged
 // value is bracketed to a few ulps at once); otherwise round 0 spreads CH_THREADS points over the Gershgorin interval.
-// Later rounds: P uniformly spaced points per eigenvalue, until no bracket moves.  Returns the norm bound tn.
-__device__ double leading_eigenvalues(const CheckSmem& cs, int n, int want, bool have_prev) {
+// Later rounds: P uniformly spaced points per eigenvalue, until no bracket moves (max_rounds = 0) or for max_rounds rounds
+// (tracking: the brackets stay in cs.lo / cs.hi); resume = continue from the brackets a tracking call left.  Returns the
+// norm bound tn.
+__device__ double leading_eigenvalues(const CheckSmem& cs, int n, int want, bool have_prev, bool resume, int max_rounds) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double glo = 1e300, ghi = -1e300, tn = 0.0;
     for (int i = tid; i < n; i += CH_THREADS) {
@@ -278,10 +283,13 @@ __device__ double leading_eigenvalues(const CheckSmem& cs, int n, int want, bool
     const double span = ghi - glo;
     glo -= 1e-12 * span + 1e-300; ghi += 1e-12 * span + 1e-300;
     const double d0 = 4.0 * 2.220446049250313e-16 * tn;          // first geometric offset above an old eigenvalue
-    if (tid < want) { cs.lo[tid] = have_prev ? fmax(glo, cs.prev[tid] - d0) : glo; cs.hi[tid] = ghi; }
+    if (!resume && tid < want) { cs.lo[tid] = have_prev ? fmax(glo, cs.prev[tid] - d0) : glo; cs.hi[tid] = ghi; }
     __syncthreads();
-    const int P = CH_THREADS / want;                                // points per eigenvalue
-    for (int round = 0; round < 80; ++round) {
+    // points per eigenvalue and round: the Sturm recurrences are FP64-throughput bound (measured: 512 of them cost 30k cycles
+    // at n = 185), so a round uses 16 points per eigenvalue (6 warps for 11 values) rather than all threads
+    const int P = min(CH_THREADS / want, CH_POINTS);
+    const int round_end = (max_rounds > 0 && !resume) ? max_rounds : 80;
+    for (int round = resume ? 1 : 0; round < round_end; ++round) {
         const bool global_scan = (round == 0 && !have_prev);
         double x = 0.0; int e = -1;
         if (global_scan) {
@@ -291,7 +299,7 @@ __device__ double leading_eigenvalues(const CheckSmem& cs, int n, int want, bool
             const int q = tid - e * P;
             if (e < want) {
                 const double l = cs.lo[e], h = cs.hi[e];
-                if (round == 0) x = fmin(l + ldexp(d0, 2 * q + 1), h);                       // lo + 2 d0 4^q
+                if (round == 0) x = fmin(l + ldexp(d0, 4 * q + 1), h);                       // lo + 2 d0 16^q
                 else x = l + (h - l) * ((double)(q + 1) / (double)(P + 1));
             }
         }
@@ -322,12 +330,13 @@ __device__ double leading_eigenvalues(const CheckSmem& cs, int n, int want, bool
     return tn;
 }
 
-// Unit eigenvectors of T_n for cs.theta[0..want) in cs.y (inverse iteration, one thread per vector; the vectors of a
-// cluster |theta_i - theta_{i-1}| <= 1e-3 |T| are orthogonalised against each other in index order, LAPACK dstein's rule,
-// by all threads: coefficients by one warp per earlier vector, then the update).  Returns (in every thread) whether
-// the kw leading pairs (and the guard pairs at 1e-5) have converged: |beta_n s_{n,i}| <= tol |theta_0|.
-__device__ bool ritz_vectors_converged(const CheckSmem& cs, int n, int cap, int kw, int want, double tol, double tn) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// Unit eigenvectors of T_n for cs.theta[0..want) in cs.y by inverse iteration, one thread per vector (LAPACK dstein's scheme):
+// ritz_prepare factors T - theta_i I and draws the start vectors; ritz_iterate does one solve for every vector, then (all
+// threads) orthogonalises the vectors of a cluster |theta_i - theta_{i-1}| <= 1e-3 |T| against each other in index order
+// (coefficients by one warp per earlier vector, then the update; skipped when ortho = false) and normalises them;
+// ritz_residuals_ok tests |beta_n s_{n,i}| <= factor tol |theta_0| for the kw leading pairs (guard pairs: 1e-5).
+__device__ void ritz_prepare(const CheckSmem& cs, int n, int cap, int want, double tn) {
+    const int tid = threadIdx.x;
     const double tiny = fmax(tn * 2.2e-16, 1e-300);
     const double cluster_tol = 1e-3 * tn;
     if (tid < want) {
@@ -341,55 +350,76 @@ __device__ bool ritz_vectors_converged(const CheckSmem& cs, int n, int cap, int 
         for (int r = 0; r < n; ++r) { seed = seed * 1664525u + 1013904223u; y[r] = ((double)(seed >> 8) / 16777216.0) - 0.5; }
     }
     __syncthreads();
-    for (int it = 0; it < 3; ++it) {
-        if (tid < want) inverse_solve_thread(cs, n, cap, tid);
-        __syncthreads();
-        int cstart = 0;
-        for (int i = 0; i < want; ++i) {
-            if (i > 0 && fabs(cs.theta[i] - cs.theta[i - 1]) > cluster_tol) cstart = i;
-            double* yi = cs.y + (size_t)i * cap;
-            if (i > cstart) {
-                for (int pass = 0; pass < 2; ++pass) {
-                    for (int pp = cstart + warp; pp < i; pp += CH_WARPS) {
-                        const double* yp = cs.y + (size_t)pp * cap;
-                        double dot = 0.0;
-                        for (int r = lane; r < n; r += 32) dot = fma(yp[r], yi[r], dot);
-                        dot = wsum(dot);
-                        if (lane == 0) cs.dots[pp] = dot;
-                    }
-                    __syncthreads();
-                    for (int r = tid; r < n; r += CH_THREADS) {
-                        double acc = yi[r];
-                        for (int pp = cstart; pp < i; ++pp) acc = fma(-cs.dots[pp], cs.y[(size_t)pp * cap + r], acc);
-                        yi[r] = acc;
-                    }
-                    __syncthreads();
+}
+
+__device__ void ritz_iterate(const CheckSmem& cs, int n, int cap, int want, double tn, bool ortho) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double cluster_tol = 1e-3 * tn;
+    if (tid < want) inverse_solve_thread(cs, n, cap, tid);
+    __syncthreads();
+    int cstart = 0;
+    for (int i = 0; i < want; ++i) {
+        if (i > 0 && fabs(cs.theta[i] - cs.theta[i - 1]) > cluster_tol) cstart = i;
+        double* yi = cs.y + (size_t)i * cap;
+        if (ortho && i > cstart) {
+            for (int pass = 0; pass < 2; ++pass) {
+                for (int pp = cstart + warp; pp < i; pp += CH_WARPS) {
+                    const double* yp = cs.y + (size_t)pp * cap;
+                    double dot = 0.0;
+                    for (int r = lane; r < n; r += 32) dot = fma(yp[r], yi[r], dot);
+                    dot = wsum(dot);
+                    if (lane == 0) cs.dots[pp] = dot;
                 }
+                __syncthreads();
+                for (int r = tid; r < n; r += CH_THREADS) {
+                    double acc = yi[r];
+                    for (int pp = cstart; pp < i; ++pp) acc = fma(-cs.dots[pp], cs.y[(size_t)pp * cap + r], acc);
+                    yi[r] = acc;
+                }
+                __syncthreads();
             }
-            // normalise (fixed-order block sum)
-            double nrm = 0.0;
-            for (int r = tid; r < n; r += CH_THREADS) nrm = fma(yi[r], yi[r], nrm);
-            nrm = wsum(nrm);
-            if (lane == 0) cs.red[warp] = nrm;
-            __syncthreads();
-            double tot = 0.0;
-            for (int w = 0; w < CH_WARPS; ++w) tot += cs.red[w];
-            tot = sqrt(tot);
-            if (!(tot > 0.0) || !(tot < 1e300)) {
-                for (int r = tid; r < n; r += CH_THREADS) yi[r] = (r == (i % n)) ? 1.0 : 0.0;
-            } else {
-                const double inv = 1.0 / tot;
-                for (int r = tid; r < n; r += CH_THREADS) yi[r] *= inv;
-            }
-            __syncthreads();
         }
+        if (!ortho) continue;                                   // the vectors of the early test are normalised by their own warp below
+        double nrm = 0.0;
+        for (int r = tid; r < n; r += CH_THREADS) nrm = fma(yi[r], yi[r], nrm);
+        nrm = wsum(nrm);
+        if (lane == 0) cs.red[warp] = nrm;
+        __syncthreads();
+        double tot = 0.0;
+        for (int w = 0; w < CH_WARPS; ++w) tot += cs.red[w];
+        tot = sqrt(tot);
+        if (!(tot > 0.0) || !(tot < 1e300)) {
+            for (int r = tid; r < n; r += CH_THREADS) yi[r] = (r == (i % n)) ? 1.0 : 0.0;
+        } else {
+            const double inv = 1.0 / tot;
+            for (int r = tid; r < n; r += CH_THREADS) yi[r] *= inv;
+        }
+        __syncthreads();
     }
+    if (!ortho) {                                               // one warp per vector, no block barriers
+        for (int i = warp; i < want; i += CH_WARPS) {
+            double* yi = cs.y + (size_t)i * cap;
+            double nrm = 0.0;
+            for (int r = lane; r < n; r += 32) nrm = fma(yi[r], yi[r], nrm);
+            nrm = sqrt(wsum(nrm));
+            if (!(nrm > 0.0) || !(nrm < 1e300)) {
+                for (int r = lane; r < n; r += 32) yi[r] = (r == (i % n)) ? 1.0 : 0.0;
+            } else {
+                const double inv = 1.0 / nrm;
+                for (int r = lane; r < n; r += 32) yi[r] *= inv;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__device__ bool ritz_residuals_ok(const CheckSmem& cs, int n, int cap, int kw, int want, double tol, double factor) {
     const double scale = fmax(fabs(cs.theta[0]), 1e-300);
     const double beta_last = cs.b[n - 1];
     bool ok = (n >= kw);
     for (int i = 0; i < want; ++i) {
         const double res = fabs(beta_last * cs.y[(size_t)i * cap + (n - 1)]);
-        if (!(res <= (i < kw ? tol : 1e-5) * scale)) ok = false;
+        if (!(res <= (i < kw ? tol : 1e-5) * factor * scale)) ok = false;
     }
     return ok;
 }
@@ -447,46 +477,66 @@ __device__ void checker_main(const Params& p, double* smem, int c) {
         if (__syncthreads_or(bad)) return;
         have = n;
         const int want = min(p.kw + p.guard, n);
-        const double tn = leading_eigenvalues(cs, n, want, prev_want >= want);
-        // A converged Ritz value no longer moves (its error is residual^2 / gap): the eigenvectors are only worth computing
-        // once the kw leading values have stopped moving since this checker's previous test.
-        bool stagnant = (prev_want >= want) && n >= p.kw;
+        const bool have_prev = prev_want >= want;
+        const bool track = have_prev && mode == 1;
+        // Tracking: cs.prev holds lower bounds of the leading eigenvalues from this checker's previous test (by interlacing
+        // they only grow with n).  Two multisection rounds from them bracket every value to ~2 % of its growth; a converged
+        // Ritz value no longer grows (its error is residual^2 / gap), so the eigenvectors are only worth computing once the
+        // kw leading values have stayed within a few ulps of |T| above their old bounds.
+        const long long tc0 = now();
+        double tn = leading_eigenvalues(cs, n, want, have_prev, false, track ? 2 : 0);
+        if (p.prof_on && tid == 0) p.ctl->prof[8 + 2 * c] += (1LL << 32) + (now() - tc0);      // tests, eigenvalue-tracking cycles
+        bool stagnant = track && n >= p.kw;
         if (stagnant) {
             const double thr = fmax(64.0 * 2.220446049250313e-16 * tn, 1e3 * p.tol * p.tol * tn);
             for (int i = 0; i < min(p.kw, want); ++i)
-                if (!(fabs(cs.theta[i] - cs.prev[i]) <= thr)) stagnant = false;
+                if (!(cs.hi[i] - cs.prev[i] <= thr)) stagnant = false;
         }
         __syncthreads();
-        if (tid < want) cs.prev[tid] = cs.theta[tid];
+        if (tid < want) cs.prev[tid] = track ? cs.lo[tid] : cs.theta[tid];
         prev_want = want;
         __syncthreads();
-        bool ok = false;
-        if (stagnant || mode != 1) ok = ritz_vectors_converged(cs, n, cap, p.kw, want, p.tol, tn);
-        if (ok || mode != 1) {
-            if (ok || mode == 4) {
-                // publish theta and S [n][kw] of this checker, then try to win the stop word
-                double* th = p.theta_out + (size_t)c * CH_MAXWANT;
-                double* S = p.S_out + (size_t)c * p.s_stride;
-                if (tid < CH_MAXWANT) th[tid] = tid < want ? cs.theta[tid] : 0.0;
-                for (int idx = tid; idx < n * p.kw; idx += CH_THREADS) {
-                    const int l = idx / p.kw, i = idx - l * p.kw;
-                    S[idx] = i < want ? cs.y[(size_t)i * cap + l] : 0.0;
-                }
-                publish_fence();
-                __syncthreads();
-                if (tid == 0) {
-                    const unsigned int word = 0x80000000u | ((unsigned int)c << 16) | (unsigned int)n;
-                    if (cas_word(&p.ctl->stop, 0u, word) == 0u) {
-                        p.ctl->n_final = n; p.ctl->winner = c; p.ctl->status = (want >= p.kw) ? 1 : 2;
-                    }
-                }
-            } else if (tid == 0) {
-                if (cas_word(&p.ctl->stop, 0u, 0x80000000u) == 0u) { p.ctl->n_final = n; p.ctl->winner = -1; p.ctl->status = 2; }
-            }
-            return;
-        }
-        next_n = n + p.n_checkers;
+        if (mode == 1 && !stagnant) { next_n = n + p.n_checkers; continue; }
+        const long long tc1 = now();
+        if (!track) { /* theta is final */ }
+        else if (tid < want) cs.theta[tid] = 0.5 * (cs.lo[tid] + cs.hi[tid]);      // stagnant: the bracket is a few ulps of |T| wide
         __syncthreads();
+        ritz_prepare(cs, n, cap, want, tn);
+        bool won = false;
+        if (mode == 1) {
+            // first solve: the residual estimates are already good to a small factor.  Raise the stop word on them (with a
+            // margin), so that the workers leave while the vectors are refined.
+            ritz_iterate(cs, n, cap, want, tn, false);
+            if (p.prof_on && tid == 0) p.ctl->prof[9 + 2 * c] += (1LL << 32) + (now() - tc1);  // vector tests, cycles up to the decision
+            if (!ritz_residuals_ok(cs, n, cap, p.kw, want, p.tol, 0.25)) { next_n = n + p.n_checkers; __syncthreads(); continue; }
+            if (tid == 0) s_mode = (cas_word(&p.ctl->stop, 0u, 0x80000000u | ((unsigned int)c << 16) | (unsigned int)n) == 0u) ? 1 : 0;
+            __syncthreads();
+            won = s_mode != 0;
+            __syncthreads();
+            if (!won) return;                                               // another checker stopped the iteration first
+            // the workers are leaving: now the eigenvalues down to the last ulp and the vectors from scratch
+            tn = leading_eigenvalues(cs, n, want, true, true, 0);
+            ritz_prepare(cs, n, cap, want, tn);
+        }
+        for (int it = 0; it < 3; ++it) ritz_iterate(cs, n, cap, want, tn, true);
+        const bool ok = ritz_residuals_ok(cs, n, cap, p.kw, want, p.tol, 1.0);
+        {
+            double* th = p.theta_out + (size_t)c * CH_MAXWANT;
+            double* S = p.S_out + (size_t)c * p.s_stride;
+            if (tid < CH_MAXWANT) th[tid] = tid < want ? cs.theta[tid] : 0.0;
+            for (int idx = tid; idx < n * p.kw; idx += CH_THREADS) {
+                const int l = idx / p.kw, i = idx - l * p.kw;
+                S[idx] = i < want ? cs.y[(size_t)i * cap + l] : 0.0;
+            }
+            publish_fence();
+            __syncthreads();
+            if (tid == 0) {
+                const bool accept = (ok || mode == 4) && want >= p.kw;
+                if (!won) won = cas_word(&p.ctl->stop, 0u, 0x80000000u | ((unsigned int)c << 16) | (unsigned int)n) == 0u;
+                if (won) { p.ctl->n_final = n; p.ctl->winner = accept ? c : -1; p.ctl->status = accept ? 1 : 2; }
+            }
+        }
+        return;
     }
 }
 
@@ -860,6 +910,11 @@ int chain_result(esper_ctx* c, int k, double* theta_out, int* iters_out) {
         const double n = h->steps_run > 0 ? (double)h->steps_run : 1.0;
         fprintf(stderr, "[chain] CTA0 cycles/step: S0 %.0f | P1-P3 %.0f | norm+publish %.0f | P4 %.0f | second pass %.0f ; prologue %lld\n",
                 h->prof[1] / n, h->prof[2] / n, h->prof[3] / n, h->prof[4] / n, h->prof[6] / n, h->prof[0]);
+        for (int cc = 0; cc < CH_MAXCHK; ++cc) {
+            const long long e = h->prof[8 + 2 * cc], v = h->prof[9 + 2 * cc];
+            if (e >> 32) fprintf(stderr, "[chain] checker %d: %lld eigenvalue tests, %.0f cycles each; %lld vector tests, %.0f cycles each up to the decision\n", cc, e >> 32,
+                                 (double)(e & 0xffffffffLL) / (double)(e >> 32), v >> 32, (v >> 32) ? (double)(v & 0xffffffffLL) / (double)(v >> 32) : 0.0);
+        }
     }
     if (h->abort != 0u) return fail(c, ESPER_E_CUDA, "lanczos (chain): a packet wait timed out (CTAs not co-resident?)");
     if (h->status != 1 || h->winner < 0) return 1;

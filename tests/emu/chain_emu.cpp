@@ -23,6 +23,7 @@ constexpr int CH_REGROWS = 4;
 constexpr int CH_MAXM = 2048;
 constexpr int CH_MAXWANT = 24;
 constexpr int CH_MAXCHK = 4;
+constexpr int CH_POINTS = 16;
 constexpr int CH_HWARP = 8;
 constexpr int CH_PK = 8;
 constexpr long long CH_TIMEOUT = 4000000000LL;

@@ -402,7 +402,7 @@ def chain_bin(tmp_path_factory):
 
 
 @pytest.mark.parametrize('m,grid,kw,max_steps,expect', [(45, 5, 4, 40, 'converged'), (20, 10, 4, 19, 'exhausted'), (45, 5, 4, 10, 'noconv'),
-                                                         (100, 9, 6, 90, 'converged')])
+                                                         (100, 9, 6, 90, 'converged'), (40, 16, 4, 36, 'converged')])
 def test_chain_lanczos_kernel_on_the_cpu(chain_bin, m, grid, kw, max_steps, expect):
     """Workers (rows of Ms and of the basis on chip, packet hand-overs, no grid barrier) and checker CTAs (multisection
     Sturm counts, inverse iteration, stop word) together: alpha / beta against a numpy Lanczos with the same start,
