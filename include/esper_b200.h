@@ -89,6 +89,11 @@ int esper_upload_images(esper_ctx* ctx, const float* imgs, int n, int P);
  * units fill the SMs); refine_tau (0.05: pairs with D^2*P < 0.05(|x|^2+|y|^2), i.e. near-duplicate images, where
  * Gram cancellation would exceed 1e-5; calibrated with tools/calib_gram_error.py). */
 int esper_dist_config(esper_ctx* ctx, int split_k, double refine_tau);
+/* With ESPER_DIST_REFINE, stacks of at most this many images are computed pair by pair in the reference's own arithmetic
+ * (float64 sum of squared differences of the float32 z-scores, Distances.py:96-104): the reference's CPU-runnable inputs (400
+ * noise-free states) sit entirely in the Gram-cancellation regime, and the exp(-D^2/2eps) of stage 3 amplifies a 1e-5
+ * distance error ~20x.  Larger stacks use the tensor-core contraction with refinement of the near-duplicate pairs only. */
+#define ESPER_EXACT_PAIRS_MAX_N 512
 /* Operand format of the stage-1 tensor-core contraction.  mode 0: 3xTF32 -- every centred z-score c is split into
  * two TF32 values, hi*hi + hi*lo + lo*hi accumulate in FP32.  mode 1 (default): 3xFP16 -- the same split into two FP16 values of
  * c * 2^s (an FP16 significand has the same 11 bits as a TF32 one; s is chosen from P so that |c| <= 2 sqrt(P) stays in

@@ -192,7 +192,8 @@ int esper_dist_rms(esper_ctx* c, const float* imgs, int n, int P, unsigned flags
     const int ld = (int)round_up((size_t)P, hs >= 0 ? 64 : 32);
     ESPER_RESERVE(c, c->dist, sizeof(double) * (size_t)n * n);
     c->dist_m = 0;
-    int rc = run_prep(c, n, P, flags, rows_pad, ld, false, hs);
+    const bool exact_small = (flags & ESPER_DIST_REFINE) && (flags & ESPER_DIST_STANDARDIZE) && n <= ESPER_EXACT_PAIRS_MAX_N;
+    int rc = run_prep(c, n, P, flags, rows_pad, ld, false, hs, exact_small);
     if (rc) return rc;
     rc = run_gram(c, n, P, rows_pad, ld, flags, -1, 0, nullptr, hs);
     if (rc) return rc;

@@ -173,7 +173,7 @@ inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 struct RowStat;
 // ---- per-stage entry points implemented in the .cu files (host side) ----
 int prep_and_gram(esper_ctx* c, int n, int P, unsigned flags);                 // k0_prep.cu + k1_gram.cu
-int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld, bool exact_center = false, int half_scale_log2 = -1);
+int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld, bool exact_center = false, int half_scale_log2 = -1, bool numpy_stats = false);
 int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, int row0 = -1, int nrows = 0, double* gram_out = nullptr,
              int half_scale_log2 = -1);
 int gram_f16_scale_log2(int P);
@@ -188,7 +188,7 @@ int run_moment_accum_rows(esper_ctx* c, int rows, int m, const double* coef_h, i
 void moment_layout_host(int* out5);
 int run_product(esper_ctx* c, float* a_hi, float* a_lo, int na, float* b_hi, float* b_lo, int nb, int ld, double* M);
 int run_ctf_dist(esper_ctx* c, int n, int box, const double* params_h, unsigned flags, bool want_wiener);
-int row_stats_numpy(esper_ctx* c, int n, int P, RowStat* st);
+int row_stats_numpy(esper_ctx* c, int n, int P, RowStat* st, int centered_std = 0);
 int run_markov(esper_ctx* c, int m, double eps);
 int run_lanczos(esper_ctx* c, int m, int k, double tol, int max_iter, double* val_h, double* vec_h, int* iters, bool plain = false);
 int run_rot_eval(esper_ctx* c, const double* Uinit, int n_pd, int m, int dim, const double* R,

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict_
         if (threadIdx.x == 0) { st[i].mean = 0.f; st[i].stdv = 1.f; st[i].norm2 = 0.0; }
         return;
     }
+    if (standardize == 2) return;                        // statistics already in st (np_stats_kernel)
     float m32, s32;
     row_stats(raw + (size_t)i * P, P, sh, m32, s32);
     if (threadIdx.x == 0) { st[i].mean = m32; st[i].stdv = s32; st[i].norm2 = 0.0; }
@@ -109,7 +110,8 @@ __global__ void __launch_bounds__(512) stats_split_kernel(const float* __restric
     int i = blockIdx.x;
     const float* row = raw + (size_t)i * P;
     float m = 0.f, sd = 1.f;
-    if (standardize) row_stats(row, P, sh, m, sd);
+    if (standardize == 1) row_stats(row, P, sh, m, sd);
+    else if (standardize == 2) { m = st[i].mean; sd = st[i].stdv; }      // numpy's own float32 statistics (np_stats_kernel)
     const bool vec = ((P & 3) == 0);
     double acc = 0.0;
     int nq = ld >> 2;
@@ -177,11 +179,14 @@ __global__ void __launch_bounds__(512) stats_split_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------------
 struct PwNode { int left, right, out; };
 
-__device__ __forceinline__ float pw_leaf(const float* __restrict__ a, int len, int lane8, float mean, int squared) {
+// kind 0: x;  1: (x - mean)^2;  2: x - mean;  3: ((x - mean) - mean2)^2   (every operation rounded to float32)
+__device__ __forceinline__ float pw_leaf(const float* __restrict__ a, int len, int lane8, float mean, float mean2, int kind) {
     auto elem = [&](int i) -> float {
         const float x = __ldg(a + i);
-        if (!squared) return x;
-        const float d = __fsub_rn(x, mean);
+        if (kind == 0) return x;
+        float d = __fsub_rn(x, mean);
+        if (kind == 2) return d;
+        if (kind == 3) d = __fsub_rn(d, mean2);
         return __fmul_rn(d, d);
     };
     if (len < 8) {                                   // only a whole array shorter than 8 elements
@@ -199,19 +204,24 @@ __device__ __forceinline__ float pw_leaf(const float* __restrict__ a, int len, i
     return r;
 }
 
+// centered_std = 0: mean() and std() of the image as it is (`(tmp - tmp.mean()) / tmp.std()`, Distances.py:114-115).
+// centered_std = 1: the non-CTF branch (Distances.py:89-91) subtracts the mean in place first and takes std() of the centred
+//                   float32 image, whose own float32 mean is a tiny non-zero number that numpy subtracts again inside std().
 __global__ void __launch_bounds__(256) np_stats_kernel(const float* __restrict__ raw, int P, const int2* __restrict__ leaves,
                                                        int L, const PwNode* __restrict__ nodes, const int* __restrict__ level_off,
-                                                       int n_levels, int root, RowStat* __restrict__ st) {
+                                                       int n_levels, int root, RowStat* __restrict__ st, int centered_std) {
     extern __shared__ float slot[];
     const int img = blockIdx.x;
     const float* a = raw + (size_t)img * P;
     const int group = threadIdx.x >> 3, lane8 = threadIdx.x & 7, n_groups = blockDim.x >> 3;
-    float mean = 0.f, stdv = 1.f;
-    for (int pass = 0; pass < 2; ++pass) {
+    float mean = 0.f, mean2 = 0.f, stdv = 1.f;
+    const int n_pass = centered_std ? 3 : 2;
+    for (int pass = 0; pass < n_pass; ++pass) {
+        const int kind = centered_std ? (pass == 0 ? 0 : pass == 1 ? 2 : 3) : pass;
         for (int lf = group; lf < ((L + n_groups - 1) / n_groups) * n_groups; lf += n_groups) {   // whole warps stay converged
             const bool live = lf < L;
             const int2 ol = live ? leaves[lf] : make_int2(0, 8);
-            const float v = pw_leaf(a + ol.x, live ? ol.y : (P < 8 ? P : 8), lane8, mean, pass);
+            const float v = pw_leaf(a + ol.x, live ? ol.y : (P < 8 ? P : 8), lane8, mean, mean2, kind);
             if (live && lane8 == 0) slot[lf] = v;
         }
         __syncthreads();
@@ -225,6 +235,7 @@ __global__ void __launch_bounds__(256) np_stats_kernel(const float* __restrict__
         const float total = slot[root];
         __syncthreads();
         if (pass == 0) mean = __fdiv_rn(total, (float)P);
+        else if (centered_std && pass == 1) mean2 = __fdiv_rn(total, (float)P);
         else stdv = __fsqrt_rn(__fdiv_rn(total, (float)P));
     }
     if (threadIdx.x == 0) { st[img].mean = mean; st[img].stdv = stdv; st[img].norm2 = 0.0; }
@@ -251,7 +262,7 @@ struct PwBuild {
 }  // namespace
 
 // float32 mean / population std of every image of the resident stack, bit-identical to numpy's (see above)
-int row_stats_numpy(esper_ctx* c, int n, int P, RowStat* st) {
+int row_stats_numpy(esper_ctx* c, int n, int P, RowStat* st, int centered_std) {
     if (c->pw_P != P) {
         PwBuild b;
         const int root = b.build(0, P);
@@ -281,14 +292,14 @@ int row_stats_numpy(esper_ctx* c, int n, int P, RowStat* st) {
     const int* level_off = reinterpret_cast<const int*>(base + sizeof(int2) * (size_t)c->pw_L + sizeof(PwNode) * ((size_t)c->pw_nodes + 1));
     const size_t smem = sizeof(float) * (size_t)(c->pw_L + c->pw_nodes + 1);
     if (smem > 48 * 1024) return fail(c, ESPER_E_ARG, "row statistics: %d pixels per image need %zu bytes of shared memory", P, smem);
-    np_stats_kernel<<<n, 256, smem, c->stream>>>(c->imgs.as<float>(), P, leaves, c->pw_L, nodes, level_off, c->pw_levels, c->pw_root, st);
+    np_stats_kernel<<<n, 256, smem, c->stream>>>(c->imgs.as<float>(), P, leaves, c->pw_L, nodes, level_off, c->pw_levels, c->pw_root, st, centered_std);
     ESPER_CUDA(c, cudaGetLastError());
     return ESPER_OK;
 }
 
 // half_scale_log2 < 0: TF32 planes (float32 storage, ld a multiple of 32); >= 0: FP16 planes scaled by 2^half_scale_log2
 // (ld a multiple of 64).
-int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld, bool exact_center, int half_scale_log2) {
+int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld, bool exact_center, int half_scale_log2, bool numpy_stats) {
     const float* raw = c->imgs.as<float>();
     ESPER_RESERVE(c, c->row_stats, sizeof(RowStat) * (size_t)rows_pad);
     const bool half = half_scale_log2 >= 0;
@@ -296,8 +307,16 @@ int run_prep(esper_ctx* c, int n, int P, unsigned flags, int rows_pad, int ld, b
     ESPER_RESERVE(c, c->plane_hi, esz * (size_t)rows_pad * ld);
     ESPER_RESERVE(c, c->plane_lo, esz * (size_t)rows_pad * ld);
     RowStat* st = c->row_stats.as<RowStat>();
-    const int standardize = (flags & ESPER_DIST_STANDARDIZE) ? 1 : 0;
+    int standardize = (flags & ESPER_DIST_STANDARDIZE) ? 1 : 0;
     const int center = (flags & ESPER_DIST_CENTER) ? 1 : 0;
+    if (standardize && numpy_stats && (size_t)P <= (size_t)1 << 19) {
+        // small stacks: mean32 / std32 exactly as numpy computes them for `image -= image.mean(); image /= image.std()`
+        // (Distances.py:89-91), so that the z-scores -- and with them the pair-by-pair distances -- carry the reference's bits
+        LaunchScope ls(c, "prep");
+        int rc = row_stats_numpy(c, n, P, st, 1);
+        if (rc) return rc;
+        standardize = 2;
+    }
     float* xbar = nullptr;
     if (center) {
         // distances: any common image may be subtracted, a subset mean (images 0, stride, 2*stride, ...) serves;

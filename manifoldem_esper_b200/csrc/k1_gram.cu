@@ -955,7 +955,11 @@ int run_gram(esper_ctx* c, int n, int P, int rows_pad, int ld, unsigned flags, i
         {
             LaunchScope ls(c, "refine");
             const long long tot = (long long)nrows * n;
-            flag_pairs_kernel<<<ceil_div(tot, 256), 256, 0, c->stream>>>(D, n, row0, nrows, rect ? 1 : 0, P, st, c->refine_tau, pairs, count, cap);
+            // Small stacks (the reference's own CPU-runnable inputs: 400 pristine states, config 1) are noise-free, every pair is
+            // "close" and the 1e-5 error budget of D is amplified ~20x by exp(-D^2 / 2 eps) downstream: there all pairs are
+            // recomputed in the reference's arithmetic (|c_i - c_j|^2 < 2 (|c_i|^2 + |c_j|^2) always holds).
+            const double tau = (n <= ESPER_EXACT_PAIRS_MAX_N) ? fmax(c->refine_tau, 2.0) : c->refine_tau;
+            flag_pairs_kernel<<<ceil_div(tot, 256), 256, 0, c->stream>>>(D, n, row0, nrows, rect ? 1 : 0, P, st, tau, pairs, count, cap);
         }
         {
             LaunchScope ls(c, "refine");
