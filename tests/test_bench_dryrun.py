@@ -37,8 +37,20 @@ class FakeCtx:
     def gram_config(self, mode=0):
         self.cfg['gram'] = mode
 
-    def prep_config(self, mode=0):
-        self.cfg['prep'] = mode
+    def close(self):
+        pass
+
+    def pd_embed_fused(self, imgs, logEps, a0, k=16, n=None, P=None, out=None, **kw):
+        from manifoldem_esper_b200 import _capi
+        D = self.dist_rms(imgs, n=n, P=P, download=True, out=out)
+        L = self.eps_sweep(None, 1. / (2. * np.exp(np.asarray(logEps))), 10.0, m=n)
+        popt, resnorm, R2, info, _ = _capi.tanh_fit(logEps, L, a0)
+        eps = float(np.exp(-(popt[1] / popt[0])))
+        val, vec, it = self.dmap_embed(None, eps, k=k, m=n)
+        r = dict(logSumWij=L, popt=popt, resnorm=resnorm, R2=R2, eps=eps, slope=popt[0] * popt[2], val=val, vec=vec, iters=it)
+        if out is not None:
+            r['D'] = D
+        return r
 
     def sweep_config(self, mode=0):
         self.cfg['sweep'] = mode
@@ -94,7 +106,7 @@ class _Stream:
         pass
 
 
-@pytest.mark.parametrize('flags', [[], ['--gram-f16', '--prep-cluster', '--sweep-moments', '--eig-mode', '2', '--scipy-fit']])
+@pytest.mark.parametrize('flags', [[], ['--gram-tf32', '--sweep-general', '--eig-mode', '2', '--scipy-fit']])
 def test_bench_gpu_arm_dry_run(monkeypatch, flags):
     import torch
     import bench
@@ -121,7 +133,7 @@ def test_bench_gpu_arm_dry_run(monkeypatch, flags):
                                                                          'vectorised_dist_s': 0.8, 'vectorised_total_s': 25.0}))
     for var in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE'):
         monkeypatch.delenv(var, raising=False)
-    monkeypatch.setattr(sys, 'argv', ['bench.py', '--steps', '4', '--warmup', '3', '--inflight', '2'] + flags + ([] if flags else ['--no-probe']))
+    monkeypatch.setattr(sys, 'argv', ['bench.py', '--steps', '4', '--warmup', '3', '--inflight', '2', '--no-extras'] + flags)
     buf = io.StringIO()
     with redirect_stdout(buf):
         assert bench.main() == 0
@@ -145,12 +157,9 @@ def test_bench_gpu_arm_dry_run(monkeypatch, flags):
     for key in ('value', 'unit', 'cores', 'kind', 'sample'):
         assert key in d['cpu_baseline'], key
     assert d['gpu_launches'] == 4 * 13                               # counted over the timed region only
-    exp = d['config']['experimental']
-    assert exp == {'gram_f16': bool(flags), 'sweep_moments': bool(flags), 'prep_cluster': bool(flags)}
-    assert d['dtype'] == ('f16x3+f64' if flags else 'tf32x3+f64')
-    assert ('curve_fit' in d['config']['tanh_fit']) == bool(flags)
-    if flags:                                                        # the probes ran as subprocesses; without a GPU each reports an error
-        assert set(d['experimental_probe']) == {'sweep', 'prep', 'eig', 'gram'}
-        assert all(v['ok'] is False and 'error' in v for v in d['experimental_probe'].values())
-    else:
-        assert 'experimental_probe' not in d
+    assert d['config']['kernels'] == {'gram_f16': not flags, 'sweep_moments': not flags}
+    assert d['dtype'] == ('tf32x3+f64' if flags else 'f16x3+f64')
+    assert ('curve_fit' in d['config']['tanh_fit']) == bool(flags) and ('esper_pd_embed_fused' in d['config']['api']) == (not flags)
+    for key in ('frac_issued', 'frac_in_step_vs_sustained', 'peak_sustained', 'traffic_note'):
+        assert key in d['roofline'], key
+    assert 'frac_of_h2d_floor' in d['e2e'] and 'c5_rot' not in d and 'experimental_probe' not in d
