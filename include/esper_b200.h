@@ -94,6 +94,7 @@ int esper_dist_config(esper_ctx* ctx, int split_k, double refine_tau);
  * noise-free states) sit entirely in the Gram-cancellation regime, and the exp(-D^2/2eps) of stage 3 amplifies a 1e-5
  * distance error ~20x.  Larger stacks use the tensor-core contraction with refinement of the near-duplicate pairs only. */
 #define ESPER_EXACT_PAIRS_MAX_N 512
+#define ESPER_DEFAULT_EIG_TOL 1e-8
 /* Operand format of the stage-1 tensor-core contraction.  mode 0: 3xTF32 -- every centred z-score c is split into
  * two TF32 values, hi*hi + hi*lo + lo*hi accumulate in FP32.  mode 1 (default): 3xFP16 -- the same split into two FP16 values of
  * c * 2^s (an FP16 significand has the same 11 bits as a TF32 one; s is chosen from P so that |c| <= 2 sqrt(P) stays in
@@ -145,7 +146,12 @@ int esper_markov(esper_ctx* ctx, const double* D, int m, double eps, double* deg
  *   val: [k]   = lambda^2, descending (what the reference saves as PD_%s_val.npy)
  *   vec: [m,k] row-major; column 0 = sqrt(degree)/|sqrt(degree)| (steady state), unit columns,
  *              sign fixed so that the entry of largest magnitude is positive
- *   tol: relative residual |Ms v - lambda v| <= tol*lambda_1  (0 = 1e-10)
+ *   tol: relative residual |Ms v - lambda v| <= tol*lambda_1  (0 = ESPER_DEFAULT_EIG_TOL = 1e-8).  The default is tied to the
+ *        parity contract (eigenvalues 1e-6 relative, eigenvectors 1e-4): a Ritz value is off by residual^2 / gap (~1e-14 here)
+ *        and a Ritz vector by residual / gap, i.e. <= 5e-6 for every pair whose gap to its neighbours is at least 2e-3 lambda_1
+ *        (the pairs the contract compares one by one); members of tighter clusters -- the bulk edge of a noisy PD, where the
+ *        tenth and eleventh eigenvalue differ by 1e-4 relative -- are determined as a subspace, as the SVD of the reference
+ *        itself determines them.  On the benchmark matrix 1e-8 needs 164 Lanczos steps, 1e-10 needs 184 (tools/eig_probe.py).
  *   max_iter: Lanczos steps (0 = min(m-1, 1024));  iters (optional) receives the steps used.  */
 /* Eigensolver scheduling for m <= 2048.  mode 0 (default, lowest latency for one PD): every CTA keeps its rows of
  * Ms in shared memory / registers for the whole solve (the kernel owns the SMs).  mode 1 (highest throughput with

@@ -563,7 +563,7 @@ int esper_lanczos_ortho_d(esper_ctx* c, int n, int j, double* V_d, double* w_d, 
 int esper_tridiag_ritz(const double* alpha, const double* beta, int steps, int k, double tol, int* converged,
                        double* theta, double* S) {
     if (!alpha || !beta || steps < 1 || k < 2 || !converged) return ESPER_E_ARG;
-    if (tol <= 0.0) tol = 1e-10;
+    if (tol <= 0.0) tol = ESPER_DEFAULT_EIG_TOL;
     const int kw = k - 1;
     std::vector<double> a(alpha, alpha + steps), b(beta, beta + steps), th, Sv;
     const int guard = 2;

@@ -1408,7 +1408,7 @@ int run_lanczos(esper_ctx* c, int m, int k, double tol, int max_iter, double* va
         k += 1;
     }
     if (k < 1 || k > m || k > KMAX) return fail(c, ESPER_E_ARG, "k=%d out of range (1..min(m,%d))", k, KMAX);
-    if (tol <= 0.0) tol = 1e-10;
+    if (tol <= 0.0) tol = ESPER_DEFAULT_EIG_TOL;
     if (max_iter <= 0) max_iter = 1024;
     if (max_iter > m - 1) max_iter = m - 1;
     // Default: full reorthogonalisation (three grid barriers per step).  The partial-reorthogonalisation kernel

@@ -191,14 +191,14 @@ def test_rowblock_cuda_backend_single_rank(ctx):
         ctx.dist_config(split_k=4)                           # the same K chunks in the full matrix and in the row blocks: same bits
         D = ctx.dist_rms(X)
         eps = 0.35
-        val_r, vec_r, _ = ctx.dmap_embed(None, eps, k=8, m=n)
+        val_r, vec_r, _ = ctx.dmap_embed(None, eps, k=8, m=n, tol=1e-11)
         dev = torch.device('cuda', 0)
         outs = []
         for fused in (False, True):
             be = RB.CudaBackend(ctx, X, n, P, dev, fused=fused)
             comm = RB.TorchComm(dev, stream=be.stream)
             for rep in range(2 if fused else 1):                                     # a second embedding on the same communicator
-                out = RB.embed_oversized(be, comm, n, k=8, eps=eps)
+                out = RB.embed_oversized(be, comm, n, k=8, eps=eps, tol=1e-11)
                 outs.append(out)
                 assert np.max(np.abs(out['val'] - val_r) / val_r) < 1e-10
                 for i in range(5):
@@ -212,7 +212,7 @@ def test_rowblock_cuda_backend_single_rank(ctx):
         o1 = RB.embed_oversized(be, comm, n, k=4, moments=True)
         o2 = RB.embed_oversized(be, comm, n, k=4, moments=False)
         assert o1['sweep_path'] == 'moments' and o2['sweep_path'] == 'general'
-        assert np.max(np.abs(o1['logSumWij'] - o2['logSumWij'])) < 1e-12 and abs(o1['eps'] - o2['eps']) / o2['eps'] < 1e-9
+        assert np.max(np.abs(o1['logSumWij'] - o2['logSumWij'])) < 1e-12 and abs(o1['eps'] - o2['eps']) / o2['eps'] < 1e-7
         np.random.seed(12345)
         L = GaussianBandwidth.sweep(D, LOG_EPS, ctx=ctx)
         assert np.max(np.abs(o2['logSumWij'] - L)) < 1e-12
