@@ -44,7 +44,8 @@ def embed(Dist, k=16, eps=None, a0=None, tol=0.0, ctx=None, verbose=True):
     return out
 
 
-def op(pyDir, PD, k=16, eps=None, ctx=None):
+def run(pyDir, PD, k=16, eps=None, ctx=None):
+    """`op` that also returns a summary dict (eps, R2, slope, lanczos_steps) -- what the launcher records per PD."""
     outDir = os.path.join(pyDir, 'Data_Manifolds')
     if not os.path.exists(outDir):
         os.mkdir(outDir)
@@ -53,9 +54,35 @@ def op(pyDir, PD, k=16, eps=None, ctx=None):
     res = embed(Dist, k=k, eps=eps, ctx=ctx)
     np.save(os.path.join(outDir, 'PD_%s_val.npy' % PD), res['val'])
     np.save(os.path.join(outDir, 'PD_%s_vec.npy' % PD), res['vec'])
-    # the reference returns None; the summary below is what its prints show (:94-96) plus the solver's step count
+    # what the reference prints (:94-96) plus the solver's step count
     return {'eps': float(res['eps']), 'R2': float(res['R2']) if 'R2' in res else None,
             'slope': float(res['slope']) if 'slope' in res else None, 'lanczos_steps': int(res['iters'])}
+
+
+def op(pyDir, PD, k=16, eps=None, ctx=None):
+    """Same call as the reference's DiffusionMaps.op(pyDir, PD) (:57): writes the two files, returns None."""
+    run(pyDir, PD, k=k, eps=eps, ctx=ctx)
+
+
+def embed_stack_to_files(pyDir, PD, stackPath=None, k=16, a0=None, ctx=None, n=None, P=None):
+    """Distances.op (non-CTF branch) + DiffusionMaps.op of one PD in ONE library call (esper_pd_embed_fused): the stack goes from
+    the MRC file (or, stackPath=None with n and P given, from the stack already resident on the device) to
+    Data_Distances/PD_%s_dist.npy, Data_Manifolds/PD_%s_val.npy and PD_%s_vec.npy without the distance matrix making the
+    round trip through a file.  `a0` is the tanh-fit start (drawn from numpy's global RNG like the reference when None)."""
+    ctx = ctx or _capi.default_context()
+    if stackPath is not None:
+        n, N1, N2 = ctx.upload_mrc(stackPath)
+        P = N1 * N2
+    if a0 is None:
+        a0 = 1 * (np.random.rand(4, 1) - .5)
+    res = ctx.pd_embed_fused(None, LOG_EPS, a0, k=min(k, n), n=n, P=P, want_D=True)
+    for sub_, name, arr in (('Data_Distances', 'PD_%s_dist.npy', res['D']), ('Data_Manifolds', 'PD_%s_val.npy', res['val']),
+                            ('Data_Manifolds', 'PD_%s_vec.npy', res['vec'])):
+        d = os.path.join(pyDir, sub_)
+        if not os.path.exists(d):
+            os.makedirs(d, exist_ok=True)
+        np.save(os.path.join(d, name % PD), arr)
+    return {'eps': float(res['eps']), 'R2': float(res['R2']), 'slope': float(res['slope']), 'lanczos_steps': int(res['iters'])}
 
 
 if __name__ == '__main__':

@@ -121,10 +121,18 @@ def _stage_fns(root, stages, dim, pca, k, skip_existing, device, ctf=True):
             out = os.path.join(dm_dir, 'Data_Distances', 'PD_%s_dist.npy' % pd)
             if not (skip_existing and os.path.exists(out)):
                 t = time.time(); Distances.op(dm_dir, pd, CTF=ctf, ctx=ctx); info['dist_s'] = time.time() - t
+        if 'embed' in stages:                        # dist + dm of the non-CTF branch in one library call (esper_pd_embed_fused)
+            out = os.path.join(dm_dir, 'Data_Manifolds', 'PD_%s_vec.npy' % pd)
+            if not (skip_existing and os.path.exists(out)):
+                data = os.path.join(root, '0_Data_Inputs', 'CTF5k15k_SNRpt1_ELS_2D')
+                path = os.path.join(data, 'PD%s_SNR_tau5_stack.mrcs' % pd)
+                if not os.path.exists(path):
+                    path = os.path.join(data, 'PD_%s.mrcs' % pd)
+                t = time.time(); info.update(DiffusionMaps.embed_stack_to_files(dm_dir, pd, stackPath=path, k=k, ctx=ctx)); info['embed_s'] = time.time() - t
         if 'dm' in stages:
             out = os.path.join(dm_dir, 'Data_Manifolds', 'PD_%s_vec.npy' % pd)
             if not (skip_existing and os.path.exists(out)):
-                t = time.time(); info.update(DiffusionMaps.op(dm_dir, pd, k=k, ctx=ctx) or {}); info['dm_s'] = time.time() - t
+                t = time.time(); info.update(DiffusionMaps.run(dm_dir, pd, k=k, ctx=ctx) or {}); info['dm_s'] = time.time() - t
         if 'pca' in stages:
             out = os.path.join(pca_dir, 'Data_Manifolds', 'PD_%s_vec.npy' % pd)
             if not (skip_existing and os.path.exists(out)):
@@ -141,7 +149,7 @@ def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__.split('\n')[0])
     ap.add_argument('--root', required=True)
     ap.add_argument('--pds', default='1-126')
-    ap.add_argument('--stages', default='dist,dm,rot', help='comma list of dist, dm, pca, rot')
+    ap.add_argument('--stages', default='dist,dm,rot', help='comma list of dist, dm, embed (= dist + dm of the non-CTF branch in one library call), pca, rot')
     ap.add_argument('--dim', type=int, default=6)
     ap.add_argument('--pca', action='store_true')
     ap.add_argument('--no-ctf', action='store_true', help='Distances: CTF = False branch (the reference ships CTF = True)')

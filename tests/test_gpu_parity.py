@@ -124,7 +124,7 @@ def test_distances_op_files(ctx, tmp_path):
     Distances.op(str(dm), '003', CTF=False, ctx=ctx)
     D = np.load(str(dm / 'Data_Distances' / 'PD_003_dist.npy'))
     assert D.dtype == np.float64 and D.flags.c_contiguous and d_err(D, g['D']) < D_TOL
-    DiffusionMaps.op(str(dm), '003', k=8, ctx=ctx)
+    assert DiffusionMaps.op(str(dm), '003', k=8, ctx=ctx) is None                 # the reference's op returns nothing (:57)
     val = np.load(str(dm / 'Data_Manifolds' / 'PD_003_val.npy'))
     vec = np.load(str(dm / 'Data_Manifolds' / 'PD_003_vec.npy'))
     assert val.shape == (8,) and vec.shape == (D.shape[0], 8) and abs(val[0] - 1) < 1e-12
@@ -599,7 +599,6 @@ def test_eigensolver_modes_agree(ctx):
             ctx.dmap_config(0)
     assert ctx.stat('lanczos_fallbacks') == 0                                 # the chain kernel converged by itself
     v3, U3, it3 = res[3]
-    assert res[1][2] == it3
     for mode in (1, 0):
         v, U, it = res[mode]
         assert np.max(np.abs(v - v3) / v3) < 1e-12, mode
@@ -923,3 +922,17 @@ def test_whole_chain_through_files_with_the_launcher(ctx, tmp_path):
         out = rot / 'Data_Rotations' / ('PD%s' % pd)
         assert np.array_equal(np.load(str(out / ('PD%s_RotMatrices.npy' % pd))), ref['RotMatrices'])
         assert np.array_equal(np.load(str(out / ('PD%s_RotEigenfunctions.npy' % pd))), ref['RotEigenfunctions'])
+        # the consumer's side of the contract: the files load the way 3_Manifold_Binning/Manifold_Binning.py:88-139 loads them
+        from consumer_contract import load_like_manifold_binning
+        c = load_like_manifold_binning(str(root), pd)
+        assert c['dim'] == 4 and c['rotMatrix'].shape[1] == 6
+    # the same tree through the fused stage (Distances.op + DiffusionMaps.op in one library call): same files
+    import shutil
+    D1 = np.load(str(dm / 'Data_Distances' / 'PD_001_dist.npy')); vec1 = np.load(str(dm / 'Data_Manifolds' / 'PD_001_vec.npy'))
+    shutil.rmtree(str(dm / 'Data_Distances')); shutil.rmtree(str(dm / 'Data_Manifolds'))
+    work = launcher._stage_fns(str(root), {'embed'}, 4, False, 8, False, ctx.device, ctf=False)
+    recs = launcher.run_sharded(pds, work, 0, 1)
+    assert all(r['ok'] for r in recs), recs
+    assert np.array_equal(np.load(str(dm / 'Data_Distances' / 'PD_001_dist.npy')), D1)
+    vec2 = np.load(str(dm / 'Data_Manifolds' / 'PD_001_vec.npy'))
+    assert vec2.shape == vec1.shape and all(vec_err(vec1[:, i], vec2[:, i]) < 1e-3 for i in range(3))   # own random fit starts: eps differs ~1e-6

@@ -169,5 +169,5 @@ def test_cuda_backend_implements_the_backend_interface():
     import re
     names = set(re.findall(r'^    def ([a-z][a-z_]*)\(', WORKER.split('class NumpyBackend')[1].split('\ndef ')[0], flags=re.M))
     assert {'dist_rows', 'symv', 'ortho', 'read_ab', 'ritz_vectors'} <= names
-    for name in sorted(names) + ['symv_allgather', 'comm_check', 'lanczos_free', 'comm_close', 'sync']:
+    for name in sorted(names) + ['symv_allgather', 'comm_check', 'comm_close', 'sync']:
         assert callable(getattr(rowblock.CudaBackend, name, None)), name
