@@ -410,7 +410,9 @@ def run_ours(args):
     pipelined(NF, True)
     ms_e2e = pipelined(args.steps, True)
 
-    # raw host->device rate of this box for one 500 MB stack (what bounds the e2e figure)
+    # raw host->device rate of this box for one 500 MB stack (what bounds the e2e figure); all ranks copy at the same time, so at
+    # N > 1 this is the per-GPU share of the box's aggregate pinned-copy ceiling, not the link rate of one GPU
+    barrier()
     probe = torch.empty((N_IMG, P), dtype=torch.float32, device='cuda')
     probe.copy_(pinned[0], non_blocking=True)
     torch.cuda.synchronize()
@@ -536,7 +538,8 @@ def run_ours(args):
                 'ms_per_step': ms_e2e / args.steps, 'h2d_probe_gbs': round(h2d_gbs, 2),
                 'h2d_floor_ms_per_step': round(N_IMG * P * 4 / (h2d_gbs * 1e9) * 1e3, 3),
                 'eigensolver_mode': eig_mode_e2e,
-                'note': 'bounded by the host->device copy of the 500 MB stack (probe: bare pinned cudaMemcpyAsync rate on this box)'},
+                'note': 'bounded by the host->device copy of the 500 MB stack; h2d_probe_gbs = bare pinned cudaMemcpyAsync rate per GPU with all %d '
+                        'ranks copying at once (the box ceiling at this N), h2d_floor_ms_per_step = 500 MB at that rate, frac_of_h2d_floor = floor / measured' % world},
         'gpu_launches': launches,
         'clocks': clocks,
         'roofline': {'bound': 'tensor', 'kernel': gram_kernel_name,

@@ -258,6 +258,10 @@ int esper_comm_close(esper_ctx* ctx);
 int esper_symv_allgather_d(esper_ctx* ctx, int nrows, int n, int row0, const double* q_d, int step);
 int esper_comm_wait_d(esper_ctx* ctx, int step, int n, double** w_full_d);
 int esper_comm_status(esper_ctx* ctx, unsigned int* status);
+/* n_steps Lanczos steps j0 .. j0+n_steps-1 of the fused exchange enqueued by ONE host call: per step esper_symv_allgather_d (tag
+ * step0 + i) -> esper_comm_wait_d -> esper_lanczos_ortho_d on the gathered vector; alpha_beta_d is the [max_steps, 2] array, row j-1
+ * receives step j.  The host paces the iteration once per convergence test instead of once per step. */
+int esper_lanczos_fused_steps_d(esper_ctx* ctx, int nrows, int n, int row0, double* V_d, double* alpha_beta_d, int j0, int n_steps, int step0);
 /* Replicated Lanczos state, vectors owned by the caller on the device: V_d is [max_steps+2, n].
  * start: V_d[0] = sqrt(degree)/|.| (locked), V_d[1] = start vector.  ortho (step j >= 1, w_d = gathered
  * Ms V_d[j]): Gram-Schmidt twice against V_d[0..j], alpha_beta_d = {alpha_j, beta_j}, V_d[j+1] = w/beta_j. */

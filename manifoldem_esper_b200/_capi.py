@@ -87,6 +87,7 @@ SIGNATURES = {
     'esper_symv_allgather_d': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     'esper_comm_wait_d': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     'esper_comm_status': (C.c_int, [C.c_void_p, C.POINTER(C.c_uint)]),
+    'esper_lanczos_fused_steps_d': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     'esper_tau_snr_stack': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_ulonglong,
                                       C.c_void_p, C.c_void_p]),
     'esper_download_images': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
@@ -443,6 +444,11 @@ class Context:
         st = C.c_uint(0)
         self._check(self._lib.esper_comm_status(self._h, C.byref(st)))
         return int(st.value)
+
+    def lanczos_fused_steps_d(self, nrows, n, row0, V_ptr, ab_ptr, j0, n_steps, step0):
+        """n_steps Lanczos steps (fused SYMV + packet gather + orthogonalisation) enqueued by one host call."""
+        self._check(self._lib.esper_lanczos_fused_steps_d(self._h, int(nrows), int(n), int(row0), C.c_void_p(V_ptr), C.c_void_p(ab_ptr),
+                                                          int(j0), int(n_steps), int(step0)))
 
     def lanczos_start_d(self, n, degree_all, V_ptr):
         degree_all = _as(degree_all, np.float64).reshape(-1)

@@ -542,6 +542,23 @@ int esper_comm_wait_d(esper_ctx* c, int step, int n, double** w_full_d) {
     return run_comm_wait(c, step, n, w_full_d);
 }
 
+int esper_lanczos_fused_steps_d(esper_ctx* c, int nrows, int n, int row0, double* V_d, double* ab_d, int j0, int n_steps, int step0) {
+    ESPER_ENTER(c);
+    if (!V_d || !ab_d || nrows < 1 || n < 2 || j0 < 1 || n_steps < 1 || step0 < 1 || !c->markov.p)
+        return fail(c, ESPER_E_ARG, "lanczos_fused_steps_d: bad argument or no resident Ms block");
+    for (int i = 0; i < n_steps; ++i) {
+        const int j = j0 + i;
+        int rc = run_symv_allgather(c, nrows, n, row0, V_d + (size_t)j * n, step0 + i);
+        if (rc) return rc;
+        double* w = nullptr;
+        rc = run_comm_wait(c, step0 + i, n, &w);
+        if (rc) return rc;
+        rc = run_lanczos_ortho(c, n, j, V_d, w, ab_d + 2 * (size_t)(j - 1));
+        if (rc) return rc;
+    }
+    return ESPER_OK;
+}
+
 int esper_comm_status(esper_ctx* c, unsigned int* status) {
     ESPER_ENTER(c);
     if (!status) return fail(c, ESPER_E_ARG, "comm_status: status is NULL");

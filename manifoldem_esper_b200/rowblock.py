@@ -153,6 +153,13 @@ class CudaBackend:
         self.ctx.symv_allgather_d(self.nrows, self.n, self.row0, self.V[j].data_ptr(), step)
         self._w_ptr = self.ctx.comm_wait_d(step, self.n)
 
+    def fused_steps(self, j0, n_steps):
+        """Steps j0 .. j0 + n_steps - 1 of the fused exchange enqueued by ONE library call (esper_lanczos_fused_steps_d): the host
+        paces the iteration once per convergence test, not once per step."""
+        step0 = self._step + 1
+        self._step += n_steps                             # the same sequence of tags on every rank
+        self.ctx.lanczos_fused_steps_d(self.nrows, self.n, self.row0, self.V.data_ptr(), self.ab.data_ptr(), j0, n_steps, step0)
+
     def ortho(self, j):
         w_ptr = self._w_ptr if self.fused else self.w_full.data_ptr()
         self.ctx.lanczos_ortho_d(self.n, j, self.V.data_ptr(), w_ptr, self.ab[j - 1].data_ptr())
@@ -256,13 +263,19 @@ def embed_oversized(backend, comm, n, k=16, eps=None, a0=None, tol=0.0, max_step
     next_check = min(max_steps, max(3 * (kw + 2) + 8, 32))
     while not converged and steps < max_steps:
         j = steps + 1
-        if getattr(backend, 'fused', False):
+        if getattr(backend, 'fused', False) and hasattr(backend, 'fused_steps'):
+            nb = max(1, min(next_check, max_steps) - steps)       # all steps up to the next convergence test in one library call
+            backend.fused_steps(j, nb)
+            steps += nb
+        elif getattr(backend, 'fused', False):
             backend.symv_allgather(j)                             # SYMV writing wire-format packets + the pull
+            backend.ortho(j)
+            steps += 1
         else:
             backend.symv(j)                                       # w_local = Ms[rows, :] q_j
             comm.allgather_vec(backend.w_full, backend.w_local)   # the per-step collective
-        backend.ortho(j)                                          # replicated, deterministic
-        steps += 1
+            backend.ortho(j)                                      # replicated, deterministic
+            steps += 1
         if steps >= next_check or steps == max_steps:
             alpha, beta = backend.read_ab(steps)
             getattr(backend, 'comm_check', lambda: None)()
