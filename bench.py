@@ -156,15 +156,23 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Statistics over the samples that arrived inside [t_begin, t_end + 0.1 s] (the timed region); the sampler is started
+        earlier (nvidia-smi needs ~0.1 s to deliver its first line), and when a short timed region caught no sample the
+        samples of the serial pass directly before it are used and the fact is noted."""
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        inside = [ln for (t, ln) in self.lines if t_begin is None or (t_begin <= t <= (t_end or t) + 0.1)]
+        window = 'timed region'
+        if not inside:
+            inside, window = [ln for (_, ln) in self.lines], 'serial pass + timed region (no sample arrived inside the short timed region)'
+        self.window = window
+        for ln in inside:
             f = [x.strip() for x in ln.split(',')]
             if len(f) < 9:
                 continue
@@ -176,7 +184,7 @@ class ClockSampler:
                 if v.lower().startswith('active'):
                     reasons.add(name)
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm), 'window': window}
 
 
 NATIVE_FIT = True      # stage 2b through esper_tanh_fit (MINPACK lmdif restated in C, no interpreter lock); --scipy-fit: curve_fit
@@ -362,6 +370,9 @@ def run_ours(args):
         embed_step(ctxs[w % NF], GB, coef, a0, N_IMG, P)
     pipelined(NF, False)
     # serial profiled pass (per-kernel CUDA-event durations; single stream, nothing overlapping)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                        # nvidia-smi needs ~0.1 s for its first line: started ahead of the timed region
     for c in ctxs:
         c.set_profiling(True); c.reset_profiling()
     barrier()
@@ -385,13 +396,12 @@ def run_ours(args):
     # the timed region: K steps, two in flight
     iters_used.clear()
     launches0 = sum(c.launch_count() for c in ctxs)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     for c in ctxs:
         c.set_profiling(2); c.reset_profiling()          # CUDA events around the Gram launches of the timed region only
+    t_begin = time.time()
     ms = pipelined(args.steps, False)
-    clocks = sampler.stop() if rank == 0 else None
+    t_end = time.time()
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     gram_live = [c.kernel_ms('gram') for c in ctxs]
     gram_live_ms = sum(a for a, _ in gram_live) / max(sum(b_ for _, b_ in gram_live), 1)
     for c in ctxs:

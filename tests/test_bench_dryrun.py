@@ -128,7 +128,7 @@ def test_bench_gpu_arm_dry_run(monkeypatch, flags):
     fake_cuda = types.SimpleNamespace(set_device=lambda d: None, Stream=_Stream, Event=_Evt, synchronize=lambda: None)
     monkeypatch.setattr(torch, 'cuda', fake_cuda)
     monkeypatch.setattr(bench, 'ClockSampler', lambda idx: types.SimpleNamespace(
-        start=lambda: None, stop=lambda: {'sm_mhz': 1965.0, 'sm_max_mhz': 1965.0, 'reasons': [], 'samples': 3}))
+        start=lambda: None, stop=lambda *a: {'sm_mhz': 1965.0, 'sm_max_mhz': 1965.0, 'reasons': [], 'samples': 3}))
     monkeypatch.setattr(bench, 'cpu_sample', lambda stack, **kw: (200.0, {'dist_loop_s': 176.0, 'sweep_s': 23.0, 'kernel_svd_s': 1.0,
                                                                          'vectorised_dist_s': 0.8, 'vectorised_total_s': 25.0}))
     for var in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE'):
