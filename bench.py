@@ -605,7 +605,7 @@ def main():
     ap.add_argument('--gram-tf32', action='store_true', help='3xTF32 operand planes for the Gram kernel (esper_gram_config 0) instead of the default 3xFP16')
     ap.add_argument('--scipy-fit', action='store_true', help='tanh fit with scipy.optimize.curve_fit (the reference\'s call) instead of esper_tanh_fit')
     ap.add_argument('--sweep-general', action='store_true', help='general sweep kernel (esper_sweep_config 0) instead of the default moment sweep')
-    ap.add_argument('--inflight', type=int, default=4, help='PDs in flight per GPU (host threads / ctxs / streams)')
+    ap.add_argument('--inflight', type=int, default=6, help='PDs in flight per GPU (host threads / ctxs / streams)')
     ap.add_argument('--no-extras', action='store_true', help='skip the post-measurement c5_rot (N=1) / c4_rowblock (N>1) runs')
     args = ap.parse_args()
     args.gram_f16, args.sweep_moments = not args.gram_tf32, not args.sweep_general

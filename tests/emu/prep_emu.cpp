@@ -1,6 +1,6 @@
 // prep_emu.cpp -- TEST INFRASTRUCTURE ONLY: runs the standardise-and-split kernels of csrc/k0_prep.cu (cut into
 // prep_kernels.inc by tests/test_emu.py, `__shared__` declarations rewritten to the per-block arena) on the CPU:
-// stats_split_kernel<HALF> (one CTA per image).
+// stats_split_kernel<HALF> (one CTA per image); the L2 cache-policy loads / stores are plain accesses here.
 //   prep_emu raw.bin n P ld standardize xbar.bin|- half scale cs hi.bin lo.bin stat.bin
 #define EMU_ARENA_SHARED
 #define EMU_NO_WARP_SUM
@@ -11,6 +11,10 @@ inline float tf32_rna(float x) {                 // cvt.rna.tf32.f32: nearest, t
 }
 
 namespace esper {
+inline float4 ld_keep(const float4* p) { return *p; }
+inline float4 ld_last_use(const float4* p) { return *p; }
+inline void st_stream(uint2* p, uint2 v) { *p = v; }
+inline void st_stream(float4* p, float4 v) { *p = v; }
 #include "devutil_body.inc"
 #include "prep_kernels.inc"
 }  // namespace esper
@@ -42,7 +46,7 @@ int main(int argc, char** argv) {
         if (half) emu_launch_cluster(n, 512, 1, 0, stats_split_kernel<true>, (const float*)raw.data(), n, P, ld, standardize, st.data(), xb, (int)center, scale, (void*)hi.data(), (void*)lo.data());
         else emu_launch_cluster(n, 512, 1, 0, stats_split_kernel<false>, (const float*)raw.data(), n, P, ld, standardize, st.data(), xb, (int)center, scale, (void*)hi.data(), (void*)lo.data());
     } else {
-        fprintf(stderr, "prep_emu: cs must be 0 (the cluster kernel was removed)\n");
+        fprintf(stderr, "prep_emu: cs must be 0\n");
         return 2;
     }
     write_bin(argv[10], hi.data(), hi.size());
