@@ -126,14 +126,16 @@ struct GridBarrier {
         if (threadIdx.x == 0) {
             ++epoch;
             int ab = 0;
-            // release-arrive / acquire-poll: bar.sync above orders the CTA's writes before the release
+            // release-arrive / relaxed poll + ONE acquire fence after the last poll (an acquire on every polling load costs a
+            // fence per poll: measured 2790 -> 2440 cycles per barrier, profiles/r2_handover_microbench.md); bar.sync above
+            // orders the CTA's writes before the release
             asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
             const unsigned int target = epoch * gridDim.x;
             const long long t0 = clock64();
             for (unsigned int polls = 1;; ++polls) {
                 unsigned int seen;
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
-                if (seen >= target) break;
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+                if (seen >= target) { asm volatile("fence.acq_rel.gpu;" ::: "memory"); break; }
                 if ((polls & 255u) == 0u) {                      // watchdog: another CTA gave up, or ~2 s without progress
                     if (*((volatile unsigned int*)(bar + 1)) != 0u) { ab = 1; break; }
                     if (clock64() - t0 > 4000000000LL) { atomicExch(bar + 1, 1u); ab = 1; break; }

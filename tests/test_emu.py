@@ -329,7 +329,8 @@ def lanczos_bin(tmp_path_factory):
     src = open(os.path.join(ROOT, 'manifoldem_esper_b200', 'csrc', 'k4_eigen.cu')).read()
     text = cut(src, '__device__ __forceinline__ double ld_cg(const double* p)', '// ------------------------------------------------------------------------------------------------\n// Small-m variant (the whole Lanczos vector fits in shared memory): ONE grid barrier per step.')
     text = text.replace('asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");', 'emu_red_release_add(bar);')
-    text = text.replace('asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");', 'seen = emu_ld_acquire(bar);')
+    text = text.replace('asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");', 'seen = emu_ld_acquire(bar);')
+    text = text.replace('asm volatile("fence.acq_rel.gpu;" ::: "memory");', '__atomic_thread_fence(__ATOMIC_SEQ_CST);')
     assert 'asm' not in text and 'lanczos_resident_kernel' in text and 'lanczos_steps_kernel' in text
     text = scalar_shared(arena_shared(text))
     assert '__shared__' not in text

@@ -513,6 +513,53 @@ __global__ void __launch_bounds__(512, 1) barrier_kernel(unsigned* bar, int iter
     if (tid == 0) out[b] = clock64() - t0;
 }
 
+
+// two-level grid barrier: groups of GS CTAs arrive on their own counter (one 128-byte line each); the last arriver of a group
+// arrives on the top counter; everybody polls the top counter.  poll_kind 0: ld.acquire polling, 1: ld.relaxed polling + one fence
+__global__ void __launch_bounds__(512, 1) barrier2_kernel(unsigned* bar, int GS, int poll_kind, int iters, long long* out) {
+    const int b = blockIdx.x, nb = gridDim.x, tid = threadIdx.x;
+    const int g = b / GS, ng = (nb + GS - 1) / GS, gsize = min(GS, nb - g * GS);
+    unsigned* gcnt = bar + 64 + 32 * g;
+    long long t0 = 0;
+    for (int it = 1; it <= iters; ++it) {
+        if (it == 2) t0 = clock64();
+        __syncthreads();
+        if (tid == 0) {
+            unsigned old;
+            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(gcnt) : "memory");
+            if (old + 1 == (unsigned)it * gsize) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+            unsigned seen;
+            const long long tw_ = clock64();
+            if (poll_kind == 0) {
+                do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory"); SPIN_GUARD(tw_) } while (seen < (unsigned)it * ng);
+            } else {
+                do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory"); SPIN_GUARD(tw_) } while (seen < (unsigned)it * ng);
+                __threadfence();
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) out[b] = clock64() - t0;
+}
+// flat barrier with relaxed polling + fence
+__global__ void __launch_bounds__(512, 1) barrier_relaxed_kernel(unsigned* bar, int iters, long long* out) {
+    const int b = blockIdx.x, nb = gridDim.x, tid = threadIdx.x;
+    long long t0 = 0;
+    for (int it = 1; it <= iters; ++it) {
+        if (it == 2) t0 = clock64();
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+            unsigned seen;
+            const long long tw_ = clock64();
+            do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory"); SPIN_GUARD(tw_) } while (seen < (unsigned)it * nb);
+            __threadfence();
+        }
+        __syncthreads();
+    }
+    if (tid == 0) out[b] = clock64() - t0;
+}
+
 template <class K, class... A> static void coop(K kern, int grid, int threads, A... args) {
     void* argv[] = {(void*)&args...};
     unsigned z = 0; CK(cudaMemcpyToSymbol(g_timeout, &z, 4));
@@ -529,7 +576,7 @@ int main() {
     const int nsm = prop.multiProcessorCount;
     printf("device %s, %d SMs\n", prop.name, nsm);
     uint4* buf; long long* out; double* sink; unsigned* bar;
-    CK(cudaMalloc(&buf, 64 << 20)); CK(cudaMalloc(&out, 8 * 1024)); CK(cudaMalloc(&sink, 64)); CK(cudaMalloc(&bar, 64));
+    CK(cudaMalloc(&buf, 64 << 20)); CK(cudaMalloc(&out, 8 * 1024)); CK(cudaMalloc(&sink, 64)); CK(cudaMalloc(&bar, 8192));
     std::vector<long long> h(1024);
     const int iters = 1000;
     const char* names[4] = {"st.volatile/ld.volatile", "st.relaxed.gpu/ld.relaxed.gpu", "st.release.gpu/ld.acquire.gpu", "st.cg/ld.cg"};
@@ -658,6 +705,21 @@ int main() {
             printf("skeleton D: %d workers, %d aggregators, %3d slots, 8 replicas: %7.0f cycles per step (reduce+bcast %6.0f, allgather %6.0f), errors %u\n",
                    nW, nA, S, (double)mx / 499.0, (double)m1 / 500.0, (double)m3 / 500.0, he);
         }
+    }
+
+    {
+        for (int GS : {4, 8, 12, 16, 24, 37}) for (int pk = 0; pk < 2; ++pk) {
+            CK(cudaMemset(bar, 0, 8192));
+            coop(barrier2_kernel, nsm, 512, bar, GS, pk, 1000, out);
+            CK(cudaMemcpy(h.data(), out, 8 * nsm, cudaMemcpyDeviceToHost));
+            long long mx = 0; for (int i = 0; i < nsm; ++i) mx = h[i] > mx ? h[i] : mx;
+            printf("two-level barrier, groups of %2d, %s polling, %d CTAs: %7.0f cycles per barrier\n", GS, pk ? "relaxed+fence" : "acquire", nsm, (double)mx / 999.0);
+        }
+        CK(cudaMemset(bar, 0, 8192));
+        coop(barrier_relaxed_kernel, nsm, 512, bar, 1000, out);
+        CK(cudaMemcpy(h.data(), out, 8 * nsm, cudaMemcpyDeviceToHost));
+        long long mx = 0; for (int i = 0; i < nsm; ++i) mx = h[i] > mx ? h[i] : mx;
+        printf("flat barrier, relaxed polling + fence, %d CTAs: %7.0f cycles per barrier\n", nsm, (double)mx / 999.0);
     }
     return 0;
 }
