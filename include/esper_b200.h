@@ -142,7 +142,10 @@ int esper_sweep_info(esper_ctx* ctx, int* last_path, int* bins);
  * (Ms = D^-1/2 A D^-1/2, i.e. alpha = 0) and :166-169 (svd; saves s^2 and U).
  * esper_markov exposes the intermediate for tests: degree [m] and Ms [m, m] (either may be NULL). */
 int esper_markov(esper_ctx* ctx, const double* D, int m, double eps, double* degree, double* Ms);
-/* Leading k eigenpairs of Ms by deflated Lanczos with full reorthogonalisation.
+/* Leading k eigenpairs of Ms by deflated Lanczos with full reorthogonalisation, 1 <= k <= m.  k <= 64: the iteration stops when
+ * the k pairs have converged.  k > 64, up to k = m (the reference's full U): Lanczos is run to exhaustion (m - 1 steps), the host
+ * diagonalises the tridiagonal matrix by implicit QL recording its plane rotations, the device applies them to the rows of the
+ * basis (csrc/k4_full.cu; 0.4 s at m = 2000); ESPER_E_NOCONV when fewer than k pairs exist (duplicated images: rank-deficient Ms).
  *   val: [k]   = lambda^2, descending (what the reference saves as PD_%s_val.npy)
  *   vec: [m,k] row-major; column 0 = sqrt(degree)/|sqrt(degree)| (steady state), unit columns,
  *              sign fixed so that the entry of largest magnitude is positive
@@ -269,6 +272,10 @@ int esper_lanczos_start_d(esper_ctx* ctx, int n, const double* degree_all, doubl
 int esper_lanczos_ortho_d(esper_ctx* ctx, int n, int j, double* V_d, double* w_d, double* alpha_beta_d);
 /* Host only: Ritz values/vectors of T = tridiag(beta, alpha, beta) (steps x steps), convergence of the leading
  * k-1 pairs to relative residual tol; theta [k-1] (may be NULL), S [steps, k-1] (may be NULL). */
+/* Host only: ALL eigenpairs of T = tridiag(beta, alpha, beta) of order n (implicit QL with recorded plane rotations, the host
+ * half of the full-spectrum path of esper_dmap_embed for k > 64): theta [n] descending, Z [n, n] row-major, eigenvectors in
+ * the columns.  beta[n-1] is ignored. */
+int esper_tridiag_eigen_all(const double* alpha, const double* beta, int n, double* theta, double* Z);
 int esper_tridiag_ritz(const double* alpha, const double* beta, int steps, int k, double tol, int* converged,
                        double* theta, double* S);
 /* vec [n, k] = [V_d[0], V_d[1..steps] S], unit columns, sign fixed (same convention as esper_dmap_embed). */

@@ -69,6 +69,7 @@ SIGNATURES = {
     'esper_symv_rows_d': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     'esper_lanczos_start_d': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'esper_lanczos_ortho_d': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'esper_tridiag_eigen_all': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'esper_tridiag_ritz': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, _i32p, C.c_void_p, C.c_void_p]),
     'esper_ritz_vectors_d': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     'esper_nd_rotation': (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
@@ -626,6 +627,20 @@ def tanh_fit(x, y, a0):
     if rc != ESPER_OK:
         raise ValueError('tanh_fit: array must not contain infs or NaNs (and needs at least 4 points)')
     return popt, rn.value, r2.value, info.value, nfev.value
+
+
+def tridiag_eigen_all(alpha, beta):
+    """Host only: (theta[n] descending, Z[n, n]) = all eigenpairs of T = tridiag(beta[:-1], alpha, beta[:-1]) (esper_tridiag_eigen_all)."""
+    lib = load_library()
+    alpha, beta = _as(alpha, np.float64).reshape(-1), _as(beta, np.float64).reshape(-1)
+    n = alpha.shape[0]
+    if beta.shape[0] < n:
+        beta = np.concatenate([beta, np.zeros(n - beta.shape[0])])
+    theta, Z = np.empty(n), np.empty((n, n))
+    rc = lib.esper_tridiag_eigen_all(_ptr(alpha), _ptr(beta), n, _ptr(theta), _ptr(Z))
+    if rc != ESPER_OK:
+        raise EsperError('tridiag_eigen_all: QL iteration did not converge')
+    return theta, Z
 
 
 def nd_rotation(n, theta):

@@ -176,6 +176,7 @@ int esper_gram_info(esper_ctx* c, int* last_operands) {
 
 int esper_dist_rms(esper_ctx* c, const float* imgs, int n, int P, unsigned flags, double* D) {
     ESPER_ENTER(c);
+    NvtxScope nvtx_("esper_dist_rms");
     if (n < 1 || P < 1) return fail(c, ESPER_E_ARG, "dist_rms: need n >= 1 and P >= 1 (got n=%d, P=%d)", n, P);
     if (imgs) {
         int rc = esper_upload_images(c, imgs, n, P);
@@ -228,6 +229,7 @@ static int need_dist(esper_ctx* c, const double* D, int m, const char* who) {
 // ---- stage 2 -----------------------------------------------------------------------------------
 int esper_eps_sweep(esper_ctx* c, const double* D, int m, const double* coef, int n_eps, double thr, double* logSum) {
     ESPER_ENTER(c);
+    NvtxScope nvtx_("esper_eps_sweep");
     if (!coef || !logSum || n_eps < 1) return fail(c, ESPER_E_ARG, "eps_sweep: need coef, logSum != NULL and n_eps >= 1");
     int rc = need_dist(c, D, m, "eps_sweep");
     if (rc) return rc;
@@ -277,6 +279,7 @@ int esper_dmap_config(esper_ctx* c, int mode) {
 int esper_dmap_embed(esper_ctx* c, const double* D, int m, double eps, int k, double tol, int max_iter,
                      double* val, double* vec, int* iters) {
     ESPER_ENTER(c);
+    NvtxScope nvtx_("esper_dmap_embed");
     if (!(eps > 0.0)) return fail(c, ESPER_E_ARG, "dmap_embed: eps must be > 0");
     if (k < 1 || k > m) return fail(c, ESPER_E_ARG, "dmap_embed: need 1 <= k <= m (k=%d, m=%d)", k, m);
     int rc = need_dist(c, D, m, "dmap_embed");
@@ -294,6 +297,7 @@ int esper_pd_embed_fused(esper_ctx* c, const float* imgs, int n, int P, unsigned
                          const double* coef, int n_eps, const double* a0, int k, double tol, int max_iter,
                          double* D, double* logSum, double* fit, double* val, double* vec, int* iters) {
     ESPER_ENTER(c);
+    NvtxScope nvtx_("esper_pd_embed_fused");
     if (!logEps || !coef || !a0 || !logSum || !fit || !val || !vec || n_eps < 4)
         return fail(c, ESPER_E_ARG, "pd_embed_fused: logEps, coef, a0, logSum, fit, val, vec must not be NULL and n_eps >= 4");
     if (k < 1 || k > n) return fail(c, ESPER_E_ARG, "pd_embed_fused: need 1 <= k <= n (k=%d, n=%d)", k, n);
@@ -577,6 +581,11 @@ int esper_lanczos_ortho_d(esper_ctx* c, int n, int j, double* V_d, double* w_d, 
     return run_lanczos_ortho(c, n, j, V_d, w_d, alpha_beta_d);
 }
 
+int esper_tridiag_eigen_all(const double* alpha, const double* beta, int n, double* theta, double* Z) {
+    if (!alpha || !beta || !theta || !Z || n < 1) return ESPER_E_ARG;
+    return tridiag_eigen_all_host(alpha, beta, n, theta, Z);
+}
+
 int esper_tridiag_ritz(const double* alpha, const double* beta, int steps, int k, double tol, int* converged,
                        double* theta, double* S) {
     if (!alpha || !beta || steps < 1 || k < 2 || !converged) return ESPER_E_ARG;
@@ -625,6 +634,7 @@ int esper_rot_sweep(esper_ctx* c, const double* Uinit, int n_pd, int m, int dim,
                     const int* n_sub, int max_sub, const int* rij, int n_rij, const double* theta_grid,
                     int n_theta, int bins, double lo, double hi, double* thetas_out, int* counts_out) {
     ESPER_ENTER(c);
+    NvtxScope nvtx_("esper_rot_sweep");
     if (!combo || !n_sub || (!rij && n_rij > 0) || !theta_grid || !thetas_out || n_pd < 1 || m < 1)
         return fail(c, ESPER_E_ARG, "rot_sweep: NULL argument or empty batch");
     if (!Uinit && (c->rot_n_pd != n_pd || c->rot_m != m || c->rot_dim != dim))

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -144,6 +145,12 @@ inline int fail(esper_ctx* c, int code, const char* fmt, ...) {
                                (size_t)(bytes), #buf);                                         \
     } while (0)
 
+// NVTX range around one stage of the path (tracing); visible in Nsight Systems / Compute timelines.
+struct NvtxScope {
+    explicit NvtxScope(const char* name) { nvtxRangePushA(name); }
+    ~NvtxScope() { nvtxRangePop(); }
+};
+
 // Scoped CUDA-event timer around one kernel launch (only when profiling is on).
 struct LaunchScope {
     esper_ctx* c;
@@ -197,6 +204,9 @@ int run_rot_eval(esper_ctx* c, const double* Uinit, int n_pd, int m, int dim, co
 int run_rot_sweep(esper_ctx* c, const double* Uinit, int n_pd, int m, int dim, const int* combo,
                   const int* n_sub, int max_sub, const int* rij, int n_rij, const double* theta_grid,
                   int n_theta, int bins, double lo, double hi, double* thetas_out, int* counts_out);
+int finish_full_spectrum(esper_ctx* c, int m, int k, int steps, const std::vector<double>& a, const std::vector<double>& b, double* V,
+                         double** U_out, std::vector<double>& theta_out);
+int tridiag_eigen_all_host(const double* alpha, const double* beta, int n, double* theta, double* Z);
 int run_lanczos_chain(esper_ctx* c, int m, int k, int guard, double tol, int max_iter, double* V, double* U_d);
 int chain_result(esper_ctx* c, int k, double* theta_out, int* iters_out);
 int run_symv_rows(esper_ctx* c, int rows, int m, const double* q_d, double* w_rows_d);

@@ -1130,7 +1130,7 @@ bool ritz_converged(const std::vector<double>& a, const std::vector<double>& b, 
 }
 
 static int lanczos_attempt(esper_ctx* c, int m, int k, double tol, int max_iter, bool use_pro, double* val_h, double* vec_h,
-                           int* iters_out, bool* suspicious, bool plain) {
+                           int* iters_out, bool* suspicious, bool plain, bool full = false) {
     using namespace lanczos;
     constexpr int KMAX = 64;
     const int kw = k - 1;                               // non-trivial pairs wanted
@@ -1230,7 +1230,7 @@ static int lanczos_attempt(esper_ctx* c, int m, int k, double tol, int max_iter,
     // Default schedule (esper_dmap_config 0): the barrier-free chain kernel with on-device convergence tests (k4_chain.cu).
     // It returns +1 for shapes it does not cover or when it did not converge within its shared-memory basis capacity;
     // the barrier kernels below then run the whole iteration from the same start vector.
-    if (!use_pro && kw > 0 && c->lanczos_mode == 0 && !getenv("ESPER_LANCZOS_NO_CHAIN")) {
+    if (!use_pro && kw > 0 && c->lanczos_mode == 0 && !full && !getenv("ESPER_LANCZOS_NO_CHAIN")) {
         ESPER_RESERVE(c, c->lan_small, sizeof(double) * ((size_t)m * k + (size_t)(max_iter + 8) * KMAX + 2 * KMAX * KMAX + 4096 + (size_t)ceil_div(m, 8) * 2));
         double* Uc = c->lan_small.as<double>();
         int rcc = run_lanczos_chain(c, m, k, guard, tol, max_iter, V, Uc);
@@ -1294,8 +1294,8 @@ static int lanczos_attempt(esper_ctx* c, int m, int k, double tol, int max_iter,
     };
     int rc = ESPER_OK;
     if (!converged) {
-        const int first = std::min(max_iter, std::max(3 * (kw + guard) + 8, 32));
-        const int batch = resident ? 24 : 16;                    // resident rows are reloaded per launch: longer batches
+        const int first = full ? std::min(max_iter, 64) : std::min(max_iter, std::max(3 * (kw + guard) + 8, 32));
+        const int batch = full ? 64 : (resident ? 24 : 16);      // resident rows are reloaded per launch: longer batches
         // Mode 2 (opt-in, not yet run on hardware): no speculative batch.  The batch launched while the host tests the
         // previous one runs to its end even when that test finds convergence (measured on the CPU for the benchmark
         // matrix: the test first passes at 161 steps, is seen at 169 and the GPU executes 185).  With several PDs in
@@ -1320,8 +1320,14 @@ static int lanczos_attempt(esper_ctx* c, int m, int k, double tol, int max_iter,
                 if (atoi(getenv("ESPER_DEBUG_LANCZOS")) > 1) for (int i = 0; i < steps_done; ++i) fprintf(stderr, "  %3d alpha=%.6e beta=%.6e\n", i, a[i], b[i]);
             }
             const double scale0 = std::max(fabs(a[0]), 1e-300);
-            const bool breakdown = !(b[steps_done - 1] > 1e-14 * scale0);
-            if (ritz_converged(a, b, steps_done, kw, guard, tol, theta, S) || breakdown || steps_done >= cap) { converged = true; break; }
+            bool breakdown = !(b[steps_done - 1] > 1e-14 * scale0);
+            if (full) {                                          // the Krylov space may end inside a batch: keep the steps before it
+                for (int i = 0; i < steps_done; ++i)
+                    if (!(b[i] > 1e-14 * scale0)) { steps_done = i + 1; breakdown = true; break; }
+                a.resize(steps_done); b.resize(steps_done);
+            }
+            // full spectrum: the iteration runs until the Krylov space is exhausted, no Ritz test in between
+            if (full ? (breakdown || steps_done >= cap) : (ritz_converged(a, b, steps_done, kw, guard, tol, theta, S) || breakdown || steps_done >= cap)) { converged = true; break; }
             if (!more) break;
             if (!ahead) { slot ^= 1; rc = issue_batch(std::min(8, max_iter - steps_issued), slot); if (rc) break; }
         }
@@ -1344,6 +1350,20 @@ static int lanczos_attempt(esper_ctx* c, int m, int k, double tol, int max_iter,
         }
     }
     if (!converged) { cudaStreamSynchronize(st); return fail(c, ESPER_E_NOCONV, "Lanczos did not converge in %d steps", steps); }
+    if (full) {
+        // every column on request (k4_full.cu): QL on the host records the rotations, the device applies them to the rows of V^T
+        ESPER_CUDA(c, cudaStreamSynchronize(st));
+        double* Uf = nullptr;
+        std::vector<double> th;
+        int rcf = finish_full_spectrum(c, m, k, steps, a, b, V, &Uf, th);
+        if (rcf) return rcf;
+        { LaunchScope ls(c, "lanczos"); fix_columns_kernel<<<k, 256, 0, st>>>(Uf, m, k); }
+        ESPER_CUDA(c, cudaGetLastError());
+        if (vec_h) ESPER_CUDA(c, cudaMemcpyAsync(vec_h, Uf, sizeof(double) * (size_t)m * k, cudaMemcpyDeviceToHost, st));
+        ESPER_CUDA(c, cudaStreamSynchronize(st));
+        if (val_h) { val_h[0] = 1.0; for (int i = 0; i + 1 < k; ++i) val_h[1 + i] = th[(size_t)i] * th[(size_t)i]; }
+        return ESPER_OK;
+    }
 
     // Ritz vectors U = [v0, V_1..V_steps S]
     ESPER_RESERVE(c, c->lan_small, sizeof(double) * ((size_t)m * k + (size_t)(max_iter + 8) * KMAX + 2 * KMAX * KMAX + 4096 + (size_t)ceil_div(m, 8) * 2));
@@ -1409,7 +1429,17 @@ int run_lanczos(esper_ctx* c, int m, int k, double tol, int max_iter, double* va
         if (k < 1 || k > m - 1 || k + 1 > KMAX) return fail(c, ESPER_E_ARG, "k=%d out of range (1..min(m-1,%d))", k, KMAX - 1);
         k += 1;
     }
-    if (k < 1 || k > m || k > KMAX) return fail(c, ESPER_E_ARG, "k=%d out of range (1..min(m,%d))", k, KMAX);
+    if (k < 1 || k > m) return fail(c, ESPER_E_ARG, "k=%d out of range (1..m = %d)", k, m);
+    if (k > KMAX) {
+        // more than KMAX columns (up to the reference's full U, k = m): Lanczos to exhaustion + QL on the tridiagonal matrix
+        if (m < 3) return fail(c, ESPER_E_ARG, "k=%d: the full-spectrum path needs m >= 3", k);
+        bool susp = false;
+        const int mode_saved = c->lanczos_mode;
+        if (c->lanczos_mode == 0) c->lanczos_mode = 3;               // barrier kernels (the chain kernel's basis capacity is ~440 vectors)
+        const int rcf = lanczos_attempt(c, m, k, tol > 0.0 ? tol : ESPER_DEFAULT_EIG_TOL, m - 1, false, val_h, vec_h, iters_out, &susp, false, true);
+        c->lanczos_mode = mode_saved;
+        return rcf;
+    }
     if (tol <= 0.0) tol = ESPER_DEFAULT_EIG_TOL;
     if (max_iter <= 0) max_iter = 1024;
     if (max_iter > m - 1) max_iter = m - 1;

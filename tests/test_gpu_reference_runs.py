@@ -254,3 +254,34 @@ def test_rowblock_two_ranks_vs_single_gpu():
     assert len(re.findall(r'fused == NCCL bit for bit at fixed eps: True', out)) == 2, out[-3000:]
     diffs = [float(x) for x in re.findall(r'val rel diff ([0-9.e+-]+)', out)]
     assert len(diffs) == 2 and max(diffs) < 1e-9, out[-3000:]
+
+
+def test_full_spectrum_on_request(ctx):
+    """k = m (the reference saves the full U of its SVD, DiffusionMaps.py:166-169): Lanczos to exhaustion + QL rotations applied on
+    the device.  All m eigenpairs of the N=400 golden matrix: eigenvalues against the oracle's SVD, U orthonormal, residuals, the
+    leading columns against the reference run."""
+    g = golden('stage23_medium.npz')
+    D, eps = g['D'], float(g['eps'])
+    m = D.shape[0]
+    val_r, U_r = O.dmap_embed(D, eps)
+    val, vec, iters = ctx.dmap_embed(D, eps, k=m)
+    assert val.shape == (m,) and vec.shape == (m, m) and iters == m - 1
+    lam, lam_r = np.sqrt(val), np.sqrt(val_r)
+    assert np.max(np.abs(lam - lam_r)) < 1e-12                                 # every eigenvalue, absolute (lambda_0 = 1)
+    assert np.max(np.abs(val[:32] - g['val'][:32]) / g['val'][:32]) < VAL_TOL
+    assert np.max(np.abs(vec.T @ vec - np.eye(m))) < 1e-10
+    _, _, Ms = O.markov_symmetric(D, eps)
+    assert np.max(np.abs(Ms @ vec - vec * lam[None, :])) < 1e-10
+    for i in range(5):
+        assert vec_err(vec[:, i], g['vec'][:, i]) < VEC_TOL, i
+    # an intermediate request (64 < k < m) takes the same path
+    val2, vec2, _ = ctx.dmap_embed(None, eps, k=100, m=m)
+    assert np.array_equal(val2, val[:100]) and np.array_equal(vec2, vec[:, :100])
+    # duplicated images: the Krylov space ends early, fewer than m pairs exist -> the call says so
+    idx = np.repeat(np.arange(80), 2)
+    Dd = np.ascontiguousarray(D[np.ix_(idx, idx)])                             # 160 images, every one twice: rank(Ms) <= 80
+    with pytest.raises(_capi.EsperError):
+        ctx.dmap_embed(Dd, eps, k=160)
+    val3, vec3, it3 = ctx.dmap_embed(Dd, eps, k=70)                            # ... but the pairs that exist are available
+    val3r, _ = O.dmap_embed(Dd, eps)
+    assert it3 <= 100 and np.max(np.abs(np.sqrt(val3) - np.sqrt(val3r[:70]))) < 1e-12

@@ -388,3 +388,21 @@ def test_moment_sweep_statement_random_spreads_and_thresholds():
         assert np.array_equal(np.isfinite(L), fin) and (not fin.any() or np.max(np.abs(L[fin] - ref[fin])) < 1e-13)
         used += 1
     assert used >= 40
+
+
+def test_tridiag_eigen_all_matches_numpy(lib_built):
+    """esper_tridiag_eigen_all (host half of the full-spectrum path: implicit QL with recorded rotations) against numpy's eigh."""
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 3, 17, 160):
+        a, b = rng.uniform(0.0, 0.05, n), np.abs(rng.normal(0.006, 0.002, n))
+        T = np.diag(a) + np.diag(b[:n - 1], 1) + np.diag(b[:n - 1], -1)
+        w, v = np.linalg.eigh(T)
+        th, Z = _capi.tridiag_eigen_all(a, b)
+        assert np.max(np.abs(th - w[::-1])) < 1e-15 and np.all(np.diff(th) <= 0)
+        assert np.max(np.abs(Z.T @ Z - np.eye(n))) < 1e-13
+        assert np.max(np.abs(T @ Z - Z * th[None, :])) < 1e-15
+    # a matrix that splits (a zero off-diagonal element) and one with repeated eigenvalues
+    a, b = np.array([3.0, 1.0, 2.0, 2.0, 5.0]), np.array([0.5, 0.0, 0.0, 0.25, 0.0])
+    th, Z = _capi.tridiag_eigen_all(a, b)
+    T = np.diag(a) + np.diag(b[:4], 1) + np.diag(b[:4], -1)
+    assert np.allclose(th, np.linalg.eigvalsh(T)[::-1], atol=1e-14) and np.max(np.abs(T @ Z - Z * th[None, :])) < 1e-14
