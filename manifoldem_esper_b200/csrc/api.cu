@@ -72,7 +72,7 @@ void esper_destroy(esper_ctx* c) {
                       &c->pair_list, &c->sweep_part, &c->sweep_aux, &c->markov, &c->degree, &c->lan_V, &c->lan_w,
                       &c->lan_h, &c->lan_small, &c->rot_U, &c->rot_R, &c->rot_idx, &c->rot_out, &c->rot_H,
                       &c->rot_theta, &c->rot_aux, &c->prep_src, &c->prep_out,
-                      &c->ctf_par, &c->ctf_T, &c->ctf_fy, &c->ctf_C, &c->ctf_ab, &c->ctf_T12, &c->ctf_wiener, &c->pw_plan, &c->chain_ws};
+                      &c->ctf_par, &c->ctf_T, &c->ctf_fy, &c->ctf_C, &c->ctf_ab, &c->ctf_T12, &c->ctf_wiener, &c->pw_plan, &c->chain_ws, &c->chain_trace};
     run_comm_close(c);
     c->comm_buf.release();
     for (DevBuf* b : bufs) b->release();
@@ -139,6 +139,7 @@ long long esper_launch_count(esper_ctx* c) { return c ? c->launches : 0; }
 long long esper_stat(esper_ctx* c, const char* name) {
     if (!c || !name) return -1;
     if (!strcmp(name, "lanczos_fallbacks")) return c->lanczos_fallbacks;
+    if (!strcmp(name, "cluster_launches")) return c->cluster_launches;
     if (!strcmp(name, "launches")) return c->launches;
     return -1;
 }

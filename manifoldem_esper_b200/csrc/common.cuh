@@ -102,6 +102,8 @@ struct esper_ctx {
     esper::DevBuf pw_plan; int pw_P = -1, pw_L = 0, pw_nodes = 0, pw_levels = 0, pw_root = 0;   // numpy pairwise-sum tree (k0_prep.cu)
     esper::DevBuf lan_V, lan_w, lan_h, lan_small;              // Lanczos basis etc.
     esper::DevBuf chain_ws; esper::PinBuf pin_chain; long long chain_smem_set = 0;   // barrier-free schedule (k4_chain.cu)
+    esper::DevBuf chain_trace; int chain_trace_ctas = 0;      // diagnostic timeline of one step (ESPER_DEBUG_LANCZOS)
+    int cluster_cap_size = -1, cluster_cap = 0, cluster_launches = 0; long long cluster_smem = 0;   // its cluster variant: resident clusters of that size
     // stage-4 workspaces
     esper::DevBuf rot_U, rot_R, rot_idx, rot_out, rot_H, rot_theta, rot_aux;
     int rot_n_pd = 0, rot_m = 0, rot_dim = 0;                  // shape of the normalised manifolds resident in rot_U

@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include "devutil.cuh"
 #include <algorithm>
+#include <vector>
 
 namespace esper {
 namespace chain {
@@ -43,6 +44,13 @@ constexpr int CH_POINTS = 16;           // multisection points per eigenvalue an
 constexpr int CH_HWARP = 8;             // warps 0..7 may own coefficient slots (P2); warps 8..11 fetch the coefficients (P3)
 constexpr int CH_PK = 8;                // partial packets per lane and slot: workers <= 32 * CH_PK
 constexpr long long CH_TIMEOUT = 4000000000LL;     // ~2 s
+// cluster schedule (lanczos_cluster_kernel): thread-block clusters with distributed shared memory as the first exchange level
+constexpr int CL_MAXROWS = 17;          // rows of Ms per worker CTA (a B200 keeps 15 clusters of 8 resident: 118 workers at m = 2000)
+constexpr int CL_REGROWS = 7;           // of which in registers
+constexpr int CL_GPK = 4;               // packets per thread in flight in the gather
+constexpr int CL_SMROWS = CL_MAXROWS - CL_REGROWS;   // rows in shared memory
+constexpr int CL_LD = 2048;             // row stride in shared memory: fixed, so that the products need no address arithmetic
+constexpr int CL_MAXCLUSTERS = 32;      // clusters that take part in an exchange (one lane each)
 
 struct Ctl {
     unsigned int stop;                  // 0, or 0x80000000 | checker << 16 | n  (first passing check)
@@ -51,7 +59,7 @@ struct Ctl {
     unsigned int progress;              // steps completed (alpha/beta published)
     int status;                         // 1 converged, 2 not converged at max_steps
     int n_final, winner, steps_run;
-    long long prof[16];
+    long long prof[32];
 };
 
 struct Params {
@@ -73,10 +81,18 @@ struct Params {
     double* S_out;                      // [n_checkers][max_steps * kw]
     int s_stride;                       // doubles per checker in S_out
     int prof_on;
+    // cluster schedule only
+    int cl_size;                        // CTAs per cluster
+    int cl_count;                       // clusters that hold workers
+    int cl_group;                       // lanes per slot in the gather: smallest power of two >= cl_count
+    uint4* cbuf;                        // [slots + 1][cl_count] per-cluster partial coefficients
+    long long* trace;                   // diagnostic (ESPER_DEBUG_LANCZOS): [CTAs][16] globaltimer stamps of thread 0 in step trace_step
+    int trace_step;
 };
 
 // ---- packet and flag primitives (the CPU stand-in of tests/emu replaces exactly these) ----------------------------------
 #ifndef ESPER_CHAIN_EMU
+__constant__ unsigned int g_relax_ns = 0;      // experiment knob (ESPER_CLUSTER_RELAX_NS)
 __device__ __forceinline__ void st_ll(uint4* p, double v, unsigned int tag) {
     asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned int)__double2loint(v)), "r"(tag),
                  "r"((unsigned int)__double2hiint(v)), "r"(tag) : "memory");
@@ -93,6 +109,37 @@ __device__ __forceinline__ unsigned int cas_word(unsigned int* p, unsigned int c
 __device__ __forceinline__ void publish_fence() { __threadfence(); }
 __device__ __forceinline__ long long now() { return clock64(); }
 __device__ __forceinline__ void relax() { __nanosleep(40); }
+__device__ __forceinline__ void relax_short() { if (g_relax_ns) __nanosleep(g_relax_ns); }   // cluster kernel: the reload itself paces the poll
+// Distributed shared memory.  dsm_send stores v at the copy of `dst_local` in the shared memory of CTA `rank` of this cluster
+// and completes 8 transaction bytes on that CTA's copy of the mbarrier `bar_local` (st.async): the consumer waits on its own
+// mbarrier, the producer neither fences nor arrives.  An mbarrier is armed once per phase by ONE local thread (mbar_expect =
+// arrive + expected bytes); bytes that land before the arming only drive the transaction count negative.
+typedef unsigned long long Mbar;
+__device__ __forceinline__ unsigned int smem_addr(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ int cluster_rank() { unsigned int r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return (int)r; }
+__device__ __forceinline__ void mbar_init(Mbar* b) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect(Mbar* b, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(Mbar* b, unsigned int parity) {
+    unsigned int ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_addr(b)), "r"(parity) : "memory");
+    return ok != 0u;
+}
+__device__ __forceinline__ void dsm_send(double* dst_local, int rank, double v, Mbar* bar_local) {
+    unsigned int ra, rb;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_addr(dst_local)), "r"(rank));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(smem_addr(bar_local)), "r"(rank));
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(ra), "l"(__double_as_longlong(v)), "r"(rb) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ long long wall_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #endif
 
 // ---- begin chain kernel text (tests/test_emu.py cuts from here) ----
@@ -102,6 +149,19 @@ __device__ __forceinline__ bool wait_ll(const uint4* p, unsigned int tag, double
     const long long t0 = now();
     for (unsigned int polls = 1;; ++polls) {
         relax();
+        if (ld_ll(p, tag, v)) return true;
+        if ((polls & 63u) == 0u) {
+            if (ld_word(&ctl->abort) != 0u) return false;
+            if (now() - t0 > CH_TIMEOUT) { st_word(&ctl->abort, 1u); return false; }
+        }
+    }
+}
+
+__device__ __forceinline__ bool wait_ll_short(const uint4* p, unsigned int tag, double& v, Ctl* ctl) {
+    if (ld_ll(p, tag, v)) return true;
+    const long long t0 = now();
+    for (unsigned int polls = 1;; ++polls) {
+        relax_short();
         if (ld_ll(p, tag, v)) return true;
         if ((polls & 63u) == 0u) {
             if (ld_word(&ctl->abort) != 0u) return false;
@@ -514,11 +574,12 @@ __device__ void checker_main(const Params& p, double* smem, int c) {
             won = s_mode != 0;
             __syncthreads();
             if (!won) return;                                               // another checker stopped the iteration first
-            // the workers are leaving: now the eigenvalues down to the last ulp and the vectors from scratch
+            // The workers are leaving: now the eigenvalues down to the last ulp.  The vectors continue from the first solve with
+            // the stored factorisation (its shifts are within a few ulps of |T| of the final values, which is all inverse
+            // iteration asks of a shift): two more solves, clusters orthogonalised.
             tn = leading_eigenvalues(cs, n, want, true, true, 0);
-            ritz_prepare(cs, n, cap, want, tn);
         }
-        for (int it = 0; it < 3; ++it) ritz_iterate(cs, n, cap, want, tn, true);
+        for (int it = 0; it < (mode == 1 ? 2 : 3); ++it) ritz_iterate(cs, n, cap, want, tn, true);
         const bool ok = ritz_residuals_ok(cs, n, cap, p.kw, want, p.tol, 1.0);
         {
             double* th = p.theta_out + (size_t)c * CH_MAXWANT;
@@ -777,6 +838,330 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_chain_kernel(Params p) 
 #undef CH_PROF
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Cluster schedule.  The flat kernel above pays 5 000 - 10 000 cycles for every exchange 143 CTAs take part in
+// (profiles/r2_handover_microbench.md).  Here the CTAs form thread-block clusters of S (8) and every exchange has two
+// levels: distributed shared memory inside the cluster (st.async: the store itself completes bytes on the consumer's
+// mbarrier, ~250 cycles per hop), flag-carrying packets through L2 between the cl_count (16) clusters only.
+//   A1  thread s: partial coefficient of the owned rows  -> DSMEM of the CTA (rank s mod W) that owns slot s in this cluster
+//   A2  owner: adds the W partials in rank order          -> packet cbuf[s][cluster]
+//   A3  owner: reads the packets of ALL clusters for its slots (one lane per cluster), adds them in a fixed shuffle tree
+//       (every cluster computes the same bits)            -> DSMEM s_h[s] of the W CTAs of the cluster
+//   Q   new vector: own rows -> DSMEM of the W CTAs and packets qbuf; rank r reads the r-th share of the rows of the OTHER
+//       clusters from the packets and forwards them       -> DSMEM s_vec of the W CTAs
+// Slot j + 2 of the coefficient exchange carries the stop word (CTA 0 contributes it, everybody else 0).
+// A buffer that peers write (s_part, s_h, s_vec) cannot be overwritten early: whatever a peer sends for the next phase
+// depends on a total that needs this CTA's contribution to the next phase, which follows its last read in program order.
+// ---------------------------------------------------------------------------------------------------------------------
+// Dynamic shared memory of a worker of the cluster kernel, in doubles: coefficients | partials | vector | rows of Ms | basis rows.
+__host__ __device__ inline int cl_round16(int x) { return (x + 15) & ~15; }
+__host__ __device__ inline size_t cluster_worker_doubles(int chunk, int cap) {
+    (void)chunk;                                                             // the basis always has CL_MAXROWS (zero-padded) rows
+    return (size_t)cl_round16(cap + 8) + (size_t)cl_round16(cap + 24) + (size_t)CL_LD * (1 + CL_SMROWS) + (size_t)CL_MAXROWS * cap;
+}
+
+__device__ __forceinline__ bool wait_mbar(Mbar* bar, unsigned int parity, Ctl* ctl) {
+    if (mbar_test(bar, parity)) return true;
+    const long long t0 = now();
+    for (unsigned int polls = 1;; ++polls) {
+        if (mbar_test(bar, parity)) return true;
+        if ((polls & 255u) == 0u) {
+            if (ld_word(&ctl->abort) != 0u) return false;
+            if (now() - t0 > CH_TIMEOUT) { st_word(&ctl->abort, 1u); return false; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 1) lanczos_cluster_kernel(Params p) {
+    extern __shared__ __align__(128) double ch_smem[];
+    __shared__ Mbar s_bar[4];                                                // 0 partial coefficients | 1 coefficients | 2 vector
+    __shared__ double s_red[CH_WARPS * CL_MAXROWS];
+    __shared__ double s_w[CL_MAXROWS + 1];
+    __shared__ double s_upd[CL_MAXROWS + 1];
+    __shared__ double s_sc[4];
+    __shared__ long long s_prof[32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.x;
+    const int S = p.cl_size, C = p.cl_count, G = p.cl_group;
+    const int rank = cluster_rank(), cid = b / S;
+    Ctl* ctl = p.ctl;
+    if (p.trace && b == 0 && tid == 0) p.trace[150 * 16] = wall_ns();
+    if (tid == 0) { mbar_init(&s_bar[0]); mbar_init(&s_bar[1]); mbar_init(&s_bar[2]); mbar_init_fence(); }
+    __syncthreads();
+    cluster_sync_all();
+    if (b >= p.n_workers) {
+        if (b - p.n_workers < p.n_checkers) checker_main(p, ch_smem, b - p.n_workers);
+        if (p.trace && tid == 0 && b - p.n_workers < p.n_checkers) p.trace[150 * 16 + 4 + (b - p.n_workers)] = wall_ns();
+        cluster_sync_all();
+        return;
+    }
+    const int W = min(S, p.n_workers - cid * S);                             // workers in this cluster
+    const int m = p.m, cap = p.vs_cap;
+    const int row0 = b * p.chunk, n_own = min(p.chunk, m - row0);            // 1 .. CL_MAXROWS
+    const int n_sm = max(0, n_own - CL_REGROWS);
+    const int crow0 = cid * S * p.chunk, crow1 = min(m, crow0 + S * p.chunk);   // rows owned inside this cluster
+    const int per = (m + W - 1) / W, f_lo = rank * per, f_hi = min(m, f_lo + per);   // share of the vector this CTA forwards
+    // Rows and vector are padded with zeros to CL_SMROWS x CL_LD, the basis to CL_MAXROWS rows: no bounds inside the step.
+    double* s_h = ch_smem;                                                   // [cap + 8]   coefficients of the step   } written by the peers:
+    double* s_part = s_h + cl_round16(cap + 8);                              // [cap + 24]  [owned slot][source rank]  } same offsets in
+    double* s_vec = s_part + cl_round16(cap + 24);                           // [CL_LD]     q_j                        } every CTA
+    double* s_rows = s_vec + CL_LD;                                          // [CL_SMROWS][CL_LD]
+    double* Vs = s_rows + (size_t)CL_SMROWS * CL_LD;                         // [CL_MAXROWS][cap]
+    long long t_prof = now();
+    // profile of thread 0 of CTA 0, kept in shared memory during the solve (a global read-modify-write per probe would cost more than the phases)
+#define CL_PROF(slot) do { if (p.prof_on && b == 0 && tid == 0) { const long long t_ = now(); s_prof[slot] += t_ - t_prof; t_prof = t_; } } while (0)
+    if (tid < 32) s_prof[tid] = 0;
+#define CL_TRACE(k) do { if (p.trace && tid == 0 && j == p.trace_step) p.trace[b * 16 + (k)] = wall_ns(); } while (0)
+    if (tid <= CL_MAXROWS) { s_w[tid] = 0.0; s_upd[tid] = 0.0; }
+
+    for (int rr = 0; rr < CL_SMROWS; ++rr) {
+        const double* a = p.Ms + (size_t)(row0 + rr) * m;
+        for (int c = tid; c < CL_LD; c += CH_THREADS) s_rows[rr * CL_LD + c] = (rr < n_sm && c < m) ? __ldg(a + c) : 0.0;
+    }
+    double rrow[CL_REGROWS][4];
+#pragma unroll
+    for (int e = 0; e < CL_REGROWS; ++e)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = tid + CH_THREADS * u;
+            rrow[e][u] = (n_sm + e < n_own && c < m) ? __ldg(p.Ms + (size_t)(row0 + n_sm + e) * m + c) : 0.0;
+        }
+    for (int c = tid; c < CL_LD; c += CH_THREADS) s_vec[c] = c < m ? p.V[(size_t)m + c] : 0.0;
+    for (int i = tid; i < CL_MAXROWS * cap; i += CH_THREADS) Vs[i] = 0.0;
+    __syncthreads();
+    if (tid < 2 * n_own) { const int r = tid >> 1, i = tid & 1; Vs[(size_t)r * cap + i] = p.V[(size_t)i * m + row0 + r]; }
+    double sigma = 0.0, beta_prev = 0.0, alpha1 = 0.0;
+    unsigned int phA = 0u, phH = 0u, phQ = 0u;
+    __syncthreads();
+    CL_PROF(0);
+    if (p.trace && b == 0 && tid == 0) p.trace[150 * 16 + 1] = wall_ns();
+
+    int j = 1;
+    int end_reason = 0;                                                      // 1 stop word, 2 breakdown, 3 max_steps, 4 abort
+    for (; j <= p.max_steps; ++j) {
+        if (b == 0 && tid == CH_THREADS - 1) s_sc[1] = ld_word(&ctl->stop) != 0u ? 1.0 : 0.0;   // consumed after the barriers of S0
+        CL_TRACE(0);
+        // ---- S0: w = Ms q_j - sigma q_j - beta_{j-1} q_{j-1} on the owned rows ----
+        {
+            double acc[CL_MAXROWS];
+#pragma unroll
+            for (int q = 0; q < CL_MAXROWS; ++q) acc[q] = 0.0;
+            const double* rp = s_rows + tid;
+            const double* vp = s_vec + tid;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double qv = vp[CH_THREADS * u];
+                double t[CL_SMROWS];
+#pragma unroll
+                for (int q = 0; q < CL_SMROWS; ++q) t[q] = rp[q * CL_LD + CH_THREADS * u];
+#pragma unroll
+                for (int q = 0; q < CL_SMROWS; ++q) acc[q] = fma(t[q], qv, acc[q]);
+#pragma unroll
+                for (int e = 0; e < CL_REGROWS; ++e) acc[CL_SMROWS + e] = fma(rrow[e][u], qv, acc[CL_SMROWS + e]);
+            }
+            CL_PROF(19);
+            CL_TRACE(1);
+            const double t16 = wsum(acc[16]);
+            double (&acc16)[16] = reinterpret_cast<double (&)[16]>(acc);
+            const double t = multi_sum16(acc16, lane);
+            if ((lane & 1) == 0) s_red[warp * CL_MAXROWS + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = t;
+            if (lane == 0) s_red[warp * CL_MAXROWS + 16] = t16;
+            CL_PROF(20);
+            __syncthreads();
+            CL_PROF(21);
+            if (tid < n_own) {
+                const int slot = tid < n_sm ? tid : (CL_MAXROWS - CL_REGROWS) + (tid - n_sm);
+                double tot = 0.0, tot2 = 0.0;
+#pragma unroll
+                for (int w2 = 0; w2 < CH_WARPS; w2 += 2) { tot += s_red[w2 * CL_MAXROWS + slot]; tot2 += s_red[(w2 + 1) * CL_MAXROWS + slot]; }
+                tot += tot2;
+                const double qr = Vs[(size_t)tid * cap + j];
+                double x = fma(-sigma, qr, tot);
+                if (j >= 2) x = fma(-beta_prev, Vs[(size_t)tid * cap + j - 1], x);
+                s_w[tid] = x;
+            }
+            __syncthreads();
+        }
+        CL_PROF(1);
+
+        CL_TRACE(2);
+        double alpha_j = sigma, beta_j = 0.0;
+        bool leave = false;
+        for (int pass = 0; pass < 2; ++pass) {
+            const unsigned int tag = 2u * (unsigned int)j + (unsigned int)pass;
+            const int n_tot = j + 3;                                         // slot 0: |w|^2, slot 1 + i: V_i . w (i = 0..j), slot j + 2: stop word
+            const int n_mine = rank < n_tot ? (n_tot - rank + W - 1) / W : 0;   // slots rank, rank + W, ... are added up by this CTA
+            if (tid == CH_THREADS - 1) { mbar_expect(&s_bar[0], 8u * (unsigned int)(n_mine * W)); mbar_expect(&s_bar[1], 8u * (unsigned int)n_tot); }
+            // ---- A1: partial coefficients of the owned rows -> the owner of the slot in this cluster ----
+            if (tid < n_tot) {
+                const int s = tid;
+                double v = 0.0;
+                if (s == n_tot - 1) v = (b == 0) ? s_sc[1] : 0.0;
+                else {                                                       // rows beyond n_own hold zeros
+                    const double* vcol = s == 0 ? s_w : Vs + (s - 1);
+                    const int vstep = s == 0 ? 1 : cap;
+                    double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+#pragma unroll
+                    for (int r = 0; r + 2 < CL_MAXROWS; r += 3) {
+                        v0 = fma(vcol[r * vstep], s_w[r], v0);
+                        v1 = fma(vcol[(r + 1) * vstep], s_w[r + 1], v1);
+                        v2 = fma(vcol[(r + 2) * vstep], s_w[r + 2], v2);
+                    }
+#pragma unroll
+                    for (int r = CL_MAXROWS - CL_MAXROWS % 3; r < CL_MAXROWS; ++r) v0 = fma(vcol[r * vstep], s_w[r], v0);
+                    v = (v0 + v1) + v2;
+                }
+                const int idx = s / W, owner = s - idx * W;
+                dsm_send(&s_part[idx * W + rank], owner, v, &s_bar[0]);
+            }
+            if (pass == 0) CL_TRACE(3);
+            int bad = 0;
+            // ---- A2: cluster totals of the owned slots -> packets ----
+            if (!wait_mbar(&s_bar[0], phA, ctl)) bad = 1;
+            phA ^= 1u;
+            if (pass == 0) CL_PROF(16);
+            if (pass == 0) CL_TRACE(4);
+            if (tid < n_mine && !bad) {
+                double tot = s_part[tid * W];
+                for (int src = 1; src < W; ++src) tot += s_part[tid * W + src];
+                st_ll(p.cbuf + (size_t)(tid * W + rank) * C + cid, tot, tag);
+            }
+            // ---- A3: totals over all clusters (G lanes per slot, lane c reads cluster c), broadcast inside the cluster ----
+            if (pass == 0) CL_TRACE(5);
+            // every thread first has all its packets in flight (up to CL_GPK), then the totals are formed group by group
+            const int per_pass = CH_THREADS / G;
+            const int c = tid & (G - 1);
+            for (int i0 = 0; i0 < n_mine; i0 += per_pass * CL_GPK) {
+                double x[CL_GPK];
+                unsigned int pend = 0u;
+#pragma unroll
+                for (int q = 0; q < CL_GPK; ++q) { x[q] = 0.0; if (i0 + q * per_pass + tid / G < n_mine && c < C) pend |= 1u << q; }
+                const uint4* src = p.cbuf + (size_t)((i0 + tid / G) * W + rank) * C + c;
+                const size_t src_step = (size_t)per_pass * W * C;
+                const long long t0 = now();
+                for (unsigned int rounds = 1; pend != 0u; ++rounds) {
+                    const unsigned int cur = pend;
+#pragma unroll
+                    for (int q = 0; q < CL_GPK; ++q)
+                        if ((cur >> q) & 1u) { double v; if (ld_ll(src + q * src_step, tag, v)) { x[q] = v; pend &= ~(1u << q); } }
+                    if (pend != 0u) {
+                        relax_short();
+                        if ((rounds & 63u) == 0u && (ld_word(&ctl->abort) != 0u || now() - t0 > CH_TIMEOUT)) { st_word(&ctl->abort, 1u); bad = 1; break; }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < CL_GPK; ++q) {
+                    if (i0 + q * per_pass >= n_mine) break;                  // uniform in the CTA
+                    double v = x[q];
+                    for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    const int idx = i0 + q * per_pass + tid / G;
+                    if (idx < n_mine)
+                        for (int d = c; d < W; d += G) dsm_send(&s_h[idx * W + rank], d, v, &s_bar[1]);
+                }
+            }
+            if (pass == 0) CL_TRACE(6);
+            if (pass == 0) CL_PROF(17);
+            if (!wait_mbar(&s_bar[1], phH, ctl)) bad = 1;
+            phH ^= 1u;
+            if (pass == 0) CL_TRACE(7);
+            if (__syncthreads_or(bad)) { end_reason = 4; leave = true; break; }
+            if (s_h[n_tot - 1] != 0.0) { end_reason = 1; leave = true; break; }
+            CL_PROF(2 + pass * 4);
+            // update of the owned rows (warp r) and sum of squares of the coefficients (last warp)
+            {
+                const int task = tid >> 4, l16 = tid & 15;                   // 32 half-warps: rows 0 .. n_own - 1, the last one the squares
+                double a0 = 0.0, a1 = 0.0;
+                if (task < n_own) {
+                    const double* vr = Vs + (size_t)task * cap;
+                    int i = l16;
+                    for (; i + 16 <= j; i += 32) { a0 = fma(vr[i], s_h[1 + i], a0); a1 = fma(vr[i + 16], s_h[1 + i + 16], a1); }
+                    if (i <= j) a0 = fma(vr[i], s_h[1 + i], a0);
+                } else if (task == 31) {
+                    int i = l16;
+                    for (; i + 16 <= j; i += 32) { a0 = fma(s_h[1 + i], s_h[1 + i], a0); a1 = fma(s_h[1 + i + 16], s_h[1 + i + 16], a1); }
+                    if (i <= j) a0 = fma(s_h[1 + i], s_h[1 + i], a0);
+                }
+                double tot = a0 + a1;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+                if (l16 == 0) {
+                    if (task < n_own) s_upd[task] = s_w[task] - tot;
+                    else if (task == 31) s_sc[0] = tot;
+                }
+            }
+            if (pass == 0) CL_TRACE(8);
+            if (pass == 0) CL_PROF(22);
+            __syncthreads();
+            if (pass == 0) CL_PROF(23);
+            const double ww = s_h[0], after = ww - s_sc[0];
+            alpha_j += s_h[1 + j];
+            if (tid < n_own) s_w[tid] = s_upd[tid];
+            if (pass == 0 && after < 0.5 * ww) { __syncthreads(); continue; }   // DGKS: orthogonalise once more
+            beta_j = after > 0.0 ? sqrt(after) : 0.0;
+            break;
+        }
+        if (leave) break;
+        if (j == 1) alpha1 = alpha_j;
+        // ---- q_{j+1} on the owned rows -> Vs, global V, the CTAs of this cluster, packets for the other clusters ----
+        const bool breakdown = !(beta_j > 1e-14 * fmax(fabs(alpha1), 1e-300));
+        const bool last = breakdown || j == p.max_steps;                     // nobody waits for this vector: no sends to CTAs that leave
+        const double inv = beta_j > 0.0 ? 1.0 / beta_j : 0.0;
+        __syncthreads();
+        CL_TRACE(9);
+        if (tid == CH_THREADS - 1 && !last) mbar_expect(&s_bar[2], 8u * (unsigned int)m);
+        if (tid < n_own) {
+            const double x = s_w[tid] * inv;
+            Vs[(size_t)tid * cap + j + 1] = x;
+            p.V[(size_t)(j + 1) * m + row0 + tid] = x;
+            if (!last) st_ll(p.qbuf + row0 + tid, x, 2u * (unsigned int)j);
+        }
+        if (!last && tid < n_own * W) {
+            const int r = tid / W, d = tid - r * W;
+            dsm_send(&s_vec[row0 + r], d, s_w[r] * inv, &s_bar[2]);
+        }
+        if (b == 0 && tid == 32) {
+            p.alpha[j - 1] = alpha_j; p.beta[j - 1] = beta_j;
+            st_ll(p.abuf + 2 * (size_t)j, alpha_j, 1u);
+            st_ll(p.abuf + 2 * (size_t)j + 1, beta_j, 1u);
+            st_word(&ctl->progress, (unsigned int)j);                        // a hint: the checkers wait for the packets themselves
+        }
+        CL_TRACE(10);
+        CL_PROF(3);
+        if (breakdown) { end_reason = 2; ++j; break; }
+        if (j == p.max_steps) { end_reason = 3; ++j; break; }
+        // ---- Q: this CTA's share of the other clusters' rows, forwarded to the CTAs of this cluster ----
+        int bad = 0;
+        const unsigned int qtag = 2u * (unsigned int)j;
+        for (int c = f_lo + tid; c < f_hi; c += CH_THREADS) {
+            if (c >= crow0 && c < crow1) continue;
+            double x;
+            if (!wait_ll_short(p.qbuf + c, qtag, x, ctl)) { bad = 1; continue; }
+            for (int d = 0; d < W; ++d) dsm_send(&s_vec[c], d, x, &s_bar[2]);
+        }
+        CL_TRACE(11);
+        CL_PROF(18);
+        if (!wait_mbar(&s_bar[2], phQ, ctl)) bad = 1;
+        phQ ^= 1u;
+        CL_TRACE(12);
+        if (__syncthreads_or(bad)) { end_reason = 4; ++j; break; }
+        sigma = alpha_j; beta_prev = beta_j;
+        CL_PROF(4);
+    }
+    if (p.trace && b == 0 && tid == 0) p.trace[150 * 16 + 2] = wall_ns();
+    if (p.prof_on && b == 0 && tid == 0)
+        for (int i = 0; i < 8; ++i) { ctl->prof[i] += s_prof[i]; ctl->prof[16 + i] += s_prof[16 + i]; }
+    if (b == 0 && tid == 0) {
+        ctl->steps_run = j - 1;
+        if (end_reason == 2 || end_reason == 3) {
+            publish_fence();
+            st_word(&ctl->final_n, 0x80000000u | (end_reason == 2 ? 0x40000000u : 0u) | (unsigned int)(j - 1));
+        }
+    }
+    cluster_sync_all();                                                      // no CTA leaves while a peer may still store into it
+#undef CL_PROF
+#undef CL_TRACE
+}
+
 // U[r][1+i] = sum_l V_{1+l}[r] S[l][i] with the step count and S of the winning checker read on the device; U[r][0] = V_0[r].
 __global__ void __launch_bounds__(128) ritz_chain_kernel(const double* __restrict__ V, int m, const Ctl* __restrict__ ctl,
                                                          const double* __restrict__ S_base, int s_stride, int kw,
@@ -803,10 +1188,83 @@ __global__ void __launch_bounds__(128) ritz_chain_kernel(const double* __restric
 
 }  // namespace chain
 
+// Ritz vectors, normalised, largest-magnitude entry positive -- ritz_chain_kernel + fix_columns_kernel (k4_eigen.cu) in one launch:
+// block i forms column i of U = [V_0 | (V_1 .. V_n) S] for all rows (step count and S of the winning checker read on the device).
+__global__ void __launch_bounds__(1024) ritz_fix_chain_kernel(const double* __restrict__ V, int m, const chain::Ctl* __restrict__ ctl,
+                                                              const double* __restrict__ S_base, int s_stride, int kw,
+                                                              double* __restrict__ U, int k) {
+    __shared__ double s_col[chain::CH_THREADS + 8];
+    __shared__ double sh[32];
+    __shared__ double sb[32];
+    __shared__ int si[32];
+    __shared__ double s_scale;
+    const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int steps = ctl->n_final, win = ctl->winner;
+    const bool dead = (i > 0) && (win < 0 || steps < 1);
+    if (i > 0 && !dead) {
+        const double* S = S_base + (size_t)win * s_stride;
+        for (int l = tid; l < steps; l += 1024) s_col[l] = S[(size_t)l * kw + (i - 1)];
+    }
+    __syncthreads();
+    constexpr int RPT = 2;                                                   // rows per thread per sweep
+    double sq = 0.0, best = -1.0; int best_r = 0x7fffffff;
+    for (int r0 = 0; r0 < m; r0 += 1024 * RPT) {
+        double x[RPT];
+#pragma unroll
+        for (int u = 0; u < RPT; ++u) {
+            const int r = r0 + tid + 1024 * u;
+            x[u] = 0.0;
+            if (r >= m) continue;
+            if (i == 0) { x[u] = V[r]; continue; }
+            if (dead) continue;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            const double* v = V + (size_t)m + r;
+            int l = 0;
+            for (; l + 3 < steps; l += 4) {
+                a0 = fma(v[(size_t)l * m], s_col[l], a0);
+                a1 = fma(v[(size_t)(l + 1) * m], s_col[l + 1], a1);
+                a2 = fma(v[(size_t)(l + 2) * m], s_col[l + 2], a2);
+                a3 = fma(v[(size_t)(l + 3) * m], s_col[l + 3], a3);
+            }
+            for (; l < steps; ++l) a0 = fma(v[(size_t)l * m], s_col[l], a0);
+            x[u] = (a0 + a1) + (a2 + a3);
+        }
+#pragma unroll
+        for (int u = 0; u < RPT; ++u) {
+            const int r = r0 + tid + 1024 * u;
+            if (r >= m) continue;
+            U[(size_t)r * k + i] = x[u];
+            sq = fma(x[u], x[u], sq);
+            if (fabs(x[u]) > best) { best = fabs(x[u]); best_r = r; }
+        }
+    }
+    // arg-max of |x| (ties -> smallest row), then the scale
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int orr = __shfl_xor_sync(0xffffffffu, best_r, o);
+        if (ob > best || (ob == best && orr < best_r)) { best = ob; best_r = orr; }
+    }
+    if (lane == 0) { sb[warp] = best; si[warp] = best_r; }
+    sq = block_sum(sq, sh);                                                  // (barriers inside)
+    if (tid == 0) {
+        double bb = -1.0; int br = 0x7fffffff;
+        for (int t = 0; t < 32; ++t)
+            if (sb[t] > bb || (sb[t] == bb && si[t] < br)) { bb = sb[t]; br = si[t]; }
+        const double nrm = sqrt(sq);
+        double sc = nrm > 0.0 ? 1.0 / nrm : 0.0;
+        if (br < m && U[(size_t)br * k + i] < 0.0) sc = -sc;
+        s_scale = sc;
+    }
+    __syncthreads();
+    const double sc = s_scale;
+    for (int r = tid; r < m; r += 1024) U[(size_t)r * k + i] *= sc;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Host side.  Preconditions (checked by chain_plan): 32 <= m <= 2048, ceil(m / (SMs - 1)) <= 14, kw + guard <= 16.
-// V[0] (locked vector) and V[1] (start vector) are already on the device.  On success U_d [m, k] holds the unnormalised Ritz
-// vectors (column 0 = V[0]) and the result block is on its way to the host; the caller synchronises.
+// V[0] (locked vector) and V[1] (start vector) are already on the device.  On success U_d [m, k] holds the Ritz vectors (column 0 =
+// V[0]; unit columns, largest-magnitude entry positive) and the result block is on its way to the host; the caller synchronises.
 // Returns ESPER_OK, an error, or +1 = "not handled / not converged here: use the barrier kernels".
 // ---------------------------------------------------------------------------------------------------------------------
 struct ChainPlan {
@@ -840,6 +1298,66 @@ static ChainPlan chain_plan(esper_ctx* c, int m, int kw, int guard, int max_iter
     return pl;
 }
 
+// Plan of the cluster schedule: clusters of S CTAs, as many as the device keeps resident at once (cooperative launch: the CTAs
+// spin on each other), CL_MAXROWS rows per worker at most, at least one CTA left over for a checker.
+struct ClusterPlan {
+    bool ok = false;
+    int S = 0, total = 0, chunk = 0, n_workers = 0, n_checkers = 0, cl_count = 0, cl_group = 1, n_sm = 0, vs_cap = 0, max_steps = 0;
+    size_t smem = 0;
+};
+
+static ClusterPlan cluster_plan(int S, int n_clusters, int m, int kw, int guard, int max_iter, long long smem_limit) {
+    using namespace chain;
+    ClusterPlan pl;
+    pl.S = S; pl.total = S * n_clusters;
+    if (m < 32 || m > CH_MAXM || kw < 1 || kw + guard > CH_MAXWANT || pl.total < 2) return pl;
+    pl.chunk = ceil_div(m, pl.total - 1);
+    if (pl.chunk > CL_MAXROWS) return pl;
+    pl.n_workers = ceil_div(m, pl.chunk);
+    pl.n_checkers = std::min(pl.total - pl.n_workers, CH_MAXCHK);
+    if (pl.n_checkers < 1) return pl;
+    pl.cl_count = ceil_div(pl.n_workers, S);
+    if (pl.cl_count > CL_MAXCLUSTERS) return pl;
+    while (pl.cl_group < pl.cl_count) pl.cl_group *= 2;
+    pl.n_sm = std::max(0, pl.chunk - CL_REGROWS);
+    const int want = kw + guard;
+    int steps = std::min(max_iter, CH_THREADS - 3);                            // j + 3 slots of a step: one thread each
+    while (steps >= 32 && (sizeof(double) * cluster_worker_doubles(pl.chunk, steps + 2) > (size_t)smem_limit ||
+                           sizeof(double) * checker_doubles(want, steps + 2) > (size_t)smem_limit)) steps -= 2;
+    if (steps < std::min(max_iter, 96)) return pl;
+    pl.max_steps = steps;
+    pl.vs_cap = steps + 2;
+    pl.smem = std::max(sizeof(double) * cluster_worker_doubles(pl.chunk, pl.vs_cap), sizeof(double) * checker_doubles(want, steps + 2));
+    pl.ok = (long long)pl.smem <= smem_limit;
+    return pl;
+}
+
+// Clusters of the cluster kernel the device holds at once (0: clusters of this size cannot be launched); cached per ctx.
+static int cluster_capacity(esper_ctx* c, int S) {
+    using namespace chain;
+    if (c->cluster_cap_size == S) return c->cluster_cap;
+    int optin = 0, n = 0;
+    cudaFuncAttributes fa;
+    if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device) != cudaSuccess ||
+        cudaFuncGetAttributes(&fa, lanczos_cluster_kernel) != cudaSuccess ||
+        cudaFuncSetAttribute(lanczos_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes) != cudaSuccess) {
+        cudaGetLastError();
+        c->cluster_cap_size = S; c->cluster_cap = 0;
+        return 0;
+    }
+    c->cluster_smem = optin - (long long)fa.sharedSizeBytes;
+    if (S > 8 && cudaFuncSetAttribute(lanczos_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(S * 64); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = (size_t)c->cluster_smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, (void*)lanczos_cluster_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    c->cluster_cap_size = S; c->cluster_cap = n;
+    return n;
+}
+
 int run_lanczos_chain(esper_ctx* c, int m, int k, int guard, double tol, int max_iter, double* V, double* U_d) {
     using namespace chain;
     const int kw = k - 1;
@@ -852,18 +1370,37 @@ int run_lanczos_chain(esper_ctx* c, int m, int k, int guard, double tol, int max
         ESPER_CUDA(c, cudaFuncSetAttribute(lanczos_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
         c->chain_smem_set = optin - (long long)fa.sharedSizeBytes;
     }
+    // cluster schedule first (ESPER_CLUSTER_SIZE = 0 switches it off, 2 / 4 / 8 / 16 choose the cluster size; default 8)
+    ClusterPlan cp;
+    {
+        const char* e = getenv("ESPER_CLUSTER_SIZE");
+        const int S = e ? atoi(e) : 8;
+        if (S == 2 || S == 4 || S == 8 || S == 16) {
+            const int cap = cluster_capacity(c, S);
+            if (cap > 0) cp = cluster_plan(S, cap, m, kw, guard, max_iter, c->cluster_smem);
+            if (getenv("ESPER_DEBUG_LANCZOS"))
+                fprintf(stderr, "[chain] clusters of %d: %d resident -> plan %s: %d rows per CTA, %d workers in %d clusters, %d checkers, %d steps, %zu B of shared memory\n", S, cap,
+                        cp.ok ? "ok" : "rejected", cp.chunk, cp.n_workers, cp.cl_count, cp.n_checkers, cp.max_steps, cp.smem);
+        }
+    }
     const ChainPlan pl = chain_plan(c, m, kw, guard, max_iter, c->chain_smem_set);
-    if (!pl.ok) return 1;
-    int per_sm = 0;
-    ESPER_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lanczos_chain_kernel, CH_THREADS, pl.smem));
-    if (per_sm < 1) return 1;
+    if (!cp.ok && !pl.ok) return 1;
+    const bool cluster = cp.ok;
+    if (!cluster) {
+        int per_sm = 0;
+        ESPER_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lanczos_chain_kernel, CH_THREADS, pl.smem));
+        if (per_sm < 1) return 1;
+    }
+    const int max_steps = cluster ? cp.max_steps : pl.max_steps;
+    const int n_workers = cluster ? cp.n_workers : pl.n_workers;
 
     // workspace: packets | ctl | theta | S | alpha, beta
-    const int slots = pl.max_steps + 3;
-    const size_t n_p = (size_t)slots * pl.n_workers, n_h = (size_t)slots + 1, n_q = (size_t)m, n_a = 2 * ((size_t)pl.max_steps + 2);
+    const int slots = max_steps + 4;
+    const size_t n_p = cluster ? (size_t)slots * cp.cl_count : (size_t)slots * n_workers;      // cbuf or pbuf
+    const size_t n_h = (size_t)slots + 1, n_q = (size_t)m, n_a = 2 * ((size_t)max_steps + 2);
     const size_t pk_bytes = sizeof(uint4) * (n_p + n_h + n_q + n_a);
-    const int s_stride = pl.max_steps * kw;
-    const size_t bytes = pk_bytes + sizeof(Ctl) + 64 + sizeof(double) * ((size_t)CH_MAXCHK * CH_MAXWANT + (size_t)CH_MAXCHK * s_stride + 2 * ((size_t)pl.max_steps + 8));
+    const int s_stride = max_steps * kw;
+    const size_t bytes = pk_bytes + sizeof(Ctl) + 64 + sizeof(double) * ((size_t)CH_MAXCHK * CH_MAXWANT + (size_t)CH_MAXCHK * s_stride + 2 * ((size_t)max_steps + 8));
     ESPER_RESERVE(c, c->chain_ws, bytes);
     char* base = c->chain_ws.as<char>();
     uint4* pbuf = reinterpret_cast<uint4*>(base);
@@ -872,26 +1409,49 @@ int run_lanczos_chain(esper_ctx* c, int m, int k, int guard, double tol, int max
     double* theta_d = reinterpret_cast<double*>(base + pk_bytes + ((sizeof(Ctl) + 63) / 64) * 64);
     double* S_d = theta_d + (size_t)CH_MAXCHK * CH_MAXWANT;
     double* alpha_d = S_d + (size_t)CH_MAXCHK * s_stride;
-    double* beta_d = alpha_d + pl.max_steps + 4;
+    double* beta_d = alpha_d + max_steps + 4;
     // tags repeat from one solve to the next: the packet buffers and the control block start from zero every time
     ESPER_CUDA(c, cudaMemsetAsync(base, 0, pk_bytes + sizeof(Ctl), st));
 
     Params p;
     p.Ms = c->markov.as<double>(); p.m = m; p.V = V; p.alpha = alpha_d; p.beta = beta_d;
-    p.chunk = pl.chunk; p.n_workers = pl.n_workers; p.n_checkers = pl.n_checkers;
-    p.max_steps = pl.max_steps; p.vs_cap = pl.vs_cap;
+    p.chunk = cluster ? cp.chunk : pl.chunk; p.n_workers = n_workers; p.n_checkers = cluster ? cp.n_checkers : pl.n_checkers;
+    p.max_steps = max_steps; p.vs_cap = cluster ? cp.vs_cap : pl.vs_cap;
     p.kw = kw; p.guard = guard; p.cap_steps = m - 1; p.tol = tol;
-    p.first_check = std::min(pl.max_steps, std::max(3 * (kw + guard) + 8, 32));
+    p.first_check = std::min(max_steps, std::max(3 * (kw + guard) + 8, 32));
     p.pbuf = pbuf; p.hbuf = hbuf; p.qbuf = qbuf; p.abuf = abuf; p.ctl = ctl;
     p.theta_out = theta_d; p.S_out = S_d; p.s_stride = s_stride;
     p.prof_on = getenv("ESPER_DEBUG_LANCZOS") ? 1 : 0;
-    {
+    p.cl_size = cluster ? cp.S : 0; p.cl_count = cp.cl_count; p.cl_group = cp.cl_group; p.cbuf = pbuf;
+    p.trace = nullptr; p.trace_step = 0;
+    if (cluster && getenv("ESPER_CLUSTER_RELAX_NS")) { const unsigned int ns = (unsigned int)atoi(getenv("ESPER_CLUSTER_RELAX_NS")); cudaMemcpyToSymbolAsync(g_relax_ns, &ns, sizeof ns, 0, cudaMemcpyHostToDevice, st); }
+    if (cluster && p.prof_on) {
+        ESPER_RESERVE(c, c->chain_trace, sizeof(long long) * 16 * 160);
+        ESPER_CUDA(c, cudaMemsetAsync(c->chain_trace.p, 0, sizeof(long long) * 16 * 160, st));
+        p.trace = c->chain_trace.as<long long>();
+        p.trace_step = getenv("ESPER_TRACE_STEP") ? atoi(getenv("ESPER_TRACE_STEP")) : 100;
+        c->chain_trace_ctas = cp.n_workers;
+    }
+    if (cluster) {
+        LaunchScope ls(c, "lanczos");
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cp.total); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = cp.smem; cfg.stream = st;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cp.S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeCooperative;
+        at[1].val.cooperative = 1;
+        cfg.attrs = at; cfg.numAttrs = 2;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, lanczos_cluster_kernel, p);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(c, ESPER_E_CUDA, "cooperative cluster launch (%d x %d): %s", cp.S, cp.total / cp.S, cudaGetErrorString(e)); }
+        c->cluster_launches++;
+    } else {
         LaunchScope ls(c, "lanczos");
         void* args[] = {&p};
         cudaError_t e = cudaLaunchCooperativeKernel((void*)lanczos_chain_kernel, dim3(c->sm_count), dim3(CH_THREADS), args, pl.smem, st);
         if (e != cudaSuccess) { cudaGetLastError(); return fail(c, ESPER_E_CUDA, "cooperative launch (chain): %s", cudaGetErrorString(e)); }
     }
-    { LaunchScope ls(c, "lanczos"); ritz_chain_kernel<<<dim3(ceil_div(m, 128), k), 128, 0, st>>>(V, m, ctl, S_d, s_stride, kw, U_d, k); }
+    { LaunchScope ls(c, "lanczos"); ritz_fix_chain_kernel<<<k, 1024, 0, st>>>(V, m, ctl, S_d, s_stride, kw, U_d, k); }
     ESPER_CUDA(c, cudaGetLastError());
     // result block -> pinned host memory (same stream; the caller's final synchronise covers it)
     if (c->pin_chain.reserve(sizeof(Ctl) + sizeof(double) * CH_MAXCHK * CH_MAXWANT) != 0) return fail(c, ESPER_E_NOMEM, "pinned alloc failed");
@@ -910,11 +1470,35 @@ int chain_result(esper_ctx* c, int k, double* theta_out, int* iters_out) {
         const double n = h->steps_run > 0 ? (double)h->steps_run : 1.0;
         fprintf(stderr, "[chain] CTA0 cycles/step: S0 %.0f | P1-P3 %.0f | norm+publish %.0f | P4 %.0f | second pass %.0f ; prologue %lld\n",
                 h->prof[1] / n, h->prof[2] / n, h->prof[3] / n, h->prof[4] / n, h->prof[6] / n, h->prof[0]);
+        if (h->prof[16]) fprintf(stderr, "[chain] cluster schedule, CTA0 cycles/step: partials in DSMEM %.0f | packets + gather %.0f | coefficients in DSMEM %.0f ; forward packets %.0f | vector in DSMEM %.0f\n",
+                                 h->prof[16] / n, h->prof[17] / n, h->prof[2] / n, h->prof[18] / n, h->prof[4] / n);
+        if (h->prof[16]) fprintf(stderr, "[chain] cluster schedule, thread 0 of CTA0: S0 = products %.0f | warp sums %.0f | barrier %.0f | row totals + barrier %.0f ; update: own row %.0f | barrier %.0f | rest %.0f\n",
+                                 h->prof[19] / n, h->prof[20] / n, h->prof[21] / n, h->prof[1] / n, h->prof[22] / n, h->prof[23] / n, h->prof[3] / n);
         for (int cc = 0; cc < CH_MAXCHK; ++cc) {
             const long long e = h->prof[8 + 2 * cc], v = h->prof[9 + 2 * cc];
             if (e >> 32) fprintf(stderr, "[chain] checker %d: %lld eigenvalue tests, %.0f cycles each; %lld vector tests, %.0f cycles each up to the decision\n", cc, e >> 32,
                                  (double)(e & 0xffffffffLL) / (double)(e >> 32), v >> 32, (v >> 32) ? (double)(v & 0xffffffffLL) / (double)(v >> 32) : 0.0);
         }
+    }
+    if (getenv("ESPER_DEBUG_LANCZOS") && c->chain_trace_ctas > 0 && c->chain_trace.p) {
+        std::vector<long long> tr((size_t)16 * 160);
+        cudaMemcpy(tr.data(), c->chain_trace.p, sizeof(long long) * tr.size(), cudaMemcpyDeviceToHost);
+        long long t0 = -1;
+        for (int b = 0; b < c->chain_trace_ctas; ++b) if (tr[(size_t)b * 16] && (t0 < 0 || tr[(size_t)b * 16] < t0)) t0 = tr[(size_t)b * 16];
+        static const char* names[13] = {"step start", "products done", "w ready", "partials sent", "partials complete", "packets published", "gather + broadcast sent",
+                                        "coefficients complete", "update done", "norm known", "vector published", "forwarded", "vector complete"};
+        fprintf(stderr, "[chain] timeline of one step over %d worker CTAs (thread 0 each), ns after the first CTA started it: min / median / max\n", c->chain_trace_ctas);
+        for (int k = 0; k < 13; ++k) {
+            std::vector<long long> v;
+            for (int b = 0; b < c->chain_trace_ctas; ++b) if (tr[(size_t)b * 16 + k]) v.push_back(tr[(size_t)b * 16 + k] - t0);
+            if (v.empty()) continue;
+            std::sort(v.begin(), v.end());
+            fprintf(stderr, "[chain]   %-24s %6lld %6lld %6lld\n", names[k], v.front(), v[v.size() / 2], v.back());
+        }
+        const long long* e = tr.data() + 150 * 16;
+        fprintf(stderr, "[chain] kernel timeline (ns after the start of CTA 0): prologue done %lld | workers leave %lld | checkers leave %lld %lld %lld %lld\n", e[1] - e[0], e[2] - e[0],
+                e[4] ? e[4] - e[0] : 0, e[5] ? e[5] - e[0] : 0, e[6] ? e[6] - e[0] : 0, e[7] ? e[7] - e[0] : 0);
+        c->chain_trace_ctas = 0;
     }
     if (h->abort != 0u) return fail(c, ESPER_E_CUDA, "lanczos (chain): a packet wait timed out (CTAs not co-resident?)");
     if (h->status != 1 || h->winner < 0) return 1;

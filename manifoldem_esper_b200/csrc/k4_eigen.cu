@@ -947,6 +947,46 @@ __global__ void __launch_bounds__(128) ritz_kernel(const double* __restrict__ V,
 }
 
 // Normalise each column to unit length and make its largest-magnitude entry positive (first on ties).
+// V[0] = sqrt(deg) / |sqrt(deg)| (the locked vector) and, with_start, V[1] = the deterministic start vector of init_kernel
+// orthogonalised twice against V[0] and normalised.  One block: seven launches of the kernels above in one.
+__global__ void __launch_bounds__(1024) start_vectors_kernel(const double* __restrict__ deg, int m, double* __restrict__ V, int with_start) {
+    __shared__ double sh[32];
+    __shared__ double s_val;
+    const int tid = threadIdx.x;
+    double* V0 = V; double* V1 = V + m;
+    double s = 0.0;
+    for (int r = tid; r < m; r += 1024) { const double x = sqrt(deg[r]); V0[r] = x; s = fma(x, x, s); }
+    s = block_sum(s, sh);
+    if (tid == 0) { const double n = sqrt(s); s_val = n > 0.0 ? 1.0 / n : 0.0; }
+    __syncthreads();
+    const double inv0 = s_val;
+    for (int r = tid; r < m; r += 1024) V0[r] *= inv0;
+    if (!with_start) return;
+    for (int r = tid; r < m; r += 1024) {
+        uint32_t x = (uint32_t)r * 2654435761u + 0x9E3779B9u;
+        x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+        V1[r] = (double)x * (1.0 / 4294967296.0) - 0.5;
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        double d = 0.0;
+        for (int r = tid; r < m; r += 1024) d = fma(V0[r], V1[r], d);
+        __syncthreads();
+        d = block_sum(d, sh);
+        if (tid == 0) s_val = d;
+        __syncthreads();
+        const double h = s_val;
+        for (int r = tid; r < m; r += 1024) V1[r] = fma(-h, V0[r], V1[r]);
+    }
+    double q = 0.0;
+    for (int r = tid; r < m; r += 1024) { const double x = V1[r]; q = fma(x, x, q); }
+    __syncthreads();
+    q = block_sum(q, sh);
+    if (tid == 0) { const double n = sqrt(q); s_val = n > 0.0 ? 1.0 / n : 0.0; }
+    __syncthreads();
+    const double inv1 = s_val;
+    for (int r = tid; r < m; r += 1024) V1[r] *= inv1;
+}
+
 __global__ void __launch_bounds__(256) fix_columns_kernel(double* __restrict__ U, int m, int k) {
     __shared__ double sh[32];
     __shared__ double s_scale;
@@ -1216,16 +1256,8 @@ static int lanczos_attempt(esper_ctx* c, int m, int k, double tol, int max_iter,
         ESPER_CUDA(c, cudaMemcpyAsync(omega_d + 1, &one, sizeof(double), cudaMemcpyHostToDevice, st));   // omega_{1,1} = 1
     }
 
-    // locked vector v0 and the start vector q1 (orthogonal to v0)
-    { LaunchScope ls(c, "lanczos"); init_kernel<<<ceil_div(m, 256), 256, 0, st>>>(c->degree.as<double>(), m, w, w2); }
-    { LaunchScope ls(c, "lanczos"); normalize_kernel<<<1, 1024, 0, st>>>(w, m, V, nullptr); }
-    if (kw > 0) {
-        for (int pass = 0; pass < 2; ++pass) {
-            { LaunchScope ls(c, "lanczos"); dots_kernel<<<1, 256, 0, st>>>(V, m, w2, h); }
-            { LaunchScope ls(c, "lanczos"); update_kernel<<<ceil_div(m, 256), 256, 0, st>>>(V, m, 1, h, w2, nullptr); }
-        }
-        { LaunchScope ls(c, "lanczos"); normalize_kernel<<<1, 1024, 0, st>>>(w2, m, V + m, nullptr); }
-    }
+    // locked vector v0 and the start vector q1 (orthogonal to v0): one single-block launch
+    { LaunchScope ls(c, "lanczos"); start_vectors_kernel<<<1, 1024, 0, st>>>(c->degree.as<double>(), m, V, kw > 0 ? 1 : 0); }
 
     // Default schedule (esper_dmap_config 0): the barrier-free chain kernel with on-device convergence tests (k4_chain.cu).
     // It returns +1 for shapes it does not cover or when it did not converge within its shared-memory basis capacity;
@@ -1236,8 +1268,6 @@ static int lanczos_attempt(esper_ctx* c, int m, int k, double tol, int max_iter,
         int rcc = run_lanczos_chain(c, m, k, guard, tol, max_iter, V, Uc);
         if (rcc < 0) return rcc;
         if (rcc == 0) {
-            { LaunchScope ls(c, "lanczos"); fix_columns_kernel<<<k, 256, 0, st>>>(Uc, m, k); }
-            ESPER_CUDA(c, cudaGetLastError());
             if (vec_h) {
                 if (plain) ESPER_CUDA(c, cudaMemcpy2DAsync(vec_h, sizeof(double) * kw, Uc + 1, sizeof(double) * k, sizeof(double) * kw, m, cudaMemcpyDeviceToHost, st));
                 else ESPER_CUDA(c, cudaMemcpyAsync(vec_h, Uc, sizeof(double) * (size_t)m * k, cudaMemcpyDeviceToHost, st));

@@ -26,6 +26,7 @@ static EmuDim blockDim, gridDim;
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __align__(x)
 #ifndef EMU_ARENA_SHARED
 #define __shared__ static       // one block at a time: a function-local static is the block's shared variable
 #endif

@@ -130,7 +130,7 @@ DEVUTIL = os.path.join(ROOT, 'manifoldem_esper_b200', 'csrc', 'devutil.cuh')
 
 def arena_shared(text):
     import re
-    text = re.sub(r'extern\s+__shared__\s+(\w+)\s+(\w+)\[\];', r'\1* \2 = emu_dyn<\1>();', text)
+    text = re.sub(r'extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];', r'\1* \2 = emu_dyn<\1>();', text)
     return re.sub(r'__shared__\s+(\w+)\s+(\w+)\[([^\]]+)\];', r'\1* \2 = emu_smem<\1>(\3);', text)
 
 
@@ -390,10 +390,10 @@ def chain_bin(tmp_path_factory):
     src = open(os.path.join(ROOT, 'manifoldem_esper_b200', 'csrc', 'k4_chain.cu')).read()
     (d / 'chain_structs.inc').write_text(cut(src, 'struct Ctl {', '// ---- packet and flag primitives'))
     text = cut(src, '// ---- begin chain kernel text', '// ---- end chain kernel text')
-    text = re.sub(r'extern\s+__shared__\s+(\w+)\s+(\w+)\[\];', r'\1* \2 = emu_dyn<\1>();', text)
+    text = re.sub(r'extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];', r'\1* \2 = emu_dyn<\1>();', text)
     text = re.sub(r'__shared__\s+(\w+(?:\s+\w+)?)\s+(\w+)\[([^\]]+)\];', r'\1* \2 = emu_smem<\1>(\3);', text)
     text = re.sub(r'__shared__\s+(\w+(?:\s+\w+)?)\s+(\w+);', r'\1& \2 = *emu_smem<\1>(1);', text)
-    assert '__shared__' not in text and 'asm' not in text and 'lanczos_chain_kernel' in text and 'checker_main' in text
+    assert '__shared__' not in text and 'asm' not in text and 'lanczos_chain_kernel' in text and 'checker_main' in text and 'lanczos_cluster_kernel' in text
     (d / 'chain.inc').write_text(text)
     exe = str(d / 'chain_emu')
     res = subprocess.run(['g++', '-O1', '-std=c++20', '-pthread', '-Wno-unknown-pragmas', '-I', EMU, '-I', str(d),
@@ -408,6 +408,23 @@ def test_chain_lanczos_kernel_on_the_cpu(chain_bin, m, grid, kw, max_steps, expe
     """Workers (rows of Ms and of the basis on chip, packet hand-overs, no grid barrier) and checker CTAs (multisection
     Sturm counts, inverse iteration, stop word) together: alpha / beta against a numpy Lanczos with the same start,
     orthonormal basis, Ritz pairs of the winning checker against numpy's eigh; exhausted Krylov space and max_steps."""
+    run_chain_case(chain_bin, m, grid, kw, max_steps, expect, 0)
+
+
+@pytest.mark.parametrize('m,grid,S,kw,max_steps,expect', [(45, 6, 2, 4, 40, 'converged'),      # 3 clusters of 2, the last one: 1 worker + 1 checker
+                                                           (100, 12, 4, 6, 90, 'converged'),     # 10 rows per worker, 10 workers: 4 + 4 + 2, two checkers
+                                                           (20, 8, 4, 4, 19, 'exhausted'),       # 3 rows per worker, 7 workers, Krylov space exhausted
+                                                           (45, 8, 8, 4, 10, 'noconv'),          # ONE cluster (no packet level), max_steps reached
+                                                           (61, 9, 3, 4, 50, 'converged'),       # odd cluster size: gather groups of 4 lanes for 3 clusters
+                                                           (50, 4, 2, 4, 45, 'converged')])      # 17 rows per worker (10 in shared memory, 7 in registers)
+def test_cluster_lanczos_kernel_on_the_cpu(chain_bin, m, grid, S, kw, max_steps, expect):
+    """The cluster schedule (lanczos_cluster_kernel): partial coefficients and the vector exchanged through distributed shared
+    memory (st.async on the consumer's mbarrier) inside clusters of S CTAs and through packets between the clusters; same checks
+    as for the flat kernel.  Covers clusters that are not full, one cluster, rows in registers only and in shared memory."""
+    run_chain_case(chain_bin, m, grid, kw, max_steps, expect, S)
+
+
+def run_chain_case(chain_bin, m, grid, kw, max_steps, expect, S):
     exe, d = chain_bin
     g = golden('stage23_medium.npz' if m > 64 else 'stage123_pristine.npz')
     Ms = O.markov_symmetric_dense(g['D'][:m, :m], float(g['eps']))
@@ -418,8 +435,8 @@ def test_chain_lanczos_kernel_on_the_cpu(chain_bin, m, grid, kw, max_steps, expe
         q -= v0 * (v0 @ q)
     q /= np.linalg.norm(q)
     Ms.tofile(str(d / 'Ms.bin')); np.stack([v0, q]).tofile(str(d / 'V0.bin'))
-    res = subprocess.run([exe, str(d / 'Ms.bin'), str(m), str(d / 'V0.bin'), str(kw), '2', '1e-10', str(grid), str(max_steps), str(d / 'out.bin')],
-                         capture_output=True, text=True, timeout=1500)
+    res = subprocess.run([exe, str(d / 'Ms.bin'), str(m), str(d / 'V0.bin'), str(kw), '2', '1e-10', str(grid), str(max_steps), str(d / 'out.bin'), str(S)],
+                         capture_output=True, text=True, timeout=900, env=dict(os.environ, EMU_TIMEOUT_S='240'))
     check_run(res)
     out = np.fromfile(str(d / 'out.bin'))
     status, n_final, winner, steps_run, abort = (int(x) for x in out[:5])
