@@ -44,6 +44,7 @@ constexpr int CH_POINTS = 16;           // multisection points per eigenvalue an
 constexpr int CH_HWARP = 8;             // warps 0..7 may own coefficient slots (P2); warps 8..11 fetch the coefficients (P3)
 constexpr int CH_PK = 8;                // partial packets per lane and slot: workers <= 32 * CH_PK
 constexpr long long CH_TIMEOUT = 4000000000LL;     // ~2 s
+constexpr int CH_MAXTESTS = 192;        // convergence tests of one solve (sizes first_check + t check_stride)
 // cluster schedule (lanczos_cluster_kernel): thread-block clusters with distributed shared memory as the first exchange level
 constexpr int CL_MAXROWS = 17;          // rows of Ms per worker CTA (a B200 keeps 15 clusters of 8 resident: 118 workers at m = 2000)
 constexpr int CL_REGROWS = 7;           // of which in registers
@@ -60,6 +61,7 @@ struct Ctl {
     int status;                         // 1 converged, 2 not converged at max_steps
     int n_final, winner, steps_run;
     long long prof[32];
+    unsigned int verdict[CH_MAXTESTS];  // per scheduled test t: 0 not decided, 1 failed, 2 passed (the OLDEST passing test stops the iteration)
 };
 
 struct Params {
@@ -71,7 +73,7 @@ struct Params {
     int vs_cap;                         // basis vectors per owned row held in shared memory
     int kw, guard, cap_steps;           // pairs wanted (without the locked one), guard pairs, Krylov dimension m - 1
     double tol;
-    int first_check;
+    int first_check, check_stride;      // convergence tests at the sizes first_check + t check_stride, t = 0, 1, ...; checker c takes t = c (mod n_checkers)
     uint4* pbuf;                        // [slots][n_workers]
     uint4* hbuf;                        // [slots + 1]; the last packet is the control word
     uint4* qbuf;                        // [m]
@@ -501,7 +503,12 @@ __device__ void checker_main(const Params& p, double* smem, int c) {
     __shared__ int s_n;
     __shared__ int s_mode;
     int have = 0;                                              // alpha/beta of steps 1..have are in shared memory
-    int next_n = p.first_check + c;                            // checker c follows the sizes first_check + c + i n_checkers
+    // The sizes tested are a fixed schedule (first_check + t check_stride; checker c takes t = c, c + n_checkers, ...) and the
+    // OLDEST passing test stops the iteration, whichever checker finishes first: the step count of the result -- and with it
+    // every bit of the output -- does not depend on how fast the checkers run next to the workers.
+    int t_idx = c;
+    int next_n = p.first_check + t_idx * p.check_stride;
+#define CH_TEST_FAILED() do { if (tid == 0 && mode == 1 && t_idx < CH_MAXTESTS) st_word(&p.ctl->verdict[t_idx], 1u); t_idx += p.n_checkers; next_n = p.first_check + t_idx * p.check_stride; } while (0)
     int prev_want = 0;                                         // eigenvalues of this checker's previous test in cs.prev
     for (;;) {
         // ---- wait for the next size to test (thread 0 decides) ----
@@ -518,7 +525,7 @@ __device__ void checker_main(const Params& p, double* smem, int c) {
                     break;
                 }
                 const int prog = (int)ld_word(&p.ctl->progress);
-                if (prog >= next_n) { n = prog - ((prog - next_n) % p.n_checkers); mode = 1; break; }
+                if (prog >= next_n && t_idx < CH_MAXTESTS) { n = next_n; mode = 1; break; }
                 if (now() - t0 > CH_TIMEOUT) { st_word(&p.ctl->abort, 1u); mode = 3; break; }
                 relax();
             }
@@ -556,7 +563,7 @@ __device__ void checker_main(const Params& p, double* smem, int c) {
         if (tid < want) cs.prev[tid] = track ? cs.lo[tid] : cs.theta[tid];
         prev_want = want;
         __syncthreads();
-        if (mode == 1 && !stagnant) { next_n = n + p.n_checkers; continue; }
+        if (mode == 1 && !stagnant) { CH_TEST_FAILED(); continue; }
         const long long tc1 = now();
         if (!track) { /* theta is final */ }
         else if (tid < want) cs.theta[tid] = 0.5 * (cs.lo[tid] + cs.hi[tid]);      // stagnant: the bracket is a few ulps of |T| wide
@@ -568,8 +575,26 @@ __device__ void checker_main(const Params& p, double* smem, int c) {
             // margin), so that the workers leave while the vectors are refined.
             ritz_iterate(cs, n, cap, want, tn, false);
             if (p.prof_on && tid == 0) p.ctl->prof[9 + 2 * c] += (1LL << 32) + (now() - tc1);  // vector tests, cycles up to the decision
-            if (!ritz_residuals_ok(cs, n, cap, p.kw, want, p.tol, 0.25)) { next_n = n + p.n_checkers; __syncthreads(); continue; }
-            if (tid == 0) s_mode = (cas_word(&p.ctl->stop, 0u, 0x80000000u | ((unsigned int)c << 16) | (unsigned int)n) == 0u) ? 1 : 0;
+            if (!ritz_residuals_ok(cs, n, cap, p.kw, want, p.tol, 0.25)) { CH_TEST_FAILED(); __syncthreads(); continue; }
+            if (tid == 0) {
+                // passed: wait for the verdicts of the tests just before this one (one per other checker); an older pass wins
+                bool lose = false;
+                const long long t0 = now();
+                for (int u = t_idx - 1; u >= 0 && u > t_idx - p.n_checkers && !lose; --u) {
+                    for (;;) {
+                        const unsigned int v = ld_word(&p.ctl->verdict[u]);
+                        if (v == 2u || ld_word(&p.ctl->stop) != 0u || ld_word(&p.ctl->abort) != 0u) { lose = true; break; }
+                        if (v == 1u) break;
+                        if (now() - t0 > CH_TIMEOUT) { st_word(&p.ctl->abort, 1u); lose = true; break; }
+                        relax();
+                    }
+                }
+                if (!lose) {
+                    st_word(&p.ctl->verdict[t_idx], 2u);
+                    lose = cas_word(&p.ctl->stop, 0u, 0x80000000u | ((unsigned int)c << 16) | (unsigned int)n) != 0u;
+                }
+                s_mode = lose ? 0 : 1;
+            }
             __syncthreads();
             won = s_mode != 0;
             __syncthreads();
@@ -599,6 +624,7 @@ __device__ void checker_main(const Params& p, double* smem, int c) {
         }
         return;
     }
+#undef CH_TEST_FAILED
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1419,6 +1445,7 @@ int run_lanczos_chain(esper_ctx* c, int m, int k, int guard, double tol, int max
     p.max_steps = max_steps; p.vs_cap = cluster ? cp.vs_cap : pl.vs_cap;
     p.kw = kw; p.guard = guard; p.cap_steps = m - 1; p.tol = tol;
     p.first_check = std::min(max_steps, std::max(3 * (kw + guard) + 8, 32));
+    p.check_stride = p.n_checkers >= 2 ? 4 : 8;
     p.pbuf = pbuf; p.hbuf = hbuf; p.qbuf = qbuf; p.abuf = abuf; p.ctl = ctl;
     p.theta_out = theta_d; p.S_out = S_d; p.s_stride = s_stride;
     p.prof_on = getenv("ESPER_DEBUG_LANCZOS") ? 1 : 0;

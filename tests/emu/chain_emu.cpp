@@ -30,6 +30,7 @@ constexpr int CH_POINTS = 16;
 constexpr int CH_HWARP = 8;
 constexpr int CH_PK = 8;
 static long long CH_TIMEOUT = 4000000000LL;      // nanoseconds here; EMU_TIMEOUT_S shortens it (then a timed-out wait reports itself)
+constexpr int CH_MAXTESTS = 192;
 constexpr int CL_MAXROWS = 17;
 constexpr int CL_REGROWS = 7;
 constexpr int CL_GPK = 4;
@@ -155,6 +156,7 @@ int main(int argc, char** argv) {
     p.max_steps = max_steps; p.vs_cap = max_steps + 2;
     p.kw = kw; p.guard = guard; p.cap_steps = m - 1; p.tol = tol;
     p.first_check = std::min(max_steps, std::max(3 * (kw + guard) + 8, 12));
+    p.check_stride = getenv("EMU_CHECK_STRIDE") ? atoi(getenv("EMU_CHECK_STRIDE")) : (p.n_checkers >= 2 ? 2 : 3);
     const int slots = max_steps + 4;
     p.cl_size = CS; p.cl_count = CS > 0 ? (p.n_workers + CS - 1) / CS : 0; p.cl_group = 1;
     while (p.cl_group < p.cl_count) p.cl_group *= 2;
