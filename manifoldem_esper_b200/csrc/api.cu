@@ -140,6 +140,7 @@ long long esper_stat(esper_ctx* c, const char* name) {
     if (!c || !name) return -1;
     if (!strcmp(name, "lanczos_fallbacks")) return c->lanczos_fallbacks;
     if (!strcmp(name, "cluster_launches")) return c->cluster_launches;
+    if (!strcmp(name, "merged_launches")) return c->merged_launches;
     if (!strcmp(name, "launches")) return c->launches;
     return -1;
 }

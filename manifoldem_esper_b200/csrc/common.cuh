@@ -104,6 +104,7 @@ struct esper_ctx {
     esper::DevBuf chain_ws; esper::PinBuf pin_chain; long long chain_smem_set = 0;   // barrier-free schedule (k4_chain.cu)
     esper::DevBuf chain_trace; int chain_trace_ctas = 0;      // diagnostic timeline of one step (ESPER_DEBUG_LANCZOS)
     int cluster_cap_size = -1, cluster_cap = 0, cluster_launches = 0; long long cluster_smem = 0;   // its cluster variant: resident clusters of that size
+    int merged_cap_size = -1, merged_cap = 0, merged_launches = 0; long long merged_smem = 0; bool chain_trace_merged = false;   // merged (one-exchange) schedule
     // stage-4 workspaces
     esper::DevBuf rot_U, rot_R, rot_idx, rot_out, rot_H, rot_theta, rot_aux;
     int rot_n_pd = 0, rot_m = 0, rot_dim = 0;                  // shape of the normalised manifolds resident in rot_U
@@ -209,7 +210,7 @@ int run_rot_sweep(esper_ctx* c, const double* Uinit, int n_pd, int m, int dim, c
 int finish_full_spectrum(esper_ctx* c, int m, int k, int steps, const std::vector<double>& a, const std::vector<double>& b, double* V,
                          double** U_out, std::vector<double>& theta_out);
 int tridiag_eigen_all_host(const double* alpha, const double* beta, int n, double* theta, double* Z);
-int run_lanczos_chain(esper_ctx* c, int m, int k, int guard, double tol, int max_iter, double* V, double* U_d);
+int run_lanczos_chain(esper_ctx* c, int m, int k, int guard, double tol, int max_iter, double* V, double* U_d, bool unit_locked);
 int chain_result(esper_ctx* c, int k, double* theta_out, int* iters_out);
 int run_symv_rows(esper_ctx* c, int rows, int m, const double* q_d, double* w_rows_d);
 int run_comm_alloc(esper_ctx* c, int n_pad, int world, void* handle_out);

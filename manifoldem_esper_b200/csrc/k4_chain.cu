@@ -88,6 +88,9 @@ struct Params {
     int cl_count;                       // clusters that hold workers
     int cl_group;                       // lanes per slot in the gather: smallest power of two >= cl_count
     uint4* cbuf;                        // [slots + 1][cl_count] per-cluster partial coefficients
+    int merged;                         // 1: lanczos_merged_kernel (one exchange per step): cbuf has 4 buffers of cb_stride packets, qbuf 2 of m
+    size_t cb_stride;
+    double lambda0;                     // merged schedule: eigenvalue of the locked vector V[0] (1 for the Markov matrix)
     long long* trace;                   // diagnostic (ESPER_DEBUG_LANCZOS): [CTAs][16] globaltimer stamps of thread 0 in step trace_step
     int trace_step;
 };
@@ -137,6 +140,16 @@ __device__ __forceinline__ void dsm_send(double* dst_local, int rank, double v, 
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_addr(dst_local)), "r"(rank));
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(smem_addr(bar_local)), "r"(rank));
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(ra), "l"(__double_as_longlong(v)), "r"(rb) : "memory");
+}
+// count-based mbarrier (no transaction bytes): `count` arrivals complete a phase; dsm_arrive arrives at the copy of `bar_local`
+// in CTA `rank` of this cluster (release at cluster scope: what the arriving thread read before is done)
+__device__ __forceinline__ void mbar_init_count(Mbar* b, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void dsm_arrive(Mbar* bar_local, int rank) {
+    unsigned int rb;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(smem_addr(bar_local)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rb) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -1188,6 +1201,362 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_cluster_kernel(Params p
 #undef CL_TRACE
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Merged schedule (lanczos_merged_kernel): ONE exchange per step instead of two.  The cluster kernel above exchanges the
+// coefficients h = V^T w (reduce), orthogonalises, and then exchanges the new vector q_{j+1} (gather) before the next
+// product.  Here the UNorthogonalised candidate w_j is gathered together with the reduction of its coefficients, and the
+// product is taken of w_j: by linearity
+//     q_{j+1} = (w_j - V h) / beta_j                      Ms q_{j+1} = (Ms w_j - (Ms V) h) / beta_j
+// and Ms V is known in the basis itself: Ms v_0 = lambda0 v_0 (locked pair), Ms q_i = beta_i q_{i+1} + alpha_i q_i +
+// beta_{i-1} q_{i-1} for the earlier steps (their tiny reorthogonalisation terms enter multiplied by the tiny h_i: second
+// order), and for i = j EXACTLY  Ms q_j = beta_j q_{j+1} + sigma q_j + beta_{j-1} q_{j-1} + V h  (the definition of this
+// step).  So  Ms q_{j+1} = (y - V g) / beta_j - h_j q_{j+1}  with  y = Ms w_j  and  g = T~ h + h_j h  (T~ = tridiag(beta, alpha,
+// beta) with sigma in place of alpha_j, lambda0 in row 0) -- one more pass over the owned basis rows, no storage.  The next
+// candidate w_{j+1} = Ms q_{j+1} - alpha_j q_{j+1} - beta_j q_j and its partial coefficients follow on the owned rows at once.
+// Numerically this is the same iteration (numpy model on the benchmark matrix: alpha, beta within 1e-15, the recurrence for
+// Ms q stays within 1e-13 of the direct product over 320 steps; the locked pair must be an eigenpair: lambda0 wrong -> unstable).
+//   per step:  partial coefficients -> DSMEM | candidate rows -> DSMEM + packets | owners: cluster totals -> packets |
+//              forward the other clusters' rows | owners: totals over the clusters -> DSMEM | vector complete: copy out, "buffer
+//              free" arrive to the peers, product y = Ms w_j | coefficients complete: g, update, next candidate
+// The vector buffer is single: peers write the next candidate into it only after every CTA of the cluster has copied the
+// current one out (count-based mbarrier s_bar[3], remote arrives).  DGKS second pass (rare): coefficients of w - V h are
+// exchanged alone, H = h + h2, and the update is redone from w_j and y with H.
+// ---------------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t merged_worker_doubles(int cap) {
+    return (size_t)2 * cl_round16(cap + 8) + (size_t)cl_round16(cap + 24) + (size_t)CL_LD * (1 + CL_SMROWS) + (size_t)CL_MAXROWS * cap;
+}
+
+// y = Ms[own rows, :] x for the vector x held as 4 values per thread (columns tid + 512 u): rows in shared memory and registers.
+__device__ __forceinline__ void merged_symv(const double* s_rows, const double (&rrow)[CL_REGROWS][4], const double (&qv)[4], double* s_red, double* s_y,
+                                            int n_own, int n_sm, int tid, int warp, int lane) {
+    double acc[CL_MAXROWS];
+#pragma unroll
+    for (int q = 0; q < CL_MAXROWS; ++q) acc[q] = 0.0;
+    const double* rp = s_rows + tid;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        double t[CL_SMROWS];
+#pragma unroll
+        for (int q = 0; q < CL_SMROWS; ++q) t[q] = rp[q * CL_LD + CH_THREADS * u];
+#pragma unroll
+        for (int q = 0; q < CL_SMROWS; ++q) acc[q] = fma(t[q], qv[u], acc[q]);
+#pragma unroll
+        for (int e = 0; e < CL_REGROWS; ++e) acc[CL_SMROWS + e] = fma(rrow[e][u], qv[u], acc[CL_SMROWS + e]);
+    }
+    const double t16 = wsum(acc[16]);
+    double (&acc16)[16] = reinterpret_cast<double (&)[16]>(acc);
+    const double t = multi_sum16(acc16, lane);
+    if ((lane & 1) == 0) s_red[warp * CL_MAXROWS + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = t;
+    if (lane == 0) s_red[warp * CL_MAXROWS + 16] = t16;
+    __syncthreads();
+    if (tid < n_own) {
+        const int slot = tid < n_sm ? tid : (CL_MAXROWS - CL_REGROWS) + (tid - n_sm);
+        double tot = 0.0, tot2 = 0.0;
+#pragma unroll
+        for (int w2 = 0; w2 < CH_WARPS; w2 += 2) { tot += s_red[w2 * CL_MAXROWS + slot]; tot2 += s_red[(w2 + 1) * CL_MAXROWS + slot]; }
+        s_y[tid] = tot + tot2;
+    }
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 1) lanczos_merged_kernel(Params p) {
+    extern __shared__ __align__(128) double ch_smem[];
+    __shared__ Mbar s_bar[4];                                                // 0 partial coefficients | 1 coefficients | 2 vector | 3 vector buffer free
+    __shared__ double s_red[CH_WARPS * CL_MAXROWS];
+    __shared__ double s_w[CL_MAXROWS + 1];                                   // own rows of the gathered candidate w_j
+    __shared__ double s_y[CL_MAXROWS + 1];                                   // own rows of Ms w_j
+    __shared__ double s_upd[CL_MAXROWS + 1];                                 // w_j - V h
+    __shared__ double s_z[CL_MAXROWS + 1];                                   // y - V g
+    __shared__ double s_nw[CL_MAXROWS + 1];                                  // own rows of the next candidate
+    __shared__ double s_sc[4];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.x;
+    const int S = p.cl_size, C = p.cl_count, G = p.cl_group;
+    const int rank = cluster_rank(), cid = b / S;
+    Ctl* ctl = p.ctl;
+    const int W = min(S, p.n_workers - cid * S);                             // workers in this cluster (<= 0 in a cluster of checkers)
+    if (p.trace && b == 0 && tid == 0) p.trace[150 * 16] = wall_ns();
+    if (tid == 0) { mbar_init(&s_bar[0]); mbar_init(&s_bar[1]); mbar_init(&s_bar[2]); mbar_init_count(&s_bar[3], (unsigned int)max(W, 1)); mbar_init_fence(); }
+    __syncthreads();
+    cluster_sync_all();
+    if (b >= p.n_workers) {
+        if (b - p.n_workers < p.n_checkers) checker_main(p, ch_smem, b - p.n_workers);
+        if (p.trace && tid == 0 && b - p.n_workers < p.n_checkers) p.trace[150 * 16 + 4 + (b - p.n_workers)] = wall_ns();
+        cluster_sync_all();
+        return;
+    }
+    const int m = p.m, cap = p.vs_cap;
+    const int row0 = b * p.chunk, n_own = min(p.chunk, m - row0);            // 1 .. CL_MAXROWS
+    const int n_sm = max(0, n_own - CL_REGROWS);
+    const int crow0 = cid * S * p.chunk, crow1 = min(m, crow0 + S * p.chunk);   // rows owned inside this cluster
+    const int per = (m + W - 1) / W, f_lo = rank * per, f_hi = min(m, f_lo + per);   // share of the vector this CTA forwards
+    double* s_h = ch_smem;                                                   // [cap + 8]   coefficients of the step   } written by the peers:
+    double* s_part = s_h + cl_round16(cap + 8);                              // [cap + 24]  [owned slot][source rank]  } same offsets in
+    double* s_vec = s_part + cl_round16(cap + 24);                           // [CL_LD]     gathered candidate w_j     } every CTA
+    double* s_g = s_vec + CL_LD;                                             // [cap + 8]   g (local)
+    double* s_rows = s_g + cl_round16(cap + 8);                              // [CL_SMROWS][CL_LD]
+    double* Vs = s_rows + (size_t)CL_SMROWS * CL_LD;                         // [CL_MAXROWS][cap]
+#define MG_TRACE(k) do { if (p.trace && tid == 0 && j == p.trace_step) p.trace[b * 16 + (k)] = wall_ns(); } while (0)
+    if (tid <= CL_MAXROWS) { s_w[tid] = 0.0; s_y[tid] = 0.0; s_upd[tid] = 0.0; s_z[tid] = 0.0; s_nw[tid] = 0.0; }
+
+    for (int rr = 0; rr < CL_SMROWS; ++rr) {
+        const double* a = p.Ms + (size_t)(row0 + rr) * m;
+        for (int c = tid; c < CL_LD; c += CH_THREADS) s_rows[rr * CL_LD + c] = (rr < n_sm && c < m) ? __ldg(a + c) : 0.0;
+    }
+    double rrow[CL_REGROWS][4];
+#pragma unroll
+    for (int e = 0; e < CL_REGROWS; ++e)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = tid + CH_THREADS * u;
+            rrow[e][u] = (n_sm + e < n_own && c < m) ? __ldg(p.Ms + (size_t)(row0 + n_sm + e) * m + c) : 0.0;
+        }
+    double qv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int c = tid + CH_THREADS * u; qv[u] = c < m ? p.V[(size_t)m + c] : 0.0; }
+    for (int c = tid; c < CL_LD; c += CH_THREADS) s_vec[c] = 0.0;            // columns m .. CL_LD - 1 stay zero for the whole solve
+    for (int i = tid; i < CL_MAXROWS * cap; i += CH_THREADS) Vs[i] = 0.0;
+    __syncthreads();
+    if (tid < 2 * n_own) { const int r = tid >> 1, i = tid & 1; Vs[(size_t)r * cap + i] = p.V[(size_t)i * m + row0 + r]; }
+    if (tid < W) dsm_arrive(&s_bar[3], tid);                                 // this CTA's vector buffer may be written
+    if (tid == CH_THREADS - 1) mbar_expect(&s_bar[2], 8u * (unsigned int)m);
+    // first candidate: w_1 = Ms q_1 (sigma = 0)
+    merged_symv(s_rows, rrow, qv, s_red, s_y, n_own, n_sm, tid, warp, lane);
+    if (b == 0 && tid == CH_THREADS - 1) s_sc[1] = ld_word(&ctl->stop) != 0u ? 1.0 : 0.0;
+    __syncthreads();
+    if (tid < n_own) s_nw[tid] = s_y[tid];
+    double sigma = 0.0, alpha1 = 0.0;
+    double my_alpha = 0.0, my_beta = 0.0, my_beta_prev = 0.0;                // alpha_i, beta_i, beta_{i-1} of step i = tid
+    unsigned int phA = 0u, phH = 0u, phQ = 0u, phF = 0u;
+    __syncthreads();
+    if (p.trace && b == 0 && tid == 0) p.trace[150 * 16 + 1] = wall_ns();
+
+    int j = 1;                                                               // the candidate w_j is exchanged; step j completes with its coefficients
+    int end_reason = 0;                                                      // 1 stop word, 2 breakdown, 3 max_steps, 4 abort
+    for (; j <= p.max_steps; ++j) {
+        MG_TRACE(0);
+        double alpha_j = sigma, beta_j = 0.0, hj = 0.0, h_keep = 0.0;
+        bool leave = false;
+        for (int pass = 0; pass < 2; ++pass) {
+            const unsigned int tag = 2u * (unsigned int)j + (unsigned int)pass;
+            const int n_tot = j + 3;                                         // slot 0: |w|^2, slot 1 + i: V_i . w (i = 0..j), slot j + 2: stop word
+            const int n_mine = rank < n_tot ? (n_tot - rank + W - 1) / W : 0;   // slots rank, rank + W, ... are added up by this CTA
+            // A cluster may run one exchange ahead of a slow reader in another cluster (its next packets depend on the vector and on
+            // its OWN gathers only): packets alternate between buffers by step parity (and pass), the vector packets by step parity.
+            uint4* cb = p.cbuf + (size_t)(2 * (j & 1) + pass) * p.cb_stride;
+            uint4* qb = p.qbuf + (size_t)(j & 1) * m;
+            if (tid == CH_THREADS - 1) { mbar_expect(&s_bar[0], 8u * (unsigned int)(n_mine * W)); mbar_expect(&s_bar[1], 8u * (unsigned int)n_tot); }
+            const double* cand = pass == 0 ? s_nw : s_upd;                   // second pass: coefficients of w_j - V h
+            // ---- A1: partial coefficients of the owned rows -> the owner of the slot in this cluster ----
+            if (tid < n_tot) {
+                const int s = tid;
+                double v = 0.0;
+                if (s == n_tot - 1) v = (b == 0) ? s_sc[1] : 0.0;
+                else {                                                       // rows beyond n_own hold zeros
+                    const double* vcol = s == 0 ? cand : Vs + (s - 1);
+                    const int vstep = s == 0 ? 1 : cap;
+                    double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+#pragma unroll
+                    for (int r = 0; r + 2 < CL_MAXROWS; r += 3) {
+                        v0 = fma(vcol[r * vstep], cand[r], v0);
+                        v1 = fma(vcol[(r + 1) * vstep], cand[r + 1], v1);
+                        v2 = fma(vcol[(r + 2) * vstep], cand[r + 2], v2);
+                    }
+#pragma unroll
+                    for (int r = CL_MAXROWS - CL_MAXROWS % 3; r < CL_MAXROWS; ++r) v0 = fma(vcol[r * vstep], cand[r], v0);
+                    v = (v0 + v1) + v2;
+                }
+                const int idx = s / W, owner = s - idx * W;
+                dsm_send(&s_part[idx * W + rank], owner, v, &s_bar[0]);
+            }
+            int bad = 0;
+            // ---- the candidate itself: own rows -> the CTAs of this cluster and packets for the other clusters ----
+            if (pass == 0) {
+                if (!wait_mbar(&s_bar[3], phF, ctl)) bad = 1;                // every CTA of the cluster has copied the previous vector out
+                phF ^= 1u;
+                if (!bad) {
+                    if (tid < n_own) st_ll(qb + row0 + tid, s_nw[tid], 2u * (unsigned int)j);
+                    if (tid < n_own * W) {
+                        const int r = tid / W, d = tid - r * W;
+                        dsm_send(&s_vec[row0 + r], d, s_nw[r], &s_bar[2]);
+                    }
+                }
+                MG_TRACE(1);
+            }
+            // ---- A2: cluster totals of the owned slots -> packets ----
+            if (!wait_mbar(&s_bar[0], phA, ctl)) bad = 1;
+            phA ^= 1u;
+            if (pass == 0) MG_TRACE(2);
+            if (tid < n_mine && !bad) {
+                double tot = s_part[tid * W];
+                for (int src = 1; src < W; ++src) tot += s_part[tid * W + src];
+                st_ll(cb + (size_t)(tid * W + rank) * C + cid, tot, tag);
+            }
+            if (pass == 0) MG_TRACE(3);
+            // ---- Q: this CTA's share of the other clusters' rows, forwarded to the CTAs of this cluster ----
+            if (pass == 0 && !bad) {
+                const unsigned int qtag = 2u * (unsigned int)j;
+                for (int c = f_lo + tid; c < f_hi; c += CH_THREADS) {
+                    if (c >= crow0 && c < crow1) continue;
+                    double x;
+                    if (!wait_ll_short(qb + c, qtag, x, ctl)) { bad = 1; continue; }
+                    for (int d = 0; d < W; ++d) dsm_send(&s_vec[c], d, x, &s_bar[2]);
+                }
+                MG_TRACE(4);
+            }
+            // ---- A3: totals over all clusters (G lanes per slot, lane c reads cluster c), broadcast inside the cluster ----
+            {
+                const int per_pass = CH_THREADS / G;
+                const int c = tid & (G - 1);
+                for (int i0 = 0; i0 < n_mine; i0 += per_pass * CL_GPK) {
+                    double x[CL_GPK];
+                    unsigned int pend = 0u;
+#pragma unroll
+                    for (int q = 0; q < CL_GPK; ++q) { x[q] = 0.0; if (i0 + q * per_pass + tid / G < n_mine && c < C) pend |= 1u << q; }
+                    const uint4* src = cb + (size_t)((i0 + tid / G) * W + rank) * C + c;
+                    const size_t src_step = (size_t)per_pass * W * C;
+                    const long long t0 = now();
+                    for (unsigned int rounds = 1; pend != 0u; ++rounds) {
+                        const unsigned int cur = pend;
+#pragma unroll
+                        for (int q = 0; q < CL_GPK; ++q)
+                            if ((cur >> q) & 1u) { double v; if (ld_ll(src + q * src_step, tag, v)) { x[q] = v; pend &= ~(1u << q); } }
+                        if (pend != 0u) {
+                            relax_short();
+                            if ((rounds & 63u) == 0u && (ld_word(&ctl->abort) != 0u || now() - t0 > CH_TIMEOUT)) { st_word(&ctl->abort, 1u); bad = 1; break; }
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < CL_GPK; ++q) {
+                        if (i0 + q * per_pass >= n_mine) break;              // uniform in the CTA
+                        double v = x[q];
+                        for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                        const int idx = i0 + q * per_pass + tid / G;
+                        if (idx < n_mine)
+                            for (int d = c; d < W; d += G) dsm_send(&s_h[idx * W + rank], d, v, &s_bar[1]);
+                    }
+                }
+            }
+            if (pass == 0) MG_TRACE(5);
+            // ---- the gathered candidate: copy out, release the buffer, y = Ms w_j on the owned rows ----
+            if (pass == 0) {
+                if (!bad && !wait_mbar(&s_bar[2], phQ, ctl)) bad = 1;
+                phQ ^= 1u;
+                MG_TRACE(6);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) qv[u] = s_vec[tid + CH_THREADS * u];
+                if (tid < n_own) s_w[tid] = s_vec[row0 + tid];
+                if (__syncthreads_or(bad)) { end_reason = 4; leave = true; break; }
+                if (tid < W) dsm_arrive(&s_bar[3], tid);
+                if (tid == CH_THREADS - 1) mbar_expect(&s_bar[2], 8u * (unsigned int)m);
+                merged_symv(s_rows, rrow, qv, s_red, s_y, n_own, n_sm, tid, warp, lane);
+                MG_TRACE(7);
+            }
+            // ---- the coefficients ----
+            if (!bad && !wait_mbar(&s_bar[1], phH, ctl)) bad = 1;
+            phH ^= 1u;
+            if (pass == 0) MG_TRACE(8);
+            if (__syncthreads_or(bad)) { end_reason = 4; leave = true; break; }          // also: s_y of all rows is visible
+            if (s_h[n_tot - 1] != 0.0) { end_reason = 1; leave = true; break; }
+            double ww = s_h[0], sum_h2 = 0.0;
+            if (pass == 0) { if (tid <= j) h_keep = s_h[1 + tid]; }
+            else {
+                // second pass: |h2|^2 first, then H = h + h2 in place
+                double a0 = 0.0;
+                if (warp == 0) { for (int i = lane; i <= j; i += 32) a0 = fma(s_h[1 + i], s_h[1 + i], a0); a0 = wsum(a0); if (lane == 0) s_sc[2] = a0; }
+                __syncthreads();
+                sum_h2 = s_sc[2];
+                if (tid <= j) s_h[1 + tid] += h_keep;
+                __syncthreads();
+            }
+            // g = T~ H + H_j H (thread i: coefficient of V_i)
+            hj = s_h[1 + j];
+            if (tid <= j) {
+                const int i = tid;
+                const double hi = s_h[1 + i];
+                double g;
+                if (i == 0) g = p.lambda0 * hi;
+                else {
+                    g = (i < j ? my_alpha : sigma) * hi;
+                    if (i >= 2) g = fma(my_beta_prev, s_h[i], g);            // beta_{i-1} H_{i-1}
+                    if (i + 1 <= j) g = fma(my_beta, s_h[2 + i], g);         // beta_i H_{i+1}
+                }
+                s_g[1 + i] = fma(hj, hi, g);
+            }
+            __syncthreads();
+            // update of the owned rows (half-warp r): w_j - V H and y - V g; sum of squares of the coefficients (half-warp 31)
+            {
+                const int task = tid >> 4, l16 = tid & 15;
+                double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+                if (task < n_own) {
+                    const double* vr = Vs + (size_t)task * cap;
+                    int i = l16;
+                    for (; i + 16 <= j; i += 32) {
+                        const double x0 = vr[i], x1 = vr[i + 16];
+                        a0 = fma(x0, s_h[1 + i], a0); a1 = fma(x1, s_h[1 + i + 16], a1);
+                        b0 = fma(x0, s_g[1 + i], b0); b1 = fma(x1, s_g[1 + i + 16], b1);
+                    }
+                    if (i <= j) { const double x0 = vr[i]; a0 = fma(x0, s_h[1 + i], a0); b0 = fma(x0, s_g[1 + i], b0); }
+                } else if (task == 31) {
+                    int i = l16;
+                    for (; i + 16 <= j; i += 32) { a0 = fma(s_h[1 + i], s_h[1 + i], a0); a1 = fma(s_h[1 + i + 16], s_h[1 + i + 16], a1); }
+                    if (i <= j) a0 = fma(s_h[1 + i], s_h[1 + i], a0);
+                }
+                double ta = a0 + a1, tb = b0 + b1;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) { ta += __shfl_xor_sync(0xffffffffu, ta, o); tb += __shfl_xor_sync(0xffffffffu, tb, o); }
+                if (l16 == 0) {
+                    if (task < n_own) { s_upd[task] = s_w[task] - ta; s_z[task] = s_y[task] - tb; }
+                    else if (task == 31) s_sc[0] = ta;
+                }
+            }
+            __syncthreads();
+            if (pass == 0) MG_TRACE(9);
+            if (pass == 0) sum_h2 = s_sc[0];
+            const double after = ww - sum_h2;
+            alpha_j = sigma + hj;
+            if (pass == 0 && after < 0.5 * ww) continue;                     // DGKS: orthogonalise once more (s_upd is the candidate)
+            beta_j = after > 0.0 ? sqrt(after) : 0.0;
+            break;
+        }
+        if (leave) break;
+        if (j == 1) alpha1 = alpha_j;
+        // ---- q_{j+1}, Ms q_{j+1} and the next candidate on the owned rows ----
+        const bool breakdown = !(beta_j > 1e-14 * fmax(fabs(alpha1), 1e-300));
+        const double inv = beta_j > 0.0 ? 1.0 / beta_j : 0.0;
+        if (tid < n_own) {
+            const double q = s_upd[tid] * inv;
+            const double z = fma(-hj, q, s_z[tid] * inv);
+            Vs[(size_t)tid * cap + j + 1] = q;
+            p.V[(size_t)(j + 1) * m + row0 + tid] = q;
+            s_nw[tid] = fma(-beta_j, Vs[(size_t)tid * cap + j], fma(-alpha_j, q, z));
+        }
+        if (tid == j) { my_alpha = alpha_j; my_beta = beta_j; }
+        if (tid == j + 1) my_beta_prev = beta_j;
+        if (b == 0 && tid == 32) {
+            p.alpha[j - 1] = alpha_j; p.beta[j - 1] = beta_j;
+            st_ll(p.abuf + 2 * (size_t)j, alpha_j, 1u);
+            st_ll(p.abuf + 2 * (size_t)j + 1, beta_j, 1u);
+            st_word(&ctl->progress, (unsigned int)j);                        // a hint: the checkers wait for the packets themselves
+        }
+        if (b == 0 && tid == CH_THREADS - 1) s_sc[1] = ld_word(&ctl->stop) != 0u ? 1.0 : 0.0;
+        MG_TRACE(10);
+        if (breakdown) { end_reason = 2; ++j; break; }
+        if (j == p.max_steps) { end_reason = 3; ++j; break; }
+        sigma = alpha_j;
+        __syncthreads();
+    }
+    if (p.trace && b == 0 && tid == 0) p.trace[150 * 16 + 2] = wall_ns();
+    if (b == 0 && tid == 0) {
+        ctl->steps_run = j - 1;
+        if (end_reason == 2 || end_reason == 3) {
+            publish_fence();
+            st_word(&ctl->final_n, 0x80000000u | (end_reason == 2 ? 0x40000000u : 0u) | (unsigned int)(j - 1));
+        }
+    }
+    cluster_sync_all();                                                      // no CTA leaves while a peer may still store into it
+#undef MG_TRACE
+}
+
 // U[r][1+i] = sum_l V_{1+l}[r] S[l][i] with the step count and S of the winning checker read on the device; U[r][0] = V_0[r].
 __global__ void __launch_bounds__(128) ritz_chain_kernel(const double* __restrict__ V, int m, const Ctl* __restrict__ ctl,
                                                          const double* __restrict__ S_base, int s_stride, int kw,
@@ -1332,9 +1701,10 @@ struct ClusterPlan {
     size_t smem = 0;
 };
 
-static ClusterPlan cluster_plan(int S, int n_clusters, int m, int kw, int guard, int max_iter, long long smem_limit) {
+static ClusterPlan cluster_plan(int S, int n_clusters, int m, int kw, int guard, int max_iter, long long smem_limit, bool merged = false) {
     using namespace chain;
     ClusterPlan pl;
+    auto cluster_worker_doubles = [merged](int chunk, int cap) { return merged ? merged_worker_doubles(cap) : chain::cluster_worker_doubles(chunk, cap); };
     pl.S = S; pl.total = S * n_clusters;
     if (m < 32 || m > CH_MAXM || kw < 1 || kw + guard > CH_MAXWANT || pl.total < 2) return pl;
     pl.chunk = ceil_div(m, pl.total - 1);
@@ -1359,32 +1729,36 @@ static ClusterPlan cluster_plan(int S, int n_clusters, int m, int kw, int guard,
 }
 
 // Clusters of the cluster kernel the device holds at once (0: clusters of this size cannot be launched); cached per ctx.
-static int cluster_capacity(esper_ctx* c, int S) {
+static int cluster_capacity(esper_ctx* c, int S, bool merged = false) {
     using namespace chain;
-    if (c->cluster_cap_size == S) return c->cluster_cap;
+    int& cap_size = merged ? c->merged_cap_size : c->cluster_cap_size;
+    int& cap = merged ? c->merged_cap : c->cluster_cap;
+    long long& smem = merged ? c->merged_smem : c->cluster_smem;
+    void (*kernel)(Params) = merged ? lanczos_merged_kernel : lanczos_cluster_kernel;
+    if (cap_size == S) return cap;
     int optin = 0, n = 0;
     cudaFuncAttributes fa;
     if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device) != cudaSuccess ||
-        cudaFuncGetAttributes(&fa, lanczos_cluster_kernel) != cudaSuccess ||
-        cudaFuncSetAttribute(lanczos_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes) != cudaSuccess) {
+        cudaFuncGetAttributes(&fa, kernel) != cudaSuccess ||
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes) != cudaSuccess) {
         cudaGetLastError();
-        c->cluster_cap_size = S; c->cluster_cap = 0;
+        cap_size = S; cap = 0;
         return 0;
     }
-    c->cluster_smem = optin - (long long)fa.sharedSizeBytes;
-    if (S > 8 && cudaFuncSetAttribute(lanczos_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) cudaGetLastError();
+    smem = optin - (long long)fa.sharedSizeBytes;
+    if (S > 8 && cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) cudaGetLastError();
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(S * 64); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = (size_t)c->cluster_smem;
+    cfg.gridDim = dim3(S * 64); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = (size_t)smem;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    if (cudaOccupancyMaxActiveClusters(&n, (void*)lanczos_cluster_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
-    c->cluster_cap_size = S; c->cluster_cap = n;
+    if (cudaOccupancyMaxActiveClusters(&n, (void*)kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    cap_size = S; cap = n;
     return n;
 }
 
-int run_lanczos_chain(esper_ctx* c, int m, int k, int guard, double tol, int max_iter, double* V, double* U_d) {
+int run_lanczos_chain(esper_ctx* c, int m, int k, int guard, double tol, int max_iter, double* V, double* U_d, bool unit_locked) {
     using namespace chain;
     const int kw = k - 1;
     cudaStream_t st = c->stream;
@@ -1396,17 +1770,29 @@ int run_lanczos_chain(esper_ctx* c, int m, int k, int guard, double tol, int max
         ESPER_CUDA(c, cudaFuncSetAttribute(lanczos_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
         c->chain_smem_set = optin - (long long)fa.sharedSizeBytes;
     }
-    // cluster schedule first (ESPER_CLUSTER_SIZE = 0 switches it off, 2 / 4 / 8 / 16 choose the cluster size; default 8)
+    // cluster schedules first (ESPER_CLUSTER_SIZE = 0 switches them off, 2 / 4 / 8 / 16 choose the cluster size; default 8).  The merged
+    // schedule (one exchange per step; ESPER_CHAIN_MERGED = 0 switches it off) needs the locked pair to be an eigenpair with a known
+    // eigenvalue (unit_locked: the Markov matrix, lambda0 = 1); its basis capacity is a little smaller (one more coefficient array).
     ClusterPlan cp;
+    bool merged = false;
     {
         const char* e = getenv("ESPER_CLUSTER_SIZE");
         const int S = e ? atoi(e) : 8;
+        const char* em = getenv("ESPER_CHAIN_MERGED");
+        const bool want_merged = unit_locked && !(em && atoi(em) == 0);
         if (S == 2 || S == 4 || S == 8 || S == 16) {
-            const int cap = cluster_capacity(c, S);
-            if (cap > 0) cp = cluster_plan(S, cap, m, kw, guard, max_iter, c->cluster_smem);
+            if (want_merged) {
+                const int cap = cluster_capacity(c, S, true);
+                if (cap > 0) cp = cluster_plan(S, cap, m, kw, guard, max_iter, c->merged_smem, true);
+                merged = cp.ok;
+            }
+            if (!cp.ok) {
+                const int cap = cluster_capacity(c, S);
+                if (cap > 0) cp = cluster_plan(S, cap, m, kw, guard, max_iter, c->cluster_smem);
+            }
             if (getenv("ESPER_DEBUG_LANCZOS"))
-                fprintf(stderr, "[chain] clusters of %d: %d resident -> plan %s: %d rows per CTA, %d workers in %d clusters, %d checkers, %d steps, %zu B of shared memory\n", S, cap,
-                        cp.ok ? "ok" : "rejected", cp.chunk, cp.n_workers, cp.cl_count, cp.n_checkers, cp.max_steps, cp.smem);
+                fprintf(stderr, "[chain] clusters of %d (%s schedule): %d resident -> plan %s: %d rows per CTA, %d workers in %d clusters, %d checkers, %d steps, %zu B of shared memory\n", S,
+                        merged ? "merged" : "two-exchange", merged ? c->merged_cap : c->cluster_cap, cp.ok ? "ok" : "rejected", cp.chunk, cp.n_workers, cp.cl_count, cp.n_checkers, cp.max_steps, cp.smem);
         }
     }
     const ChainPlan pl = chain_plan(c, m, kw, guard, max_iter, c->chain_smem_set);
@@ -1422,8 +1808,9 @@ int run_lanczos_chain(esper_ctx* c, int m, int k, int guard, double tol, int max
 
     // workspace: packets | ctl | theta | S | alpha, beta
     const int slots = max_steps + 4;
-    const size_t n_p = cluster ? (size_t)slots * cp.cl_count : (size_t)slots * n_workers;      // cbuf or pbuf
-    const size_t n_h = (size_t)slots + 1, n_q = (size_t)m, n_a = 2 * ((size_t)max_steps + 2);
+    const size_t cb_stride = (size_t)slots * (size_t)std::max(cp.cl_count, 1);
+    const size_t n_p = merged ? 4 * cb_stride : cluster ? cb_stride : (size_t)slots * n_workers;      // cbuf (4 buffers: merged schedule) or pbuf
+    const size_t n_h = (size_t)slots + 1, n_q = (merged ? 2 : 1) * (size_t)m, n_a = 2 * ((size_t)max_steps + 2);
     const size_t pk_bytes = sizeof(uint4) * (n_p + n_h + n_q + n_a);
     const int s_stride = max_steps * kw;
     const size_t bytes = pk_bytes + sizeof(Ctl) + 64 + sizeof(double) * ((size_t)CH_MAXCHK * CH_MAXWANT + (size_t)CH_MAXCHK * s_stride + 2 * ((size_t)max_steps + 8));
@@ -1450,6 +1837,7 @@ int run_lanczos_chain(esper_ctx* c, int m, int k, int guard, double tol, int max
     p.theta_out = theta_d; p.S_out = S_d; p.s_stride = s_stride;
     p.prof_on = getenv("ESPER_DEBUG_LANCZOS") ? 1 : 0;
     p.cl_size = cluster ? cp.S : 0; p.cl_count = cp.cl_count; p.cl_group = cp.cl_group; p.cbuf = pbuf;
+    p.merged = merged ? 1 : 0; p.cb_stride = cb_stride; p.lambda0 = 1.0;
     p.trace = nullptr; p.trace_step = 0;
     if (cluster && getenv("ESPER_CLUSTER_RELAX_NS")) { const unsigned int ns = (unsigned int)atoi(getenv("ESPER_CLUSTER_RELAX_NS")); cudaMemcpyToSymbolAsync(g_relax_ns, &ns, sizeof ns, 0, cudaMemcpyHostToDevice, st); }
     if (cluster && p.prof_on) {
@@ -1469,9 +1857,11 @@ int run_lanczos_chain(esper_ctx* c, int m, int k, int guard, double tol, int max
         at[1].id = cudaLaunchAttributeCooperative;
         at[1].val.cooperative = 1;
         cfg.attrs = at; cfg.numAttrs = 2;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, lanczos_cluster_kernel, p);
+        cudaError_t e = merged ? cudaLaunchKernelEx(&cfg, lanczos_merged_kernel, p) : cudaLaunchKernelEx(&cfg, lanczos_cluster_kernel, p);
         if (e != cudaSuccess) { cudaGetLastError(); return fail(c, ESPER_E_CUDA, "cooperative cluster launch (%d x %d): %s", cp.S, cp.total / cp.S, cudaGetErrorString(e)); }
         c->cluster_launches++;
+        if (merged) c->merged_launches++;
+        c->chain_trace_merged = merged;
     } else {
         LaunchScope ls(c, "lanczos");
         void* args[] = {&p};
@@ -1512,8 +1902,11 @@ int chain_result(esper_ctx* c, int k, double* theta_out, int* iters_out) {
         cudaMemcpy(tr.data(), c->chain_trace.p, sizeof(long long) * tr.size(), cudaMemcpyDeviceToHost);
         long long t0 = -1;
         for (int b = 0; b < c->chain_trace_ctas; ++b) if (tr[(size_t)b * 16] && (t0 < 0 || tr[(size_t)b * 16] < t0)) t0 = tr[(size_t)b * 16];
-        static const char* names[13] = {"step start", "products done", "w ready", "partials sent", "partials complete", "packets published", "gather + broadcast sent",
-                                        "coefficients complete", "update done", "norm known", "vector published", "forwarded", "vector complete"};
+        static const char* names2[13] = {"step start", "products done", "w ready", "partials sent", "partials complete", "packets published", "gather + broadcast sent",
+                                         "coefficients complete", "update done", "norm known", "vector published", "forwarded", "vector complete"};
+        static const char* names1[13] = {"step start", "partials + rows sent", "partials complete", "packets published", "forwarded", "gather + broadcast sent", "vector complete",
+                                         "product done", "coefficients complete", "update done", "step end", "", ""};
+        const char** names = c->chain_trace_merged ? names1 : names2;
         fprintf(stderr, "[chain] timeline of one step over %d worker CTAs (thread 0 each), ns after the first CTA started it: min / median / max\n", c->chain_trace_ctas);
         for (int k = 0; k < 13; ++k) {
             std::vector<long long> v;

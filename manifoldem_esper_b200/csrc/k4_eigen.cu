@@ -1265,7 +1265,7 @@ static int lanczos_attempt(esper_ctx* c, int m, int k, double tol, int max_iter,
     if (!use_pro && kw > 0 && c->lanczos_mode == 0 && !full && !getenv("ESPER_LANCZOS_NO_CHAIN")) {
         ESPER_RESERVE(c, c->lan_small, sizeof(double) * ((size_t)m * k + (size_t)(max_iter + 8) * KMAX + 2 * KMAX * KMAX + 4096 + (size_t)ceil_div(m, 8) * 2));
         double* Uc = c->lan_small.as<double>();
-        int rcc = run_lanczos_chain(c, m, k, guard, tol, max_iter, V, Uc);
+        int rcc = run_lanczos_chain(c, m, k, guard, tol, max_iter, V, Uc, !plain);
         if (rcc < 0) return rcc;
         if (rcc == 0) {
             if (vec_h) {

@@ -1,7 +1,8 @@
 // chain_emu.cpp -- TEST INFRASTRUCTURE ONLY: the barrier-free Lanczos kernel of csrc/k4_chain.cu (cut into chain.inc by
 // tests/test_emu.py) on the CPU.  ALL blocks run concurrently, one OS thread per CUDA thread; the packet primitives
 // (st_ll / ld_ll: 16-byte {lo, tag, hi, tag} stores whose 8-byte halves are atomic) become two 64-bit atomics.
-//   chain_emu Ms.bin m V0.bin kw guard tol grid max_steps out.bin [S]
+//   chain_emu Ms.bin m V0.bin kw guard tol grid max_steps out.bin [S] [merged]
+//   merged = 1: lanczos_merged_kernel (one exchange per step; count-based mbarrier with remote arrives for the vector buffer)
 //   S > 0: the cluster schedule (lanczos_cluster_kernel) with clusters of S consecutive blocks; distributed shared memory is the
 //   peer block's arena, an mbarrier a {pending arrivals, transaction bytes, phase} record, st.async a store + complete_tx.
 //   V0.bin: [2, m] = locked vector v0 and normalised start q1.
@@ -44,14 +45,15 @@ static thread_local unsigned emu_last_tag = 0;
 static bool emu_clock = false;
 static int emu_S = 1;                                              // cluster size of the running launch
 static std::vector<std::unique_ptr<std::barrier<>>> emu_cl_bars;   // one per cluster
-struct Mbar { std::atomic<long long> tx; std::atomic<int> pending; std::atomic<unsigned> phase; std::atomic<int> lock; };
+struct Mbar { std::atomic<long long> tx; std::atomic<int> pending; std::atomic<unsigned> phase; std::atomic<int> lock; std::atomic<int> count; };
 inline void mbar_lock(Mbar* b) { int z = 0; while (!b->lock.compare_exchange_weak(z, 1, std::memory_order_acquire)) { z = 0; std::this_thread::yield(); } }
 inline void mbar_unlock(Mbar* b) { b->lock.store(0, std::memory_order_release); }
 inline void mbar_settle(Mbar* b) {                                 // phase completes when no arrival and no byte is pending
-    if (b->pending.load() == 0 && b->tx.load() == 0) { b->pending.store(1); b->phase.store(b->phase.load() ^ 1u, std::memory_order_release); }
+    if (b->pending.load() == 0 && b->tx.load() == 0) { b->pending.store(b->count.load()); b->phase.store(b->phase.load() ^ 1u, std::memory_order_release); }
 }
 inline int cluster_rank() { return (int)(blockIdx.x % (unsigned)emu_S); }
-inline void mbar_init(Mbar* b) { b->tx.store(0); b->pending.store(1); b->phase.store(0); b->lock.store(0); }
+inline void mbar_init(Mbar* b) { b->tx.store(0); b->pending.store(1); b->count.store(1); b->phase.store(0); b->lock.store(0); }
+inline void mbar_init_count(Mbar* b, unsigned int count) { b->tx.store(0); b->pending.store((int)count); b->count.store((int)count); b->phase.store(0); b->lock.store(0); }
 inline void mbar_init_fence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void mbar_expect(Mbar* b, unsigned int bytes) {
     mbar_lock(b);
@@ -73,6 +75,14 @@ inline void dsm_send(double* dst_local, int rank, double v, Mbar* bar_local) {
     __atomic_store_n(reinterpret_cast<uint64_t*>(dst), bits, __ATOMIC_RELAXED);
     mbar_lock(bar);
     if (bar->tx.fetch_sub(8) - 8 < -(1LL << 20)) { fprintf(stderr, "emu: transaction count underflow\n"); abort(); }
+    mbar_settle(bar);
+    mbar_unlock(bar);
+}
+inline void dsm_arrive(Mbar* bar_local, int rank) {                // remote arrive on a count-based mbarrier
+    const unsigned peer = blockIdx.x - (blockIdx.x % (unsigned)emu_S) + (unsigned)rank;
+    Mbar* bar = reinterpret_cast<Mbar*>(emu_arenas[peer].data() + (reinterpret_cast<char*>(bar_local) - emu_arena));
+    mbar_lock(bar);
+    if (bar->pending.fetch_sub(1) - 1 < 0) { fprintf(stderr, "emu: more arrivals than the mbarrier counts in one phase\n"); abort(); }
     mbar_settle(bar);
     mbar_unlock(bar);
 }
@@ -141,6 +151,7 @@ int main(int argc, char** argv) {
     using namespace esper::chain;
     if (argc < 10) return 2;
     const int CS = argc > 10 ? atoi(argv[10]) : 0;
+    const bool merged = argc > 11 && atoi(argv[11]) != 0 && CS > 0;
     const int m = atoi(argv[2]), kw = atoi(argv[4]), guard = atoi(argv[5]);
     const double tol = atof(argv[6]);
     const int grid = atoi(argv[7]), max_steps = atoi(argv[8]);
@@ -160,9 +171,10 @@ int main(int argc, char** argv) {
     const int slots = max_steps + 4;
     p.cl_size = CS; p.cl_count = CS > 0 ? (p.n_workers + CS - 1) / CS : 0; p.cl_group = 1;
     while (p.cl_group < p.cl_count) p.cl_group *= 2;
-    std::vector<uint4> pk((size_t)slots * p.n_workers + slots + 1 + m + 2 * (max_steps + 2), uint4{0, 0, 0, 0});
+    std::vector<uint4> pk((size_t)4 * slots * p.n_workers + slots + 1 + 2 * m + 2 * (max_steps + 2), uint4{0, 0, 0, 0});
     p.cbuf = pk.data();
-    p.pbuf = pk.data(); p.hbuf = p.pbuf + (size_t)slots * p.n_workers; p.qbuf = p.hbuf + slots + 1; p.abuf = p.qbuf + m;
+    p.pbuf = pk.data(); p.hbuf = p.pbuf + (size_t)4 * slots * p.n_workers; p.qbuf = p.hbuf + slots + 1; p.abuf = p.qbuf + 2 * m;
+    p.merged = merged ? 1 : 0; p.cb_stride = (size_t)slots * (size_t)std::max(p.cl_count, 1); p.lambda0 = 1.0;
     Ctl ctl; std::memset(&ctl, 0, sizeof ctl);
     p.ctl = &ctl;
     emu_ctl = &ctl; emu_pk_base = pk.data(); emu_off_h = p.hbuf - pk.data(); emu_off_q = p.qbuf - pk.data(); emu_off_a = p.abuf - pk.data();
@@ -172,13 +184,14 @@ int main(int argc, char** argv) {
     p.theta_out = theta.data(); p.S_out = S.data(); p.s_stride = s_stride; p.alpha = alpha.data(); p.beta = beta.data();
     p.prof_on = 0; p.trace = nullptr; p.trace_step = 0;
     const int n_sm = std::max(0, p.chunk - (CS > 0 ? CL_REGROWS : CH_REGROWS));
-    const size_t worker = CS > 0 ? sizeof(double) * cluster_worker_doubles(p.chunk, p.vs_cap) : sizeof(double) * ((size_t)m + (size_t)n_sm * m + (size_t)p.chunk * p.vs_cap);
+    const size_t worker = merged ? sizeof(double) * merged_worker_doubles(p.vs_cap) : CS > 0 ? sizeof(double) * cluster_worker_doubles(p.chunk, p.vs_cap) : sizeof(double) * ((size_t)m + (size_t)n_sm * m + (size_t)p.chunk * p.vs_cap);
     const size_t dyn = std::max(worker, sizeof(double) * checker_doubles(kw + guard, max_steps + 2));
     if (CS > 0) {
         if (grid % CS) { fprintf(stderr, "grid must be a multiple of the cluster size\n"); return 3; }
         emu_S = CS;
         for (int i = 0; i < grid / CS; ++i) emu_cl_bars.push_back(std::make_unique<std::barrier<>>(CS * CH_THREADS));
-        emu_launch_cluster(grid, CH_THREADS, grid, dyn, lanczos_cluster_kernel, p);
+        if (merged) emu_launch_cluster(grid, CH_THREADS, grid, dyn, lanczos_merged_kernel, p);
+        else emu_launch_cluster(grid, CH_THREADS, grid, dyn, lanczos_cluster_kernel, p);
     } else {
         emu_launch_cluster(grid, CH_THREADS, grid, dyn, lanczos_chain_kernel, p);
     }

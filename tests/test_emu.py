@@ -393,7 +393,7 @@ def chain_bin(tmp_path_factory):
     text = re.sub(r'extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];', r'\1* \2 = emu_dyn<\1>();', text)
     text = re.sub(r'__shared__\s+(\w+(?:\s+\w+)?)\s+(\w+)\[([^\]]+)\];', r'\1* \2 = emu_smem<\1>(\3);', text)
     text = re.sub(r'__shared__\s+(\w+(?:\s+\w+)?)\s+(\w+);', r'\1& \2 = *emu_smem<\1>(1);', text)
-    assert '__shared__' not in text and 'asm' not in text and 'lanczos_chain_kernel' in text and 'checker_main' in text and 'lanczos_cluster_kernel' in text
+    assert '__shared__' not in text and 'asm' not in text and 'lanczos_chain_kernel' in text and 'checker_main' in text and 'lanczos_cluster_kernel' in text and 'lanczos_merged_kernel' in text
     (d / 'chain.inc').write_text(text)
     exe = str(d / 'chain_emu')
     res = subprocess.run(['g++', '-O1', '-std=c++20', '-pthread', '-Wno-unknown-pragmas', '-I', EMU, '-I', str(d),
@@ -424,7 +424,17 @@ def test_cluster_lanczos_kernel_on_the_cpu(chain_bin, m, grid, S, kw, max_steps,
     run_chain_case(chain_bin, m, grid, kw, max_steps, expect, S)
 
 
-def run_chain_case(chain_bin, m, grid, kw, max_steps, expect, S):
+@pytest.mark.parametrize('m,grid,S,kw,max_steps,expect', [(45, 6, 2, 4, 40, 'converged'), (100, 12, 4, 6, 90, 'converged'), (20, 8, 4, 4, 19, 'exhausted'),
+                                                           (45, 8, 8, 4, 10, 'noconv'), (61, 9, 3, 4, 50, 'converged'), (50, 4, 2, 4, 45, 'converged')])
+def test_merged_lanczos_kernel_on_the_cpu(chain_bin, m, grid, S, kw, max_steps, expect):
+    """The merged schedule (lanczos_merged_kernel): the unorthogonalised candidate is gathered together with the reduction of its
+    coefficients (ONE exchange per step), Ms q_{j+1} follows from Ms w_j by linearity and the three-term relation of the basis.
+    Same cases and checks as the two-exchange cluster kernel: alpha / beta against a numpy Lanczos with direct products,
+    orthonormal basis, Ritz pairs; the single vector buffer is guarded by the count-based mbarrier with remote arrives."""
+    run_chain_case(chain_bin, m, grid, kw, max_steps, expect, S, merged=1)
+
+
+def run_chain_case(chain_bin, m, grid, kw, max_steps, expect, S, merged=0):
     exe, d = chain_bin
     g = golden('stage23_medium.npz' if m > 64 else 'stage123_pristine.npz')
     Ms = O.markov_symmetric_dense(g['D'][:m, :m], float(g['eps']))
@@ -435,7 +445,7 @@ def run_chain_case(chain_bin, m, grid, kw, max_steps, expect, S):
         q -= v0 * (v0 @ q)
     q /= np.linalg.norm(q)
     Ms.tofile(str(d / 'Ms.bin')); np.stack([v0, q]).tofile(str(d / 'V0.bin'))
-    res = subprocess.run([exe, str(d / 'Ms.bin'), str(m), str(d / 'V0.bin'), str(kw), '2', '1e-10', str(grid), str(max_steps), str(d / 'out.bin'), str(S)],
+    res = subprocess.run([exe, str(d / 'Ms.bin'), str(m), str(d / 'V0.bin'), str(kw), '2', '1e-10', str(grid), str(max_steps), str(d / 'out.bin'), str(S), str(merged)],
                          capture_output=True, text=True, timeout=900, env=dict(os.environ, EMU_TIMEOUT_S='240'))
     check_run(res)
     out = np.fromfile(str(d / 'out.bin'))
