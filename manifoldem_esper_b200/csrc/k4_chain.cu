@@ -90,6 +90,7 @@ struct Params {
     uint4* cbuf;                        // [slots + 1][cl_count] per-cluster partial coefficients
     int merged;                         // 1: lanczos_merged_kernel (one exchange per step): cbuf has 4 buffers of cb_stride packets, qbuf 2 of m
     size_t cb_stride;
+    int mg_order;                       // merged schedule: 0 gather the coefficients before the product, 1 after it
     double lambda0;                     // merged schedule: eigenvalue of the locked vector V[0] (1 for the Markov matrix)
     long long* trace;                   // diagnostic (ESPER_DEBUG_LANCZOS): [CTAs][16] globaltimer stamps of thread 0 in step trace_step
     int trace_step;
@@ -105,6 +106,16 @@ __device__ __forceinline__ void st_ll(uint4* p, double v, unsigned int tag) {
 __device__ __forceinline__ bool ld_ll(const uint4* p, unsigned int tag, double& v) {
     uint4 x;
     asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "l"(p) : "memory");
+    v = __hiloint2double((int)x.z, (int)x.x);
+    return x.y == tag && x.w == tag;
+}
+// the same in two halves: the load may be issued long before the packet is looked at
+__device__ __forceinline__ uint4 ld_ll_raw(const uint4* p) {
+    uint4 x;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "l"(p) : "memory");
+    return x;
+}
+__device__ __forceinline__ bool ll_decode(const uint4& x, unsigned int tag, double& v) {
     v = __hiloint2double((int)x.z, (int)x.x);
     return x.y == tag && x.w == tag;
 }
@@ -155,6 +166,7 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ long long wall_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define CH_DEBUG_TEST(c, n, mode, track, stagnant)
 #endif
 
 // ---- begin chain kernel text (tests/test_emu.py cuts from here) ----
@@ -336,7 +348,10 @@ __device__ void inverse_solve_thread(const CheckSmem& cs, int n, int cap, int co
 // Later rounds: P uniformly spaced points per eigenvalue, until no bracket moves (max_rounds = 0) or for max_rounds rounds
 // (tracking: the brackets stay in cs.lo / cs.hi); resume = continue from the brackets a tracking call left.  Returns the
 // norm bound tn.
-__device__ double leading_eigenvalues(const CheckSmem& cs, int n, int want, bool have_prev, bool resume, int max_rounds) {
+// gate_kw > 0 (tracking): after max_rounds rounds the search goes on (10 rounds at most) while for one of the gate_kw leading values
+// the question "has it grown by more than gate_rel |T| since cs.prev" is still open (hi - prev > thr but lo - prev <= thr): the
+// tests of one checker may lie many steps apart, and a bracket that is merely loose must not read as growth.
+__device__ double leading_eigenvalues(const CheckSmem& cs, int n, int want, bool have_prev, bool resume, int max_rounds, int gate_kw = 0, double gate_rel = 0.0) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double glo = 1e300, ghi = -1e300, tn = 0.0;
     for (int i = tid; i < n; i += CH_THREADS) {
@@ -363,7 +378,9 @@ __device__ double leading_eigenvalues(const CheckSmem& cs, int n, int want, bool
     // points per eigenvalue and round: the Sturm recurrences are FP64-throughput bound (measured: 512 of them cost 30k cycles
     // at n = 185), so a round uses 16 points per eigenvalue (6 warps for 11 values) rather than all threads
     const int P = min(CH_THREADS / want, CH_POINTS);
-    const int round_end = (max_rounds > 0 && !resume) ? max_rounds : 80;
+    const bool gated = gate_kw > 0 && max_rounds > 0 && !resume;
+    const double gate_thr = gate_rel * tn;
+    const int round_end = gated ? max(max_rounds, 10) : (max_rounds > 0 && !resume) ? max_rounds : 80;
     for (int round = resume ? 1 : 0; round < round_end; ++round) {
         const bool global_scan = (round == 0 && !have_prev);
         double x = 0.0; int e = -1;
@@ -396,6 +413,10 @@ __device__ double leading_eigenvalues(const CheckSmem& cs, int n, int want, bool
             }
             moved = (l != cs.lo[tid]) || (h != cs.hi[tid]);
             cs.lo[tid] = l; cs.hi[tid] = h;
+            if (gated && round + 1 >= max_rounds) {                  // beyond the fixed rounds only while a gate question is open
+                const bool open = tid < gate_kw && (h - cs.prev[tid] > gate_thr) && (l - cs.prev[tid] <= gate_thr);
+                moved = moved && open;
+            }
         }
         const int any = __syncthreads_or(moved ? 1 : 0);
         if (!any && round > 0) break;
@@ -521,7 +542,14 @@ __device__ void checker_main(const Params& p, double* smem, int c) {
     // every bit of the output -- does not depend on how fast the checkers run next to the workers.
     int t_idx = c;
     int next_n = p.first_check + t_idx * p.check_stride;
-#define CH_TEST_FAILED() do { if (tid == 0 && mode == 1 && t_idx < CH_MAXTESTS) st_word(&p.ctl->verdict[t_idx], 1u); t_idx += p.n_checkers; next_n = p.first_check + t_idx * p.check_stride; } while (0)
+    // A failed test of the eigenVECTORS (they cost 2 - 3 times an eigenvalue test) also gives up this checker's next slot, so that the
+    // checkers keep up with the workers; the slot is marked failed for whoever waits for its verdict.
+#define CH_TEST_FAILED(skip_one) do { \
+        if (tid == 0 && mode == 1) { \
+            if (t_idx < CH_MAXTESTS) st_word(&p.ctl->verdict[t_idx], 1u); \
+            if ((skip_one) && t_idx + p.n_checkers < CH_MAXTESTS) st_word(&p.ctl->verdict[t_idx + p.n_checkers], 1u); \
+        } \
+        t_idx += ((skip_one) ? 2 : 1) * p.n_checkers; next_n = p.first_check + t_idx * p.check_stride; } while (0)
     int prev_want = 0;                                         // eigenvalues of this checker's previous test in cs.prev
     for (;;) {
         // ---- wait for the next size to test (thread 0 decides) ----
@@ -564,19 +592,21 @@ __device__ void checker_main(const Params& p, double* smem, int c) {
         // Ritz value no longer grows (its error is residual^2 / gap), so the eigenvectors are only worth computing once the
         // kw leading values have stayed within a few ulps of |T| above their old bounds.
         const long long tc0 = now();
-        double tn = leading_eigenvalues(cs, n, want, have_prev, false, track ? 2 : 0);
+        const double gate_rel = fmax(64.0 * 2.220446049250313e-16, 1e3 * p.tol * p.tol);
+        double tn = leading_eigenvalues(cs, n, want, have_prev, false, track ? 2 : 0, track ? min(p.kw, want) : 0, gate_rel);
         if (p.prof_on && tid == 0) p.ctl->prof[8 + 2 * c] += (1LL << 32) + (now() - tc0);      // tests, eigenvalue-tracking cycles
         bool stagnant = track && n >= p.kw;
         if (stagnant) {
-            const double thr = fmax(64.0 * 2.220446049250313e-16 * tn, 1e3 * p.tol * p.tol * tn);
+            const double thr = gate_rel * tn;
             for (int i = 0; i < min(p.kw, want); ++i)
                 if (!(cs.hi[i] - cs.prev[i] <= thr)) stagnant = false;
         }
+        CH_DEBUG_TEST(c, n, mode, track, stagnant);
         __syncthreads();
         if (tid < want) cs.prev[tid] = track ? cs.lo[tid] : cs.theta[tid];
         prev_want = want;
         __syncthreads();
-        if (mode == 1 && !stagnant) { CH_TEST_FAILED(); continue; }
+        if (mode == 1 && !stagnant) { CH_TEST_FAILED(false); continue; }
         const long long tc1 = now();
         if (!track) { /* theta is final */ }
         else if (tid < want) cs.theta[tid] = 0.5 * (cs.lo[tid] + cs.hi[tid]);      // stagnant: the bracket is a few ulps of |T| wide
@@ -588,7 +618,7 @@ __device__ void checker_main(const Params& p, double* smem, int c) {
             // margin), so that the workers leave while the vectors are refined.
             ritz_iterate(cs, n, cap, want, tn, false);
             if (p.prof_on && tid == 0) p.ctl->prof[9 + 2 * c] += (1LL << 32) + (now() - tc1);  // vector tests, cycles up to the decision
-            if (!ritz_residuals_ok(cs, n, cap, p.kw, want, p.tol, 0.25)) { CH_TEST_FAILED(); __syncthreads(); continue; }
+            if (!ritz_residuals_ok(cs, n, cap, p.kw, want, p.tol, 0.25)) { CH_TEST_FAILED(true); __syncthreads(); continue; }
             if (tid == 0) {
                 // passed: wait for the verdicts of the tests just before this one (one per other checker); an older pass wins
                 bool lose = false;
@@ -1227,8 +1257,7 @@ __host__ __device__ inline size_t merged_worker_doubles(int cap) {
 }
 
 // y = Ms[own rows, :] x for the vector x held as 4 values per thread (columns tid + 512 u): rows in shared memory and registers.
-__device__ __forceinline__ void merged_symv(const double* s_rows, const double (&rrow)[CL_REGROWS][4], const double (&qv)[4], double* s_red, double* s_y,
-                                            int n_own, int n_sm, int tid, int warp, int lane) {
+__device__ __forceinline__ void merged_symv(const double* s_rows, const double (&rrow)[CL_REGROWS][4], const double (&qv)[4], double* s_red, int tid, int warp, int lane) {
     double acc[CL_MAXROWS];
 #pragma unroll
     for (int q = 0; q < CL_MAXROWS; ++q) acc[q] = 0.0;
@@ -1248,7 +1277,9 @@ __device__ __forceinline__ void merged_symv(const double* s_rows, const double (
     const double t = multi_sum16(acc16, lane);
     if ((lane & 1) == 0) s_red[warp * CL_MAXROWS + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = t;
     if (lane == 0) s_red[warp * CL_MAXROWS + 16] = t16;
-    __syncthreads();
+}
+// second half (after a __syncthreads): the row totals of the 16 warps -> s_y
+__device__ __forceinline__ void merged_symv_totals(const double* s_red, double* s_y, int n_own, int n_sm, int tid) {
     if (tid < n_own) {
         const int slot = tid < n_sm ? tid : (CL_MAXROWS - CL_REGROWS) + (tid - n_sm);
         double tot = 0.0, tot2 = 0.0;
@@ -1320,7 +1351,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_merged_kernel(Params p)
     if (tid < W) dsm_arrive(&s_bar[3], tid);                                 // this CTA's vector buffer may be written
     if (tid == CH_THREADS - 1) mbar_expect(&s_bar[2], 8u * (unsigned int)m);
     // first candidate: w_1 = Ms q_1 (sigma = 0)
-    merged_symv(s_rows, rrow, qv, s_red, s_y, n_own, n_sm, tid, warp, lane);
+    merged_symv(s_rows, rrow, qv, s_red, tid, warp, lane);
+    __syncthreads();
+    merged_symv_totals(s_red, s_y, n_own, n_sm, tid);
     if (b == 0 && tid == CH_THREADS - 1) s_sc[1] = ld_word(&ctl->stop) != 0u ? 1.0 : 0.0;
     __syncthreads();
     if (tid < n_own) s_nw[tid] = s_y[tid];
@@ -1366,6 +1399,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_merged_kernel(Params p)
                     v = (v0 + v1) + v2;
                 }
                 const int idx = s / W, owner = s - idx * W;
+                if (pass == 0) MG_TRACE(12);
                 dsm_send(&s_part[idx * W + rank], owner, v, &s_bar[0]);
             }
             int bad = 0;
@@ -1404,7 +1438,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_merged_kernel(Params p)
                 MG_TRACE(4);
             }
             // ---- A3: totals over all clusters (G lanes per slot, lane c reads cluster c), broadcast inside the cluster ----
-            {
+            auto gather_coefficients = [&]() {
                 const int per_pass = CH_THREADS / G;
                 const int c = tid & (G - 1);
                 for (int i0 = 0; i0 < n_mine; i0 += per_pass * CL_GPK) {
@@ -1435,22 +1469,32 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_merged_kernel(Params p)
                             for (int d = c; d < W; d += G) dsm_send(&s_h[idx * W + rank], d, v, &s_bar[1]);
                     }
                 }
-            }
-            if (pass == 0) MG_TRACE(5);
-            // ---- the gathered candidate: copy out, release the buffer, y = Ms w_j on the owned rows ----
+            };
+            // ---- the gathered candidate: copy out, release the buffer, y = Ms w_j on the owned rows; false = a wait failed ----
+            // order 1 (default): the product first -- the gather then finds every packet in place; order 0: gather first.  (Loading the
+            // packets before the product and decoding them after it was measured too: the four live registers spill and the
+            // product slows down by more than the L2 round trip that is saved.)
+            bool vec_ok = true;
             if (pass == 0) {
+                if (p.mg_order == 0) { gather_coefficients(); MG_TRACE(5); }
                 if (!bad && !wait_mbar(&s_bar[2], phQ, ctl)) bad = 1;
                 phQ ^= 1u;
                 MG_TRACE(6);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) qv[u] = s_vec[tid + CH_THREADS * u];
                 if (tid < n_own) s_w[tid] = s_vec[row0 + tid];
-                if (__syncthreads_or(bad)) { end_reason = 4; leave = true; break; }
-                if (tid < W) dsm_arrive(&s_bar[3], tid);
-                if (tid == CH_THREADS - 1) mbar_expect(&s_bar[2], 8u * (unsigned int)m);
-                merged_symv(s_rows, rrow, qv, s_red, s_y, n_own, n_sm, tid, warp, lane);
-                MG_TRACE(7);
-            }
+                vec_ok = __syncthreads_or(bad) == 0;
+                if (vec_ok) {
+                    if (tid < W) dsm_arrive(&s_bar[3], tid);
+                    if (tid == CH_THREADS - 1) mbar_expect(&s_bar[2], 8u * (unsigned int)m);
+                    merged_symv(s_rows, rrow, qv, s_red, tid, warp, lane);
+                    __syncthreads();
+                    merged_symv_totals(s_red, s_y, n_own, n_sm, tid);
+                    MG_TRACE(7);
+                    if (p.mg_order != 0) { gather_coefficients(); MG_TRACE(5); }
+                }
+            } else gather_coefficients();
+            if (!vec_ok) { end_reason = 4; leave = true; break; }
             // ---- the coefficients ----
             if (!bad && !wait_mbar(&s_bar[1], phH, ctl)) bad = 1;
             phH ^= 1u;
@@ -1483,6 +1527,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_merged_kernel(Params p)
                 s_g[1 + i] = fma(hj, hi, g);
             }
             __syncthreads();
+            if (pass == 0) MG_TRACE(9);
             // update of the owned rows (half-warp r): w_j - V H and y - V g; sum of squares of the coefficients (half-warp 31)
             {
                 const int task = tid >> 4, l16 = tid & 15;
@@ -1510,7 +1555,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_merged_kernel(Params p)
                 }
             }
             __syncthreads();
-            if (pass == 0) MG_TRACE(9);
+            if (pass == 0) MG_TRACE(10);
             if (pass == 0) sum_h2 = s_sc[0];
             const double after = ww - sum_h2;
             alpha_j = sigma + hj;
@@ -1539,7 +1584,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_merged_kernel(Params p)
             st_word(&ctl->progress, (unsigned int)j);                        // a hint: the checkers wait for the packets themselves
         }
         if (b == 0 && tid == CH_THREADS - 1) s_sc[1] = ld_word(&ctl->stop) != 0u ? 1.0 : 0.0;
-        MG_TRACE(10);
+        MG_TRACE(11);
         if (breakdown) { end_reason = 2; ++j; break; }
         if (j == p.max_steps) { end_reason = 3; ++j; break; }
         sigma = alpha_j;
@@ -1832,12 +1877,13 @@ int run_lanczos_chain(esper_ctx* c, int m, int k, int guard, double tol, int max
     p.max_steps = max_steps; p.vs_cap = cluster ? cp.vs_cap : pl.vs_cap;
     p.kw = kw; p.guard = guard; p.cap_steps = m - 1; p.tol = tol;
     p.first_check = std::min(max_steps, std::max(3 * (kw + guard) + 8, 32));
-    p.check_stride = p.n_checkers >= 2 ? 4 : 8;
+    p.check_stride = (p.chunk >= 12 ? 4 : 6) * (p.n_checkers >= 2 ? 1 : 2);       // an eigenvalue test takes about the time of 4 steps (6 short ones)
     p.pbuf = pbuf; p.hbuf = hbuf; p.qbuf = qbuf; p.abuf = abuf; p.ctl = ctl;
     p.theta_out = theta_d; p.S_out = S_d; p.s_stride = s_stride;
     p.prof_on = getenv("ESPER_DEBUG_LANCZOS") ? 1 : 0;
     p.cl_size = cluster ? cp.S : 0; p.cl_count = cp.cl_count; p.cl_group = cp.cl_group; p.cbuf = pbuf;
     p.merged = merged ? 1 : 0; p.cb_stride = cb_stride; p.lambda0 = 1.0;
+    p.mg_order = getenv("ESPER_MERGED_ORDER") ? atoi(getenv("ESPER_MERGED_ORDER")) : 1;
     p.trace = nullptr; p.trace_step = 0;
     if (cluster && getenv("ESPER_CLUSTER_RELAX_NS")) { const unsigned int ns = (unsigned int)atoi(getenv("ESPER_CLUSTER_RELAX_NS")); cudaMemcpyToSymbolAsync(g_relax_ns, &ns, sizeof ns, 0, cudaMemcpyHostToDevice, st); }
     if (cluster && p.prof_on) {
@@ -1905,7 +1951,7 @@ int chain_result(esper_ctx* c, int k, double* theta_out, int* iters_out) {
         static const char* names2[13] = {"step start", "products done", "w ready", "partials sent", "partials complete", "packets published", "gather + broadcast sent",
                                          "coefficients complete", "update done", "norm known", "vector published", "forwarded", "vector complete"};
         static const char* names1[13] = {"step start", "partials + rows sent", "partials complete", "packets published", "forwarded", "gather + broadcast sent", "vector complete",
-                                         "product done", "coefficients complete", "update done", "step end", "", ""};
+                                         "product done", "coefficients complete", "g done", "update done", "step end", "own partial computed"};
         const char** names = c->chain_trace_merged ? names1 : names2;
         fprintf(stderr, "[chain] timeline of one step over %d worker CTAs (thread 0 each), ns after the first CTA started it: min / median / max\n", c->chain_trace_ctas);
         for (int k = 0; k < 13; ++k) {
@@ -1914,6 +1960,21 @@ int chain_result(esper_ctx* c, int k, double* theta_out, int* iters_out) {
             if (v.empty()) continue;
             std::sort(v.begin(), v.end());
             fprintf(stderr, "[chain]   %-24s %6lld %6lld %6lld\n", names[k], v.front(), v[v.size() / 2], v.back());
+        }
+        if (getenv("ESPER_TRACE_CLUSTERS")) {
+            const int S = atoi(getenv("ESPER_TRACE_CLUSTERS"));
+            fprintf(stderr, "[chain] the same per cluster of %d CTAs (median of its CTAs)\n", S);
+            for (int k = 0; k < 13; ++k) {
+                if (!names[k][0]) continue;
+                fprintf(stderr, "[chain]   %-24s", names[k]);
+                for (int b0 = 0; b0 < c->chain_trace_ctas; b0 += S) {
+                    std::vector<long long> v;
+                    for (int b = b0; b < std::min(b0 + S, c->chain_trace_ctas); ++b) if (tr[(size_t)b * 16 + k]) v.push_back(tr[(size_t)b * 16 + k] - t0);
+                    std::sort(v.begin(), v.end());
+                    fprintf(stderr, " %5lld", v.empty() ? -1LL : v[v.size() / 2]);
+                }
+                fprintf(stderr, "\n");
+            }
         }
         const long long* e = tr.data() + 150 * 16;
         fprintf(stderr, "[chain] kernel timeline (ns after the start of CTA 0): prologue done %lld | workers leave %lld | checkers leave %lld %lld %lld %lld\n", e[1] - e[0], e[2] - e[0],

@@ -105,6 +105,16 @@ inline bool ld_ll(const uint4* p, unsigned int tag, double& v) {
     if (!ok) { emu_last_wait = p; emu_last_tag = tag; std::this_thread::yield(); }
     return ok;
 }
+inline uint4 ld_ll_raw(const uint4* p) {
+    const uint64_t* q = reinterpret_cast<const uint64_t*>(p);
+    const uint64_t lo = __atomic_load_n(q, __ATOMIC_RELAXED), hi = __atomic_load_n(q + 1, __ATOMIC_RELAXED);
+    return uint4{(uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32)};
+}
+inline bool ll_decode(const uint4& x, unsigned int tag, double& v) {
+    const uint64_t bits = (uint64_t)x.x | ((uint64_t)x.z << 32);
+    std::memcpy(&v, &bits, 8);
+    return x.y == tag && x.w == tag;
+}
 static const uint4* emu_pk_base = nullptr; static size_t emu_off_h = 0, emu_off_q = 0, emu_off_a = 0;
 static Ctl* emu_ctl = nullptr;
 inline void emu_report(const char* why) {
@@ -135,6 +145,10 @@ inline void publish_fence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline long long now() { return emu_clock ? (long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count() : 0; }
 inline void relax() { std::this_thread::yield(); }
 inline void relax_short() { std::this_thread::yield(); }
+#define CH_DEBUG_TEST(c, n, mode, track, stagnant) do { if (getenv("EMU_DEBUG_TESTS") && threadIdx.x == 0) { \
+    fprintf(stderr, "checker %d: n %d mode %d track %d stagnant %d tn %.3e:", c, n, mode, (int)(track), (int)(stagnant), tn); \
+    for (int i_ = 0; i_ < min(p.kw, want); ++i_) fprintf(stderr, " [%.1e %.1e]", (cs.lo[i_] - cs.prev[i_]) / tn, (cs.hi[i_] - cs.prev[i_]) / tn); \
+    fprintf(stderr, "\n"); } } while (0)
 #include "chain.inc"
 }  // namespace chain
 }  // namespace esper
@@ -174,7 +188,7 @@ int main(int argc, char** argv) {
     std::vector<uint4> pk((size_t)4 * slots * p.n_workers + slots + 1 + 2 * m + 2 * (max_steps + 2), uint4{0, 0, 0, 0});
     p.cbuf = pk.data();
     p.pbuf = pk.data(); p.hbuf = p.pbuf + (size_t)4 * slots * p.n_workers; p.qbuf = p.hbuf + slots + 1; p.abuf = p.qbuf + 2 * m;
-    p.merged = merged ? 1 : 0; p.cb_stride = (size_t)slots * (size_t)std::max(p.cl_count, 1); p.lambda0 = 1.0;
+    p.merged = merged ? 1 : 0; p.cb_stride = (size_t)slots * (size_t)std::max(p.cl_count, 1); p.lambda0 = 1.0; p.mg_order = getenv("EMU_MERGED_ORDER") ? atoi(getenv("EMU_MERGED_ORDER")) : 1;
     Ctl ctl; std::memset(&ctl, 0, sizeof ctl);
     p.ctl = &ctl;
     emu_ctl = &ctl; emu_pk_base = pk.data(); emu_off_h = p.hbuf - pk.data(); emu_off_q = p.qbuf - pk.data(); emu_off_a = p.abuf - pk.data();
