@@ -317,7 +317,10 @@ def run_ours(args):
     # stream each) so that the host-side tanh fit / Lanczos convergence tests of one PD overlap the
     # kernels of the other; a serial pass on one stream provides clean per-kernel timings. ----
     NF = max(1, args.inflight)
-    eig_mode = args.eig_mode if args.eig_mode >= 0 else (1 if NF > 1 else 0)
+    # mode 0 (one persistent kernel for the whole solve, convergence test on the device) for both arms since the merged schedule:
+    # its 120 CTAs (15 clusters of 8) leave 28 SMs to the kernels of the other PDs in flight (measured: 391 PD/s with 3 in flight
+    # against 380 PD/s with the streamed barrier kernel and 6 in flight).
+    eig_mode = args.eig_mode if args.eig_mode >= 0 else 0
     ctxs, streams = [ctx], [stream]
     for _ in range(NF - 1):
         st_ = torch.cuda.Stream()
@@ -537,7 +540,7 @@ def run_ours(args):
         'config': {'workload': WORKLOAD, 'pd_per_rank_per_step': 1, 'sharding': 'independent PDs per rank, no data-path collective',
                    'pipelining': '%d PDs in flight per GPU (one host thread / ctx / stream each)' % NF, 'serial_ms_per_step': ms_serial / args.steps,
                    'api': 'esper_pd_embed_fused (one C call per PD)' if NATIVE_FIT else 'staged calls with scipy curve_fit',
-                   'eigensolver': {0: 'mode 0: barrier-free chain kernel, on-device convergence test', 1: 'mode 1: streamed barrier kernel, two grids per SM',
+                   'eigensolver': {0: 'mode 0: one persistent cluster kernel, one exchange per Lanczos step, on-device convergence test', 1: 'mode 1: streamed barrier kernel, two grids per SM',
                                    2: 'mode 2: streamed, no speculative batch', 3: 'mode 3: resident barrier kernel'}.get(eig_mode),
                    'l2': 'inputs larger than L2 (500 MB stack per PD, two alternating stacks per rank)',
                    'lanczos_steps': iters_used[-1] if iters_used else None, 'numa_bind_rank0': numa,
@@ -601,11 +604,11 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-numa-bind', action='store_true', help='do not restrict ranks to the CPUs of their GPU\'s NUMA node')
-    ap.add_argument('--eig-mode', type=int, default=-1, help='esper_dmap_config mode (-1 = throughput when several PDs are in flight)')
+    ap.add_argument('--eig-mode', type=int, default=-1, help='esper_dmap_config mode (-1 = the library default, mode 0)')
     ap.add_argument('--gram-tf32', action='store_true', help='3xTF32 operand planes for the Gram kernel (esper_gram_config 0) instead of the default 3xFP16')
     ap.add_argument('--scipy-fit', action='store_true', help='tanh fit with scipy.optimize.curve_fit (the reference\'s call) instead of esper_tanh_fit')
     ap.add_argument('--sweep-general', action='store_true', help='general sweep kernel (esper_sweep_config 0) instead of the default moment sweep')
-    ap.add_argument('--inflight', type=int, default=6, help='PDs in flight per GPU (host threads / ctxs / streams)')
+    ap.add_argument('--inflight', type=int, default=3, help='PDs in flight per GPU (host threads / ctxs / streams)')
     ap.add_argument('--no-extras', action='store_true', help='skip the post-measurement c5_rot (N=1) / c4_rowblock (N>1) runs')
     args = ap.parse_args()
     args.gram_f16, args.sweep_moments = not args.gram_tf32, not args.sweep_general

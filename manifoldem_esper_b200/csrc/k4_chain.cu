@@ -73,6 +73,7 @@ struct Params {
     int vs_cap;                         // basis vectors per owned row held in shared memory
     int kw, guard, cap_steps;           // pairs wanted (without the locked one), guard pairs, Krylov dimension m - 1
     double tol;
+    int check_back;                     // the gate of a test compares T_n with T_{n - check_back}
     int first_check, check_stride;      // convergence tests at the sizes first_check + t check_stride, t = 0, 1, ...; checker c takes t = c (mod n_checkers)
     uint4* pbuf;                        // [slots][n_workers]
     uint4* hbuf;                        // [slots + 1]; the last packet is the control word
@@ -90,7 +91,7 @@ struct Params {
     uint4* cbuf;                        // [slots + 1][cl_count] per-cluster partial coefficients
     int merged;                         // 1: lanczos_merged_kernel (one exchange per step): cbuf has 4 buffers of cb_stride packets, qbuf 2 of m
     size_t cb_stride;
-    int mg_order;                       // merged schedule: 0 gather the coefficients before the product, 1 after it
+    int mg_order;                       // merged schedule: 1 forward, product, gather (default); 2 forward and gather side by side, then the product
     double lambda0;                     // merged schedule: eigenvalue of the locked vector V[0] (1 for the Markov matrix)
     long long* trace;                   // diagnostic (ESPER_DEBUG_LANCZOS): [CTAs][16] globaltimer stamps of thread 0 in step trace_step
     int trace_step;
@@ -348,10 +349,8 @@ __device__ void inverse_solve_thread(const CheckSmem& cs, int n, int cap, int co
 // Later rounds: P uniformly spaced points per eigenvalue, until no bracket moves (max_rounds = 0) or for max_rounds rounds
 // (tracking: the brackets stay in cs.lo / cs.hi); resume = continue from the brackets a tracking call left.  Returns the
 // norm bound tn.
-// gate_kw > 0 (tracking): after max_rounds rounds the search goes on (10 rounds at most) while for one of the gate_kw leading values
-// the question "has it grown by more than gate_rel |T| since cs.prev" is still open (hi - prev > thr but lo - prev <= thr): the
-// tests of one checker may lie many steps apart, and a bracket that is merely loose must not read as growth.
-__device__ double leading_eigenvalues(const CheckSmem& cs, int n, int want, bool have_prev, bool resume, int max_rounds, int gate_kw = 0, double gate_rel = 0.0) {
+// resume with max_rounds > 0: that many more rounds on the brackets a tracking call left.
+__device__ double leading_eigenvalues(const CheckSmem& cs, int n, int want, bool have_prev, bool resume, int max_rounds) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double glo = 1e300, ghi = -1e300, tn = 0.0;
     for (int i = tid; i < n; i += CH_THREADS) {
@@ -378,9 +377,7 @@ __device__ double leading_eigenvalues(const CheckSmem& cs, int n, int want, bool
     // points per eigenvalue and round: the Sturm recurrences are FP64-throughput bound (measured: 512 of them cost 30k cycles
     // at n = 185), so a round uses 16 points per eigenvalue (6 warps for 11 values) rather than all threads
     const int P = min(CH_THREADS / want, CH_POINTS);
-    const bool gated = gate_kw > 0 && max_rounds > 0 && !resume;
-    const double gate_thr = gate_rel * tn;
-    const int round_end = gated ? max(max_rounds, 10) : (max_rounds > 0 && !resume) ? max_rounds : 80;
+    const int round_end = max_rounds > 0 ? (resume ? 1 + max_rounds : max_rounds) : 80;
     for (int round = resume ? 1 : 0; round < round_end; ++round) {
         const bool global_scan = (round == 0 && !have_prev);
         double x = 0.0; int e = -1;
@@ -413,10 +410,6 @@ __device__ double leading_eigenvalues(const CheckSmem& cs, int n, int want, bool
             }
             moved = (l != cs.lo[tid]) || (h != cs.hi[tid]);
             cs.lo[tid] = l; cs.hi[tid] = h;
-            if (gated && round + 1 >= max_rounds) {                  // beyond the fixed rounds only while a gate question is open
-                const bool open = tid < gate_kw && (h - cs.prev[tid] > gate_thr) && (l - cs.prev[tid] <= gate_thr);
-                moved = moved && open;
-            }
         }
         const int any = __syncthreads_or(moved ? 1 : 0);
         if (!any && round > 0) break;
@@ -592,14 +585,31 @@ __device__ void checker_main(const Params& p, double* smem, int c) {
         // Ritz value no longer grows (its error is residual^2 / gap), so the eigenvectors are only worth computing once the
         // kw leading values have stayed within a few ulps of |T| above their old bounds.
         const long long tc0 = now();
-        const double gate_rel = fmax(64.0 * 2.220446049250313e-16, 1e3 * p.tol * p.tol);
-        double tn = leading_eigenvalues(cs, n, want, have_prev, false, track ? 2 : 0, track ? min(p.kw, want) : 0, gate_rel);
+        double tn = leading_eigenvalues(cs, n, want, have_prev, false, track ? 2 : 0);
         if (p.prof_on && tid == 0) p.ctl->prof[8 + 2 * c] += (1LL << 32) + (now() - tc0);      // tests, eigenvalue-tracking cycles
-        bool stagnant = track && n >= p.kw;
+        // The gate in front of the eigenvector test: have the kw leading values grown by more than thr over the last check_back
+        // steps?  T_{n - back} is a leading block of T_n, so one Sturm count per value on the shorter recurrence answers
+        // "theta_i(n - back) >= lo_i(n) - thr" -- no: grown, whatever the bracket (lo is a lower bound); yes: the growth is at most
+        // hi - lo + thr, and the bracket at n is refined (one round at a time) until that is decisive.  Self-contained: the answer
+        // does not depend on how far back this checker's previous test lies.
+        bool stagnant = track && n - p.check_back >= want;
         if (stagnant) {
-            const double thr = gate_rel * tn;
-            for (int i = 0; i < min(p.kw, want); ++i)
-                if (!(cs.hi[i] - cs.prev[i] <= thr)) stagnant = false;
+            const double thr = fmax(64.0 * 2.220446049250313e-16, 1e3 * p.tol * p.tol) * tn;
+            const int gk = min(p.kw, want), nb = n - p.check_back;
+            for (int it = 0; it < 12; ++it) {
+                int open = 0, grown = 0;
+                if (tid < gk) {
+                    const int below = sturm_below(cs.a, cs.b2, nb, cs.lo[tid] - thr);
+                    if (nb - below < tid + 1) grown = 1;
+                    else if (cs.hi[tid] - cs.lo[tid] > thr) open = 1;
+                }
+                const int any_grown = __syncthreads_or(grown);
+                const int any_open = __syncthreads_or(open);
+                if (any_grown) { stagnant = false; break; }
+                if (!any_open) break;
+                if (it == 11) { stagnant = false; break; }
+                tn = leading_eigenvalues(cs, n, want, true, true, 1);
+            }
         }
         CH_DEBUG_TEST(c, n, mode, track, stagnant);
         __syncthreads();
@@ -1327,6 +1337,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_merged_kernel(Params p)
     double* s_rows = s_g + cl_round16(cap + 8);                              // [CL_SMROWS][CL_LD]
     double* Vs = s_rows + (size_t)CL_SMROWS * CL_LD;                         // [CL_MAXROWS][cap]
 #define MG_TRACE(k) do { if (p.trace && tid == 0 && j == p.trace_step) p.trace[b * 16 + (k)] = wall_ns(); } while (0)
+#define MG_TRACE_ANY(k) do { if (p.trace && j == p.trace_step) p.trace[b * 16 + (k)] = wall_ns(); } while (0)
     if (tid <= CL_MAXROWS) { s_w[tid] = 0.0; s_y[tid] = 0.0; s_upd[tid] = 0.0; s_z[tid] = 0.0; s_nw[tid] = 0.0; }
 
     for (int rr = 0; rr < CL_SMROWS; ++rr) {
@@ -1426,20 +1437,20 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_merged_kernel(Params p)
                 st_ll(cb + (size_t)(tid * W + rank) * C + cid, tot, tag);
             }
             if (pass == 0) MG_TRACE(3);
-            // ---- Q: this CTA's share of the other clusters' rows, forwarded to the CTAs of this cluster ----
-            if (pass == 0 && !bad) {
+            // ---- Q: this CTA's share of the other clusters' rows, forwarded to the CTAs of this cluster (threads t0 .. t0 + nt - 1) ----
+            auto forward_rows = [&](int t0, int nt) {
                 const unsigned int qtag = 2u * (unsigned int)j;
-                for (int c = f_lo + tid; c < f_hi; c += CH_THREADS) {
+                for (int c = f_lo + (tid - t0); c < f_hi; c += nt) {
                     if (c >= crow0 && c < crow1) continue;
                     double x;
                     if (!wait_ll_short(qb + c, qtag, x, ctl)) { bad = 1; continue; }
                     for (int d = 0; d < W; ++d) dsm_send(&s_vec[c], d, x, &s_bar[2]);
                 }
-                MG_TRACE(4);
-            }
+            };
             // ---- A3: totals over all clusters (G lanes per slot, lane c reads cluster c), broadcast inside the cluster ----
-            auto gather_coefficients = [&]() {
-                const int per_pass = CH_THREADS / G;
+            // (threads 0 .. gt - 1 take part, gt a multiple of 32)
+            auto gather_coefficients = [&](int gt) {
+                const int per_pass = gt / G;
                 const int c = tid & (G - 1);
                 for (int i0 = 0; i0 < n_mine; i0 += per_pass * CL_GPK) {
                     double x[CL_GPK];
@@ -1470,13 +1481,23 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_merged_kernel(Params p)
                     }
                 }
             };
-            // ---- the gathered candidate: copy out, release the buffer, y = Ms w_j on the owned rows; false = a wait failed ----
-            // order 1 (default): the product first -- the gather then finds every packet in place; order 0: gather first.  (Loading the
-            // packets before the product and decoding them after it was measured too: the four live registers spill and the
-            // product slows down by more than the L2 round trip that is saved.)
+            // ---- the gathered candidate: copy out, release the buffer, y = Ms w_j on the owned rows ----
+            // order 1 (default): forward the rows, the product, then the gather (it finds every packet in place): 1.51 ms at C2.
+            // order 2 (ESPER_MERGED_ORDER=2): the last four warps forward the rows WHILE the others gather the coefficients, then the
+            // product -- measured slower (1.70 ms): whenever the coefficient broadcast lands in shared memory during the product, the
+            // product takes 2.6 instead of 1.9 us (the same was seen with the gather in front of the product, 1.58 ms).  Loading the
+            // packets before the product and decoding them after it: the four live registers spill, 1.48 ms -- no gain either.
             bool vec_ok = true;
             if (pass == 0) {
-                if (p.mg_order == 0) { gather_coefficients(); MG_TRACE(5); }
+                constexpr int FW = 128;
+                if (p.mg_order == 2) {
+                    if (!bad) { if (tid >= CH_THREADS - FW) forward_rows(CH_THREADS - FW, FW); else gather_coefficients(CH_THREADS - FW); }
+                    if (tid == CH_THREADS - FW) MG_TRACE_ANY(4);
+                    MG_TRACE(5);
+                } else {
+                    if (!bad) forward_rows(0, CH_THREADS);
+                    MG_TRACE(4);
+                }
                 if (!bad && !wait_mbar(&s_bar[2], phQ, ctl)) bad = 1;
                 phQ ^= 1u;
                 MG_TRACE(6);
@@ -1491,9 +1512,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_merged_kernel(Params p)
                     __syncthreads();
                     merged_symv_totals(s_red, s_y, n_own, n_sm, tid);
                     MG_TRACE(7);
-                    if (p.mg_order != 0) { gather_coefficients(); MG_TRACE(5); }
+                    if (p.mg_order != 2) { gather_coefficients(CH_THREADS); MG_TRACE(5); }
                 }
-            } else gather_coefficients();
+            } else gather_coefficients(CH_THREADS);
             if (!vec_ok) { end_reason = 4; leave = true; break; }
             // ---- the coefficients ----
             if (!bad && !wait_mbar(&s_bar[1], phH, ctl)) bad = 1;
@@ -1600,6 +1621,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_merged_kernel(Params p)
     }
     cluster_sync_all();                                                      // no CTA leaves while a peer may still store into it
 #undef MG_TRACE
+#undef MG_TRACE_ANY
 }
 
 // U[r][1+i] = sum_l V_{1+l}[r] S[l][i] with the step count and S of the winning checker read on the device; U[r][0] = V_0[r].
@@ -1877,6 +1899,7 @@ int run_lanczos_chain(esper_ctx* c, int m, int k, int guard, double tol, int max
     p.max_steps = max_steps; p.vs_cap = cluster ? cp.vs_cap : pl.vs_cap;
     p.kw = kw; p.guard = guard; p.cap_steps = m - 1; p.tol = tol;
     p.first_check = std::min(max_steps, std::max(3 * (kw + guard) + 8, 32));
+    p.check_back = 8;                        // growth over 8 steps: the gate opens when the eigenvector test is likely to pass at once
     p.check_stride = (p.chunk >= 12 ? 4 : 6) * (p.n_checkers >= 2 ? 1 : 2);       // an eigenvalue test takes about the time of 4 steps (6 short ones)
     p.pbuf = pbuf; p.hbuf = hbuf; p.qbuf = qbuf; p.abuf = abuf; p.ctl = ctl;
     p.theta_out = theta_d; p.S_out = S_d; p.s_stride = s_stride;

@@ -181,6 +181,7 @@ int main(int argc, char** argv) {
     p.max_steps = max_steps; p.vs_cap = max_steps + 2;
     p.kw = kw; p.guard = guard; p.cap_steps = m - 1; p.tol = tol;
     p.first_check = std::min(max_steps, std::max(3 * (kw + guard) + 8, 12));
+    p.check_back = 4;
     p.check_stride = getenv("EMU_CHECK_STRIDE") ? atoi(getenv("EMU_CHECK_STRIDE")) : (p.n_checkers >= 2 ? 2 : 3);
     const int slots = max_steps + 4;
     p.cl_size = CS; p.cl_count = CS > 0 ? (p.n_workers + CS - 1) / CS : 0; p.cl_group = 1;
