@@ -333,14 +333,15 @@ def run_ours(args):
         c.sync()
     iters_used = []
 
-    def pipelined(n_steps, e2e):
-        """n_steps PDs over the two ctxs (thread t takes steps t, t+2, ...); returns device ms."""
+    def pipelined(n_steps, e2e, nf=None):
+        """n_steps PDs over nf ctxs (thread t takes steps t, t + nf, ...); returns device ms."""
         errs = []
+        nf = NF if nf is None else nf
 
         def worker(t):
             try:
                 torch.cuda.set_device(local_rank)
-                for s in range(t, n_steps, NF):
+                for s in range(t, n_steps, nf):
                     if e2e:
                         embed_step(ctxs[t], GB, coef, a0, N_IMG, P, imgs=pinned[t % n_stacks].numpy(), download=True,
                                    out=d_out[t].numpy())
@@ -354,7 +355,7 @@ def run_ours(args):
         e0.record(streams[0])
         for st_ in streams[1:]:
             st_.wait_event(e0)
-        th = [threading.Thread(target=worker, args=(t,)) for t in range(NF)]
+        th = [threading.Thread(target=worker, args=(t,)) for t in range(nf)]
         for x in th:
             x.start()
         for x in th:
@@ -420,8 +421,11 @@ def run_ours(args):
     eig_mode_e2e = args.eig_mode if args.eig_mode >= 0 else 0
     for c in ctxs:
         c.dmap_config(eig_mode_e2e)
-    pipelined(NF, True)
-    ms_e2e = pipelined(args.steps, True)
+    # two in flight: the copy of one stack runs under the kernels of the other; more only split the link (measured: 108 PD/s with 2,
+    # 94 - 108 with 3, 105 with 4)
+    NF_E2E = min(NF, max(1, args.inflight_e2e))
+    pipelined(NF_E2E, True, NF_E2E)
+    ms_e2e = pipelined(args.steps, True, NF_E2E)
 
     # raw host->device rate of this box for one 500 MB stack (what bounds the e2e figure); all ranks copy at the same time, so at
     # N > 1 this is the per-GPU share of the box's aggregate pinned-copy ceiling, not the link rate of one GPU
@@ -550,7 +554,7 @@ def run_ours(args):
                 'd2h_bytes_per_step': int(N_IMG * N_IMG * 8 + len(LOG_EPS) * 8 + K_EIG * 8 + N_IMG * K_EIG * 8),
                 'ms_per_step': ms_e2e / args.steps, 'h2d_probe_gbs': round(h2d_gbs, 2),
                 'h2d_floor_ms_per_step': round(N_IMG * P * 4 / (h2d_gbs * 1e9) * 1e3, 3),
-                'eigensolver_mode': eig_mode_e2e,
+                'eigensolver_mode': eig_mode_e2e, 'pds_in_flight': NF_E2E,
                 'note': 'bounded by the host->device copy of the 500 MB stack; h2d_probe_gbs = bare pinned cudaMemcpyAsync rate per GPU with all %d '
                         'ranks copying at once (the box ceiling at this N), h2d_floor_ms_per_step = 500 MB at that rate, frac_of_h2d_floor = floor / measured' % world},
         'gpu_launches': launches,
@@ -609,6 +613,7 @@ def main():
     ap.add_argument('--scipy-fit', action='store_true', help='tanh fit with scipy.optimize.curve_fit (the reference\'s call) instead of esper_tanh_fit')
     ap.add_argument('--sweep-general', action='store_true', help='general sweep kernel (esper_sweep_config 0) instead of the default moment sweep')
     ap.add_argument('--inflight', type=int, default=3, help='PDs in flight per GPU (host threads / ctxs / streams)')
+    ap.add_argument('--inflight-e2e', type=int, default=2, help='PDs in flight per GPU in the end-to-end arm (copy-bound)')
     ap.add_argument('--no-extras', action='store_true', help='skip the post-measurement c5_rot (N=1) / c4_rowblock (N>1) runs')
     args = ap.parse_args()
     args.gram_f16, args.sweep_moments = not args.gram_tf32, not args.sweep_general

@@ -1925,7 +1925,9 @@ int run_lanczos_chain(esper_ctx* c, int m, int k, int guard, double tol, int max
         at[0].val.clusterDim.x = cp.S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         at[1].id = cudaLaunchAttributeCooperative;
         at[1].val.cooperative = 1;
-        cfg.attrs = at; cfg.numAttrs = 2;
+        // ESPER_CHAIN_NOCOOP=1 (profiling only): without the cooperative attribute -- Nsight Compute 2025.2 fails to launch a kernel that is
+        // both cooperative and clustered; on an otherwise idle device the CTAs are co-resident anyway (the plan never exceeds the occupancy query)
+        cfg.attrs = at; cfg.numAttrs = getenv("ESPER_CHAIN_NOCOOP") ? 1 : 2;
         cudaError_t e = merged ? cudaLaunchKernelEx(&cfg, lanczos_merged_kernel, p) : cudaLaunchKernelEx(&cfg, lanczos_cluster_kernel, p);
         if (e != cudaSuccess) { cudaGetLastError(); return fail(c, ESPER_E_CUDA, "cooperative cluster launch (%d x %d): %s", cp.S, cp.total / cp.S, cudaGetErrorString(e)); }
         c->cluster_launches++;
