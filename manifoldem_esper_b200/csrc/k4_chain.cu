@@ -1624,95 +1624,79 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_merged_kernel(Params p)
 #undef MG_TRACE_ANY
 }
 
-// U[r][1+i] = sum_l V_{1+l}[r] S[l][i] with the step count and S of the winning checker read on the device; U[r][0] = V_0[r].
-__global__ void __launch_bounds__(128) ritz_chain_kernel(const double* __restrict__ V, int m, const Ctl* __restrict__ ctl,
-                                                         const double* __restrict__ S_base, int s_stride, int kw,
-                                                         double* __restrict__ U, int k) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
-    if (r >= m) return;
-    if (i == 0) { U[(size_t)r * k] = V[r]; return; }
-    const int steps = ctl->n_final, win = ctl->winner;
-    if (win < 0 || steps < 1) { U[(size_t)r * k + i] = 0.0; return; }
-    const double* S = S_base + (size_t)win * s_stride;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int l = 0;
-    for (; l + 3 < steps; l += 4) {
-        a0 = fma(V[(size_t)(1 + l) * m + r], S[(size_t)l * kw + (i - 1)], a0);
-        a1 = fma(V[(size_t)(2 + l) * m + r], S[(size_t)(l + 1) * kw + (i - 1)], a1);
-        a2 = fma(V[(size_t)(3 + l) * m + r], S[(size_t)(l + 2) * kw + (i - 1)], a2);
-        a3 = fma(V[(size_t)(4 + l) * m + r], S[(size_t)(l + 3) * kw + (i - 1)], a3);
-    }
-    for (; l < steps; ++l) a0 = fma(V[(size_t)(1 + l) * m + r], S[(size_t)l * kw + (i - 1)], a0);
-    U[(size_t)r * k + i] = (a0 + a1) + (a2 + a3);
-}
 // ---- end chain kernel text ----
 
 }  // namespace chain
 
-// Ritz vectors, normalised, largest-magnitude entry positive -- ritz_chain_kernel + fix_columns_kernel (k4_eigen.cu) in one launch:
-// block i forms column i of U = [V_0 | (V_1 .. V_n) S] for all rows (step count and S of the winning checker read on the device).
-__global__ void __launch_bounds__(1024) ritz_fix_chain_kernel(const double* __restrict__ V, int m, const chain::Ctl* __restrict__ ctl,
-                                                              const double* __restrict__ S_base, int s_stride, int kw,
-                                                              double* __restrict__ U, int k) {
-    __shared__ double s_col[chain::CH_THREADS + 8];
-    __shared__ double sh[32];
-    __shared__ double sb[32];
-    __shared__ int si[32];
-    __shared__ double s_scale;
-    const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// Ritz vectors U = [V_0 | (V_1 .. V_n) S] with the step count and S of the winning checker read on the device; unit columns, largest-magnitude
+// entry positive.  Two launches that use the whole device (a single launch with one CTA per column took 0.095 ms at C2: 10 CTAs):
+// ritz_rows_kernel -- a CTA forms ALL columns for 32 rows (lane = row, warp = every 8th basis vector, partial sums added over the warps in
+// a fixed order), stores them unscaled and leaves per-CTA column statistics (sum of squares, largest magnitude and its row);
+// ritz_scale_kernel -- CTA i reduces the statistics of column i in CTA order and scales / orients the column.
+constexpr int RZ_ROWS = 32, RZ_SLICES = 8;
+__global__ void __launch_bounds__(RZ_ROWS * RZ_SLICES) ritz_rows_kernel(const double* __restrict__ V, int m, const chain::Ctl* __restrict__ ctl,
+                                                                          const double* __restrict__ S_base, int s_stride, int kw,
+                                                                          double* __restrict__ U, int k, double* __restrict__ part) {
+    __shared__ double s_acc[RZ_SLICES][RZ_ROWS + 1];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int r = blockIdx.x * RZ_ROWS + lane;
     const int steps = ctl->n_final, win = ctl->winner;
-    const bool dead = (i > 0) && (win < 0 || steps < 1);
-    if (i > 0 && !dead) {
-        const double* S = S_base + (size_t)win * s_stride;
-        for (int l = tid; l < steps; l += 1024) s_col[l] = S[(size_t)l * kw + (i - 1)];
-    }
-    __syncthreads();
-    constexpr int RPT = 2;                                                   // rows per thread per sweep
-    double sq = 0.0, best = -1.0; int best_r = 0x7fffffff;
-    for (int r0 = 0; r0 < m; r0 += 1024 * RPT) {
-        double x[RPT];
+    const bool dead = (win < 0 || steps < 1);
+    const double* S = S_base + (size_t)max(win, 0) * s_stride;
+    double acc[chain::CH_MAXWANT];
 #pragma unroll
-        for (int u = 0; u < RPT; ++u) {
-            const int r = r0 + tid + 1024 * u;
-            x[u] = 0.0;
-            if (r >= m) continue;
-            if (i == 0) { x[u] = V[r]; continue; }
-            if (dead) continue;
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            const double* v = V + (size_t)m + r;
-            int l = 0;
-            for (; l + 3 < steps; l += 4) {
-                a0 = fma(v[(size_t)l * m], s_col[l], a0);
-                a1 = fma(v[(size_t)(l + 1) * m], s_col[l + 1], a1);
-                a2 = fma(v[(size_t)(l + 2) * m], s_col[l + 2], a2);
-                a3 = fma(v[(size_t)(l + 3) * m], s_col[l + 3], a3);
+    for (int i = 0; i < chain::CH_MAXWANT; ++i) acc[i] = 0.0;
+    if (!dead && r < m) {
+        const double* v = V + (size_t)m + r;
+        for (int l = w; l < steps; l += RZ_SLICES) {
+            const double x = v[(size_t)l * m];
+            const double* sl = S + (size_t)l * kw;
+#pragma unroll
+            for (int i = 0; i < chain::CH_MAXWANT; ++i) if (i < kw) acc[i] = fma(x, __ldg(sl + i), acc[i]);
+        }
+    }
+    double* pb = part + (size_t)blockIdx.x * k * 3;
+    // column i of U (i = 0 the locked vector, else Ritz vector i - 1): store, statistics of this CTA's 32 rows
+    auto emit = [&](int i, double x) {
+        if (r < m) U[(size_t)r * k + i] = x;
+        double sq = x * x, best = r < m ? fabs(x) : -1.0; int best_r = r < m ? r : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int orr = __shfl_xor_sync(0xffffffffu, best_r, o);
+            if (ob > best || (ob == best && orr < best_r)) { best = ob; best_r = orr; }
+        }
+        if (lane == 0) { pb[i * 3] = sq; pb[i * 3 + 1] = best; pb[i * 3 + 2] = (double)best_r; }
+    };
+    if (w == 0) emit(0, r < m ? V[r] : 0.0);
+#pragma unroll
+    for (int q = 0; q < chain::CH_MAXWANT; ++q) {
+        if (q + 1 < k) {                                                     // uniform
+            s_acc[w][lane] = acc[q];
+            __syncthreads();
+            if (w == 0) {
+                double x = 0.0;
+#pragma unroll
+                for (int t = 0; t < RZ_SLICES; ++t) x += s_acc[t][lane];
+                emit(q + 1, x);
             }
-            for (; l < steps; ++l) a0 = fma(v[(size_t)l * m], s_col[l], a0);
-            x[u] = (a0 + a1) + (a2 + a3);
-        }
-#pragma unroll
-        for (int u = 0; u < RPT; ++u) {
-            const int r = r0 + tid + 1024 * u;
-            if (r >= m) continue;
-            U[(size_t)r * k + i] = x[u];
-            sq = fma(x[u], x[u], sq);
-            if (fabs(x[u]) > best) { best = fabs(x[u]); best_r = r; }
+            __syncthreads();
         }
     }
-    // arg-max of |x| (ties -> smallest row), then the scale
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int orr = __shfl_xor_sync(0xffffffffu, best_r, o);
-        if (ob > best || (ob == best && orr < best_r)) { best = ob; best_r = orr; }
-    }
-    if (lane == 0) { sb[warp] = best; si[warp] = best_r; }
-    sq = block_sum(sq, sh);                                                  // (barriers inside)
+}
+
+__global__ void __launch_bounds__(256) ritz_scale_kernel(double* __restrict__ U, int m, int k, const double* __restrict__ part, int nblk) {
+    __shared__ double s_scale;
+    const int i = blockIdx.x, tid = threadIdx.x;
     if (tid == 0) {
-        double bb = -1.0; int br = 0x7fffffff;
-        for (int t = 0; t < 32; ++t)
-            if (sb[t] > bb || (sb[t] == bb && si[t] < br)) { bb = sb[t]; br = si[t]; }
+        double sq = 0.0, bb = -1.0; int br = 0x7fffffff;
+        for (int b = 0; b < nblk; ++b) {                                      // CTA order: fixed
+            const double* pb = part + ((size_t)b * k + i) * 3;
+            sq += pb[0];
+            const int rr = (int)pb[2];
+            if (pb[1] > bb || (pb[1] == bb && rr < br)) { bb = pb[1]; br = rr; }
+        }
         const double nrm = sqrt(sq);
         double sc = nrm > 0.0 ? 1.0 / nrm : 0.0;
         if (br < m && U[(size_t)br * k + i] < 0.0) sc = -sc;
@@ -1720,7 +1704,7 @@ __global__ void __launch_bounds__(1024) ritz_fix_chain_kernel(const double* __re
     }
     __syncthreads();
     const double sc = s_scale;
-    for (int r = tid; r < m; r += 1024) U[(size_t)r * k + i] *= sc;
+    for (int r = tid; r < m; r += 256) U[(size_t)r * k + i] *= sc;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1880,7 +1864,8 @@ int run_lanczos_chain(esper_ctx* c, int m, int k, int guard, double tol, int max
     const size_t n_h = (size_t)slots + 1, n_q = (merged ? 2 : 1) * (size_t)m, n_a = 2 * ((size_t)max_steps + 2);
     const size_t pk_bytes = sizeof(uint4) * (n_p + n_h + n_q + n_a);
     const int s_stride = max_steps * kw;
-    const size_t bytes = pk_bytes + sizeof(Ctl) + 64 + sizeof(double) * ((size_t)CH_MAXCHK * CH_MAXWANT + (size_t)CH_MAXCHK * s_stride + 2 * ((size_t)max_steps + 8));
+    const size_t n_ritz_part = (size_t)ceil_div(m, RZ_ROWS) * k * 3;
+    const size_t bytes = pk_bytes + sizeof(Ctl) + 64 + sizeof(double) * ((size_t)CH_MAXCHK * CH_MAXWANT + (size_t)CH_MAXCHK * s_stride + 2 * ((size_t)max_steps + 8) + n_ritz_part);
     ESPER_RESERVE(c, c->chain_ws, bytes);
     char* base = c->chain_ws.as<char>();
     uint4* pbuf = reinterpret_cast<uint4*>(base);
@@ -1890,6 +1875,7 @@ int run_lanczos_chain(esper_ctx* c, int m, int k, int guard, double tol, int max
     double* S_d = theta_d + (size_t)CH_MAXCHK * CH_MAXWANT;
     double* alpha_d = S_d + (size_t)CH_MAXCHK * s_stride;
     double* beta_d = alpha_d + max_steps + 4;
+    double* ritz_part_d = beta_d + max_steps + 4;
     // tags repeat from one solve to the next: the packet buffers and the control block start from zero every time
     ESPER_CUDA(c, cudaMemsetAsync(base, 0, pk_bytes + sizeof(Ctl), st));
 
@@ -1939,7 +1925,11 @@ int run_lanczos_chain(esper_ctx* c, int m, int k, int guard, double tol, int max
         cudaError_t e = cudaLaunchCooperativeKernel((void*)lanczos_chain_kernel, dim3(c->sm_count), dim3(CH_THREADS), args, pl.smem, st);
         if (e != cudaSuccess) { cudaGetLastError(); return fail(c, ESPER_E_CUDA, "cooperative launch (chain): %s", cudaGetErrorString(e)); }
     }
-    { LaunchScope ls(c, "lanczos"); ritz_fix_chain_kernel<<<k, 1024, 0, st>>>(V, m, ctl, S_d, s_stride, kw, U_d, k); }
+    {
+        const int nblk = ceil_div(m, RZ_ROWS);
+        { LaunchScope ls(c, "lanczos"); ritz_rows_kernel<<<nblk, RZ_ROWS * RZ_SLICES, 0, st>>>(V, m, ctl, S_d, s_stride, kw, U_d, k, ritz_part_d); }
+        { LaunchScope ls(c, "lanczos"); ritz_scale_kernel<<<k, 256, 0, st>>>(U_d, m, k, ritz_part_d, nblk); }
+    }
     ESPER_CUDA(c, cudaGetLastError());
     // result block -> pinned host memory (same stream; the caller's final synchronise covers it)
     if (c->pin_chain.reserve(sizeof(Ctl) + sizeof(double) * CH_MAXCHK * CH_MAXWANT) != 0) return fail(c, ESPER_E_NOMEM, "pinned alloc failed");
