@@ -1292,10 +1292,15 @@ __device__ __forceinline__ void merged_symv(const double* s_rows, const double (
 __device__ __forceinline__ void merged_symv_totals(const double* s_red, double* s_y, int n_own, int n_sm, int tid) {
     if (tid < n_own) {
         const int slot = tid < n_sm ? tid : (CL_MAXROWS - CL_REGROWS) + (tid - n_sm);
-        double tot = 0.0, tot2 = 0.0;
+        // a dependent FP64 add costs ~50 cycles here: pairwise tree (depth 4) instead of two chains of 8
+        double t[CH_WARPS];
 #pragma unroll
-        for (int w2 = 0; w2 < CH_WARPS; w2 += 2) { tot += s_red[w2 * CL_MAXROWS + slot]; tot2 += s_red[(w2 + 1) * CL_MAXROWS + slot]; }
-        s_y[tid] = tot + tot2;
+        for (int w2 = 0; w2 < CH_WARPS; ++w2) t[w2] = s_red[w2 * CL_MAXROWS + slot];
+#pragma unroll
+        for (int st = 1; st < CH_WARPS; st *= 2)
+#pragma unroll
+            for (int w2 = 0; w2 + st < CH_WARPS; w2 += 2 * st) t[w2] += t[w2 + st];
+        s_y[tid] = t[0];
     }
 }
 
@@ -1378,7 +1383,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_merged_kernel(Params p)
     int end_reason = 0;                                                      // 1 stop word, 2 breakdown, 3 max_steps, 4 abort
     for (; j <= p.max_steps; ++j) {
         MG_TRACE(0);
-        double alpha_j = sigma, beta_j = 0.0, hj = 0.0, h_keep = 0.0;
+        double alpha_j = sigma, beta_j = 0.0, inv_beta = 0.0, hj = 0.0, h_keep = 0.0;
         bool leave = false;
         for (int pass = 0; pass < 2; ++pass) {
             const unsigned int tag = 2u * (unsigned int)j + (unsigned int)pass;
@@ -1398,16 +1403,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_merged_kernel(Params p)
                 else {                                                       // rows beyond n_own hold zeros
                     const double* vcol = s == 0 ? cand : Vs + (s - 1);
                     const int vstep = s == 0 ? 1 : cap;
-                    double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+                    double vv[6];                                            // six chains of three (a dependent FMA costs ~50 cycles)
 #pragma unroll
-                    for (int r = 0; r + 2 < CL_MAXROWS; r += 3) {
-                        v0 = fma(vcol[r * vstep], cand[r], v0);
-                        v1 = fma(vcol[(r + 1) * vstep], cand[r + 1], v1);
-                        v2 = fma(vcol[(r + 2) * vstep], cand[r + 2], v2);
-                    }
+                    for (int q = 0; q < 6; ++q) vv[q] = vcol[q * vstep] * cand[q];
 #pragma unroll
-                    for (int r = CL_MAXROWS - CL_MAXROWS % 3; r < CL_MAXROWS; ++r) v0 = fma(vcol[r * vstep], cand[r], v0);
-                    v = (v0 + v1) + v2;
+                    for (int r = 6; r < CL_MAXROWS; ++r) vv[r % 6] = fma(vcol[r * vstep], cand[r], vv[r % 6]);
+                    v = ((vv[0] + vv[1]) + (vv[2] + vv[3])) + (vv[4] + vv[5]);
                 }
                 const int idx = s / W, owner = s - idx * W;
                 if (pass == 0) MG_TRACE(12);
@@ -1432,8 +1433,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_merged_kernel(Params p)
             phA ^= 1u;
             if (pass == 0) MG_TRACE(2);
             if (tid < n_mine && !bad) {
-                double tot = s_part[tid * W];
-                for (int src = 1; src < W; ++src) tot += s_part[tid * W + src];
+                double t[8];                                                 // pairwise tree in rank order (W <= 16: two per leaf)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { t[q] = q < W ? s_part[tid * W + q] : 0.0; if (q + 8 < W) t[q] += s_part[tid * W + q + 8]; }
+                const double tot = ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
                 st_ll(cb + (size_t)(tid * W + rank) * C + cid, tot, tag);
             }
             if (pass == 0) MG_TRACE(3);
@@ -1538,14 +1541,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_merged_kernel(Params p)
             if (tid <= j) {
                 const int i = tid;
                 const double hi = s_h[1 + i];
-                double g;
-                if (i == 0) g = p.lambda0 * hi;
-                else {
-                    g = (i < j ? my_alpha : sigma) * hi;
-                    if (i >= 2) g = fma(my_beta_prev, s_h[i], g);            // beta_{i-1} H_{i-1}
-                    if (i + 1 <= j) g = fma(my_beta, s_h[2 + i], g);         // beta_i H_{i+1}
-                }
-                s_g[1 + i] = fma(hj, hi, g);
+                // (diagonal + H_j) H_i and the two neighbour terms are independent: depth 2 instead of 4
+                const double diag = (i == 0 ? p.lambda0 : (i < j ? my_alpha : sigma)) + hj;
+                const double lo_t = (i >= 2) ? my_beta_prev * s_h[i] : 0.0;             // beta_{i-1} H_{i-1}
+                const double up_t = (i >= 1 && i + 1 <= j) ? my_beta * s_h[2 + i] : 0.0;   // beta_i H_{i+1}
+                s_g[1 + i] = fma(diag, hi, lo_t + up_t);
             }
             __syncthreads();
             if (pass == 0) MG_TRACE(9);
@@ -1581,14 +1581,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_merged_kernel(Params p)
             const double after = ww - sum_h2;
             alpha_j = sigma + hj;
             if (pass == 0 && after < 0.5 * ww) continue;                     // DGKS: orthogonalise once more (s_upd is the candidate)
-            beta_j = after > 0.0 ? sqrt(after) : 0.0;
+            inv_beta = after > 0.0 ? rsqrt(after) : 0.0;                    // one reciprocal square root instead of sqrt + divide on the critical path
+            beta_j = after * inv_beta;
             break;
         }
         if (leave) break;
         if (j == 1) alpha1 = alpha_j;
         // ---- q_{j+1}, Ms q_{j+1} and the next candidate on the owned rows ----
         const bool breakdown = !(beta_j > 1e-14 * fmax(fabs(alpha1), 1e-300));
-        const double inv = beta_j > 0.0 ? 1.0 / beta_j : 0.0;
+        const double inv = inv_beta;
         if (tid < n_own) {
             const double q = s_upd[tid] * inv;
             const double z = fma(-hj, q, s_z[tid] * inv);

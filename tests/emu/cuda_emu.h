@@ -96,6 +96,7 @@ inline float __half2float(__half h) {
 inline unsigned short __half_as_ushort(__half h) { return h.bits; }
 inline long long __double_as_longlong(double d) { long long r; std::memcpy(&r, &d, 8); return r; }
 inline double __longlong_as_double(long long v) { double r; std::memcpy(&r, &v, 8); return r; }
+inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }
 struct uint4 { uint32_t x, y, z, w; };
