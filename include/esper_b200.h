@@ -156,12 +156,17 @@ int esper_markov(esper_ctx* ctx, const double* D, int m, double eps, double* deg
  *        tenth and eleventh eigenvalue differ by 1e-4 relative -- are determined as a subspace, as the SVD of the reference
  *        itself determines them.  On the benchmark matrix 1e-8 needs 164 Lanczos steps, 1e-10 needs 184 (tools/eig_probe.py).
  *   max_iter: Lanczos steps (0 = min(m-1, 1024));  iters (optional) receives the steps used.  */
-/* Eigensolver scheduling for m <= 2048.  mode 0 (default, lowest latency for one PD): every CTA keeps its rows of
- * Ms in shared memory / registers for the whole solve (the kernel owns the SMs).  mode 1 (highest throughput with
- * several ctxs per GPU): rows are streamed from L2 and the kernel fits twice per SM, so the solves of two PDs
- * overlap and hide each other's grid-barrier latency.  Same arithmetic, same results.  mode 2 (opt-in, not yet run on
- * hardware): mode 1 without the speculatively launched batch -- batches of 8 steps issued after each failed convergence
- * test, ~20 fewer steps executed per PD when other streams fill the gaps. */
+/* Eigensolver scheduling for m <= 2048.  mode 0 (default; lowest latency AND, since the merged schedule, highest throughput):
+ * ONE persistent kernel for the whole solve -- 15 thread-block clusters of 8 CTAs keep the rows of Ms and of the Lanczos basis
+ * in shared memory / registers, one exchange per step (distributed shared memory inside a cluster, flag-carrying packets
+ * between clusters), convergence tested on the device by checker CTAs on a fixed schedule of sizes (the step count of the
+ * result is reproducible); the host is not involved between the launch and the final copy (csrc/k4_chain.cu).  It covers
+ * m <= 2048 and up to ~300 steps; anything else, and a solve that does not converge within that, runs on the barrier kernels.
+ * mode 1: rows streamed from L2, batches of 16 steps, convergence tests on the host while the next batch runs; the kernel fits
+ * twice per SM.  mode 2: mode 1 without the speculatively launched batch.  mode 3: rows in shared memory, three grid barriers
+ * per step (round-1 default).  Same arithmetic, same results to rounding (the modes stop at different steps).
+ * Environment (experiments only): ESPER_CHAIN_MERGED=0 two exchanges per step; ESPER_CLUSTER_SIZE=0/2/4/8/16; ESPER_CHAIN_NOCOOP=1
+ * launches the cluster kernel without the cooperative attribute (Nsight Compute cannot launch it otherwise). */
 int esper_dmap_config(esper_ctx* ctx, int mode);
 int esper_dmap_embed(esper_ctx* ctx, const double* D, int m, double eps, int k, double tol,
                      int max_iter, double* val, double* vec, int* iters);
