@@ -609,6 +609,36 @@ def test_eigensolver_modes_agree(ctx):
         ctx.dmap_config(7)
 
 
+@pytest.mark.parametrize('m', [33, 64, 129, 257, 400])
+def test_merged_chain_kernel_over_sizes(ctx, m):
+    """The default eigensolver schedule (one persistent cluster kernel, one exchange per step) on leading blocks of the medium golden:
+    partial clusters, few rows per CTA, rows in registers only -- same pairs as the resident barrier kernel, the step count of the
+    result identical from call to call (fixed schedule of convergence tests), no fallback to the barrier kernels."""
+    g = golden('stage23_medium.npz')
+    D = np.ascontiguousarray(g['D'][:m, :m])
+    k = 6
+    ctx.dmap_config(3)
+    try:
+        v3, U3, it3 = ctx.dmap_embed(D, float(g['eps']), k=k, tol=1e-10)
+    finally:
+        ctx.dmap_config(0)
+    f0, m0, c0 = ctx.stat('lanczos_fallbacks'), ctx.stat('merged_launches'), ctx.stat('cluster_launches')
+    runs = [ctx.dmap_embed(D, float(g['eps']), k=k, tol=1e-10) for _ in range(3)]
+    assert ctx.stat('lanczos_fallbacks') == f0
+    if ctx.stat('cluster_launches') > c0:                                      # clusters available on this device: the merged kernel ran
+        assert ctx.stat('merged_launches') - m0 == 3
+    v, U, it = runs[0]
+    for v2, U2, it2 in runs[1:]:
+        assert it2 == it and np.array_equal(v2, v) and np.array_equal(U2, U)    # bit-reproducible
+    assert np.max(np.abs(v - v3) / v3) < 1e-11
+    lam = np.sqrt(v3)
+    for i in range(k):
+        gap = min(abs(lam[i] - lam[i - 1]) if i else 1.0, abs(lam[i] - lam[i + 1]) if i + 1 < k else 1.0)
+        if gap > 1e-3 * lam[1]:
+            assert vec_err(U[:, i], U3[:, i]) < 1e-7, (m, i)
+    assert abs(it - it3) <= 48
+
+
 def test_eigensolver_without_speculative_batch(ctx):
     """esper_dmap_config(2): batches of 8 steps issued after each failed convergence test; same pairs, no more steps."""
     for name, k in (('stage23_medium', 10), ('stage123_pristine', 12)):
