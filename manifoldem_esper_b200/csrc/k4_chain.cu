@@ -441,16 +441,18 @@ __device__ void ritz_prepare(const CheckSmem& cs, int n, int cap, int want, doub
     __syncthreads();
 }
 
-__device__ void ritz_iterate(const CheckSmem& cs, int n, int cap, int want, double tn, bool ortho) {
+// Clusters |theta_i - theta_{i-1}| <= 1e-3 |T| orthogonalised in index order (two passes, coefficients by one warp per earlier
+// vector), every vector normalised.  All threads.
+// unit_in: the vectors arrive normalised -- only the members of a cluster that were modified are normalised again.
+__device__ void ritz_orthonormalise(const CheckSmem& cs, int n, int cap, int want, double tn, bool unit_in = false) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double cluster_tol = 1e-3 * tn;
-    if (tid < want) inverse_solve_thread(cs, n, cap, tid);
-    __syncthreads();
     int cstart = 0;
     for (int i = 0; i < want; ++i) {
         if (i > 0 && fabs(cs.theta[i] - cs.theta[i - 1]) > cluster_tol) cstart = i;
+        if (unit_in && i == cstart) continue;                           // uniform: theta is shared
         double* yi = cs.y + (size_t)i * cap;
-        if (ortho && i > cstart) {
+        if (i > cstart) {
             for (int pass = 0; pass < 2; ++pass) {
                 for (int pp = cstart + warp; pp < i; pp += CH_WARPS) {
                     const double* yp = cs.y + (size_t)pp * cap;
@@ -468,7 +470,6 @@ __device__ void ritz_iterate(const CheckSmem& cs, int n, int cap, int want, doub
                 __syncthreads();
             }
         }
-        if (!ortho) continue;                                   // the vectors of the early test are normalised by their own warp below
         double nrm = 0.0;
         for (int r = tid; r < n; r += CH_THREADS) nrm = fma(yi[r], yi[r], nrm);
         nrm = wsum(nrm);
@@ -485,21 +486,126 @@ __device__ void ritz_iterate(const CheckSmem& cs, int n, int cap, int want, doub
         }
         __syncthreads();
     }
-    if (!ortho) {                                               // one warp per vector, no block barriers
-        for (int i = warp; i < want; i += CH_WARPS) {
-            double* yi = cs.y + (size_t)i * cap;
-            double nrm = 0.0;
-            for (int r = lane; r < n; r += 32) nrm = fma(yi[r], yi[r], nrm);
-            nrm = sqrt(wsum(nrm));
-            if (!(nrm > 0.0) || !(nrm < 1e300)) {
-                for (int r = lane; r < n; r += 32) yi[r] = (r == (i % n)) ? 1.0 : 0.0;
-            } else {
-                const double inv = 1.0 / nrm;
-                for (int r = lane; r < n; r += 32) yi[r] *= inv;
+}
+
+__device__ void ritz_iterate(const CheckSmem& cs, int n, int cap, int want, double tn) {
+    if (threadIdx.x < want) inverse_solve_thread(cs, n, cap, threadIdx.x);
+    __syncthreads();
+    ritz_orthonormalise(cs, n, cap, want, tn);
+}
+
+// Unit eigenvectors of T_n for cs.theta[0..want) in cs.y by the three-term recurrence run BACKWARDS, one thread per vector.  Row k of
+// (T - theta) s = 0 gives s_{k-1} = -((a_k - theta) s_k + b_k s_{k+1}) / b_{k-1}; from s_n = 1 upwards the wanted solution grows (a
+// converged Ritz vector is tiny at the bottom), so rounding errors stay relatively small; ~100 cycles per row and no division
+// (reciprocals of the off-diagonals once, all threads), a fifth of the pivoted factorisation + solve of inverse iteration.  Row 1
+// is not used: the result solves (T - theta) s = rho e_1 exactly (one inverse-iteration step from e_1), and |rho| / |s| IS its
+// residual -- returned in cs.dots[i] relative to tn, so the caller knows how good each vector is (theta within a few ulps of |T| of
+// a separated eigenvalue: ~1e-16).  cs.di[0..n), cs.ff[0..n), cs.du and cs.xs[0..want) are scratch here (ritz_prepare rewrites them).
+constexpr int RR_MAXEV = 4;                                                 // rescaling events per vector (32 + want * 9 <= CH_THREADS doubles of cs.xs)
+__device__ void ritz_recurrence(const CheckSmem& cs, int n, int cap, int want, double tn, long long* prof = nullptr) {
+    const int tid = threadIdx.x;
+    long long t0 = now();
+#define RR_PROF(i) do { if (prof && tid == 0) { const long long t_ = now(); prof[i] += t_ - t0; t0 = t_; } } while (0)
+    double* rb = cs.di;                                                      // [n]  1 / b_k
+    double* Q = cs.ff;                                                       // [n]  q_k = -b_k / b_{k-1}   (b_{n-1} := 0: there is no s_n)
+    double* P = cs.du;                                                       // [want][cap]  p_k = -(a_k - theta_i) / b_{k-1}
+    for (int i = tid; i + 1 < n; i += CH_THREADS) rb[i] = cs.b[i] != 0.0 ? 1.0 / cs.b[i] : 0.0;
+    __syncthreads();
+    RR_PROF(0);
+    for (int k = 1 + tid; k < n; k += CH_THREADS) Q[k] = (k < n - 1) ? -cs.b[k] * rb[k - 1] : 0.0;
+    for (int idx = tid; idx < want * n; idx += CH_THREADS) {
+        const int i = idx / n, k = idx - i * n;
+        if (k >= 1) P[(size_t)i * cap + k] = -(cs.a[k] - cs.theta[i]) * rb[k - 1];
+    }
+    __syncthreads();
+    RR_PROF(1);
+    if (tid < want) {
+        // s_{k-1} = p_k s_k + q_k s_{k+1}: ONE dependent FMA per row; eight rows at a time with their factors loaded first and their
+        // results stored last (loads cannot be moved across the stores by the compiler, and a warp issues in order)
+        const double* Pk = P + (size_t)tid * cap;
+        double* y = cs.y + (size_t)tid * cap;
+        double s_cur = 1.0, s_next = 0.0, nrm2 = 1.0;
+        y[n - 1] = 1.0;
+        double* ev = cs.xs + 32 + (2 * RR_MAXEV + 1) * tid;                  // rescaling events of this vector: (row, exponent) pairs, then the count
+        int n_ev = 0;
+        int k = n - 1;
+        while (k >= 1) {
+            const int cnt = min(8, k);
+            double pr[8], qr[8], out[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { pr[u] = u < cnt ? Pk[k - u] : 0.0; qr[u] = u < cnt ? Q[k - u] : 0.0; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const double s_prev = fma(pr[u], s_cur, qr[u] * s_next);
+                if (u < cnt) { s_next = s_cur; s_cur = s_prev; nrm2 = fma(s_prev, s_prev, nrm2); }
+                out[u] = s_prev;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (u < cnt) y[k - 1 - u] = out[u];
+            k -= cnt;
+            if (k >= 1 && (!(fabs(s_cur) < 1e100) || !(fabs(s_next) < 1e100))) {
+                // keep the magnitudes in range (a pair that converged long ago is tiny at the bottom: 1e-100 and less): continue
+                // scaled by 2^-e and remember from which row on the stored entries owe that factor -- they get it in the parallel
+                // scaling pass below (rescaling them here, one ldexp per stored row, cost more than the whole recurrence)
+                int e;
+                frexp(fmax(fabs(s_cur), fabs(s_next)), &e);
+                s_cur = ldexp(s_cur, -e); s_next = ldexp(s_next, -e); nrm2 = ldexp(nrm2, -2 * e);
+                y[k] = s_cur;                                                // row k was stored unscaled a moment ago; rows > k owe the factor
+                if (n_ev < RR_MAXEV) { ev[2 * n_ev] = (double)k; ev[2 * n_ev + 1] = (double)e; }
+                ++n_ev;
             }
         }
-        __syncthreads();
+        const double x = cs.theta[tid];
+        const double nr = sqrt(nrm2);
+        const bool fine = nr > 0.0 && nr < 1e300 && n_ev <= RR_MAXEV;
+        const double rho = n > 1 ? fma(cs.a[0] - x, y[0], cs.b[0] * y[1]) : (cs.a[0] - x);
+        ev[2 * RR_MAXEV] = (double)min(n_ev, RR_MAXEV);
+        cs.xs[tid] = fine ? 1.0 / nr : 0.0;
+        cs.dots[tid] = fine ? fabs(rho) / (nr * fmax(tn, 1e-300)) : 1.0;
     }
+    __syncthreads();
+    RR_PROF(2);
+    for (int idx = tid; idx < want * n; idx += CH_THREADS) {
+        const int i = idx / n, r = idx - i * n;
+        const double* ev = cs.xs + 32 + (2 * RR_MAXEV + 1) * i;
+        const int n_ev = (int)ev[2 * RR_MAXEV];
+        int e = 0;
+        for (int j = 0; j < n_ev; ++j) if (r > (int)ev[2 * j]) e += (int)ev[2 * j + 1];     // rows below an event row were stored before it
+        double v = cs.y[(size_t)i * cap + r] * cs.xs[i];
+        if (e != 0) v = ldexp(v, -e);
+        cs.y[(size_t)i * cap + r] = v;
+    }
+    __syncthreads();
+    RR_PROF(3);
+#undef RR_PROF
+}
+
+// The decision needs only the LAST component of every Ritz vector: the same recurrence without storing the vector (measured:
+// 18 000 cycles at n = 165 against 56 000 with the stores and 84 000 for the pivoted factorisation + first solve of inverse
+// iteration).  Result in cs.y[i * cap + n - 1], the only entry ritz_residuals_ok reads; cs.di[0..n) is scratch.
+__device__ void ritz_last_components(const CheckSmem& cs, int n, int cap, int want) {
+    const int tid = threadIdx.x;
+    double* rb = cs.di;
+    for (int i = tid; i + 1 < n; i += CH_THREADS) rb[i] = cs.b[i] != 0.0 ? 1.0 / cs.b[i] : 0.0;
+    __syncthreads();
+    if (tid < want) {
+        const double x = cs.theta[tid];
+        double s_cur = 1.0, carry = 0.0, last = 1.0, nrm2 = 1.0;             // carry = b_k s_{k+1}
+        for (int k = n - 1; k >= 1; --k) {
+            const double s_prev = -fma(cs.a[k] - x, s_cur, carry) * rb[k - 1];
+            carry = cs.b[k - 1] * s_cur;
+            s_cur = s_prev;
+            nrm2 = fma(s_prev, s_prev, nrm2);
+            if ((k & 7) == 0 && !(fabs(s_cur) < 1e100)) {                    // keep the magnitudes in range: everything by 2^-e
+                int e;
+                frexp(fmax(fabs(s_cur), fabs(carry)), &e);
+                s_cur = ldexp(s_cur, -e); carry = ldexp(carry, -e); last = ldexp(last, -e); nrm2 = ldexp(nrm2, -2 * e);
+            }
+        }
+        const double nr = sqrt(nrm2);
+        cs.y[(size_t)tid * cap + (n - 1)] = (nr > 0.0 && nr < 1e300) ? last / nr : 1.0;
+    }
+    __syncthreads();
 }
 
 __device__ bool ritz_residuals_ok(const CheckSmem& cs, int n, int cap, int kw, int want, double tol, double factor) {
@@ -621,12 +727,10 @@ __device__ void checker_main(const Params& p, double* smem, int c) {
         if (!track) { /* theta is final */ }
         else if (tid < want) cs.theta[tid] = 0.5 * (cs.lo[tid] + cs.hi[tid]);      // stagnant: the bracket is a few ulps of |T| wide
         __syncthreads();
-        ritz_prepare(cs, n, cap, want, tn);
         bool won = false;
         if (mode == 1) {
-            // first solve: the residual estimates are already good to a small factor.  Raise the stop word on them (with a
-            // margin), so that the workers leave while the vectors are refined.
-            ritz_iterate(cs, n, cap, want, tn, false);
+            // The decision needs the last component of every Ritz vector: the three-term recurrence run backwards (ritz_last_components).
+            ritz_last_components(cs, n, cap, want);
             if (p.prof_on && tid == 0) p.ctl->prof[9 + 2 * c] += (1LL << 32) + (now() - tc1);  // vector tests, cycles up to the decision
             if (!ritz_residuals_ok(cs, n, cap, p.kw, want, p.tol, 0.25)) { CH_TEST_FAILED(true); __syncthreads(); continue; }
             if (tid == 0) {
@@ -652,12 +756,31 @@ __device__ void checker_main(const Params& p, double* smem, int c) {
             won = s_mode != 0;
             __syncthreads();
             if (!won) return;                                               // another checker stopped the iteration first
-            // The workers are leaving: now the eigenvalues down to the last ulp.  The vectors continue from the first solve with
-            // the stored factorisation (its shifts are within a few ulps of |T| of the final values, which is all inverse
-            // iteration asks of a shift): two more solves, clusters orthogonalised.
-            tn = leading_eigenvalues(cs, n, want, true, true, 0);
+            // The workers are leaving: two more multisection rounds on the eigenvalues (17^2 times tighter: the last ulp), then the
+            // vectors for the final values by the same recurrence, stored this time.
+            tn = leading_eigenvalues(cs, n, want, true, true, 2);
+            ritz_recurrence(cs, n, cap, want, tn, p.prof_on ? &p.ctl->prof[26] : nullptr);
         }
-        for (int it = 0; it < (mode == 1 ? 2 : 3); ++it) ritz_iterate(cs, n, cap, want, tn, true);
+        // The recurrence vectors are kept when each solves (T - theta) s = rho e_1 with |rho| <= 1e-12 |T| |s| (clusters orthogonalised as
+        // dstein does); otherwise, and for the final tests at max_steps / breakdown, inverse iteration with the pivoted factorisation:
+        // three solves from a random start.
+        bool by_recurrence = (mode == 1);
+        if (by_recurrence) {
+            int bad_q = 0;
+            if (p.prof_on && tid == 0) {
+                double mw = 0.0, mg = 0.0;
+                for (int i = 0; i < want; ++i) { if (i < p.kw) mw = fmax(mw, cs.dots[i]); else mg = fmax(mg, cs.dots[i]); }
+                p.ctl->prof[24] = __double_as_longlong(mw); p.ctl->prof[25] = __double_as_longlong(mg);
+            }
+            if (tid < want && !(cs.dots[tid] <= (tid < p.kw ? 1e-12 : 1e-8))) bad_q = 1;   // guard pairs are not output: their test is the residual one
+            by_recurrence = __syncthreads_or(bad_q) == 0;
+        }
+        if (by_recurrence) ritz_orthonormalise(cs, n, cap, want, tn, true);
+        else {
+            ritz_prepare(cs, n, cap, want, tn);
+            for (int it = 0; it < 3; ++it) ritz_iterate(cs, n, cap, want, tn);
+        }
+        if (p.prof_on && tid == 0 && mode == 1) p.ctl->prof[7] += by_recurrence ? 1 : 1000;
         const bool ok = ritz_residuals_ok(cs, n, cap, p.kw, want, p.tol, 1.0);
         {
             double* th = p.theta_out + (size_t)c * CH_MAXWANT;
@@ -1953,6 +2076,9 @@ int chain_result(esper_ctx* c, int k, double* theta_out, int* iters_out) {
                                  h->prof[16] / n, h->prof[17] / n, h->prof[2] / n, h->prof[18] / n, h->prof[4] / n);
         if (h->prof[16]) fprintf(stderr, "[chain] cluster schedule, thread 0 of CTA0: S0 = products %.0f | warp sums %.0f | barrier %.0f | row totals + barrier %.0f ; update: own row %.0f | barrier %.0f | rest %.0f\n",
                                  h->prof[19] / n, h->prof[20] / n, h->prof[21] / n, h->prof[1] / n, h->prof[22] / n, h->prof[23] / n, h->prof[3] / n);
+        { double mw, mg; memcpy(&mw, &h->prof[24], 8); memcpy(&mg, &h->prof[25], 8); fprintf(stderr, "[chain] recurrence residuals |rho| / (|s| |T|): wanted pairs %.2e, guard pairs %.2e\n", mw, mg); }
+        fprintf(stderr, "[chain] recurrence phases (cycles, summed over the vector tests of all checkers): reciprocals %lld | factors %lld | rows %lld | scaling %lld\n", h->prof[26], h->prof[27], h->prof[28], h->prof[29]);
+        fprintf(stderr, "[chain] Ritz vectors of the winner: %s\n", h->prof[7] == 1 ? "backward recurrence" : h->prof[7] >= 1000 ? "inverse iteration (recurrence residual too large)" : "inverse iteration");
         for (int cc = 0; cc < CH_MAXCHK; ++cc) {
             const long long e = h->prof[8 + 2 * cc], v = h->prof[9 + 2 * cc];
             if (e >> 32) fprintf(stderr, "[chain] checker %d: %lld eigenvalue tests, %.0f cycles each; %lld vector tests, %.0f cycles each up to the decision\n", cc, e >> 32,
