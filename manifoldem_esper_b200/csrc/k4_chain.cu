@@ -168,6 +168,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 __device__ __forceinline__ long long wall_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define CH_DEBUG_TEST(c, n, mode, track, stagnant)
+#define CH_RR_BIG 1e100                 // the backward recurrences of the checkers rescale themselves beyond this magnitude
 #endif
 
 // ---- begin chain kernel text (tests/test_emu.py cuts from here) ----
@@ -543,7 +544,7 @@ __device__ void ritz_recurrence(const CheckSmem& cs, int n, int cap, int want, d
 #pragma unroll
             for (int u = 0; u < 8; ++u) if (u < cnt) y[k - 1 - u] = out[u];
             k -= cnt;
-            if (k >= 1 && (!(fabs(s_cur) < 1e100) || !(fabs(s_next) < 1e100))) {
+            if (k >= 1 && (!(fabs(s_cur) < CH_RR_BIG) || !(fabs(s_next) < CH_RR_BIG))) {
                 // keep the magnitudes in range (a pair that converged long ago is tiny at the bottom: 1e-100 and less): continue
                 // scaled by 2^-e and remember from which row on the stored entries owe that factor -- they get it in the parallel
                 // scaling pass below (rescaling them here, one ldexp per stored row, cost more than the whole recurrence)
@@ -596,7 +597,7 @@ __device__ void ritz_last_components(const CheckSmem& cs, int n, int cap, int wa
             carry = cs.b[k - 1] * s_cur;
             s_cur = s_prev;
             nrm2 = fma(s_prev, s_prev, nrm2);
-            if ((k & 7) == 0 && !(fabs(s_cur) < 1e100)) {                    // keep the magnitudes in range: everything by 2^-e
+            if ((k & 7) == 0 && !(fabs(s_cur) < CH_RR_BIG)) {                // keep the magnitudes in range: everything by 2^-e
                 int e;
                 frexp(fmax(fabs(s_cur), fabs(carry)), &e);
                 s_cur = ldexp(s_cur, -e); carry = ldexp(carry, -e); last = ldexp(last, -e); nrm2 = ldexp(nrm2, -2 * e);

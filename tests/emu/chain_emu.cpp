@@ -149,6 +149,7 @@ inline void relax_short() { std::this_thread::yield(); }
     fprintf(stderr, "checker %d: n %d mode %d track %d stagnant %d tn %.3e:", c, n, mode, (int)(track), (int)(stagnant), tn); \
     for (int i_ = 0; i_ < min(p.kw, want); ++i_) fprintf(stderr, " [%.1e %.1e]", (cs.lo[i_] - cs.prev[i_]) / tn, (cs.hi[i_] - cs.prev[i_]) / tn); \
     fprintf(stderr, "\n"); } } while (0)
+#define CH_RR_BIG 1e6                   // (device: 1e100) small, so that the rescaling events of the recurrences are exercised at the test sizes
 #include "chain.inc"
 }  // namespace chain
 }  // namespace esper
