@@ -149,7 +149,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                                          '-lms', '50'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          '-lms', '20'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -165,6 +165,10 @@ class ClockSampler:
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)
+        if not self.lines:                     # nothing yet at all: take one late sample rather than none (marked in `window`)
+            t_wait = time.time()
+            while not self.lines and time.time() - t_wait < 3.0:
+                time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         inside = [ln for (t, ln) in self.lines if t_begin is None or (t_begin <= t <= (t_end or t) + 0.1)]
@@ -297,6 +301,10 @@ def run_ours(args):
     ctx = _capi.Context(local_rank, stream=stream.cuda_stream)
 
     # two distinct PD stacks per rank in pinned host memory (inputs of successive steps differ)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                        # started before the stacks are generated: nvidia-smi can take a second for its first line on a
+                                               # fresh box (a default run once ended with no sample at all); samples are selected by time later
     n_stacks = 2
     ms_serial = 0.0
     pinned = []
@@ -374,9 +382,6 @@ def run_ours(args):
         embed_step(ctxs[w % NF], GB, coef, a0, N_IMG, P)
     pipelined(NF, False)
     # serial profiled pass (per-kernel CUDA-event durations; single stream, nothing overlapping)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()                        # nvidia-smi needs ~0.1 s for its first line: started ahead of the timed region
     for c in ctxs:
         c.set_profiling(True); c.reset_profiling()
     barrier()
