@@ -1812,15 +1812,32 @@ __global__ void __launch_bounds__(RZ_ROWS * RZ_SLICES) ritz_rows_kernel(const do
 }
 
 __global__ void __launch_bounds__(256) ritz_scale_kernel(double* __restrict__ U, int m, int k, const double* __restrict__ part, int nblk) {
-    __shared__ double s_scale;
-    const int i = blockIdx.x, tid = threadIdx.x;
+    __shared__ double s_sq[8], s_bb[8], s_scale;
+    __shared__ int s_br[8];
+    const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // statistics of column i over the CTAs of ritz_rows_kernel: thread t takes CTAs t, t + 256, ... (one load each at the usual sizes),
+    // then a fixed shuffle tree and the eight warp results in warp order -- the same bits in every run
+    double sq = 0.0, bb = -1.0; int br = 0x7fffffff;
+    for (int b = tid; b < nblk; b += 256) {
+        const double* pb = part + ((size_t)b * k + i) * 3;
+        sq += pb[0];
+        const int rr = (int)pb[2];
+        if (pb[1] > bb || (pb[1] == bb && rr < br)) { bb = pb[1]; br = rr; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const double ob = __shfl_xor_sync(0xffffffffu, bb, o);
+        const int orr = __shfl_xor_sync(0xffffffffu, br, o);
+        if (ob > bb || (ob == bb && orr < br)) { bb = ob; br = orr; }
+    }
+    if (lane == 0) { s_sq[warp] = sq; s_bb[warp] = bb; s_br[warp] = br; }
+    __syncthreads();
     if (tid == 0) {
-        double sq = 0.0, bb = -1.0; int br = 0x7fffffff;
-        for (int b = 0; b < nblk; ++b) {                                      // CTA order: fixed
-            const double* pb = part + ((size_t)b * k + i) * 3;
-            sq += pb[0];
-            const int rr = (int)pb[2];
-            if (pb[1] > bb || (pb[1] == bb && rr < br)) { bb = pb[1]; br = rr; }
+        sq = 0.0; bb = -1.0; br = 0x7fffffff;
+        for (int w = 0; w < 8; ++w) {
+            sq += s_sq[w];
+            if (s_bb[w] > bb || (s_bb[w] == bb && s_br[w] < br)) { bb = s_bb[w]; br = s_br[w]; }
         }
         const double nrm = sqrt(sq);
         double sc = nrm > 0.0 ? 1.0 / nrm : 0.0;
