@@ -1507,7 +1507,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_merged_kernel(Params p)
     int end_reason = 0;                                                      // 1 stop word, 2 breakdown, 3 max_steps, 4 abort
     for (; j <= p.max_steps; ++j) {
         MG_TRACE(0);
-        double alpha_j = sigma, beta_j = 0.0, inv_beta = 0.0, hj = 0.0, h_keep = 0.0;
+        double alpha_j = sigma, beta_j = 0.0, inv_beta = 0.0, hj = 0.0, h_keep = 0.0, ww0 = 0.0;
         bool leave = false;
         for (int pass = 0; pass < 2; ++pass) {
             const unsigned int tag = 2u * (unsigned int)j + (unsigned int)pass;
@@ -1650,6 +1650,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_merged_kernel(Params p)
             if (__syncthreads_or(bad)) { end_reason = 4; leave = true; break; }          // also: s_y of all rows is visible
             if (s_h[n_tot - 1] != 0.0) { end_reason = 1; leave = true; break; }
             double ww = s_h[0], sum_h2 = 0.0;
+            if (pass == 0) ww0 = ww;
             if (pass == 0) { if (tid <= j) h_keep = s_h[1 + tid]; }
             else {
                 // second pass: |h2|^2 first, then H = h + h2 in place
@@ -1733,6 +1734,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) lanczos_merged_kernel(Params p)
         MG_TRACE(11);
         if (breakdown) { end_reason = 2; ++j; break; }
         if (j == p.max_steps) { end_reason = 3; ++j; break; }
+        // Ms q_{j+1} came from a recurrence that divides by beta_j: when the candidate lost eight digits in the orthogonalisation
+        // (numerically exhausted Krylov space that the breakdown threshold has not caught yet: duplicated images, rank-deficient Ms)
+        // its error is no longer at rounding level and would be amplified step after step.  T_j is still good: stop here like at
+        // max_steps -- checker 0 tests T_j, and the host falls back to the barrier kernels if that is not enough.
+        if (!(beta_j * beta_j > 1e-16 * fmax(ww0, alpha1 * alpha1))) { end_reason = 3; ++j; break; }
         sigma = alpha_j;
         __syncthreads();
     }

@@ -639,6 +639,31 @@ def test_merged_chain_kernel_over_sizes(ctx, m):
     assert abs(it - it3) <= 48
 
 
+def test_eigensolver_on_duplicated_images(ctx):
+    """Every image twice (stage1_dupes golden): Ms has rank n / 2, the Krylov space of the default kernel ends early (breakdown path:
+    the workers stop by themselves, checker 0 accepts T_n as exact, vectors by inverse iteration) -- leading pairs as the oracle's SVD."""
+    g = golden('stage1_dupes.npz')
+    D = g['D']
+    eps = float(np.median(D[D > 0]) ** 2 / 2.0)
+    val_ref, U_ref = O.dmap_embed(D, eps)
+    k = 6
+    f0 = ctx.stat('lanczos_fallbacks')
+    val, vec, iters = ctx.dmap_embed(D, eps, k=k)
+    assert iters <= D.shape[0] // 2 + 8                                        # the rank (plus the few steps rounding noise survives)
+    assert np.max(np.abs(val - val_ref[:k]) / val_ref[:k]) < VAL_TOL
+    lam = np.sqrt(val_ref)
+    for i in range(k):
+        gap = min(abs(lam[i] - lam[i - 1]) if i else 1.0, abs(lam[i] - lam[i + 1]))
+        if gap > 2e-3 * lam[1]:
+            assert vec_err(vec[:, i], U_ref[:, i]) < VEC_TOL, i
+    ctx.dmap_config(3)
+    try:
+        v3, U3, it3 = ctx.dmap_embed(D, eps, k=k)
+    finally:
+        ctx.dmap_config(0)
+    assert np.max(np.abs(val - v3) / v3) < 1e-10
+
+
 def test_eigensolver_without_speculative_batch(ctx):
     """esper_dmap_config(2): batches of 8 steps issued after each failed convergence test; same pairs, no more steps."""
     for name, k in (('stage23_medium', 10), ('stage123_pristine', 12)):
