@@ -664,6 +664,34 @@ def test_eigensolver_on_duplicated_images(ctx):
     assert np.max(np.abs(val - v3) / v3) < 1e-10
 
 
+@pytest.mark.parametrize('case', ['eps/10', 'eps*10', 'eps*1e4', 'eps/1e3', 'duplicated', 'near-duplicate'])
+def test_default_eigensolver_over_regimes(ctx, case):
+    """The default schedule against the resident barrier kernel where the merged recurrence could suffer: nearly rank-one Ms (large
+    bandwidth), nearly diagonal Ms (tiny bandwidth: every eigenvalue ~1, the Krylov space ends at once), every image twice (rank
+    n / 2) and one near-duplicate pair -- same pairs (the default may fall back to the barrier kernels; it must not return others)."""
+    g = golden('stage23_medium.npz')
+    D, eps = g['D'], float(g['eps'])
+    if case == 'duplicated':
+        D = np.repeat(np.repeat(D[:150, :150], 2, axis=0), 2, axis=1)
+    elif case == 'near-duplicate':
+        D = D[:200, :200].copy(); D[1, :] = D[0, :] * (1 + 1e-9); D[:, 1] = D[1, :]; D[1, 1] = 0; D[0, 1] = D[1, 0] = 1e-9
+    else:
+        eps *= {'eps/10': 0.1, 'eps*10': 10.0, 'eps*1e4': 1e4, 'eps/1e3': 1e-3}[case]
+    D = np.ascontiguousarray(D)
+    ctx.dmap_config(3)
+    try:
+        v3, U3, it3 = ctx.dmap_embed(D, eps, k=8)
+    finally:
+        ctx.dmap_config(0)
+    v0, U0, it0 = ctx.dmap_embed(D, eps, k=8)
+    assert np.max(np.abs(v0 - v3) / np.maximum(v3, 1e-300)) < 1e-9, case
+    lam = np.sqrt(v3)
+    for i in range(4):
+        gap = min(abs(lam[i] - lam[i - 1]) if i else 1.0, abs(lam[i] - lam[i + 1]))
+        if gap > 1e-3 * lam[1]:
+            assert vec_err(U0[:, i], U3[:, i]) < 1e-8, (case, i)
+
+
 def test_eigensolver_without_speculative_batch(ctx):
     """esper_dmap_config(2): batches of 8 steps issued after each failed convergence test; same pairs, no more steps."""
     for name, k in (('stage23_medium', 10), ('stage123_pristine', 12)):
