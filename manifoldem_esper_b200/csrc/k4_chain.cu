@@ -1,6 +1,15 @@
 // k4_chain.cu -- K4, default schedule for m <= 2048: Lanczos with full reorthogonalisation as ONE persistent kernel
 // WITHOUT grid barriers.  Replaces the full SVD of 1_Embedding/DM/DiffusionMaps.py:166-169 (leading pairs only).
 //
+// Three generations of worker kernels share the checker CTAs, the packet protocol and the host side of this file:
+//   lanczos_merged_kernel   (default for the Markov matrix)  clusters of 8 CTAs, ONE exchange per step: the unorthogonalised
+//                            candidate is gathered together with the reduction of its coefficients, Ms q by linearity
+//                            (comment in front of the kernel)
+//   lanczos_cluster_kernel  clusters of 8 CTAs, two exchanges per step (coefficients, then the new vector); distributed shared
+//                            memory inside a cluster, packets between clusters; used when the locked pair's eigenvalue is unknown
+//   lanczos_chain_kernel    no clusters: every hand-over is a packet through L2 (described below); used when clusters of 8
+//                            cannot be made resident
+//
 // The three-barrier kernel of k4_eigen.cu spent 40 % of every step inside grid barriers and the rest waiting for one L2
 // round trip per phase (profiles/r1_bench_lines.md).  Here every hand-over between CTAs is a flag-carrying 16-byte packet
 // {lo, tag, hi, tag} (the protocol NCCL calls LL; already used by the row-block all-gather): the consumer polls the data
@@ -18,10 +27,13 @@
 //   Three dependent hand-overs per step, no barrier, every reduction in a fixed order (deterministic, identical in all CTAs).
 //
 //   checker CTAs (the CTAs that own no rows): follow alpha_j / beta_j (packets abuf[j] from CTA 0) and test convergence of
-//   the leading Ritz pairs on the device: multisection Sturm counts with all threads (division-free scaled recurrence),
-//   inverse iteration with a stored pivoted LU (one thread per Ritz vector), residual |beta_n s_{n,i}|.  The first checker
-//   whose test passes publishes theta, S and n and raises the stop word; CTA 0 forwards it to all workers inside the control
-//   packet of the next P2, so that all of them leave at the same step.  The host is not involved until the final copy.
+//   the leading Ritz pairs on the device, at a FIXED schedule of sizes (the oldest passing test wins: the step count of the
+//   result does not depend on timing): multisection Sturm counts with all threads (division-free scaled recurrence); a gate
+//   ("have the values grown over the last 8 steps": one Sturm count per value on the leading block T_{n-8}); the last components
+//   of the Ritz vectors by the three-term recurrence run backwards (one thread per vector) for the residuals |beta_n s_{n,i}|.
+//   The winner raises the stop word; CTA 0 forwards it to all workers inside the coefficient exchange of the next step, so
+//   that all of them leave at the same step; it then forms the Ritz vectors (the same recurrence, stored, its residual measured;
+//   inverse iteration with a pivoted LU as the fallback) and publishes theta, S and n.  The host is not involved until the final copy.
 //
 // A failure of any spin wait (~2 s) raises the abort word and ends the kernel; the host then falls back to the
 // barrier kernels of k4_eigen.cu, as it does for sizes this schedule does not cover.
